@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native LibRec MF path.
+
+Contract (one JSON line on stdout, rank 0):
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+N=1 workload = BASELINE.json configs[1]: BiasedMF k=64 on the synthetic ML-20M shape
+(138 493 x 26 744, 20 000 263 ratings).  A "step" is one SGD epoch (one pass of trainModel()'s inner
+loop over all ratings).  metric = MF SGD rating-updates/s.
+  value    : device-resident epochs (inputs already in HBM), CUDA events, max over ranks
+  e2e      : the same metric through the C ABI with HOST buffers -- one trainModel() call of the
+             shim = stage CSR + factors H2D, E epochs, factors D2H -- all inside the timed region
+  roofline : algorithmic bytes (1052 B / BiasedMF update) / kernel time vs measured HBM peak
+  cpu_baseline : the oracle's single-thread fp64 restatement of the reference loop on this box
+--impl reference times that CPU restatement alone (the Java reference cannot run: no JVM).
+N>1 (torchrun, one process per GPU): the same matrix trained with DSGD strata, item blocks rotated
+over NCCL; value = ratings processed by all ranks / max-over-ranks time ("scaling": "strong").
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MF SGD rating-updates/s"
+UNIT = "updates/s"
+K_FACTORS = 64
+LR, REG, REG_B = 0.002, 0.01, 0.01           # biasedmf-test.properties
+BYTES_PER_UPDATE = 12 + 4 * K_FACTORS * 4 + 16   # 1052 B for k=64 fp32
+E2E_EPOCHS = 10                               # epochs per trainModel() call in the e2e leg
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """samples SM clock + throttle reasons while the timed region runs (pynvml, nvidia-smi fallback)"""
+
+    def __init__(self, index=0, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._dev, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            log("pynvml unavailable:", e)
+            self._nvml = None
+
+    def _decode(self, mask):
+        n = self._nvml
+        names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(n, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        return [k for k, bit in names.items() if mask & bit]
+
+    def _run(self):
+        n = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self._dev, n.NVML_CLOCK_SM))
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._dev)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev)
+                self.reasons.update(self._decode(mask))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self._nvml:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+        if not self._nvml:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [int(x) for x in out.strip().split(",")]
+                self.samples, self.max_mhz = [a], b
+            except Exception:
+                pass
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def workload_desc(d):
+    return "BiasedMF k=%d SGD epoch, synthetic ML-20M shape (%d users x %d items, %d ratings), lr %g reg %g" % (
+        K_FACTORS, d["U"], d["I"], d["rowptr"][-1], LR, REG)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(d, sample_ratings, steps, warmup, nthreads=1):
+    """time the oracle's faithful restatement (1 thread, CSR order, fp64) on a CSR prefix"""
+    from oracle import oracle as O
+    from librec_b200 import synth
+    L = O.lib()
+    U, I = d["U"], d["I"]
+    nnz = int(d["rowptr"][-1])
+    n = min(nnz, sample_ratings)
+    u_end = int(np.searchsorted(d["rowptr"], n, side="left"))
+    u_end = max(1, min(U, u_end))
+    n = int(d["rowptr"][u_end])
+    rowptr = np.ascontiguousarray(d["rowptr"][:u_end + 1])
+    P, Q, bu, bi = synth.init_factors(U, I, K_FACTORS, 7, True)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        L.lro_biasedmf_epoch(u_end, rowptr, d["col"], d["val"], K_FACTORS, P, Q, bu, bi, 3.5, LR, REG, REG, REG_B, None, None)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    return n * len(times) / total, n, total / len(times)
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from librec_b200 import synth
+    d = synth.make_ratings("ml-20m")
+    nnz = int(d["rowptr"][-1])
+    # probe 1M ratings to size the per-step sample so K+W steps end within ~2.5 minutes
+    rate, _, _ = cpu_reference_rate(d, 1_000_000, 1, 0)
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    sample = int(min(nnz, max(1_000_000, rate * budget_s)))
+    rate, n, sec = cpu_reference_rate(d, sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_desc(d), "reference": "oracle port of BiasedMFRecommender.trainModel (Java reference cannot run: no JVM)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "one epoch over the first %d ratings in CSR order per step (of %d); the reference's trainModel is single-threaded" % (n, nnz)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def pinned_array(capi, shape, dtype):
+    """numpy view over a cudaMallocHost buffer from the C ABI (what the Java shim's direct buffers are)"""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = ctypes.c_void_p()
+    rc = capi.load().lrk_host_alloc(ctypes.byref(p), nbytes)
+    if rc != 0:
+        raise RuntimeError("lrk_host_alloc failed")
+    buf = (ctypes.c_char * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr, p
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from librec_b200 import _build, capi, synth
+
+    rank, world, local = dist_env()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not os.path.exists(_build.LIB_PATH):
+        _build.build()
+    capi.load()
+
+    if world > 1 and rank != 0:
+        dist.barrier()           # rank 0 generates / caches the data first
+    d = synth.make_ratings("ml-20m")
+    if world > 1 and rank == 0:
+        dist.barrier()
+    U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
+    P0, Q0, bu0, bi0 = synth.init_factors(U, I, K_FACTORS, 1, True)
+    mu = float(d["val"].mean())
+
+    h = capi.Handle(capi.MODEL_BIASEDMF, K_FACTORS, device=local, seed=1)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(rank, world, uid[0])
+    h.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
+    h.set_factors(P0, Q0, bu0, bi0, mu)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        h.sgd_epoch(LR, REG, REG, REG_B, w + 1)
+    sampler = ClockSampler(index=local)
+    launches0 = h.launch_count()
+    barrier()
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms, losses = [], []
+    for s in range(args.steps):
+        flush.zero_()                                   # evict L2 between timed steps (not timed)
+        evs[s][0].record(stream)
+        losses.append(h.sgd_epoch(LR, REG, REG, REG_B, args.warmup + s + 1))
+        evs[s][1].record(stream)
+        kernel_ms.append(h.last_epoch_ms())
+    barrier()
+    clocks = sampler.stop()
+    launches = h.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(np.sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = nnz * args.steps / (total_ms * 1e-3)
+    kms = float(np.mean(kernel_ms))
+
+    line = None
+    if rank == 0:
+        peaks, which = measured_peaks()
+        achieved = BYTES_PER_UPDATE * nnz / (kms * 1e-3) / 1e9 * (1.0 / world if world > 1 else 1.0)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("sgd_rating_epoch_kernel_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_desc(d), "update_mode": "atomic (REDG.E.ADD.F32x4)",
+                       "l2": "L2 flushed between timed steps (256 MiB memset, untimed); COO stream 240 MB > L2",
+                       "parallelism": "single GPU" if world == 1 else "DSGD %d strata, NCCL ring rotation of item blocks" % world,
+                       "final_loss": losses[-1]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
+                         "kernel": "sgd_rating_epoch_kernel<16,1,true,true>", "kernel_ms": kms,
+                         "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * nnz // world},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+
+    # ---- e2e: one trainModel() call of the shim per step, host buffers, copies inside the timed region
+    if world == 1 and not args.no_e2e:
+        bufs = []
+        rp, p1 = pinned_array(capi, (U + 1,), np.int64); rp[:] = d["rowptr"]
+        cl, p2 = pinned_array(capi, (nnz,), np.int32); cl[:] = d["col"]
+        vl, p3 = pinned_array(capi, (nnz,), np.float64); vl[:] = d["val"]
+        hP, p4 = pinned_array(capi, (U, K_FACTORS), np.float64); hQ, p5 = pinned_array(capi, (I, K_FACTORS), np.float64)
+        hbu, p6 = pinned_array(capi, (U,), np.float64); hbi, p7 = pinned_array(capi, (I,), np.float64)
+        bufs = [p1, p2, p3, p4, p5, p6, p7]
+        L = capi.load()
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        loss = ctypes.c_double()
+
+        def train_model_call():
+            hP[:] = P0; hQ[:] = Q0; hbu[:] = bu0; hbi[:] = bi0
+            t0 = time.perf_counter()
+            rc = L.lrk_set_train_csr(h._h, U, I, vp(rp), vp(cl), vp(vl))
+            rc |= L.lrk_set_factors(h._h, vp(hP), vp(hQ), vp(hbu), vp(hbi), mu)
+            for it in range(E2E_EPOCHS):
+                rc |= L.lrk_sgd_epoch(h._h, LR, REG, REG, REG_B, it + 1, ctypes.byref(loss))
+            rc |= L.lrk_get_factors(h._h, vp(hP), vp(hQ), vp(hbu), vp(hbi))
+            torch.cuda.synchronize()
+            if rc != 0:
+                raise RuntimeError("e2e call failed: %s" % L.lrk_last_error(h._h))
+            return time.perf_counter() - t0
+
+        e2e_steps = max(2, min(args.steps, 5))
+        train_model_call()                                  # warm-up
+        tt = [train_model_call() for _ in range(e2e_steps)]
+        h2d = rp.nbytes + cl.nbytes + vl.nbytes + hP.nbytes + hQ.nbytes + hbu.nbytes + hbi.nbytes
+        d2h = hP.nbytes + hQ.nbytes + hbu.nbytes + hbi.nbytes + 8 * E2E_EPOCHS
+        line["e2e"] = {"value": nnz * E2E_EPOCHS * e2e_steps / float(np.sum(tt)), "unit": UNIT,
+                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "step": "one trainModel() call through the C ABI from pinned host buffers: lrk_set_train_csr + "
+                               "lrk_set_factors + %d x lrk_sgd_epoch + lrk_get_factors" % E2E_EPOCHS,
+                       "ms_per_call": float(np.mean(tt)) * 1e3, "calls": e2e_steps}
+        for p in bufs:
+            L.lrk_host_free(p)
+    elif rank == 0:
+        line["e2e"] = None
+
+    # ---- cpu baseline: oracle port on this box's host cores (rank 0, N=1 only)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, n, sec = cpu_reference_rate(d, nnz, 1, 0)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "one full epoch (%d ratings) of the oracle's restatement of BiasedMFRecommender.trainModel, "
+                                          "CSR order, fp64, 1 thread (the reference loop is single-threaded); %.1f s" % (n, sec)}
+        try:
+            from oracle import oracle as O
+            nt = O.lib().lro_max_threads()
+            rows = np.repeat(np.arange(U, dtype=np.int32), np.diff(d["rowptr"]))
+            perm = np.random.default_rng(0).permutation(nnz)
+            us, is_, rs = rows[perm], d["col"][perm], d["val"][perm].astype(np.float32)
+            P, Q, bu, bi = [a.astype(np.float32) for a in (P0, Q0, bu0, bi0)]
+            t0 = time.perf_counter()
+            O.lib().lro_sgd_epoch_hogwild_f32(0, us, is_, rs, nnz, K_FACTORS, P, Q, bu.ctypes.data, bi.ctypes.data,
+                                              mu, LR, REG, REG, REG_B, nt)
+            dt = time.perf_counter() - t0
+            line["cpu_best_effort"] = {"value": nnz / dt, "unit": UNIT, "cores": nt,
+                                       "what": "OpenMP Hogwild fp32 epoch over shuffled triples (NOT the reference's algorithm)"}
+        except Exception as e:  # pragma: no cover
+            log("best-effort cpu leg failed:", e)
+
+    h.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+/* =====================================================================================
+ * librec_b200.h -- C ABI of the B200-native LibRec matrix-factorisation hot path.
+ *
+ * The reference (szkb/librec, LibRec 3.0.0) is pure Java and has NO FFI of its own
+ * (SURVEY.md 2.1), so these entry points are what a JNI / Panama shim for this path binds
+ * (INTEGRATION.md shows that shim).  Each function names the reference interface it
+ * replaces; paths are relative to core/src/main/java/net/librec/ in the reference.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every buffer is caller-allocated and caller-freed,
+ *     row-major, 0-based LibRec inner ids (math/structure/DataFrame.java:370-379).
+ *   - every call returns LRK_OK (0) or a negative lrk_status; the text of the last error is
+ *     available from lrk_last_error().  Nothing throws or aborts across the ABI; the Java
+ *     shim maps a non-zero status to LibrecException (common/LibrecException.java).
+ *   - a handle is NOT thread-safe: one handle per recommender instance, caller serialises
+ *     (the reference calls train/recommend from one thread: job/RecommenderJob.java:121-143).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     LRK_ERR_CUDA.
+ * ===================================================================================== */
+#ifndef LIBREC_B200_H
+#define LIBREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define LRK_API __attribute__((visibility("default")))
+#else
+#define LRK_API
+#endif
+
+typedef struct lrk_handle_s* lrk_handle_t;
+
+typedef enum {
+    LRK_OK = 0,
+    LRK_ERR_INVALID = -1,   /* bad argument / call order                       */
+    LRK_ERR_CUDA = -2,      /* CUDA runtime error (incl. no device)            */
+    LRK_ERR_NCCL = -3,      /* NCCL error                                      */
+    LRK_ERR_NOMEM = -4,     /* host or device allocation failed                */
+    LRK_ERR_DIVERGED = -5   /* loss is NaN/Inf: AbstractRecommender.java:259-262 */
+} lrk_status;
+
+/* rec.recommender.class values served by this path (resources/driver.classes.props):
+ * biasedmf -> recommender/cf/rating/BiasedMFRecommender.java
+ * pmf      -> vanilla PMF loop, recommender/cf/rating/PMFSimilarityRecommender.java:59-90
+ * bpr      -> recommender/cf/ranking/BPRRecommender.java */
+typedef enum { LRK_MODEL_BIASEDMF = 0, LRK_MODEL_PMF = 1, LRK_MODEL_BPR = 2 } lrk_model;
+
+/* how concurrent updates to one factor row are combined */
+typedef enum {
+    LRK_UPDATE_ATOMIC = 0,  /* red.global.add.v4.f32: no lost updates (default; needed for RMSE parity) */
+    LRK_UPDATE_HOGWILD = 1  /* plain racy read-modify-write stores                                      */
+} lrk_update_mode;
+
+typedef struct {
+    int32_t device;        /* CUDA device ordinal                                               */
+    int32_t model;         /* lrk_model                                                         */
+    int32_t num_factors;   /* rec.factor.number  (MatrixFactorizationRecommender.java:75), 1..256 */
+    int32_t update_mode;   /* lrk_update_mode                                                   */
+    uint64_t seed;         /* shuffle / BPR-sampling seed (rec.cuda.seed)                       */
+    int32_t topn_path;     /* 0 auto, 1 exact fp64 kernel only, 2 force tensor-core candidates  */
+    int32_t reserved[7];   /* must be zero                                                      */
+} lrk_config_t;
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+LRK_API const char* lrk_version(void);
+LRK_API int32_t lrk_abi_version(void);
+/* number of visible CUDA devices (0 when none / driver missing); never fails */
+LRK_API int32_t lrk_device_count(void);
+/* replaces: the no-arg constructor + setup() allocation of DenseMatrix factors
+ * (recommender/MatrixFactorizationRecommender.java:67-94). */
+LRK_API int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out);
+LRK_API int lrk_destroy(lrk_handle_t h);
+/* h may be NULL: returns the last error of the calling thread for calls that had no handle */
+LRK_API const char* lrk_last_error(lrk_handle_t h);
+/* run all work of this handle on an externally owned cudaStream_t (NULL = handle's own stream) */
+LRK_API int lrk_set_stream(lrk_handle_t h, void* cuda_stream);
+LRK_API int lrk_synchronize(lrk_handle_t h);
+
+/* pinned host staging buffers for the shim's flatten step (direct ByteBuffers on the Java side) */
+LRK_API int lrk_host_alloc(void** out, uint64_t bytes);
+LRK_API int lrk_host_free(void* p);
+
+/* ---- staging ------------------------------------------------------------------------ */
+/* replaces: trainMatrix = (SequentialAccessSparseMatrix) getDataModel().getTrainDataSet()
+ * (recommender/MatrixRecommender.java:90) -- the per-row int[]/double[] pieces
+ * (math/structure/RowSequentialAccessSparseMatrix.java:19, OrderedIntDoubleMapping) flattened to
+ * rowptr[U+1], col[nnz] (ascending inside a row), val[nnz].  Builds the device CSR and a
+ * device-shuffled COO stream for the SGD epoch. */
+LRK_API int lrk_set_train_csr(lrk_handle_t h, int32_t num_users, int32_t num_items,
+                      const int64_t* rowptr, const int32_t* col, const double* val);
+/* replaces: DenseMatrix userFactors/itemFactors (double[][], math/structure/DenseMatrix.java:20),
+ * VectorBasedDenseVector userBiases/itemBiases (BiasedMFRecommender.java:40-45), globalMean
+ * (MatrixRecommender.java:109).  P is U x k, Q is I x k; bu/bi may be NULL unless model is BIASEDMF. */
+LRK_API int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const double* bu, const double* bi,
+                    double global_mean);
+/* copies the current factors back (any pointer may be NULL to skip it) so the inherited Java
+ * predict()/recommendRating()/evaluators keep working on DenseMatrix. */
+LRK_API int lrk_get_factors(lrk_handle_t h, double* P, double* Q, double* bu, double* bi);
+
+/* ---- training ----------------------------------------------------------------------- */
+/* replaces ONE iteration of trainModel():
+ *   BiasedMFRecommender.java:68-100, PMFSimilarityRecommender.java:59-90, BPRRecommender.java:48-93.
+ * lr/reg_u/reg_i are the float fields of MatrixFactorizationRecommender.java:16,54,59; reg_b is the
+ * double regBias (BiasedMFRecommender.java:36; ignored unless BIASEDMF).  epoch_idx is the 1-based
+ * iteration number (selects the BPR sample stream).  *loss_out receives the epoch loss with the
+ * reference's definition (0.5 * (sum e^2 + reg terms); BPR: sum -ln sigma(x) + reg terms, no 0.5),
+ * so isConverged()/updateLRate() stay on the caller's side.  Returns LRK_ERR_DIVERGED (and still
+ * writes *loss_out) when the loss is NaN/Inf. */
+LRK_API int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg_b,
+                  int32_t epoch_idx, double* loss_out);
+/* device time of the last lrk_sgd_epoch kernel in milliseconds (CUDA events on its stream) */
+LRK_API int lrk_last_epoch_ms(lrk_handle_t h, float* ms_out);
+/* number of kernels this handle has launched since creation */
+LRK_API int lrk_launch_count(lrk_handle_t h, uint64_t* out);
+/* debug / test aid: the (user, positive item, negative item) triples that BPR epoch `epoch_idx`
+ * draws for samples [first, first+n) -- out is int32[3*n]. */
+LRK_API int lrk_bpr_peek_samples(lrk_handle_t h, int32_t epoch_idx, int64_t first, int64_t n, int32_t* out);
+
+/* ---- prediction --------------------------------------------------------------------- */
+/* replaces predict(u,i) without bound: MatrixFactorizationRecommender.java:104-106 /
+ * BiasedMFRecommender.java:118-120, fp64, summed f = 0..k-1 left to right like
+ * math/structure/DenseVector.java:104-111.  Bit-exact for identical factors. */
+LRK_API int lrk_predict_pairs(lrk_handle_t h, const int32_t* users, const int32_t* items, int64_t n, double* out);
+/* replaces recommendRating(DataSet) + RMSE/MAE evaluators
+ * (MatrixRecommender.java:211-248,272-284; eval/rating/RMSEEvaluator.java:33-69, MAEEvaluator.java:34-70):
+ * bounded predictions for every test-CSR entry (pred_out may be NULL) and the two metrics. */
+LRK_API int lrk_eval_rating(lrk_handle_t h, int32_t num_users, const int64_t* t_rowptr, const int32_t* t_col,
+                    const double* t_val, double min_rate, double max_rate,
+                    double* pred_out, double* rmse_out, double* mae_out);
+
+/* ---- top-N ranking ------------------------------------------------------------------ */
+/* replaces recommendRank(): MatrixRecommender.java:137-201 + util/Lists.java:416-468
+ * (+ recommender/item/RecommendedList.java:85-88).  For each queried user (users == NULL means
+ * users 0..nq-1) scores every item not in the user's train row (exclude_train != 0), drops NaN,
+ * keeps the top `topn` with java.util.PriorityQueue + stable-sort tie semantics.
+ * out_items / out_scores are [nq x topn] (unused slots: item -1, score 0), out_counts[nq]. */
+LRK_API int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int32_t exclude_train,
+             int32_t* out_items, double* out_scores, int32_t* out_counts);
+/* statistics of the last lrk_topn call: users served by the tensor-core candidate path, users
+ * that failed the exactness certificate and were re-done by the exact fp64 kernel, device ms */
+LRK_API int lrk_topn_stats(lrk_handle_t h, int64_t* fast_users, int64_t* fallback_users, float* ms_out);
+
+/* ---- multi-GPU DSGD (one process per GPU) ----------------------------- */
+/* 128-byte NCCL unique id, created on rank 0 and broadcast by the host (torch.distributed / MPI / JVM) */
+LRK_API int lrk_comm_unique_id(uint8_t out[128]);
+/* joins the handle to a world of `world` ranks.  After this, lrk_set_train_csr expects the FULL
+ * matrix on every rank and keeps only the rank's user block; lrk_set_factors likewise. */
+LRK_API int lrk_comm_init(lrk_handle_t h, int32_t rank, int32_t world, const uint8_t unique_id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBREC_B200_H */

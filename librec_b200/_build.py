@@ -1,0 +1,55 @@
+"""In-tree build of the CUDA library (sm_100a only).  nvcc cross-compiles without a GPU."""
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_DIR = os.path.join(_PKG, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "liblibrec_b200.so")
+_SRC_DIR = os.path.join(_PKG, "csrc")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-lcuda", "-ldl",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _sources():
+    return sorted(os.path.join(_SRC_DIR, f) for f in os.listdir(_SRC_DIR) if f.endswith((".cu", ".cuh")))
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = _sources() + [os.path.join(_ROOT, "include", "librec_b200.h")]
+    return any(os.path.getmtime(s) > t for s in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile librec_b200/csrc/lrk_api.cu (one translation unit) into _lib/liblibrec_b200.so."""
+    if not force and not is_stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB_PATH, os.path.join(_SRC_DIR, "lrk_api.cu")]
+    env = dict(os.environ)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout[-8000:])
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,434 @@
+// C ABI of the B200-native LibRec MF path (include/librec_b200.h).  Single translation unit:
+// staging, SGD epoch, exact prediction / top-N, tensor-core top-N candidates, DSGD.
+#include "lrk_common.cuh"
+#include "staging.cuh"
+#include "sgd.cuh"
+#include "topn_exact.cuh"
+#include "topn_tc.cuh"
+#include "dsgd.cuh"
+
+#include <cmath>
+#include <new>
+
+thread_local std::string g_lrk_tls_error;
+
+extern "C" {
+
+const char* lrk_version(void) { return "librec_b200 0.1.0 (sm_100a; LibRec 3.0.0 MF path)"; }
+int32_t lrk_abi_version(void) { return LRK_ABI_VERSION; }
+
+int32_t lrk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* lrk_last_error(lrk_handle_t h) { return h ? h->err.c_str() : g_lrk_tls_error.c_str(); }
+
+int lrk_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_host_alloc", "out is NULL", __FILE__, __LINE__);
+    LRK_CUDA(nullptr, cudaMallocHost(out, bytes ? bytes : 1));
+    return LRK_OK;
+}
+int lrk_host_free(void* p) {
+    if (p) LRK_CUDA(nullptr, cudaFreeHost(p));
+    return LRK_OK;
+}
+
+static void layout_for_k(int k, int* ld, int* G, int* V) {
+    int l = 4;
+    while (l < k && l < 128) l <<= 1;
+    if (k > 128) l = ((k + 127) / 128) * 128;
+    *ld = l;
+    if (l <= 128) { *G = l / 4; *V = 1; } else { *G = 32; *V = l / 128; }
+}
+
+int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out) {
+    if (!cfg || !out) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "NULL argument", __FILE__, __LINE__);
+    *out = nullptr;
+    if (cfg->num_factors < 1 || cfg->num_factors > LRK_MAX_FACTORS)
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "num_factors must be in 1..256", __FILE__, __LINE__);
+    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_BPR)
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown model", __FILE__, __LINE__);
+    if (cfg->update_mode != LRK_UPDATE_ATOMIC && cfg->update_mode != LRK_UPDATE_HOGWILD)
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown update_mode", __FILE__, __LINE__);
+    int ndev = 0;
+    LRK_CUDA(nullptr, cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return lrk_fail(nullptr, LRK_ERR_CUDA, "lrk_create", "no such CUDA device (there is no CPU fallback)", __FILE__, __LINE__);
+    cudaDeviceProp prop;
+    LRK_CUDA(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return lrk_fail(nullptr, LRK_ERR_CUDA, "lrk_create", "device is not sm_100 (this library is built for sm_100a only)", __FILE__, __LINE__);
+    lrk_handle_s* h = new (std::nothrow) lrk_handle_s();
+    if (!h) return lrk_fail(nullptr, LRK_ERR_NOMEM, "lrk_create", "host allocation failed", __FILE__, __LINE__);
+    h->cfg = *cfg;
+    h->k = cfg->num_factors;
+    layout_for_k(h->k, &h->ld, &h->G, &h->V);
+    h->sm_count = prop.multiProcessorCount;
+    int rc = LRK_OK;
+    do {
+        if (cudaSetDevice(cfg->device) != cudaSuccess) { rc = LRK_ERR_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = LRK_ERR_CUDA; break; }
+        h->stream = h->own_stream;
+        if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) { rc = LRK_ERR_CUDA; break; }
+        if (cudaMalloc((void**)&h->d_loss, 64) != cudaSuccess) { rc = LRK_ERR_NOMEM; break; }
+        if (cudaMallocHost((void**)&h->h_loss, 64) != cudaSuccess) { rc = LRK_ERR_NOMEM; break; }
+    } while (0);
+    if (rc != LRK_OK) {
+        lrk_fail(nullptr, rc, "lrk_create", cudaGetErrorString(cudaGetLastError()), __FILE__, __LINE__);
+        lrk_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return LRK_OK;
+}
+
+int lrk_destroy(lrk_handle_t h) {
+    if (!h) return LRK_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    dsgd_release(h);
+    topn_tc_release(h);
+    lrk_dev_free(&h->d_rowptr); lrk_dev_free(&h->d_col);
+    lrk_dev_free(&h->d_su); lrk_dev_free(&h->d_si); lrk_dev_free(&h->d_sr);
+    lrk_dev_free(&h->P32); lrk_dev_free(&h->Q32); lrk_dev_free(&h->bu32); lrk_dev_free(&h->bi32);
+    lrk_dev_free(&h->P64); lrk_dev_free(&h->Q64); lrk_dev_free(&h->bu64); lrk_dev_free(&h->bi64);
+    lrk_dev_free(&h->d_loss);
+    if (h->h_loss) cudaFreeHost(h->h_loss);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return LRK_OK;
+}
+
+int lrk_set_stream(lrk_handle_t h, void* cuda_stream) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return LRK_OK;
+}
+int lrk_synchronize(lrk_handle_t h) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    LRK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return LRK_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, U > 0 && I > 0 && rowptr && (col || rowptr[U] == 0) && (val || rowptr[U] == 0), "bad CSR arguments");
+    LRK_REQUIRE(h, !h->has_factors || (h->U == U && h->I == I), "CSR shape differs from the factors already set");
+    const int64_t nnz = rowptr[U];
+    LRK_REQUIRE(h, nnz >= 0 && nnz < (int64_t)0xffffffffLL, "nnz out of range");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->world > 1) return dsgd_set_train_csr(h, U, I, rowptr, col, val);
+    cudaStream_t st = h->stream;
+    h->has_train = false;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_rowptr, (size_t)U + 1))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_col, (size_t)nnz))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_su, (size_t)nnz))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_si, (size_t)nnz))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_sr, (size_t)nnz))) return rc;
+    LRK_CUDA(h, cudaMemcpyAsync(h->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)U + 1), cudaMemcpyHostToDevice, st));
+    LRK_CUDA(h, cudaMemcpyAsync(h->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    h->U = U; h->I = I; h->nnz = nnz;
+    rc = stage_coo_from_csr(h, h->d_rowptr, h->d_col, val, U, I, nnz, h->d_su, h->d_si, h->d_sr, /*validate=*/true);
+    if (rc) return rc;
+    h->has_train = true;
+    topn_tc_invalidate(h);
+    return LRK_OK;
+}
+
+int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const double* bu, const double* bi, double mu) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, h->has_train, "call lrk_set_train_csr first (it fixes numUsers / numItems)");
+    LRK_REQUIRE(h, P && Q, "P and Q are required");
+    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    LRK_REQUIRE(h, !biased || (bu && bi), "BiasedMF needs userBiases and itemBiases");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->world > 1) return dsgd_set_factors(h, P, Q, bu, bi, mu);
+    cudaStream_t st = h->stream;
+    const int k = h->k, ld = h->ld;
+    const int64_t U = h->U, I = h->I;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &h->P64, (size_t)U * k))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->Q64, (size_t)I * k))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->P32, (size_t)U * ld))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->Q32, (size_t)I * ld))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bu64, (size_t)U))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bi64, (size_t)I))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bu32, (size_t)U))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bi32, (size_t)I))) return rc;
+    LRK_CUDA(h, cudaMemcpyAsync(h->P64, P, sizeof(double) * (size_t)U * k, cudaMemcpyHostToDevice, st));
+    LRK_CUDA(h, cudaMemcpyAsync(h->Q64, Q, sizeof(double) * (size_t)I * k, cudaMemcpyHostToDevice, st));
+    if (biased) {
+        LRK_CUDA(h, cudaMemcpyAsync(h->bu64, bu, sizeof(double) * (size_t)U, cudaMemcpyHostToDevice, st));
+        LRK_CUDA(h, cudaMemcpyAsync(h->bi64, bi, sizeof(double) * (size_t)I, cudaMemcpyHostToDevice, st));
+    } else {
+        LRK_CUDA(h, cudaMemsetAsync(h->bu64, 0, sizeof(double) * (size_t)U, st));
+        LRK_CUDA(h, cudaMemsetAsync(h->bi64, 0, sizeof(double) * (size_t)I, st));
+    }
+    f64_to_f32_rows_kernel<<<lrk_ceil_div(U * ld, 256), 256, 0, st>>>(h->P64, h->P32, U, k, ld); LRK_LAUNCH_CHECK(h);
+    f64_to_f32_rows_kernel<<<lrk_ceil_div(I * ld, 256), 256, 0, st>>>(h->Q64, h->Q32, I, k, ld); LRK_LAUNCH_CHECK(h);
+    f64_to_f32_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu64, h->bu32, U, 1, 1); LRK_LAUNCH_CHECK(h);
+    f64_to_f32_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi64, h->bi32, I, 1, 1); LRK_LAUNCH_CHECK(h);
+    LRK_CUDA(h, cudaStreamSynchronize(st));   // host buffers may be reused by the caller on return
+    h->mu = mu;
+    h->has_factors = true;
+    h->f64_valid = true;
+    topn_tc_invalidate(h);
+    return LRK_OK;
+}
+
+// bring the fp64 masters up to date with the fp32 working copies (exact widening)
+static int refresh_masters(lrk_handle_s* h) {
+    if (h->f64_valid) return LRK_OK;
+    cudaStream_t st = h->stream;
+    const int64_t U = h->U, I = h->I;
+    f32_to_f64_rows_kernel<<<lrk_ceil_div(U * h->k, 256), 256, 0, st>>>(h->P32, h->P64, U, h->k, h->ld); LRK_LAUNCH_CHECK(h);
+    f32_to_f64_rows_kernel<<<lrk_ceil_div(I * h->k, 256), 256, 0, st>>>(h->Q32, h->Q64, I, h->k, h->ld); LRK_LAUNCH_CHECK(h);
+    if (h->cfg.model == LRK_MODEL_BIASEDMF) {
+        f32_to_f64_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu32, h->bu64, U, 1, 1); LRK_LAUNCH_CHECK(h);
+        f32_to_f64_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi32, h->bi64, I, 1, 1); LRK_LAUNCH_CHECK(h);
+    }
+    h->f64_valid = true;
+    return LRK_OK;
+}
+
+int lrk_get_factors(lrk_handle_t h, double* P, double* Q, double* bu, double* bi) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, h->has_factors, "no factors set");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->world > 1) return dsgd_get_factors(h, P, Q, bu, bi);
+    int rc = refresh_masters(h);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    if (P) LRK_CUDA(h, cudaMemcpyAsync(P, h->P64, sizeof(double) * (size_t)h->U * h->k, cudaMemcpyDeviceToHost, st));
+    if (Q) LRK_CUDA(h, cudaMemcpyAsync(Q, h->Q64, sizeof(double) * (size_t)h->I * h->k, cudaMemcpyDeviceToHost, st));
+    if (bu) LRK_CUDA(h, cudaMemcpyAsync(bu, h->bu64, sizeof(double) * (size_t)h->U, cudaMemcpyDeviceToHost, st));
+    if (bi) LRK_CUDA(h, cudaMemcpyAsync(bi, h->bi64, sizeof(double) * (size_t)h->I, cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    return LRK_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+static void fill_sgd_params(lrk_handle_s* h, SgdParams& sp, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx) {
+    memset(&sp, 0, sizeof sp);
+    sp.su = h->d_su; sp.si = h->d_si; sp.sr = h->d_sr; sp.n = h->nnz;
+    sp.P = h->P32; sp.Q = h->Q32; sp.bu = h->bu32; sp.bi = h->bi32;
+    sp.mu = (float)h->mu; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i; sp.reg_b = (float)reg_b;
+    sp.loss = h->d_loss; sp.ld = h->ld;
+    sp.rowptr = h->d_rowptr; sp.col = h->d_col; sp.U = h->U; sp.I = h->I;
+    sp.seed_lo = (uint32_t)h->cfg.seed; sp.seed_hi = (uint32_t)(h->cfg.seed >> 32); sp.epoch = (uint32_t)epoch_idx;
+}
+
+int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, double* loss_out) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, h->has_train && h->has_factors, "set the train CSR and the factors before training");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->world > 1) return dsgd_epoch(h, lr, reg_u, reg_i, reg_b, epoch_idx, loss_out);
+    cudaStream_t st = h->stream;
+    SgdParams sp;
+    fill_sgd_params(h, sp, lr, reg_u, reg_i, reg_b, epoch_idx);
+    LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
+    LRK_CUDA(h, cudaEventRecord(h->ev0, st));
+    if (h->nnz > 0) {
+        int rc = sgd_launch(h, sp);
+        if (rc) return rc;
+    }
+    LRK_CUDA(h, cudaEventRecord(h->ev1, st));
+    h->f64_valid = false;
+    topn_tc_invalidate(h);
+    LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    LRK_CUDA(h, cudaEventElapsedTime(&h->last_epoch_ms, h->ev0, h->ev1));
+    double loss = h->h_loss[0];
+    if (h->cfg.model != LRK_MODEL_BPR) loss *= 0.5;   // BiasedMFRecommender.java:101 ; BPR has no 0.5
+    if (loss_out) *loss_out = loss;
+    if (std::isnan(loss) || std::isinf(loss))
+        return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);
+    return LRK_OK;
+}
+
+int lrk_last_epoch_ms(lrk_handle_t h, float* ms_out) {
+    LRK_REQUIRE(h, h != nullptr && ms_out != nullptr, "NULL argument");
+    *ms_out = h->last_epoch_ms;
+    return LRK_OK;
+}
+int lrk_launch_count(lrk_handle_t h, uint64_t* out) {
+    LRK_REQUIRE(h, h != nullptr && out != nullptr, "NULL argument");
+    *out = h->launches;
+    return LRK_OK;
+}
+
+int lrk_bpr_peek_samples(lrk_handle_t h, int32_t epoch_idx, int64_t first, int64_t n, int32_t* out) {
+    LRK_REQUIRE(h, h != nullptr && out != nullptr && n >= 0 && first >= 0, "bad arguments");
+    LRK_REQUIRE(h, h->has_train, "no train CSR");
+    LRK_REQUIRE(h, h->world == 1, "not available in DSGD mode");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (n == 0) return LRK_OK;
+    SgdParams sp;
+    fill_sgd_params(h, sp, 0.f, 0.f, 0.f, 0.0, epoch_idx);
+    int32_t* d_out = nullptr;
+    LRK_CUDA(h, cudaMalloc((void**)&d_out, sizeof(int32_t) * 3 * (size_t)n));
+    bpr_peek_kernel<<<lrk_ceil_div(n, 256), 256, 0, h->stream>>>(sp, first, n, d_out);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(int32_t) * 3 * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    LRK_CUDA(h, e);
+    return LRK_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+int lrk_predict_pairs(lrk_handle_t h, const int32_t* users, const int32_t* items, int64_t n, double* out) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, h->has_factors, "no factors set");
+    LRK_REQUIRE(h, n >= 0 && (n == 0 || (users && items && out)), "bad arguments");
+    LRK_REQUIRE(h, h->world == 1, "gather the factors with lrk_get_factors in DSGD mode");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (n == 0) return LRK_OK;
+    for (int64_t t = 0; t < n; ++t)
+        LRK_REQUIRE(h, users[t] >= 0 && users[t] < h->U && items[t] >= 0 && items[t] < h->I, "user/item index out of range");
+    int rc = refresh_masters(h);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    int32_t *d_u = nullptr, *d_i = nullptr; double* d_o = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_u, sizeof(int32_t) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_i, sizeof(int32_t) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_o, sizeof(double) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, users, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, items, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        predict_pairs_kernel<<<lrk_ceil_div(n, 128), 128, 0, st>>>(h->P64, h->Q64, h->bu64, h->bi64, h->mu,
+                                                                   h->cfg.model == LRK_MODEL_BIASEDMF, h->k, d_u, d_i, n, d_o);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_u); cudaFree(d_i); cudaFree(d_o);
+    LRK_CUDA(h, e);
+    return LRK_OK;
+}
+
+int lrk_eval_rating(lrk_handle_t h, int32_t U, const int64_t* t_rowptr, const int32_t* t_col, const double* t_val,
+                    double min_rate, double max_rate, double* pred_out, double* rmse_out, double* mae_out) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, h->has_factors, "no factors set");
+    LRK_REQUIRE(h, U == h->U && t_rowptr, "test matrix must have numUsers rows");
+    LRK_REQUIRE(h, h->world == 1, "gather the factors with lrk_get_factors in DSGD mode");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int64_t nnz = t_rowptr[U];
+    if (nnz == 0) { if (rmse_out) *rmse_out = 0.0; if (mae_out) *mae_out = 0.0; return LRK_OK; }   // RMSEEvaluator.java:35-37
+    LRK_REQUIRE(h, t_col && t_val, "NULL test arrays");
+    int rc = refresh_masters(h);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    const int nb = lrk_ceil_div(nnz, 256);
+    int64_t* d_rp = nullptr; int32_t* d_c = nullptr; double *d_v = nullptr, *d_p = nullptr, *d_part = nullptr;
+    double res[2] = {0, 0};
+    cudaError_t e = cudaMalloc((void**)&d_rp, sizeof(int64_t) * ((size_t)U + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_c, sizeof(int32_t) * (size_t)nnz);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_v, sizeof(double) * (size_t)nnz);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_p, sizeof(double) * (size_t)nnz);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_part, sizeof(double) * ((size_t)nb * 2 + 2));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rp, t_rowptr, sizeof(int64_t) * ((size_t)U + 1), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_c, t_col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, t_val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        eval_rating_kernel<<<nb, 256, 0, st>>>(h->P64, h->Q64, h->bu64, h->bi64, h->mu, h->cfg.model == LRK_MODEL_BIASEDMF,
+                                               h->k, U, d_rp, d_c, d_v, min_rate, max_rate, d_p, d_part, d_part + nb);
+        eval_rating_final_kernel<<<1, 32, 0, st>>>(d_part, d_part + nb, nb, nnz, d_part + 2 * (size_t)nb);
+        h->launches += 2;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && pred_out) e = cudaMemcpyAsync(pred_out, d_p, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(res, d_part + 2 * (size_t)nb, sizeof(double) * 2, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_rp); cudaFree(d_c); cudaFree(d_v); cudaFree(d_p); cudaFree(d_part);
+    LRK_CUDA(h, e);
+    if (rmse_out) *rmse_out = res[0];
+    if (mae_out) *mae_out = res[1];
+    return LRK_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// exact fp64 top-N for `nq` query slots whose user ids are in d_users (device) or NULL (= 0..nq-1);
+// results to device buffers
+static int topn_exact_launch(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int topn, int exclude_train,
+                             int32_t* d_items, double* d_scores, int32_t* d_counts) {
+    const size_t smem = topn_exact_smem(h->k, topn);
+    LRK_CUDA(h, cudaFuncSetAttribute(topn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = lrk_ceil_div(nq, TOPN_UPB);
+    topn_exact_kernel<<<grid, TOPN_WARPS * 32, smem, h->stream>>>(
+        h->P64, h->Q64, h->bu64, h->bi64, h->mu, h->cfg.model == LRK_MODEL_BIASEDMF, h->k, h->I,
+        h->d_rowptr, h->d_col, exclude_train, d_users, nq, topn, d_items, d_scores, d_counts);
+    LRK_LAUNCH_CHECK(h);
+    return LRK_OK;
+}
+
+int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int32_t exclude_train,
+             int32_t* out_items, double* out_scores, int32_t* out_counts) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, h->has_factors, "no factors set");
+    LRK_REQUIRE(h, topn > 0, "rec.recommender.ranking.topn should be more than 0!");   // AbstractRecommender.java:115-117
+    LRK_REQUIRE(h, topn <= LRK_MAX_TOPN, "topn above LRK_MAX_TOPN (512)");
+    LRK_REQUIRE(h, nq >= 0 && (nq == 0 || (out_items && out_scores && out_counts)), "bad arguments");
+    LRK_REQUIRE(h, !exclude_train || h->has_train, "exclude_train needs the train CSR");
+    LRK_REQUIRE(h, h->world == 1, "gather the factors with lrk_get_factors in DSGD mode; top-N shards by user block");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    h->topn_fast_users = 0; h->topn_fallback_users = 0; h->topn_ms = 0.f;
+    if (nq == 0) return LRK_OK;
+    if (users) for (int32_t c = 0; c < nq; ++c) LRK_REQUIRE(h, users[c] >= 0 && users[c] < h->U, "user index out of range");
+    else LRK_REQUIRE(h, nq <= h->U, "nq exceeds numUsers");
+    int rc = refresh_masters(h);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    int32_t *d_users = nullptr, *d_items = nullptr, *d_counts = nullptr; double* d_scores = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (users) {
+        e = cudaMalloc((void**)&d_users, sizeof(int32_t) * (size_t)nq);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_users, users, sizeof(int32_t) * (size_t)nq, cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_items, sizeof(int32_t) * (size_t)nq * topn);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_scores, sizeof(double) * (size_t)nq * topn);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_counts, sizeof(int32_t) * (size_t)nq);
+    if (e == cudaSuccess) {
+        cudaEventRecord(h->ev0, st);
+        const bool want_tc = h->cfg.topn_path == 2 || (h->cfg.topn_path == 0 && topn_tc_profitable(h, nq, topn));
+        if (want_tc) rc = topn_tc_run(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts);
+        else { rc = topn_exact_launch(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts); h->topn_fallback_users = nq; }
+        cudaEventRecord(h->ev1, st);
+    }
+    if (rc == LRK_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_items, d_items, sizeof(int32_t) * (size_t)nq * topn, cudaMemcpyDeviceToHost, st);
+    if (rc == LRK_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_scores, sizeof(double) * (size_t)nq * topn, cudaMemcpyDeviceToHost, st);
+    if (rc == LRK_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_counts, d_counts, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && rc == LRK_OK) cudaEventElapsedTime(&h->topn_ms, h->ev0, h->ev1);
+    cudaFree(d_users); cudaFree(d_items); cudaFree(d_scores); cudaFree(d_counts);
+    if (rc) return rc;
+    LRK_CUDA(h, e);
+    return LRK_OK;
+}
+
+int lrk_topn_stats(lrk_handle_t h, int64_t* fast_users, int64_t* fallback_users, float* ms_out) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    if (fast_users) *fast_users = h->topn_fast_users;
+    if (fallback_users) *fallback_users = h->topn_fallback_users;
+    if (ms_out) *ms_out = h->topn_ms;
+    return LRK_OK;
+}
+
+int lrk_comm_unique_id(uint8_t out[128]) { return dsgd_unique_id(out); }
+int lrk_comm_init(lrk_handle_t h, int32_t rank, int32_t world, const uint8_t unique_id[128]) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    return dsgd_comm_init(h, rank, world, unique_id);
+}
+
+}  // extern "C"

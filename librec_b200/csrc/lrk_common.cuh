@@ -1,0 +1,101 @@
+// Shared declarations of the B200-native LibRec MF path (handle layout, error plumbing).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "../../include/librec_b200.h"
+
+#define LRK_MAX_FACTORS 256
+#define LRK_MAX_TOPN 512
+
+struct lrk_handle_s {
+    lrk_config_t cfg{};
+    int k = 0;        // rec.factor.number
+    int ld = 0;       // padded fp32 row length: power of two >= max(k,4); multiple of 128 above 128
+    int G = 0;        // lanes cooperating on one rating (each lane owns V float4 of a row)
+    int V = 1;
+    int32_t U = 0, I = 0;
+    int64_t nnz = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+
+    // train CSR (device): membership for BPR sampling and the top-N train mask
+    int64_t* d_rowptr = nullptr;
+    int32_t* d_col = nullptr;
+    // shuffled COO stream for the SGD epoch (SoA, 12 B / rating)
+    int32_t* d_su = nullptr;
+    int32_t* d_si = nullptr;
+    float* d_sr = nullptr;
+    bool has_train = false;
+
+    // factors: fp32 working copies (padded rows) + fp64 masters (dense rows, what Java sees)
+    float *P32 = nullptr, *Q32 = nullptr, *bu32 = nullptr, *bi32 = nullptr;
+    double *P64 = nullptr, *Q64 = nullptr, *bu64 = nullptr, *bi64 = nullptr;
+    double mu = 0.0;
+    bool has_factors = false;
+    bool f64_valid = false;   // masters are in sync with the fp32 working copies
+
+    double* d_loss = nullptr;   // device accumulator
+    double* h_loss = nullptr;   // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_epoch_ms = 0.f;
+    uint64_t launches = 0;
+
+    // top-N statistics
+    int64_t topn_fast_users = 0, topn_fallback_users = 0;
+    float topn_ms = 0.f;
+    // tensor-core top-N state (bf16 copies, norms); see topn_tc.cuh
+    void* tc = nullptr;
+
+    // DSGD
+    void* comm = nullptr;   // ncclComm_t
+    int rank = 0, world = 1;
+    void* dsgd = nullptr;   // DsgdState*
+
+    std::string err;
+};
+
+extern thread_local std::string g_lrk_tls_error;
+
+static inline int lrk_fail(lrk_handle_s* h, int code, const char* what, const char* detail, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s:%d)", what, detail ? detail : "", file, line);
+    if (h) h->err = buf;
+    g_lrk_tls_error = buf;
+    return code;
+}
+
+#define LRK_CUDA(h, call)                                                                        \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return lrk_fail((h), e__ == cudaErrorMemoryAllocation ? LRK_ERR_NOMEM : LRK_ERR_CUDA, \
+                            #call, cudaGetErrorString(e__), __FILE__, __LINE__);                 \
+    } while (0)
+
+#define LRK_REQUIRE(h, cond, msg)                                                         \
+    do {                                                                                  \
+        if (!(cond)) return lrk_fail((h), LRK_ERR_INVALID, "invalid argument", msg, __FILE__, __LINE__); \
+    } while (0)
+
+#define LRK_LAUNCH_CHECK(h)                  \
+    do {                                     \
+        (h)->launches++;                     \
+        LRK_CUDA((h), cudaGetLastError());   \
+    } while (0)
+
+template <typename T>
+static inline int lrk_dev_alloc(lrk_handle_s* h, T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    LRK_CUDA(h, cudaMalloc((void**)p, count * sizeof(T)));
+    return LRK_OK;
+}
+template <typename T>
+static inline void lrk_dev_free(T** p) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+static inline int lrk_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

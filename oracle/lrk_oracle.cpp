@@ -1,0 +1,683 @@
+// =====================================================================================
+// oracle/lrk_oracle.cpp  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement (C-style C++17, fp64, single thread unless stated) of the LibRec 3.0.0
+// matrix-factorisation hot path, used ONLY as the checker by tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs.  Nothing under librec_b200/ may
+// import, link or call it.
+//
+// PARITY UNPINNED: the reference (pure Java) cannot be executed in the build container
+// (no JVM) and its own tests for this path assert nothing, so there are
+// no golden vectors from the reference itself.  What IS pinned (tests/test_oracle_*.py):
+//   * java.util.Random / nextGaussian / fdlibm log  against published JDK-8 known answers,
+//   * the loader against TextDataModelTestCase's row counts (matrix4by4.txt -> 13 entries),
+//   * the splitter against RatioDataSplitterTestCase's |ratio-0.8| <= 0.01 bound,
+//   * hand-worked one-update micro cases for BiasedMF / PMF / BPR,
+//   * java.util.PriorityQueue heap order against an independent pure-Python replay.
+//
+// Every function cites the reference file:line it restates (paths relative to
+// /root/reference/core/src/main/java/net/librec/).  JDK behaviour (not vendored by the
+// reference; JDK 8, pom.xml:17) is restated from its published algorithms, see SURVEY.md section 9.
+// Build: oracle/Makefile  (g++ -O2 -ffp-contract=off: Java never contracts a*b+c into an FMA).
+// =====================================================================================
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <unordered_map>
+#include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define LRO_API extern "C" __attribute__((visibility("default")))
+
+// -------------------------------------------------------------------------------------
+// fdlibm __ieee754_log  ==  java.lang.StrictMath.log  (called by Random.nextGaussian).
+// Restated from the published fdlibm 5.3 e_log.c algorithm (Sun Microsystems, freely
+// distributable) so that Gaussian init is bit-identical to a JVM, independent of glibc.
+// -------------------------------------------------------------------------------------
+static inline int32_t hi_word(double x) { uint64_t b; memcpy(&b, &x, 8); return (int32_t)(b >> 32); }
+static inline uint32_t lo_word(double x) { uint64_t b; memcpy(&b, &x, 8); return (uint32_t)b; }
+static inline double with_hi(double x, int32_t hi) {
+    uint64_t b; memcpy(&b, &x, 8);
+    b = (b & 0xffffffffULL) | ((uint64_t)(uint32_t)hi << 32);
+    memcpy(&x, &b, 8); return x;
+}
+
+static double fdlibm_log(double x) {
+    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                        two54 = 1.80143985094819840000e+16,
+                        Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+                        Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+                        Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                        Lg7 = 1.479819860511658591e-01;
+    const double zero = 0.0;
+    double hfsq, f, s, z, R, w, t1, t2, dk;
+    int32_t k, hx, i, j;
+    uint32_t lx;
+    hx = hi_word(x); lx = lo_word(x);
+    k = 0;
+    if (hx < 0x00100000) {
+        if (((hx & 0x7fffffff) | lx) == 0) return -two54 / zero;
+        if (hx < 0) return (x - x) / zero;
+        k -= 54; x *= two54; hx = hi_word(x);
+    }
+    if (hx >= 0x7ff00000) return x + x;
+    k += (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    i = (hx + 0x95f64) & 0x100000;
+    x = with_hi(x, hx | (i ^ 0x3ff00000));
+    k += (i >> 20);
+    f = x - 1.0;
+    if ((0x000fffff & (2 + hx)) < 3) {
+        if (f == zero) { if (k == 0) return zero; dk = (double)k; return dk * ln2_hi + dk * ln2_lo; }
+        R = f * f * (0.5 - 0.33333333333333333 * f);
+        if (k == 0) return f - R;
+        dk = (double)k; return dk * ln2_hi - ((R - dk * ln2_lo) - f);
+    }
+    s = f / (2.0 + f);
+    dk = (double)k;
+    z = s * s;
+    i = hx - 0x6147a;
+    w = z * z;
+    j = 0x6b851 - hx;
+    t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    i |= j;
+    R = t2 + t1;
+    if (i > 0) {
+        hfsq = 0.5 * f * f;
+        if (k == 0) return f - (hfsq - s * (hfsq + R));
+        return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+    } else {
+        if (k == 0) return f - s * (f - R);
+        return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+    }
+}
+LRO_API double lro_strictmath_log(double x) { return fdlibm_log(x); }
+
+// -------------------------------------------------------------------------------------
+// java.util.Random (JDK 8) -- the ONE global generator behind math/algorithm/Randoms.java:31
+// (static Random r), seeded once by job/RecommenderJob.java:72-79.
+// -------------------------------------------------------------------------------------
+struct JRandom {
+    uint64_t seed = 0;
+    bool have_next = false;
+    double next_gauss = 0.0;
+};
+static JRandom g_rng;
+
+static inline void jr_seed(JRandom* r, int64_t s) {
+    r->seed = ((uint64_t)s ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);
+    r->have_next = false;
+}
+static inline int32_t jr_next(JRandom* r, int bits) {
+    r->seed = (r->seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+    return (int32_t)(uint32_t)(r->seed >> (48 - bits));
+}
+static inline int32_t jr_next_int(JRandom* r) { return jr_next(r, 32); }
+static inline int32_t jr_next_int_bound(JRandom* r, int32_t bound) {
+    int32_t v = jr_next(r, 31);
+    int32_t m = bound - 1;
+    if ((bound & m) == 0) {
+        v = (int32_t)(((int64_t)bound * (int64_t)v) >> 31);
+    } else {
+        int32_t u = v;
+        for (;;) {
+            v = u % bound;
+            // Java int arithmetic wraps: "u - r + m < 0"
+            int32_t t = (int32_t)((uint32_t)u - (uint32_t)v + (uint32_t)m);
+            if (t >= 0) break;
+            u = jr_next(r, 31);
+        }
+    }
+    return v;
+}
+static inline double jr_next_double(JRandom* r) {
+    int64_t a = jr_next(r, 26);
+    int64_t b = jr_next(r, 27);
+    return (double)((a << 27) + b) * 0x1.0p-53;
+}
+static inline double jr_next_gaussian(JRandom* r) {
+    if (r->have_next) { r->have_next = false; return r->next_gauss; }
+    double v1, v2, s;
+    do {
+        v1 = 2 * jr_next_double(r) - 1;
+        v2 = 2 * jr_next_double(r) - 1;
+        s = v1 * v1 + v2 * v2;
+    } while (s >= 1 || s == 0);
+    double multiplier = sqrt(-2 * fdlibm_log(s) / s);  // StrictMath.sqrt is IEEE-exact
+    r->next_gauss = v2 * multiplier;
+    r->have_next = true;
+    return v1 * multiplier;
+}
+
+// Randoms.seed / uniform(int) / uniform() / gaussian : math/algorithm/Randoms.java:41-58,117-130,158-160
+LRO_API void lro_seed(int64_t seed) { jr_seed(&g_rng, seed); }
+LRO_API int32_t lro_next_int() { return jr_next_int(&g_rng); }
+LRO_API int32_t lro_uniform_int(int32_t range) { return 0 + jr_next_int_bound(&g_rng, range - 0); }
+LRO_API double lro_uniform() { return 0.0 + (1.0 - 0.0) * jr_next_double(&g_rng); }
+LRO_API double lro_next_gaussian() { return jr_next_gaussian(&g_rng); }
+LRO_API double lro_gaussian(double mu, double sigma) { return mu + sigma * jr_next_gaussian(&g_rng); }
+// DenseMatrix.init -> assign row-major (math/structure/DenseMatrix.java:77-97); DenseVector.init (DenseVector.java:26-28)
+LRO_API void lro_gaussian_fill(double* out, int64_t n, double mu, double sigma) {
+    for (int64_t i = 0; i < n; ++i) out[i] = lro_gaussian(mu, sigma);
+}
+LRO_API void lro_rng_get_state(uint64_t* seed, int32_t* have, double* nextg) {
+    *seed = g_rng.seed; *have = g_rng.have_next; *nextg = g_rng.next_gauss;
+}
+LRO_API void lro_rng_set_state(uint64_t seed, int32_t have, double nextg) {
+    g_rng.seed = seed; g_rng.have_next = have != 0; g_rng.next_gauss = nextg;
+}
+
+// Float.valueOf(str) then widening to double (conf/Configuration.java:232-239; the float fields
+// learnRate/regUser/regItem at recommender/MatrixFactorizationRecommender.java:16,54,59).
+LRO_API double lro_float_promote(const char* s) { return (double)strtof(s, nullptr); }
+
+// -------------------------------------------------------------------------------------
+// Loader: data/convertor/TextDataConvertor.java:142-200 (regex "[\t;, ]" from
+// data/model/TextDataModel.java:65; first blank line stops the file :176-178),
+// math/structure/DataFrame.java:370-379 (first-seen dense ids), :237-261 (reverse scan into a
+// table => on a duplicate (u,i) the EARLIEST line wins; binThold>=0 -> rate>thold ? 1.0 : -1.0),
+// rows sorted by column (math/structure/VectorBasedSequentialSparseVector.java:74-117).
+// -------------------------------------------------------------------------------------
+struct LroCsr {
+    int32_t U = 0, I = 0;
+    std::vector<int64_t> rowptr;
+    std::vector<int32_t> col;
+    std::vector<double> val;
+    std::vector<std::string> user_ids, item_ids;
+};
+
+static void split_fields(const std::string& line, const char* seps, std::vector<std::string>& out) {
+    out.clear();
+    std::string cur;
+    for (char c : line) {
+        if (strchr(seps, c) != nullptr && c != '\0') { out.push_back(cur); cur.clear(); }
+        else cur.push_back(c);
+    }
+    out.push_back(cur);
+    while (!out.empty() && out.back().empty()) out.pop_back();  // Pattern.split drops trailing empties
+}
+static bool is_blank(const std::string& s) {
+    for (char c : s) if ((unsigned char)c > ' ') return false;  // String.trim(): chars <= U+0020
+    return true;
+}
+
+LRO_API void* lro_csr_load_text(const char* path, double bin_thold) {
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return nullptr;
+    std::unordered_map<std::string, int32_t> umap, imap;
+    std::vector<int32_t> us, is;
+    std::vector<double> rs;
+    LroCsr* m = new LroCsr();
+    std::vector<std::string> f;
+    std::string line;
+    char buf[1 << 16];
+    while (fgets(buf, sizeof buf, fp)) {
+        line.assign(buf);
+        while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
+        if (is_blank(line)) break;
+        split_fields(line, "\t;, ", f);
+        if (f.size() < 3) continue;
+        auto iu = umap.find(f[0]);
+        int32_t u;
+        if (iu == umap.end()) { u = (int32_t)umap.size(); umap.emplace(f[0], u); m->user_ids.push_back(f[0]); }
+        else u = iu->second;
+        auto ii = imap.find(f[1]);
+        int32_t i;
+        if (ii == imap.end()) { i = (int32_t)imap.size(); imap.emplace(f[1], i); m->item_ids.push_back(f[1]); }
+        else i = ii->second;
+        us.push_back(u); is.push_back(i); rs.push_back(strtod(f[2].c_str(), nullptr));
+    }
+    fclose(fp);
+    m->U = (int32_t)umap.size(); m->I = (int32_t)imap.size();
+    // earliest line wins: stable sort by (u,i), keep first of each run
+    const size_t n = us.size();
+    std::vector<size_t> ord(n);
+    for (size_t t = 0; t < n; ++t) ord[t] = t;
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+        if (us[a] != us[b]) return us[a] < us[b];
+        return is[a] < is[b];
+    });
+    m->rowptr.assign((size_t)m->U + 1, 0);
+    for (size_t t = 0; t < n; ++t) {
+        size_t a = ord[t];
+        if (t > 0 && us[ord[t - 1]] == us[a] && is[ord[t - 1]] == is[a]) continue;
+        double r = rs[a];
+        if (bin_thold >= 0) r = r > bin_thold ? 1.0 : -1.0;
+        m->col.push_back(is[a]); m->val.push_back(r);
+        m->rowptr[(size_t)us[a] + 1]++;
+    }
+    for (int32_t u = 0; u < m->U; ++u) m->rowptr[u + 1] += m->rowptr[u];
+    return m;
+}
+LRO_API void lro_csr_dims(void* h, int32_t* U, int32_t* I, int64_t* nnz) {
+    LroCsr* m = (LroCsr*)h; *U = m->U; *I = m->I; *nnz = (int64_t)m->col.size();
+}
+LRO_API void lro_csr_copy(void* h, int64_t* rowptr, int32_t* col, double* val) {
+    LroCsr* m = (LroCsr*)h;
+    memcpy(rowptr, m->rowptr.data(), m->rowptr.size() * 8);
+    memcpy(col, m->col.data(), m->col.size() * 4);
+    memcpy(val, m->val.data(), m->val.size() * 8);
+}
+// outer (raw string) id of an inner user/item index, parsed as integer (-1 when not numeric)
+LRO_API int64_t lro_csr_outer_id(void* h, int32_t is_item, int32_t inner) {
+    LroCsr* m = (LroCsr*)h;
+    const std::string& s = is_item ? m->item_ids[inner] : m->user_ids[inner];
+    char* e = nullptr; long long v = strtoll(s.c_str(), &e, 10);
+    return (e && *e == 0) ? (int64_t)v : -1;
+}
+LRO_API void lro_csr_free(void* h) { delete (LroCsr*)h; }
+
+// -------------------------------------------------------------------------------------
+// Splitter: data/splitter/RatioDataSplitter.java:136-156 -- one Randoms.uniform() per entry of
+// the preference matrix in CSR order; rdm < ratio -> train.  reshape() then drops exact 0.0
+// values from both sides (math/structure/OrderedIntDoubleMapping.java:342-359).
+// is_train[e] = 1 train, 0 test, 2 dropped (value == 0.0).
+// -------------------------------------------------------------------------------------
+LRO_API void lro_split_ratio(int64_t nnz, const double* val, double ratio, uint8_t* is_train) {
+    for (int64_t e = 0; e < nnz; ++e) {
+        double rdm = lro_uniform();
+        uint8_t t = rdm < ratio ? 1 : 0;
+        if (val[e] == 0.0) t = 2;
+        is_train[e] = t;
+    }
+}
+
+// -------------------------------------------------------------------------------------
+// MatrixRecommender.setup: recommender/MatrixRecommender.java:88-128
+// globalMean = sum in CSR order / nnz (math/structure/RowSequentialAccessSparseMatrix.java:161-167);
+// minRate/maxRate from the rating set, minRate=0 if equal (:103-107).
+// -------------------------------------------------------------------------------------
+LRO_API void lro_matrix_setup(int64_t nnz, const double* val, double* global_mean, double* min_rate, double* max_rate) {
+    double s = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (int64_t e = 0; e < nnz; ++e) { s += val[e]; mn = std::min(mn, val[e]); mx = std::max(mx, val[e]); }
+    *global_mean = s / (double)nnz;
+    if (mn == mx) mn = 0;
+    *min_rate = mn; *max_rate = mx;
+}
+
+// MatrixFactorizationRecommender.setup: recommender/MatrixFactorizationRecommender.java:80-93.
+// Gaussian init N(0, (double)0.001f) in the order userFactors, itemFactors, impUserFactors,
+// impItemFactors (the fork's two extra matrices consume RNG draws), then for BiasedMF the
+// biases userBiases, itemBiases (recommender/cf/rating/BiasedMFRecommender.java:59-63).
+LRO_API void lro_mf_setup(int32_t U, int32_t I, int32_t k, double* P, double* Q, double* bu, double* bi) {
+    const double mean = (double)0.0f, sd = (double)0.001f;
+    lro_gaussian_fill(P, (int64_t)U * k, mean, sd);
+    lro_gaussian_fill(Q, (int64_t)I * k, mean, sd);
+    for (int64_t t = 0; t < (int64_t)U * k; ++t) (void)lro_gaussian(mean, sd);  // impUserFactors
+    for (int64_t t = 0; t < (int64_t)I * k; ++t) (void)lro_gaussian(mean, sd);  // impItemFactors
+    if (bu) lro_gaussian_fill(bu, U, mean, sd);
+    if (bi) lro_gaussian_fill(bi, I, mean, sd);
+}
+
+// DenseVector.dot: math/structure/DenseVector.java:104-111 -- left to right from 0.0
+static inline double dot_lr(const double* a, const double* b, int k) {
+    double r = 0.0;
+    for (int f = 0; f < k; ++f) r += b[f] * a[f];
+    return r;
+}
+
+enum { LRO_BIASEDMF = 0, LRO_PMF = 1, LRO_BPR = 2 };
+
+// predict(): BiasedMFRecommender.java:118-120 ; MatrixFactorizationRecommender.java:104-106
+static inline double predict_raw(int model, int k, const double* P, const double* Q, const double* bu,
+                                 const double* bi, double mu, int32_t u, int32_t i) {
+    double d = dot_lr(P + (int64_t)u * k, Q + (int64_t)i * k, k);
+    if (model == LRO_BIASEDMF) return d + bu[u] + bi[i] + mu;
+    return d;
+}
+
+// -------------------------------------------------------------------------------------
+// One BiasedMF epoch: recommender/cf/rating/BiasedMFRecommender.java:68-100.
+// `order` (optional) replaces CSR order by an explicit entry permutation -- that is NOT the
+// reference's behaviour; it exists to separate ordering error from kernel error.
+// lr/regU/regI are the float fields promoted to double; regB is a double (:36,:56).
+// -------------------------------------------------------------------------------------
+LRO_API double lro_biasedmf_epoch(int32_t U, const int64_t* rowptr, const int32_t* col, const double* val,
+                                  int32_t k, double* P, double* Q, double* bu, double* bi, double mu,
+                                  float lr_f, float regU_f, float regI_f, double regB,
+                                  const int64_t* order, const int32_t* row_of) {
+    const double learnRate = (double)lr_f, regUser = (double)regU_f, regItem = (double)regI_f;
+    double loss = 0.0;
+    const int64_t nnz = rowptr[U];
+    int32_t u = 0;
+    for (int64_t t = 0; t < nnz; ++t) {
+        int64_t e = order ? order[t] : t;
+        if (order) u = row_of[e];
+        else while (rowptr[u + 1] <= e) ++u;
+        const int32_t i = col[e];
+        double* pu = P + (int64_t)u * k;
+        double* qi = Q + (int64_t)i * k;
+        const double predictRating = dot_lr(pu, qi, k) + bu[u] + bi[i] + mu;
+        const double error = val[e] - predictRating;
+        loss += error * error;
+        const double ub = bu[u];
+        bu[u] += learnRate * (error - regB * ub);
+        loss += regB * ub * ub;
+        const double ib = bi[i];
+        bi[i] += learnRate * (error - regB * ib);
+        loss += regB * ib * ib;
+        for (int f = 0; f < k; ++f) {
+            const double uf = pu[f], itf = qi[f];
+            pu[f] += learnRate * (error * itf - regUser * uf);
+            qi[f] += learnRate * (error * uf - regItem * itf);
+            loss += regUser * uf * uf + regItem * itf * itf;
+        }
+    }
+    loss *= 0.5;
+    return loss;
+}
+
+// Vanilla PMF epoch: recommender/cf/rating/PMFSimilarityRecommender.java:59-90 (identical loop kept
+// commented in PMFRatingRecommender.java:130-162); predict = MatrixFactorizationRecommender.java:104-106.
+LRO_API double lro_pmf_epoch(int32_t U, const int64_t* rowptr, const int32_t* col, const double* val,
+                             int32_t k, double* P, double* Q, float lr_f, float regU_f, float regI_f,
+                             const int64_t* order, const int32_t* row_of) {
+    const double learnRate = (double)lr_f, regUser = (double)regU_f, regItem = (double)regI_f;
+    double loss = 0.0;
+    const int64_t nnz = rowptr[U];
+    int32_t u = 0;
+    for (int64_t t = 0; t < nnz; ++t) {
+        int64_t e = order ? order[t] : t;
+        if (order) u = row_of[e];
+        else while (rowptr[u + 1] <= e) ++u;
+        const int32_t i = col[e];
+        double* pu = P + (int64_t)u * k;
+        double* qi = Q + (int64_t)i * k;
+        const double error = val[e] - dot_lr(pu, qi, k);
+        loss += error * error;
+        for (int f = 0; f < k; ++f) {
+            const double uf = pu[f], itf = qi[f];
+            pu[f] += learnRate * (error * itf - regUser * uf);
+            qi[f] += learnRate * (error * uf - regItem * itf);
+            loss += regUser * uf * uf + regItem * itf * itf;
+        }
+    }
+    loss *= 0.5;
+    return loss;
+}
+
+// Maths.logistic: math/algorithm/Maths.java:127-129  (1 / (1 + Math.exp(-x)))
+static inline double logistic(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// One BPR epoch: recommender/cf/ranking/BPRRecommender.java:48-93.  Draws come from the global
+// java.util.Random, interleaved with updates.  Membership test (fastutil IntOpenHashSet,
+// :101-112) is restated as a binary search in the sorted row -- same truth value.
+// When `trip` is non-null the (u,i,j) triples are taken from it instead of the RNG
+// (3*n int32) -- NOT reference behaviour; used to feed the GPU kernel's own samples through
+// the reference arithmetic.  When `trip_out` is non-null the drawn triples are recorded.
+LRO_API double lro_bpr_epoch(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, int32_t k,
+                             double* P, double* Q, float lr_f, float regU_f, float regI_f,
+                             int64_t n_samples, const int32_t* trip, int32_t* trip_out) {
+    const double learnRate = (double)lr_f, regUser = (double)regU_f, regItem = (double)regI_f;
+    double loss = 0.0;
+    for (int64_t s = 0; s < n_samples; ++s) {
+        int32_t u, pi, nj;
+        if (trip) { u = trip[3 * s]; pi = trip[3 * s + 1]; nj = trip[3 * s + 2]; }
+        else {
+            for (;;) {
+                u = lro_uniform_int(U);
+                const int64_t b = rowptr[u], e = rowptr[u + 1];
+                const int64_t len = e - b;
+                if (len == 0 || len == I) continue;
+                pi = col[b + lro_uniform_int((int32_t)len)];
+                do { nj = lro_uniform_int(I); } while (std::binary_search(col + b, col + e, nj));
+                break;
+            }
+        }
+        if (trip_out) { trip_out[3 * s] = u; trip_out[3 * s + 1] = pi; trip_out[3 * s + 2] = nj; }
+        double* pu = P + (int64_t)u * k;
+        double* qi = Q + (int64_t)pi * k;
+        double* qj = Q + (int64_t)nj * k;
+        const double diff = dot_lr(pu, qi, k) - dot_lr(pu, qj, k);
+        loss += -log(logistic(diff));
+        const double deri = logistic(-diff);
+        for (int f = 0; f < k; ++f) {
+            const double uf = pu[f], pf = qi[f], nf = qj[f];
+            pu[f] += learnRate * (deri * (pf - nf) - regUser * uf);
+            qi[f] += learnRate * (deri * uf - regItem * pf);
+            qj[f] += learnRate * (deri * (-uf) - regItem * nf);
+            loss += regUser * uf * uf + regItem * pf * pf + regItem * nf * nf;
+        }
+    }
+    return loss;  // no *0.5 for BPR
+}
+
+// AbstractRecommender.isConverged: recommender/AbstractRecommender.java:249-267.
+// returns 1 converged, 0 not, -1 = would throw LibrecException (NaN / Inf loss)
+LRO_API int32_t lro_is_converged(double last_loss, double loss, float* delta_out) {
+    float delta = (float)(last_loss - loss);
+    if (delta_out) *delta_out = delta;
+    if (std::isnan(loss) || std::isinf(loss)) return -1;
+    return fabs((double)delta) < 1e-5 ? 1 : 0;   // Math.abs(float) widened against the double literal
+}
+
+// MatrixFactorizationRecommender.updateLRate: recommender/MatrixFactorizationRecommender.java:121-139
+// (float arithmetic on learnRate).  Returns the new learn rate; *last_loss is updated.
+LRO_API float lro_update_lrate(float learnRate, float maxLearnRate, int32_t iter, int32_t bold_driver, float decay,
+                               double loss, double* last_loss) {
+    if (learnRate < 0.0) { *last_loss = loss; return learnRate; }
+    if (bold_driver && iter > 1) {
+        learnRate = fabs(*last_loss) > fabs(loss) ? learnRate * 1.05f : learnRate * 0.5f;
+    } else if (decay > 0 && decay < 1) {
+        learnRate *= decay;
+    }
+    if (maxLearnRate > 0 && learnRate > maxLearnRate) learnRate = maxLearnRate;
+    *last_loss = loss;
+    return learnRate;
+}
+
+// Full trainModel loop (BiasedMF :67-107, PMF, BPR :45-99).  losses_out[iter-1] = loss of iter.
+// returns iterations executed, or -iter when isConverged would throw at that iteration.
+LRO_API int32_t lro_train(int32_t model, int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col,
+                          const double* val, int32_t k, double* P, double* Q, double* bu, double* bi, double mu,
+                          float learnRate, float maxLearnRate, float regU, float regI, double regB,
+                          int32_t num_iter, int32_t early_stop, int32_t bold_driver, float decay,
+                          double* losses_out) {
+    double last_loss = 0.0;   // AbstractRecommender.lastLoss initial value (:76)
+    int32_t done = 0;
+    for (int32_t iter = 1; iter <= num_iter; ++iter) {
+        double loss;
+        if (model == LRO_BIASEDMF) loss = lro_biasedmf_epoch(U, rowptr, col, val, k, P, Q, bu, bi, mu, learnRate, regU, regI, regB, nullptr, nullptr);
+        else if (model == LRO_PMF) loss = lro_pmf_epoch(U, rowptr, col, val, k, P, Q, learnRate, regU, regI, nullptr, nullptr);
+        else loss = lro_bpr_epoch(U, I, rowptr, col, k, P, Q, learnRate, regU, regI, rowptr[U], nullptr, nullptr);
+        if (losses_out) losses_out[iter - 1] = loss;
+        done = iter;
+        int32_t c = lro_is_converged(last_loss, loss, nullptr);
+        if (c < 0) return -iter;
+        if (c == 1 && early_stop) break;
+        learnRate = lro_update_lrate(learnRate, maxLearnRate, iter, bold_driver, decay, loss, &last_loss);
+    }
+    return done;
+}
+
+// -------------------------------------------------------------------------------------
+// Rating prediction + RMSE / MAE:
+// recommender/MatrixRecommender.java:211-248,272-284 (clamp to [minRate,maxRate]; NaN -> globalMean),
+// eval/rating/RMSEEvaluator.java:33-69 (Math.pow(d,2) == d*d exactly), eval/rating/MAEEvaluator.java:34-70,
+// both accumulated in test-CSR order.  pred_out (optional) receives the bounded predictions.
+// -------------------------------------------------------------------------------------
+LRO_API void lro_eval_rating(int32_t model, int32_t U, const int64_t* t_rowptr, const int32_t* t_col, const double* t_val,
+                             int32_t k, const double* P, const double* Q, const double* bu, const double* bi, double mu,
+                             double min_rate, double max_rate, double* rmse, double* mae, double* pred_out) {
+    double se = 0.0, ae = 0.0;
+    int64_t n = 0;
+    for (int32_t u = 0; u < U; ++u)
+        for (int64_t e = t_rowptr[u]; e < t_rowptr[u + 1]; ++e) {
+            double p = predict_raw(model, k, P, Q, bu, bi, mu, u, t_col[e]);
+            if (p > max_rate) p = max_rate; else if (p < min_rate) p = min_rate;
+            if (std::isnan(p)) p = mu;
+            if (pred_out) pred_out[e] = p;
+            const double d = t_val[e] - p;
+            se += d * d; ae += fabs(d); ++n;
+        }
+    *rmse = n > 0 ? sqrt(se / (double)n) : 0.0;
+    *mae = n > 0 ? ae / (double)n : 0.0;
+}
+
+LRO_API void lro_predict_pairs(int32_t model, int32_t k, const double* P, const double* Q, const double* bu,
+                               const double* bi, double mu, const int32_t* us, const int32_t* is, int64_t n, double* out) {
+    for (int64_t t = 0; t < n; ++t) out[t] = predict_raw(model, k, P, Q, bu, bi, mu, us[t], is[t]);
+}
+
+// -------------------------------------------------------------------------------------
+// Top-N: recommender/MatrixRecommender.java:153-201 + util/Lists.java:416-468
+// (+ recommender/item/RecommendedList.java:85-88).
+// java.util.PriorityQueue (JDK 8) siftUp / siftDown restated; comparator for inverse=true is
+// Double.compareTo ascending (min-heap); entry replaces the min only if STRICTLY greater;
+// result = heap-array order, then a stable descending sort (Collections.sort == TimSort).
+// -------------------------------------------------------------------------------------
+static inline int jcompare(double a, double b) {     // Double.compare
+    if (a < b) return -1;
+    if (a > b) return 1;
+    int64_t x, y; memcpy(&x, &a, 8); memcpy(&y, &b, 8);   // doubleToLongBits (NaN never reaches here)
+    return x == y ? 0 : (x < y ? -1 : 1);
+}
+struct KV { int32_t key; double value; };
+struct JHeap {
+    std::vector<KV> q; int size = 0;
+    void sift_up(int kpos, KV x) {
+        while (kpos > 0) {
+            int parent = (int)((unsigned)(kpos - 1) >> 1);
+            if (jcompare(x.value, q[parent].value) >= 0) break;
+            q[kpos] = q[parent]; kpos = parent;
+        }
+        q[kpos] = x;
+    }
+    void sift_down(int kpos, KV x) {
+        int half = (int)((unsigned)size >> 1);
+        while (kpos < half) {
+            int child = (kpos << 1) + 1; int right = child + 1;
+            if (right < size && jcompare(q[child].value, q[right].value) > 0) child = right;
+            if (jcompare(x.value, q[child].value) <= 0) break;
+            q[kpos] = q[child]; kpos = child;
+        }
+        q[kpos] = x;
+    }
+    void add(KV x) { int i = size; size = i + 1; if (i == 0) q[0] = x; else sift_up(i, x); }
+    void poll() { int s = --size; KV x = q[s]; if (s != 0) sift_down(0, x); }
+};
+
+static int topn_user(int model, int32_t I, int32_t k, const double* P, const double* Q, const double* bu,
+                     const double* bi, double mu, const int32_t* tcol, int64_t tlen, int32_t u, int32_t topN,
+                     int32_t* out_items, double* out_scores, JHeap& h, std::vector<KV>& list) {
+    // MatrixRecommender.java:168-190 : all items not in the train row, NaN dropped
+    list.clear();
+    int64_t tp = 0;
+    for (int32_t i = 0; i < I; ++i) {
+        if (tp < tlen && tcol[tp] == i) { ++tp; continue; }
+        double pr = predict_raw(model, k, P, Q, bu, bi, mu, u, i);
+        if (std::isnan(pr)) continue;
+        list.push_back(KV{i, pr});
+    }
+    // Lists.sortKeyValueListTopK(list, true, topN) : Lists.java:416-445
+    int kk = (int)list.size() > topN ? topN : (int)list.size();
+    if (kk == 0) return 0;
+    h.q.resize(kk); h.size = 0;
+    size_t it = 0;
+    for (int t = 0; t < kk; ++t) h.add(list[it++]);
+    for (; it < list.size(); ++it) {
+        int res = jcompare(list[it].value, h.q[0].value);
+        if (-res < 0) { h.poll(); h.add(list[it]); }
+    }
+    std::vector<KV> out(h.q.begin(), h.q.begin() + h.size);
+    std::stable_sort(out.begin(), out.end(), [](const KV& a, const KV& b) { return jcompare(a.value, b.value) > 0; });
+    for (int t = 0; t < kk; ++t) { out_items[t] = out[t].key; out_scores[t] = out[t].value; }
+    return kk;
+}
+
+// users == NULL -> users 0..nq-1 (MatrixRecommender.recommendRank() :137-144).
+// nthreads mirrors contextList.parallelStream() (:164); results are per-user independent.
+LRO_API void lro_recommend_rank(int32_t model, int32_t U, int32_t I, int32_t k, const double* P, const double* Q,
+                                const double* bu, const double* bi, double mu, const int64_t* tr_rowptr,
+                                const int32_t* tr_col, int32_t topN, const int32_t* users, int32_t nq,
+                                int32_t* out_items, double* out_scores, int32_t* out_counts, int32_t nthreads) {
+    (void)U;
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        JHeap h; std::vector<KV> list; list.reserve((size_t)I);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 16)
+#endif
+        for (int32_t c = 0; c < nq; ++c) {
+            int32_t u = users ? users[c] : c;
+            const int64_t b = tr_rowptr ? tr_rowptr[u] : 0, e = tr_rowptr ? tr_rowptr[u + 1] : 0;
+            for (int t = 0; t < topN; ++t) { out_items[(int64_t)c * topN + t] = -1; out_scores[(int64_t)c * topN + t] = 0.0; }
+            out_counts[c] = topn_user(model, I, k, P, Q, bu, bi, mu, tr_col ? tr_col + b : nullptr, e - b, u, topN,
+                                      out_items + (int64_t)c * topN, out_scores + (int64_t)c * topN, h, list);
+        }
+    }
+}
+
+// Raw heap trace for the PriorityQueue pin test: feeds `n` values through
+// sortKeyValueListTopK(inverse=true,k) and returns the heap-array order BEFORE the final sort.
+LRO_API int32_t lro_heap_trace(const double* values, int32_t n, int32_t k, int32_t* heap_keys) {
+    int kk = n > k ? k : n;
+    if (kk == 0) return 0;
+    JHeap h; h.q.resize(kk);
+    int it = 0;
+    for (int t = 0; t < kk; ++t, ++it) h.add(KV{it, values[it]});
+    for (; it < n; ++it) if (-jcompare(values[it], h.q[0].value) < 0) { h.poll(); h.add(KV{it, values[it]}); }
+    for (int t = 0; t < kk; ++t) heap_keys[t] = h.q[t].key;
+    return kk;
+}
+
+// -------------------------------------------------------------------------------------
+// "Best-effort CPU" variant (NOT the reference's behaviour, reported separately by bench.py):
+// fp32 Hogwild over an explicit order with OpenMP threads.  SURVEY.md 8(d).
+// -------------------------------------------------------------------------------------
+LRO_API double lro_sgd_epoch_hogwild_f32(int32_t model, const int32_t* us, const int32_t* is, const float* rs, int64_t n,
+                                         int32_t k, float* P, float* Q, float* bu, float* bi, float mu,
+                                         float lr, float regU, float regI, float regB, int32_t nthreads) {
+    double loss = 0.0;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads) reduction(+ : loss) schedule(static)
+#endif
+    for (int64_t t = 0; t < n; ++t) {
+        const int32_t u = us[t], i = is[t];
+        float* pu = P + (int64_t)u * k; float* qi = Q + (int64_t)i * k;
+        float d = 0.f;
+        for (int f = 0; f < k; ++f) d += pu[f] * qi[f];
+        float l = 0.f;
+        if (model == LRO_BIASEDMF) {
+            d += bu[u] + bi[i] + mu;
+            const float e = rs[t] - d;
+            const float ub = bu[u], ib = bi[i];
+            bu[u] = ub + lr * (e - regB * ub); bi[i] = ib + lr * (e - regB * ib);
+            l = e * e + regB * ub * ub + regB * ib * ib;
+            for (int f = 0; f < k; ++f) {
+                const float uf = pu[f], itf = qi[f];
+                pu[f] = uf + lr * (e * itf - regU * uf); qi[f] = itf + lr * (e * uf - regI * itf);
+                l += regU * uf * uf + regI * itf * itf;
+            }
+        } else {
+            const float e = rs[t] - d;
+            l = e * e;
+            for (int f = 0; f < k; ++f) {
+                const float uf = pu[f], itf = qi[f];
+                pu[f] = uf + lr * (e * itf - regU * uf); qi[f] = itf + lr * (e * uf - regI * itf);
+                l += regU * uf * uf + regI * itf * itf;
+            }
+        }
+        loss += (double)l;
+    }
+    return 0.5 * loss;
+}
+
+LRO_API int32_t lro_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+LRO_API const char* lro_version() { return "lrk-oracle 0.1 (LibRec 3.0.0 MF path restatement; parity unpinned)"; }

@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/librec_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "librec_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lrk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(capi):
+    names = _declared()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(capi.lib_path())
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    # and the ctypes binding knows every one of them
+    assert sorted(capi.SIGNATURES) == names
+
+
+def test_version_and_abi(capi):
+    L = capi.load()
+    assert b"sm_100a" in L.lrk_version()
+    assert L.lrk_abi_version() == 1
+    assert L.lrk_device_count() >= 0
+
+
+def test_no_cpu_fallback(capi):
+    """without a B200 every compute entry fails loudly -- there is no CPU path in the product"""
+    if capi.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(capi.LibrecException) as e:
+        capi.Handle(capi.MODEL_BIASEDMF, 8)
+    assert e.value.status in (capi.ERR_CUDA, capi.ERR_INVALID)
+
+
+def test_bad_config_is_rejected(capi):
+    for kw in (dict(model=7, num_factors=8), dict(model=0, num_factors=0), dict(model=0, num_factors=257)):
+        with pytest.raises(capi.LibrecException):
+            capi.Handle(kw["model"], kw["num_factors"])
+
+
+def test_product_never_imports_oracle():
+    """librec_b200/ must not reference oracle/ (the oracle is test infrastructure)"""
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "librec_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"(from|import)\s+oracle|lrk_oracle|lro_", txt):
+                    bad.append(f)
+    assert not bad, bad

@@ -1,0 +1,180 @@
+"""GPU: SGD epoch parity through the C ABI against the oracle (same seeded inputs)."""
+import numpy as np
+import pytest
+
+from conftest import rng_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def _conflict_free(O, n, I, seed):
+    """every user and item appears exactly once -> no concurrent updates, result is order-free"""
+    rng = np.random.default_rng(seed)
+    items = rng.permutation(I)[:n].astype(np.int32)
+    vals = rng.integers(1, 11, n).astype(np.float64) / 2.0
+    return O.Csr(n, I, np.arange(n + 1, dtype=np.int64), items, vals)
+
+
+@pytest.mark.parametrize("model_name,k", [("biasedmf", 64), ("biasedmf", 20), ("pmf", 128), ("pmf", 6), ("biasedmf", 200), ("pmf", 1)])
+@pytest.mark.parametrize("mode", ["atomic", "hogwild"])
+def test_conflict_free_epoch_matches_oracle(O, capi, model_name, k, mode):
+    n, I = 3000, 4000
+    tr = _conflict_free(O, n, I, 3)
+    rng = np.random.default_rng(1)
+    P = rng.normal(0, 0.1, (n, k)); Q = rng.normal(0, 0.1, (I, k))
+    biased = model_name == "biasedmf"
+    bu = rng.normal(0, 0.1, n) if biased else None
+    bi = rng.normal(0, 0.1, I) if biased else None
+    mu = 3.0
+    # the device works on fp32 copies: start the oracle from the same rounded values
+    P, Q = P.astype(np.float32).astype(np.float64), Q.astype(np.float32).astype(np.float64)
+    if biased:
+        bu, bi = bu.astype(np.float32).astype(np.float64), bi.astype(np.float32).astype(np.float64)
+    model = capi.MODEL_BIASEDMF if biased else capi.MODEL_PMF
+    with capi.Handle(model, k, update_mode=capi.UPDATE_ATOMIC if mode == "atomic" else capi.UPDATE_HOGWILD) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q, bu, bi, mu)
+        loss = h.sgd_epoch(0.01, 0.02, 0.03, 0.04)
+        gP, gQ, gbu, gbi = h.get_factors()
+    oP, oQ = P.copy(), Q.copy()
+    if biased:
+        obu, obi = bu.copy(), bi.copy()
+        oloss = O.lib().lro_biasedmf_epoch(tr.U, tr.rowptr, tr.col, tr.val, k, oP, oQ, obu, obi, mu, 0.01, 0.02, 0.03, 0.04, None, None)
+    else:
+        oloss = O.lib().lro_pmf_epoch(tr.U, tr.rowptr, tr.col, tr.val, k, oP, oQ, 0.01, 0.02, 0.03, None, None)
+    # fp32 arithmetic vs fp64: tolerance = a few fp32 ulps of the operands (|values| <= ~5)
+    assert np.allclose(gP, oP, rtol=0, atol=2e-6) and np.allclose(gQ, oQ, rtol=0, atol=2e-6)
+    if biased:
+        assert np.allclose(gbu, obu, rtol=0, atol=2e-6) and np.allclose(gbi, obi, rtol=0, atol=2e-6)
+    assert abs(loss - oloss) <= 2e-5 * abs(oloss)
+    # rows of users/items without ratings are untouched
+    untouched = np.setdiff1d(np.arange(I), tr.col)
+    assert np.array_equal(gQ[untouched], Q[untouched])
+
+
+def _train_gpu(capi, model, tr, k, P, Q, bu, bi, mu, lr, reg_u, reg_i, reg_b, iters, seed=1):
+    with capi.Handle(model, k, seed=seed) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q, bu, bi, mu)
+        losses = [h.sgd_epoch(lr, reg_u, reg_i, reg_b, it) for it in range(1, iters + 1)]
+        return h.get_factors(), losses
+
+
+def test_c1_biasedmf_rmse_mae_within_1e3(O, capi, c1):
+    """config C1 (biasedmf-test.properties on the seeded ml-100k split): RMSE / MAE within 1e-3 of the reference order"""
+    tr, te, pins = c1["train"], c1["test"], c1["pins"]
+    O.lib().lro_rng_set_state(*c1["rng_state"])
+    P, Q, bu, bi = O.mf_setup(tr.U, tr.I, 20, True)
+    (gP, gQ, gbu, gbi), losses = _train_gpu(capi, capi.MODEL_BIASEDMF, tr, 20, P, Q, bu, bi, pins["global_mean"],
+                                            0.002, 0.01, 0.01, 0.01, 100)
+    rmse, mae = O.eval_rating(O.BIASEDMF, te, 20, gP, gQ, gbu, gbi, pins["global_mean"], 1.0, 5.0)
+    assert abs(rmse - pins["biasedmf"]["rmse"]) < 1e-3, (rmse, pins["biasedmf"]["rmse"])
+    assert abs(mae - pins["biasedmf"]["mae"]) < 1e-3, (mae, pins["biasedmf"]["mae"])
+    # loss curve: same definition as the reference, close to the sequential run, decreasing
+    assert abs(losses[0] - pins["biasedmf"]["loss_1"]) < 0.01 * pins["biasedmf"]["loss_1"]
+    assert abs(losses[-1] - pins["biasedmf"]["loss_100"]) < 0.01 * pins["biasedmf"]["loss_100"]
+    assert all(b < a for a, b in zip(losses, losses[1:]))
+
+
+def test_c1_pmf_rmse_mae_within_1e3(O, capi, c1):
+    tr, te, pins = c1["train"], c1["test"], c1["pins"]
+    O.lib().lro_rng_set_state(*c1["rng_state"])
+    P, Q, _, _ = O.mf_setup(tr.U, tr.I, 6, False)
+    (gP, gQ, _, _), losses = _train_gpu(capi, capi.MODEL_PMF, tr, 6, P, Q, None, None, pins["global_mean"],
+                                        0.01, 0.08, 0.08, 0.0, 70)
+    rmse, mae = O.eval_rating(O.PMF, te, 6, gP, gQ, None, None, pins["global_mean"], 1.0, 5.0)
+    assert abs(rmse - pins["pmf"]["rmse"]) < 1e-3, (rmse, pins["pmf"]["rmse"])
+    assert abs(mae - pins["pmf"]["mae"]) < 1e-3, (mae, pins["pmf"]["mae"])
+    assert abs(losses[-1] - pins["pmf"]["loss_70"]) < 0.01 * pins["pmf"]["loss_70"]
+
+
+def test_bpr_samples_are_valid_and_uniform(O, capi):
+    tr = rng_csr(O, 400, 300, 0.05, 7, values=(1.0,))
+    tr.rowptr[5:] -= (tr.rowptr[5] - tr.rowptr[4])       # make user 4 empty
+    lo, hi = tr.rowptr[4], tr.rowptr[4] + (len(tr.col) - tr.rowptr[-1])
+    keep = np.ones(len(tr.col), bool); keep[lo:hi] = False
+    tr = O.Csr(tr.U, tr.I, tr.rowptr, tr.col[keep], tr.val[keep])
+    with capi.Handle(capi.MODEL_BPR, 16, seed=5) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        s1 = h.bpr_peek_samples(1, 0, 60000)
+        s1b = h.bpr_peek_samples(1, 0, 1000)
+        s2 = h.bpr_peek_samples(2, 0, 1000)
+    assert np.array_equal(s1[:1000], s1b) and not np.array_equal(s1b, s2)
+    member = set((int(u) << 32) | int(i) for u, i in zip(tr.rows(), tr.col))
+    u, i, j = s1[:, 0], s1[:, 1], s1[:, 2]
+    assert u.min() >= 0 and u.max() < tr.U and 4 not in set(u.tolist())
+    assert all(((int(a) << 32) | int(b)) in member for a, b in zip(u[:5000], i[:5000]))
+    assert not any(((int(a) << 32) | int(b)) in member for a, b in zip(u[:5000], j[:5000]))
+    # BPRRecommender.java:58 draws users uniformly (not by degree): chi-square over users
+    cnt = np.bincount(u, minlength=tr.U).astype(np.float64)
+    exp = len(u) / (tr.U - 1)
+    chi2 = ((np.delete(cnt, 4) - exp) ** 2 / exp).sum()
+    assert chi2 < 1.35 * (tr.U - 2)
+
+
+def test_bpr_epoch_tracks_oracle_on_its_own_samples(O, capi):
+    """feed the kernel's own (u,i,j) draws through the reference arithmetic: same loss, close factors"""
+    tr = rng_csr(O, 3000, 2000, 0.01, 3, values=(1.0,))
+    k = 32
+    rng = np.random.default_rng(0)
+    P = rng.normal(0, 0.1, (tr.U, k)).astype(np.float32).astype(np.float64)
+    Q = rng.normal(0, 0.1, (tr.I, k)).astype(np.float32).astype(np.float64)
+    n = tr.nnz
+    with capi.Handle(capi.MODEL_BPR, k, seed=9) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q)
+        trip = h.bpr_peek_samples(1, 0, n)
+        loss = h.sgd_epoch(0.01, 0.01, 0.01, 0.0, 1)
+        gP, gQ, _, _ = h.get_factors()
+    oP, oQ = P.copy(), Q.copy()
+    trip = np.ascontiguousarray(trip.reshape(-1))
+    oloss = O.lib().lro_bpr_epoch(tr.U, tr.I, tr.rowptr, tr.col, k, oP, oQ, 0.01, 0.01, 0.01, n, trip.ctypes.data, None)
+    assert abs(loss - oloss) < 2e-3 * oloss
+    # same samples, different interleaving: factor movement agrees to a small fraction of the step
+    step = np.abs(oP - P).max()
+    assert np.abs(gP - oP).max() < 0.1 * step + 1e-6
+    assert np.abs(gQ - oQ).max() < 0.1 * np.abs(oQ - Q).max() + 1e-6
+
+
+def test_diverged_loss_is_reported(O, capi):
+    tr = rng_csr(O, 50, 40, 0.5, 1)
+    P = np.full((50, 8), 1e18); Q = np.full((40, 8), 1e18)
+    with capi.Handle(capi.MODEL_PMF, 8) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q)
+        with pytest.raises(capi.LibrecException) as e:
+            for it in range(3):
+                h.sgd_epoch(0.01, 0.01, 0.01, 0.0, it + 1)
+        assert e.value.status == capi.ERR_DIVERGED and "NaN or Infinity" in str(e.value)
+
+
+def test_argument_errors(O, capi):
+    tr = rng_csr(O, 10, 12, 0.5, 1)
+    with capi.Handle(capi.MODEL_BIASEDMF, 8) as h:
+        with pytest.raises(capi.LibrecException):
+            h.set_factors(np.zeros((10, 8)), np.zeros((12, 8)), np.zeros(10), np.zeros(12), 0.0)   # CSR first
+        bad = tr.col.copy(); bad[0] = 99
+        with pytest.raises(capi.LibrecException):
+            h.set_train_csr(tr.U, tr.I, tr.rowptr, bad, tr.val)
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        with pytest.raises(capi.LibrecException):
+            h.set_factors(np.zeros((10, 8)), np.zeros((12, 8)), None, None, 0.0)                   # biases required
+        with pytest.raises(capi.LibrecException):
+            h.sgd_epoch(0.01, 0.01, 0.01, 0.01)                                                    # no factors yet
+
+
+def test_empty_and_ragged_inputs(O, capi):
+    # users without ratings, items without ratings, and an all-empty matrix
+    tr = O.Csr(5, 6, [0, 0, 3, 3, 4, 4], [0, 2, 5, 1], [1.0, 2.0, 3.0, 4.0])
+    P = np.ones((5, 4)) * 0.1; Q = np.ones((6, 4)) * 0.1
+    with capi.Handle(capi.MODEL_PMF, 4) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q)
+        loss = h.sgd_epoch(0.01, 0.01, 0.01)
+        gP, gQ, _, _ = h.get_factors()
+    assert np.array_equal(gP[[0, 2, 4]], P[[0, 2, 4]].astype(np.float32).astype(np.float64)) and loss > 0
+    empty = O.Csr(3, 3, [0, 0, 0, 0], np.zeros(0, np.int32), np.zeros(0))
+    with capi.Handle(capi.MODEL_PMF, 4) as h:
+        h.set_train_csr(3, 3, empty.rowptr, empty.col, empty.val)
+        h.set_factors(np.ones((3, 4)), np.ones((3, 4)))
+        assert h.sgd_epoch(0.01, 0.01, 0.01) == 0.0

@@ -1,0 +1,110 @@
+"""GPU: prediction / top-N through the C ABI must be bit-identical to the oracle for identical factors."""
+import numpy as np
+import pytest
+
+from conftest import rng_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(capi, O, model, U, I, k, seed, density=0.05, scale=0.1, topn_path=1):
+    rng = np.random.default_rng(seed)
+    P = rng.normal(0, scale, (U, k)); Q = rng.normal(0, scale, (I, k))
+    biased = model == capi.MODEL_BIASEDMF
+    bu = rng.normal(0, scale, U) if biased else None
+    bi = rng.normal(0, scale, I) if biased else None
+    tr = rng_csr(O, U, I, density, seed + 1)
+    h = capi.Handle(model, k, topn_path=topn_path)
+    h.set_train_csr(U, I, tr.rowptr, tr.col, tr.val)
+    h.set_factors(P, Q, bu, bi, 3.53)
+    return h, tr, P, Q, bu, bi
+
+
+def _omodel(capi, O, model):
+    return {capi.MODEL_BIASEDMF: O.BIASEDMF, capi.MODEL_PMF: O.PMF, capi.MODEL_BPR: O.BPR}[model]
+
+
+@pytest.mark.parametrize("model", [0, 1, 2])
+@pytest.mark.parametrize("U,I,k,N", [(70, 333, 20, 10), (33, 1000, 64, 10), (40, 257, 128, 7), (9, 31, 3, 50), (64, 96, 200, 10)])
+def test_topn_exact_bit_identical(O, capi, model, U, I, k, N):
+    h, tr, P, Q, bu, bi = _setup(capi, O, model, U, I, k, seed=U + k)
+    with h:
+        items, scores, counts = h.topn(N)
+    oi, os_, oc = O.recommend_rank(_omodel(capi, O, model), U, I, k, P, Q, bu, bi, 3.53, tr, N)
+    assert np.array_equal(counts, oc) and np.array_equal(items, oi)
+    assert np.array_equal(scores.view(np.int64), os_.view(np.int64))      # bit-exact fp64
+
+
+def test_topn_ties_follow_java_heap_order(O, capi):
+    U, I, k, N = 50, 400, 8, 10
+    rng = np.random.default_rng(4)
+    P = rng.integers(-2, 3, (U, k)).astype(np.float64)      # small integers -> massive score ties
+    Q = rng.integers(-1, 2, (I, k)).astype(np.float64)
+    Q[::7] = 0.0; P[3] = 0.0; Q[5, 0] = -0.0
+    tr = rng_csr(O, U, I, 0.1, 8)
+    with capi.Handle(capi.MODEL_PMF, k, topn_path=1) as h:
+        h.set_train_csr(U, I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q)
+        items, scores, counts = h.topn(N)
+    oi, os_, oc = O.recommend_rank(O.PMF, U, I, k, P, Q, None, None, 0.0, tr, N)
+    assert np.array_equal(counts, oc) and np.array_equal(items, oi)
+    assert np.array_equal(scores.view(np.int64), os_.view(np.int64))
+
+
+def test_topn_edge_cases(O, capi):
+    U, I, k = 6, 40, 4
+    rng = np.random.default_rng(0)
+    P = rng.normal(size=(U, k)); Q = rng.normal(size=(I, k))
+    Q[7, 1] = np.nan                                           # NaN score dropped (MatrixRecommender.java:186)
+    rowptr = [0, 40, 40, 78, 79, 79, 79]                       # user0: everything trained; user2: all but 2 items
+    col = list(range(40)) + [c for c in range(40) if c not in (3, 30)] + [39]
+    tr = O.Csr(U, I, rowptr, col, np.ones(len(col)))
+    with capi.Handle(capi.MODEL_PMF, k, topn_path=1) as h:
+        h.set_train_csr(U, I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q)
+        full = h.topn(10)
+        sub = h.topn(10, users=[5, 2, 2, 0])
+        noex = h.topn(45, exclude_train=False)
+        with pytest.raises(capi.LibrecException):
+            h.topn(0)
+    oi, os_, oc = O.recommend_rank(O.PMF, U, I, k, P, Q, None, None, 0.0, tr, 10)
+    assert oc.tolist()[:3] == [0, 10, 2]
+    for got, exp in zip(full, (oi, os_, oc)):
+        assert np.array_equal(got, exp, equal_nan=True)
+    si, ss, sc = O.recommend_rank(O.PMF, U, I, k, P, Q, None, None, 0.0, tr, 10, users=[5, 2, 2, 0])
+    assert np.array_equal(sub[0], si) and np.array_equal(sub[1], ss) and np.array_equal(sub[2], sc)
+    ni, ns, nc = O.recommend_rank(O.PMF, U, I, k, P, Q, None, None, 0.0, None, 45)
+    assert np.array_equal(noex[0], ni) and np.array_equal(noex[1], ns) and nc.tolist() == [39] * U
+
+
+def test_predict_pairs_and_eval_rating_bit_identical(O, capi):
+    U, I, k = 300, 500, 20
+    h, tr, P, Q, bu, bi = _setup(capi, O, capi.MODEL_BIASEDMF, U, I, k, seed=5, scale=0.7)
+    te = rng_csr(O, U, I, 0.03, 77)
+    rng = np.random.default_rng(1)
+    us = rng.integers(0, U, 4000).astype(np.int32); its = rng.integers(0, I, 4000).astype(np.int32)
+    with h:
+        got = h.predict_pairs(us, its)
+        rmse, mae, pred = h.eval_rating(U, te.rowptr, te.col, te.val, 1.0, 5.0, want_pred=True)
+    exp = np.zeros(4000)
+    O.lib().lro_predict_pairs(O.BIASEDMF, k, P, Q, bu.ctypes.data, bi.ctypes.data, 3.53, us, its, 4000, exp)
+    assert np.array_equal(got.view(np.int64), exp.view(np.int64))
+    ormse, omae, opred = O.eval_rating(O.BIASEDMF, te, k, P, Q, bu, bi, 3.53, 1.0, 5.0, want_pred=True)
+    assert np.array_equal(pred.view(np.int64), opred.view(np.int64))            # bounded predictions bit-exact
+    assert abs(rmse - ormse) <= 1e-13 * ormse and abs(mae - omae) <= 1e-13 * omae   # tree vs sequential fp64 sum
+
+
+def test_topn_after_training_uses_current_factors(O, capi, c1):
+    tr = c1["train"]
+    O.lib().lro_rng_set_state(*c1["rng_state"])
+    P, Q, bu, bi = O.mf_setup(tr.U, tr.I, 20, True)
+    mu = c1["pins"]["global_mean"]
+    with capi.Handle(capi.MODEL_BIASEDMF, 20, topn_path=1) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q, bu, bi, mu)
+        for it in range(5):
+            h.sgd_epoch(0.002, 0.01, 0.01, 0.01, it + 1)
+        items, scores, counts = h.topn(10)
+        gP, gQ, gbu, gbi = h.get_factors()
+    oi, os_, oc = O.recommend_rank(O.BIASEDMF, tr.U, tr.I, 20, gP, gQ, gbu, gbi, mu, tr, 10)
+    assert np.array_equal(items, oi) and np.array_equal(scores.view(np.int64), os_.view(np.int64)) and np.array_equal(counts, oc)
