@@ -12,8 +12,9 @@ loop over all ratings).  metric = MF SGD rating-updates/s.
   roofline : algorithmic bytes (1052 B / BiasedMF update) / kernel time vs measured HBM peak
   cpu_baseline : the oracle's single-thread fp64 restatement of the reference loop on this box
 --impl reference times that CPU restatement alone (the Java reference cannot run: no JVM).
-N>1 (torchrun, one process per GPU): the same matrix trained with DSGD strata, item blocks rotated
-over NCCL; value = ratings processed by all ranks / max-over-ranks time ("scaling": "strong").
+N>1 (torchrun, one process per GPU): every rank owns one ML-20M-shaped user shard over the same item
+catalogue (N x 20 000 263 ratings in total), trained with DSGD strata, item blocks rotated over NCCL;
+value = ratings processed by all ranks / max-over-ranks time ("scaling": "weak").
 """
 import argparse
 import ctypes
@@ -163,7 +164,7 @@ def run_reference(args):
     rate, n, sec = cpu_reference_rate(d, sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_desc(d), "reference": "oracle port of BiasedMFRecommender.trainModel (Java reference cannot run: no JVM)"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
@@ -201,14 +202,17 @@ def run_ours(args):
         _build.build()
     capi.load()
 
-    if world > 1 and rank != 0:
-        dist.barrier()           # rank 0 generates / caches the data first
-    d = synth.make_ratings("ml-20m")
-    if world > 1 and rank == 0:
-        dist.barrier()
+    # N=1: the ML-20M-shaped matrix.  N>1 (weak scaling): every rank owns one ML-20M-shaped user shard
+    # over the same item catalogue -> N x 138 493 users, N x 20 000 263 ratings in total.
+    d = synth.make_ratings("ml-20m", shard=rank)
     U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
-    P0, Q0, bu0, bi0 = synth.init_factors(U, I, K_FACTORS, 1, True)
+    P0, _, bu0, _ = synth.init_factors(U, I, K_FACTORS, 100 + rank, True)
+    _, Q0, _, bi0 = synth.init_factors(U, I, K_FACTORS, 1, True)          # item side identical on every rank
     mu = float(d["val"].mean())
+    if world > 1:
+        m = torch.tensor([mu], dtype=torch.float64, device=dev)
+        dist.all_reduce(m)
+        mu = float(m.item()) / world
 
     h = capi.Handle(capi.MODEL_BIASEDMF, K_FACTORS, device=local, seed=1)
     stream = torch.cuda.current_stream()
@@ -250,13 +254,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = nnz * args.steps / (total_ms * 1e-3)
+    value = nnz * world * args.steps / (total_ms * 1e-3)
     kms = float(np.mean(kernel_ms))
 
     line = None
     if rank == 0:
         peaks, which = measured_peaks()
-        achieved = BYTES_PER_UPDATE * nnz / (kms * 1e-3) / 1e9 * (1.0 / world if world > 1 else 1.0)
+        achieved = BYTES_PER_UPDATE * nnz / (kms * 1e-3) / 1e9        # per GPU (rank 0's kernels)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -266,16 +270,19 @@ def run_ours(args):
                 traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_desc(d), "update_mode": "atomic (REDG.E.ADD.F32x4)",
+            "config": {"workload": workload_desc(d) if world == 1 else
+                       "BiasedMF k=%d SGD epoch, %d ML-20M-shaped user shards (%d users x %d items, %d ratings in total), "
+                       "lr %g reg %g" % (K_FACTORS, world, U * world, I, nnz * world, LR, REG),
+                       "update_mode": "atomic (REDG.E.ADD.F32x4)",
                        "l2": "L2 flushed between timed steps (256 MiB memset, untimed); COO stream 240 MB > L2",
                        "parallelism": "single GPU" if world == 1 else "DSGD %d strata, NCCL ring rotation of item blocks" % world,
                        "final_loss": losses[-1]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
                          "kernel": "sgd_rating_epoch_kernel<16,1,true,true>", "kernel_ms": kms,
-                         "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * nnz // world},
+                         "algorithmic_bytes_per_epoch_per_gpu": BYTES_PER_UPDATE * nnz},
             "gpu_launches": int(launches), "clocks": clocks,
         }
 
@@ -292,21 +299,30 @@ def run_ours(args):
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         loss = ctypes.c_double()
 
-        def train_model_call():
+        breakdown = {"set_train_csr": [], "set_factors": [], "epochs": [], "get_factors": []}
+
+        def train_model_call(record=True):
             hP[:] = P0; hQ[:] = Q0; hbu[:] = bu0; hbi[:] = bi0
             t0 = time.perf_counter()
             rc = L.lrk_set_train_csr(h._h, U, I, vp(rp), vp(cl), vp(vl))
+            t1 = time.perf_counter()
             rc |= L.lrk_set_factors(h._h, vp(hP), vp(hQ), vp(hbu), vp(hbi), mu)
+            t2 = time.perf_counter()
             for it in range(E2E_EPOCHS):
                 rc |= L.lrk_sgd_epoch(h._h, LR, REG, REG, REG_B, it + 1, ctypes.byref(loss))
+            t3 = time.perf_counter()
             rc |= L.lrk_get_factors(h._h, vp(hP), vp(hQ), vp(hbu), vp(hbi))
             torch.cuda.synchronize()
+            t4 = time.perf_counter()
             if rc != 0:
                 raise RuntimeError("e2e call failed: %s" % L.lrk_last_error(h._h))
-            return time.perf_counter() - t0
+            if record:
+                for key, dt in zip(breakdown, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                    breakdown[key].append(dt * 1e3)
+            return t4 - t0
 
         e2e_steps = max(2, min(args.steps, 5))
-        train_model_call()                                  # warm-up
+        train_model_call(record=False)                      # warm-up
         tt = [train_model_call() for _ in range(e2e_steps)]
         h2d = rp.nbytes + cl.nbytes + vl.nbytes + hP.nbytes + hQ.nbytes + hbu.nbytes + hbi.nbytes
         d2h = hP.nbytes + hQ.nbytes + hbu.nbytes + hbi.nbytes + 8 * E2E_EPOCHS
@@ -314,7 +330,8 @@ def run_ours(args):
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "step": "one trainModel() call through the C ABI from pinned host buffers: lrk_set_train_csr + "
                                "lrk_set_factors + %d x lrk_sgd_epoch + lrk_get_factors" % E2E_EPOCHS,
-                       "ms_per_call": float(np.mean(tt)) * 1e3, "calls": e2e_steps}
+                       "ms_per_call": float(np.mean(tt)) * 1e3, "calls": e2e_steps,
+                       "breakdown_ms": {k_: float(np.mean(v)) for k_, v in breakdown.items()}}
         for p in bufs:
             L.lrk_host_free(p)
     elif rank == 0:

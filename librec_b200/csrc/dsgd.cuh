@@ -1,10 +1,384 @@
-// DSGD strata over NCCL -- see DESIGN.md "Multi-GPU".  Filled in below.
+// DSGD (Gemulla et al., KDD'11 -- the paper the reference cites at
+// recommender/MatrixFactorizationRecommender.java:111-112) across the GPUs of one box, one process
+// per GPU.  SURVEY.md 8(e).
+//
+//   * users are sharded: rank g owns its user block (P rows, user biases) for the whole run;
+//   * items are cut into G contiguous blocks balanced by global rating count; the rank's ratings
+//     are bucketed by item block into G independently shuffled COO segments;
+//   * sub-epoch s in [0,G): rank g runs the SGD kernel on segment b = (g+s) mod G against the item
+//     block it currently holds, then the ring rotates: send block b to rank g-1, receive block
+//     (g+s+1) mod G from rank g+1 (grouped ncclSend/ncclRecv on the handle's stream, NVLink 5);
+//   * strata of one sub-epoch touch disjoint users AND items, so there is no cross-GPU race;
+//   * one fp64 ncclAllReduce of the loss per epoch.
+// NCCL is dlopen'ed lazily so that the single-GPU path has no NCCL dependency.
 #pragma once
 #include "lrk_common.cuh"
-static inline void dsgd_release(lrk_handle_s*) {}
-static inline int dsgd_unique_id(uint8_t*) { return lrk_fail(nullptr, LRK_ERR_NCCL, "lrk_comm_unique_id", "DSGD not built", __FILE__, __LINE__); }
-static inline int dsgd_comm_init(lrk_handle_s* h, int, int, const uint8_t*) { return lrk_fail(h, LRK_ERR_NCCL, "lrk_comm_init", "DSGD not built", __FILE__, __LINE__); }
-static inline int dsgd_set_train_csr(lrk_handle_s* h, int32_t, int32_t, const int64_t*, const int32_t*, const double*) { return lrk_fail(h, LRK_ERR_INVALID, "dsgd", "not built", __FILE__, __LINE__); }
-static inline int dsgd_set_factors(lrk_handle_s* h, const double*, const double*, const double*, const double*, double) { return lrk_fail(h, LRK_ERR_INVALID, "dsgd", "not built", __FILE__, __LINE__); }
-static inline int dsgd_get_factors(lrk_handle_s* h, double*, double*, double*, double*) { return lrk_fail(h, LRK_ERR_INVALID, "dsgd", "not built", __FILE__, __LINE__); }
-static inline int dsgd_epoch(lrk_handle_s* h, float, float, float, double, int32_t, double*) { return lrk_fail(h, LRK_ERR_INVALID, "dsgd", "not built", __FILE__, __LINE__); }
+#include "staging.cuh"
+#include "sgd.cuh"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <vector>
+#include <algorithm>
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.lib ? &api : nullptr;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+    if (!api.lib) return nullptr;
+#define LRK_SYM(field, sym) *(void**)(&api.field) = dlsym(api.lib, sym); if (!api.field) { api.lib = nullptr; return nullptr; }
+    LRK_SYM(GetUniqueId, "ncclGetUniqueId") LRK_SYM(CommInitRank, "ncclCommInitRank") LRK_SYM(CommDestroy, "ncclCommDestroy")
+    LRK_SYM(Send, "ncclSend") LRK_SYM(Recv, "ncclRecv") LRK_SYM(AllReduce, "ncclAllReduce") LRK_SYM(AllGather, "ncclAllGather")
+    LRK_SYM(GroupStart, "ncclGroupStart") LRK_SYM(GroupEnd, "ncclGroupEnd") LRK_SYM(GetErrorString, "ncclGetErrorString")
+#undef LRK_SYM
+    return &api;
+}
+
+#define LRK_NCCL(h, call)                                                                                         \
+    do {                                                                                                          \
+        ncclResult_t r__ = (call);                                                                                \
+        if (r__ != ncclSuccess) return lrk_fail((h), LRK_ERR_NCCL, #call, nccl_api()->GetErrorString(r__), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- the DSGD plan: pure functions of (rank, world, sub-epoch); mirrored by librec_b200/dsgd_plan.py
+static inline int dsgd_block_at(int rank, int world, int sub) { return (rank + sub) % world; }
+static inline int dsgd_send_peer(int rank, int world) { return (rank - 1 + world) % world; }
+static inline int dsgd_recv_peer(int rank, int world) { return (rank + 1) % world; }
+// contiguous item blocks balanced by rating count: block b = [bounds[b], bounds[b+1])
+static inline void dsgd_item_bounds(const int64_t* item_count, int32_t I, int world, std::vector<int32_t>& bounds) {
+    int64_t total = 0;
+    for (int32_t i = 0; i < I; ++i) total += item_count[i];
+    bounds.assign(world + 1, I);
+    bounds[0] = 0;
+    int64_t acc = 0;
+    int b = 1;
+    for (int32_t i = 0; i < I && b < world; ++i) {
+        acc += item_count[i];
+        // close block b-1 after item i once it holds its share; keep at least one item per remaining block
+        while (b < world && (acc * world >= total * b || I - (i + 1) <= world - b)) { bounds[b] = i + 1; ++b; }
+    }
+    for (int j = 1; j <= world; ++j) if (bounds[j] < bounds[j - 1]) bounds[j] = bounds[j - 1];
+    bounds[world] = I;
+}
+
+struct DsgdState {
+    std::vector<int32_t> bounds;        // world+1 item block bounds
+    std::vector<int64_t> seg_off;       // world+1 offsets of the COO segments
+    int32_t max_blk = 0;                // rows of the largest item block
+    size_t buf_floats = 0;              // floats per rotating buffer: max_blk*ld + max_blk
+    float* qbuf[2] = {nullptr, nullptr};
+    int cur = 0;                        // which buffer holds the current block
+    int cur_block = 0;                  // item block id currently held
+    int32_t* d_bounds = nullptr;
+};
+
+__global__ void item_hist_kernel(const int32_t* __restrict__ col, int64_t nnz, unsigned long long* __restrict__ cnt) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nnz) atomicAdd(cnt + col[t], 1ULL);
+}
+// key = (item block << 32) | hash  -> a radix sort groups by block and shuffles inside the block
+__global__ void dsgd_keys_kernel(const int64_t* __restrict__ rowptr, int32_t U, const int32_t* __restrict__ col, int64_t nnz,
+                                 const int32_t* __restrict__ bounds, int world, uint64_t seed,
+                                 int32_t* __restrict__ row_of, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int32_t lo = 0, hi = U;
+    while (hi - lo > 1) { const int32_t m = (lo + hi) >> 1; if (rowptr[m] <= e) lo = m; else hi = m; }
+    row_of[e] = lo;
+    const int32_t c = col[e];
+    int b = 0;
+    while (b + 1 < world && c >= bounds[b + 1]) ++b;
+    keys[e] = ((uint64_t)b << 32) | lrk_hash32((uint64_t)e ^ (seed * 0xD6E8FEB86659FD93ull));
+    idx[e] = (uint32_t)e;
+}
+__global__ void dsgd_gather_kernel(const uint32_t* __restrict__ perm, const uint64_t* __restrict__ keys_sorted,
+                                   const int32_t* __restrict__ row_of, const int32_t* __restrict__ col,
+                                   const double* __restrict__ val, const int32_t* __restrict__ bounds, int64_t nnz,
+                                   int32_t* __restrict__ su, int32_t* __restrict__ si, float* __restrict__ sr) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nnz) return;
+    const uint32_t e = perm[t];
+    const int b = (int)(keys_sorted[t] >> 32);
+    su[t] = row_of[e]; si[t] = col[e] - bounds[b]; sr[t] = (float)val[e];
+}
+__global__ void dsgd_pack_block_kernel(const float* __restrict__ Q, const float* __restrict__ bi, int32_t first, int32_t rows,
+                                       int ld, int32_t max_blk, float* __restrict__ buf) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nq = (int64_t)rows * ld;
+    if (t < nq) buf[t] = Q[(int64_t)first * ld + t];
+    else if (t < nq + rows) buf[(int64_t)max_blk * ld + (t - nq)] = bi ? bi[first + (t - nq)] : 0.f;
+}
+__global__ void dsgd_unpack_block_kernel(float* __restrict__ Q, float* __restrict__ bi, int32_t first, int32_t rows, int ld,
+                                         int32_t max_blk, const float* __restrict__ buf) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nq = (int64_t)rows * ld;
+    if (t < nq) Q[(int64_t)first * ld + t] = buf[t];
+    else if (t < nq + rows && bi) bi[first + (t - nq)] = buf[(int64_t)max_blk * ld + (t - nq)];
+}
+
+static void dsgd_release(lrk_handle_s* h) {
+    DsgdState* s = (DsgdState*)h->dsgd;
+    if (s) {
+        cudaFree(s->qbuf[0]); cudaFree(s->qbuf[1]); cudaFree(s->d_bounds);
+        delete s;
+        h->dsgd = nullptr;
+    }
+    if (h->comm && nccl_api()) { nccl_api()->CommDestroy((ncclComm_t)h->comm); h->comm = nullptr; }
+}
+
+static int dsgd_unique_id(uint8_t* out) {
+    NcclApi* n = nccl_api();
+    if (!n) return lrk_fail(nullptr, LRK_ERR_NCCL, "lrk_comm_unique_id", "libnccl.so.2 could not be loaded", __FILE__, __LINE__);
+    if (!out) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_comm_unique_id", "out is NULL", __FILE__, __LINE__);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    LRK_NCCL(nullptr, n->GetUniqueId(&id));
+    memcpy(out, &id, 128);
+    return LRK_OK;
+}
+
+static int dsgd_comm_init(lrk_handle_s* h, int rank, int world, const uint8_t* uid) {
+    NcclApi* n = nccl_api();
+    if (!n) return lrk_fail(h, LRK_ERR_NCCL, "lrk_comm_init", "libnccl.so.2 could not be loaded", __FILE__, __LINE__);
+    LRK_REQUIRE(h, uid != nullptr && world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+    LRK_REQUIRE(h, h->comm == nullptr, "communicator already initialised");
+    LRK_REQUIRE(h, !h->has_train && !h->has_factors, "lrk_comm_init must precede staging");
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_BPR, "DSGD is implemented for BiasedMF and PMF (BPR needs stratified sampling)");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    ncclUniqueId id;
+    memcpy(&id, uid, 128);
+    ncclComm_t comm;
+    LRK_NCCL(h, n->CommInitRank(&comm, world, id, rank));
+    h->comm = comm; h->rank = rank; h->world = world;
+    return LRK_OK;
+}
+
+// rank-local user block: CSR with U_local rows and GLOBAL item ids
+static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val) {
+    NcclApi* n = nccl_api();
+    cudaStream_t st = h->stream;
+    const int world = h->world;
+    const int64_t nnz = rowptr[U];
+    DsgdState* s = (DsgdState*)h->dsgd;
+    if (!s) { s = new DsgdState(); h->dsgd = s; }
+    h->has_train = false;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_rowptr, (size_t)U + 1))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_col, (size_t)nnz))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_su, (size_t)nnz))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_si, (size_t)nnz))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_sr, (size_t)nnz))) return rc;
+    if ((rc = lrk_dev_alloc(h, &s->d_bounds, (size_t)world + 1))) return rc;
+    LRK_CUDA(h, cudaMemcpyAsync(h->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)U + 1), cudaMemcpyHostToDevice, st));
+    LRK_CUDA(h, cudaMemcpyAsync(h->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    h->U = U; h->I = I; h->nnz = nnz;
+
+    // global item popularity -> identical block bounds on every rank
+    unsigned long long* d_cnt = nullptr;
+    LRK_CUDA(h, cudaMalloc((void**)&d_cnt, sizeof(unsigned long long) * (size_t)I));
+    std::vector<int64_t> cnt((size_t)I);
+    cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * (size_t)I, st);
+    if (e == cudaSuccess && nnz > 0) { item_hist_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(h->d_col, nnz, d_cnt); h->launches++; e = cudaGetLastError(); }
+    if (e != cudaSuccess) { cudaFree(d_cnt); LRK_CUDA(h, e); }
+    ncclResult_t nr = n->AllReduce(d_cnt, d_cnt, (size_t)I, ncclUint64, ncclSum, (ncclComm_t)h->comm, st);
+    if (nr == ncclSuccess) e = cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int64_t) * (size_t)I, cudaMemcpyDeviceToHost, st);
+    if (nr == ncclSuccess && e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_cnt);
+    LRK_NCCL(h, nr);
+    LRK_CUDA(h, e);
+    dsgd_item_bounds(cnt.data(), I, world, s->bounds);
+    s->max_blk = 0;
+    for (int b = 0; b < world; ++b) s->max_blk = std::max(s->max_blk, s->bounds[b + 1] - s->bounds[b]);
+    LRK_CUDA(h, cudaMemcpyAsync(s->d_bounds, s->bounds.data(), sizeof(int32_t) * ((size_t)world + 1), cudaMemcpyHostToDevice, st));
+
+    // bucket + shuffle the local ratings
+    s->seg_off.assign((size_t)world + 1, 0);
+    if (nnz > 0) {
+        double* d_val = nullptr; int32_t* row_of = nullptr; uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *idx = nullptr, *perm = nullptr;
+        void* tmp = nullptr; size_t tmp_bytes = 0;
+        std::vector<uint64_t> hk;
+        e = cudaMalloc((void**)&d_val, sizeof(double) * (size_t)nnz);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&row_of, sizeof(int32_t) * (size_t)nnz);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&keys, sizeof(uint64_t) * (size_t)nnz);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&keys2, sizeof(uint64_t) * (size_t)nnz);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&idx, sizeof(uint32_t) * (size_t)nnz);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&perm, sizeof(uint32_t) * (size_t)nnz);
+        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, perm, (int)nnz, 0, 40, st);
+        if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            dsgd_keys_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(h->d_rowptr, U, h->d_col, nnz, s->d_bounds, world, h->cfg.seed + 977u * h->rank, row_of, keys, idx);
+            h->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, perm, (int)nnz, 0, 40, st);
+        if (e == cudaSuccess) {
+            dsgd_gather_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(perm, keys2, row_of, h->d_col, d_val, s->d_bounds, nnz, h->d_su, h->d_si, h->d_sr);
+            h->launches++;
+            e = cudaGetLastError();
+        }
+        // segment offsets: per-block counts from the (host) item counts of THIS rank
+        std::vector<int64_t> local_cnt((size_t)world, 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        for (int64_t t = 0; t < nnz; ++t) {
+            const int32_t c = col[t];
+            int b = (int)(std::upper_bound(s->bounds.begin(), s->bounds.end(), c) - s->bounds.begin()) - 1;
+            if (b >= world) b = world - 1;
+            local_cnt[(size_t)b]++;
+        }
+        for (int b = 0; b < world; ++b) s->seg_off[(size_t)b + 1] = s->seg_off[(size_t)b] + local_cnt[(size_t)b];
+        cudaFree(d_val); cudaFree(row_of); cudaFree(keys); cudaFree(keys2); cudaFree(idx); cudaFree(perm); cudaFree(tmp);
+        LRK_CUDA(h, e);
+    }
+    s->buf_floats = (size_t)s->max_blk * h->ld + (size_t)s->max_blk;
+    for (int j = 0; j < 2; ++j) if ((rc = lrk_dev_alloc(h, &s->qbuf[j], s->buf_floats))) return rc;
+    h->has_train = true;
+    return LRK_OK;
+}
+
+// P/bu: the rank's user block; Q/bi: the FULL item factors (identical on every rank)
+static int dsgd_set_factors(lrk_handle_s* h, const double* P, const double* Q, const double* bu, const double* bi, double mu) {
+    DsgdState* s = (DsgdState*)h->dsgd;
+    cudaStream_t st = h->stream;
+    const int k = h->k, ld = h->ld;
+    const int64_t U = h->U, I = h->I;
+    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &h->P64, (size_t)U * k))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->Q64, (size_t)I * k))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->P32, (size_t)U * ld))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->Q32, (size_t)I * ld))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bu64, (size_t)U))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bi64, (size_t)I))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bu32, (size_t)U))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bi32, (size_t)I))) return rc;
+    LRK_CUDA(h, cudaMemcpyAsync(h->P64, P, sizeof(double) * (size_t)U * k, cudaMemcpyHostToDevice, st));
+    LRK_CUDA(h, cudaMemcpyAsync(h->Q64, Q, sizeof(double) * (size_t)I * k, cudaMemcpyHostToDevice, st));
+    if (biased) {
+        LRK_CUDA(h, cudaMemcpyAsync(h->bu64, bu, sizeof(double) * (size_t)U, cudaMemcpyHostToDevice, st));
+        LRK_CUDA(h, cudaMemcpyAsync(h->bi64, bi, sizeof(double) * (size_t)I, cudaMemcpyHostToDevice, st));
+    } else {
+        LRK_CUDA(h, cudaMemsetAsync(h->bu64, 0, sizeof(double) * (size_t)U, st));
+        LRK_CUDA(h, cudaMemsetAsync(h->bi64, 0, sizeof(double) * (size_t)I, st));
+    }
+    f64_to_f32_rows_kernel<<<lrk_ceil_div(U * ld, 256), 256, 0, st>>>(h->P64, h->P32, U, k, ld); LRK_LAUNCH_CHECK(h);
+    f64_to_f32_rows_kernel<<<lrk_ceil_div(I * ld, 256), 256, 0, st>>>(h->Q64, h->Q32, I, k, ld); LRK_LAUNCH_CHECK(h);
+    f64_to_f32_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu64, h->bu32, U, 1, 1); LRK_LAUNCH_CHECK(h);
+    f64_to_f32_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi64, h->bi32, I, 1, 1); LRK_LAUNCH_CHECK(h);
+    // the rank starts the epoch holding item block `rank`
+    const int b = dsgd_block_at(h->rank, h->world, 0);
+    const int32_t first = s->bounds[b], rows = s->bounds[b + 1] - first;
+    LRK_CUDA(h, cudaMemsetAsync(s->qbuf[0], 0, sizeof(float) * s->buf_floats, st));
+    LRK_CUDA(h, cudaMemsetAsync(s->qbuf[1], 0, sizeof(float) * s->buf_floats, st));
+    if (rows > 0) {
+        dsgd_pack_block_kernel<<<lrk_ceil_div((int64_t)rows * ld + rows, 256), 256, 0, st>>>(h->Q32, h->bi32, first, rows, ld, s->max_blk, s->qbuf[0]);
+        LRK_LAUNCH_CHECK(h);
+    }
+    s->cur = 0; s->cur_block = b;
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    h->mu = mu; h->has_factors = true; h->f64_valid = false;
+    return LRK_OK;
+}
+
+static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, double* loss_out) {
+    NcclApi* n = nccl_api();
+    DsgdState* s = (DsgdState*)h->dsgd;
+    cudaStream_t st = h->stream;
+    const int world = h->world, rank = h->rank;
+    LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
+    LRK_CUDA(h, cudaEventRecord(h->ev0, st));
+    for (int sub = 0; sub < world; ++sub) {
+        const int b = dsgd_block_at(rank, world, sub);
+        float* buf = s->qbuf[s->cur];
+        const int64_t off = s->seg_off[(size_t)b], cnt = s->seg_off[(size_t)b + 1] - off;
+        if (cnt > 0) {
+            SgdParams sp;
+            memset(&sp, 0, sizeof sp);
+            sp.su = h->d_su + off; sp.si = h->d_si + off; sp.sr = h->d_sr + off; sp.n = cnt;
+            sp.P = h->P32; sp.Q = buf; sp.bu = h->bu32; sp.bi = buf + (size_t)s->max_blk * h->ld;
+            sp.mu = (float)h->mu; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i; sp.reg_b = (float)reg_b;
+            sp.loss = h->d_loss; sp.ld = h->ld; sp.epoch = (uint32_t)epoch_idx;
+            int rc = sgd_launch(h, sp);
+            if (rc) return rc;
+        }
+        if (world > 1) {
+            float* nxt = s->qbuf[s->cur ^ 1];
+            LRK_NCCL(h, n->GroupStart());
+            LRK_NCCL(h, n->Send(buf, s->buf_floats, ncclFloat32, dsgd_send_peer(rank, world), (ncclComm_t)h->comm, st));
+            LRK_NCCL(h, n->Recv(nxt, s->buf_floats, ncclFloat32, dsgd_recv_peer(rank, world), (ncclComm_t)h->comm, st));
+            LRK_NCCL(h, n->GroupEnd());
+            s->cur ^= 1;
+        }
+        s->cur_block = dsgd_block_at(rank, world, sub + 1);
+    }
+    LRK_NCCL(h, n->AllReduce(h->d_loss, h->d_loss, 1, ncclFloat64, ncclSum, (ncclComm_t)h->comm, st));
+    LRK_CUDA(h, cudaEventRecord(h->ev1, st));
+    h->f64_valid = false;
+    LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    LRK_CUDA(h, cudaEventElapsedTime(&h->last_epoch_ms, h->ev0, h->ev1));
+    const double loss = 0.5 * h->h_loss[0];
+    if (loss_out) *loss_out = loss;
+    if (std::isnan(loss) || std::isinf(loss))
+        return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);
+    return LRK_OK;
+}
+
+// P/bu: the rank's user block; Q/bi: the full item factors, gathered from the ring
+static int dsgd_get_factors(lrk_handle_s* h, double* P, double* Q, double* bu, double* bi) {
+    NcclApi* n = nccl_api();
+    DsgdState* s = (DsgdState*)h->dsgd;
+    cudaStream_t st = h->stream;
+    const int world = h->world;
+    const int64_t U = h->U, I = h->I;
+    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    // all-gather the rotating buffers (every rank holds block `cur_block`), then unpack into Q32 / bi32
+    float* all = nullptr;
+    LRK_CUDA(h, cudaMalloc((void**)&all, sizeof(float) * s->buf_floats * (size_t)world));
+    ncclResult_t nr = n->AllGather(s->qbuf[s->cur], all, s->buf_floats, ncclFloat32, (ncclComm_t)h->comm, st);
+    cudaError_t e = cudaSuccess;
+    if (nr == ncclSuccess) {
+        for (int r = 0; r < world && e == cudaSuccess; ++r) {
+            const int b = dsgd_block_at(r, world, 0);     // between epochs rank r holds block r
+            const int32_t first = s->bounds[b], rows = s->bounds[b + 1] - first;
+            if (rows > 0) {
+                dsgd_unpack_block_kernel<<<lrk_ceil_div((int64_t)rows * h->ld + rows, 256), 256, 0, st>>>(
+                    h->Q32, biased ? h->bi32 : nullptr, first, rows, h->ld, s->max_blk, all + s->buf_floats * (size_t)r);
+                h->launches++;
+                e = cudaGetLastError();
+            }
+        }
+    }
+    if (nr == ncclSuccess && e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(all);
+    LRK_NCCL(h, nr);
+    LRK_CUDA(h, e);
+    f32_to_f64_rows_kernel<<<lrk_ceil_div(U * h->k, 256), 256, 0, st>>>(h->P32, h->P64, U, h->k, h->ld); LRK_LAUNCH_CHECK(h);
+    f32_to_f64_rows_kernel<<<lrk_ceil_div(I * h->k, 256), 256, 0, st>>>(h->Q32, h->Q64, I, h->k, h->ld); LRK_LAUNCH_CHECK(h);
+    if (biased) {
+        f32_to_f64_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu32, h->bu64, U, 1, 1); LRK_LAUNCH_CHECK(h);
+        f32_to_f64_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi32, h->bi64, I, 1, 1); LRK_LAUNCH_CHECK(h);
+    }
+    if (P) LRK_CUDA(h, cudaMemcpyAsync(P, h->P64, sizeof(double) * (size_t)U * h->k, cudaMemcpyDeviceToHost, st));
+    if (Q) LRK_CUDA(h, cudaMemcpyAsync(Q, h->Q64, sizeof(double) * (size_t)I * h->k, cudaMemcpyDeviceToHost, st));
+    if (bu && biased) LRK_CUDA(h, cudaMemcpyAsync(bu, h->bu64, sizeof(double) * (size_t)U, cudaMemcpyDeviceToHost, st));
+    if (bi && biased) LRK_CUDA(h, cudaMemcpyAsync(bi, h->bi64, sizeof(double) * (size_t)I, cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    return LRK_OK;
+}

@@ -95,6 +95,7 @@ int lrk_destroy(lrk_handle_t h) {
     lrk_dev_free(&h->P32); lrk_dev_free(&h->Q32); lrk_dev_free(&h->bu32); lrk_dev_free(&h->bi32);
     lrk_dev_free(&h->P64); lrk_dev_free(&h->Q64); lrk_dev_free(&h->bu64); lrk_dev_free(&h->bi64);
     lrk_dev_free(&h->d_loss);
+    if (h->scratch) cudaFree(h->scratch);
     if (h->h_loss) cudaFreeHost(h->h_loss);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include "../../include/librec_b200.h"
 
 #define LRK_MAX_FACTORS 256
@@ -54,6 +55,11 @@ struct lrk_handle_s {
     int rank = 0, world = 1;
     void* dsgd = nullptr;   // DsgdState*
 
+    // allocation bookkeeping: device buffers are reused across calls when they are large enough
+    std::unordered_map<void*, size_t> caps;
+    void* scratch = nullptr;      // staging workspace (temporaries of lrk_set_train_csr), grown on demand
+    size_t scratch_bytes = 0;
+
     std::string err;
 };
 
@@ -88,14 +94,44 @@ static inline int lrk_fail(lrk_handle_s* h, int code, const char* what, const ch
 
 template <typename T>
 static inline int lrk_dev_alloc(lrk_handle_s* h, T** p, size_t count) {
-    if (*p) { cudaFree(*p); *p = nullptr; }
     if (count == 0) count = 1;
-    LRK_CUDA(h, cudaMalloc((void**)p, count * sizeof(T)));
+    const size_t bytes = count * sizeof(T);
+    if (*p) {
+        auto it = h->caps.find((void*)*p);
+        if (it != h->caps.end() && it->second >= bytes) return LRK_OK;   // reuse
+        if (it != h->caps.end()) h->caps.erase(it);
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    LRK_CUDA(h, cudaMalloc((void**)p, bytes));
+    h->caps[(void*)*p] = bytes;
     return LRK_OK;
 }
 template <typename T>
 static inline void lrk_dev_free(T** p) {
     if (*p) { cudaFree(*p); *p = nullptr; }
+}
+// bump allocator over the handle's staging workspace
+struct LrkScratch {
+    char* base = nullptr;
+    size_t used = 0, cap = 0;
+    template <typename T>
+    T* take(size_t count) {
+        const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        if (used + bytes > cap) return nullptr;
+        T* r = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        return r;
+    }
+};
+static inline int lrk_scratch_begin(lrk_handle_s* h, size_t bytes, LrkScratch* out) {
+    if (h->scratch_bytes < bytes) {
+        if (h->scratch) { cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
+        LRK_CUDA(h, cudaMalloc(&h->scratch, bytes));
+        h->scratch_bytes = bytes;
+    }
+    out->base = (char*)h->scratch; out->used = 0; out->cap = h->scratch_bytes;
+    return LRK_OK;
 }
 
 static inline int lrk_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -71,42 +71,38 @@ static int stage_coo_from_csr(lrk_handle_s* h, const int64_t* d_rowptr, const in
                               int32_t U, int32_t I, int64_t nnz, int32_t* su, int32_t* si, float* sr, bool validate) {
     cudaStream_t st = h->stream;
     if (nnz == 0) { LRK_CUDA(h, cudaStreamSynchronize(st)); return LRK_OK; }
-    double* d_val = nullptr; int32_t* row_of = nullptr; uint32_t *keys = nullptr, *idx = nullptr, *keys2 = nullptr, *perm = nullptr;
-    void* tmp = nullptr; int* d_flags = nullptr; size_t tmp_bytes = 0;
+    size_t tmp_bytes = 0;
+    LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                (uint32_t*)nullptr, (int)nnz, 0, 32, st));
+    const size_t n = (size_t)nnz;
+    LrkScratch sc;
+    int rc = lrk_scratch_begin(h, n * (8 + 4 * 5) + tmp_bytes + 16 * 256, &sc);
+    if (rc) return rc;
+    double* d_val = sc.take<double>(n);
+    int32_t* row_of = sc.take<int32_t>(n);
+    uint32_t *keys = sc.take<uint32_t>(n), *idx = sc.take<uint32_t>(n), *keys2 = sc.take<uint32_t>(n), *perm = sc.take<uint32_t>(n);
+    void* tmp = sc.take<char>(tmp_bytes ? tmp_bytes : 1);
+    int* d_flags = sc.take<int>(1);
+    if (!d_val || !row_of || !keys || !idx || !keys2 || !perm || !tmp || !d_flags)
+        return lrk_fail(h, LRK_ERR_NOMEM, "stage_coo_from_csr", "scratch arena too small", __FILE__, __LINE__);
     int flags = 0;
-    cudaError_t e = cudaMalloc((void**)&d_val, sizeof(double) * (size_t)nnz);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&row_of, sizeof(int32_t) * (size_t)nnz);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&keys, sizeof(uint32_t) * (size_t)nnz);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&idx, sizeof(uint32_t) * (size_t)nnz);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&keys2, sizeof(uint32_t) * (size_t)nnz);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&perm, sizeof(uint32_t) * (size_t)nnz);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_flags, sizeof(int));
-    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, perm, (int)nnz, 0, 32, st);
-    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_val, h_val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_flags, 0, sizeof(int), st);
-    if (e == cudaSuccess) {
-        const int nb = lrk_ceil_div(nnz, 256);
-        coo_expand_kernel<<<nb, 256, 0, st>>>(d_rowptr, U, nnz, h->cfg.seed, row_of, keys, idx);
-        h->launches++;
-        if (validate) {
-            const int64_t m = nnz > U ? nnz : U;
-            csr_validate_kernel<<<lrk_ceil_div(m, 256), 256, 0, st>>>(d_rowptr, d_col, U, I, nnz, d_flags);
-            csr_validate_rows_kernel<<<nb, 256, 0, st>>>(d_rowptr, d_col, row_of, nnz, d_flags);
-            h->launches += 2;
-        }
-        e = cudaGetLastError();
+    LRK_CUDA(h, cudaMemcpyAsync(d_val, h_val, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    LRK_CUDA(h, cudaMemsetAsync(d_flags, 0, sizeof(int), st));
+    const int nb = lrk_ceil_div(nnz, 256);
+    coo_expand_kernel<<<nb, 256, 0, st>>>(d_rowptr, U, nnz, h->cfg.seed, row_of, keys, idx);
+    LRK_LAUNCH_CHECK(h);
+    if (validate) {
+        const int64_t m = nnz > U ? nnz : U;
+        csr_validate_kernel<<<lrk_ceil_div(m, 256), 256, 0, st>>>(d_rowptr, d_col, U, I, nnz, d_flags);
+        LRK_LAUNCH_CHECK(h);
+        csr_validate_rows_kernel<<<nb, 256, 0, st>>>(d_rowptr, d_col, row_of, nnz, d_flags);
+        LRK_LAUNCH_CHECK(h);
     }
-    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, perm, (int)nnz, 0, 32, st);
-    if (e == cudaSuccess) {
-        coo_gather_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(perm, row_of, d_col, d_val, nnz, su, si, sr);
-        h->launches++;
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_val); cudaFree(row_of); cudaFree(keys); cudaFree(idx); cudaFree(keys2); cudaFree(perm); cudaFree(tmp); cudaFree(d_flags);
-    LRK_CUDA(h, e);
+    LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, perm, (int)nnz, 0, 32, st));
+    coo_gather_kernel<<<nb, 256, 0, st>>>(perm, row_of, d_col, d_val, nnz, su, si, sr);
+    LRK_LAUNCH_CHECK(h);
+    LRK_CUDA(h, cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
     if (flags & 1) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "rowptr is not a monotone prefix sum ending at nnz", __FILE__, __LINE__);
     if (flags & 2) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "column index out of range", __FILE__, __LINE__);
     if (flags & 4) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "columns must be strictly ascending inside a row", __FILE__, __LINE__);

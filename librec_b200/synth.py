@@ -24,14 +24,17 @@ def _cache_dir():
     return d
 
 
-def make_ratings(shape="ml-20m", binary=False, cache=True):
-    """-> dict(U, I, rowptr int64[U+1], col int32[nnz], val float64[nnz]) ; exactly SHAPES[shape] nnz"""
+def make_ratings(shape="ml-20m", binary=False, cache=True, shard=0):
+    """-> dict(U, I, rowptr int64[U+1], col int32[nnz], val float64[nnz]) ; exactly SHAPES[shape] nnz.
+    `shard` selects an independent block of users over the SAME item catalogue (same popularity and
+    planted item factors) -- the per-rank user shard of the weak-scaling DSGD runs."""
     U, I, nnz, seed = SHAPES[shape]
-    path = os.path.join(_cache_dir(), "%s_%s.npz" % (shape, "bin" if binary else "rat"))
+    path = os.path.join(_cache_dir(), "%s_%s_s%d.npz" % (shape, "bin" if binary else "rat", shard))
     if cache and os.path.exists(path):
         z = np.load(path)
         return {"U": U, "I": I, "rowptr": z["rowptr"], "col": z["col"], "val": z["val"].astype(np.float64)}
-    rng = np.random.default_rng(seed)
+    rng_items = np.random.default_rng(seed)               # shared by all shards
+    rng = np.random.default_rng([seed, shard])            # user side of this shard
     # user activity: log-normal, clipped to [20, I/2], rescaled to the target total
     deg = np.exp(rng.normal(0.0, 1.0, U))
     deg = deg / deg.sum() * nnz
@@ -39,7 +42,7 @@ def make_ratings(shape="ml-20m", binary=False, cache=True):
     deg = deg / deg.sum() * nnz
     # item popularity: Zipf(1.0) over a random permutation of item ids
     pop = 1.0 / np.arange(1, I + 1, dtype=np.float64)
-    pop = pop[rng.permutation(I)]
+    pop = pop[rng_items.permutation(I)]
     cdf = np.cumsum(pop / pop.sum())
     keys = np.zeros(0, np.int64)
     over = 1.9
@@ -66,9 +69,9 @@ def make_ratings(shape="ml-20m", binary=False, cache=True):
     else:
         r = 16
         ps = rng.normal(0, 1.0, (U, r)).astype(np.float32)
-        qs = rng.normal(0, 1.0, (I, r)).astype(np.float32)
+        qs = rng_items.normal(0, 1.0, (I, r)).astype(np.float32)
         bu = rng.normal(0, 0.3, U).astype(np.float32)
-        bi = rng.normal(0, 0.3, I).astype(np.float32)
+        bi = rng_items.normal(0, 0.3, I).astype(np.float32)
         val = np.empty(nnz, np.float32)
         step = 1 << 22
         for a in range(0, nnz, step):
