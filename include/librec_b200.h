@@ -54,7 +54,11 @@ typedef enum { LRK_MODEL_BIASEDMF = 0, LRK_MODEL_PMF = 1, LRK_MODEL_BPR = 2 } lr
 /* how concurrent updates to one factor row are combined */
 typedef enum {
     LRK_UPDATE_ATOMIC = 0,  /* red.global.add.v4.f32: no lost updates (default; needed for RMSE parity) */
-    LRK_UPDATE_HOGWILD = 1  /* plain racy read-modify-write stores                                      */
+    LRK_UPDATE_HOGWILD = 1, /* plain racy read-modify-write stores                                      */
+    /* parity mode: the reference's sequential CSR-order walk executed as a dependency wavefront in
+     * fp64 with Java's operation order -- learned factors are bit-identical to the reference
+     * arithmetic; throughput is bounded by the longest dependency chain (BiasedMF / PMF only) */
+    LRK_UPDATE_REFERENCE_ORDER = 2
 } lrk_update_mode;
 
 typedef struct {

@@ -3,6 +3,7 @@
 #include "lrk_common.cuh"
 #include "staging.cuh"
 #include "sgd.cuh"
+#include "sgd_exact.cuh"
 #include "topn_exact.cuh"
 #include "topn_tc.cuh"
 #include "dsgd.cuh"
@@ -50,8 +51,10 @@ int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out) {
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "num_factors must be in 1..256", __FILE__, __LINE__);
     if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_BPR)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown model", __FILE__, __LINE__);
-    if (cfg->update_mode != LRK_UPDATE_ATOMIC && cfg->update_mode != LRK_UPDATE_HOGWILD)
+    if (cfg->update_mode < LRK_UPDATE_ATOMIC || cfg->update_mode > LRK_UPDATE_REFERENCE_ORDER)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown update_mode", __FILE__, __LINE__);
+    if (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER && cfg->model == LRK_MODEL_BPR)
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "reference-order mode covers BiasedMF and PMF (BPR draws from a sequential RNG)", __FILE__, __LINE__);
     int ndev = 0;
     LRK_CUDA(nullptr, cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev)
@@ -90,6 +93,7 @@ int lrk_destroy(lrk_handle_t h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     dsgd_release(h);
     topn_tc_release(h);
+    exact_release((ExactSchedule*)h->exact);
     lrk_dev_free(&h->d_rowptr); lrk_dev_free(&h->d_col);
     lrk_dev_free(&h->d_su); lrk_dev_free(&h->d_si); lrk_dev_free(&h->d_sr);
     lrk_dev_free(&h->P32); lrk_dev_free(&h->Q32); lrk_dev_free(&h->bu32); lrk_dev_free(&h->bi32);
@@ -139,6 +143,13 @@ int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowpt
     h->U = U; h->I = I; h->nnz = nnz;
     rc = stage_coo_from_csr(h, h->d_rowptr, h->d_col, val, U, I, nnz, h->d_su, h->d_si, h->d_sr, /*validate=*/true);
     if (rc) return rc;
+    if (h->cfg.update_mode == LRK_UPDATE_REFERENCE_ORDER) {
+        exact_release((ExactSchedule*)h->exact);
+        h->exact = nullptr;
+        ExactSchedule* es = nullptr;
+        if ((rc = exact_build_schedule(h, &es, U, I, rowptr, col, val))) return rc;
+        h->exact = es;
+    }
     h->has_train = true;
     topn_tc_invalidate(h);
     return LRK_OK;
@@ -233,6 +244,24 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->world > 1) return dsgd_epoch(h, lr, reg_u, reg_i, reg_b, epoch_idx, loss_out);
     cudaStream_t st = h->stream;
+    if (h->cfg.update_mode == LRK_UPDATE_REFERENCE_ORDER) {
+        // fp64 masters are the working set in this mode
+        int rc = refresh_masters(h);
+        if (rc) return rc;
+        LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
+        LRK_CUDA(h, cudaEventRecord(h->ev0, st));
+        if (h->nnz > 0 && (rc = exact_epoch(h, (ExactSchedule*)h->exact, lr, reg_u, reg_i, reg_b, &h->bar_generation))) return rc;
+        LRK_CUDA(h, cudaEventRecord(h->ev1, st));
+        topn_tc_invalidate(h);
+        LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+        LRK_CUDA(h, cudaStreamSynchronize(st));
+        LRK_CUDA(h, cudaEventElapsedTime(&h->last_epoch_ms, h->ev0, h->ev1));
+        const double loss = 0.5 * h->h_loss[0];
+        if (loss_out) *loss_out = loss;
+        if (std::isnan(loss) || std::isinf(loss))
+            return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);
+        return LRK_OK;
+    }
     SgdParams sp;
     fill_sgd_params(h, sp, lr, reg_u, reg_i, reg_b, epoch_idx);
     LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
@@ -429,6 +458,7 @@ int lrk_topn_stats(lrk_handle_t h, int64_t* fast_users, int64_t* fallback_users,
 int lrk_comm_unique_id(uint8_t out[128]) { return dsgd_unique_id(out); }
 int lrk_comm_init(lrk_handle_t h, int32_t rank, int32_t world, const uint8_t unique_id[128]) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, h->cfg.update_mode != LRK_UPDATE_REFERENCE_ORDER, "reference-order mode is single-GPU");
     return dsgd_comm_init(h, rank, world, unique_id);
 }
 

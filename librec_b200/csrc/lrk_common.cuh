@@ -50,6 +50,10 @@ struct lrk_handle_s {
     // tensor-core top-N state (bf16 copies, norms); see topn_tc.cuh
     void* tc = nullptr;
 
+    // reference-order (wavefront) schedule, see sgd_exact.cuh
+    void* exact = nullptr;
+    unsigned long long bar_generation = 0;
+
     // DSGD
     void* comm = nullptr;   // ncclComm_t
     int rank = 0, world = 1;

@@ -351,14 +351,21 @@ __global__ void __launch_bounds__(256) sgd_bpr_epoch_kernel(SgdParams p) {
 // ---------------------------------------------------------------------------------------------
 // launch plumbing
 // ---------------------------------------------------------------------------------------------
+// Grid: whole multiples of the SM count for big inputs.  For small inputs the number of ratings in
+// flight is capped at nnz/16 (8 warps x ratings-per-step x 2 pipeline stages per block): with the
+// whole matrix in flight at once the epoch degenerates into one full-batch gradient step, which is
+// unstable at SGD learning rates (observed: PMF on ml-100k diverges) -- DESIGN.md "staleness cap".
 template <typename K>
-static int sgd_grid_for(lrk_handle_s* h, K kernel, int64_t n, int* grid_out) {
+static int sgd_grid_for(lrk_handle_s* h, K kernel, int64_t n, int rps, int* grid_out) {
     int per_sm = 0;
     LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)h->sm_count * per_sm;           // whole multiples of the SM count
     const int64_t need = ((n + 31) / 32 + 7) / 8;           // 8 warps per block, one tile per warp
-    if (need < grid) grid = need < 1 ? 1 : need;
+    if (need < grid) grid = need;
+    const int64_t stale_cap = (n / 16) / (8 * (int64_t)rps * 2);
+    if (stale_cap < grid) grid = stale_cap;
+    if (grid < 1) grid = 1;
     *grid_out = (int)grid;
     return LRK_OK;
 }
@@ -369,7 +376,7 @@ static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp) {
     int grid = 1;
 #define LRK_GO(KERN)                                                          \
     do {                                                                      \
-        int rc__ = sgd_grid_for(h, KERN, sp.n, &grid);                        \
+        int rc__ = sgd_grid_for(h, KERN, sp.n, 32 / G, &grid);                        \
         if (rc__) return rc__;                                                \
         KERN<<<grid, 256, 0, h->stream>>>(sp);                                \
     } while (0)
