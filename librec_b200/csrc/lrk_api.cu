@@ -389,20 +389,6 @@ int lrk_eval_rating(lrk_handle_t h, int32_t U, const int64_t* t_rowptr, const in
 }
 
 // -------------------------------------------------------------------------------------------
-// exact fp64 top-N for `nq` query slots whose user ids are in d_users (device) or NULL (= 0..nq-1);
-// results to device buffers
-static int topn_exact_launch(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int topn, int exclude_train,
-                             int32_t* d_items, double* d_scores, int32_t* d_counts) {
-    const size_t smem = topn_exact_smem(h->k, topn);
-    LRK_CUDA(h, cudaFuncSetAttribute(topn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = lrk_ceil_div(nq, TOPN_UPB);
-    topn_exact_kernel<<<grid, TOPN_WARPS * 32, smem, h->stream>>>(
-        h->P64, h->Q64, h->bu64, h->bi64, h->mu, h->cfg.model == LRK_MODEL_BIASEDMF, h->k, h->I,
-        h->d_rowptr, h->d_col, exclude_train, d_users, nq, topn, d_items, d_scores, d_counts);
-    LRK_LAUNCH_CHECK(h);
-    return LRK_OK;
-}
-
 int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int32_t exclude_train,
              int32_t* out_items, double* out_scores, int32_t* out_counts) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");

@@ -1,9 +1,637 @@
-// Tensor-core (tcgen05 / TMA) top-N candidate path -- see DESIGN.md "Top-N".  Filled in below.
+// Tensor-core top-N (sm_100a): recommendRank()'s user x item score sweep
+// (recommender/MatrixRecommender.java:153-201) as a tcgen05 / TMA bf16 GEMM with the selection fused
+// into the epilogue, followed by an exact fp64 re-score -- so the lists that leave the library are
+// still bit-identical to the reference (util/Lists.java:416-468 semantics).
+//
+//   1. operands: A = queried user factors, B = item factors, both K-major bf16, K padded to 64;
+//      BiasedMF folds the item bias into two extra K columns (hi/lo bf16 split against 1.0 in A).
+//   2. topn_tc_kernel (persistent, warp-specialised, 1 CTA/SM, 320 threads):
+//        warp 0  TMA producer   cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier ring
+//        warp 1  MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16; two user
+//                               sub-tiles (256 users) share every item tile -> halves L2->SM traffic;
+//                               accumulators double-buffered in all 512 TMEM columns
+//        warps 2-9 epilogue     tcgen05.ld 32x32b.x32: one thread owns one user row; a score is
+//                               appended to the row's candidate list only if it beats the row's running
+//                               threshold tau (1 FMNMX per score + 1 compare per 8 scores in the common
+//                               case); train items are masked on the rare append path; full lists are
+//                               compacted warp-cooperatively to the best K' (tau rises).
+//      Invariant: every item that is NOT in a row's candidate list has approximate score <= tau_row
+//      (or is a train item / NaN / out of range).
+//   3. topn_tc_rescore_kernel: exact fp64 scores of the candidates in Java's summation order, top-N,
+//      and an exactness certificate: N-th exact score > tau + error bound of the bf16 sweep, and no
+//      exact ties among the first N+1.  Rows that fail are re-done by the exact kernel (topn_exact.cuh).
 #pragma once
 #include "lrk_common.cuh"
-static inline void topn_tc_release(lrk_handle_s*) {}
-static inline void topn_tc_invalidate(lrk_handle_s*) {}
-static inline bool topn_tc_profitable(lrk_handle_s*, int32_t, int) { return false; }
-static inline int topn_tc_run(lrk_handle_s* h, const int32_t*, int32_t, int, int, int32_t*, double*, int32_t*) {
-    return lrk_fail(h, LRK_ERR_INVALID, "lrk_topn", "tensor-core candidate path not built into this library", __FILE__, __LINE__);
+#include "topn_exact.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cudaTypedefs.h>
+#include <cmath>
+#include <algorithm>
+
+#define TC_TILE_M 128          // users per accumulator
+#define TC_UT 2                // user sub-tiles per CTA
+#define TC_TILE_N 128          // items per MMA tile
+#define TC_KB 64               // bf16 elements per 128-byte swizzle row
+#define TC_CAP 96              // candidate slots per (row, chunk)
+#define TC_KEEP 32             // K': entries kept by a compaction
+#define TC_THREADS 320
+#define TC_MAX_CHUNKS 16
+
+struct TcState {
+    __nv_bfloat16* Bq = nullptr;      // [I x Kp]
+    int Kp = 0;
+    bool valid = false;
+    double qnorm_max = 0.0, bi_max = 0.0;
+    unsigned long long* d_stats = nullptr;   // [0] max ||q||^2 bits, [1] max |bi| bits
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+};
+
+static inline TcState* tc_state(lrk_handle_s* h) {
+    if (!h->tc) h->tc = new TcState();
+    return (TcState*)h->tc;
+}
+static inline void topn_tc_release(lrk_handle_s* h) {
+    TcState* s = (TcState*)h->tc;
+    if (!s) return;
+    cudaFree(s->Bq); cudaFree(s->d_stats);
+    delete s;
+    h->tc = nullptr;
+}
+static inline void topn_tc_invalidate(lrk_handle_s* h) {
+    if (h->tc) ((TcState*)h->tc)->valid = false;
+}
+static inline int tc_kp(lrk_handle_s* h) {
+    const int kaug = h->k + (h->cfg.model == LRK_MODEL_BIASEDMF ? 2 : 0);
+    return ((kaug + TC_KB - 1) / TC_KB) * TC_KB;
+}
+static inline bool topn_tc_profitable(lrk_handle_s* h, int32_t nq, int topn) {
+    return topn <= 16 && tc_kp(h) <= 192 && h->I >= 8192 && nq >= 512;
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand builders
+// ------------------------------------------------------------------------------------------------
+__global__ void tc_build_items_kernel(const double* __restrict__ Q, const double* __restrict__ bi, int biased, int k, int Kp,
+                                      int32_t I, __nv_bfloat16* __restrict__ out, unsigned long long* __restrict__ stats) {
+    const int32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= I) return;
+    double n2 = 0.0;
+    for (int f = lane; f < Kp; f += 32) {
+        float v = 0.f;
+        if (f < k) { const double q = Q[(int64_t)i * k + f]; n2 += q * q; v = (float)q; }
+        else if (biased && f == k) v = __bfloat162float(__float2bfloat16_rn((float)bi[i]));
+        else if (biased && f == k + 1) { const float b = (float)bi[i]; v = b - __bfloat162float(__float2bfloat16_rn(b)); }
+        out[(int64_t)i * Kp + f] = __float2bfloat16_rn(v);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, m);
+    if (lane == 0) {
+        atomicMax(stats, (unsigned long long)__double_as_longlong(n2));
+        if (biased) atomicMax(stats + 1, (unsigned long long)__double_as_longlong(fabs(bi[i])));
+    }
+}
+__global__ void tc_build_users_kernel(const double* __restrict__ P, int biased, int k, int Kp, const int32_t* __restrict__ users,
+                                      int32_t nq, __nv_bfloat16* __restrict__ out, double* __restrict__ pnorm) {
+    const int32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= nq) return;
+    const int32_t u = users ? users[c] : c;
+    double n2 = 0.0;
+    for (int f = lane; f < Kp; f += 32) {
+        float v = 0.f;
+        if (f < k) { const double p = P[(int64_t)u * k + f]; n2 += p * p; v = (float)p; }
+        else if (biased && (f == k || f == k + 1)) v = 1.f;
+        out[(int64_t)c * Kp + f] = __float2bfloat16_rn(v);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, m);
+    if (lane == 0) pnorm[c] = sqrt(n2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);      // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=128, M=128
+#define TC_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE_N >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24))
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+struct TcParams {
+    int32_t nq, I;
+    int n_chunks, tiles_per_chunk, total_tiles, num_kb, stages;
+    int exclude_train;
+    const int64_t* __restrict__ rowptr;
+    const int32_t* __restrict__ col;
+    const int32_t* __restrict__ users;
+    float* cand_score;      // [nq_pad][n_chunks][TC_CAP]
+    int32_t* cand_item;
+    int32_t* cand_cnt;      // [nq_pad][n_chunks]
+    float* cand_tau;
+};
+
+// warp-cooperative compaction of the candidate list of the row owned by lane `src`:
+// keeps the entries strictly above the TC_KEEP-th largest value, which becomes the row's new tau
+__device__ __forceinline__ void tc_compact(float* cs, int32_t* ci, int cnt, int lane, int& new_cnt, float& new_tau) {
+    float v[3]; int32_t it[3]; int rank[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int e = lane + 32 * j;
+        v[j] = e < cnt ? __ldcg(cs + e) : -INFINITY;
+        it[j] = e < cnt ? __ldcg(ci + e) : -1;
+        rank[j] = 0;
+    }
+#pragma unroll
+    for (int oj = 0; oj < 3; ++oj) {
+        for (int ol = 0; ol < 32; ++ol) {
+            const float o = __shfl_sync(0xffffffffu, v[oj], ol);
+            const int oe = ol + 32 * oj;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int e = lane + 32 * j;
+                rank[j] += (o > v[j] || (o == v[j] && oe < e)) ? 1 : 0;
+            }
+        }
+    }
+    // the entry of rank TC_KEEP-1 is the new threshold
+    float tau = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) if (rank[j] == TC_KEEP - 1) tau = v[j];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, m));
+    __syncwarp();
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const bool keep = v[j] > tau;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            __stcg(cs + pos, v[j]); __stcg(ci + pos, it[j]);
+        }
+        base += __popc(m);
+    }
+    __syncwarp();
+    new_cnt = base; new_tau = tau;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    // carve: 1024-aligned operand tiles, then barriers
+    unsigned char* base = (unsigned char*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t tile_bytes = TC_TILE_M * TC_KB * 2;               // 16 KB: 128 rows x 128 B
+    unsigned char* smA = base;                                       // [UT][num_kb] tiles
+    unsigned char* smB = smA + (size_t)TC_UT * p.num_kb * tile_bytes; // [stages][num_kb] tiles
+    uint64_t* bars = (uint64_t*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);
+    // barrier map: [0..S) b_full, [S..2S) b_empty, 2S a_full, 2S+1 a_empty, 2S+2.. tmem_full[2], tmem_empty[2]
+    const int S = p.stages;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 6);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto BAR = [&](int i) { return smem_u32(bars + i); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(S + s), 1); }
+        mbar_init(BAR(2 * S), 1); mbar_init(BAR(2 * S + 1), 1);
+        mbar_init(BAR(2 * S + 2), 1); mbar_init(BAR(2 * S + 3), 1);
+        mbar_init(BAR(2 * S + 4), 8); mbar_init(BAR(2 * S + 5), 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tiles = (p.nq + TC_TILE_M * TC_UT - 1) / (TC_TILE_M * TC_UT);
+    const int num_units = m_tiles * p.n_chunks;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0, a_ph = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int mt = unit / p.n_chunks, ch = unit - mt * p.n_chunks;
+                mbar_wait(BAR(2 * S + 1), a_ph ^ 1);                       // A slot free
+                mbar_expect_tx(BAR(2 * S), TC_UT * p.num_kb * tile_bytes);
+                for (int a = 0; a < TC_UT; ++a)
+                    for (int kb = 0; kb < p.num_kb; ++kb)
+                        tma_load_2d(smem_u32(smA + (size_t)(a * p.num_kb + kb) * tile_bytes), &tmA, kb * TC_KB,
+                                    (mt * TC_UT + a) * TC_TILE_M, BAR(2 * S));
+                a_ph ^= 1;
+                const int t0 = ch * p.tiles_per_chunk;
+                const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(BAR(S + st), ph ^ 1);                        // B slot free
+                    mbar_expect_tx(BAR(st), p.num_kb * tile_bytes);
+                    for (int kb = 0; kb < p.num_kb; ++kb)
+                        tma_load_2d(smem_u32(smB + (size_t)(st * p.num_kb + kb) * tile_bytes), &tmB, kb * TC_KB, t * TC_TILE_N, BAR(st));
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0, a_ph = 0; int as = 0; uint32_t as_ph = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int mt = unit / p.n_chunks, ch = unit - mt * p.n_chunks;
+                (void)mt;
+                mbar_wait(BAR(2 * S), a_ph);                               // A landed
+                a_ph ^= 1;
+                const int t0 = ch * p.tiles_per_chunk;
+                const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(BAR(2 * S + 4 + as), as_ph ^ 1);             // accumulator stage drained
+                    mbar_wait(BAR(st), ph);                                // B landed
+                    tc_fence_after();
+                    for (int a = 0; a < TC_UT; ++a) {
+                        const uint32_t d = tmem_base + (uint32_t)(as * 256 + a * TC_TILE_N);
+                        for (int kb = 0; kb < p.num_kb; ++kb) {
+                            const uint32_t a_addr = smem_u32(smA + (size_t)(a * p.num_kb + kb) * tile_bytes);
+                            const uint32_t b_addr = smem_u32(smB + (size_t)(st * p.num_kb + kb) * tile_bytes);
+#pragma unroll
+                            for (int k4 = 0; k4 < TC_KB / 16; ++k4)
+                                tc_mma_f16(d, tc_smem_desc(a_addr + k4 * 32), tc_smem_desc(b_addr + k4 * 32), TC_IDESC,
+                                           (kb | k4) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(BAR(S + st));                                // B slot reusable once these MMAs retire
+                    tc_commit(BAR(2 * S + 2 + as));                        // accumulators ready for the epilogue
+                    if (++st == S) { st = 0; ph ^= 1; }
+                    if (++as == 2) { as = 0; as_ph ^= 1; }
+                }
+                tc_commit(BAR(2 * S + 1));                                 // A slot reusable
+            }
+        }
+    } else {
+        // ================= epilogue: one thread == one user row =================
+        const int ew = warp - 2;
+        const int a = ew >> 2;                 // user sub-tile
+        const int q = warp & 3;                // TMEM lane quarter this warp may read
+        const int row_in_cta = a * TC_TILE_M + q * 32 + lane;
+        int as = 0; uint32_t as_ph = 0;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            const int mt = unit / p.n_chunks, ch = unit - mt * p.n_chunks;
+            const int32_t c = mt * (TC_TILE_M * TC_UT) + row_in_cta;
+            const bool valid = c < p.nq;
+            const int t0 = ch * p.tiles_per_chunk;
+            const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+            const int32_t i1 = min(p.I, t1 * TC_TILE_N);
+            float* cs = p.cand_score + ((size_t)c * p.n_chunks + ch) * TC_CAP;
+            int32_t* ci = p.cand_item + ((size_t)c * p.n_chunks + ch) * TC_CAP;
+            int64_t tp = 0, tend = 0;
+            if (valid && p.exclude_train) {
+                const int32_t u = p.users ? p.users[c] : c;
+                tp = p.rowptr[u]; tend = p.rowptr[u + 1];
+                const int32_t i0 = t0 * TC_TILE_N;
+                int64_t lo = tp, hi = tend;
+                while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (__ldg(p.col + m) < i0) lo = m + 1; else hi = m; }
+                tp = lo;
+            }
+            float tau = -INFINITY;
+            int cnt = 0;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(BAR(2 * S + 2 + as), as_ph);
+                tc_fence_after();
+                const int32_t n0 = t * TC_TILE_N;
+#pragma unroll 1
+                for (int cb = 0; cb < TC_TILE_N / 32; ++cb) {
+                    float v[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + a * TC_TILE_N + cb * 32), v);
+                    if (cb == TC_TILE_N / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(2 * S + 4 + as));      // this warp has drained the stage
+                    }
+                    float m = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                    if (valid && m > tau) {
+                        // rare path: some of the 32 scores beat the row threshold
+                        float lv[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) lv[j] = v[j];
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = lv[j];
+                            if (!(x > tau)) continue;
+                            const int32_t item = n0 + cb * 32 + j;
+                            if (item >= i1) continue;
+                            if (p.exclude_train) {             // MatrixRecommender.java:170-174
+                                int64_t lo = tp, hi = tend;
+                                while (lo < hi) { const int64_t mm = (lo + hi) >> 1; if (__ldg(p.col + mm) < item) lo = mm + 1; else hi = mm; }
+                                tp = lo;
+                                if (lo < tend && __ldg(p.col + lo) == item) continue;
+                            }
+                            __stcg(cs + cnt, x); __stcg(ci + cnt, item);
+                            ++cnt;
+                        }
+                    }
+                    // lists that could overflow during the next 32 columns are compacted now (warp-uniform)
+                    uint32_t need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int scnt = __shfl_sync(0xffffffffu, cnt, src);
+                        const int32_t sc = c - lane + src;
+                        int ncnt; float ntau;
+                        tc_compact(p.cand_score + ((size_t)sc * p.n_chunks + ch) * TC_CAP,
+                                   p.cand_item + ((size_t)sc * p.n_chunks + ch) * TC_CAP, scnt, lane, ncnt, ntau);
+                        if (lane == src) { cnt = ncnt; tau = ntau; }
+                    }
+                }
+                if (++as == 2) { as = 0; as_ph ^= 1; }
+            }
+            if (valid) {
+                p.cand_cnt[(size_t)c * p.n_chunks + ch] = cnt;
+                p.cand_tau[(size_t)c * p.n_chunks + ch] = tau;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact re-score + certificate, one warp per query slot
+// ------------------------------------------------------------------------------------------------
+#define TC_RS_WARPS 4
+__global__ void __launch_bounds__(TC_RS_WARPS * 32) topn_tc_rescore_kernel(
+    const double* __restrict__ P, const double* __restrict__ Q, const double* __restrict__ bu, const double* __restrict__ bi,
+    double mu, int biased, int k, const int32_t* __restrict__ users, int32_t nq, int n_chunks, int topn,
+    const float* __restrict__ cand_score, const int32_t* __restrict__ cand_item, const int32_t* __restrict__ cand_cnt,
+    const float* __restrict__ cand_tau, const double* __restrict__ pnorm, double qnorm_max, double bi_max, double c_err,
+    int32_t* __restrict__ out_items, double* __restrict__ out_scores, int32_t* __restrict__ out_counts,
+    int32_t* __restrict__ fail_slots, int32_t* __restrict__ fail_users, int* __restrict__ fail_count) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int max_cand = n_chunks * TC_CAP;
+    double* sv = reinterpret_cast<double*>(rs_smem) + (size_t)warp * max_cand;
+    int32_t* si = reinterpret_cast<int32_t*>(reinterpret_cast<double*>(rs_smem) + (size_t)TC_RS_WARPS * max_cand) + (size_t)warp * max_cand;
+    const int32_t c = blockIdx.x * TC_RS_WARPS + warp;
+    if (c >= nq) return;
+    const int32_t u = users ? users[c] : c;
+    // gather candidates of all chunks
+    int M = 0;
+    float tau_max = -INFINITY;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int cnt = cand_cnt[(size_t)c * n_chunks + ch];
+        tau_max = fmaxf(tau_max, cand_tau[(size_t)c * n_chunks + ch]);
+        for (int e = lane; e < cnt; e += 32) si[M + e] = cand_item[((size_t)c * n_chunks + ch) * TC_CAP + e];
+        M += cnt;
+    }
+    __syncwarp();
+    // exact scores in Java's order (DenseVector.java:104-111; BiasedMFRecommender.java:119)
+    const double* pu = P + (int64_t)u * k;
+    for (int e = lane; e < M; e += 32) {
+        const int32_t it = si[e];
+        double d = dot_lr_f64(pu, Q + (int64_t)it * k, k);
+        if (biased) d = __dadd_rn(__dadd_rn(__dadd_rn(d, bu[u]), bi[it]), mu);
+        sv[e] = d;
+    }
+    __syncwarp();
+    bool ok = M >= topn;
+    // selection of the best topn+1 by (Double.compareTo desc); a tie anywhere in that prefix fails the row
+    double prev = 0.0;
+    const int want = min(M, topn + 1);
+    for (int r = 0; ok && r < want; ++r) {
+        double bv = -INFINITY; int be = -1;
+        for (int e = lane; e < M; e += 32) {
+            const double x = sv[e];
+            if (si[e] >= 0 && (be < 0 || jcompare(x, bv) > 0)) { bv = x; be = e; }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, m);
+            const int oe = __shfl_xor_sync(0xffffffffu, be, m);
+            if (oe >= 0 && (be < 0 || jcompare(ov, bv) > 0 || (jcompare(ov, bv) == 0 && oe < be))) { bv = ov; be = oe; }
+        }
+        if (be < 0 || bv != bv) { ok = false; break; }
+        if (r > 0 && jcompare(bv, prev) == 0) { ok = false; break; }      // exact tie: heap-order semantics needed
+        if (r < topn && lane == 0) { out_items[(int64_t)c * topn + r] = si[be]; out_scores[(int64_t)c * topn + r] = bv; }
+        if (r == topn - 1) {
+            // certificate: nothing outside the candidate lists can reach the N-th exact score
+            const double ub = biased ? bu[u] : 0.0;
+            const double scale = pnorm[c] * qnorm_max + bi_max;
+            const double bound = c_err * scale + 1e-12 * (scale + fabs(ub) + fabs(mu) + fabs((double)tau_max));
+            const double reach = (double)tau_max + bound + (biased ? (ub + mu) : 0.0);
+            if (!(bv > reach)) { ok = false; break; }
+        }
+        prev = bv;
+        __syncwarp();
+        if (lane == 0) si[be] = -1 - si[be];     // taken
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (ok) out_counts[c] = topn;
+        else {
+            const int pos = atomicAdd(fail_count, 1);
+            fail_slots[pos] = c; fail_users[pos] = u;
+        }
+    }
+}
+
+__global__ void tc_scatter_fallback_kernel(const int32_t* __restrict__ slots, int nfail, int topn, const int32_t* __restrict__ fi,
+                                           const double* __restrict__ fs, const int32_t* __restrict__ fc,
+                                           int32_t* __restrict__ out_items, double* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nfail * topn) return;
+    const int f = t / topn, r = t - f * topn;
+    const int32_t c = slots[f];
+    out_items[(int64_t)c * topn + r] = fi[t];
+    out_scores[(int64_t)c * topn + r] = fs[t];
+    if (r == 0) out_counts[c] = fc[f];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+static int tc_make_map(lrk_handle_s* h, TcState* s, CUtensorMap* map, const void* gptr, int Kp, int64_t rows) {
+    if (!s->encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        LRK_CUDA(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess)
+            return lrk_fail(h, LRK_ERR_CUDA, "cuTensorMapEncodeTiled", "driver entry point not available", __FILE__, __LINE__);
+        s->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {TC_KB, TC_TILE_M};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = s->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return lrk_fail(h, LRK_ERR_CUDA, "cuTensorMapEncodeTiled", "encode failed", __FILE__, __LINE__);
+    return LRK_OK;
+}
+
+static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int topn, int exclude_train,
+                       int32_t* d_items, double* d_scores, int32_t* d_counts) {
+    TcState* s = tc_state(h);
+    cudaStream_t st = h->stream;
+    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    const int Kp = tc_kp(h);
+    const int num_kb = Kp / TC_KB;
+    if (num_kb > 3 || topn > TC_KEEP / 2)
+        return lrk_fail(h, LRK_ERR_INVALID, "lrk_topn", "tensor-core path supports k (+2 for BiasedMF) <= 192 and topn <= 16", __FILE__, __LINE__);
+    // ---- item operand (cached until the factors change)
+    if (!s->valid || s->Kp != Kp) {
+        if (s->Bq) { cudaFree(s->Bq); s->Bq = nullptr; }
+        LRK_CUDA(h, cudaMalloc((void**)&s->Bq, sizeof(__nv_bfloat16) * (size_t)h->I * Kp));
+        if (!s->d_stats) LRK_CUDA(h, cudaMalloc((void**)&s->d_stats, 16));
+        LRK_CUDA(h, cudaMemsetAsync(s->d_stats, 0, 16, st));
+        tc_build_items_kernel<<<lrk_ceil_div(h->I, 8), 256, 0, st>>>(h->Q64, h->bi64, biased, h->k, Kp, h->I, s->Bq, s->d_stats);
+        LRK_LAUNCH_CHECK(h);
+        unsigned long long stats[2];
+        LRK_CUDA(h, cudaMemcpyAsync(stats, s->d_stats, 16, cudaMemcpyDeviceToHost, st));
+        LRK_CUDA(h, cudaStreamSynchronize(st));
+        double n2, bm;
+        memcpy(&n2, &stats[0], 8); memcpy(&bm, &stats[1], 8);
+        s->qnorm_max = sqrt(n2); s->bi_max = biased ? bm : 0.0;
+        s->Kp = Kp; s->valid = true;
+    }
+    // ---- work decomposition
+    const int total_tiles = lrk_ceil_div(h->I, TC_TILE_N);
+    const int m_tiles = lrk_ceil_div(nq, TC_TILE_M * TC_UT);
+    int n_chunks = lrk_ceil_div(h->sm_count, m_tiles);
+    n_chunks = std::max(1, std::min(n_chunks, std::min(TC_MAX_CHUNKS, std::max(1, total_tiles / 16))));
+    const int tiles_per_chunk = lrk_ceil_div(total_tiles, n_chunks);
+    n_chunks = lrk_ceil_div(total_tiles, tiles_per_chunk);
+    const int64_t nq_pad = (int64_t)m_tiles * TC_TILE_M * TC_UT;
+    const size_t tile_bytes = (size_t)TC_TILE_M * TC_KB * 2;
+    const size_t a_bytes = (size_t)TC_UT * num_kb * tile_bytes, b_stage = (size_t)num_kb * tile_bytes;
+    int stages = (int)((200 * 1024 - a_bytes) / b_stage);
+    stages = std::max(2, std::min(stages, 6));
+    const size_t smem = 1024 + a_bytes + (size_t)stages * b_stage + (2 * stages + 6) * 8 + 16;
+    // ---- query operand + scratch
+    __nv_bfloat16* Aq = nullptr; double* pnorm = nullptr; float *cscore = nullptr, *ctau = nullptr; int32_t *citem = nullptr, *ccnt = nullptr;
+    int32_t *fail_slots = nullptr, *fail_users = nullptr; int* fail_count = nullptr;
+    int32_t *fi = nullptr, *fc = nullptr; double* fs = nullptr;
+    int rc = LRK_OK;
+    cudaError_t e = cudaMalloc((void**)&Aq, sizeof(__nv_bfloat16) * (size_t)nq_pad * Kp);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pnorm, sizeof(double) * (size_t)nq_pad);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&cscore, sizeof(float) * (size_t)nq_pad * n_chunks * TC_CAP);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&citem, sizeof(int32_t) * (size_t)nq_pad * n_chunks * TC_CAP);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ccnt, sizeof(int32_t) * (size_t)nq_pad * n_chunks);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctau, sizeof(float) * (size_t)nq_pad * n_chunks);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&fail_slots, sizeof(int32_t) * (size_t)nq);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&fail_users, sizeof(int32_t) * (size_t)nq);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&fail_count, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(fail_count, 0, sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(Aq, 0, sizeof(__nv_bfloat16) * (size_t)nq_pad * Kp, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ccnt, 0, sizeof(int32_t) * (size_t)nq_pad * n_chunks, st);
+    int nfail = 0;
+    do {
+        if (e != cudaSuccess) break;
+        tc_build_users_kernel<<<lrk_ceil_div(nq, 8), 256, 0, st>>>(h->P64, biased, h->k, Kp, d_users, nq, Aq, pnorm);
+        h->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        CUtensorMap tmA, tmB;
+        if ((rc = tc_make_map(h, s, &tmA, Aq, Kp, nq_pad))) break;
+        if ((rc = tc_make_map(h, s, &tmB, s->Bq, Kp, h->I))) break;
+        TcParams p;
+        memset(&p, 0, sizeof p);
+        p.nq = nq; p.I = h->I; p.n_chunks = n_chunks; p.tiles_per_chunk = tiles_per_chunk; p.total_tiles = total_tiles;
+        p.num_kb = num_kb; p.stages = stages; p.exclude_train = exclude_train ? 1 : 0;
+        p.rowptr = h->d_rowptr; p.col = h->d_col; p.users = d_users;
+        p.cand_score = cscore; p.cand_item = citem; p.cand_cnt = ccnt; p.cand_tau = ctau;
+        if ((e = cudaFuncSetAttribute(topn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) break;
+        const int grid = std::min(h->sm_count, m_tiles * n_chunks);
+        topn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+        h->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        // ---- exact re-score + certificate
+        const double c_err = ldexp(1.0, -7) * (1.0 + ldexp(1.0, -6)) + (double)(Kp + 8) * ldexp(1.0, -22);
+        const size_t rs_smem_bytes = (size_t)TC_RS_WARPS * n_chunks * TC_CAP * (sizeof(double) + sizeof(int32_t));
+        if ((e = cudaFuncSetAttribute(topn_tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes)) != cudaSuccess) break;
+        topn_tc_rescore_kernel<<<lrk_ceil_div(nq, TC_RS_WARPS), TC_RS_WARPS * 32, rs_smem_bytes, st>>>(
+            h->P64, h->Q64, h->bu64, h->bi64, h->mu, biased, h->k, d_users, nq, n_chunks, topn, cscore, citem, ccnt, ctau, pnorm,
+            s->qnorm_max, s->bi_max, c_err, d_items, d_scores, d_counts, fail_slots, fail_users, fail_count);
+        h->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(&nfail, fail_count, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+        if (nfail > 0) {
+            // rows without a certificate: exact fp64 kernel (java.util.PriorityQueue replay)
+            if ((e = cudaMalloc((void**)&fi, sizeof(int32_t) * (size_t)nfail * topn)) != cudaSuccess) break;
+            if ((e = cudaMalloc((void**)&fs, sizeof(double) * (size_t)nfail * topn)) != cudaSuccess) break;
+            if ((e = cudaMalloc((void**)&fc, sizeof(int32_t) * (size_t)nfail)) != cudaSuccess) break;
+            if ((rc = topn_exact_launch(h, fail_users, nfail, topn, exclude_train, fi, fs, fc))) break;
+            tc_scatter_fallback_kernel<<<lrk_ceil_div((int64_t)nfail * topn, 256), 256, 0, st>>>(fail_slots, nfail, topn, fi, fs, fc,
+                                                                                              d_items, d_scores, d_counts);
+            h->launches++;
+            if ((e = cudaGetLastError()) != cudaSuccess) break;
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+        }
+    } while (0);
+    if (e == cudaSuccess && rc == LRK_OK) e = cudaStreamSynchronize(st);
+    cudaFree(Aq); cudaFree(pnorm); cudaFree(cscore); cudaFree(citem); cudaFree(ccnt); cudaFree(ctau);
+    cudaFree(fail_slots); cudaFree(fail_users); cudaFree(fail_count); cudaFree(fi); cudaFree(fs); cudaFree(fc);
+    if (rc) return rc;
+    LRK_CUDA(h, e);
+    h->topn_fast_users = nq - nfail;
+    h->topn_fallback_users = nfail;
+    return LRK_OK;
 }

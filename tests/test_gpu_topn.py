@@ -108,3 +108,70 @@ def test_topn_after_training_uses_current_factors(O, capi, c1):
         gP, gQ, gbu, gbi = h.get_factors()
     oi, os_, oc = O.recommend_rank(O.BIASEDMF, tr.U, tr.I, 20, gP, gQ, gbu, gbi, mu, tr, 10)
     assert np.array_equal(items, oi) and np.array_equal(scores.view(np.int64), os_.view(np.int64)) and np.array_equal(counts, oc)
+
+
+# ---- tensor-core candidate path (tcgen05 / TMA) must still deliver the reference's lists bit for bit ----
+@pytest.mark.parametrize("model,U,I,k,N,scale", [
+    (1, 700, 9000, 128, 10, 0.1),      # PMF, two K blocks
+    (2, 300, 5000, 64, 10, 0.1),       # BPR, one K block
+    (0, 513, 4097, 20, 10, 0.3),       # BiasedMF: item bias folded into two extra K columns (Kp = 64)
+    (0, 260, 3000, 128, 16, 0.1),      # BiasedMF k=128 -> Kp = 192 (three K blocks), N = 16
+    (1, 1000, 20000, 128, 1, 0.05),    # N = 1
+])
+def test_topn_tensor_core_path_bit_identical(O, capi, model, U, I, k, N, scale):
+    h, tr, P, Q, bu, bi = _setup(capi, O, model, U, I, k, seed=U + I + k, density=0.01, scale=scale, topn_path=2)
+    with h:
+        items, scores, counts = h.topn(N)
+        stats = h.topn_stats()
+        sub_users = np.random.default_rng(0).integers(0, U, 300).astype(np.int32)
+        sub = h.topn(N, users=sub_users)
+        noex = h.topn(N, exclude_train=False, nq=128)
+    oi, os_, oc = O.recommend_rank(_omodel(capi, O, model), U, I, k, P, Q, bu, bi, 3.53, tr, N)
+    assert np.array_equal(counts, oc) and np.array_equal(items, oi)
+    assert np.array_equal(scores.view(np.int64), os_.view(np.int64))
+    # random Gaussian factors: the certificate should hold for (almost) every user
+    assert stats["fast_users"] + stats["fallback_users"] == U and stats["fast_users"] >= 0.9 * U, stats
+    si, ss, sc = O.recommend_rank(_omodel(capi, O, model), U, I, k, P, Q, bu, bi, 3.53, tr, N, users=sub_users)
+    assert np.array_equal(sub[0], si) and np.array_equal(sub[1].view(np.int64), ss.view(np.int64)) and np.array_equal(sub[2], sc)
+    ni, ns, nc = O.recommend_rank(_omodel(capi, O, model), U, I, k, P, Q, bu, bi, 3.53, None, N, users=np.arange(128))
+    assert np.array_equal(noex[0], ni) and np.array_equal(noex[1].view(np.int64), ns.view(np.int64)) and np.array_equal(noex[2], nc)
+
+
+def test_topn_tensor_core_path_degenerate_rows_fall_back(O, capi):
+    """ties / zero rows / heavy train rows cannot be certified -> exact kernel re-does them, result still exact"""
+    U, I, k, N = 300, 4000, 16, 10
+    rng = np.random.default_rng(4)
+    P = rng.integers(-2, 3, (U, k)).astype(np.float64)
+    Q = rng.integers(-1, 2, (I, k)).astype(np.float64)
+    P[3] = 0.0; Q[::7] = 0.0
+    P[100:] = rng.normal(0, 0.1, (U - 100, k))
+    Q2 = Q.copy(); Q2[2000:] = rng.normal(0, 0.1, (I - 2000, k))
+    tr = rng_csr(O, U, I, 0.05, 8)
+    with capi.Handle(capi.MODEL_PMF, k, topn_path=2) as h:
+        h.set_train_csr(U, I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q2)
+        items, scores, counts = h.topn(N)
+        stats = h.topn_stats()
+    oi, os_, oc = O.recommend_rank(O.PMF, U, I, k, P, Q2, None, None, 0.0, tr, N)
+    assert np.array_equal(counts, oc) and np.array_equal(items, oi)
+    assert np.array_equal(scores.view(np.int64), os_.view(np.int64))
+    assert stats["fallback_users"] >= 1
+
+
+def test_topn_tensor_core_after_training(O, capi, c1):
+    """learned (non-Gaussian) factors: ml-100k BPR-style ranking through the tensor-core path"""
+    tr = c1["train"]
+    O.lib().lro_rng_set_state(*c1["rng_state"])
+    P, Q, bu, bi = O.mf_setup(tr.U, tr.I, 64, True)
+    mu = c1["pins"]["global_mean"]
+    with capi.Handle(capi.MODEL_BIASEDMF, 64, topn_path=2) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q, bu, bi, mu)
+        for it in range(30):
+            h.sgd_epoch(0.01, 0.01, 0.01, 0.01, it + 1)
+        items, scores, counts = h.topn(10)
+        stats = h.topn_stats()
+        gP, gQ, gbu, gbi = h.get_factors()
+    oi, os_, oc = O.recommend_rank(O.BIASEDMF, tr.U, tr.I, 64, gP, gQ, gbu, gbi, mu, tr, 10)
+    assert np.array_equal(items, oi) and np.array_equal(scores.view(np.int64), os_.view(np.int64)) and np.array_equal(counts, oc)
+    print("ml-100k learned factors:", stats)
