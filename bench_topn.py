@@ -37,22 +37,10 @@ def main():
     P = rng.normal(0, 0.1, (U, k)).astype(np.float32).astype(np.float64)
     Q = rng.normal(0, 0.1, (I, k)).astype(np.float32).astype(np.float64)
     tpu = min(args.train_per_user, I // 2)
-    cols = np.sort(rng.integers(0, I, (U, tpu)), axis=1).astype(np.int32)
-    # make columns strictly ascending per row (duplicates bumped)
-    cols = np.maximum.accumulate(cols + np.arange(tpu, dtype=np.int32)[None, :] * 0, axis=1)
-    dup = np.concatenate([np.zeros((U, 1), bool), cols[:, 1:] <= cols[:, :-1]], axis=1)
-    while dup.any():
-        cols = cols + dup.astype(np.int32)
-        cols = np.minimum(cols, I - 1)
-        cols.sort(axis=1)
-        dup = np.concatenate([np.zeros((U, 1), bool), cols[:, 1:] == cols[:, :-1]], axis=1)
-        if dup.any():
-            keep = ~dup
-            # fall back: drop duplicates by regenerating those rows
-            bad = np.nonzero(dup.any(axis=1))[0]
-            for b in bad:
-                cols[b] = np.sort(rng.choice(I, tpu, replace=False))
-            dup = np.concatenate([np.zeros((U, 1), bool), cols[:, 1:] == cols[:, :-1]], axis=1)
+    # train mask: one random item out of each of tpu equal strata of the catalogue -> distinct, ascending
+    edges = np.linspace(0, I, tpu + 1).astype(np.int64)
+    width = np.diff(edges)
+    cols = (edges[:-1][None, :] + (rng.random((U, tpu)) * width[None, :]).astype(np.int64)).astype(np.int32)
     rowptr = (np.arange(U + 1, dtype=np.int64) * tpu)
     col = np.ascontiguousarray(cols.reshape(-1))
     val = np.ones(col.shape[0], np.float64)

@@ -33,8 +33,9 @@
 #define TC_UT 2                // user sub-tiles per CTA
 #define TC_TILE_N 128          // items per MMA tile
 #define TC_KB 64               // bf16 elements per 128-byte swizzle row
-#define TC_CAP 96              // candidate slots per (row, chunk)
-#define TC_KEEP 32             // K': entries kept by a compaction
+#define TC_KEEP 32             // K': candidates kept per (row, chunk) -- a min-heap in shared memory
+#define TC_CAP TC_KEEP         // candidate slots per (row, chunk) in global memory
+#define TC_ROWS (TC_TILE_M * TC_UT)   // user rows per CTA
 #define TC_THREADS 320
 #define TC_MAX_CHUNKS 16
 
@@ -45,6 +46,8 @@ struct TcState {
     double qnorm_max = 0.0, bi_max = 0.0;
     unsigned long long* d_stats = nullptr;   // [0] max ||q||^2 bits, [1] max |bi| bits
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    void* work = nullptr;                    // per-call scratch (user operand, candidate lists, ...), grown on demand
+    size_t work_bytes = 0;
 };
 
 static inline TcState* tc_state(lrk_handle_s* h) {
@@ -54,7 +57,7 @@ static inline TcState* tc_state(lrk_handle_s* h) {
 static inline void topn_tc_release(lrk_handle_s* h) {
     TcState* s = (TcState*)h->tc;
     if (!s) return;
-    cudaFree(s->Bq); cudaFree(s->d_stats);
+    cudaFree(s->Bq); cudaFree(s->d_stats); cudaFree(s->work);
     delete s;
     h->tc = nullptr;
 }
@@ -66,7 +69,7 @@ static inline int tc_kp(lrk_handle_s* h) {
     return ((kaug + TC_KB - 1) / TC_KB) * TC_KB;
 }
 static inline bool topn_tc_profitable(lrk_handle_s* h, int32_t nq, int topn) {
-    return topn <= 16 && tc_kp(h) <= 192 && h->I >= 8192 && nq >= 512;
+    return topn <= 16 && tc_kp(h) <= 128 && h->I >= 8192 && nq >= 512;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -156,21 +159,6 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=128, M=128
 #define TC_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE_N >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24))
 
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-}
-
 struct TcParams {
     int32_t nq, I;
     int n_chunks, tiles_per_chunk, total_tiles, num_kb, stages;
@@ -184,50 +172,59 @@ struct TcParams {
     float* cand_tau;
 };
 
-// warp-cooperative compaction of the candidate list of the row owned by lane `src`:
-// keeps the entries strictly above the TC_KEEP-th largest value, which becomes the row's new tau
-__device__ __forceinline__ void tc_compact(float* cs, int32_t* ci, int cnt, int lane, int& new_cnt, float& new_tau) {
-    float v[3]; int32_t it[3]; int rank[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const int e = lane + 32 * j;
-        v[j] = e < cnt ? __ldcg(cs + e) : -INFINITY;
-        it[j] = e < cnt ? __ldcg(ci + e) : -1;
-        rank[j] = 0;
+// Rare path of the epilogue: score x of `item` beat the row's threshold.  Masks train items
+// (MatrixRecommender.java:170-174: monotone lower_bound in the sorted CSR row), then offers x to the row's
+// min-heap of TC_KEEP entries in shared memory (slot stride TC_ROWS).  Returns the new threshold in the low
+// word, the advanced train pointer in bits 32..62 and "inserted" in bit 63.
+__device__ __noinline__ unsigned long long tc_hit(float* hv, int32_t* hi, int size, float tau, float x, int32_t item,
+                                                  const int32_t* __restrict__ col_row, int tp, int tlen) {
+    if (tlen > 0) {
+        int lo = tp, hi_ = tlen;
+        while (lo < hi_) { const int mm = (lo + hi_) >> 1; if (__ldg(col_row + mm) < item) lo = mm + 1; else hi_ = mm; }
+        tp = lo;
+        if (lo < tlen && __ldg(col_row + lo) == item)
+            return ((unsigned long long)(uint32_t)tp << 32) | (unsigned long long)__float_as_uint(tau);
     }
-#pragma unroll
-    for (int oj = 0; oj < 3; ++oj) {
-        for (int ol = 0; ol < 32; ++ol) {
-            const float o = __shfl_sync(0xffffffffu, v[oj], ol);
-            const int oe = ol + 32 * oj;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int e = lane + 32 * j;
-                rank[j] += (o > v[j] || (o == v[j] && oe < e)) ? 1 : 0;
-            }
+    if (size < TC_KEEP) {
+        int pos = size;
+        while (pos > 0) {
+            const int par = (pos - 1) >> 1;
+            const float pv = hv[par * TC_ROWS];
+            if (!(x < pv)) break;
+            hv[pos * TC_ROWS] = pv; hi[pos * TC_ROWS] = hi[par * TC_ROWS];
+            pos = par;
         }
-    }
-    // the entry of rank TC_KEEP-1 is the new threshold
-    float tau = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) if (rank[j] == TC_KEEP - 1) tau = v[j];
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, m));
-    __syncwarp();
-    int base = 0;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const bool keep = v[j] > tau;
-        const uint32_t m = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int pos = base + __popc(m & ((1u << lane) - 1u));
-            __stcg(cs + pos, v[j]); __stcg(ci + pos, it[j]);
+        hv[pos * TC_ROWS] = x; hi[pos * TC_ROWS] = item;
+        tau = (size + 1 == TC_KEEP) ? hv[0] : -INFINITY;
+    } else {
+        int pos = 0;
+        for (;;) {
+            int ch = 2 * pos + 1;
+            if (ch >= TC_KEEP) break;
+            float cv = hv[ch * TC_ROWS];
+            if (ch + 1 < TC_KEEP) { const float rv = hv[(ch + 1) * TC_ROWS]; if (rv < cv) { cv = rv; ++ch; } }
+            if (!(cv < x)) break;
+            hv[pos * TC_ROWS] = cv; hi[pos * TC_ROWS] = hi[ch * TC_ROWS];
+            pos = ch;
         }
-        base += __popc(m);
+        hv[pos * TC_ROWS] = x; hi[pos * TC_ROWS] = item;
+        tau = hv[0];
     }
-    __syncwarp();
-    new_cnt = base; new_tau = tau;
+    return (1ull << 63) | ((unsigned long long)(uint32_t)tp << 32) | (unsigned long long)__float_as_uint(tau);
 }
+
+// raw TMEM load of 32 accumulator columns of this thread's row (no wait)
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
@@ -237,7 +234,9 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tile_bytes = TC_TILE_M * TC_KB * 2;               // 16 KB: 128 rows x 128 B
     unsigned char* smA = base;                                       // [UT][num_kb] tiles
     unsigned char* smB = smA + (size_t)TC_UT * p.num_kb * tile_bytes; // [stages][num_kb] tiles
-    uint64_t* bars = (uint64_t*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);
+    float* heap_v = (float*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);   // [TC_KEEP][TC_ROWS]
+    int32_t* heap_i = (int32_t*)(heap_v + TC_KEEP * TC_ROWS);
+    uint64_t* bars = (uint64_t*)(heap_i + TC_KEEP * TC_ROWS);
     // barrier map: [0..S) b_full, [S..2S) b_empty, 2S a_full, 2S+1 a_empty, 2S+2.. tmem_full[2], tmem_empty[2]
     const int S = p.stages;
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 6);
@@ -335,71 +334,70 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int t0 = ch * p.tiles_per_chunk;
             const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
             const int32_t i1 = min(p.I, t1 * TC_TILE_N);
-            float* cs = p.cand_score + ((size_t)c * p.n_chunks + ch) * TC_CAP;
-            int32_t* ci = p.cand_item + ((size_t)c * p.n_chunks + ch) * TC_CAP;
-            int64_t tp = 0, tend = 0;
+            float* hv = heap_v + row_in_cta;
+            int32_t* hi = heap_i + row_in_cta;
+            const int32_t* col_row = p.col;
+            int tp = 0, tlen = 0;
             if (valid && p.exclude_train) {
                 const int32_t u = p.users ? p.users[c] : c;
-                tp = p.rowptr[u]; tend = p.rowptr[u + 1];
+                const int64_t rb = p.rowptr[u], re = p.rowptr[u + 1];
+                col_row = p.col + rb; tlen = (int)(re - rb);
                 const int32_t i0 = t0 * TC_TILE_N;
-                int64_t lo = tp, hi = tend;
-                while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (__ldg(p.col + m) < i0) lo = m + 1; else hi = m; }
+                int lo = 0, hi_ = tlen;
+                while (lo < hi_) { const int m = (lo + hi_) >> 1; if (__ldg(col_row + m) < i0) lo = m + 1; else hi_ = m; }
                 tp = lo;
             }
             float tau = -INFINITY;
             int cnt = 0;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_TILE_N);
+            // one 32-column slab: common case 31 FMNMX + 1 compare; rare case 32 compares + tc_hit per survivor
+#define TC_PROCESS(R, CB)                                                                                          \
+            do {                                                                                                   \
+                float m_ = __uint_as_float(R[0]);                                                                  \
+                _Pragma("unroll") for (int j = 1; j < 32; ++j) m_ = fmaxf(m_, __uint_as_float(R[j]));             \
+                if (valid && m_ > tau) {                                                                           \
+                    _Pragma("unroll") for (int j = 0; j < 32; ++j) {                                              \
+                        const float x_ = __uint_as_float(R[j]);                                                    \
+                        if (x_ > tau) {                                                                            \
+                            const int32_t item_ = n0 + (CB) * 32 + j;                                              \
+                            if (item_ < i1) {                                                                      \
+                                const unsigned long long r_ = tc_hit(hv, hi, cnt, tau, x_, item_, col_row, tp, tlen); \
+                                tau = __uint_as_float((uint32_t)r_);                                               \
+                                tp = (int)((r_ >> 32) & 0x7fffffffu);                                              \
+                                if ((r_ >> 63) && cnt < TC_KEEP) ++cnt;                                            \
+                            }                                                                                      \
+                        }                                                                                          \
+                    }                                                                                              \
+                }                                                                                                  \
+            } while (0)
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(BAR(2 * S + 2 + as), as_ph);
                 tc_fence_after();
                 const int32_t n0 = t * TC_TILE_N;
-#pragma unroll 1
-                for (int cb = 0; cb < TC_TILE_N / 32; ++cb) {
-                    float v[32];
-                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + a * TC_TILE_N + cb * 32), v);
-                    if (cb == TC_TILE_N / 32 - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR(2 * S + 4 + as));      // this warp has drained the stage
-                    }
-                    float m = v[0];
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-                    if (valid && m > tau) {
-                        // rare path: some of the 32 scores beat the row threshold
-                        float lv[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) lv[j] = v[j];
-                        for (int j = 0; j < 32; ++j) {
-                            const float x = lv[j];
-                            if (!(x > tau)) continue;
-                            const int32_t item = n0 + cb * 32 + j;
-                            if (item >= i1) continue;
-                            if (p.exclude_train) {             // MatrixRecommender.java:170-174
-                                int64_t lo = tp, hi = tend;
-                                while (lo < hi) { const int64_t mm = (lo + hi) >> 1; if (__ldg(p.col + mm) < item) lo = mm + 1; else hi = mm; }
-                                tp = lo;
-                                if (lo < tend && __ldg(p.col + lo) == item) continue;
-                            }
-                            __stcg(cs + cnt, x); __stcg(ci + cnt, item);
-                            ++cnt;
-                        }
-                    }
-                    // lists that could overflow during the next 32 columns are compacted now (warp-uniform)
-                    uint32_t need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);
-                    while (need) {
-                        const int src = __ffs(need) - 1;
-                        need &= need - 1;
-                        const int scnt = __shfl_sync(0xffffffffu, cnt, src);
-                        const int32_t sc = c - lane + src;
-                        int ncnt; float ntau;
-                        tc_compact(p.cand_score + ((size_t)sc * p.n_chunks + ch) * TC_CAP,
-                                   p.cand_item + ((size_t)sc * p.n_chunks + ch) * TC_CAP, scnt, lane, ncnt, ntau);
-                        if (lane == src) { cnt = ncnt; tau = ntau; }
-                    }
-                }
+                const uint32_t tcol = trow + (uint32_t)(as * 256);
+                uint32_t ra[32], rb_[32];
+                tc_ld32_nowait(tcol, ra);
+                tc_ld_wait();
+                tc_ld32_nowait(tcol + 32, rb_);
+                TC_PROCESS(ra, 0);
+                tc_ld_wait();
+                tc_ld32_nowait(tcol + 64, ra);
+                TC_PROCESS(rb_, 1);
+                tc_ld_wait();
+                tc_ld32_nowait(tcol + 96, rb_);
+                TC_PROCESS(ra, 2);
+                tc_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(2 * S + 4 + as));          // this warp has drained the stage
+                TC_PROCESS(rb_, 3);
                 if (++as == 2) { as = 0; as_ph ^= 1; }
             }
+#undef TC_PROCESS
             if (valid) {
+                float* cs = p.cand_score + ((size_t)c * p.n_chunks + ch) * TC_CAP;
+                int32_t* ci = p.cand_item + ((size_t)c * p.n_chunks + ch) * TC_CAP;
+                for (int e = 0; e < cnt; ++e) { cs[e] = hv[e * TC_ROWS]; ci[e] = hi[e * TC_ROWS]; }
                 p.cand_cnt[(size_t)c * p.n_chunks + ch] = cnt;
                 p.cand_tau[(size_t)c * p.n_chunks + ch] = tau;
             }
@@ -534,8 +532,8 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
     const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
     const int Kp = tc_kp(h);
     const int num_kb = Kp / TC_KB;
-    if (num_kb > 3 || topn > TC_KEEP / 2)
-        return lrk_fail(h, LRK_ERR_INVALID, "lrk_topn", "tensor-core path supports k (+2 for BiasedMF) <= 192 and topn <= 16", __FILE__, __LINE__);
+    if (num_kb > 2 || topn > TC_KEEP / 2)
+        return lrk_fail(h, LRK_ERR_INVALID, "lrk_topn", "tensor-core path supports k (+2 for BiasedMF) <= 128 and topn <= 16", __FILE__, __LINE__);
     // ---- item operand (cached until the factors change)
     if (!s->valid || s->Kp != Kp) {
         if (s->Bq) { cudaFree(s->Bq); s->Bq = nullptr; }
@@ -562,25 +560,36 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
     const int64_t nq_pad = (int64_t)m_tiles * TC_TILE_M * TC_UT;
     const size_t tile_bytes = (size_t)TC_TILE_M * TC_KB * 2;
     const size_t a_bytes = (size_t)TC_UT * num_kb * tile_bytes, b_stage = (size_t)num_kb * tile_bytes;
-    int stages = (int)((200 * 1024 - a_bytes) / b_stage);
+    const size_t heap_bytes = (size_t)TC_KEEP * TC_ROWS * 8;                   // per-row min-heaps
+    int stages = (int)((225 * 1024 - heap_bytes - a_bytes) / b_stage);
     stages = std::max(2, std::min(stages, 6));
-    const size_t smem = 1024 + a_bytes + (size_t)stages * b_stage + (2 * stages + 6) * 8 + 16;
+    const size_t smem = 1024 + a_bytes + (size_t)stages * b_stage + heap_bytes + (2 * stages + 6) * 8 + 16;
     // ---- query operand + scratch
-    __nv_bfloat16* Aq = nullptr; double* pnorm = nullptr; float *cscore = nullptr, *ctau = nullptr; int32_t *citem = nullptr, *ccnt = nullptr;
-    int32_t *fail_slots = nullptr, *fail_users = nullptr; int* fail_count = nullptr;
     int32_t *fi = nullptr, *fc = nullptr; double* fs = nullptr;
     int rc = LRK_OK;
-    cudaError_t e = cudaMalloc((void**)&Aq, sizeof(__nv_bfloat16) * (size_t)nq_pad * Kp);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&pnorm, sizeof(double) * (size_t)nq_pad);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&cscore, sizeof(float) * (size_t)nq_pad * n_chunks * TC_CAP);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&citem, sizeof(int32_t) * (size_t)nq_pad * n_chunks * TC_CAP);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ccnt, sizeof(int32_t) * (size_t)nq_pad * n_chunks);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ctau, sizeof(float) * (size_t)nq_pad * n_chunks);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&fail_slots, sizeof(int32_t) * (size_t)nq);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&fail_users, sizeof(int32_t) * (size_t)nq);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&fail_count, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemsetAsync(fail_count, 0, sizeof(int), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(Aq, 0, sizeof(__nv_bfloat16) * (size_t)nq_pad * Kp, st);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_aq = up(sizeof(__nv_bfloat16) * (size_t)nq_pad * Kp), b_pn = up(sizeof(double) * (size_t)nq_pad);
+    const size_t b_cs = up(sizeof(float) * (size_t)nq_pad * n_chunks * TC_CAP), b_ci = up(sizeof(int32_t) * (size_t)nq_pad * n_chunks * TC_CAP);
+    const size_t b_cc = up(sizeof(int32_t) * (size_t)nq_pad * n_chunks), b_ct = up(sizeof(float) * (size_t)nq_pad * n_chunks);
+    const size_t b_fl = up(sizeof(int32_t) * (size_t)nq);
+    const size_t need = b_aq + b_pn + b_cs + b_ci + b_cc + b_ct + 2 * b_fl + 256;
+    if (s->work_bytes < need) {
+        if (s->work) { cudaFree(s->work); s->work = nullptr; s->work_bytes = 0; }
+        LRK_CUDA(h, cudaMalloc(&s->work, need));
+        s->work_bytes = need;
+    }
+    char* w = (char*)s->work;
+    __nv_bfloat16* Aq = (__nv_bfloat16*)w; w += b_aq;
+    double* pnorm = (double*)w; w += b_pn;
+    float* cscore = (float*)w; w += b_cs;
+    int32_t* citem = (int32_t*)w; w += b_ci;
+    int32_t* ccnt = (int32_t*)w; w += b_cc;
+    float* ctau = (float*)w; w += b_ct;
+    int32_t* fail_slots = (int32_t*)w; w += b_fl;
+    int32_t* fail_users = (int32_t*)w; w += b_fl;
+    int* fail_count = (int*)w;
+    cudaError_t e = cudaMemsetAsync(fail_count, 0, sizeof(int), st);
+    if (e == cudaSuccess && nq_pad > nq) e = cudaMemsetAsync(Aq + (size_t)nq * Kp, 0, sizeof(__nv_bfloat16) * (size_t)(nq_pad - nq) * Kp, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(ccnt, 0, sizeof(int32_t) * (size_t)nq_pad * n_chunks, st);
     int nfail = 0;
     do {
@@ -627,8 +636,7 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
         }
     } while (0);
     if (e == cudaSuccess && rc == LRK_OK) e = cudaStreamSynchronize(st);
-    cudaFree(Aq); cudaFree(pnorm); cudaFree(cscore); cudaFree(citem); cudaFree(ccnt); cudaFree(ctau);
-    cudaFree(fail_slots); cudaFree(fail_users); cudaFree(fail_count); cudaFree(fi); cudaFree(fs); cudaFree(fc);
+    cudaFree(fi); cudaFree(fs); cudaFree(fc);
     if (rc) return rc;
     LRK_CUDA(h, e);
     h->topn_fast_users = nq - nfail;
