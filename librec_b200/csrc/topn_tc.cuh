@@ -34,6 +34,8 @@
 #define TC_TILE_N 128          // items per MMA tile
 #define TC_KB 64               // bf16 elements per 128-byte swizzle row
 #define TC_KEEP 32             // K': candidates kept per (row, chunk) -- a min-heap in shared memory
+#define TC_PEND 8              // pending hits parked per row before all lanes of the warp offer them together
+#define TC_SLOTS (TC_KEEP + TC_PEND)
 #define TC_CAP TC_KEEP         // candidate slots per (row, chunk) in global memory
 #define TC_ROWS (TC_TILE_M * TC_UT)   // user rows per CTA
 #define TC_THREADS 320
@@ -69,7 +71,7 @@ static inline int tc_kp(lrk_handle_s* h) {
     return ((kaug + TC_KB - 1) / TC_KB) * TC_KB;
 }
 static inline bool topn_tc_profitable(lrk_handle_s* h, int32_t nq, int topn) {
-    return topn <= 16 && tc_kp(h) <= 128 && h->I >= 8192 && nq >= 512;
+    return topn <= TC_KEEP / 2 && tc_kp(h) <= 128 && h->I >= 8192 && nq >= 512;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -172,18 +174,15 @@ struct TcParams {
     float* cand_tau;
 };
 
-// Rare path of the epilogue: score x of `item` beat the row's threshold.  Masks train items
-// (MatrixRecommender.java:170-174: monotone lower_bound in the sorted CSR row), then offers x to the row's
-// min-heap of TC_KEEP entries in shared memory (slot stride TC_ROWS).  Returns the new threshold in the low
-// word, the advanced train pointer in bits 32..62 and "inserted" in bit 63.
+// Offers (x, item) to a row's min-heap of TC_KEEP entries in shared memory (slot stride TC_ROWS) after
+// masking train items (MatrixRecommender.java:170-174: binary search in the sorted CSR row).
+// Returns the row's new threshold in the low word and "inserted" in bit 32.
 __device__ __noinline__ unsigned long long tc_hit(float* hv, int32_t* hi, int size, float tau, float x, int32_t item,
-                                                  const int32_t* __restrict__ col_row, int tp, int tlen) {
+                                                  const int32_t* __restrict__ col_row, int tlen) {
     if (tlen > 0) {
-        int lo = tp, hi_ = tlen;
+        int lo = 0, hi_ = tlen;
         while (lo < hi_) { const int mm = (lo + hi_) >> 1; if (__ldg(col_row + mm) < item) lo = mm + 1; else hi_ = mm; }
-        tp = lo;
-        if (lo < tlen && __ldg(col_row + lo) == item)
-            return ((unsigned long long)(uint32_t)tp << 32) | (unsigned long long)__float_as_uint(tau);
+        if (lo < tlen && __ldg(col_row + lo) == item) return (unsigned long long)__float_as_uint(tau);
     }
     if (size < TC_KEEP) {
         int pos = size;
@@ -210,7 +209,7 @@ __device__ __noinline__ unsigned long long tc_hit(float* hv, int32_t* hi, int si
         hv[pos * TC_ROWS] = x; hi[pos * TC_ROWS] = item;
         tau = hv[0];
     }
-    return (1ull << 63) | ((unsigned long long)(uint32_t)tp << 32) | (unsigned long long)__float_as_uint(tau);
+    return (1ull << 32) | (unsigned long long)__float_as_uint(tau);
 }
 
 // raw TMEM load of 32 accumulator columns of this thread's row (no wait)
@@ -234,9 +233,9 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tile_bytes = TC_TILE_M * TC_KB * 2;               // 16 KB: 128 rows x 128 B
     unsigned char* smA = base;                                       // [UT][num_kb] tiles
     unsigned char* smB = smA + (size_t)TC_UT * p.num_kb * tile_bytes; // [stages][num_kb] tiles
-    float* heap_v = (float*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);   // [TC_KEEP][TC_ROWS]
-    int32_t* heap_i = (int32_t*)(heap_v + TC_KEEP * TC_ROWS);
-    uint64_t* bars = (uint64_t*)(heap_i + TC_KEEP * TC_ROWS);
+    float* heap_v = (float*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);   // [TC_SLOTS][TC_ROWS]: heap slots, then pending slots
+    int32_t* heap_i = (int32_t*)(heap_v + TC_SLOTS * TC_ROWS);
+    uint64_t* bars = (uint64_t*)(heap_i + TC_SLOTS * TC_ROWS);
     // barrier map: [0..S) b_full, [S..2S) b_empty, 2S a_full, 2S+1 a_empty, 2S+2.. tmem_full[2], tmem_empty[2]
     const int S = p.stages;
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 6);
@@ -336,39 +335,60 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int32_t i1 = min(p.I, t1 * TC_TILE_N);
             float* hv = heap_v + row_in_cta;
             int32_t* hi = heap_i + row_in_cta;
+            float* pv_ = hv + TC_KEEP * TC_ROWS;          // this row's pending slots
+            int32_t* pi_ = hi + TC_KEEP * TC_ROWS;
             const int32_t* col_row = p.col;
-            int tp = 0, tlen = 0;
+            int tlen = 0;
             if (valid && p.exclude_train) {
                 const int32_t u = p.users ? p.users[c] : c;
                 const int64_t rb = p.rowptr[u], re = p.rowptr[u + 1];
                 col_row = p.col + rb; tlen = (int)(re - rb);
-                const int32_t i0 = t0 * TC_TILE_N;
-                int lo = 0, hi_ = tlen;
-                while (lo < hi_) { const int m = (lo + hi_) >> 1; if (__ldg(col_row + m) < i0) lo = m + 1; else hi_ = m; }
-                tp = lo;
             }
             float tau = -INFINITY;
-            int cnt = 0;
+            int cnt = 0, pend = 0;
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_TILE_N);
-            // one 32-column slab: common case 31 FMNMX + 1 compare; rare case 32 compares + tc_hit per survivor
-#define TC_PROCESS(R, CB)                                                                                          \
+            // A hit is parked in the row's pending slots (plain STS); when some row of the warp is about to run
+            // out of slots ALL 32 lanes offer their pending hits to their heaps in lock-step rounds, so the
+            // expensive part (train mask + heap sift) runs with many active lanes instead of one.
+#define TC_OFFER(X, ITEM)                                                                                          \
             do {                                                                                                   \
-                float m_ = __uint_as_float(R[0]);                                                                  \
-                _Pragma("unroll") for (int j = 1; j < 32; ++j) m_ = fmaxf(m_, __uint_as_float(R[j]));             \
-                if (valid && m_ > tau) {                                                                           \
-                    _Pragma("unroll") for (int j = 0; j < 32; ++j) {                                              \
-                        const float x_ = __uint_as_float(R[j]);                                                    \
-                        if (x_ > tau) {                                                                            \
-                            const int32_t item_ = n0 + (CB) * 32 + j;                                              \
-                            if (item_ < i1) {                                                                      \
-                                const unsigned long long r_ = tc_hit(hv, hi, cnt, tau, x_, item_, col_row, tp, tlen); \
-                                tau = __uint_as_float((uint32_t)r_);                                               \
-                                tp = (int)((r_ >> 32) & 0x7fffffffu);                                              \
-                                if ((r_ >> 63) && cnt < TC_KEEP) ++cnt;                                            \
-                            }                                                                                      \
-                        }                                                                                          \
+                const unsigned long long r_ = tc_hit(hv, hi, cnt, tau, (X), (ITEM), col_row, tlen);                \
+                tau = __uint_as_float((uint32_t)r_);                                                               \
+                if ((r_ >> 32) && cnt < TC_KEEP) ++cnt;                                                            \
+            } while (0)
+#define TC_FLUSH()                                                                                                 \
+            do {                                                                                                   \
+                for (int rr_ = 0; __any_sync(0xffffffffu, rr_ < pend); ++rr_) {                                    \
+                    if (rr_ < pend) {                                                                              \
+                        const float fx_ = pv_[rr_ * TC_ROWS];                                                      \
+                        const int32_t fi_ = pi_[rr_ * TC_ROWS];                                                    \
+                        if (fx_ > tau) TC_OFFER(fx_, fi_);                                                         \
                     }                                                                                              \
                 }                                                                                                  \
+                pend = 0;                                                                                          \
+            } while (0)
+#define TC_CHECK1(R, J, CB)                                                                                        \
+            do {                                                                                                   \
+                const float x_ = __uint_as_float(R[J]);                                                            \
+                const int32_t item_ = n0 + (CB) * 32 + (J);                                                        \
+                if (x_ > tau && item_ < i1) {                                                                      \
+                    if (pend < TC_PEND) { pv_[pend * TC_ROWS] = x_; pi_[pend * TC_ROWS] = item_; ++pend; }         \
+                    else TC_OFFER(x_, item_);                                                                      \
+                }                                                                                                  \
+            } while (0)
+#define TC_MAX8(R, O) fmaxf(fmaxf(fmaxf(__uint_as_float(R[O]), __uint_as_float(R[O + 1])), fmaxf(__uint_as_float(R[O + 2]), __uint_as_float(R[O + 3]))), \
+                            fmaxf(fmaxf(__uint_as_float(R[O + 4]), __uint_as_float(R[O + 5])), fmaxf(__uint_as_float(R[O + 6]), __uint_as_float(R[O + 7]))))
+#define TC_GROUP(R, O, CB)                                                                                         \
+            do {                                                                                                   \
+                if (TC_MAX8(R, O) > tau) {                                                                         \
+                    TC_CHECK1(R, O, CB); TC_CHECK1(R, O + 1, CB); TC_CHECK1(R, O + 2, CB); TC_CHECK1(R, O + 3, CB); \
+                    TC_CHECK1(R, O + 4, CB); TC_CHECK1(R, O + 5, CB); TC_CHECK1(R, O + 6, CB); TC_CHECK1(R, O + 7, CB); \
+                }                                                                                                  \
+            } while (0)
+#define TC_PROCESS(R, CB)                                                                                          \
+            do {                                                                                                   \
+                if (valid) { TC_GROUP(R, 0, CB); TC_GROUP(R, 8, CB); TC_GROUP(R, 16, CB); TC_GROUP(R, 24, CB); }   \
+                if (__any_sync(0xffffffffu, pend >= TC_PEND - 2)) TC_FLUSH();                                      \
             } while (0)
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(BAR(2 * S + 2 + as), as_ph);
@@ -393,7 +413,13 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 TC_PROCESS(rb_, 3);
                 if (++as == 2) { as = 0; as_ph ^= 1; }
             }
+            TC_FLUSH();
 #undef TC_PROCESS
+#undef TC_GROUP
+#undef TC_MAX8
+#undef TC_CHECK1
+#undef TC_FLUSH
+#undef TC_OFFER
             if (valid) {
                 float* cs = p.cand_score + ((size_t)c * p.n_chunks + ch) * TC_CAP;
                 int32_t* ci = p.cand_item + ((size_t)c * p.n_chunks + ch) * TC_CAP;
@@ -560,8 +586,8 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
     const int64_t nq_pad = (int64_t)m_tiles * TC_TILE_M * TC_UT;
     const size_t tile_bytes = (size_t)TC_TILE_M * TC_KB * 2;
     const size_t a_bytes = (size_t)TC_UT * num_kb * tile_bytes, b_stage = (size_t)num_kb * tile_bytes;
-    const size_t heap_bytes = (size_t)TC_KEEP * TC_ROWS * 8;                   // per-row min-heaps
-    int stages = (int)((225 * 1024 - heap_bytes - a_bytes) / b_stage);
+    const size_t heap_bytes = (size_t)TC_SLOTS * TC_ROWS * 8;                  // per-row min-heaps + pending slots
+    int stages = (int)((225 * 1024 + 512 - heap_bytes - a_bytes) / b_stage);
     stages = std::max(2, std::min(stages, 6));
     const size_t smem = 1024 + a_bytes + (size_t)stages * b_stage + heap_bytes + (2 * stages + 6) * 8 + 16;
     // ---- query operand + scratch

@@ -1,0 +1,412 @@
+// Host-side mirror of the reference's recommender plugin interface; see librec_host.hpp.
+#include "librec_host.hpp"
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <sstream>
+
+namespace librec {
+
+// ------------------------------------------------------------------------------------------------
+// Java number formatting (the per-iteration log line concatenates a double and a float:
+// recommender/AbstractRecommender.java:253-257)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static std::string java_fp_to_string(T v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "Infinity" : "-Infinity";
+    if (v == 0) return std::signbit(v) ? "-0.0" : "0.0";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);   // shortest round-trip digits
+    std::string s(buf, r.ptr);                       // d[.ddd]e[+-]XX
+    const size_t epos = s.find('e');
+    std::string mant = s.substr(0, epos);
+    const int exp10 = std::stoi(s.substr(epos + 1));
+    bool neg = false;
+    if (mant[0] == '-') { neg = true; mant = mant.substr(1); }
+    std::string digits;
+    for (char c : mant) if (c != '.') digits.push_back(c);
+    std::string out;
+    const double a = std::fabs((double)v);
+    if (a >= 1e-3 && a < 1e7) {
+        if (exp10 >= 0) {
+            std::string ip = digits.substr(0, std::min((size_t)exp10 + 1, digits.size()));
+            while ((int)ip.size() < exp10 + 1) ip.push_back('0');
+            std::string fp = (int)digits.size() > exp10 + 1 ? digits.substr((size_t)exp10 + 1) : "0";
+            out = ip + "." + fp;
+        } else {
+            out = "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+        }
+    } else {
+        std::string fp = digits.size() > 1 ? digits.substr(1) : "0";
+        out = digits.substr(0, 1) + "." + fp + "E" + std::to_string(exp10);
+    }
+    return neg ? "-" + out : out;
+}
+std::string java_double_to_string(double v) { return java_fp_to_string<double>(v); }
+std::string java_float_to_string(float v) { return java_fp_to_string<float>(v); }
+
+// ------------------------------------------------------------------------------------------------
+// Configuration
+// ------------------------------------------------------------------------------------------------
+static std::string trim(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && (unsigned char)s[a] <= ' ') ++a;
+    while (b > a && (unsigned char)s[b - 1] <= ' ') --b;
+    return s.substr(a, b - a);
+}
+void Configuration::load_properties(const std::string& text) {
+    std::istringstream in(text);
+    std::string line;
+    while (std::getline(in, line)) {
+        std::string t = trim(line);
+        if (t.empty() || t[0] == '#' || t[0] == '!') continue;
+        size_t p = t.find_first_of("=:");
+        if (p == std::string::npos) { props_[t] = ""; continue; }
+        props_[trim(t.substr(0, p))] = trim(t.substr(p + 1));
+    }
+}
+static bool is_blank(const std::string& s) { return trim(s).empty(); }
+bool Configuration::has(const std::string& k) const { auto it = props_.find(k); return it != props_.end() && !is_blank(it->second); }
+std::string Configuration::get(const std::string& k, const std::string& def) const {
+    auto it = props_.find(k);
+    return it == props_.end() ? def : it->second;
+}
+int Configuration::getInt(const std::string& k, int def) const { return has(k) ? std::stoi(get(k)) : def; }
+long long Configuration::getLong(const std::string& k, long long def) const { return has(k) ? std::stoll(get(k)) : def; }
+float Configuration::getFloat(const std::string& k, float def) const { return has(k) ? std::strtof(get(k).c_str(), nullptr) : def; }
+double Configuration::getDouble(const std::string& k, double def) const { return has(k) ? std::strtod(get(k).c_str(), nullptr) : def; }
+bool Configuration::getBoolean(const std::string& k, bool def) const {
+    if (!has(k)) return def;
+    std::string v = trim(get(k));
+    std::transform(v.begin(), v.end(), v.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    return v == "true";                                 // Boolean.valueOf
+}
+
+// ------------------------------------------------------------------------------------------------
+// java.util.Random (JDK 8): LCG 0x5DEECE66D; nextInt(bound) rejection; nextDouble 26+27 bits;
+// nextGaussian = Marsaglia polar with StrictMath.log (fdlibm __ieee754_log) and a cached second value.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct JavaRandom {
+    uint64_t seed = 0;
+    bool have = false;
+    double next_gauss = 0.0;
+    void setSeed(long long s) { seed = ((uint64_t)s ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1); have = false; }
+    int32_t next(int bits) {
+        seed = (seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+        return (int32_t)(uint32_t)(seed >> (48 - bits));
+    }
+    int32_t nextInt(int32_t bound) {
+        int32_t r = next(31);
+        const int32_t m = bound - 1;
+        if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+        for (int32_t u = r;; u = next(31)) {
+            r = u % bound;
+            if ((int32_t)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) return r;
+        }
+    }
+    double nextDouble() {
+        const int64_t a = next(26), b = next(27);
+        return (double)((a << 27) + b) * 0x1.0p-53;
+    }
+    static double strict_log(double x);
+    double nextGaussian() {
+        if (have) { have = false; return next_gauss; }
+        double v1, v2, s;
+        do { v1 = 2 * nextDouble() - 1; v2 = 2 * nextDouble() - 1; s = v1 * v1 + v2 * v2; } while (s >= 1 || s == 0);
+        const double mul = std::sqrt(-2 * strict_log(s) / s);
+        next_gauss = v2 * mul; have = true;
+        return v1 * mul;
+    }
+};
+// fdlibm e_log.c (freely distributable, Sun Microsystems 1993) restated: what StrictMath.log executes
+double JavaRandom::strict_log(double x) {
+    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10, two54 = 1.80143985094819840000e+16,
+                        Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                        Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                        Lg7 = 1.479819860511658591e-01;
+    auto hi = [](double d) { uint64_t b; memcpy(&b, &d, 8); return (int32_t)(b >> 32); };
+    auto lo = [](double d) { uint64_t b; memcpy(&b, &d, 8); return (uint32_t)b; };
+    auto sethi = [](double d, int32_t h) { uint64_t b; memcpy(&b, &d, 8); b = (b & 0xffffffffULL) | ((uint64_t)(uint32_t)h << 32); memcpy(&d, &b, 8); return d; };
+    int32_t hx = hi(x), k = 0, i, j;
+    const uint32_t lx = lo(x);
+    if (hx < 0x00100000) {
+        if (((hx & 0x7fffffff) | lx) == 0) return -two54 / 0.0;
+        if (hx < 0) return (x - x) / 0.0;
+        k -= 54; x *= two54; hx = hi(x);
+    }
+    if (hx >= 0x7ff00000) return x + x;
+    k += (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    i = (hx + 0x95f64) & 0x100000;
+    x = sethi(x, hx | (i ^ 0x3ff00000));
+    k += (i >> 20);
+    const double f = x - 1.0;
+    double dk, R;
+    if ((0x000fffff & (2 + hx)) < 3) {
+        if (f == 0.0) { if (k == 0) return 0.0; dk = (double)k; return dk * ln2_hi + dk * ln2_lo; }
+        R = f * f * (0.5 - 0.33333333333333333 * f);
+        if (k == 0) return f - R;
+        dk = (double)k; return dk * ln2_hi - ((R - dk * ln2_lo) - f);
+    }
+    const double s = f / (2.0 + f);
+    dk = (double)k;
+    const double z = s * s;
+    i = hx - 0x6147a;
+    const double w = z * z;
+    j = 0x6b851 - hx;
+    const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    i |= j;
+    R = t2 + t1;
+    if (i > 0) {
+        const double hfsq = 0.5 * f * f;
+        if (k == 0) return f - (hfsq - s * (hfsq + R));
+        return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+    }
+    if (k == 0) return f - s * (f - R);
+    return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+}
+JavaRandom g_r;
+}  // namespace
+
+void Randoms::seed(long long s) { g_r.setSeed(s); }
+int Randoms::uniform(int range) { return 0 + g_r.nextInt(range - 0); }
+double Randoms::uniform() { return 0.0 + (1.0 - 0.0) * g_r.nextDouble(); }
+double Randoms::gaussian(double mu, double sigma) { return mu + sigma * g_r.nextGaussian(); }
+
+void DenseMatrix::init(double mean, double sigma) { for (double& v : values) v = Randoms::gaussian(mean, sigma); }
+void VectorBasedDenseVector::init(double mean, double sigma) { for (double& v : values) v = Randoms::gaussian(mean, sigma); }
+double SequentialAccessSparseMatrix::mean() const {
+    double m = 0.0;
+    for (double v : val) m += v;
+    return m / (double)val.size();
+}
+
+// ------------------------------------------------------------------------------------------------
+// AbstractRecommender / MatrixRecommender / MatrixFactorizationRecommender
+// ------------------------------------------------------------------------------------------------
+void AbstractRecommender::train(const Configuration& c, const SequentialAccessSparseMatrix& tr, const SequentialAccessSparseMatrix& te) {
+    conf = c; trainMatrix = &tr; testMatrix = &te;
+    setup();
+    info("Job Setup completed.");
+    trainModel();
+    info("Job Train completed.");
+    cleanup();
+}
+void AbstractRecommender::setup() {
+    isRanking = conf.getBoolean("rec.recommender.isranking");
+    if (isRanking) {
+        topN = conf.getInt("rec.recommender.ranking.topn", 10);
+        if (topN <= 0) throw std::out_of_range("rec.recommender.ranking.topn should be more than 0!");
+    }
+    earlyStop = conf.getBoolean("rec.recommender.earlystop", false);
+    verbose = conf.getBoolean("rec.recommender.verbose", true);
+}
+bool AbstractRecommender::isConverged(int iter) {
+    const float delta_loss = (float)(lastLoss - loss);
+    if (verbose)
+        info(simpleName() + " iter " + std::to_string(iter) + ": loss = " + java_double_to_string(loss) + ", delta_loss = " +
+             java_float_to_string(delta_loss));
+    if (std::isnan(loss) || std::isinf(loss))
+        throw LibrecException("Loss = NaN or Infinity: current settings does not fit the recommender! Change the settings and try again!");
+    return std::fabs(delta_loss) < 1e-5;
+}
+
+void MatrixRecommender::setup() {
+    AbstractRecommender::setup();
+    numUsers = trainMatrix->rowSize();
+    numItems = trainMatrix->columnSize();
+    numRates = trainMatrix->size();
+    std::set<double> rs(trainMatrix->val.begin(), trainMatrix->val.end());
+    ratingScale.assign(rs.begin(), rs.end());
+    if (ratingScale.empty()) throw LibrecException("empty train matrix");
+    maxRate = ratingScale.back(); minRate = ratingScale.front();
+    if (minRate == maxRate) minRate = 0;
+    globalMean = trainMatrix->mean();
+}
+double MatrixRecommender::predict(int u, int i, bool bound) {
+    double p = predict(u, i);
+    if (bound) { if (p > maxRate) p = maxRate; else if (p < minRate) p = minRate; }
+    return p;
+}
+
+void MatrixFactorizationRecommender::setup() {
+    MatrixRecommender::setup();
+    numIterations = conf.getInt("rec.iterator.maximum", 100);
+    learnRate = conf.getFloat("rec.iterator.learnrate", 0.01f);
+    maxLearnRate = conf.getFloat("rec.iterator.learnrate.maximum", 1000.0f);
+    regUser = conf.getFloat("rec.user.regularization", 0.01f);
+    regItem = conf.getFloat("rec.item.regularization", 0.01f);
+    numFactors = conf.getInt("rec.factor.number", 10);
+    isBoldDriver = conf.getBoolean("rec.learnrate.bolddriver", false);
+    decay = conf.getFloat("rec.learnrate.decay", 1.0f);
+    userFactors = DenseMatrix(numUsers, numFactors);
+    itemFactors = DenseMatrix(numItems, numFactors);
+    impUserFactors = DenseMatrix(numUsers, numFactors);     // the fork's two extra matrices: they consume RNG draws
+    impItemFactors = DenseMatrix(numItems, numFactors);
+    initMean = 0.0f; initStd = 0.001f;
+    userFactors.init(initMean, initStd);
+    itemFactors.init(initMean, initStd);
+    impUserFactors.init(initMean, initStd);
+    impItemFactors.init(initMean, initStd);
+}
+double MatrixFactorizationRecommender::predict(int u, int i) {
+    const double* p = userFactors.row(u); const double* q = itemFactors.row(i);
+    double r = 0.0;
+    for (int f = 0; f < numFactors; ++f) r += q[f] * p[f];             // DenseVector.java:104-111
+    return r;
+}
+void MatrixFactorizationRecommender::updateLRate(int iter) {
+    if (learnRate < 0.0) { lastLoss = loss; return; }
+    if (isBoldDriver && iter > 1) learnRate = std::fabs(lastLoss) > std::fabs(loss) ? learnRate * 1.05f : learnRate * 0.5f;
+    else if (decay > 0 && decay < 1) learnRate *= decay;
+    if (maxLearnRate > 0 && learnRate > maxLearnRate) learnRate = maxLearnRate;
+    lastLoss = loss;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the CUDA drop-ins
+// ------------------------------------------------------------------------------------------------
+MatrixFactorizationCudaRecommender::~MatrixFactorizationCudaRecommender() {
+    if (handle) lrk_destroy(handle);
+}
+void MatrixFactorizationCudaRecommender::check(int status) const {
+    if (status != LRK_OK) throw LibrecException(lrk_last_error(handle));
+}
+void MatrixFactorizationCudaRecommender::setup() {
+    MatrixFactorizationRecommender::setup();
+    biased = model() == LRK_MODEL_BIASEDMF;
+    lrk_config_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.device = conf.getInt("rec.cuda.device", 0);
+    cfg.model = model();
+    cfg.num_factors = numFactors;
+    cfg.update_mode = conf.get("rec.cuda.order", "shuffled") == "reference" ? LRK_UPDATE_REFERENCE_ORDER : LRK_UPDATE_ATOMIC;
+    cfg.seed = (uint64_t)conf.getLong("rec.cuda.seed", 1);
+    cfg.topn_path = conf.getInt("rec.cuda.topn.path", 0);
+    if (handle) { lrk_destroy(handle); handle = nullptr; }
+    if (lrk_create(&cfg, &handle) != LRK_OK) throw LibrecException(lrk_last_error(nullptr));
+    check(lrk_set_train_csr(handle, numUsers, numItems, trainMatrix->rowptr.data(), trainMatrix->col.data(), trainMatrix->val.data()));
+}
+void MatrixFactorizationCudaRecommender::trainModel() {
+    check(lrk_set_factors(handle, userFactors.values.data(), itemFactors.values.data(),
+                          biased ? userBiases.values.data() : nullptr, biased ? itemBiases.values.data() : nullptr, globalMean));
+    for (int iter = 1; iter <= numIterations; ++iter) {
+        const int st = lrk_sgd_epoch(handle, learnRate, regUser, regItem, regBias, iter, &loss);
+        if (st != LRK_OK && st != LRK_ERR_DIVERGED) check(st);      // a NaN/Inf loss is reported by isConverged, like the reference
+        if (isConverged(iter) && earlyStop) break;
+        updateLRate(iter);
+    }
+    check(lrk_get_factors(handle, userFactors.values.data(), itemFactors.values.data(),
+                          biased ? userBiases.values.data() : nullptr, biased ? itemBiases.values.data() : nullptr));
+}
+RecommendedList MatrixFactorizationCudaRecommender::recommendRank() {
+    std::vector<int> all((size_t)numUsers);
+    for (int u = 0; u < numUsers; ++u) all[(size_t)u] = u;
+    return recommendRank(all);
+}
+RecommendedList MatrixFactorizationCudaRecommender::recommendRank(const std::vector<int>& userIds) {
+    info("begin recommend");
+    const int n = (int)userIds.size();
+    std::vector<int32_t> items((size_t)n * topN), counts((size_t)n);
+    std::vector<double> scores((size_t)n * topN);
+    check(lrk_topn(handle, userIds.data(), n, topN, 1, items.data(), scores.data(), counts.data()));
+    RecommendedList list;
+    for (int c = 0; c < n; ++c) {
+        list.addList();
+        for (int t = 0; t < counts[(size_t)c]; ++t) list.add(c, items[(size_t)c * topN + t], scores[(size_t)c * topN + t]);
+    }
+    if (list.size() == 0)
+        throw std::out_of_range("No item is recommended, there is something error in the recommendation algorithm! Please check it!");
+    info("end recommend");
+    return list;
+}
+RecommendedList MatrixFactorizationCudaRecommender::recommendRating(const SequentialAccessSparseMatrix& pm) {
+    std::vector<double> pred((size_t)pm.size());
+    double rmse = 0, mae = 0;
+    check(lrk_eval_rating(handle, pm.numRows, pm.rowptr.data(), pm.col.data(), pm.val.data(), minRate, maxRate,
+                          pred.data(), &rmse, &mae));
+    RecommendedList list;
+    for (int u = 0; u < pm.numRows; ++u) {
+        list.addList();
+        for (int64_t e = pm.rowptr[(size_t)u]; e < pm.rowptr[(size_t)u + 1]; ++e) list.add(u, pm.col[(size_t)e], pred[(size_t)e]);
+    }
+    return list;
+}
+
+void BiasedMFCudaRecommender::setup() {
+    MatrixFactorizationCudaRecommender::setup();
+    regBias = conf.getDouble("rec.bias.regularization", 0.01);
+    userBiases = VectorBasedDenseVector(numUsers);
+    itemBiases = VectorBasedDenseVector(numItems);
+    userBiases.init(initMean, initStd);
+    itemBiases.init(initMean, initStd);
+}
+double BiasedMFCudaRecommender::predict(int u, int i) {
+    return MatrixFactorizationRecommender::predict(u, i) + userBiases.get(u) + itemBiases.get(i) + globalMean;
+}
+
+std::unique_ptr<MatrixFactorizationCudaRecommender> newRecommender(const std::string& name) {
+    std::string n = name;
+    std::transform(n.begin(), n.end(), n.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    if (n == "biasedmf" || n == "net.librec.recommender.cuda.biasedmfcudarecommender") return std::make_unique<BiasedMFCudaRecommender>();
+    if (n == "pmf" || n == "net.librec.recommender.cuda.pmfcudarecommender") return std::make_unique<PMFCudaRecommender>();
+    if (n == "bpr" || n == "net.librec.recommender.cuda.bprcudarecommender") return std::make_unique<BPRCudaRecommender>();
+    throw LibrecException("ClassNotFoundException: " + name);
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluators + job
+// ------------------------------------------------------------------------------------------------
+static void zip_eval(const SequentialAccessSparseMatrix& test, const RecommendedList& rec, double* se, double* ae, int64_t* n) {
+    *se = 0; *ae = 0; *n = 0;
+    for (int u = 0; u < test.numRows; ++u) {
+        const auto& lst = rec.lists[(size_t)u];
+        size_t t = 0;
+        for (int64_t e = test.rowptr[(size_t)u]; e < test.rowptr[(size_t)u + 1]; ++e, ++t) {
+            if (t >= lst.size()) throw std::out_of_range("index cardinality of recommendedList does not equal testMatrix index cardinality");
+            if (lst[t].key != test.col[(size_t)e]) throw std::out_of_range("index of recommendedList does not equal testMatrix index");
+            const double d = test.val[(size_t)e] - lst[t].value;
+            *se += d * d; *ae += std::fabs(d); ++*n;
+        }
+    }
+}
+double evaluateRMSE(const SequentialAccessSparseMatrix& test, const RecommendedList& rec) {
+    if (test.size() == 0) return 0.0;
+    double se, ae; int64_t n; zip_eval(test, rec, &se, &ae, &n);
+    return n > 0 ? std::sqrt(se / (double)n) : 0.0;
+}
+double evaluateMAE(const SequentialAccessSparseMatrix& test, const RecommendedList& rec) {
+    if (test.size() == 0) return 0.0;
+    double se, ae; int64_t n; zip_eval(test, rec, &se, &ae, &n);
+    return n > 0 ? ae / (double)n : 0.0;
+}
+
+RecommenderJob::RecommenderJob(const Configuration& c) : conf(c) {
+    if (conf.has("rec.random.seed")) Randoms::seed(conf.getLong("rec.random.seed", 1));      // RecommenderJob.java:74-77
+}
+void RecommenderJob::setData(const SequentialAccessSparseMatrix& tr, const SequentialAccessSparseMatrix& te) { train = tr; test = te; }
+void RecommenderJob::runJob() {
+    recommender = newRecommender(conf.get("rec.recommender.class"));
+    recommender->train(conf, train, test);
+    const bool ranking = conf.getBoolean("rec.recommender.isranking");
+    if (conf.getBoolean("rec.eval.enable", true)) {                                          // :205-271
+        recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
+        if (!ranking) {
+            evaluatedMap["RMSE"] = evaluateRMSE(test, recommendedList);
+            evaluatedMap["MAE"] = evaluateMAE(test, recommendedList);
+        }
+    } else {
+        recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
+    }
+    log = recommender->log();
+    for (const auto& kv : evaluatedMap) log.push_back("Evaluator value:" + kv.first + " is " + java_double_to_string(kv.second));   // :257-260
+}
+
+}  // namespace librec

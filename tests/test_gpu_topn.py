@@ -115,7 +115,7 @@ def test_topn_after_training_uses_current_factors(O, capi, c1):
     (1, 700, 9000, 128, 10, 0.1),      # PMF, two K blocks
     (2, 300, 5000, 64, 10, 0.1),       # BPR, one K block
     (0, 513, 4097, 20, 10, 0.3),       # BiasedMF: item bias folded into two extra K columns (Kp = 64)
-    (0, 260, 3000, 100, 16, 0.1),      # BiasedMF k=100 -> Kp = 128 (two K blocks), N = 16
+    (0, 260, 3000, 100, 15, 0.1),      # BiasedMF k=100 -> Kp = 128 (two K blocks), N = 15
     (1, 1000, 20000, 128, 1, 0.05),    # N = 1
 ])
 def test_topn_tensor_core_path_bit_identical(O, capi, model, U, I, k, N, scale):

@@ -1,0 +1,58 @@
+"""CPU: the C++ host mirror's own logic (Configuration, Randoms, Java number formatting) against the oracle /
+JDK known answers.  No GPU: nothing here touches a compute entry point."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def H():
+    from librec_b200.host import binding
+    return binding.load()
+
+
+def test_host_randoms_match_jdk_and_oracle(H, O):
+    L = O.lib()
+    H.lrh_randoms_seed(42)
+    assert H.lrh_randoms_gaussian(0.0, 1.0) == 1.1419053154730547
+    for seed in (0, 1, 20251018):
+        H.lrh_randoms_seed(seed); L.lro_seed(seed)
+        for _ in range(50):
+            assert H.lrh_randoms_uniform_int(943) == L.lro_uniform_int(943)
+            assert H.lrh_randoms_uniform() == L.lro_uniform()
+            assert H.lrh_randoms_gaussian(0.0, float(np.float32(0.001))) == L.lro_gaussian(0.0, float(np.float32(0.001)))
+
+
+def test_java_number_formatting(H):
+    def fd(v):
+        b = C.create_string_buffer(64); H.lrh_format_double(v, b, 64); return b.value.decode()
+
+    def ff(v):
+        b = C.create_string_buffer(64); H.lrh_format_float(v, b, 64); return b.value.decode()
+    # Double.toString / Float.toString known answers
+    assert fd(46802.94873760634) == "46802.94873760634"
+    assert fd(1.0) == "1.0" and fd(100.0) == "100.0" and fd(0.001) == "0.001" and fd(-2.5) == "-2.5"
+    assert fd(1.0e7) == "1.0E7" and fd(12345678.9) == "1.23456789E7" and fd(1.0e-4) == "1.0E-4" and fd(0.00012345) == "1.2345E-4"
+    assert fd(float("nan")) == "NaN" and fd(float("inf")) == "Infinity" and fd(-0.0) == "-0.0"
+    assert ff(0.002) == "0.002" and ff(1234.5) == "1234.5" and ff(1.0e10) == "1.0E10"
+
+
+def test_configuration_getters(H):
+    props = b"# comment\nrec.iterator.learnrate=0.002\nrec.factor.number = 20\nrec.learnrate.bolddriver=TRUE\nrec.empty=\n"
+    assert H.lrh_conf_probe(props, b"rec.factor.number", 0, 10) == 20
+    assert H.lrh_conf_probe(props, b"rec.iterator.learnrate", 1, 0.01) == float(np.float32(0.002))      # Float.valueOf then widened
+    assert H.lrh_conf_probe(props, b"rec.iterator.learnrate", 2, 0.01) == 0.002
+    assert H.lrh_conf_probe(props, b"rec.learnrate.bolddriver", 3, 0) == 1.0                              # Boolean.valueOf ignores case
+    assert H.lrh_conf_probe(props, b"rec.missing", 0, 7) == 7 and H.lrh_conf_probe(props, b"rec.empty", 0, 9) == 9   # blank -> default
+
+
+def test_unknown_recommender_class_is_reported(H):
+    from librec_b200.host.binding import RecommenderJob, LibrecException
+    from oracle import oracle as O
+    tr = O.Csr(2, 2, [0, 1, 2], [0, 1], [1.0, 2.0])
+    job = RecommenderJob({"rec.recommender.class": "svdpp", "rec.random.seed": "1"})
+    job.set_data(2, 2, tr, tr)
+    with pytest.raises(LibrecException) as e:
+        job.run_job()
+    assert "ClassNotFoundException" in str(e.value)
