@@ -419,7 +419,10 @@ int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int
         cudaEventRecord(h->ev0, st);
         const bool want_tc = h->cfg.topn_path == 2 || (h->cfg.topn_path == 0 && topn_tc_profitable(h, nq, topn));
         if (want_tc) rc = topn_tc_run(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts);
-        else { rc = topn_exact_launch(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts); h->topn_fallback_users = nq; }
+        else if (d_users && h->cfg.topn_path != 1 && nq <= 4 * h->sm_count && h->I >= 32768) {
+            rc = topn_exact_parallel_launch(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts);
+            h->topn_fallback_users = nq;
+        } else { rc = topn_exact_launch(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts); h->topn_fallback_users = nq; }
         cudaEventRecord(h->ev1, st);
     }
     if (rc == LRK_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_items, d_items, sizeof(int32_t) * (size_t)nq * topn, cudaMemcpyDeviceToHost, st);

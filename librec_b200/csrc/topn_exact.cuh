@@ -269,3 +269,196 @@ static int topn_exact_launch(lrk_handle_s* h, const int32_t* d_users, int32_t nq
     return LRK_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Item-parallel exact top-N for FEW users over a LARGE catalogue (the fallback of the tensor-core
+// path and small query batches).  The Java heap replay above is sequential per user; but when the
+// best N+1 exact scores of a user are pairwise different under Double.compareTo, the reference's
+// result is simply those N items in descending order (ties are the only place where heap order
+// matters).  So: (1) score item parts in parallel in fp64 with the reference's summation order and
+// keep each part's best T=N+1, (2) merge per user and test for ties; users with a tie among the
+// first N+1 (rare) are replayed by topn_exact_kernel.
+// ---------------------------------------------------------------------------------------------
+#define TOPN_PAR_THREADS 256
+__global__ void __launch_bounds__(TOPN_PAR_THREADS) topn_exact_parts_kernel(
+    const double* __restrict__ P, const double* __restrict__ Q, const double* __restrict__ bu, const double* __restrict__ bi,
+    double mu, int biased, int k, int32_t I, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+    int exclude_train, const int32_t* __restrict__ users, int n_parts, int32_t part_items, int T,
+    int32_t* __restrict__ part_item_out, double* __restrict__ part_score_out, int32_t* __restrict__ part_cnt_out) {
+    extern __shared__ __align__(16) unsigned char par_smem[];
+    double* ps = reinterpret_cast<double*>(par_smem);                         // [k] user row
+    double* lv = ps + k;                                                      // [T][256] per-thread sorted lists (slot-major)
+    int32_t* li = reinterpret_cast<int32_t*>(lv + (size_t)T * TOPN_PAR_THREADS);
+    double* red_v = reinterpret_cast<double*>(li + (size_t)T * TOPN_PAR_THREADS);   // [8]
+    int32_t* red_i = reinterpret_cast<int32_t*>(red_v + 8);                   // [8] item
+    int32_t* red_t = red_i + 8;                                               // [8] owner thread
+    const int slot = blockIdx.x / n_parts, part = blockIdx.x - slot * n_parts;
+    const int32_t u = users[slot];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int f = tid; f < k; f += blockDim.x) ps[f] = P[(int64_t)u * k + f];
+    __syncthreads();
+    const int64_t tb = (exclude_train && rowptr) ? rowptr[u] : 0, te = (exclude_train && rowptr) ? rowptr[u + 1] : 0;
+    const double ub = biased ? bu[u] : 0.0;
+    const int32_t i0 = part * part_items, i1 = min(I, i0 + part_items);
+    int cnt = 0;
+    for (int32_t it = i0 + tid; it < i1; it += blockDim.x) {
+        bool skip = false;
+        if (te > tb) {
+            int64_t lo = tb, hi = te;
+            while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (__ldg(col + m) < it) lo = m + 1; else hi = m; }
+            skip = lo < te && __ldg(col + lo) == it;
+        }
+        if (skip) continue;
+        double s = dot_lr_f64(ps, Q + (int64_t)it * k, k);
+        if (biased) s = __dadd_rn(__dadd_rn(__dadd_rn(s, ub), bi[it]), mu);
+        if (s != s) continue;                                                  // NaN dropped (MatrixRecommender.java:186)
+        // sorted insertion (descending by Double.compareTo, earlier item first among equals)
+        if (cnt == T && jcompare(s, lv[(size_t)(T - 1) * TOPN_PAR_THREADS + tid]) <= 0) continue;
+        int pos = cnt < T ? cnt : T - 1;
+        while (pos > 0 && jcompare(lv[(size_t)(pos - 1) * TOPN_PAR_THREADS + tid], s) < 0) {
+            lv[(size_t)pos * TOPN_PAR_THREADS + tid] = lv[(size_t)(pos - 1) * TOPN_PAR_THREADS + tid];
+            li[(size_t)pos * TOPN_PAR_THREADS + tid] = li[(size_t)(pos - 1) * TOPN_PAR_THREADS + tid];
+            --pos;
+        }
+        lv[(size_t)pos * TOPN_PAR_THREADS + tid] = s; li[(size_t)pos * TOPN_PAR_THREADS + tid] = it;
+        if (cnt < T) ++cnt;
+    }
+    // merge the 256 sorted lists: T rounds of block-wide argmax over the list heads
+    int head = 0, out_n = 0;
+    const int64_t obase = ((int64_t)slot * n_parts + part) * T;
+    for (int r = 0; r < T; ++r) {
+        double bv = 0.0; int32_t bi_ = -1; int bt = -1;
+        if (head < cnt) { bv = lv[(size_t)head * TOPN_PAR_THREADS + tid]; bi_ = li[(size_t)head * TOPN_PAR_THREADS + tid]; bt = tid; }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, m);
+            const int32_t oi = __shfl_xor_sync(0xffffffffu, bi_, m);
+            const int ot = __shfl_xor_sync(0xffffffffu, bt, m);
+            if (oi >= 0 && (bi_ < 0 || jcompare(ov, bv) > 0 || (jcompare(ov, bv) == 0 && oi < bi_))) { bv = ov; bi_ = oi; bt = ot; }
+        }
+        if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi_; red_t[warp] = bt; }
+        __syncthreads();
+        bv = red_v[0]; bi_ = red_i[0]; bt = red_t[0];
+        for (int w = 1; w < TOPN_PAR_THREADS / 32; ++w) {
+            const double ov = red_v[w]; const int32_t oi = red_i[w];
+            if (oi >= 0 && (bi_ < 0 || jcompare(ov, bv) > 0 || (jcompare(ov, bv) == 0 && oi < bi_))) { bv = ov; bi_ = oi; bt = red_t[w]; }
+        }
+        __syncthreads();
+        if (bi_ < 0) break;
+        if (tid == bt) ++head;
+        if (tid == 0) { part_item_out[obase + r] = bi_; part_score_out[obase + r] = bv; }
+        ++out_n;
+    }
+    if (tid == 0) part_cnt_out[(int64_t)slot * n_parts + part] = out_n;
+}
+
+// one warp per user: merge the parts, tie test, write the list (or flag the user for the heap replay)
+__global__ void topn_exact_merge_kernel(int nq, int n_parts, int T, int topn, const int32_t* __restrict__ part_item,
+                                        const double* __restrict__ part_score, const int32_t* __restrict__ part_cnt,
+                                        int32_t* __restrict__ out_items, double* __restrict__ out_scores, int32_t* __restrict__ out_counts,
+                                        int32_t* __restrict__ tie_flags) {
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (slot >= nq) return;
+    int heads = 0;                       // lane p < n_parts walks part p (n_parts <= 32)
+    const int mycnt = lane < n_parts ? part_cnt[(int64_t)slot * n_parts + lane] : 0;
+    double prev = 0.0;
+    bool tie = false;
+    int n = 0;
+    for (int r = 0; r < topn + 1; ++r) {
+        double bv = 0.0; int32_t bi_ = -1; int bl = -1;
+        if (heads < mycnt) {
+            const int64_t o = ((int64_t)slot * n_parts + lane) * T + heads;
+            bv = part_score[o]; bi_ = part_item[o]; bl = lane;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, m);
+            const int32_t oi = __shfl_xor_sync(0xffffffffu, bi_, m);
+            const int ol = __shfl_xor_sync(0xffffffffu, bl, m);
+            if (oi >= 0 && (bi_ < 0 || jcompare(ov, bv) > 0 || (jcompare(ov, bv) == 0 && oi < bi_))) { bv = ov; bi_ = oi; bl = ol; }
+        }
+        if (bi_ < 0) break;
+        if (r > 0 && jcompare(bv, prev) == 0) { tie = true; break; }
+        if (r < topn) {
+            if (lane == 0) { out_items[(int64_t)slot * topn + r] = bi_; out_scores[(int64_t)slot * topn + r] = bv; }
+            ++n;
+        }
+        if (lane == bl) ++heads;
+        prev = bv;
+    }
+    if (lane == 0) {
+        for (int t = n; t < topn; ++t) { out_items[(int64_t)slot * topn + t] = -1; out_scores[(int64_t)slot * topn + t] = 0.0; }
+        out_counts[slot] = n;
+        tie_flags[slot] = tie ? 1 : 0;
+    }
+}
+
+__global__ void topn_collect_ties_kernel(const int32_t* __restrict__ tie_flags, const int32_t* __restrict__ users, int nq,
+                                         int32_t* __restrict__ tie_slots, int32_t* __restrict__ tie_users, int* __restrict__ tie_count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nq && tie_flags[t]) { const int pos = atomicAdd(tie_count, 1); tie_slots[pos] = t; tie_users[pos] = users[t]; }
+}
+__global__ void topn_scatter_kernel(const int32_t* __restrict__ slots, int n, int topn, const int32_t* __restrict__ fi,
+                                    const double* __restrict__ fs, const int32_t* __restrict__ fc,
+                                    int32_t* __restrict__ out_items, double* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * topn) return;
+    const int f = t / topn, r = t - f * topn;
+    const int32_t c = slots[f];
+    out_items[(int64_t)c * topn + r] = fi[t];
+    out_scores[(int64_t)c * topn + r] = fs[t];
+    if (r == 0) out_counts[c] = fc[f];
+}
+
+// d_users: device array of nq user ids (required).  Results to device buffers [nq x topn].
+static int topn_exact_parallel_launch(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int topn, int exclude_train,
+                                      int32_t* d_items, double* d_scores, int32_t* d_counts) {
+    cudaStream_t st = h->stream;
+    const int T = topn + 1;
+    int n_parts = lrk_ceil_div(2 * h->sm_count, nq);
+    n_parts = n_parts < 1 ? 1 : (n_parts > 32 ? 32 : n_parts);
+    int32_t part_items = lrk_ceil_div(h->I, n_parts);
+    part_items = ((part_items + TOPN_PAR_THREADS - 1) / TOPN_PAR_THREADS) * TOPN_PAR_THREADS;
+    n_parts = lrk_ceil_div(h->I, part_items);
+    int32_t *pi = nullptr, *pc = nullptr, *tie = nullptr, *tslots = nullptr, *tusers = nullptr, *fi = nullptr, *fc = nullptr;
+    double *psc = nullptr, *fs = nullptr; int* tcount = nullptr;
+    int ntie = 0, rc = LRK_OK;
+    cudaError_t e = cudaMalloc((void**)&pi, sizeof(int32_t) * (size_t)nq * n_parts * T);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&psc, sizeof(double) * (size_t)nq * n_parts * T);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pc, sizeof(int32_t) * (size_t)nq * n_parts);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&tie, sizeof(int32_t) * (size_t)nq * 3);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&tcount, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(tcount, 0, sizeof(int), st);
+    do {
+        if (e != cudaSuccess) break;
+        tslots = tie + nq; tusers = tie + 2 * (size_t)nq;
+        const size_t smem = sizeof(double) * ((size_t)h->k + (size_t)T * TOPN_PAR_THREADS + 8) + sizeof(int32_t) * ((size_t)T * TOPN_PAR_THREADS + 16);
+        if ((e = cudaFuncSetAttribute(topn_exact_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) break;
+        topn_exact_parts_kernel<<<nq * n_parts, TOPN_PAR_THREADS, smem, st>>>(
+            h->P64, h->Q64, h->bu64, h->bi64, h->mu, h->cfg.model == LRK_MODEL_BIASEDMF, h->k, h->I, h->d_rowptr, h->d_col,
+            exclude_train, d_users, n_parts, part_items, T, pi, psc, pc);
+        h->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        topn_exact_merge_kernel<<<lrk_ceil_div(nq, 4), 128, 0, st>>>(nq, n_parts, T, topn, pi, psc, pc, d_items, d_scores, d_counts, tie);
+        topn_collect_ties_kernel<<<lrk_ceil_div(nq, 256), 256, 0, st>>>(tie, d_users, nq, tslots, tusers, tcount);
+        h->launches += 2;
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(&ntie, tcount, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+        if (ntie > 0) {
+            if ((e = cudaMalloc((void**)&fi, sizeof(int32_t) * (size_t)ntie * topn)) != cudaSuccess) break;
+            if ((e = cudaMalloc((void**)&fs, sizeof(double) * (size_t)ntie * topn)) != cudaSuccess) break;
+            if ((e = cudaMalloc((void**)&fc, sizeof(int32_t) * (size_t)ntie)) != cudaSuccess) break;
+            if ((rc = topn_exact_launch(h, tusers, ntie, topn, exclude_train, fi, fs, fc))) break;
+            topn_scatter_kernel<<<lrk_ceil_div((int64_t)ntie * topn, 256), 256, 0, st>>>(tslots, ntie, topn, fi, fs, fc, d_items, d_scores, d_counts);
+            h->launches++;
+            if ((e = cudaGetLastError()) != cudaSuccess) break;
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+        }
+    } while (0);
+    cudaFree(pi); cudaFree(psc); cudaFree(pc); cudaFree(tie); cudaFree(tcount); cudaFree(fi); cudaFree(fs); cudaFree(fc);
+    if (rc) return rc;
+    LRK_CUDA(h, e);
+    return LRK_OK;
+}

@@ -34,7 +34,7 @@
 #define TC_TILE_N 128          // items per MMA tile
 #define TC_KB 64               // bf16 elements per 128-byte swizzle row
 #define TC_KEEP 32             // K': candidates kept per (row, chunk) -- a min-heap in shared memory
-#define TC_PEND 8              // pending hits parked per row before all lanes of the warp offer them together
+#define TC_PEND 16             // pending hits parked per row before all lanes of the warp offer them together
 #define TC_SLOTS (TC_KEEP + TC_PEND)
 #define TC_CAP TC_KEEP         // candidate slots per (row, chunk) in global memory
 #define TC_ROWS (TC_TILE_M * TC_UT)   // user rows per CTA
@@ -174,40 +174,41 @@ struct TcParams {
     float* cand_tau;
 };
 
-// Offers (x, item) to a row's min-heap of TC_KEEP entries in shared memory (slot stride TC_ROWS) after
-// masking train items (MatrixRecommender.java:170-174: binary search in the sorted CSR row).
-// Returns the row's new threshold in the low word and "inserted" in bit 32.
-__device__ __noinline__ unsigned long long tc_hit(float* hv, int32_t* hi, int size, float tau, float x, int32_t item,
+// Offers (x, item) to a row's min-heap of TC_KEEP packed {score bits, item} entries in shared memory
+// (slot stride TC_ROWS) after masking train items (MatrixRecommender.java:170-174: binary search in the
+// sorted CSR row).  Returns the row's new threshold in the low word and "inserted" in bit 32.
+__device__ __noinline__ unsigned long long tc_hit(uint2* ent, int size, float tau, float x, int32_t item,
                                                   const int32_t* __restrict__ col_row, int tlen) {
     if (tlen > 0) {
         int lo = 0, hi_ = tlen;
         while (lo < hi_) { const int mm = (lo + hi_) >> 1; if (__ldg(col_row + mm) < item) lo = mm + 1; else hi_ = mm; }
         if (lo < tlen && __ldg(col_row + lo) == item) return (unsigned long long)__float_as_uint(tau);
     }
+    const uint2 me = make_uint2(__float_as_uint(x), (uint32_t)item);
     if (size < TC_KEEP) {
         int pos = size;
         while (pos > 0) {
             const int par = (pos - 1) >> 1;
-            const float pv = hv[par * TC_ROWS];
-            if (!(x < pv)) break;
-            hv[pos * TC_ROWS] = pv; hi[pos * TC_ROWS] = hi[par * TC_ROWS];
+            const uint2 pe = ent[par * TC_ROWS];
+            if (!(x < __uint_as_float(pe.x))) break;
+            ent[pos * TC_ROWS] = pe;
             pos = par;
         }
-        hv[pos * TC_ROWS] = x; hi[pos * TC_ROWS] = item;
-        tau = (size + 1 == TC_KEEP) ? hv[0] : -INFINITY;
+        ent[pos * TC_ROWS] = me;
+        tau = (size + 1 == TC_KEEP) ? __uint_as_float(ent[0].x) : -INFINITY;
     } else {
         int pos = 0;
         for (;;) {
             int ch = 2 * pos + 1;
             if (ch >= TC_KEEP) break;
-            float cv = hv[ch * TC_ROWS];
-            if (ch + 1 < TC_KEEP) { const float rv = hv[(ch + 1) * TC_ROWS]; if (rv < cv) { cv = rv; ++ch; } }
-            if (!(cv < x)) break;
-            hv[pos * TC_ROWS] = cv; hi[pos * TC_ROWS] = hi[ch * TC_ROWS];
+            uint2 ce = ent[ch * TC_ROWS];
+            if (ch + 1 < TC_KEEP) { const uint2 re = ent[(ch + 1) * TC_ROWS]; if (__uint_as_float(re.x) < __uint_as_float(ce.x)) { ce = re; ++ch; } }
+            if (!(__uint_as_float(ce.x) < x)) break;
+            ent[pos * TC_ROWS] = ce;
             pos = ch;
         }
-        hv[pos * TC_ROWS] = x; hi[pos * TC_ROWS] = item;
-        tau = hv[0];
+        ent[pos * TC_ROWS] = me;
+        tau = __uint_as_float(ent[0].x);
     }
     return (1ull << 32) | (unsigned long long)__float_as_uint(tau);
 }
@@ -233,9 +234,8 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tile_bytes = TC_TILE_M * TC_KB * 2;               // 16 KB: 128 rows x 128 B
     unsigned char* smA = base;                                       // [UT][num_kb] tiles
     unsigned char* smB = smA + (size_t)TC_UT * p.num_kb * tile_bytes; // [stages][num_kb] tiles
-    float* heap_v = (float*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);   // [TC_SLOTS][TC_ROWS]: heap slots, then pending slots
-    int32_t* heap_i = (int32_t*)(heap_v + TC_SLOTS * TC_ROWS);
-    uint64_t* bars = (uint64_t*)(heap_i + TC_SLOTS * TC_ROWS);
+    uint2* heap_ent = (uint2*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);   // [TC_SLOTS][TC_ROWS] {score bits, item}: heap, then pending
+    uint64_t* bars = (uint64_t*)(heap_ent + TC_SLOTS * TC_ROWS);
     // barrier map: [0..S) b_full, [S..2S) b_empty, 2S a_full, 2S+1 a_empty, 2S+2.. tmem_full[2], tmem_empty[2]
     const int S = p.stages;
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 6);
@@ -333,10 +333,8 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int t0 = ch * p.tiles_per_chunk;
             const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
             const int32_t i1 = min(p.I, t1 * TC_TILE_N);
-            float* hv = heap_v + row_in_cta;
-            int32_t* hi = heap_i + row_in_cta;
-            float* pv_ = hv + TC_KEEP * TC_ROWS;          // this row's pending slots
-            int32_t* pi_ = hi + TC_KEEP * TC_ROWS;
+            uint2* ent = heap_ent + row_in_cta;                                  // this row's heap (slot stride TC_ROWS)
+            const uint32_t pend_base = smem_u32(ent + TC_KEEP * TC_ROWS);       // this row's pending slots (shared-space address)
             const int32_t* col_row = p.col;
             int tlen = 0;
             if (valid && p.exclude_train) {
@@ -347,12 +345,15 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float tau = -INFINITY;
             int cnt = 0, pend = 0;
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_TILE_N);
-            // A hit is parked in the row's pending slots (plain STS); when some row of the warp is about to run
-            // out of slots ALL 32 lanes offer their pending hits to their heaps in lock-step rounds, so the
-            // expensive part (train mask + heap sift) runs with many active lanes instead of one.
+            // Common path per 32-column slab: 31 FMNMX + 4 warp votes, no divergence.  A group of 8 columns is
+            // inspected (8 predicated appends into the row's pending slots) only if SOME lane of the warp has a
+            // score above its threshold there.  Pending hits are offered to the heaps by all 32 lanes in
+            // lock-step rounds (TC_FLUSH), so the expensive part (train mask + heap sift) runs with many active
+            // lanes.  The code is deliberately compact (rolled slab loop, one noinline tc_hit): the first
+            // versions of this epilogue were instruction-cache bound.
 #define TC_OFFER(X, ITEM)                                                                                          \
             do {                                                                                                   \
-                const unsigned long long r_ = tc_hit(hv, hi, cnt, tau, (X), (ITEM), col_row, tlen);                \
+                const unsigned long long r_ = tc_hit(ent, cnt, tau, (X), (ITEM), col_row, tlen);                   \
                 tau = __uint_as_float((uint32_t)r_);                                                               \
                 if ((r_ >> 32) && cnt < TC_KEEP) ++cnt;                                                            \
             } while (0)
@@ -360,35 +361,36 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             do {                                                                                                   \
                 for (int rr_ = 0; __any_sync(0xffffffffu, rr_ < pend); ++rr_) {                                    \
                     if (rr_ < pend) {                                                                              \
-                        const float fx_ = pv_[rr_ * TC_ROWS];                                                      \
-                        const int32_t fi_ = pi_[rr_ * TC_ROWS];                                                    \
-                        if (fx_ > tau) TC_OFFER(fx_, fi_);                                                         \
+                        const uint2 pe_ = ent[(TC_KEEP + rr_) * TC_ROWS];                                          \
+                        const float fx_ = __uint_as_float(pe_.x);                                                  \
+                        if (fx_ > tau) TC_OFFER(fx_, (int32_t)pe_.y);                                              \
                     }                                                                                              \
                 }                                                                                                  \
                 pend = 0;                                                                                          \
             } while (0)
-#define TC_CHECK1(R, J, CB)                                                                                        \
+#define TC_CHECK1(R, J)                                                                                            \
             do {                                                                                                   \
                 const float x_ = __uint_as_float(R[J]);                                                            \
-                const int32_t item_ = n0 + (CB) * 32 + (J);                                                        \
-                if (x_ > tau && item_ < i1) {                                                                      \
-                    if (pend < TC_PEND) { pv_[pend * TC_ROWS] = x_; pi_[pend * TC_ROWS] = item_; ++pend; }         \
-                    else TC_OFFER(x_, item_);                                                                      \
+                if (valid && x_ > tau && item0 + (J) < i1) {                                                       \
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pend_base + (uint32_t)pend * (TC_ROWS * 8)), \
+                                 "r"(R[J]), "r"(item0 + (J)) : "memory");                                          \
+                    ++pend;                                                                                        \
                 }                                                                                                  \
             } while (0)
 #define TC_MAX8(R, O) fmaxf(fmaxf(fmaxf(__uint_as_float(R[O]), __uint_as_float(R[O + 1])), fmaxf(__uint_as_float(R[O + 2]), __uint_as_float(R[O + 3]))), \
                             fmaxf(fmaxf(__uint_as_float(R[O + 4]), __uint_as_float(R[O + 5])), fmaxf(__uint_as_float(R[O + 6]), __uint_as_float(R[O + 7]))))
-#define TC_GROUP(R, O, CB)                                                                                         \
+#define TC_GROUP(R, O)                                                                                             \
             do {                                                                                                   \
-                if (TC_MAX8(R, O) > tau) {                                                                         \
-                    TC_CHECK1(R, O, CB); TC_CHECK1(R, O + 1, CB); TC_CHECK1(R, O + 2, CB); TC_CHECK1(R, O + 3, CB); \
-                    TC_CHECK1(R, O + 4, CB); TC_CHECK1(R, O + 5, CB); TC_CHECK1(R, O + 6, CB); TC_CHECK1(R, O + 7, CB); \
+                if (__any_sync(0xffffffffu, valid && TC_MAX8(R, O) > tau)) {                                       \
+                    if (__any_sync(0xffffffffu, pend > TC_PEND - 8)) TC_FLUSH();                                   \
+                    TC_CHECK1(R, O); TC_CHECK1(R, O + 1); TC_CHECK1(R, O + 2); TC_CHECK1(R, O + 3);                \
+                    TC_CHECK1(R, O + 4); TC_CHECK1(R, O + 5); TC_CHECK1(R, O + 6); TC_CHECK1(R, O + 7);            \
                 }                                                                                                  \
             } while (0)
 #define TC_PROCESS(R, CB)                                                                                          \
             do {                                                                                                   \
-                if (valid) { TC_GROUP(R, 0, CB); TC_GROUP(R, 8, CB); TC_GROUP(R, 16, CB); TC_GROUP(R, 24, CB); }   \
-                if (__any_sync(0xffffffffu, pend >= TC_PEND - 2)) TC_FLUSH();                                      \
+                const int32_t item0 = n0 + (CB) * 32;                                                              \
+                TC_GROUP(R, 0); TC_GROUP(R, 8); TC_GROUP(R, 16); TC_GROUP(R, 24);                                  \
             } while (0)
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(BAR(2 * S + 2 + as), as_ph);
@@ -398,19 +400,20 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t ra[32], rb_[32];
                 tc_ld32_nowait(tcol, ra);
                 tc_ld_wait();
-                tc_ld32_nowait(tcol + 32, rb_);
-                TC_PROCESS(ra, 0);
-                tc_ld_wait();
-                tc_ld32_nowait(tcol + 64, ra);
-                TC_PROCESS(rb_, 1);
-                tc_ld_wait();
-                tc_ld32_nowait(tcol + 96, rb_);
-                TC_PROCESS(ra, 2);
-                tc_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(2 * S + 4 + as));          // this warp has drained the stage
-                TC_PROCESS(rb_, 3);
+#pragma unroll 1
+                for (int pair = 0; pair < 2; ++pair) {
+                    tc_ld32_nowait(tcol + (uint32_t)(pair * 64 + 32), rb_);
+                    TC_PROCESS(ra, pair * 2);
+                    tc_ld_wait();
+                    if (pair == 0) tc_ld32_nowait(tcol + 64, ra);
+                    else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(2 * S + 4 + as));      // this warp has drained the stage
+                    }
+                    TC_PROCESS(rb_, pair * 2 + 1);
+                    if (pair == 0) tc_ld_wait();
+                }
                 if (++as == 2) { as = 0; as_ph ^= 1; }
             }
             TC_FLUSH();
@@ -423,7 +426,7 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (valid) {
                 float* cs = p.cand_score + ((size_t)c * p.n_chunks + ch) * TC_CAP;
                 int32_t* ci = p.cand_item + ((size_t)c * p.n_chunks + ch) * TC_CAP;
-                for (int e = 0; e < cnt; ++e) { cs[e] = hv[e * TC_ROWS]; ci[e] = hi[e * TC_ROWS]; }
+                for (int e = 0; e < cnt; ++e) { const uint2 he = ent[e * TC_ROWS]; cs[e] = __uint_as_float(he.x); ci[e] = (int32_t)he.y; }
                 p.cand_cnt[(size_t)c * p.n_chunks + ch] = cnt;
                 p.cand_tau[(size_t)c * p.n_chunks + ch] = tau;
             }
@@ -514,18 +517,6 @@ __global__ void __launch_bounds__(TC_RS_WARPS * 32) topn_tc_rescore_kernel(
             fail_slots[pos] = c; fail_users[pos] = u;
         }
     }
-}
-
-__global__ void tc_scatter_fallback_kernel(const int32_t* __restrict__ slots, int nfail, int topn, const int32_t* __restrict__ fi,
-                                           const double* __restrict__ fs, const int32_t* __restrict__ fc,
-                                           int32_t* __restrict__ out_items, double* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nfail * topn) return;
-    const int f = t / topn, r = t - f * topn;
-    const int32_t c = slots[f];
-    out_items[(int64_t)c * topn + r] = fi[t];
-    out_scores[(int64_t)c * topn + r] = fs[t];
-    if (r == 0) out_counts[c] = fc[f];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -649,13 +640,13 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
         if ((e = cudaMemcpyAsync(&nfail, fail_count, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
         if (nfail > 0) {
-            // rows without a certificate: exact fp64 kernel (java.util.PriorityQueue replay)
+            // rows without a certificate: item-parallel exact fp64 path (heap replay only for exact ties)
             if ((e = cudaMalloc((void**)&fi, sizeof(int32_t) * (size_t)nfail * topn)) != cudaSuccess) break;
             if ((e = cudaMalloc((void**)&fs, sizeof(double) * (size_t)nfail * topn)) != cudaSuccess) break;
             if ((e = cudaMalloc((void**)&fc, sizeof(int32_t) * (size_t)nfail)) != cudaSuccess) break;
-            if ((rc = topn_exact_launch(h, fail_users, nfail, topn, exclude_train, fi, fs, fc))) break;
-            tc_scatter_fallback_kernel<<<lrk_ceil_div((int64_t)nfail * topn, 256), 256, 0, st>>>(fail_slots, nfail, topn, fi, fs, fc,
-                                                                                              d_items, d_scores, d_counts);
+            if ((rc = topn_exact_parallel_launch(h, fail_users, nfail, topn, exclude_train, fi, fs, fc))) break;
+            topn_scatter_kernel<<<lrk_ceil_div((int64_t)nfail * topn, 256), 256, 0, st>>>(fail_slots, nfail, topn, fi, fs, fc,
+                                                                                       d_items, d_scores, d_counts);
             h->launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) break;
             if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;

@@ -57,7 +57,7 @@ def test_biasedmf_job_reference_order_matches_oracle_bit_for_bit(O, capi, c1):
     it1 = [l for l in log if " iter 1:" in l][0]
     m = re.match(r"BiasedMFCudaRecommender iter 1: loss = ([0-9.E-]+), delta_loss = (-?[0-9.E-]+)", it1)
     assert m and abs(float(m.group(1)) - pins["loss_1"]) < 1e-6
-    assert float(m.group(2)) == float(np.float32(0.0 - float(m.group(1))))          # (float)(lastLoss - loss)
+    assert np.float32(float(m.group(2))) == np.float32(0.0 - float(m.group(1)))    # (float)(lastLoss - loss), Float.toString
     assert sum(" iter " in l for l in log) == 100
     assert any(l.startswith("Evaluator value:RMSE is 0.93324") for l in log) and any(l.startswith("Evaluator value:MAE is ") for l in log)
     P, Q, bu, bi, mu = job.factors(20, True)
