@@ -57,6 +57,7 @@ SIGNATURES = {
                                   C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lrk_topn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, _f64p, _i32p]),
     "lrk_topn_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "lrk_topn_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "lrk_comm_unique_id": (C.c_int, [C.c_void_p]),
     "lrk_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }
@@ -208,7 +209,11 @@ class Handle:
     def topn_stats(self):
         a, b, ms = C.c_int64(), C.c_int64(), C.c_float()
         _check(load().lrk_topn_stats(self._h, C.byref(a), C.byref(b), C.byref(ms)), self._h)
-        return {"fast_users": a.value, "fallback_users": b.value, "ms": ms.value}
+        ph = (C.c_float * 5)()
+        _check(load().lrk_topn_phase_ms(self._h, ph), self._h)
+        return {"fast_users": a.value, "fallback_users": b.value, "ms": ms.value,
+                "phase_ms": {"operands": ph[0], "sweep": ph[1], "rescore": ph[2], "fallback": ph[3]},
+                "sweep_error_over_bound": ph[4]}
 
     # -- DSGD
     def comm_init(self, rank, world, unique_id):

@@ -47,6 +47,8 @@ struct lrk_handle_s {
     // top-N statistics
     int64_t topn_fast_users = 0, topn_fallback_users = 0;
     float topn_ms = 0.f;
+    float topn_phase_ms[4] = {0.f, 0.f, 0.f, 0.f};
+    float topn_err_ratio = 0.f;   // largest observed |fp16 sweep score - exact score| / certificate bound (must be < 1)
     // tensor-core top-N state (bf16 copies, norms); see topn_tc.cuh
     void* tc = nullptr;
 

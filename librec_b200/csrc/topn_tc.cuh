@@ -24,32 +24,34 @@
 #include "lrk_common.cuh"
 #include "topn_exact.cuh"
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cudaTypedefs.h>
 #include <cmath>
+#include <cstdlib>
 #include <algorithm>
 
 #define TC_TILE_M 128          // users per accumulator
 #define TC_UT 2                // user sub-tiles per CTA
 #define TC_TILE_N 128          // items per MMA tile
 #define TC_KB 64               // bf16 elements per 128-byte swizzle row
-#define TC_KEEP 32             // K': candidates kept per (row, chunk) -- a min-heap in shared memory
-#define TC_PEND 16             // pending hits parked per row before all lanes of the warp offer them together
-#define TC_SLOTS (TC_KEEP + TC_PEND)
-#define TC_CAP TC_KEEP         // candidate slots per (row, chunk) in global memory
+#define TC_KEEP 32             // K': candidates kept per (row, chunk) by a compaction
+#define TC_CAP 64              // candidate slots per (row, chunk) in global memory (append buffer, compacted to TC_KEEP)
 #define TC_ROWS (TC_TILE_M * TC_UT)   // user rows per CTA
 #define TC_THREADS 320
 #define TC_MAX_CHUNKS 16
 
 struct TcState {
-    __nv_bfloat16* Bq = nullptr;      // [I x Kp]
+    __half* Bq = nullptr;             // [I x Kp] item operand: fp16(2^eQ * q), BiasedMF: + {hi, lo} split of 2^eQ * b_i
     int Kp = 0;
     bool valid = false;
-    double qnorm_max = 0.0, bi_max = 0.0;
-    unsigned long long* d_stats = nullptr;   // [0] max ||q||^2 bits, [1] max |bi| bits
+    bool finite = true;               // false: some item factor / bias is NaN or Inf -> exact path only
+    int eQ = 0;                       // power-of-two scale of the item operand
+    double qnorm_max = 0.0, bi_max = 0.0, qabs_max = 0.0;
+    unsigned long long* d_stats = nullptr;   // [0] max ||q||^2 bits, [1] max |bi| bits, [2] max |q_f| bits, [3] max err/bound (float bits)
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     void* work = nullptr;                    // per-call scratch (user operand, candidate lists, ...), grown on demand
     size_t work_bytes = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase boundaries of the last call
 };
 
 static inline TcState* tc_state(lrk_handle_s* h) {
@@ -60,6 +62,7 @@ static inline void topn_tc_release(lrk_handle_s* h) {
     TcState* s = (TcState*)h->tc;
     if (!s) return;
     cudaFree(s->Bq); cudaFree(s->d_stats); cudaFree(s->work);
+    for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
     delete s;
     h->tc = nullptr;
 }
@@ -75,44 +78,72 @@ static inline bool topn_tc_profitable(lrk_handle_s* h, int32_t nq, int topn) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// operand builders
+// operand builders.  Operands are fp16 (11 significant bits; the products are exact in the fp32 accumulator)
+// after an exact power-of-two scaling that puts the largest magnitude of the item matrix / of each user
+// row into [2^9, 2^10): |fp16(s x) - s x| <= max(2^-11 |s x|, 2^-25).
 // ------------------------------------------------------------------------------------------------
-__global__ void tc_build_items_kernel(const double* __restrict__ Q, const double* __restrict__ bi, int biased, int k, int Kp,
-                                      int32_t I, __nv_bfloat16* __restrict__ out, unsigned long long* __restrict__ stats) {
+#define TC_EXP_TARGET 9
+__host__ __device__ inline int tc_scale_exp(double maxabs, int lo, int hi) {
+    if (!(maxabs > 0.0) || !(maxabs < 1e300)) return 0;
+    int e;
+    frexp(maxabs, &e);                       // maxabs = m * 2^e, m in [0.5, 1)
+    const int s = TC_EXP_TARGET + 1 - e;     // maxabs * 2^s in [2^9, 2^10)
+    return s < lo ? lo : (s > hi ? hi : s);
+}
+// user rows: 2^e must itself be an fp16 number (BiasedMF keeps it in the two bias columns)
+#define TC_USER_EXP_LO (-24)
+#define TC_USER_EXP_HI 14
+
+__global__ void tc_item_stats_kernel(const double* __restrict__ Q, const double* __restrict__ bi, int biased, int k, int32_t I,
+                                     unsigned long long* __restrict__ stats) {
     const int32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (i >= I) return;
-    double n2 = 0.0;
-    for (int f = lane; f < Kp; f += 32) {
-        float v = 0.f;
-        if (f < k) { const double q = Q[(int64_t)i * k + f]; n2 += q * q; v = (float)q; }
-        else if (biased && f == k) v = __bfloat162float(__float2bfloat16_rn((float)bi[i]));
-        else if (biased && f == k + 1) { const float b = (float)bi[i]; v = b - __bfloat162float(__float2bfloat16_rn(b)); }
-        out[(int64_t)i * Kp + f] = __float2bfloat16_rn(v);
-    }
+    double n2 = 0.0, ma = 0.0;
+    bool bad = false;
+    for (int f = lane; f < k; f += 32) { const double q = Q[(int64_t)i * k + f]; n2 += q * q; ma = fmax(ma, fabs(q)); bad |= !(fabs(q) <= 1.7e308); }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, m);
+    for (int m = 16; m >= 1; m >>= 1) { n2 += __shfl_xor_sync(0xffffffffu, n2, m); ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, m)); }
+    bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
+        if (bad) n2 = INFINITY;                                    // NaN / Inf anywhere -> the host disables the fp16 path
         atomicMax(stats, (unsigned long long)__double_as_longlong(n2));
-        if (biased) atomicMax(stats + 1, (unsigned long long)__double_as_longlong(fabs(bi[i])));
+        atomicMax(stats + 2, (unsigned long long)__double_as_longlong(ma));
+        if (biased) { const double b = fabs(bi[i]); atomicMax(stats + 1, (unsigned long long)__double_as_longlong(b <= 1.7e308 ? b : INFINITY)); }
     }
 }
+__global__ void tc_build_items_kernel(const double* __restrict__ Q, const double* __restrict__ bi, int biased, int k, int Kp,
+                                      int32_t I, int eQ, __half* __restrict__ out) {
+    const int32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= I) return;
+    for (int f = lane; f < Kp; f += 32) {
+        double v = 0.0;
+        if (f < k) v = ldexp(Q[(int64_t)i * k + f], eQ);
+        else if (biased && f == k) v = ldexp(bi[i], eQ);
+        else if (biased && f == k + 1) { const double b = ldexp(bi[i], eQ); v = b - (double)__half2float(__double2half(b)); }
+        out[(int64_t)i * Kp + f] = __double2half(v);
+    }
+}
+// pstat[c] = {||p_u||_2, max_f |p_uf|}
 __global__ void tc_build_users_kernel(const double* __restrict__ P, int biased, int k, int Kp, const int32_t* __restrict__ users,
-                                      int32_t nq, __nv_bfloat16* __restrict__ out, double* __restrict__ pnorm) {
+                                      int32_t nq, __half* __restrict__ out, double2* __restrict__ pstat) {
     const int32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= nq) return;
     const int32_t u = users ? users[c] : c;
-    double n2 = 0.0;
-    for (int f = lane; f < Kp; f += 32) {
-        float v = 0.f;
-        if (f < k) { const double p = P[(int64_t)u * k + f]; n2 += p * p; v = (float)p; }
-        else if (biased && (f == k || f == k + 1)) v = 1.f;
-        out[(int64_t)c * Kp + f] = __float2bfloat16_rn(v);
-    }
+    double n2 = 0.0, ma = 0.0;
+    for (int f = lane; f < k; f += 32) { const double p = P[(int64_t)u * k + f]; n2 += p * p; ma = fmax(ma, fabs(p)); }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, m);
-    if (lane == 0) pnorm[c] = sqrt(n2);
+    for (int m = 16; m >= 1; m >>= 1) { n2 += __shfl_xor_sync(0xffffffffu, n2, m); ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, m)); }
+    const int e = tc_scale_exp(ma, TC_USER_EXP_LO, TC_USER_EXP_HI);
+    for (int f = lane; f < Kp; f += 32) {
+        double v = 0.0;
+        if (f < k) v = ldexp(P[(int64_t)u * k + f], e);
+        else if (biased && (f == k || f == k + 1)) v = ldexp(1.0, e);
+        out[(int64_t)c * Kp + f] = __double2half(v);
+    }
+    if (lane == 0) pstat[c] = make_double2(sqrt(n2), ma);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -158,60 +189,114 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
     d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=128, M=128
-#define TC_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE_N >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24))
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (format fields 0), K-major both, N=128, M=128
+#define TC_IDESC ((1u << 4) | ((uint32_t)(TC_TILE_N >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24))
 
 struct TcParams {
     int32_t nq, I;
     int n_chunks, tiles_per_chunk, total_tiles, num_kb, stages;
     int exclude_train;
+    int debug;              // LRK_TC_DEBUG (profiling probes only): bit0 = drain TMEM but skip the selection, bit1 = do not even read TMEM
     const int64_t* __restrict__ rowptr;
     const int32_t* __restrict__ col;
     const int32_t* __restrict__ users;
-    float* cand_score;      // [nq_pad][n_chunks][TC_CAP]
-    int32_t* cand_item;
+    uint2* cand;            // [nq_pad][n_chunks][TC_CAP] {approximate score bits, item}
     int32_t* cand_cnt;      // [nq_pad][n_chunks]
     float* cand_tau;
 };
 
-// Offers (x, item) to a row's min-heap of TC_KEEP packed {score bits, item} entries in shared memory
-// (slot stride TC_ROWS) after masking train items (MatrixRecommender.java:170-174: binary search in the
-// sorted CSR row).  Returns the row's new threshold in the low word and "inserted" in bit 32.
-__device__ __noinline__ unsigned long long tc_hit(uint2* ent, int size, float tau, float x, int32_t item,
-                                                  const int32_t* __restrict__ col_row, int tlen) {
-    if (tlen > 0) {
-        int lo = 0, hi_ = tlen;
-        while (lo < hi_) { const int mm = (lo + hi_) >> 1; if (__ldg(col_row + mm) < item) lo = mm + 1; else hi_ = mm; }
-        if (lo < tlen && __ldg(col_row + lo) == item) return (unsigned long long)__float_as_uint(tau);
-    }
-    const uint2 me = make_uint2(__float_as_uint(x), (uint32_t)item);
-    if (size < TC_KEEP) {
-        int pos = size;
-        while (pos > 0) {
-            const int par = (pos - 1) >> 1;
-            const uint2 pe = ent[par * TC_ROWS];
-            if (!(x < __uint_as_float(pe.x))) break;
-            ent[pos * TC_ROWS] = pe;
-            pos = par;
-        }
-        ent[pos * TC_ROWS] = me;
-        tau = (size + 1 == TC_KEEP) ? __uint_as_float(ent[0].x) : -INFINITY;
-    } else {
-        int pos = 0;
-        for (;;) {
-            int ch = 2 * pos + 1;
-            if (ch >= TC_KEEP) break;
-            uint2 ce = ent[ch * TC_ROWS];
-            if (ch + 1 < TC_KEEP) { const uint2 re = ent[(ch + 1) * TC_ROWS]; if (__uint_as_float(re.x) < __uint_as_float(ce.x)) { ce = re; ++ch; } }
-            if (!(__uint_as_float(ce.x) < x)) break;
-            ent[pos * TC_ROWS] = ce;
-            pos = ch;
-        }
-        ent[pos * TC_ROWS] = me;
-        tau = __uint_as_float(ent[0].x);
-    }
-    return (1ull << 32) | (unsigned long long)__float_as_uint(tau);
+__device__ __forceinline__ float tc_max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));      // FMNMX3
+    return r;
 }
+template <typename T>
+__device__ __forceinline__ T* tc_shfl_ptr(T* ptr, int src) {
+    const unsigned long long v = (unsigned long long)ptr;
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return (T*)(((unsigned long long)hi << 32) | lo);
+}
+
+// Warp-cooperative compaction of the candidate lists of every row (lane) whose list holds more than `trig`
+// entries.  A list is {entries [0,kept): survivors of earlier compactions, train items already removed;
+// entries [kept,cnt): appended since, in ascending item order}.  One row at a time, all 32 lanes:
+//   1. load the <= TC_CAP entries (two per lane);
+//   2. drop train items among the new entries (MatrixRecommender.java:170-174): the sorted CSR row is walked
+//      32 items per load from a per-row cursor, membership by a 5-step binary search across lanes;
+//   3. rank by (score desc, slot asc), keep the best TC_KEEP, tau := score of rank TC_KEEP-1.
+// Everything dropped here has approximate score <= the new tau (or is a train item), which is the invariant the
+// exactness certificate of topn_tc_rescore_kernel rests on.
+__device__ __noinline__ int4 tc_compact(uint2* lp, int cnt, int kept, float tau, const int32_t* col_row, int tlen, int tp, int trig) {
+    const int lane = threadIdx.x & 31;
+    unsigned flagged = __ballot_sync(0xffffffffu, cnt > trig);
+    while (flagged) {
+        const int r = __ffs(flagged) - 1;
+        flagged &= flagged - 1;
+        uint2* L = tc_shfl_ptr(lp, r);
+        const int32_t* cr = tc_shfl_ptr(col_row, r);
+        const int n = __shfl_sync(0xffffffffu, cnt, r), kp = __shfl_sync(0xffffffffu, kept, r);
+        const int tl = __shfl_sync(0xffffffffu, tlen, r);
+        int cur = __shfl_sync(0xffffffffu, tp, r);
+        float new_tau = __shfl_sync(0xffffffffu, tau, r);
+        __syncwarp();
+        bool al0 = lane < n, al1 = lane + 32 < n;
+        uint2 e0 = make_uint2(0u, 0u), e1 = make_uint2(0u, 0u);
+        if (al0) e0 = __ldcg(L + lane);
+        if (al1) e1 = __ldcg(L + 32 + lane);
+        if (tl > cur && n > kp) {
+            // item range of the new entries (ascending by construction)
+            const int32_t lo_a = (int32_t)__shfl_sync(0xffffffffu, e0.y, kp & 31), lo_b = (int32_t)__shfl_sync(0xffffffffu, e1.y, kp & 31);
+            const int32_t hi_a = (int32_t)__shfl_sync(0xffffffffu, e0.y, (n - 1) & 31), hi_b = (int32_t)__shfl_sync(0xffffffffu, e1.y, (n - 1) & 31);
+            const int32_t i_lo = kp < 32 ? lo_a : lo_b, i_hi = (n - 1) < 32 ? hi_a : hi_b;
+            for (;;) {
+                const int32_t tv = (cur + lane < tl) ? __ldg(cr + cur + lane) : 0x7fffffff;
+                const int32_t last = __shfl_sync(0xffffffffu, tv, 31);
+                if (last < i_lo) { cur += 32; continue; }
+                int p0 = 0, p1 = 0;
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                    const int32_t v0 = __shfl_sync(0xffffffffu, tv, p0 + s - 1), v1 = __shfl_sync(0xffffffffu, tv, p1 + s - 1);
+                    if (v0 < (int32_t)e0.y) p0 += s;
+                    if (v1 < (int32_t)e1.y) p1 += s;
+                }
+                const int32_t m0 = __shfl_sync(0xffffffffu, tv, p0), m1 = __shfl_sync(0xffffffffu, tv, p1);
+                if (lane >= kp && m0 == (int32_t)e0.y) al0 = false;
+                if (lane + 32 >= kp && m1 == (int32_t)e1.y) al1 = false;
+                if (last >= i_hi) { cur += __popc(__ballot_sync(0xffffffffu, tv <= i_hi)); break; }
+                cur += 32;
+            }
+        }
+        const float s0 = al0 ? __uint_as_float(e0.x) : -INFINITY, s1 = al1 ? __uint_as_float(e1.x) : -INFINITY;
+        int rk0 = 0, rk1 = 0;
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+            const float a = __shfl_sync(0xffffffffu, s0, j), b = __shfl_sync(0xffffffffu, s1, j);
+            rk0 += (a > s0 || (a == s0 && j < lane)) ? 1 : 0;
+            rk0 += (b > s0) ? 1 : 0;
+            rk1 += (a >= s1) ? 1 : 0;
+            rk1 += (b > s1 || (b == s1 && j < lane)) ? 1 : 0;
+        }
+        const int alive = __popc(__ballot_sync(0xffffffffu, al0)) + __popc(__ballot_sync(0xffffffffu, al1));
+        const int keep_n = min(alive, TC_KEEP);
+        __syncwarp();
+        if (al0 && rk0 < keep_n) __stcg(L + rk0, e0);
+        if (al1 && rk1 < keep_n) __stcg(L + rk1, e1);
+        if (alive >= TC_KEEP) {
+            const unsigned b0 = __ballot_sync(0xffffffffu, al0 && rk0 == TC_KEEP - 1);
+            const unsigned b1 = __ballot_sync(0xffffffffu, al1 && rk1 == TC_KEEP - 1);
+            const float t0 = __shfl_sync(0xffffffffu, s0, b0 ? __ffs(b0) - 1 : 0), t1 = __shfl_sync(0xffffffffu, s1, b1 ? __ffs(b1) - 1 : 0);
+            new_tau = b0 ? t0 : t1;
+        }
+        if (lane == r) { cnt = keep_n; kept = keep_n; tau = new_tau; tp = cur; }
+        __syncwarp();
+    }
+    return make_int4(cnt, kept, __float_as_int(tau), tp);
+}
+#define TC_COMPACT(TRIG)                                                                  \
+    do {                                                                                  \
+        const int4 r_ = tc_compact(lp, cnt, kept, tau, col_row, tlen, tp, (TRIG));        \
+        cnt = r_.x; kept = r_.y; tau = __int_as_float(r_.z); tp = r_.w;                   \
+    } while (0)
 
 // raw TMEM load of 32 accumulator columns of this thread's row (no wait)
 __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t* r) {
@@ -226,6 +311,10 @@ __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// barrier map (S = B stages): [0,S) b_full, [S,2S) b_empty, 2S a_full, 2S+1 a_empty,
+// 2S+2+slot tmem_full, 2S+6+slot tmem_empty; accumulator slot = stage*2 + user sub-tile, 128 TMEM columns each
+#define TC_NBARS(S) (2 * (S) + 10)
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
@@ -234,19 +323,16 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tile_bytes = TC_TILE_M * TC_KB * 2;               // 16 KB: 128 rows x 128 B
     unsigned char* smA = base;                                       // [UT][num_kb] tiles
     unsigned char* smB = smA + (size_t)TC_UT * p.num_kb * tile_bytes; // [stages][num_kb] tiles
-    uint2* heap_ent = (uint2*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);   // [TC_SLOTS][TC_ROWS] {score bits, item}: heap, then pending
-    uint64_t* bars = (uint64_t*)(heap_ent + TC_SLOTS * TC_ROWS);
-    // barrier map: [0..S) b_full, [S..2S) b_empty, 2S a_full, 2S+1 a_empty, 2S+2.. tmem_full[2], tmem_empty[2]
+    uint64_t* bars = (uint64_t*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);
     const int S = p.stages;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 6);
+    uint32_t* tmem_slot = (uint32_t*)(bars + TC_NBARS(S));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto BAR = [&](int i) { return smem_u32(bars + i); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(S + s), 1); }
         mbar_init(BAR(2 * S), 1); mbar_init(BAR(2 * S + 1), 1);
-        mbar_init(BAR(2 * S + 2), 1); mbar_init(BAR(2 * S + 3), 1);
-        mbar_init(BAR(2 * S + 4), 8); mbar_init(BAR(2 * S + 5), 8);
+        for (int s = 0; s < 4; ++s) { mbar_init(BAR(2 * S + 2 + s), 1); mbar_init(BAR(2 * S + 6 + s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -258,7 +344,7 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int m_tiles = (p.nq + TC_TILE_M * TC_UT - 1) / (TC_TILE_M * TC_UT);
+    const int m_tiles = (p.nq + TC_ROWS - 1) / TC_ROWS;
     const int num_units = m_tiles * p.n_chunks;
 
     if (warp == 0) {
@@ -290,18 +376,18 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int st = 0; uint32_t ph = 0, a_ph = 0; int as = 0; uint32_t as_ph = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                const int mt = unit / p.n_chunks, ch = unit - mt * p.n_chunks;
-                (void)mt;
+                const int ch = unit % p.n_chunks;
                 mbar_wait(BAR(2 * S), a_ph);                               // A landed
                 a_ph ^= 1;
                 const int t0 = ch * p.tiles_per_chunk;
                 const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
                 for (int t = t0; t < t1; ++t) {
-                    mbar_wait(BAR(2 * S + 4 + as), as_ph ^ 1);             // accumulator stage drained
                     mbar_wait(BAR(st), ph);                                // B landed
-                    tc_fence_after();
                     for (int a = 0; a < TC_UT; ++a) {
-                        const uint32_t d = tmem_base + (uint32_t)(as * 256 + a * TC_TILE_N);
+                        const int slot = as * 2 + a;
+                        mbar_wait(BAR(2 * S + 6 + slot), as_ph ^ 1);       // accumulator slot drained by its 4 epilogue warps
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + (uint32_t)(slot * TC_TILE_N);
                         for (int kb = 0; kb < p.num_kb; ++kb) {
                             const uint32_t a_addr = smem_u32(smA + (size_t)(a * p.num_kb + kb) * tile_bytes);
                             const uint32_t b_addr = smem_u32(smB + (size_t)(st * p.num_kb + kb) * tile_bytes);
@@ -310,9 +396,9 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 tc_mma_f16(d, tc_smem_desc(a_addr + k4 * 32), tc_smem_desc(b_addr + k4 * 32), TC_IDESC,
                                            (kb | k4) != 0 ? 1u : 0u);
                         }
+                        tc_commit(BAR(2 * S + 2 + slot));                  // this sub-tile's scores are ready
                     }
                     tc_commit(BAR(S + st));                                // B slot reusable once these MMAs retire
-                    tc_commit(BAR(2 * S + 2 + as));                        // accumulators ready for the epilogue
                     if (++st == S) { st = 0; ph ^= 1; }
                     if (++as == 2) { as = 0; as_ph ^= 1; }
                 }
@@ -328,105 +414,98 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int as = 0; uint32_t as_ph = 0;
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
             const int mt = unit / p.n_chunks, ch = unit - mt * p.n_chunks;
-            const int32_t c = mt * (TC_TILE_M * TC_UT) + row_in_cta;
+            const int32_t c = mt * TC_ROWS + row_in_cta;
             const bool valid = c < p.nq;
             const int t0 = ch * p.tiles_per_chunk;
             const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
             const int32_t i1 = min(p.I, t1 * TC_TILE_N);
-            uint2* ent = heap_ent + row_in_cta;                                  // this row's heap (slot stride TC_ROWS)
-            const uint32_t pend_base = smem_u32(ent + TC_KEEP * TC_ROWS);       // this row's pending slots (shared-space address)
+            uint2* lp = p.cand + ((size_t)c * p.n_chunks + ch) * TC_CAP;          // this row's candidate list (global, L2-resident)
             const int32_t* col_row = p.col;
-            int tlen = 0;
+            int tlen = 0, tp = 0;
             if (valid && p.exclude_train) {
                 const int32_t u = p.users ? p.users[c] : c;
                 const int64_t rb = p.rowptr[u], re = p.rowptr[u + 1];
                 col_row = p.col + rb; tlen = (int)(re - rb);
+                const int32_t i0 = t0 * TC_TILE_N;
+                int lo = 0, hi_ = tlen;
+                while (lo < hi_) { const int m = (lo + hi_) >> 1; if (__ldg(col_row + m) < i0) lo = m + 1; else hi_ = m; }
+                tp = lo;
             }
-            float tau = -INFINITY;
-            int cnt = 0, pend = 0;
+            // Rows past nq carry tau = +inf so that nothing ever passes.  Common path per 32-column slab:
+            // 19 FMNMX3/FMNMX + one warp vote, no divergence.  A group of 8 columns is inspected (8 predicated
+            // appends to the row's list) only if SOME lane of the warp has a score above its threshold there.
+            float tau = valid ? -INFINITY : INFINITY;
+            int cnt = 0, kept = 0;
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_TILE_N);
-            // Common path per 32-column slab: 31 FMNMX + 4 warp votes, no divergence.  A group of 8 columns is
-            // inspected (8 predicated appends into the row's pending slots) only if SOME lane of the warp has a
-            // score above its threshold there.  Pending hits are offered to the heaps by all 32 lanes in
-            // lock-step rounds (TC_FLUSH), so the expensive part (train mask + heap sift) runs with many active
-            // lanes.  The code is deliberately compact (rolled slab loop, one noinline tc_hit): the first
-            // versions of this epilogue were instruction-cache bound.
-#define TC_OFFER(X, ITEM)                                                                                          \
+#define TC_APPEND(R, J)                                                                                            \
             do {                                                                                                   \
-                const unsigned long long r_ = tc_hit(ent, cnt, tau, (X), (ITEM), col_row, tlen);                   \
-                tau = __uint_as_float((uint32_t)r_);                                                               \
-                if ((r_ >> 32) && cnt < TC_KEEP) ++cnt;                                                            \
-            } while (0)
-#define TC_FLUSH()                                                                                                 \
-            do {                                                                                                   \
-                for (int rr_ = 0; __any_sync(0xffffffffu, rr_ < pend); ++rr_) {                                    \
-                    if (rr_ < pend) {                                                                              \
-                        const uint2 pe_ = ent[(TC_KEEP + rr_) * TC_ROWS];                                          \
-                        const float fx_ = __uint_as_float(pe_.x);                                                  \
-                        if (fx_ > tau) TC_OFFER(fx_, (int32_t)pe_.y);                                              \
-                    }                                                                                              \
-                }                                                                                                  \
-                pend = 0;                                                                                          \
-            } while (0)
-#define TC_CHECK1(R, J)                                                                                            \
-            do {                                                                                                   \
-                const float x_ = __uint_as_float(R[J]);                                                            \
-                if (valid && x_ > tau && item0 + (J) < i1) {                                                       \
-                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pend_base + (uint32_t)pend * (TC_ROWS * 8)), \
-                                 "r"(R[J]), "r"(item0 + (J)) : "memory");                                          \
-                    ++pend;                                                                                        \
+                if (__uint_as_float(R[J]) > tau && item0 + (J) < i1) {                                             \
+                    __stcg(lp + cnt, make_uint2(R[J], (uint32_t)(item0 + (J))));                                   \
+                    ++cnt;                                                                                         \
                 }                                                                                                  \
             } while (0)
-#define TC_MAX8(R, O) fmaxf(fmaxf(fmaxf(__uint_as_float(R[O]), __uint_as_float(R[O + 1])), fmaxf(__uint_as_float(R[O + 2]), __uint_as_float(R[O + 3]))), \
-                            fmaxf(fmaxf(__uint_as_float(R[O + 4]), __uint_as_float(R[O + 5])), fmaxf(__uint_as_float(R[O + 6]), __uint_as_float(R[O + 7]))))
-#define TC_GROUP(R, O)                                                                                             \
+#define TC_MAX8(R, O) tc_max3(tc_max3(__uint_as_float(R[O]), __uint_as_float(R[O + 1]), __uint_as_float(R[O + 2])),     \
+                              tc_max3(__uint_as_float(R[O + 3]), __uint_as_float(R[O + 4]), __uint_as_float(R[O + 5])), \
+                              fmaxf(__uint_as_float(R[O + 6]), __uint_as_float(R[O + 7])))
+#define TC_GROUP(R, O, MG)                                                                                         \
             do {                                                                                                   \
-                if (__any_sync(0xffffffffu, valid && TC_MAX8(R, O) > tau)) {                                       \
-                    if (__any_sync(0xffffffffu, pend > TC_PEND - 8)) TC_FLUSH();                                   \
-                    TC_CHECK1(R, O); TC_CHECK1(R, O + 1); TC_CHECK1(R, O + 2); TC_CHECK1(R, O + 3);                \
-                    TC_CHECK1(R, O + 4); TC_CHECK1(R, O + 5); TC_CHECK1(R, O + 6); TC_CHECK1(R, O + 7);            \
+                if (__any_sync(0xffffffffu, (MG) > tau)) {                                                         \
+                    if (__any_sync(0xffffffffu, cnt > TC_CAP - 8)) TC_COMPACT(TC_CAP - 8);                              \
+                    TC_APPEND(R, O); TC_APPEND(R, O + 1); TC_APPEND(R, O + 2); TC_APPEND(R, O + 3);                \
+                    TC_APPEND(R, O + 4); TC_APPEND(R, O + 5); TC_APPEND(R, O + 6); TC_APPEND(R, O + 7);            \
                 }                                                                                                  \
             } while (0)
 #define TC_PROCESS(R, CB)                                                                                          \
             do {                                                                                                   \
-                const int32_t item0 = n0 + (CB) * 32;                                                              \
-                TC_GROUP(R, 0); TC_GROUP(R, 8); TC_GROUP(R, 16); TC_GROUP(R, 24);                                  \
+                const float g0_ = TC_MAX8(R, 0), g1_ = TC_MAX8(R, 8), g2_ = TC_MAX8(R, 16), g3_ = TC_MAX8(R, 24);  \
+                if (__any_sync(0xffffffffu, fmaxf(tc_max3(g0_, g1_, g2_), g3_) > tau)) {                           \
+                    const int32_t item0 = n0 + (CB) * 32;                                                          \
+                    TC_GROUP(R, 0, g0_); TC_GROUP(R, 8, g1_); TC_GROUP(R, 16, g2_); TC_GROUP(R, 24, g3_);          \
+                }                                                                                                  \
             } while (0)
             for (int t = t0; t < t1; ++t) {
-                mbar_wait(BAR(2 * S + 2 + as), as_ph);
+                const int slot = as * 2 + a;
+                mbar_wait(BAR(2 * S + 2 + slot), as_ph);
                 tc_fence_after();
                 const int32_t n0 = t * TC_TILE_N;
                 const uint32_t tcol = trow + (uint32_t)(as * 256);
-                uint32_t ra[32], rb_[32];
-                tc_ld32_nowait(tcol, ra);
-                tc_ld_wait();
-#pragma unroll 1
-                for (int pair = 0; pair < 2; ++pair) {
-                    tc_ld32_nowait(tcol + (uint32_t)(pair * 64 + 32), rb_);
-                    TC_PROCESS(ra, pair * 2);
+                // two 64-column halves (the register file holds 170 registers per thread at 10 warps per SM); the
+                // accumulator slot goes back to the MMA warp as soon as the second half sits in registers
+                uint32_t r0[32], r1[32];
+                if (!(p.debug & 2)) {
+                    tc_ld32_nowait(tcol, r0);
+                    tc_ld32_nowait(tcol + 32, r1);
                     tc_ld_wait();
-                    if (pair == 0) tc_ld32_nowait(tcol + 64, ra);
-                    else {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR(2 * S + 4 + as));      // this warp has drained the stage
-                    }
-                    TC_PROCESS(rb_, pair * 2 + 1);
-                    if (pair == 0) tc_ld_wait();
+                }
+                if (!(p.debug & 3)) {
+                    TC_PROCESS(r0, 0);
+                    TC_PROCESS(r1, 1);
+                } else if (!(p.debug & 2) && r0[0] == 0x7fc00001u && r1[1] == 1u) {
+                    tau = 0.f;      // keeps the loads alive
+                }
+                if (!(p.debug & 2)) {
+                    tc_ld32_nowait(tcol + 64, r0);
+                    tc_ld32_nowait(tcol + 96, r1);
+                    tc_ld_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(2 * S + 6 + slot));            // this warp has drained the slot
+                if (!(p.debug & 3)) {
+                    TC_PROCESS(r0, 2);
+                    TC_PROCESS(r1, 3);
+                } else if (!(p.debug & 2) && r0[0] == 0x7fc00001u && r1[1] == 1u) {
+                    tau = 0.f;
                 }
                 if (++as == 2) { as = 0; as_ph ^= 1; }
             }
-            TC_FLUSH();
 #undef TC_PROCESS
 #undef TC_GROUP
 #undef TC_MAX8
-#undef TC_CHECK1
-#undef TC_FLUSH
-#undef TC_OFFER
+#undef TC_APPEND
+            // final pass: train mask over the entries appended since the last compaction, trim to TC_KEEP
+            TC_COMPACT(kept);
             if (valid) {
-                float* cs = p.cand_score + ((size_t)c * p.n_chunks + ch) * TC_CAP;
-                int32_t* ci = p.cand_item + ((size_t)c * p.n_chunks + ch) * TC_CAP;
-                for (int e = 0; e < cnt; ++e) { const uint2 he = ent[e * TC_ROWS]; cs[e] = __uint_as_float(he.x); ci[e] = (int32_t)he.y; }
                 p.cand_cnt[(size_t)c * p.n_chunks + ch] = cnt;
                 p.cand_tau[(size_t)c * p.n_chunks + ch] = tau;
             }
@@ -447,8 +526,9 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __global__ void __launch_bounds__(TC_RS_WARPS * 32) topn_tc_rescore_kernel(
     const double* __restrict__ P, const double* __restrict__ Q, const double* __restrict__ bu, const double* __restrict__ bi,
     double mu, int biased, int k, const int32_t* __restrict__ users, int32_t nq, int n_chunks, int topn,
-    const float* __restrict__ cand_score, const int32_t* __restrict__ cand_item, const int32_t* __restrict__ cand_cnt,
-    const float* __restrict__ cand_tau, const double* __restrict__ pnorm, double qnorm_max, double bi_max, double c_err,
+    const uint2* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+    const float* __restrict__ cand_tau, const double2* __restrict__ pstat, int eQ, double qnorm_max, double bi_max,
+    double qabs_scaled_max, double c_err, int Kp, unsigned int* __restrict__ err_ratio_bits,
     int32_t* __restrict__ out_items, double* __restrict__ out_scores, int32_t* __restrict__ out_counts,
     int32_t* __restrict__ fail_slots, int32_t* __restrict__ fail_users, int* __restrict__ fail_count) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
@@ -456,27 +536,50 @@ __global__ void __launch_bounds__(TC_RS_WARPS * 32) topn_tc_rescore_kernel(
     const int max_cand = n_chunks * TC_CAP;
     double* sv = reinterpret_cast<double*>(rs_smem) + (size_t)warp * max_cand;
     int32_t* si = reinterpret_cast<int32_t*>(reinterpret_cast<double*>(rs_smem) + (size_t)TC_RS_WARPS * max_cand) + (size_t)warp * max_cand;
+    float* sa = reinterpret_cast<float*>(reinterpret_cast<int32_t*>(reinterpret_cast<double*>(rs_smem) + (size_t)TC_RS_WARPS * max_cand) +
+                                         (size_t)TC_RS_WARPS * max_cand) + (size_t)warp * max_cand;
     const int32_t c = blockIdx.x * TC_RS_WARPS + warp;
     if (c >= nq) return;
     const int32_t u = users ? users[c] : c;
+    // error bound of the fp16 sweep for this row, in the units of the exact scores.  With a = fp16(2^eu p),
+    // b = fp16(2^eQ q): |a.b - 2^(eu+eQ) p.q| <= (2^-10 + 2^-22) sum|a_f b_f| + 2^-25 (sum|a_f| + sum|b_f|) + fp32
+    // accumulation slop (Kp+8) 2^-22 sum|a_f b_f|; sum|a_f b_f| <= ||a|| ||b||.  c_err carries the relative part.
+    const double2 ps = pstat[c];
+    const int eu = tc_scale_exp(ps.y, TC_USER_EXP_LO, TC_USER_EXP_HI);
+    const double ub = biased ? bu[u] : 0.0;
+    const double scale = ps.x * qnorm_max + bi_max;
+    const double eta = ldexp((double)Kp * (ldexp(ps.y, eu) + qabs_scaled_max) * 1.001, -25 - eu - eQ);
+    const double bound0 = c_err * scale + eta;
     // gather candidates of all chunks
     int M = 0;
     float tau_max = -INFINITY;
     for (int ch = 0; ch < n_chunks; ++ch) {
         const int cnt = cand_cnt[(size_t)c * n_chunks + ch];
         tau_max = fmaxf(tau_max, cand_tau[(size_t)c * n_chunks + ch]);
-        for (int e = lane; e < cnt; e += 32) si[M + e] = cand_item[((size_t)c * n_chunks + ch) * TC_CAP + e];
+        for (int e = lane; e < cnt; e += 32) {
+            const uint2 ce = cand[((size_t)c * n_chunks + ch) * TC_CAP + e];
+            si[M + e] = (int32_t)ce.y; sa[M + e] = __uint_as_float(ce.x);
+        }
         M += cnt;
     }
     __syncwarp();
+    const double tau_d = ldexp((double)tau_max, -eu - eQ);       // threshold in exact-score units (power-of-two scaling is exact)
+    float worst = 0.f;
     // exact scores in Java's order (DenseVector.java:104-111; BiasedMFRecommender.java:119)
     const double* pu = P + (int64_t)u * k;
     for (int e = lane; e < M; e += 32) {
         const int32_t it = si[e];
         double d = dot_lr_f64(pu, Q + (int64_t)it * k, k);
+        const double core = biased ? d + bi[it] : d;
         if (biased) d = __dadd_rn(__dadd_rn(__dadd_rn(d, bu[u]), bi[it]), mu);
         sv[e] = d;
+        // observed sweep error over the bound (diagnostic: must stay below 1)
+        const double err = fabs(ldexp((double)sa[e], -eu - eQ) - core);
+        if (bound0 > 0.0 && err == err) worst = fmaxf(worst, (float)(err / bound0));
     }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, m));
+    if (lane == 0 && worst > 0.f) atomicMax(err_ratio_bits, __float_as_uint(worst));
     __syncwarp();
     bool ok = M >= topn;
     // selection of the best topn+1 by (Double.compareTo desc); a tie anywhere in that prefix fails the row
@@ -499,10 +602,8 @@ __global__ void __launch_bounds__(TC_RS_WARPS * 32) topn_tc_rescore_kernel(
         if (r < topn && lane == 0) { out_items[(int64_t)c * topn + r] = si[be]; out_scores[(int64_t)c * topn + r] = bv; }
         if (r == topn - 1) {
             // certificate: nothing outside the candidate lists can reach the N-th exact score
-            const double ub = biased ? bu[u] : 0.0;
-            const double scale = pnorm[c] * qnorm_max + bi_max;
-            const double bound = c_err * scale + 1e-12 * (scale + fabs(ub) + fabs(mu) + fabs((double)tau_max));
-            const double reach = (double)tau_max + bound + (biased ? (ub + mu) : 0.0);
+            const double bound = bound0 + 1e-12 * (scale + fabs(ub) + fabs(mu) + fabs(tau_d));
+            const double reach = tau_d + bound + (biased ? (ub + mu) : 0.0);
             if (!(bv > reach)) { ok = false; break; }
         }
         prev = bv;
@@ -535,7 +636,7 @@ static int tc_make_map(lrk_handle_s* h, TcState* s, CUtensorMap* map, const void
     cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
     cuuint32_t box[2] = {TC_KB, TC_TILE_M};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = s->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+    CUresult r = s->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return lrk_fail(h, LRK_ERR_CUDA, "cuTensorMapEncodeTiled", "encode failed", __FILE__, __LINE__);
@@ -551,21 +652,37 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
     const int num_kb = Kp / TC_KB;
     if (num_kb > 2 || topn > TC_KEEP / 2)
         return lrk_fail(h, LRK_ERR_INVALID, "lrk_topn", "tensor-core path supports k (+2 for BiasedMF) <= 128 and topn <= 16", __FILE__, __LINE__);
+    for (cudaEvent_t& ev : s->ev) if (!ev) LRK_CUDA(h, cudaEventCreate(&ev));
+    LRK_CUDA(h, cudaEventRecord(s->ev[0], st));
     // ---- item operand (cached until the factors change)
     if (!s->valid || s->Kp != Kp) {
         if (s->Bq) { cudaFree(s->Bq); s->Bq = nullptr; }
-        LRK_CUDA(h, cudaMalloc((void**)&s->Bq, sizeof(__nv_bfloat16) * (size_t)h->I * Kp));
-        if (!s->d_stats) LRK_CUDA(h, cudaMalloc((void**)&s->d_stats, 16));
-        LRK_CUDA(h, cudaMemsetAsync(s->d_stats, 0, 16, st));
-        tc_build_items_kernel<<<lrk_ceil_div(h->I, 8), 256, 0, st>>>(h->Q64, h->bi64, biased, h->k, Kp, h->I, s->Bq, s->d_stats);
+        LRK_CUDA(h, cudaMalloc((void**)&s->Bq, sizeof(__half) * (size_t)h->I * Kp));
+        if (!s->d_stats) LRK_CUDA(h, cudaMalloc((void**)&s->d_stats, 32));
+        LRK_CUDA(h, cudaMemsetAsync(s->d_stats, 0, 32, st));
+        tc_item_stats_kernel<<<lrk_ceil_div(h->I, 8), 256, 0, st>>>(h->Q64, h->bi64, biased, h->k, h->I, s->d_stats);
         LRK_LAUNCH_CHECK(h);
-        unsigned long long stats[2];
-        LRK_CUDA(h, cudaMemcpyAsync(stats, s->d_stats, 16, cudaMemcpyDeviceToHost, st));
+        unsigned long long stats[3];
+        LRK_CUDA(h, cudaMemcpyAsync(stats, s->d_stats, 24, cudaMemcpyDeviceToHost, st));
         LRK_CUDA(h, cudaStreamSynchronize(st));
-        double n2, bm;
-        memcpy(&n2, &stats[0], 8); memcpy(&bm, &stats[1], 8);
-        s->qnorm_max = sqrt(n2); s->bi_max = biased ? bm : 0.0;
+        double n2, bm, qa;
+        memcpy(&n2, &stats[0], 8); memcpy(&bm, &stats[1], 8); memcpy(&qa, &stats[2], 8);
+        s->finite = std::isfinite(n2) && std::isfinite(bm) && std::isfinite(qa);
+        s->qnorm_max = sqrt(n2); s->bi_max = biased ? bm : 0.0; s->qabs_max = qa;
+        s->eQ = tc_scale_exp(std::max(qa, s->bi_max), -60, 60);
+        if (s->finite) {
+            tc_build_items_kernel<<<lrk_ceil_div(h->I, 8), 256, 0, st>>>(h->Q64, h->bi64, biased, h->k, Kp, h->I, s->eQ, s->Bq);
+            LRK_LAUNCH_CHECK(h);
+        }
         s->Kp = Kp; s->valid = true;
+    }
+    if (!s->finite) {
+        // NaN / Inf among the item factors: Double.compareTo semantics for those need the exact kernel
+        int rc0 = topn_exact_launch(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts);
+        if (rc0) return rc0;
+        LRK_CUDA(h, cudaStreamSynchronize(st));
+        h->topn_fast_users = 0; h->topn_fallback_users = nq;
+        return LRK_OK;
     }
     // ---- work decomposition
     const int total_tiles = lrk_ceil_div(h->I, TC_TILE_N);
@@ -577,41 +694,40 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
     const int64_t nq_pad = (int64_t)m_tiles * TC_TILE_M * TC_UT;
     const size_t tile_bytes = (size_t)TC_TILE_M * TC_KB * 2;
     const size_t a_bytes = (size_t)TC_UT * num_kb * tile_bytes, b_stage = (size_t)num_kb * tile_bytes;
-    const size_t heap_bytes = (size_t)TC_SLOTS * TC_ROWS * 8;                  // per-row min-heaps + pending slots
-    int stages = (int)((225 * 1024 + 512 - heap_bytes - a_bytes) / b_stage);
-    stages = std::max(2, std::min(stages, 6));
-    const size_t smem = 1024 + a_bytes + (size_t)stages * b_stage + heap_bytes + (2 * stages + 6) * 8 + 16;
+    int stages = (int)((226 * 1024 - 1024 - 256 - a_bytes) / b_stage);
+    stages = std::max(2, std::min(stages, 8));
+    { const char* es = getenv("LRK_TC_STAGES"); if (es && atoi(es) >= 2) stages = std::min(stages, atoi(es)); }   // profiling probe
+    const size_t smem = 1024 + a_bytes + (size_t)stages * b_stage + TC_NBARS(stages) * 8 + 16;
     // ---- query operand + scratch
     int32_t *fi = nullptr, *fc = nullptr; double* fs = nullptr;
     int rc = LRK_OK;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t b_aq = up(sizeof(__nv_bfloat16) * (size_t)nq_pad * Kp), b_pn = up(sizeof(double) * (size_t)nq_pad);
-    const size_t b_cs = up(sizeof(float) * (size_t)nq_pad * n_chunks * TC_CAP), b_ci = up(sizeof(int32_t) * (size_t)nq_pad * n_chunks * TC_CAP);
+    const size_t b_aq = up(sizeof(__half) * (size_t)nq_pad * Kp), b_pn = up(sizeof(double2) * (size_t)nq_pad);
+    const size_t b_cs = up(sizeof(uint2) * (size_t)nq_pad * n_chunks * TC_CAP);
     const size_t b_cc = up(sizeof(int32_t) * (size_t)nq_pad * n_chunks), b_ct = up(sizeof(float) * (size_t)nq_pad * n_chunks);
     const size_t b_fl = up(sizeof(int32_t) * (size_t)nq);
-    const size_t need = b_aq + b_pn + b_cs + b_ci + b_cc + b_ct + 2 * b_fl + 256;
+    const size_t need = b_aq + b_pn + b_cs + b_cc + b_ct + 2 * b_fl + 256;
     if (s->work_bytes < need) {
         if (s->work) { cudaFree(s->work); s->work = nullptr; s->work_bytes = 0; }
         LRK_CUDA(h, cudaMalloc(&s->work, need));
         s->work_bytes = need;
     }
     char* w = (char*)s->work;
-    __nv_bfloat16* Aq = (__nv_bfloat16*)w; w += b_aq;
-    double* pnorm = (double*)w; w += b_pn;
-    float* cscore = (float*)w; w += b_cs;
-    int32_t* citem = (int32_t*)w; w += b_ci;
+    __half* Aq = (__half*)w; w += b_aq;
+    double2* pstat = (double2*)w; w += b_pn;
+    uint2* cand = (uint2*)w; w += b_cs;
     int32_t* ccnt = (int32_t*)w; w += b_cc;
     float* ctau = (float*)w; w += b_ct;
     int32_t* fail_slots = (int32_t*)w; w += b_fl;
     int32_t* fail_users = (int32_t*)w; w += b_fl;
     int* fail_count = (int*)w;
     cudaError_t e = cudaMemsetAsync(fail_count, 0, sizeof(int), st);
-    if (e == cudaSuccess && nq_pad > nq) e = cudaMemsetAsync(Aq + (size_t)nq * Kp, 0, sizeof(__nv_bfloat16) * (size_t)(nq_pad - nq) * Kp, st);
+    if (e == cudaSuccess && nq_pad > nq) e = cudaMemsetAsync(Aq + (size_t)nq * Kp, 0, sizeof(__half) * (size_t)(nq_pad - nq) * Kp, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(ccnt, 0, sizeof(int32_t) * (size_t)nq_pad * n_chunks, st);
     int nfail = 0;
     do {
         if (e != cudaSuccess) break;
-        tc_build_users_kernel<<<lrk_ceil_div(nq, 8), 256, 0, st>>>(h->P64, biased, h->k, Kp, d_users, nq, Aq, pnorm);
+        tc_build_users_kernel<<<lrk_ceil_div(nq, 8), 256, 0, st>>>(h->P64, biased, h->k, Kp, d_users, nq, Aq, pstat);
         h->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) break;
         CUtensorMap tmA, tmB;
@@ -621,23 +737,30 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
         memset(&p, 0, sizeof p);
         p.nq = nq; p.I = h->I; p.n_chunks = n_chunks; p.tiles_per_chunk = tiles_per_chunk; p.total_tiles = total_tiles;
         p.num_kb = num_kb; p.stages = stages; p.exclude_train = exclude_train ? 1 : 0;
+        { const char* dbg = getenv("LRK_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
         p.rowptr = h->d_rowptr; p.col = h->d_col; p.users = d_users;
-        p.cand_score = cscore; p.cand_item = citem; p.cand_cnt = ccnt; p.cand_tau = ctau;
+        p.cand = cand; p.cand_cnt = ccnt; p.cand_tau = ctau;
         if ((e = cudaFuncSetAttribute(topn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) break;
         const int grid = std::min(h->sm_count, m_tiles * n_chunks);
+        if ((e = cudaEventRecord(s->ev[1], st)) != cudaSuccess) break;
         topn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
         h->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaEventRecord(s->ev[2], st)) != cudaSuccess) break;
         // ---- exact re-score + certificate
-        const double c_err = ldexp(1.0, -7) * (1.0 + ldexp(1.0, -6)) + (double)(Kp + 8) * ldexp(1.0, -22);
-        const size_t rs_smem_bytes = (size_t)TC_RS_WARPS * n_chunks * TC_CAP * (sizeof(double) + sizeof(int32_t));
+        const double c_err = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (double)(Kp + 8) * ldexp(1.0, -22);
+        const double qabs_scaled_max = ldexp(std::max(s->qabs_max, s->bi_max), s->eQ);
+        const size_t rs_smem_bytes = (size_t)TC_RS_WARPS * n_chunks * TC_CAP * (sizeof(double) + sizeof(int32_t) + sizeof(float));
+        if ((e = cudaMemsetAsync(s->d_stats + 3, 0, 8, st)) != cudaSuccess) break;
         if ((e = cudaFuncSetAttribute(topn_tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes)) != cudaSuccess) break;
         topn_tc_rescore_kernel<<<lrk_ceil_div(nq, TC_RS_WARPS), TC_RS_WARPS * 32, rs_smem_bytes, st>>>(
-            h->P64, h->Q64, h->bu64, h->bi64, h->mu, biased, h->k, d_users, nq, n_chunks, topn, cscore, citem, ccnt, ctau, pnorm,
-            s->qnorm_max, s->bi_max, c_err, d_items, d_scores, d_counts, fail_slots, fail_users, fail_count);
+            h->P64, h->Q64, h->bu64, h->bi64, h->mu, biased, h->k, d_users, nq, n_chunks, topn, cand, ccnt, ctau, pstat,
+            s->eQ, s->qnorm_max, s->bi_max, qabs_scaled_max, c_err, Kp, (unsigned int*)(s->d_stats + 3), d_items, d_scores, d_counts, fail_slots, fail_users, fail_count);
         h->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaEventRecord(s->ev[3], st)) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(&nfail, fail_count, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(&h->topn_err_ratio, s->d_stats + 3, sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
         if (nfail > 0) {
             // rows without a certificate: item-parallel exact fp64 path (heap replay only for exact ties)
@@ -652,10 +775,12 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
             if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
         }
     } while (0);
+    if (e == cudaSuccess && rc == LRK_OK) e = cudaEventRecord(s->ev[4], st);
     if (e == cudaSuccess && rc == LRK_OK) e = cudaStreamSynchronize(st);
     cudaFree(fi); cudaFree(fs); cudaFree(fc);
     if (rc) return rc;
     LRK_CUDA(h, e);
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&h->topn_phase_ms[i], s->ev[i], s->ev[i + 1]);
     h->topn_fast_users = nq - nfail;
     h->topn_fallback_users = nfail;
     return LRK_OK;
