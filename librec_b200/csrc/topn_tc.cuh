@@ -170,6 +170,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -196,7 +201,7 @@ struct TcParams {
     int32_t nq, I;
     int n_chunks, tiles_per_chunk, total_tiles, num_kb, stages;
     int exclude_train;
-    int debug;              // LRK_TC_DEBUG (profiling probes only): bit0 = drain TMEM but skip the selection, bit1 = do not even read TMEM
+    int debug;              // LRK_TC_DEBUG (profiling probes only): bit0 = drain TMEM but skip the selection, bit1 = do not even read TMEM, bit2 = issue no MMA
     const int64_t* __restrict__ rowptr;
     const int32_t* __restrict__ col;
     const int32_t* __restrict__ users;
@@ -311,18 +316,60 @@ __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// barrier map (S = B stages): [0,S) b_full, [S,2S) b_empty, 2S a_full, 2S+1 a_empty,
-// 2S+2+slot tmem_full, 2S+6+slot tmem_empty; accumulator slot = stage*2 + user sub-tile, 128 TMEM columns each
-#define TC_NBARS(S) (2 * (S) + 10)
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+          "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+          "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the user operand is read from tensor memory, so shared-memory operand
+// bandwidth is spent on the item tile alone (an M=128 N=128 SS-mode MMA measured 113 cycles instead of 64)
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Stages one thread's operand row (fp16 pairs, Kp/2 words) into its TMEM lane once the MMAs of the previous unit
+// have retired, then tells the MMA warp (one arrival per warp).
+__device__ __noinline__ void tc_stage_user_row(const __half* row, int num_kb, uint32_t taddr, uint32_t bar_free, uint32_t parity,
+                                               uint32_t bar_ready) {
+    const uint4* src = reinterpret_cast<const uint4*>(row);
+    mbar_wait(bar_free, parity);
+    tc_fence_after();
+    for (int kb = 0; kb < num_kb; ++kb) {
+        uint32_t w[32];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const uint4 x = __ldg(src + kb * 8 + v);
+            w[v * 4] = x.x; w[v * 4 + 1] = x.y; w[v * 4 + 2] = x.z; w[v * 4 + 3] = x.w;
+        }
+        tc_st32(taddr + (uint32_t)(kb * 32), w);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar_ready);
+}
+
+// barrier map (S = B stages): [0,S) b_full, [S,2S) b_empty, 2S a_full (8 epilogue warps), 2S+1 a_empty,
+// 2S+2+slot acc_full, 2S+5+slot acc_empty (4 epilogue warps).
+// TMEM: columns [0,128) user operand (sub-tile a at a*64: fp16 pairs, row == lane), then a ring of three
+// 128-column accumulator slots; accumulator n = 2*tile + sub-tile lives in slot n % 3.
+#define TC_NBARS(S) (2 * (S) + 8)
+#define TC_ACC_BASE 128
+#define TC_ACC_SLOTS 3
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+topn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __half* __restrict__ Aq, TcParams p) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    // carve: 1024-aligned operand tiles, then barriers
+    // carve: 1024-aligned item tiles, then barriers
     unsigned char* base = (unsigned char*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
-    const uint32_t tile_bytes = TC_TILE_M * TC_KB * 2;               // 16 KB: 128 rows x 128 B
-    unsigned char* smA = base;                                       // [UT][num_kb] tiles
-    unsigned char* smB = smA + (size_t)TC_UT * p.num_kb * tile_bytes; // [stages][num_kb] tiles
+    const uint32_t tile_bytes = TC_TILE_N * TC_KB * 2;               // 16 KB: 128 rows x 128 B
+    unsigned char* smB = base;                                       // [stages][num_kb] tiles
     uint64_t* bars = (uint64_t*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);
     const int S = p.stages;
     uint32_t* tmem_slot = (uint32_t*)(bars + TC_NBARS(S));
@@ -331,8 +378,8 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(S + s), 1); }
-        mbar_init(BAR(2 * S), 1); mbar_init(BAR(2 * S + 1), 1);
-        for (int s = 0; s < 4; ++s) { mbar_init(BAR(2 * S + 2 + s), 1); mbar_init(BAR(2 * S + 6 + s), 4); }
+        mbar_init(BAR(2 * S), 8); mbar_init(BAR(2 * S + 1), 1);
+        for (int s = 0; s < TC_ACC_SLOTS; ++s) { mbar_init(BAR(2 * S + 2 + s), 1); mbar_init(BAR(2 * S + 5 + s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -347,71 +394,87 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m_tiles = (p.nq + TC_ROWS - 1) / TC_ROWS;
     const int num_units = m_tiles * p.n_chunks;
 
+    // The producer and the MMA issuer run their loops warp-uniformly (all 32 lanes wait on the barriers) and
+    // elect one lane only around the asynchronous instructions: inside a lane-divergent branch the compiler wraps
+    // every UTCHMMA in an election loop, and the issue rate of that single thread capped the tensor pipe.
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int st = 0; uint32_t ph = 0, a_ph = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                const int mt = unit / p.n_chunks, ch = unit - mt * p.n_chunks;
-                mbar_wait(BAR(2 * S + 1), a_ph ^ 1);                       // A slot free
-                mbar_expect_tx(BAR(2 * S), TC_UT * p.num_kb * tile_bytes);
-                for (int a = 0; a < TC_UT; ++a)
-                    for (int kb = 0; kb < p.num_kb; ++kb)
-                        tma_load_2d(smem_u32(smA + (size_t)(a * p.num_kb + kb) * tile_bytes), &tmA, kb * TC_KB,
-                                    (mt * TC_UT + a) * TC_TILE_M, BAR(2 * S));
-                a_ph ^= 1;
-                const int t0 = ch * p.tiles_per_chunk;
-                const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-                for (int t = t0; t < t1; ++t) {
-                    mbar_wait(BAR(S + st), ph ^ 1);                        // B slot free
+        // ================= TMA producer (item tiles) =================
+        int st = 0; uint32_t ph = 0;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            const int ch = unit % p.n_chunks;
+            const int t0 = ch * p.tiles_per_chunk;
+            const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(BAR(S + st), ph ^ 1);                            // B slot free
+                if (tc_elect_one()) {
                     mbar_expect_tx(BAR(st), p.num_kb * tile_bytes);
                     for (int kb = 0; kb < p.num_kb; ++kb)
                         tma_load_2d(smem_u32(smB + (size_t)(st * p.num_kb + kb) * tile_bytes), &tmB, kb * TC_KB, t * TC_TILE_N, BAR(st));
-                    if (++st == S) { st = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++st == S) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            int st = 0; uint32_t ph = 0, a_ph = 0; int as = 0; uint32_t as_ph = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                const int ch = unit % p.n_chunks;
-                mbar_wait(BAR(2 * S), a_ph);                               // A landed
-                a_ph ^= 1;
-                const int t0 = ch * p.tiles_per_chunk;
-                const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-                for (int t = t0; t < t1; ++t) {
-                    mbar_wait(BAR(st), ph);                                // B landed
-                    for (int a = 0; a < TC_UT; ++a) {
-                        const int slot = as * 2 + a;
-                        mbar_wait(BAR(2 * S + 6 + slot), as_ph ^ 1);       // accumulator slot drained by its 4 epilogue warps
-                        tc_fence_after();
-                        const uint32_t d = tmem_base + (uint32_t)(slot * TC_TILE_N);
-                        for (int kb = 0; kb < p.num_kb; ++kb) {
-                            const uint32_t a_addr = smem_u32(smA + (size_t)(a * p.num_kb + kb) * tile_bytes);
-                            const uint32_t b_addr = smem_u32(smB + (size_t)(st * p.num_kb + kb) * tile_bytes);
+        int st = 0; uint32_t ph = 0, a_ph = 0; int slot = 0; uint32_t slot_ph = 0;
+        const uint64_t desc0 = tc_smem_desc(smem_u32(smB));
+        const uint32_t stage_units = (uint32_t)(p.num_kb * tile_bytes) >> 4;   // descriptor address units (16 B) per B stage
+        const int nkb = (p.debug & 4) ? 0 : p.num_kb;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            const int ch = unit % p.n_chunks;
+            mbar_wait(BAR(2 * S), a_ph);                                   // user operand of this unit is in TMEM
+            a_ph ^= 1;
+            tc_fence_after();
+            const int t0 = ch * p.tiles_per_chunk;
+            const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(BAR(st), ph);                                    // B landed
+                const uint64_t bdesc = desc0 + (uint64_t)((uint32_t)st * stage_units);
 #pragma unroll
-                            for (int k4 = 0; k4 < TC_KB / 16; ++k4)
-                                tc_mma_f16(d, tc_smem_desc(a_addr + k4 * 32), tc_smem_desc(b_addr + k4 * 32), TC_IDESC,
-                                           (kb | k4) != 0 ? 1u : 0u);
+                for (int a = 0; a < TC_UT; ++a) {
+                    mbar_wait(BAR(2 * S + 5 + slot), slot_ph ^ 1);         // accumulator slot drained by its 4 epilogue warps
+                    tc_fence_after();
+                    if (tc_elect_one()) {
+                        const uint32_t d = tmem_base + (uint32_t)(TC_ACC_BASE + slot * TC_TILE_N);
+                        const uint32_t at = tmem_base + (uint32_t)(a * 64);
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb) {
+                            if (kb < nkb) {
+#pragma unroll
+                                for (int k4 = 0; k4 < TC_KB / 16; ++k4)
+                                    tc_mma_f16_ts(d, at + (uint32_t)(kb * 32 + k4 * 8), bdesc + (uint64_t)(kb * (tile_bytes >> 4) + k4 * 2),
+                                                  TC_IDESC, (kb | k4) != 0 ? 1u : 0u);
+                            }
                         }
                         tc_commit(BAR(2 * S + 2 + slot));                  // this sub-tile's scores are ready
+                        if (a == TC_UT - 1) tc_commit(BAR(S + st));        // B slot reusable once these MMAs retire
                     }
-                    tc_commit(BAR(S + st));                                // B slot reusable once these MMAs retire
-                    if (++st == S) { st = 0; ph ^= 1; }
-                    if (++as == 2) { as = 0; as_ph ^= 1; }
+                    __syncwarp();
+                    if (++slot == TC_ACC_SLOTS) { slot = 0; slot_ph ^= 1; }
                 }
-                tc_commit(BAR(2 * S + 1));                                 // A slot reusable
+                if (++st == S) { st = 0; ph ^= 1; }
             }
+            if (tc_elect_one()) tc_commit(BAR(2 * S + 1));                 // user operand may be overwritten
+            __syncwarp();
         }
     } else {
         // ================= epilogue: one thread == one user row =================
         const int ew = warp - 2;
         const int a = ew >> 2;                 // user sub-tile
-        const int q = warp & 3;                // TMEM lane quarter this warp may read
+        const int q = warp & 3;                // TMEM lane quarter this warp may access
         const int row_in_cta = a * TC_TILE_M + q * 32 + lane;
-        int as = 0; uint32_t as_ph = 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        // accumulator sequence of this sub-tile: n = a, a+2, a+4, ... ; slot = n % 3, parity = (n / 3) & 1
+        int slot = a; uint32_t slot_ph = 0;
+        uint32_t a_ph = 0;
+        auto stage_user_rows = [&](int unit) {
+            const int mt = unit / p.n_chunks;
+            tc_stage_user_row(Aq + ((size_t)mt * TC_ROWS + row_in_cta) * (size_t)(p.num_kb * TC_KB), p.num_kb,
+                              tlane + (uint32_t)(a * 64), BAR(2 * S + 1), a_ph ^ 1, BAR(2 * S));
+            a_ph ^= 1;
+        };
+        if ((int)blockIdx.x < num_units) stage_user_rows(blockIdx.x);
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
             const int mt = unit / p.n_chunks, ch = unit - mt * p.n_chunks;
             const int32_t c = mt * TC_ROWS + row_in_cta;
@@ -436,7 +499,6 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // appends to the row's list) only if SOME lane of the warp has a score above its threshold there.
             float tau = valid ? -INFINITY : INFINITY;
             int cnt = 0, kept = 0;
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_TILE_N);
 #define TC_APPEND(R, J)                                                                                            \
             do {                                                                                                   \
                 if (__uint_as_float(R[J]) > tau && item0 + (J) < i1) {                                             \
@@ -464,11 +526,10 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }                                                                                                  \
             } while (0)
             for (int t = t0; t < t1; ++t) {
-                const int slot = as * 2 + a;
-                mbar_wait(BAR(2 * S + 2 + slot), as_ph);
+                mbar_wait(BAR(2 * S + 2 + slot), slot_ph);
                 tc_fence_after();
                 const int32_t n0 = t * TC_TILE_N;
-                const uint32_t tcol = trow + (uint32_t)(as * 256);
+                const uint32_t tcol = tlane + (uint32_t)(TC_ACC_BASE + slot * TC_TILE_N);
                 // two 64-column halves (the register file holds 170 registers per thread at 10 warps per SM); the
                 // accumulator slot goes back to the MMA warp as soon as the second half sits in registers
                 uint32_t r0[32], r1[32];
@@ -490,19 +551,23 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(2 * S + 6 + slot));            // this warp has drained the slot
+                if (lane == 0) mbar_arrive(BAR(2 * S + 5 + slot));            // this warp has drained the slot
                 if (!(p.debug & 3)) {
                     TC_PROCESS(r0, 2);
                     TC_PROCESS(r1, 3);
                 } else if (!(p.debug & 2) && r0[0] == 0x7fc00001u && r1[1] == 1u) {
                     tau = 0.f;
                 }
-                if (++as == 2) { as = 0; as_ph ^= 1; }
+                // this sub-tile's next accumulator is two further down the ring of three
+                slot += 2;
+                if (slot >= TC_ACC_SLOTS) { slot -= TC_ACC_SLOTS; slot_ph ^= 1; }
             }
 #undef TC_PROCESS
 #undef TC_GROUP
 #undef TC_MAX8
 #undef TC_APPEND
+            // hand the next unit's user rows to the MMA warp before the (long) final compaction of this one
+            if (unit + (int)gridDim.x < num_units) stage_user_rows(unit + gridDim.x);
             // final pass: train mask over the entries appended since the last compaction, trim to TC_KEEP
             TC_COMPACT(kept);
             if (valid) {
@@ -693,11 +758,11 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
     n_chunks = lrk_ceil_div(total_tiles, tiles_per_chunk);
     const int64_t nq_pad = (int64_t)m_tiles * TC_TILE_M * TC_UT;
     const size_t tile_bytes = (size_t)TC_TILE_M * TC_KB * 2;
-    const size_t a_bytes = (size_t)TC_UT * num_kb * tile_bytes, b_stage = (size_t)num_kb * tile_bytes;
-    int stages = (int)((226 * 1024 - 1024 - 256 - a_bytes) / b_stage);
+    const size_t b_stage = (size_t)num_kb * tile_bytes;
+    int stages = (int)((226 * 1024 - 1024 - 256) / b_stage);
     stages = std::max(2, std::min(stages, 8));
     { const char* es = getenv("LRK_TC_STAGES"); if (es && atoi(es) >= 2) stages = std::min(stages, atoi(es)); }   // profiling probe
-    const size_t smem = 1024 + a_bytes + (size_t)stages * b_stage + TC_NBARS(stages) * 8 + 16;
+    const size_t smem = 1024 + (size_t)stages * b_stage + TC_NBARS(stages) * 8 + 16;
     // ---- query operand + scratch
     int32_t *fi = nullptr, *fc = nullptr; double* fs = nullptr;
     int rc = LRK_OK;
@@ -730,8 +795,7 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
         tc_build_users_kernel<<<lrk_ceil_div(nq, 8), 256, 0, st>>>(h->P64, biased, h->k, Kp, d_users, nq, Aq, pstat);
         h->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) break;
-        CUtensorMap tmA, tmB;
-        if ((rc = tc_make_map(h, s, &tmA, Aq, Kp, nq_pad))) break;
+        CUtensorMap tmB;
         if ((rc = tc_make_map(h, s, &tmB, s->Bq, Kp, h->I))) break;
         TcParams p;
         memset(&p, 0, sizeof p);
@@ -743,7 +807,7 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
         if ((e = cudaFuncSetAttribute(topn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) break;
         const int grid = std::min(h->sm_count, m_tiles * n_chunks);
         if ((e = cudaEventRecord(s->ev[1], st)) != cudaSuccess) break;
-        topn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+        topn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmB, Aq, p);
         h->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) break;
         if ((e = cudaEventRecord(s->ev[2], st)) != cudaSuccess) break;
