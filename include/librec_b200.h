@@ -151,10 +151,12 @@ LRK_API int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t t
 LRK_API int lrk_topn_stats(lrk_handle_t h, int64_t* fast_users, int64_t* fallback_users, float* ms_out);
 /* device time of the phases of the last tensor-core lrk_topn call, CUDA events on the handle's stream:
  * out[0] operand build, out[1] tcgen05 score sweep + fused selection (topn_tc_kernel), out[2] exact fp64
- * re-score + certificate, out[3] exact fallback for rows without a certificate.  out[4] is a self-check of the
- * certificate: the largest observed |fp16 sweep score - exact score| over all re-scored candidates divided by
- * the error bound the certificate assumes (must stay below 1).  Zeros if the exact path ran. */
-LRK_API int lrk_topn_phase_ms(lrk_handle_t h, float out[5]);
+ * re-score + certificate (and the second sweep of rows whose margin was too thin), out[3] exact fallback for rows
+ * still without a certificate.  out[4] is a self-check of the certificate: the largest observed
+ * |fp16 sweep score - exact score| over all re-scored candidates divided by the error bound the certificate
+ * assumes (must stay below 1).  out[5] = number of rows that went through the second sweep.
+ * Zeros if the exact path ran. */
+LRK_API int lrk_topn_phase_ms(lrk_handle_t h, float out[6]);
 
 /* ---- multi-GPU DSGD (one process per GPU) ----------------------------- */
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the host (torch.distributed / MPI / JVM) */

@@ -209,11 +209,11 @@ class Handle:
     def topn_stats(self):
         a, b, ms = C.c_int64(), C.c_int64(), C.c_float()
         _check(load().lrk_topn_stats(self._h, C.byref(a), C.byref(b), C.byref(ms)), self._h)
-        ph = (C.c_float * 5)()
+        ph = (C.c_float * 6)()
         _check(load().lrk_topn_phase_ms(self._h, ph), self._h)
         return {"fast_users": a.value, "fallback_users": b.value, "ms": ms.value,
                 "phase_ms": {"operands": ph[0], "sweep": ph[1], "rescore": ph[2], "fallback": ph[3]},
-                "sweep_error_over_bound": ph[4]}
+                "sweep_error_over_bound": ph[4], "resweep_users": int(ph[5])}
 
     # -- DSGD
     def comm_init(self, rank, world, unique_id):

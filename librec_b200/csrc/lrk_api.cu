@@ -401,7 +401,7 @@ int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     h->topn_fast_users = 0; h->topn_fallback_users = 0; h->topn_ms = 0.f;
     for (int i = 0; i < 4; ++i) h->topn_phase_ms[i] = 0.f;
-    h->topn_err_ratio = 0.f;
+    h->topn_err_ratio = 0.f; h->topn_resweep_users = 0;
     if (nq == 0) return LRK_OK;
     if (users) for (int32_t c = 0; c < nq; ++c) LRK_REQUIRE(h, users[c] >= 0 && users[c] < h->U, "user index out of range");
     else LRK_REQUIRE(h, nq <= h->U, "nq exceeds numUsers");
@@ -438,10 +438,11 @@ int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int
     return LRK_OK;
 }
 
-int lrk_topn_phase_ms(lrk_handle_t h, float out[5]) {
+int lrk_topn_phase_ms(lrk_handle_t h, float out[6]) {
     LRK_REQUIRE(h, h != nullptr && out != nullptr, "NULL argument");
     for (int i = 0; i < 4; ++i) out[i] = h->topn_phase_ms[i];
     out[4] = h->topn_err_ratio;
+    out[5] = (float)h->topn_resweep_users;
     return LRK_OK;
 }
 

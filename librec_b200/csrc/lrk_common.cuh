@@ -45,7 +45,7 @@ struct lrk_handle_s {
     uint64_t launches = 0;
 
     // top-N statistics
-    int64_t topn_fast_users = 0, topn_fallback_users = 0;
+    int64_t topn_fast_users = 0, topn_fallback_users = 0, topn_resweep_users = 0;
     float topn_ms = 0.f;
     float topn_phase_ms[4] = {0.f, 0.f, 0.f, 0.f};
     float topn_err_ratio = 0.f;   // largest observed |fp16 sweep score - exact score| / certificate bound (must be < 1)

@@ -1,25 +1,29 @@
 // Tensor-core top-N (sm_100a): recommendRank()'s user x item score sweep
-// (recommender/MatrixRecommender.java:153-201) as a tcgen05 / TMA bf16 GEMM with the selection fused
+// (recommender/MatrixRecommender.java:153-201) as a tcgen05 / TMA fp16 GEMM with the selection fused
 // into the epilogue, followed by an exact fp64 re-score -- so the lists that leave the library are
 // still bit-identical to the reference (util/Lists.java:416-468 semantics).
 //
-//   1. operands: A = queried user factors, B = item factors, both K-major bf16, K padded to 64;
-//      BiasedMF folds the item bias into two extra K columns (hi/lo bf16 split against 1.0 in A).
+//   1. operands: A = queried user factors, B = item factors, both K-major fp16 after an exact power-of-two
+//      scaling (per user row / per item matrix), K padded to 64; BiasedMF folds the item bias into two extra
+//      K columns (hi/lo fp16 split against the row's scale in A).
 //   2. topn_tc_kernel (persistent, warp-specialised, 1 CTA/SM, 320 threads):
-//        warp 0  TMA producer   cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier ring
-//        warp 1  MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16; two user
-//                               sub-tiles (256 users) share every item tile -> halves L2->SM traffic;
-//                               accumulators double-buffered in all 512 TMEM columns
-//        warps 2-9 epilogue     tcgen05.ld 32x32b.x32: one thread owns one user row; a score is
-//                               appended to the row's candidate list only if it beats the row's running
-//                               threshold tau (1 FMNMX per score + 1 compare per 8 scores in the common
-//                               case); train items are masked on the rare append path; full lists are
-//                               compacted warp-cooperatively to the best K' (tau rises).
-//      Invariant: every item that is NOT in a row's candidate list has approximate score <= tau_row
+//        warp 0  TMA producer   item tiles, cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier ring (7 stages at k=128)
+//        warp 1  MMA issuer     tcgen05.mma.cta_group::1.kind::f16 with the A operand in TENSOR MEMORY (.ts form),
+//                               M=128 N=128 K=16; two user sub-tiles (256 users) share every item tile; the loop is
+//                               warp-uniform with elect.sync around the issue (8 back-to-back UTCHMMA per sub-tile);
+//                               accumulators in a ring of three 128-column TMEM slots
+//        warps 2-9 epilogue     stage their user rows into TMEM (tcgen05.st), then per tile tcgen05.ld 32x32b.x32:
+//                               one thread owns one user row; a score is appended to the row's candidate list
+//                               (global memory, L2-resident) only if it beats the row's running threshold tau --
+//                               common case 15 FMNMX3/FMNMX + 1 compare + 1 warp vote per 32 scores; full lists are
+//                               compacted warp-cooperatively to the best K' (train items masked there, tau rises).
+//      Invariant: every item that is NOT in a row's candidate list has sweep score <= tau_row
 //      (or is a train item / NaN / out of range).
 //   3. topn_tc_rescore_kernel: exact fp64 scores of the candidates in Java's summation order, top-N,
-//      and an exactness certificate: N-th exact score > tau + error bound of the bf16 sweep, and no
-//      exact ties among the first N+1.  Rows that fail are re-done by the exact kernel (topn_exact.cuh).
+//      and an exactness certificate: N-th exact score > tau + error bound of the fp16 sweep, and no
+//      exact ties among the first N+1.  Rows whose margin is too thin are swept a second time from the
+//      threshold their first result implies (K' = 32); what still fails (exact ties, fewer than N
+//      candidates) is re-done by the exact kernel (topn_exact.cuh).
 #pragma once
 #include "lrk_common.cuh"
 #include "topn_exact.cuh"
@@ -34,8 +38,8 @@
 #define TC_UT 2                // user sub-tiles per CTA
 #define TC_TILE_N 128          // items per MMA tile
 #define TC_KB 64               // bf16 elements per 128-byte swizzle row
-#define TC_KEEP 32             // K': candidates kept per (row, chunk) by a compaction
-#define TC_CAP 64              // candidate slots per (row, chunk) in global memory (append buffer, compacted to TC_KEEP)
+#define TC_KEEP_MAX 32         // largest K' (candidates a compaction keeps per (row, chunk))
+#define TC_CAP 64              // candidate slots per (row, chunk) in global memory (append buffer, compacted to K')
 #define TC_ROWS (TC_TILE_M * TC_UT)   // user rows per CTA
 #define TC_THREADS 320
 #define TC_MAX_CHUNKS 16
@@ -49,8 +53,10 @@ struct TcState {
     double qnorm_max = 0.0, bi_max = 0.0, qabs_max = 0.0;
     unsigned long long* d_stats = nullptr;   // [0] max ||q||^2 bits, [1] max |bi| bits, [2] max |q_f| bits, [3] max err/bound (float bits)
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
-    void* work = nullptr;                    // per-call scratch (user operand, candidate lists, ...), grown on demand
+    void* work = nullptr;                    // per-pass scratch (user operand, candidate lists, ...), grown on demand
     size_t work_bytes = 0;
+    void* lists = nullptr;                   // per-call lists of rows without a certificate
+    size_t lists_bytes = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase boundaries of the last call
 };
 
@@ -61,7 +67,7 @@ static inline TcState* tc_state(lrk_handle_s* h) {
 static inline void topn_tc_release(lrk_handle_s* h) {
     TcState* s = (TcState*)h->tc;
     if (!s) return;
-    cudaFree(s->Bq); cudaFree(s->d_stats); cudaFree(s->work);
+    cudaFree(s->Bq); cudaFree(s->d_stats); cudaFree(s->work); cudaFree(s->lists);
     for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
     delete s;
     h->tc = nullptr;
@@ -74,7 +80,7 @@ static inline int tc_kp(lrk_handle_s* h) {
     return ((kaug + TC_KB - 1) / TC_KB) * TC_KB;
 }
 static inline bool topn_tc_profitable(lrk_handle_s* h, int32_t nq, int topn) {
-    return topn <= TC_KEEP / 2 && tc_kp(h) <= 128 && h->I >= 8192 && nq >= 512;
+    return topn <= 16 && tc_kp(h) <= 128 && h->I >= 8192 && nq >= 512;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,10 +207,12 @@ struct TcParams {
     int32_t nq, I;
     int n_chunks, tiles_per_chunk, total_tiles, num_kb, stages;
     int exclude_train;
+    int keep;               // K': candidates a compaction keeps per (row, chunk), <= TC_KEEP_MAX
     int debug;              // LRK_TC_DEBUG (profiling probes only): bit0 = drain TMEM but skip the selection, bit1 = do not even read TMEM, bit2 = issue no MMA
     const int64_t* __restrict__ rowptr;
     const int32_t* __restrict__ col;
     const int32_t* __restrict__ users;
+    const float* init_tau;  // per query slot: threshold the row starts from (second pass), or NULL = -inf
     uint2* cand;            // [nq_pad][n_chunks][TC_CAP] {approximate score bits, item}
     int32_t* cand_cnt;      // [nq_pad][n_chunks]
     float* cand_tau;
@@ -228,10 +236,11 @@ __device__ __forceinline__ T* tc_shfl_ptr(T* ptr, int src) {
 //   1. load the <= TC_CAP entries (two per lane);
 //   2. drop train items among the new entries (MatrixRecommender.java:170-174): the sorted CSR row is walked
 //      32 items per load from a per-row cursor, membership by a 5-step binary search across lanes;
-//   3. rank by (score desc, slot asc), keep the best TC_KEEP, tau := score of rank TC_KEEP-1.
+//   3. rank by (score desc, slot asc), keep the best K', tau := score of rank K'-1.
 // Everything dropped here has approximate score <= the new tau (or is a train item), which is the invariant the
 // exactness certificate of topn_tc_rescore_kernel rests on.
-__device__ __noinline__ int4 tc_compact(uint2* lp, int cnt, int kept, float tau, const int32_t* col_row, int tlen, int tp, int trig) {
+__device__ __noinline__ int4 tc_compact(uint2* lp, int cnt, int kept, float tau, const int32_t* col_row, int tlen, int tp, int32_t nt,
+                                        int trig, int keep, int32_t n_items) {
     const int lane = threadIdx.x & 31;
     unsigned flagged = __ballot_sync(0xffffffffu, cnt > trig);
     while (flagged) {
@@ -243,17 +252,21 @@ __device__ __noinline__ int4 tc_compact(uint2* lp, int cnt, int kept, float tau,
         const int tl = __shfl_sync(0xffffffffu, tlen, r);
         int cur = __shfl_sync(0xffffffffu, tp, r);
         float new_tau = __shfl_sync(0xffffffffu, tau, r);
+        const int32_t nt_r = __shfl_sync(0xffffffffu, nt, r);          // next train item at / after the row's cursor
         __syncwarp();
         bool al0 = lane < n, al1 = lane + 32 < n;
         uint2 e0 = make_uint2(0u, 0u), e1 = make_uint2(0u, 0u);
         if (al0) e0 = __ldcg(L + lane);
         if (al1) e1 = __ldcg(L + 32 + lane);
+        // columns past the catalogue end (zero-filled by TMA) are appended unchecked by the sweep; drop them here
+        if ((int32_t)e0.y >= n_items) al0 = false;
+        if ((int32_t)e1.y >= n_items) al1 = false;
         if (tl > cur && n > kp) {
-            // item range of the new entries (ascending by construction)
+            // item range of the new entries (ascending by construction); nothing to mask if the next train item lies beyond
             const int32_t lo_a = (int32_t)__shfl_sync(0xffffffffu, e0.y, kp & 31), lo_b = (int32_t)__shfl_sync(0xffffffffu, e1.y, kp & 31);
             const int32_t hi_a = (int32_t)__shfl_sync(0xffffffffu, e0.y, (n - 1) & 31), hi_b = (int32_t)__shfl_sync(0xffffffffu, e1.y, (n - 1) & 31);
             const int32_t i_lo = kp < 32 ? lo_a : lo_b, i_hi = (n - 1) < 32 ? hi_a : hi_b;
-            for (;;) {
+            if (nt_r <= i_hi) for (;;) {
                 const int32_t tv = (cur + lane < tl) ? __ldg(cr + cur + lane) : 0x7fffffff;
                 const int32_t last = __shfl_sync(0xffffffffu, tv, 31);
                 if (last < i_lo) { cur += 32; continue; }
@@ -282,13 +295,13 @@ __device__ __noinline__ int4 tc_compact(uint2* lp, int cnt, int kept, float tau,
             rk1 += (b > s1 || (b == s1 && j < lane)) ? 1 : 0;
         }
         const int alive = __popc(__ballot_sync(0xffffffffu, al0)) + __popc(__ballot_sync(0xffffffffu, al1));
-        const int keep_n = min(alive, TC_KEEP);
+        const int keep_n = min(alive, keep);
         __syncwarp();
         if (al0 && rk0 < keep_n) __stcg(L + rk0, e0);
         if (al1 && rk1 < keep_n) __stcg(L + rk1, e1);
-        if (alive >= TC_KEEP) {
-            const unsigned b0 = __ballot_sync(0xffffffffu, al0 && rk0 == TC_KEEP - 1);
-            const unsigned b1 = __ballot_sync(0xffffffffu, al1 && rk1 == TC_KEEP - 1);
+        if (alive >= keep) {
+            const unsigned b0 = __ballot_sync(0xffffffffu, al0 && rk0 == keep - 1);
+            const unsigned b1 = __ballot_sync(0xffffffffu, al1 && rk1 == keep - 1);
             const float t0 = __shfl_sync(0xffffffffu, s0, b0 ? __ffs(b0) - 1 : 0), t1 = __shfl_sync(0xffffffffu, s1, b1 ? __ffs(b1) - 1 : 0);
             new_tau = b0 ? t0 : t1;
         }
@@ -299,8 +312,9 @@ __device__ __noinline__ int4 tc_compact(uint2* lp, int cnt, int kept, float tau,
 }
 #define TC_COMPACT(TRIG)                                                                  \
     do {                                                                                  \
-        const int4 r_ = tc_compact(lp, cnt, kept, tau, col_row, tlen, tp, (TRIG));        \
-        cnt = r_.x; kept = r_.y; tau = __int_as_float(r_.z); tp = r_.w;                   \
+        const int4 r_ = tc_compact(lp, cnt, kept, tau, col_row, tlen, tp, nt, (TRIG), p.keep, p.I); \
+        cnt = r_.x; kept = r_.y; tau = __int_as_float(r_.z);                              \
+        if (r_.w != tp) { tp = r_.w; nt = tp < tlen ? __ldg(col_row + tp) : 0x7fffffff; }  \
     } while (0)
 
 // raw TMEM load of 32 accumulator columns of this thread's row (no wait)
@@ -481,10 +495,10 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __half* __restrict
             const bool valid = c < p.nq;
             const int t0 = ch * p.tiles_per_chunk;
             const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-            const int32_t i1 = min(p.I, t1 * TC_TILE_N);
             uint2* lp = p.cand + ((size_t)c * p.n_chunks + ch) * TC_CAP;          // this row's candidate list (global, L2-resident)
             const int32_t* col_row = p.col;
             int tlen = 0, tp = 0;
+            int32_t nt = 0x7fffffff;               // next train item at / after the cursor (lets a compaction skip the mask)
             if (valid && p.exclude_train) {
                 const int32_t u = p.users ? p.users[c] : c;
                 const int64_t rb = p.rowptr[u], re = p.rowptr[u + 1];
@@ -493,15 +507,18 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __half* __restrict
                 int lo = 0, hi_ = tlen;
                 while (lo < hi_) { const int m = (lo + hi_) >> 1; if (__ldg(col_row + m) < i0) lo = m + 1; else hi_ = m; }
                 tp = lo;
+                nt = tp < tlen ? __ldg(col_row + tp) : 0x7fffffff;
             }
-            // Rows past nq carry tau = +inf so that nothing ever passes.  Common path per 32-column slab:
-            // 19 FMNMX3/FMNMX + one warp vote, no divergence.  A group of 8 columns is inspected (8 predicated
-            // appends to the row's list) only if SOME lane of the warp has a score above its threshold there.
-            float tau = valid ? -INFINITY : INFINITY;
+            // Rows past nq carry tau = +inf so that nothing ever passes.  Common path per 32-column slab: 15
+            // FMNMX3/FMNMX, one compare and one warp vote, no divergence.  A slab is looked into only if SOME lane of
+            // the warp has a score above its row's threshold there: by groups of 8, then 4 columns, 4 predicated appends.
+            // The two 64-column halves of a tile run through ONE copy of this code (rolled loop): the tile loop has to
+            // stay well inside the instruction cache (at ~36 KB it stalled 3.6 cycles per issue on instruction fetch).
+            float tau = valid ? (p.init_tau ? p.init_tau[c] : -INFINITY) : INFINITY;
             int cnt = 0, kept = 0;
 #define TC_APPEND(R, J)                                                                                            \
             do {                                                                                                   \
-                if (__uint_as_float(R[J]) > tau && item0 + (J) < i1) {                                             \
+                if (__uint_as_float(R[J]) > tau) {                                                                 \
                     __stcg(lp + cnt, make_uint2(R[J], (uint32_t)(item0 + (J))));                                   \
                     ++cnt;                                                                                         \
                 }                                                                                                  \
@@ -509,19 +526,23 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __half* __restrict
 #define TC_MAX8(R, O) tc_max3(tc_max3(__uint_as_float(R[O]), __uint_as_float(R[O + 1]), __uint_as_float(R[O + 2])),     \
                               tc_max3(__uint_as_float(R[O + 3]), __uint_as_float(R[O + 4]), __uint_as_float(R[O + 5])), \
                               fmaxf(__uint_as_float(R[O + 6]), __uint_as_float(R[O + 7])))
-#define TC_GROUP(R, O, MG)                                                                                         \
+#define TC_MAX4(R, O) fmaxf(tc_max3(__uint_as_float(R[O]), __uint_as_float(R[O + 1]), __uint_as_float(R[O + 2])), __uint_as_float(R[O + 3]))
+#define TC_HALF(R, O)                                                                                              \
             do {                                                                                                   \
-                if (__any_sync(0xffffffffu, (MG) > tau)) {                                                         \
-                    if (__any_sync(0xffffffffu, cnt > TC_CAP - 8)) TC_COMPACT(TC_CAP - 8);                              \
+                if (__any_sync(0xffffffffu, TC_MAX4(R, O) > tau)) {                                                \
+                    if (__any_sync(0xffffffffu, cnt > TC_CAP - 4)) TC_COMPACT(TC_CAP - 4);                         \
                     TC_APPEND(R, O); TC_APPEND(R, O + 1); TC_APPEND(R, O + 2); TC_APPEND(R, O + 3);                \
-                    TC_APPEND(R, O + 4); TC_APPEND(R, O + 5); TC_APPEND(R, O + 6); TC_APPEND(R, O + 7);            \
                 }                                                                                                  \
             } while (0)
-#define TC_PROCESS(R, CB)                                                                                          \
+#define TC_GROUP(R, O, MG)                                                                                         \
+            do {                                                                                                   \
+                if (__any_sync(0xffffffffu, (MG) > tau)) { TC_HALF(R, O); TC_HALF(R, O + 4); }                     \
+            } while (0)
+#define TC_PROCESS(R, ITEM0)                                                                                       \
             do {                                                                                                   \
                 const float g0_ = TC_MAX8(R, 0), g1_ = TC_MAX8(R, 8), g2_ = TC_MAX8(R, 16), g3_ = TC_MAX8(R, 24);  \
                 if (__any_sync(0xffffffffu, fmaxf(tc_max3(g0_, g1_, g2_), g3_) > tau)) {                           \
-                    const int32_t item0 = n0 + (CB) * 32;                                                          \
+                    const int32_t item0 = (ITEM0);                                                                 \
                     TC_GROUP(R, 0, g0_); TC_GROUP(R, 8, g1_); TC_GROUP(R, 16, g2_); TC_GROUP(R, 24, g3_);          \
                 }                                                                                                  \
             } while (0)
@@ -530,33 +551,27 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __half* __restrict
                 tc_fence_after();
                 const int32_t n0 = t * TC_TILE_N;
                 const uint32_t tcol = tlane + (uint32_t)(TC_ACC_BASE + slot * TC_TILE_N);
-                // two 64-column halves (the register file holds 170 registers per thread at 10 warps per SM); the
-                // accumulator slot goes back to the MMA warp as soon as the second half sits in registers
-                uint32_t r0[32], r1[32];
-                if (!(p.debug & 2)) {
-                    tc_ld32_nowait(tcol, r0);
-                    tc_ld32_nowait(tcol + 32, r1);
-                    tc_ld_wait();
-                }
-                if (!(p.debug & 3)) {
-                    TC_PROCESS(r0, 0);
-                    TC_PROCESS(r1, 1);
-                } else if (!(p.debug & 2) && r0[0] == 0x7fc00001u && r1[1] == 1u) {
-                    tau = 0.f;      // keeps the loads alive
-                }
-                if (!(p.debug & 2)) {
-                    tc_ld32_nowait(tcol + 64, r0);
-                    tc_ld32_nowait(tcol + 96, r1);
-                    tc_ld_wait();
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(2 * S + 5 + slot));            // this warp has drained the slot
-                if (!(p.debug & 3)) {
-                    TC_PROCESS(r0, 2);
-                    TC_PROCESS(r1, 3);
-                } else if (!(p.debug & 2) && r0[0] == 0x7fc00001u && r1[1] == 1u) {
-                    tau = 0.f;
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    // 64 columns at a time (the register file holds 170 registers per thread at 10 warps per SM); the
+                    // accumulator slot goes back to the MMA warp as soon as the second half sits in registers
+                    uint32_t r0[32], r1[32];
+                    if (!(p.debug & 2)) {
+                        tc_ld32_nowait(tcol + (uint32_t)(hf * 64), r0);
+                        tc_ld32_nowait(tcol + (uint32_t)(hf * 64 + 32), r1);
+                        tc_ld_wait();
+                    }
+                    if (hf == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(2 * S + 5 + slot));    // this warp has drained the slot
+                    }
+                    if (!(p.debug & 3)) {
+                        TC_PROCESS(r0, n0 + hf * 64);
+                        TC_PROCESS(r1, n0 + hf * 64 + 32);
+                    } else if (!(p.debug & 2) && r0[0] == 0x7fc00001u && r1[1] == 1u) {
+                        tau = 0.f;      // keeps the loads alive
+                    }
                 }
                 // this sub-tile's next accumulator is two further down the ring of three
                 slot += 2;
@@ -564,11 +579,13 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __half* __restrict
             }
 #undef TC_PROCESS
 #undef TC_GROUP
+#undef TC_HALF
+#undef TC_MAX4
 #undef TC_MAX8
 #undef TC_APPEND
-            // hand the next unit's user rows to the MMA warp before the (long) final compaction of this one
+            // hand the next unit's user rows to the MMA warp before the final compaction of this one
             if (unit + (int)gridDim.x < num_units) stage_user_rows(unit + gridDim.x);
-            // final pass: train mask over the entries appended since the last compaction, trim to TC_KEEP
+            // final pass: masks over the entries appended since the last compaction, trim to K'
             TC_COMPACT(kept);
             if (valid) {
                 p.cand_cnt[(size_t)c * p.n_chunks + ch] = cnt;
@@ -594,8 +611,12 @@ __global__ void __launch_bounds__(TC_RS_WARPS * 32) topn_tc_rescore_kernel(
     const uint2* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
     const float* __restrict__ cand_tau, const double2* __restrict__ pstat, int eQ, double qnorm_max, double bi_max,
     double qabs_scaled_max, double c_err, int Kp, unsigned int* __restrict__ err_ratio_bits,
+    const int32_t* __restrict__ slot_map,      // output slot of query slot c (second pass), or NULL = c
     int32_t* __restrict__ out_items, double* __restrict__ out_scores, int32_t* __restrict__ out_counts,
-    int32_t* __restrict__ fail_slots, int32_t* __restrict__ fail_users, int* __restrict__ fail_count) {
+    // rows without a certificate: {output slot, user}; margin failures also get the threshold a second sweep
+    // should start from (rs_*, only if rs_count != NULL), everything else goes to the exact kernel (ex_*)
+    int32_t* __restrict__ rs_slots, int32_t* __restrict__ rs_users, float* __restrict__ rs_tau0, int* __restrict__ rs_count,
+    int32_t* __restrict__ ex_slots, int32_t* __restrict__ ex_users, int* __restrict__ ex_count) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int max_cand = n_chunks * TC_CAP;
@@ -606,6 +627,7 @@ __global__ void __launch_bounds__(TC_RS_WARPS * 32) topn_tc_rescore_kernel(
     const int32_t c = blockIdx.x * TC_RS_WARPS + warp;
     if (c >= nq) return;
     const int32_t u = users ? users[c] : c;
+    const int64_t oslot = slot_map ? slot_map[c] : c;
     // error bound of the fp16 sweep for this row, in the units of the exact scores.  With a = fp16(2^eu p),
     // b = fp16(2^eQ q): |a.b - 2^(eu+eQ) p.q| <= (2^-10 + 2^-22) sum|a_f b_f| + 2^-25 (sum|a_f| + sum|b_f|) + fp32
     // accumulation slop (Kp+8) 2^-22 sum|a_f b_f|; sum|a_f b_f| <= ||a|| ||b||.  c_err carries the relative part.
@@ -647,6 +669,8 @@ __global__ void __launch_bounds__(TC_RS_WARPS * 32) topn_tc_rescore_kernel(
     if (lane == 0 && worst > 0.f) atomicMax(err_ratio_bits, __float_as_uint(worst));
     __syncwarp();
     bool ok = M >= topn;
+    float tau0 = 0.f;
+    bool margin_fail = false;
     // selection of the best topn+1 by (Double.compareTo desc); a tie anywhere in that prefix fails the row
     double prev = 0.0;
     const int want = min(M, topn + 1);
@@ -664,12 +688,19 @@ __global__ void __launch_bounds__(TC_RS_WARPS * 32) topn_tc_rescore_kernel(
         }
         if (be < 0 || bv != bv) { ok = false; break; }
         if (r > 0 && jcompare(bv, prev) == 0) { ok = false; break; }      // exact tie: heap-order semantics needed
-        if (r < topn && lane == 0) { out_items[(int64_t)c * topn + r] = si[be]; out_scores[(int64_t)c * topn + r] = bv; }
+        if (r < topn && lane == 0) { out_items[oslot * topn + r] = si[be]; out_scores[oslot * topn + r] = bv; }
         if (r == topn - 1) {
             // certificate: nothing outside the candidate lists can reach the N-th exact score
             const double bound = bound0 + 1e-12 * (scale + fabs(ub) + fabs(mu) + fabs(tau_d));
             const double reach = tau_d + bound + (biased ? (ub + mu) : 0.0);
-            if (!(bv > reach)) { ok = false; break; }
+            if (!(bv > reach)) {
+                // A second sweep that starts from tau0 collects every item whose exact score can reach bv, and its
+                // certificate then holds with room to spare (unless more than K' items crowd that band).
+                const double core_n = bv - (biased ? (ub + mu) : 0.0);
+                tau0 = __double2float_rd(ldexp(core_n - 2.5 * bound, eu + eQ));
+                margin_fail = tau0 == tau0 && fabsf(tau0) < INFINITY;
+                ok = false; break;
+            }
         }
         prev = bv;
         __syncwarp();
@@ -677,10 +708,13 @@ __global__ void __launch_bounds__(TC_RS_WARPS * 32) topn_tc_rescore_kernel(
         __syncwarp();
     }
     if (lane == 0) {
-        if (ok) out_counts[c] = topn;
-        else {
-            const int pos = atomicAdd(fail_count, 1);
-            fail_slots[pos] = c; fail_users[pos] = u;
+        if (ok) out_counts[oslot] = topn;
+        else if (margin_fail && rs_count) {
+            const int pos = atomicAdd(rs_count, 1);
+            rs_slots[pos] = (int32_t)oslot; rs_users[pos] = u; rs_tau0[pos] = tau0;
+        } else {
+            const int pos = atomicAdd(ex_count, 1);
+            ex_slots[pos] = (int32_t)oslot; ex_users[pos] = u;
         }
     }
 }
@@ -708,6 +742,85 @@ static int tc_make_map(lrk_handle_s* h, TcState* s, CUtensorMap* map, const void
     return LRK_OK;
 }
 
+#define TC_KEEP_DEFAULT(topn) std::min(TC_KEEP_MAX, std::max(16, (topn) + 6))
+
+// One pass: operand rows of the queried users -> tcgen05 sweep with fused selection -> exact fp64 re-score with
+// certificate.  Results go to out_*[slot_map ? slot_map[c] : c]; rows without a certificate are appended to the
+// rs_* (second sweep, only for the first pass) / ex_* (exact kernel) lists.
+static int tc_pass(lrk_handle_s* h, TcState* s, const int32_t* d_users, int32_t nq, const float* init_tau, const int32_t* slot_map,
+                   int topn, int exclude_train, int keep, int32_t* d_items, double* d_scores, int32_t* d_counts,
+                   int32_t* rs_slots, int32_t* rs_users, float* rs_tau0, int* rs_count,
+                   int32_t* ex_slots, int32_t* ex_users, int* ex_count, bool first_pass) {
+    cudaStream_t st = h->stream;
+    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    const int Kp = s->Kp;
+    const int num_kb = Kp / TC_KB;
+    // ---- work decomposition
+    const int total_tiles = lrk_ceil_div(h->I, TC_TILE_N);
+    const int m_tiles = lrk_ceil_div(nq, TC_ROWS);
+    int n_chunks = lrk_ceil_div(h->sm_count, m_tiles);
+    n_chunks = std::max(1, std::min(n_chunks, std::min(TC_MAX_CHUNKS, std::max(1, total_tiles / 16))));
+    const int tiles_per_chunk = lrk_ceil_div(total_tiles, n_chunks);
+    n_chunks = lrk_ceil_div(total_tiles, tiles_per_chunk);
+    const int64_t nq_pad = (int64_t)m_tiles * TC_ROWS;
+    const size_t tile_bytes = (size_t)TC_TILE_N * TC_KB * 2;
+    const size_t b_stage = (size_t)num_kb * tile_bytes;
+    int stages = (int)((227 * 1024 - 1024 - 256) / b_stage);
+    stages = std::max(2, std::min(stages, 8));
+    { const char* es = getenv("LRK_TC_STAGES"); if (es && atoi(es) >= 2) stages = std::min(stages, atoi(es)); }   // profiling probe
+    const size_t smem = 1024 + (size_t)stages * b_stage + TC_NBARS(stages) * 8 + 16;
+    // ---- scratch
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_aq = up(sizeof(__half) * (size_t)nq_pad * Kp), b_pn = up(sizeof(double2) * (size_t)nq_pad);
+    const size_t b_cs = up(sizeof(uint2) * (size_t)nq_pad * n_chunks * TC_CAP);
+    const size_t b_cc = up(sizeof(int32_t) * (size_t)nq_pad * n_chunks), b_ct = up(sizeof(float) * (size_t)nq_pad * n_chunks);
+    const size_t need = b_aq + b_pn + b_cs + b_cc + b_ct + 256;
+    if (s->work_bytes < need) {
+        if (s->work) { cudaFree(s->work); s->work = nullptr; s->work_bytes = 0; }
+        LRK_CUDA(h, cudaMalloc(&s->work, need));
+        s->work_bytes = need;
+    }
+    char* w = (char*)s->work;
+    __half* Aq = (__half*)w; w += b_aq;
+    double2* pstat = (double2*)w; w += b_pn;
+    uint2* cand = (uint2*)w; w += b_cs;
+    int32_t* ccnt = (int32_t*)w; w += b_cc;
+    float* ctau = (float*)w; w += b_ct;
+    if (nq_pad > nq) LRK_CUDA(h, cudaMemsetAsync(Aq + (size_t)nq * Kp, 0, sizeof(__half) * (size_t)(nq_pad - nq) * Kp, st));
+    LRK_CUDA(h, cudaMemsetAsync(ccnt, 0, sizeof(int32_t) * (size_t)nq_pad * n_chunks, st));
+    tc_build_users_kernel<<<lrk_ceil_div(nq, 8), 256, 0, st>>>(h->P64, biased, h->k, Kp, d_users, nq, Aq, pstat);
+    LRK_LAUNCH_CHECK(h);
+    CUtensorMap tmB;
+    int rc = tc_make_map(h, s, &tmB, s->Bq, Kp, h->I);
+    if (rc) return rc;
+    TcParams p;
+    memset(&p, 0, sizeof p);
+    p.nq = nq; p.I = h->I; p.n_chunks = n_chunks; p.tiles_per_chunk = tiles_per_chunk; p.total_tiles = total_tiles;
+    p.num_kb = num_kb; p.stages = stages; p.exclude_train = exclude_train ? 1 : 0;
+    p.keep = keep;
+    { const char* ek = getenv("LRK_TC_KEEP"); if (first_pass && ek && atoi(ek) >= topn + 1 && atoi(ek) <= TC_KEEP_MAX) p.keep = atoi(ek); }   // tuning probe
+    { const char* dbg = getenv("LRK_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    p.rowptr = h->d_rowptr; p.col = h->d_col; p.users = d_users; p.init_tau = init_tau;
+    p.cand = cand; p.cand_cnt = ccnt; p.cand_tau = ctau;
+    LRK_CUDA(h, cudaFuncSetAttribute(topn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(h->sm_count, m_tiles * n_chunks);
+    if (first_pass) LRK_CUDA(h, cudaEventRecord(s->ev[1], st));
+    topn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmB, Aq, p);
+    LRK_LAUNCH_CHECK(h);
+    if (first_pass) LRK_CUDA(h, cudaEventRecord(s->ev[2], st));
+    // ---- exact re-score + certificate
+    const double c_err = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (double)(Kp + 8) * ldexp(1.0, -22);
+    const double qabs_scaled_max = ldexp(std::max(s->qabs_max, s->bi_max), s->eQ);
+    const size_t rs_smem_bytes = (size_t)TC_RS_WARPS * n_chunks * TC_CAP * (sizeof(double) + sizeof(int32_t) + sizeof(float));
+    LRK_CUDA(h, cudaFuncSetAttribute(topn_tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes));
+    topn_tc_rescore_kernel<<<lrk_ceil_div(nq, TC_RS_WARPS), TC_RS_WARPS * 32, rs_smem_bytes, st>>>(
+        h->P64, h->Q64, h->bu64, h->bi64, h->mu, biased, h->k, d_users, nq, n_chunks, topn, cand, ccnt, ctau, pstat,
+        s->eQ, s->qnorm_max, s->bi_max, qabs_scaled_max, c_err, Kp, (unsigned int*)(s->d_stats + 3), slot_map, d_items, d_scores, d_counts,
+        rs_slots, rs_users, rs_tau0, rs_count, ex_slots, ex_users, ex_count);
+    LRK_LAUNCH_CHECK(h);
+    return LRK_OK;
+}
+
 static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int topn, int exclude_train,
                        int32_t* d_items, double* d_scores, int32_t* d_counts) {
     TcState* s = tc_state(h);
@@ -715,7 +828,7 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
     const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
     const int Kp = tc_kp(h);
     const int num_kb = Kp / TC_KB;
-    if (num_kb > 2 || topn > TC_KEEP / 2)
+    if (num_kb > 2 || topn > 16)
         return lrk_fail(h, LRK_ERR_INVALID, "lrk_topn", "tensor-core path supports k (+2 for BiasedMF) <= 128 and topn <= 16", __FILE__, __LINE__);
     for (cudaEvent_t& ev : s->ev) if (!ev) LRK_CUDA(h, cudaEventCreate(&ev));
     LRK_CUDA(h, cudaEventRecord(s->ev[0], st));
@@ -749,102 +862,66 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
         h->topn_fast_users = 0; h->topn_fallback_users = nq;
         return LRK_OK;
     }
-    // ---- work decomposition
-    const int total_tiles = lrk_ceil_div(h->I, TC_TILE_N);
-    const int m_tiles = lrk_ceil_div(nq, TC_TILE_M * TC_UT);
-    int n_chunks = lrk_ceil_div(h->sm_count, m_tiles);
-    n_chunks = std::max(1, std::min(n_chunks, std::min(TC_MAX_CHUNKS, std::max(1, total_tiles / 16))));
-    const int tiles_per_chunk = lrk_ceil_div(total_tiles, n_chunks);
-    n_chunks = lrk_ceil_div(total_tiles, tiles_per_chunk);
-    const int64_t nq_pad = (int64_t)m_tiles * TC_TILE_M * TC_UT;
-    const size_t tile_bytes = (size_t)TC_TILE_M * TC_KB * 2;
-    const size_t b_stage = (size_t)num_kb * tile_bytes;
-    int stages = (int)((226 * 1024 - 1024 - 256) / b_stage);
-    stages = std::max(2, std::min(stages, 8));
-    { const char* es = getenv("LRK_TC_STAGES"); if (es && atoi(es) >= 2) stages = std::min(stages, atoi(es)); }   // profiling probe
-    const size_t smem = 1024 + (size_t)stages * b_stage + TC_NBARS(stages) * 8 + 16;
-    // ---- query operand + scratch
-    int32_t *fi = nullptr, *fc = nullptr; double* fs = nullptr;
-    int rc = LRK_OK;
-    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t b_aq = up(sizeof(__half) * (size_t)nq_pad * Kp), b_pn = up(sizeof(double2) * (size_t)nq_pad);
-    const size_t b_cs = up(sizeof(uint2) * (size_t)nq_pad * n_chunks * TC_CAP);
-    const size_t b_cc = up(sizeof(int32_t) * (size_t)nq_pad * n_chunks), b_ct = up(sizeof(float) * (size_t)nq_pad * n_chunks);
-    const size_t b_fl = up(sizeof(int32_t) * (size_t)nq);
-    const size_t need = b_aq + b_pn + b_cs + b_cc + b_ct + 2 * b_fl + 256;
-    if (s->work_bytes < need) {
-        if (s->work) { cudaFree(s->work); s->work = nullptr; s->work_bytes = 0; }
-        LRK_CUDA(h, cudaMalloc(&s->work, need));
-        s->work_bytes = need;
-    }
-    char* w = (char*)s->work;
-    __half* Aq = (__half*)w; w += b_aq;
-    double2* pstat = (double2*)w; w += b_pn;
-    uint2* cand = (uint2*)w; w += b_cs;
-    int32_t* ccnt = (int32_t*)w; w += b_cc;
-    float* ctau = (float*)w; w += b_ct;
-    int32_t* fail_slots = (int32_t*)w; w += b_fl;
-    int32_t* fail_users = (int32_t*)w; w += b_fl;
-    int* fail_count = (int*)w;
-    cudaError_t e = cudaMemsetAsync(fail_count, 0, sizeof(int), st);
-    if (e == cudaSuccess && nq_pad > nq) e = cudaMemsetAsync(Aq + (size_t)nq * Kp, 0, sizeof(__half) * (size_t)(nq_pad - nq) * Kp, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ccnt, 0, sizeof(int32_t) * (size_t)nq_pad * n_chunks, st);
-    int nfail = 0;
-    do {
-        if (e != cudaSuccess) break;
-        tc_build_users_kernel<<<lrk_ceil_div(nq, 8), 256, 0, st>>>(h->P64, biased, h->k, Kp, d_users, nq, Aq, pstat);
-        h->launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) break;
-        CUtensorMap tmB;
-        if ((rc = tc_make_map(h, s, &tmB, s->Bq, Kp, h->I))) break;
-        TcParams p;
-        memset(&p, 0, sizeof p);
-        p.nq = nq; p.I = h->I; p.n_chunks = n_chunks; p.tiles_per_chunk = tiles_per_chunk; p.total_tiles = total_tiles;
-        p.num_kb = num_kb; p.stages = stages; p.exclude_train = exclude_train ? 1 : 0;
-        { const char* dbg = getenv("LRK_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-        p.rowptr = h->d_rowptr; p.col = h->d_col; p.users = d_users;
-        p.cand = cand; p.cand_cnt = ccnt; p.cand_tau = ctau;
-        if ((e = cudaFuncSetAttribute(topn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) break;
-        const int grid = std::min(h->sm_count, m_tiles * n_chunks);
-        if ((e = cudaEventRecord(s->ev[1], st)) != cudaSuccess) break;
-        topn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmB, Aq, p);
-        h->launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) break;
-        if ((e = cudaEventRecord(s->ev[2], st)) != cudaSuccess) break;
-        // ---- exact re-score + certificate
-        const double c_err = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (double)(Kp + 8) * ldexp(1.0, -22);
-        const double qabs_scaled_max = ldexp(std::max(s->qabs_max, s->bi_max), s->eQ);
-        const size_t rs_smem_bytes = (size_t)TC_RS_WARPS * n_chunks * TC_CAP * (sizeof(double) + sizeof(int32_t) + sizeof(float));
-        if ((e = cudaMemsetAsync(s->d_stats + 3, 0, 8, st)) != cudaSuccess) break;
-        if ((e = cudaFuncSetAttribute(topn_tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes)) != cudaSuccess) break;
-        topn_tc_rescore_kernel<<<lrk_ceil_div(nq, TC_RS_WARPS), TC_RS_WARPS * 32, rs_smem_bytes, st>>>(
-            h->P64, h->Q64, h->bu64, h->bi64, h->mu, biased, h->k, d_users, nq, n_chunks, topn, cand, ccnt, ctau, pstat,
-            s->eQ, s->qnorm_max, s->bi_max, qabs_scaled_max, c_err, Kp, (unsigned int*)(s->d_stats + 3), d_items, d_scores, d_counts, fail_slots, fail_users, fail_count);
-        h->launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) break;
-        if ((e = cudaEventRecord(s->ev[3], st)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(&nfail, fail_count, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(&h->topn_err_ratio, s->d_stats + 3, sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
-        if (nfail > 0) {
-            // rows without a certificate: item-parallel exact fp64 path (heap replay only for exact ties)
-            if ((e = cudaMalloc((void**)&fi, sizeof(int32_t) * (size_t)nfail * topn)) != cudaSuccess) break;
-            if ((e = cudaMalloc((void**)&fs, sizeof(double) * (size_t)nfail * topn)) != cudaSuccess) break;
-            if ((e = cudaMalloc((void**)&fc, sizeof(int32_t) * (size_t)nfail)) != cudaSuccess) break;
-            if ((rc = topn_exact_parallel_launch(h, fail_users, nfail, topn, exclude_train, fi, fs, fc))) break;
-            topn_scatter_kernel<<<lrk_ceil_div((int64_t)nfail * topn, 256), 256, 0, st>>>(fail_slots, nfail, topn, fi, fs, fc,
-                                                                                       d_items, d_scores, d_counts);
-            h->launches++;
-            if ((e = cudaGetLastError()) != cudaSuccess) break;
-            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+    // ---- fail lists of the call (outside the per-pass scratch, which a second pass may regrow)
+    {
+        const size_t need_l = sizeof(int32_t) * 5 * (size_t)nq + 64;
+        if (s->lists_bytes < need_l) {
+            if (s->lists) { cudaFree(s->lists); s->lists = nullptr; s->lists_bytes = 0; }
+            LRK_CUDA(h, cudaMalloc(&s->lists, need_l));
+            s->lists_bytes = need_l;
         }
-    } while (0);
-    if (e == cudaSuccess && rc == LRK_OK) e = cudaEventRecord(s->ev[4], st);
-    if (e == cudaSuccess && rc == LRK_OK) e = cudaStreamSynchronize(st);
-    cudaFree(fi); cudaFree(fs); cudaFree(fc);
+    }
+    int* counters = (int*)s->lists;                                   // [0] second-sweep rows, [1] exact-kernel rows
+    int32_t* rs_slots = (int32_t*)((char*)s->lists + 64);
+    int32_t* rs_users = rs_slots + nq;
+    float* rs_tau0 = (float*)(rs_users + nq);
+    int32_t* ex_slots = (int32_t*)(rs_tau0 + nq);
+    int32_t* ex_users = ex_slots + nq;
+    LRK_CUDA(h, cudaMemsetAsync(counters, 0, 64, st));
+    LRK_CUDA(h, cudaMemsetAsync(s->d_stats + 3, 0, 8, st));
+    int cnts[2] = {0, 0};
+    // pass 1: every queried row from tau = -inf
+    int rc = tc_pass(h, s, d_users, nq, nullptr, nullptr, topn, exclude_train, TC_KEEP_DEFAULT(topn), d_items, d_scores, d_counts,
+                     rs_slots, rs_users, rs_tau0, counters, ex_slots, ex_users, counters + 1, true);
     if (rc) return rc;
-    LRK_CUDA(h, e);
+    LRK_CUDA(h, cudaMemcpyAsync(cnts, counters, sizeof cnts, cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    const int n_resweep = cnts[0];
+    if (n_resweep > 0) {
+        // pass 2: rows whose margin was too thin, from the threshold their first result implies, widest K'
+        rc = tc_pass(h, s, rs_users, n_resweep, rs_tau0, rs_slots, topn, exclude_train, TC_KEEP_MAX, d_items, d_scores, d_counts,
+                     nullptr, nullptr, nullptr, nullptr, ex_slots, ex_users, counters + 1, false);
+        if (rc) return rc;
+        LRK_CUDA(h, cudaMemcpyAsync(cnts, counters, sizeof cnts, cudaMemcpyDeviceToHost, st));
+        LRK_CUDA(h, cudaStreamSynchronize(st));
+    }
+    LRK_CUDA(h, cudaEventRecord(s->ev[3], st));
+    LRK_CUDA(h, cudaMemcpyAsync(&h->topn_err_ratio, s->d_stats + 3, sizeof(float), cudaMemcpyDeviceToHost, st));
+    const int nfail = cnts[1];
+    if (nfail > 0) {
+        // rows still without a certificate (exact ties, fewer than N candidates, crowded bands): exact fp64 path
+        int32_t *fi = nullptr, *fc = nullptr; double* fs = nullptr;
+        cudaError_t e = cudaMalloc((void**)&fi, sizeof(int32_t) * (size_t)nfail * topn);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&fs, sizeof(double) * (size_t)nfail * topn);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&fc, sizeof(int32_t) * (size_t)nfail);
+        if (e == cudaSuccess) {
+            rc = topn_exact_parallel_launch(h, ex_users, nfail, topn, exclude_train, fi, fs, fc);
+            if (rc == LRK_OK) {
+                topn_scatter_kernel<<<lrk_ceil_div((int64_t)nfail * topn, 256), 256, 0, st>>>(ex_slots, nfail, topn, fi, fs, fc,
+                                                                                           d_items, d_scores, d_counts);
+                h->launches++;
+                e = cudaGetLastError();
+            }
+        }
+        if (e == cudaSuccess && rc == LRK_OK) e = cudaStreamSynchronize(st);
+        cudaFree(fi); cudaFree(fs); cudaFree(fc);
+        if (rc) return rc;
+        LRK_CUDA(h, e);
+    }
+    LRK_CUDA(h, cudaEventRecord(s->ev[4], st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
     for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&h->topn_phase_ms[i], s->ev[i], s->ev[i + 1]);
+    h->topn_resweep_users = n_resweep;
     h->topn_fast_users = nq - nfail;
     h->topn_fallback_users = nfail;
     return LRK_OK;
