@@ -15,6 +15,10 @@ loop over all ratings).  metric = MF SGD rating-updates/s.
 N>1 (torchrun, one process per GPU): every rank owns one ML-20M-shaped user shard over the same item
 catalogue (N x 20 000 263 ratings in total), trained with DSGD strata, item blocks rotated over NCCL;
 value = ratings processed by all ranks / max-over-ranks time ("scaling": "weak").
+The same line carries the second half of BASELINE.json's metric in "topn": top-10 users scored/s on
+configs[4] (1 048 576 users x 1 048 576 items, k=128, sharded by user block over the N ranks, no
+collective), measured through lrk_topn with pinned host result buffers (D2H inside the timed region),
+with the tensor-pipe roofline of topn_tc_kernel from CUDA events on its stream.
 """
 import argparse
 import ctypes
@@ -360,11 +364,97 @@ def run_ours(args):
             log("best-effort cpu leg failed:", e)
 
     h.close()
+    if not args.no_topn:
+        tn = topn_leg(args, capi, torch, dist, rank, world, local, dev)
+        if rank == 0:
+            line["topn"] = tn
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+TOPN_USERS, TOPN_ITEMS, TOPN_K, TOPN_N, TOPN_TRAIN = 1 << 20, 1 << 20, 128, 10, 32
+
+
+def topn_leg(args, capi, torch, dist, rank, world, local, dev):
+    """top-10 users scored/s on configs[4]; users are sharded by contiguous block over the ranks (strong scaling,
+    no collective: every rank holds the full item matrix).  Returns the "topn" object (rank 0) or None."""
+    U, I, k, N = TOPN_USERS, TOPN_ITEMS, TOPN_K, TOPN_N
+    lo, hi = rank * U // world, (rank + 1) * U // world
+    nu = hi - lo
+    rng_q = np.random.default_rng(0x4C520005)                       # item side identical on every rank
+    Q = rng_q.normal(0, 0.1, (I, k)).astype(np.float32).astype(np.float64)
+    rng = np.random.default_rng([0x4C520005, rank, world])
+    P = rng.normal(0, 0.1, (nu, k)).astype(np.float32).astype(np.float64)
+    # train mask: one random item out of each of 32 equal strata of the catalogue -> distinct, ascending
+    edges = np.linspace(0, I, TOPN_TRAIN + 1).astype(np.int64)
+    cols = (edges[:-1][None, :] + (rng.random((nu, TOPN_TRAIN)) * np.diff(edges)[None, :]).astype(np.int64)).astype(np.int32)
+    rowptr = np.arange(nu + 1, dtype=np.int64) * TOPN_TRAIN
+    col = np.ascontiguousarray(cols.reshape(-1))
+    val = np.ones(col.shape[0], np.float64)
+    h = capi.Handle(capi.MODEL_BPR, k, device=local)
+    h.set_train_csr(nu, I, rowptr, col, val)
+    h.set_factors(P, Q)
+    items, p1 = pinned_array(capi, (nu, N), np.int32)
+    scores, p2 = pinned_array(capi, (nu, N), np.float64)
+    counts, p3 = pinned_array(capi, (nu,), np.int32)
+    h.topn(N, nq=min(nu, 4096))                                     # builds the item operand (cached afterwards)
+    h.topn(N, out=(items, scores, counts))                          # warm-up of the full call
+    steps = max(2, min(args.steps, 3))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall, sweep, dev_ms, stats = [], [], [], None
+    for s in range(steps):
+        t0 = time.perf_counter()
+        h.topn(N, out=(items, scores, counts))
+        wall.append(time.perf_counter() - t0)
+        stats = h.topn_stats()
+        sweep.append(stats["phase_ms"]["sweep"]); dev_ms.append(stats["ms"])
+    t = torch.tensor([float(np.sum(wall))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_s = float(t.item())
+    out = None
+    if rank == 0:
+        peaks, which = measured_peaks()
+        kms = float(np.mean(sweep))
+        flop = 2.0 * nu * I * k                                     # this rank's launch
+        tf = flop / (kms * 1e-3) / 1e12
+        # parity spot check against the oracle (64 users, the checker only)
+        from oracle import oracle as O
+        tr = O.Csr(nu, I, rowptr, col, val)
+        sample = np.linspace(0, nu - 1, 64).astype(np.int32)
+        t0 = time.perf_counter()
+        oi, os_, oc = O.recommend_rank(O.BPR, nu, I, k, P, Q, None, None, 0.0, tr, N, users=sample)
+        cpu_dt = time.perf_counter() - t0
+        ok = bool(np.array_equal(items[sample], oi) and np.array_equal(scores[sample].view(np.int64), os_.view(np.int64))
+                  and np.array_equal(counts[sample], oc))
+        out = {"metric": "top-%d users scored/s" % N, "value": U * steps / total_s, "unit": "users/s", "n_gpus": world, "steps": steps,
+               "scaling": "strong", "dtype": "f16 sweep (f32 accumulate) + f64 exact re-score",
+               "config": {"workload": "top-%d over %d users x %d items, k=%d, %d train items/user masked; users sharded by block over %d rank(s)"
+                                      % (N, U, I, k, TOPN_TRAIN, world)},
+               "e2e": {"value": U * steps / total_s, "unit": "users/s", "h2d_bytes_per_step": 0,
+                       "d2h_bytes_per_step": int(items.nbytes + scores.nbytes + counts.nbytes),
+                       "step": "one lrk_topn call per rank (factors resident, result lists copied into pinned host buffers inside the timed region)"},
+               "ms_per_step": total_s / steps * 1e3, "device_ms": float(np.mean(dev_ms)), "phase_ms": stats["phase_ms"],
+               "certificate": {"fallback_users": stats["fallback_users"], "resweep_users": stats["resweep_users"],
+                               "sweep_error_over_bound": stats["sweep_error_over_bound"]},
+               "roofline": {"bound": "tensor", "kernel": "topn_tc_kernel", "kernel_ms": kms, "achieved": tf, "peak": peaks["bf16_tflops"],
+                            "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
+                            "frac_of_sustained": tf / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                            "peak_source": which, "flop_per_launch": flop, "traffic": None},
+               "parity": {"users_checked": 64, "bit_identical": ok},
+               "cpu_baseline": {"value": 64 / cpu_dt, "unit": "users/s", "cores": int(O.lib().lro_max_threads()), "kind": "port",
+                                "sample": "64 users against the full catalogue, oracle restatement of recommendRank, OpenMP over users"}}
+    h.close()
+    L = capi.load()
+    for p in (p1, p2, p3):
+        L.lrk_host_free(p)
+    return out
 
 
 def main():
@@ -375,6 +465,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-topn", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

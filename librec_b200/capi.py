@@ -194,15 +194,20 @@ class Handle:
                                       float(max_rate), _ptr(pred), C.byref(rmse), C.byref(mae)), self._h)
         return (rmse.value, mae.value, pred) if want_pred else (rmse.value, mae.value)
 
-    def topn(self, topn, users=None, nq=None, exclude_train=True):
+    def topn(self, topn, users=None, nq=None, exclude_train=True, out=None):
+        """out = (items int32[nq,topn], scores float64[nq,topn], counts int32[nq]) reuses caller buffers (e.g. pinned)"""
         if users is not None:
             users = np.ascontiguousarray(users, np.int32)
             nq = users.shape[0]
         elif nq is None:
             nq = self.U
-        items = np.empty((nq, topn), np.int32)
-        scores = np.empty((nq, topn), np.float64)
-        counts = np.empty(nq, np.int32)
+        if out is not None:
+            items, scores, counts = out
+            assert items.shape == (nq, topn) and scores.shape == (nq, topn) and counts.shape == (nq,)
+        else:
+            items = np.empty((nq, topn), np.int32)
+            scores = np.empty((nq, topn), np.float64)
+            counts = np.empty(nq, np.int32)
         _check(load().lrk_topn(self._h, _ptr(users), nq, topn, int(bool(exclude_train)), items, scores, counts), self._h)
         return items, scores, counts
 

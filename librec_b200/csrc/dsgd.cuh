@@ -80,12 +80,16 @@ static inline void dsgd_item_bounds(const int64_t* item_count, int32_t I, int wo
 struct DsgdState {
     std::vector<int32_t> bounds;        // world+1 item block bounds
     std::vector<int64_t> seg_off;       // world+1 offsets of the COO segments
+    std::vector<double> seg_hot_share;  // per segment: largest share one item has of its ratings
     int32_t max_blk = 0;                // rows of the largest item block
     size_t buf_floats = 0;              // floats per rotating buffer: max_blk*ld + max_blk
     float* qbuf[2] = {nullptr, nullptr};
     int cur = 0;                        // which buffer holds the current block
     int cur_block = 0;                  // item block id currently held
     int32_t* d_bounds = nullptr;
+    // LRK_DSGD_TRACE=1: events around every sub-epoch kernel / ring exchange of the last epoch
+    std::vector<cudaEvent_t> trace_ev;
+    int trace = -1;
 };
 
 __global__ void item_hist_kernel(const int32_t* __restrict__ col, int64_t nnz, unsigned long long* __restrict__ cnt) {
@@ -114,7 +118,7 @@ __global__ void dsgd_gather_kernel(const uint32_t* __restrict__ perm, const uint
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nnz) return;
     const uint32_t e = perm[t];
-    const int b = (int)(keys_sorted[t] >> 32);
+    const int b = (int)(keys_sorted[t] >> 58);
     su[t] = row_of[e]; si[t] = col[e] - bounds[b]; sr[t] = (float)val[e];
 }
 __global__ void dsgd_pack_block_kernel(const float* __restrict__ Q, const float* __restrict__ bi, int32_t first, int32_t rows,
@@ -207,28 +211,39 @@ static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64
     for (int b = 0; b < world; ++b) s->max_blk = std::max(s->max_blk, s->bounds[b + 1] - s->bounds[b]);
     LRK_CUDA(h, cudaMemcpyAsync(s->d_bounds, s->bounds.data(), sizeof(int32_t) * ((size_t)world + 1), cudaMemcpyHostToDevice, st));
 
-    // bucket + shuffle the local ratings
+    // bucket by item block; inside a block: item-run tiles, then the shuffled rest (staging.cuh, stage_tile_keys)
     s->seg_off.assign((size_t)world + 1, 0);
     if (nnz > 0) {
         double* d_val = nullptr; int32_t* row_of = nullptr; uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *idx = nullptr, *perm = nullptr;
         void* tmp = nullptr; size_t tmp_bytes = 0;
-        std::vector<uint64_t> hk;
+        uint32_t* w32 = nullptr;
+        TileKeyWork w;
+        memset(&w, 0, sizeof w);
         e = cudaMalloc((void**)&d_val, sizeof(double) * (size_t)nnz);
         if (e == cudaSuccess) e = cudaMalloc((void**)&row_of, sizeof(int32_t) * (size_t)nnz);
         if (e == cudaSuccess) e = cudaMalloc((void**)&keys, sizeof(uint64_t) * (size_t)nnz);
         if (e == cudaSuccess) e = cudaMalloc((void**)&keys2, sizeof(uint64_t) * (size_t)nnz);
         if (e == cudaSuccess) e = cudaMalloc((void**)&idx, sizeof(uint32_t) * (size_t)nnz);
         if (e == cudaSuccess) e = cudaMalloc((void**)&perm, sizeof(uint32_t) * (size_t)nnz);
-        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, perm, (int)nnz, 0, 40, st);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&w32, sizeof(uint32_t) * (4 * (size_t)nnz + 4 * (size_t)I + 64));
+        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, perm, (int)nnz, 0, 64, st);
+        tmp_bytes = std::max(tmp_bytes, stage_tile_keys_tmp_bytes(I, nnz));
         if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) {
-            dsgd_keys_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(h->d_rowptr, U, h->d_col, nnz, s->d_bounds, world, h->cfg.seed + 977u * h->rank, row_of, keys, idx);
+            w.k32 = w32; w.v32 = w32 + nnz; w.k32_out = w32 + 2 * (size_t)nnz; w.sorted_e = w32 + 3 * (size_t)nnz;
+            w.deg = w32 + 4 * (size_t)nnz; w.item_start = w.deg + I; w.runs = w.item_start + I; w.run_base = w.runs + I;
+            w.max_deg = w.run_base + I;
+            w.tmp = tmp; w.tmp_bytes = tmp_bytes;
+            coo_rows_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(h->d_rowptr, U, nnz, row_of);
             h->launches++;
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, perm, (int)nnz, 0, 40, st);
-        if (e == cudaSuccess) {
+        int rc_k = LRK_OK;
+        if (e == cudaSuccess) rc_k = stage_tile_keys(h, h->d_col, I, nnz, s->d_bounds, world, h->cfg.seed + 977u * h->rank, w, keys, idx);
+        size_t tb = tmp_bytes;
+        if (e == cudaSuccess && rc_k == LRK_OK) e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, idx, perm, (int)nnz, 0, 64, st);
+        if (e == cudaSuccess && rc_k == LRK_OK) {
             dsgd_gather_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(perm, keys2, row_of, h->d_col, d_val, s->d_bounds, nnz, h->d_su, h->d_si, h->d_sr);
             h->launches++;
             e = cudaGetLastError();
@@ -243,7 +258,12 @@ static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64
             local_cnt[(size_t)b]++;
         }
         for (int b = 0; b < world; ++b) s->seg_off[(size_t)b + 1] = s->seg_off[(size_t)b] + local_cnt[(size_t)b];
-        cudaFree(d_val); cudaFree(row_of); cudaFree(keys); cudaFree(keys2); cudaFree(idx); cudaFree(perm); cudaFree(tmp);
+        uint32_t md[64] = {0};
+        if (e == cudaSuccess && rc_k == LRK_OK) e = cudaMemcpy(md, w.max_deg, sizeof(uint32_t) * 64, cudaMemcpyDeviceToHost);
+        s->seg_hot_share.assign((size_t)world, 0.0);
+        for (int b = 0; b < world; ++b) if (local_cnt[(size_t)b] > 0) s->seg_hot_share[(size_t)b] = (double)md[b] / (double)local_cnt[(size_t)b];
+        cudaFree(d_val); cudaFree(row_of); cudaFree(keys); cudaFree(keys2); cudaFree(idx); cudaFree(perm); cudaFree(tmp); cudaFree(w32);
+        if (rc_k) return rc_k;
         LRK_CUDA(h, e);
     }
     s->buf_floats = (size_t)s->max_blk * h->ld + (size_t)s->max_blk;
@@ -303,6 +323,12 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     const int world = h->world, rank = h->rank;
     LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
     LRK_CUDA(h, cudaEventRecord(h->ev0, st));
+    if (s->trace < 0) { const char* t = getenv("LRK_DSGD_TRACE"); s->trace = t && atoi(t) ? 1 : 0; }
+    if (s->trace && s->trace_ev.empty()) {
+        s->trace_ev.resize((size_t)2 * world + 1);
+        for (auto& ev : s->trace_ev) LRK_CUDA(h, cudaEventCreate(&ev));
+    }
+    if (s->trace) LRK_CUDA(h, cudaEventRecord(s->trace_ev[0], st));
     for (int sub = 0; sub < world; ++sub) {
         const int b = dsgd_block_at(rank, world, sub);
         float* buf = s->qbuf[s->cur];
@@ -314,9 +340,11 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
             sp.P = h->P32; sp.Q = buf; sp.bu = h->bu32; sp.bi = buf + (size_t)s->max_blk * h->ld;
             sp.mu = (float)h->mu; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i; sp.reg_b = (float)reg_b;
             sp.loss = h->d_loss; sp.ld = h->ld; sp.epoch = (uint32_t)epoch_idx;
+            sp.hot_share = (size_t)b < s->seg_hot_share.size() ? s->seg_hot_share[(size_t)b] : 0.0;
             int rc = sgd_launch(h, sp);
             if (rc) return rc;
         }
+        if (s->trace) LRK_CUDA(h, cudaEventRecord(s->trace_ev[(size_t)2 * sub + 1], st));
         if (world > 1) {
             float* nxt = s->qbuf[s->cur ^ 1];
             LRK_NCCL(h, n->GroupStart());
@@ -325,6 +353,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
             LRK_NCCL(h, n->GroupEnd());
             s->cur ^= 1;
         }
+        if (s->trace) LRK_CUDA(h, cudaEventRecord(s->trace_ev[(size_t)2 * sub + 2], st));
         s->cur_block = dsgd_block_at(rank, world, sub + 1);
     }
     LRK_NCCL(h, n->AllReduce(h->d_loss, h->d_loss, 1, ncclFloat64, ncclSum, (ncclComm_t)h->comm, st));
@@ -333,6 +362,19 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
     LRK_CUDA(h, cudaStreamSynchronize(st));
     LRK_CUDA(h, cudaEventElapsedTime(&h->last_epoch_ms, h->ev0, h->ev1));
+    if (s->trace) {
+        std::string line = "[dsgd rank " + std::to_string(rank) + " epoch " + std::to_string(epoch_idx) + "]";
+        for (int sub = 0; sub < world; ++sub) {
+            float k_ms = 0.f, x_ms = 0.f;
+            cudaEventElapsedTime(&k_ms, s->trace_ev[(size_t)2 * sub], s->trace_ev[(size_t)2 * sub + 1]);
+            cudaEventElapsedTime(&x_ms, s->trace_ev[(size_t)2 * sub + 1], s->trace_ev[(size_t)2 * sub + 2]);
+            char buf[96];
+            snprintf(buf, sizeof buf, " sub%d: kernel %.3f ms (%lld ratings) exchange %.3f ms;", sub, k_ms,
+                     (long long)(s->seg_off[(size_t)dsgd_block_at(rank, world, sub) + 1] - s->seg_off[(size_t)dsgd_block_at(rank, world, sub)]), x_ms);
+            line += buf;
+        }
+        fprintf(stderr, "%s total %.3f ms\n", line.c_str(), h->last_epoch_ms);
+    }
     const double loss = 0.5 * h->h_loss[0];
     if (loss_out) *loss_out = loss;
     if (std::isnan(loss) || std::isinf(loss))

@@ -234,6 +234,7 @@ static void fill_sgd_params(lrk_handle_s* h, SgdParams& sp, float lr, float reg_
     sp.P = h->P32; sp.Q = h->Q32; sp.bu = h->bu32; sp.bi = h->bi32;
     sp.mu = (float)h->mu; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i; sp.reg_b = (float)reg_b;
     sp.loss = h->d_loss; sp.ld = h->ld;
+    sp.hot_share = h->cfg.model == LRK_MODEL_BPR ? 0.0 : h->hot_share;
     sp.rowptr = h->d_rowptr; sp.col = h->d_col; sp.U = h->U; sp.I = h->I;
     sp.seed_lo = (uint32_t)h->cfg.seed; sp.seed_hi = (uint32_t)(h->cfg.seed >> 32); sp.epoch = (uint32_t)epoch_idx;
 }

@@ -15,6 +15,18 @@
 // ratings); factor rows are gathered as one float4 per lane through L2 (ld.global.cg -- L1 is
 // not coherent with the REDs of other SMs), next step's rows are prefetched while the current
 // step is reduced with warp shuffles.
+//
+// Item-run tiles: popular items receive most of the updates (Zipf), and the L2 atomic units serialise
+// REDs to one address, so hot item rows bound the epoch long before HBM does -- and the more so under
+// DSGD, where a sub-epoch concentrates every SM on 1/G of the catalogue (measured: 5.8 G -> 3.3 G
+// updates/s per GPU at 4 strata).  Staging therefore groups the ratings of items with >= 64 ratings into
+// runs of 32 (staging.cuh); a warp that finds all 32 items of its tile equal reads the item row once per
+// 8 ratings, accumulates their item-side deltas in registers and issues ONE vector RED for them (an
+// 8-rating mini-batch for that item; the user side is untouched): 8x fewer row reads and REDs.
+//
+// Stability: B ratings of one item in flight at once act like one step of size lr*B on its bias
+// (e' = (1 - lr*B) e), so lr*B must stay well below 2.  With the hottest item holding a share s of the
+// launch, B = s * (ratings in flight): sgd_grid_for caps the grid at lr * s * in-flight <= 1.
 #pragma once
 #include "lrk_common.cuh"
 
@@ -30,6 +42,10 @@ struct SgdParams {
     float mu, lr, reg_u, reg_i, reg_b;
     double* loss;
     int ld;
+    // tile t of the epoch is read from stream position (t * tile_mul) % ntiles: the staged stream is
+    // [item-run tiles | shuffled remainder], the multiplicative walk interleaves the two evenly in time
+    int64_t tile_mul;
+    double hot_share;       // largest share one item has of this launch's ratings (0 = unknown): stability cap of the grid
     // BPR only
     const int64_t* __restrict__ rowptr;
     const int32_t* __restrict__ col;
@@ -103,7 +119,7 @@ __global__ void __launch_bounds__(256) sgd_rating_epoch_kernel(SgdParams p) {
     int32_t u_n = -1, i_n = 0;
     float r_n = 0.f;
     if (tile < ntiles) {
-        const int64_t e = (tile << 5) + lane;
+        const int64_t e = ((int64_t)(((unsigned long long)tile * (unsigned long long)p.tile_mul) % (unsigned long long)ntiles) << 5) + lane;
         if (e < p.n) { u_n = __ldcs(p.su + e); i_n = __ldcs(p.si + e); r_n = __ldcs(p.sr + e); }
     }
     for (; tile < ntiles; tile += nwarps) {
@@ -113,11 +129,96 @@ __global__ void __launch_bounds__(256) sgd_rating_epoch_kernel(SgdParams p) {
             const int64_t tn = tile + nwarps;
             u_n = -1; i_n = 0; r_n = 0.f;
             if (tn < ntiles) {
-                const int64_t e = (tn << 5) + lane;
+                const int64_t e = ((int64_t)(((unsigned long long)tn * (unsigned long long)p.tile_mul) % (unsigned long long)ntiles) << 5) + lane;
                 if (e < p.n) { u_n = __ldcs(p.su + e); i_n = __ldcs(p.si + e); r_n = __ldcs(p.sr + e); }
             }
         }
         float loss_f = 0.f;
+        const int32_t i0 = __shfl_sync(0xffffffffu, i_l, 0);
+        if (__all_sync(0xffffffffu, u_l >= 0 && i_l == i0)) {
+            // ---- item-run tile: one item, 32 distinct users.  The item row is re-read and its accumulated delta
+            // flushed every HOT_CHUNK steps (8 ratings), which bounds the staleness a warp adds for its item.
+            constexpr int HOT_CHUNK = (STEPS >= 4) ? STEPS / 4 : 1;
+            float4 pn[V];
+            float bun = 0.f;
+            int32_t un = __shfl_sync(0xffffffffu, u_l, grp);
+            float rn = __shfl_sync(0xffffffffu, r_l, grp);
+#pragma unroll
+            for (int v = 0; v < V; ++v) pn[v] = ldcg4(p.P + (int64_t)un * p.ld + (v * G + sub) * 4);
+            if (BIASED && sub == 0) bun = __ldcg(p.bu + un);
+#pragma unroll 1
+            for (int c0 = 0; c0 < STEPS; c0 += HOT_CHUNK) {
+                float4 q[V], dq[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    q[v] = ldcg4(p.Q + (int64_t)i0 * p.ld + (v * G + sub) * 4);
+                    dq[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const float bi0 = BIASED ? __ldcg(p.bi + i0) : 0.f;
+                float dbi = 0.f;
+#pragma unroll
+                for (int sc = 0; sc < HOT_CHUNK; ++sc) {
+                    const int s = c0 + sc;
+                    float4 pc[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) pc[v] = pn[v];
+                    const float buc = bun, rc = rn;
+                    const int32_t uc = un;
+                    if (s + 1 < STEPS) {
+                        const int src = (s + 1) * RPS + grp;
+                        un = __shfl_sync(0xffffffffu, u_l, src);
+                        rn = __shfl_sync(0xffffffffu, r_l, src);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) pn[v] = ldcg4(p.P + (int64_t)un * p.ld + (v * G + sub) * 4);
+                        if (BIASED && sub == 0) bun = __ldcg(p.bu + un);
+                    }
+                    float part = 0.f;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) part += dot4(pc[v], q[v]);
+                    float pred = group_sum<G>(part);
+                    if (BIASED) pred += __shfl_sync(0xffffffffu, buc, grp * G) + bi0 + mu;
+                    const float err = rc - pred;
+                    float reg_acc = 0.f;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const float4 a = pc[v], b = q[v];
+                        float4 dp;
+                        dp.x = lr * (err * b.x - reg_u * a.x); dq[v].x += lr * (err * a.x - reg_i * b.x);
+                        dp.y = lr * (err * b.y - reg_u * a.y); dq[v].y += lr * (err * a.y - reg_i * b.y);
+                        dp.z = lr * (err * b.z - reg_u * a.z); dq[v].z += lr * (err * a.z - reg_i * b.z);
+                        dp.w = lr * (err * b.w - reg_u * a.w); dq[v].w += lr * (err * a.w - reg_i * b.w);
+                        apply4<ATOMIC>(p.P + (int64_t)uc * p.ld + (v * G + sub) * 4, a, dp);
+                        reg_acc += reg_u * dot4(a, a) + reg_i * dot4(b, b);
+                    }
+                    if (sub == 0) {
+                        reg_acc += err * err;
+                        if (BIASED) {
+                            apply1<ATOMIC>(p.bu + uc, buc, lr * (err - reg_b * buc));
+                            dbi += lr * (err - reg_b * bi0);
+                            reg_acc += reg_b * (buc * buc + bi0 * bi0);
+                        }
+                    }
+                    loss_f += reg_acc;
+                }
+                // one update of the item row for the chunk
+#pragma unroll
+                for (int m = G; m < 32; m <<= 1) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        dq[v].x += __shfl_xor_sync(0xffffffffu, dq[v].x, m); dq[v].y += __shfl_xor_sync(0xffffffffu, dq[v].y, m);
+                        dq[v].z += __shfl_xor_sync(0xffffffffu, dq[v].z, m); dq[v].w += __shfl_xor_sync(0xffffffffu, dq[v].w, m);
+                    }
+                    dbi += __shfl_xor_sync(0xffffffffu, dbi, m);
+                }
+                if (grp == 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) apply4<ATOMIC>(p.Q + (int64_t)i0 * p.ld + (v * G + sub) * 4, q[v], dq[v]);
+                    if (BIASED && sub == 0) apply1<ATOMIC>(p.bi + i0, bi0, dbi);
+                }
+            }
+            loss_d += (double)loss_f;
+            continue;
+        }
         float4 pn[V], qn[V];
         float bun = 0.f, bin = 0.f;
         int32_t un, in_;
@@ -356,7 +457,7 @@ __global__ void __launch_bounds__(256) sgd_bpr_epoch_kernel(SgdParams p) {
 // whole matrix in flight at once the epoch degenerates into one full-batch gradient step, which is
 // unstable at SGD learning rates (observed: PMF on ml-100k diverges) -- DESIGN.md "staleness cap".
 template <typename K>
-static int sgd_grid_for(lrk_handle_s* h, K kernel, int64_t n, int rps, int* grid_out) {
+static int sgd_grid_for(lrk_handle_s* h, K kernel, int64_t n, int rps, int* grid_out, double lr = 0.0, double hot_share = 0.0) {
     int per_sm = 0;
     LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0));
     if (per_sm < 1) per_sm = 1;
@@ -365,18 +466,37 @@ static int sgd_grid_for(lrk_handle_s* h, K kernel, int64_t n, int rps, int* grid
     if (need < grid) grid = need;
     const int64_t stale_cap = (n / 16) / (8 * (int64_t)rps * 2);
     if (stale_cap < grid) grid = stale_cap;
+    if (lr > 0.0 && hot_share > 0.0) {
+        // a warp keeps at most 8 ratings of one item in flight (run-tile chunk; 2 steps of the general path)
+        const double in_flight_max = 1.0 / (lr * hot_share);
+        const int64_t hot_cap = (int64_t)(in_flight_max / (8.0 * (double)(rps > 8 ? rps : 8)));
+        if (hot_cap < grid) grid = hot_cap;
+    }
     if (grid < 1) grid = 1;
     *grid_out = (int)grid;
     return LRK_OK;
 }
 
+// multiplier of the tile walk: close to the golden-ratio fraction of the tile count and coprime with it
+static int64_t sgd_tile_mul(int64_t n) {
+    const int64_t T = (n + 31) / 32;
+    if (T < 3) return 1;
+    int64_t a = (int64_t)((double)T * 0.6180339887498949);
+    if (a < 1) a = 1;
+    auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t t = x % y; x = y; y = t; } return x; };
+    while (gcd(a, T) != 1) ++a;
+    return a % T ? a % T : 1;
+}
+
 template <int G, int V>
-static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp) {
+static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp_in) {
+    SgdParams sp = sp_in;
+    sp.tile_mul = sgd_tile_mul(sp.n);
     const bool atomic = h->cfg.update_mode == LRK_UPDATE_ATOMIC;
     int grid = 1;
 #define LRK_GO(KERN)                                                          \
     do {                                                                      \
-        int rc__ = sgd_grid_for(h, KERN, sp.n, 32 / G, &grid);                        \
+        int rc__ = sgd_grid_for(h, KERN, sp.n, 32 / G, &grid, (double)sp.lr, sp.hot_share); \
         if (rc__) return rc__;                                                \
         KERN<<<grid, 256, 0, h->stream>>>(sp);                                \
     } while (0)

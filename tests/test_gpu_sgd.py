@@ -52,6 +52,52 @@ def test_conflict_free_epoch_matches_oracle(O, capi, model_name, k, mode):
     assert np.array_equal(gQ[untouched], Q[untouched])
 
 
+@pytest.mark.parametrize("model_name,k", [("biasedmf", 64), ("pmf", 128), ("biasedmf", 20), ("pmf", 3)])
+def test_item_run_tiles_are_minibatches_for_the_item(O, capi, model_name, k):
+    """Items with >= 512 ratings are staged as runs of 32 ratings (staging.cuh) and the kernel applies one item-row
+    update per 8 ratings of a run (sgd.cuh): for users that rate a single item this is a mini-batch step on q_i / b_i.
+    To first order in lr the epoch equals one step with every gradient taken at the initial q_i; which chunks see
+    which earlier updates depends on scheduling and moves the result by O(lr^2 * degree) -- hence the tolerances."""
+    n_items, per_item = 6, 512
+    n = n_items * per_item
+    rng = np.random.default_rng(5)
+    items = np.repeat(np.arange(n_items, dtype=np.int32), per_item)        # user u rates item u // 512 only
+    vals = rng.integers(1, 6, n).astype(np.float64)
+    I = 10
+    tr = O.Csr(n, I, np.arange(n + 1, dtype=np.int64), items, vals)
+    P = rng.normal(0, 0.1, (n, k)).astype(np.float32).astype(np.float64)
+    Q = rng.normal(0, 0.1, (I, k)).astype(np.float32).astype(np.float64)
+    biased = model_name == "biasedmf"
+    bu = rng.normal(0, 0.1, n).astype(np.float32).astype(np.float64) if biased else None
+    bi = rng.normal(0, 0.1, I).astype(np.float32).astype(np.float64) if biased else None
+    mu, lr, ru, ri, rb = 3.0, 0.00005, 0.02, 0.03, 0.04     # small lr: the O(lr^2) interaction of the two runs stays tiny
+    model = capi.MODEL_BIASEDMF if biased else capi.MODEL_PMF
+    with capi.Handle(model, k) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q, bu, bi, mu)
+        loss = h.sgd_epoch(lr, ru, ri, rb)
+        gP, gQ, gbu, gbi = h.get_factors()
+    # mini-batch restatement of BiasedMFRecommender.java:77-98 / PMFSimilarityRecommender.java:64-82 per item
+    q = Q[items]
+    pred = np.einsum("ij,ij->i", P, q) + ((bu + bi[items] + mu) if biased else 0.0)
+    err = vals - pred
+    eP = P + lr * (err[:, None] * q - ru * P)
+    dq = lr * (err[:, None] * P - ri * q)
+    eQ = Q.copy()
+    np.add.at(eQ, items, dq)
+    assert np.allclose(gP, eP, rtol=0, atol=5e-6)                            # user side: one rating per user
+    assert np.allclose(gQ, eQ, rtol=0, atol=1e-4) and np.abs(gQ - Q)[:n_items].max() > 2e-4
+    assert np.array_equal(gQ[n_items:], Q[n_items:])
+    eloss = np.sum(err ** 2) + np.sum(ru * P * P) + np.sum(ri * q * q)
+    if biased:
+        ebu = bu + lr * (err - rb * bu)
+        ebi = bi.copy(); np.add.at(ebi, items, lr * (err - rb * bi[items]))
+        assert np.allclose(gbu, ebu, rtol=0, atol=5e-6) and np.allclose(gbi, ebi, rtol=0, atol=1e-3)
+        assert np.abs(gbi - bi)[:n_items].max() > 5e-3
+        eloss += np.sum(rb * bu * bu) + np.sum(rb * bi[items] ** 2)
+    assert abs(loss - 0.5 * eloss) <= 1e-4 * abs(0.5 * eloss)
+
+
 def _train_gpu(capi, model, tr, k, P, Q, bu, bi, mu, lr, reg_u, reg_i, reg_b, iters, seed=1):
     with capi.Handle(model, k, seed=seed) as h:
         h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
