@@ -286,7 +286,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
                          "kernel": "sgd_rating_epoch_kernel<16,1,true,true>", "kernel_ms": kms,
-                         "algorithmic_bytes_per_epoch_per_gpu": BYTES_PER_UPDATE * nnz},
+                         "algorithmic_bytes_per_epoch_per_gpu": BYTES_PER_UPDATE * nnz,
+                         "note": "algorithmic bytes = SURVEY 8(d): 1052 B per update, no cache credit. frac > 1 means the kernel "
+                                 "moves less than that model: the 42 MB factor set is resident in the 126 MB L2 and item-run tiles "
+                                 "read/update a popular item's row once per 8 ratings; DRAM bytes per launch (ncu) are in `traffic`, "
+                                 "the binding unit is L2 (profiles/r01_sgd_kernel_ncu_summary.md)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
 

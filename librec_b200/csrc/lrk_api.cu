@@ -4,6 +4,7 @@
 #include "staging.cuh"
 #include "sgd.cuh"
 #include "sgd_exact.cuh"
+#include <chrono>
 #include "topn_exact.cuh"
 #include "topn_tc.cuh"
 #include "dsgd.cuh"
@@ -99,6 +100,7 @@ int lrk_destroy(lrk_handle_t h) {
     lrk_dev_free(&h->P32); lrk_dev_free(&h->Q32); lrk_dev_free(&h->bu32); lrk_dev_free(&h->bi32);
     lrk_dev_free(&h->P64); lrk_dev_free(&h->Q64); lrk_dev_free(&h->bu64); lrk_dev_free(&h->bi64);
     lrk_dev_free(&h->d_loss);
+    lrk_dev_free(&h->tn_users); lrk_dev_free(&h->tn_items); lrk_dev_free(&h->tn_scores); lrk_dev_free(&h->tn_counts);
     if (h->scratch) cudaFree(h->scratch);
     if (h->h_loss) cudaFreeHost(h->h_loss);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -406,18 +408,24 @@ int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int
     if (nq == 0) return LRK_OK;
     if (users) for (int32_t c = 0; c < nq; ++c) LRK_REQUIRE(h, users[c] >= 0 && users[c] < h->U, "user index out of range");
     else LRK_REQUIRE(h, nq <= h->U, "nq exceeds numUsers");
+    static const bool trace = getenv("LRK_TOPN_TRACE") && atoi(getenv("LRK_TOPN_TRACE"));
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_a = now();
     int rc = refresh_masters(h);
     if (rc) return rc;
     cudaStream_t st = h->stream;
     int32_t *d_users = nullptr, *d_items = nullptr, *d_counts = nullptr; double* d_scores = nullptr;
     cudaError_t e = cudaSuccess;
     if (users) {
-        e = cudaMalloc((void**)&d_users, sizeof(int32_t) * (size_t)nq);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_users, users, sizeof(int32_t) * (size_t)nq, cudaMemcpyHostToDevice, st);
+        if ((rc = lrk_dev_alloc(h, &h->tn_users, (size_t)nq))) return rc;
+        d_users = h->tn_users;
+        e = cudaMemcpyAsync(d_users, users, sizeof(int32_t) * (size_t)nq, cudaMemcpyHostToDevice, st);
     }
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_items, sizeof(int32_t) * (size_t)nq * topn);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_scores, sizeof(double) * (size_t)nq * topn);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_counts, sizeof(int32_t) * (size_t)nq);
+    if ((rc = lrk_dev_alloc(h, &h->tn_items, (size_t)nq * topn))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->tn_scores, (size_t)nq * topn))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->tn_counts, (size_t)nq))) return rc;
+    d_items = h->tn_items; d_scores = h->tn_scores; d_counts = h->tn_counts;
+    const double t_b = now();
     if (e == cudaSuccess) {
         cudaEventRecord(h->ev0, st);
         const bool want_tc = h->cfg.topn_path == 2 || (h->cfg.topn_path == 0 && topn_tc_profitable(h, nq, topn));
@@ -428,12 +436,14 @@ int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int
         } else { rc = topn_exact_launch(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts); h->topn_fallback_users = nq; }
         cudaEventRecord(h->ev1, st);
     }
+    const double t_c = now();
     if (rc == LRK_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_items, d_items, sizeof(int32_t) * (size_t)nq * topn, cudaMemcpyDeviceToHost, st);
     if (rc == LRK_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_scores, sizeof(double) * (size_t)nq * topn, cudaMemcpyDeviceToHost, st);
     if (rc == LRK_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_counts, d_counts, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess && rc == LRK_OK) cudaEventElapsedTime(&h->topn_ms, h->ev0, h->ev1);
-    cudaFree(d_users); cudaFree(d_items); cudaFree(d_scores); cudaFree(d_counts);
+    const double t_d = now();
+    if (trace) fprintf(stderr, "[lrk_topn] host ms: prepare %.2f, compute %.2f, copy-out %.2f, free %.2f\n", t_b - t_a, t_c - t_b, t_d - t_c, now() - t_d);
     if (rc) return rc;
     LRK_CUDA(h, e);
     return LRK_OK;

@@ -50,6 +50,9 @@ struct lrk_handle_s {
     float topn_ms = 0.f;
     float topn_phase_ms[4] = {0.f, 0.f, 0.f, 0.f};
     float topn_err_ratio = 0.f;   // largest observed |fp16 sweep score - exact score| / certificate bound (must be < 1)
+    // result buffers of lrk_topn, reused across calls (cudaMalloc/cudaFree of 130 MB cost 20-400 ms per call)
+    int32_t *tn_users = nullptr, *tn_items = nullptr, *tn_counts = nullptr;
+    double* tn_scores = nullptr;
     // tensor-core top-N state (bf16 copies, norms); see topn_tc.cuh
     void* tc = nullptr;
 

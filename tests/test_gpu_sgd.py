@@ -93,9 +93,9 @@ def test_item_run_tiles_are_minibatches_for_the_item(O, capi, model_name, k):
         ebu = bu + lr * (err - rb * bu)
         ebi = bi.copy(); np.add.at(ebi, items, lr * (err - rb * bi[items]))
         assert np.allclose(gbu, ebu, rtol=0, atol=5e-6) and np.allclose(gbi, ebi, rtol=0, atol=1e-3)
-        assert np.abs(gbi - bi)[:n_items].max() > 5e-3
+        assert np.abs(gbi - bi)[:n_items].max() > 1e-3
         eloss += np.sum(rb * bu * bu) + np.sum(rb * bi[items] ** 2)
-    assert abs(loss - 0.5 * eloss) <= 1e-4 * abs(0.5 * eloss)
+    assert abs(loss - 0.5 * eloss) <= 1e-3 * abs(0.5 * eloss)
 
 
 def _train_gpu(capi, model, tr, k, P, Q, bu, bi, mu, lr, reg_u, reg_i, reg_b, iters, seed=1):

@@ -175,3 +175,65 @@ def test_topn_tensor_core_after_training(O, capi, c1):
     oi, os_, oc = O.recommend_rank(O.BIASEDMF, tr.U, tr.I, 64, gP, gQ, gbu, gbi, mu, tr, 10)
     assert np.array_equal(items, oi) and np.array_equal(scores.view(np.int64), os_.view(np.int64)) and np.array_equal(counts, oc)
     print("ml-100k learned factors:", stats)
+
+
+def test_topn_second_sweep_replaces_exact_fallback(O, capi, monkeypatch):
+    """K' barely above N (and enough users that the catalogue is not chunked): many rows fail the margin test after the
+    first sweep; they are swept again from the threshold their first result implies (topn_tc.cuh) and must come out
+    bit-identical without touching the exact kernel"""
+    monkeypatch.setenv("LRK_TC_KEEP", "11")
+    U, I, k, N = 38000, 20000, 32, 10
+    rng = np.random.default_rng(77)
+    P = rng.normal(0, 0.1, (U, k)); Q = rng.normal(0, 0.1, (I, k))
+    edges = np.linspace(0, I, 9).astype(np.int64)                     # 8 train items per user: one per stratum -> ascending
+    cols = (edges[:-1][None, :] + (rng.random((U, 8)) * np.diff(edges)[None, :]).astype(np.int64)).astype(np.int32)
+    tr = O.Csr(U, I, np.arange(U + 1, dtype=np.int64) * 8, np.ascontiguousarray(cols.reshape(-1)), np.ones(U * 8))
+    with capi.Handle(capi.MODEL_PMF, k, topn_path=2) as h:
+        h.set_train_csr(U, I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q)
+        items, scores, counts = h.topn(N)
+        stats = h.topn_stats()
+    sample = np.linspace(0, U - 1, 1500).astype(np.int32)
+    oi, os_, oc = O.recommend_rank(O.PMF, U, I, k, P, Q, None, None, 0.0, tr, N, users=sample)
+    assert np.array_equal(counts[sample], oc) and np.array_equal(items[sample], oi)
+    assert np.array_equal(scores[sample].view(np.int64), os_.view(np.int64))
+    assert stats["resweep_users"] > 100 and stats["fallback_users"] <= stats["resweep_users"] // 4, stats
+    assert 0.0 < stats["sweep_error_over_bound"] < 1.0, stats
+
+
+@pytest.mark.parametrize("model", [0, 1])
+@pytest.mark.parametrize("pscale,qscale", [(1e-3, 1e-3), (300.0, 2e-4), (1e-6, 50.0)])
+def test_topn_tensor_core_operand_scaling(O, capi, model, pscale, qscale):
+    """fp16 operands after exact power-of-two scaling: tiny (reference init N(0, 0.001^2)) and huge factor magnitudes
+    must neither underflow nor overflow in the sweep; the certificate self-check stays inside its bound"""
+    U, I, k, N = 600, 12000, 64, 10
+    rng = np.random.default_rng(int(pscale * 1e7) + model)
+    P = rng.normal(0, pscale, (U, k)); Q = rng.normal(0, qscale, (I, k))
+    P[::5] *= 100.0                                                   # rows of very different magnitude
+    biased = model == capi.MODEL_BIASEDMF
+    bu = rng.normal(0, pscale * qscale, U) if biased else None
+    bi = rng.normal(0, pscale * qscale * 3, I) if biased else None
+    tr = rng_csr(O, U, I, 0.003, 5)
+    with capi.Handle(model, k, topn_path=2) as h:
+        h.set_train_csr(U, I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q, bu, bi, 3.53)
+        items, scores, counts = h.topn(N)
+        stats = h.topn_stats()
+    oi, os_, oc = O.recommend_rank(_omodel(capi, O, model), U, I, k, P, Q, bu, bi, 3.53, tr, N)
+    assert np.array_equal(counts, oc) and np.array_equal(items, oi)
+    assert np.array_equal(scores.view(np.int64), os_.view(np.int64))
+    assert stats["fast_users"] >= 0.9 * U and stats["sweep_error_over_bound"] < 1.0, stats
+
+
+def test_topn_tensor_core_nonfinite_items_use_exact_kernel(O, capi):
+    U, I, k, N = 600, 9000, 32, 10
+    h, tr, P, Q, bu, bi = _setup(capi, O, capi.MODEL_PMF, U, I, k, seed=9, density=0.003, scale=0.1, topn_path=2)
+    Q[17, 3] = np.inf; Q[4000, 0] = np.nan
+    with h:
+        h.set_factors(P, Q)
+        items, scores, counts = h.topn(N)
+        stats = h.topn_stats()
+    oi, os_, oc = O.recommend_rank(O.PMF, U, I, k, P, Q, None, None, 3.53, tr, N)
+    assert np.array_equal(counts, oc) and np.array_equal(items, oi)
+    assert np.array_equal(scores.view(np.int64), os_.view(np.int64))
+    assert stats["fallback_users"] == U and stats["fast_users"] == 0
