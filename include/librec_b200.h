@@ -120,6 +120,13 @@ LRK_API int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, do
                   int32_t epoch_idx, double* loss_out);
 /* device time of the last lrk_sgd_epoch kernel in milliseconds (CUDA events on its stream) */
 LRK_API int lrk_last_epoch_ms(lrk_handle_t h, float* ms_out);
+/* Safeguard of the fast (parallel) SGD modes.  The reference applies one rating at a time; here thousands are in
+ * flight, which is a larger effective step for popular items.  Every epoch starts from a device snapshot of the
+ * factors; a non-finite loss, or one above 10x the last accepted loss, rolls the epoch back and re-runs it with 4x
+ * fewer ratings in flight (kept for the following epochs, relaxed by 2x after 8 good ones).  Only if that still
+ * diverges does lrk_sgd_epoch return LRK_ERR_DIVERGED (AbstractRecommender.java:259-262).
+ * conc_div = current divisor of the grid (1 = full concurrency), rollbacks = epochs re-run since creation. */
+LRK_API int lrk_sgd_safeguard_state(lrk_handle_t h, int32_t* conc_div, int64_t* rollbacks);
 /* number of kernels this handle has launched since creation */
 LRK_API int lrk_launch_count(lrk_handle_t h, uint64_t* out);
 /* debug / test aid: the (user, positive item, negative item) triples that BPR epoch `epoch_idx`

@@ -58,6 +58,7 @@ SIGNATURES = {
     "lrk_topn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, _f64p, _i32p]),
     "lrk_topn_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "lrk_topn_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "lrk_sgd_safeguard_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "lrk_comm_unique_id": (C.c_int, [C.c_void_p]),
     "lrk_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }
@@ -210,6 +211,11 @@ class Handle:
             counts = np.empty(nq, np.int32)
         _check(load().lrk_topn(self._h, _ptr(users), nq, topn, int(bool(exclude_train)), items, scores, counts), self._h)
         return items, scores, counts
+
+    def sgd_safeguard(self):
+        d, r = C.c_int32(), C.c_int64()
+        _check(load().lrk_sgd_safeguard_state(self._h, C.byref(d), C.byref(r)), self._h)
+        return {"conc_div": d.value, "rollbacks": r.value}
 
     def topn_stats(self):
         a, b, ms = C.c_int64(), C.c_int64(), C.c_float()

@@ -312,6 +312,7 @@ static int dsgd_set_factors(lrk_handle_s* h, const double* P, const double* Q, c
     }
     s->cur = 0; s->cur_block = b;
     LRK_CUDA(h, cudaStreamSynchronize(st));
+    h->prev_loss = -1.0; h->conc_div = 1; h->good_epochs = 0;
     h->mu = mu; h->has_factors = true; h->f64_valid = false;
     return LRK_OK;
 }
@@ -321,6 +322,20 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     DsgdState* s = (DsgdState*)h->dsgd;
     cudaStream_t st = h->stream;
     const int world = h->world, rank = h->rank;
+    // safeguard (lrk_common.cuh): snapshot of what this rank owns at the epoch boundary -- its user block and the
+    // item block it holds; the loss is all-reduced, so every rank takes the same rollback decision
+    const bool biased_ = h->cfg.model == LRK_MODEL_BIASEDMF;
+    const size_t np_ = (size_t)h->U * h->ld;
+    {
+        int rc_a;
+        if ((rc_a = lrk_dev_alloc(h, &h->bk_P, np_))) return rc_a;
+        if ((rc_a = lrk_dev_alloc(h, &h->bk_Q, s->buf_floats))) return rc_a;
+        if (biased_ && (rc_a = lrk_dev_alloc(h, &h->bk_bu, (size_t)h->U))) return rc_a;
+    }
+    LRK_CUDA(h, cudaMemcpyAsync(h->bk_P, h->P32, sizeof(float) * np_, cudaMemcpyDeviceToDevice, st));
+    LRK_CUDA(h, cudaMemcpyAsync(h->bk_Q, s->qbuf[s->cur], sizeof(float) * s->buf_floats, cudaMemcpyDeviceToDevice, st));
+    if (biased_) LRK_CUDA(h, cudaMemcpyAsync(h->bk_bu, h->bu32, sizeof(float) * (size_t)h->U, cudaMemcpyDeviceToDevice, st));
+    for (int attempt = 0;; ++attempt) {
     LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
     LRK_CUDA(h, cudaEventRecord(h->ev0, st));
     if (s->trace < 0) { const char* t = getenv("LRK_DSGD_TRACE"); s->trace = t && atoi(t) ? 1 : 0; }
@@ -341,6 +356,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
             sp.mu = (float)h->mu; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i; sp.reg_b = (float)reg_b;
             sp.loss = h->d_loss; sp.ld = h->ld; sp.epoch = (uint32_t)epoch_idx;
             sp.hot_share = (size_t)b < s->seg_hot_share.size() ? s->seg_hot_share[(size_t)b] : 0.0;
+            sp.conc_div = h->conc_div;
             int rc = sgd_launch(h, sp);
             if (rc) return rc;
         }
@@ -362,6 +378,16 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
     LRK_CUDA(h, cudaStreamSynchronize(st));
     LRK_CUDA(h, cudaEventElapsedTime(&h->last_epoch_ms, h->ev0, h->ev1));
+    {
+        const double l_ = 0.5 * h->h_loss[0];
+        const bool bad = !std::isfinite(l_) || (h->prev_loss > 0.0 && l_ > 10.0 * h->prev_loss);
+        if (!bad || attempt >= 6 || h->conc_div >= 4096) break;
+        LRK_CUDA(h, cudaMemcpyAsync(h->P32, h->bk_P, sizeof(float) * np_, cudaMemcpyDeviceToDevice, st));
+        LRK_CUDA(h, cudaMemcpyAsync(s->qbuf[s->cur], h->bk_Q, sizeof(float) * s->buf_floats, cudaMemcpyDeviceToDevice, st));
+        if (biased_) LRK_CUDA(h, cudaMemcpyAsync(h->bu32, h->bk_bu, sizeof(float) * (size_t)h->U, cudaMemcpyDeviceToDevice, st));
+        h->conc_div *= 4; h->good_epochs = 0; h->rollbacks++;
+    }
+    }
     if (s->trace) {
         std::string line = "[dsgd rank " + std::to_string(rank) + " epoch " + std::to_string(epoch_idx) + "]";
         for (int sub = 0; sub < world; ++sub) {
@@ -379,6 +405,8 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     if (loss_out) *loss_out = loss;
     if (std::isnan(loss) || std::isinf(loss))
         return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);
+    h->prev_loss = loss;
+    if (h->conc_div > 1 && ++h->good_epochs >= 8) { h->conc_div /= 2; h->good_epochs = 0; }
     return LRK_OK;
 }
 

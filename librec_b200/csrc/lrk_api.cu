@@ -100,6 +100,7 @@ int lrk_destroy(lrk_handle_t h) {
     lrk_dev_free(&h->P32); lrk_dev_free(&h->Q32); lrk_dev_free(&h->bu32); lrk_dev_free(&h->bi32);
     lrk_dev_free(&h->P64); lrk_dev_free(&h->Q64); lrk_dev_free(&h->bu64); lrk_dev_free(&h->bi64);
     lrk_dev_free(&h->d_loss);
+    lrk_dev_free(&h->bk_P); lrk_dev_free(&h->bk_Q); lrk_dev_free(&h->bk_bu); lrk_dev_free(&h->bk_bi);
     lrk_dev_free(&h->tn_users); lrk_dev_free(&h->tn_items); lrk_dev_free(&h->tn_scores); lrk_dev_free(&h->tn_counts);
     if (h->scratch) cudaFree(h->scratch);
     if (h->h_loss) cudaFreeHost(h->h_loss);
@@ -194,6 +195,7 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     h->mu = mu;
     h->has_factors = true;
     h->f64_valid = true;
+    h->prev_loss = -1.0; h->conc_div = 1; h->good_epochs = 0;
     topn_tc_invalidate(h);
     return LRK_OK;
 }
@@ -267,26 +269,60 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
     }
     SgdParams sp;
     fill_sgd_params(h, sp, lr, reg_u, reg_i, reg_b, epoch_idx);
-    LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
-    LRK_CUDA(h, cudaEventRecord(h->ev0, st));
-    if (h->nnz > 0) {
-        int rc = sgd_launch(h, sp);
-        if (rc) return rc;
+    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    const size_t np_ = (size_t)h->U * h->ld, nq_ = (size_t)h->I * h->ld;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &h->bk_P, np_))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bk_Q, nq_))) return rc;
+    if (biased) {
+        if ((rc = lrk_dev_alloc(h, &h->bk_bu, (size_t)h->U))) return rc;
+        if ((rc = lrk_dev_alloc(h, &h->bk_bi, (size_t)h->I))) return rc;
     }
-    LRK_CUDA(h, cudaEventRecord(h->ev1, st));
+    LRK_CUDA(h, cudaMemcpyAsync(h->bk_P, h->P32, sizeof(float) * np_, cudaMemcpyDeviceToDevice, st));
+    LRK_CUDA(h, cudaMemcpyAsync(h->bk_Q, h->Q32, sizeof(float) * nq_, cudaMemcpyDeviceToDevice, st));
+    if (biased) {
+        LRK_CUDA(h, cudaMemcpyAsync(h->bk_bu, h->bu32, sizeof(float) * (size_t)h->U, cudaMemcpyDeviceToDevice, st));
+        LRK_CUDA(h, cudaMemcpyAsync(h->bk_bi, h->bi32, sizeof(float) * (size_t)h->I, cudaMemcpyDeviceToDevice, st));
+    }
+    double loss = 0.0;
+    for (int attempt = 0;; ++attempt) {
+        sp.conc_div = h->conc_div;
+        LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
+        LRK_CUDA(h, cudaEventRecord(h->ev0, st));
+        if (h->nnz > 0 && (rc = sgd_launch(h, sp))) return rc;
+        LRK_CUDA(h, cudaEventRecord(h->ev1, st));
+        LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+        LRK_CUDA(h, cudaStreamSynchronize(st));
+        loss = h->h_loss[0];
+        if (h->cfg.model != LRK_MODEL_BPR) loss *= 0.5;   // BiasedMFRecommender.java:101 ; BPR has no 0.5
+        const bool bad = !std::isfinite(loss) || (h->prev_loss > 0.0 && loss > 10.0 * h->prev_loss);
+        if (!bad || attempt >= 6 || h->conc_div >= 4096) break;
+        // roll the epoch back and retry with fewer ratings in flight
+        LRK_CUDA(h, cudaMemcpyAsync(h->P32, h->bk_P, sizeof(float) * np_, cudaMemcpyDeviceToDevice, st));
+        LRK_CUDA(h, cudaMemcpyAsync(h->Q32, h->bk_Q, sizeof(float) * nq_, cudaMemcpyDeviceToDevice, st));
+        if (biased) {
+            LRK_CUDA(h, cudaMemcpyAsync(h->bu32, h->bk_bu, sizeof(float) * (size_t)h->U, cudaMemcpyDeviceToDevice, st));
+            LRK_CUDA(h, cudaMemcpyAsync(h->bi32, h->bk_bi, sizeof(float) * (size_t)h->I, cudaMemcpyDeviceToDevice, st));
+        }
+        h->conc_div *= 4; h->good_epochs = 0; h->rollbacks++;
+    }
     h->f64_valid = false;
     topn_tc_invalidate(h);
-    LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
-    LRK_CUDA(h, cudaStreamSynchronize(st));
     LRK_CUDA(h, cudaEventElapsedTime(&h->last_epoch_ms, h->ev0, h->ev1));
-    double loss = h->h_loss[0];
-    if (h->cfg.model != LRK_MODEL_BPR) loss *= 0.5;   // BiasedMFRecommender.java:101 ; BPR has no 0.5
     if (loss_out) *loss_out = loss;
     if (std::isnan(loss) || std::isinf(loss))
         return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);
+    h->prev_loss = loss;
+    if (h->conc_div > 1 && ++h->good_epochs >= 8) { h->conc_div /= 2; h->good_epochs = 0; }
     return LRK_OK;
 }
 
+int lrk_sgd_safeguard_state(lrk_handle_t h, int32_t* conc_div, int64_t* rollbacks) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    if (conc_div) *conc_div = h->conc_div;
+    if (rollbacks) *rollbacks = h->rollbacks;
+    return LRK_OK;
+}
 int lrk_last_epoch_ms(lrk_handle_t h, float* ms_out) {
     LRK_REQUIRE(h, h != nullptr && ms_out != nullptr, "NULL argument");
     *ms_out = h->last_epoch_ms;

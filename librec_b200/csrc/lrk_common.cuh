@@ -39,6 +39,13 @@ struct lrk_handle_s {
     bool has_factors = false;
     bool f64_valid = false;   // masters are in sync with the fp32 working copies
 
+    // Safeguard of the fast SGD mode: factors are snapshotted before an epoch; a non-finite (or exploding) loss
+    // rolls the epoch back and re-runs it with 4x fewer ratings in flight (sticky, relaxed again after 8 good epochs)
+    float *bk_P = nullptr, *bk_Q = nullptr, *bk_bu = nullptr, *bk_bi = nullptr;
+    int conc_div = 1;           // divisor of the SGD grid
+    int good_epochs = 0;
+    double prev_loss = -1.0;    // loss of the last accepted epoch (< 0: none yet)
+    int64_t rollbacks = 0;
     double* d_loss = nullptr;   // device accumulator
     double* h_loss = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -46,6 +46,7 @@ struct SgdParams {
     // [item-run tiles | shuffled remainder], the multiplicative walk interleaves the two evenly in time
     int64_t tile_mul;
     double hot_share;       // largest share one item has of this launch's ratings (0 = unknown): stability cap of the grid
+    int conc_div;           // >= 1: divisor of the grid (rollback safeguard, lrk_common.cuh)
     // BPR only
     const int64_t* __restrict__ rowptr;
     const int32_t* __restrict__ col;
@@ -457,7 +458,8 @@ __global__ void __launch_bounds__(256) sgd_bpr_epoch_kernel(SgdParams p) {
 // whole matrix in flight at once the epoch degenerates into one full-batch gradient step, which is
 // unstable at SGD learning rates (observed: PMF on ml-100k diverges) -- DESIGN.md "staleness cap".
 template <typename K>
-static int sgd_grid_for(lrk_handle_s* h, K kernel, int64_t n, int rps, int* grid_out, double lr = 0.0, double hot_share = 0.0) {
+static int sgd_grid_for(lrk_handle_s* h, K kernel, int64_t n, int rps, int* grid_out, double lr = 0.0, double hot_share = 0.0,
+                        int conc_div = 1) {
     int per_sm = 0;
     LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0));
     if (per_sm < 1) per_sm = 1;
@@ -472,6 +474,7 @@ static int sgd_grid_for(lrk_handle_s* h, K kernel, int64_t n, int rps, int* grid
         const int64_t hot_cap = (int64_t)(in_flight_max / (8.0 * (double)(rps > 8 ? rps : 8)));
         if (hot_cap < grid) grid = hot_cap;
     }
+    if (conc_div > 1) grid /= conc_div;
     if (grid < 1) grid = 1;
     *grid_out = (int)grid;
     return LRK_OK;
@@ -496,7 +499,7 @@ static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp_in) {
     int grid = 1;
 #define LRK_GO(KERN)                                                          \
     do {                                                                      \
-        int rc__ = sgd_grid_for(h, KERN, sp.n, 32 / G, &grid, (double)sp.lr, sp.hot_share); \
+        int rc__ = sgd_grid_for(h, KERN, sp.n, 32 / G, &grid, (double)sp.lr, sp.hot_share, sp.conc_div); \
         if (rc__) return rc__;                                                \
         KERN<<<grid, 256, 0, h->stream>>>(sp);                                \
     } while (0)

@@ -233,6 +233,8 @@ def test_diverged_loss_is_reported(O, capi):
             for it in range(3):
                 h.sgd_epoch(0.01, 0.01, 0.01, 0.0, it + 1)
         assert e.value.status == capi.ERR_DIVERGED and "NaN or Infinity" in str(e.value)
+        # the safeguard re-ran the epoch with fewer ratings in flight before giving up
+        assert h.sgd_safeguard()["rollbacks"] >= 1 and h.sgd_safeguard()["conc_div"] > 1
 
 
 def test_argument_errors(O, capi):
