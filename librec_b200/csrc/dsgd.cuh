@@ -163,7 +163,6 @@ static int dsgd_comm_init(lrk_handle_s* h, int rank, int world, const uint8_t* u
     LRK_REQUIRE(h, uid != nullptr && world >= 1 && rank >= 0 && rank < world, "bad rank/world");
     LRK_REQUIRE(h, h->comm == nullptr, "communicator already initialised");
     LRK_REQUIRE(h, !h->has_train && !h->has_factors, "lrk_comm_init must precede staging");
-    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_BPR, "DSGD is implemented for BiasedMF and PMF (BPR needs stratified sampling)");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     ncclUniqueId id;
     memcpy(&id, uid, 128);
@@ -355,7 +354,14 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
             sp.P = h->P32; sp.Q = buf; sp.bu = h->bu32; sp.bi = buf + (size_t)s->max_blk * h->ld;
             sp.mu = (float)h->mu; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i; sp.reg_b = (float)reg_b;
             sp.loss = h->d_loss; sp.ld = h->ld; sp.epoch = (uint32_t)epoch_idx;
-            sp.hot_share = (size_t)b < s->seg_hot_share.size() ? s->seg_hot_share[(size_t)b] : 0.0;
+            if (h->cfg.model == LRK_MODEL_BPR) {
+                // stratified sampling inside the held block; as many samples as the rank has ratings in it
+                sp.rowptr = h->d_rowptr; sp.col = h->d_col; sp.U = h->U; sp.I = h->I;
+                sp.seed_lo = (uint32_t)(h->cfg.seed + 977u * (uint64_t)rank); sp.seed_hi = (uint32_t)((h->cfg.seed + 977u * (uint64_t)rank) >> 32);
+                sp.blk_lo = s->bounds[(size_t)b]; sp.blk_hi = s->bounds[(size_t)b + 1];
+                sp.sample_base = off;
+            }
+            sp.hot_share = (h->cfg.model != LRK_MODEL_BPR && (size_t)b < s->seg_hot_share.size()) ? s->seg_hot_share[(size_t)b] : 0.0;
             sp.conc_div = h->conc_div;
             int rc = sgd_launch(h, sp);
             if (rc) return rc;
@@ -379,7 +385,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     LRK_CUDA(h, cudaStreamSynchronize(st));
     LRK_CUDA(h, cudaEventElapsedTime(&h->last_epoch_ms, h->ev0, h->ev1));
     {
-        const double l_ = 0.5 * h->h_loss[0];
+        const double l_ = (h->cfg.model == LRK_MODEL_BPR ? 1.0 : 0.5) * h->h_loss[0];
         const bool bad = !std::isfinite(l_) || (h->prev_loss > 0.0 && l_ > 10.0 * h->prev_loss);
         if (!bad || attempt >= 6 || h->conc_div >= 4096) break;
         LRK_CUDA(h, cudaMemcpyAsync(h->P32, h->bk_P, sizeof(float) * np_, cudaMemcpyDeviceToDevice, st));
@@ -401,7 +407,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
         }
         fprintf(stderr, "%s total %.3f ms\n", line.c_str(), h->last_epoch_ms);
     }
-    const double loss = 0.5 * h->h_loss[0];
+    const double loss = (h->cfg.model == LRK_MODEL_BPR ? 1.0 : 0.5) * h->h_loss[0];   // BPR has no 0.5 (BPRRecommender.java:77-92)
     if (loss_out) *loss_out = loss;
     if (std::isnan(loss) || std::isinf(loss))
         return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);

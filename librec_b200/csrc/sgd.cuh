@@ -52,6 +52,11 @@ struct SgdParams {
     const int32_t* __restrict__ col;
     int32_t U, I;
     uint32_t seed_lo, seed_hi, epoch;
+    // BPR under DSGD: positives and negatives are drawn inside the item block [blk_lo, blk_hi) the rank holds
+    // (blk_hi == 0: whole catalogue); Q then addresses the block buffer (row = item - blk_lo); sample_base keeps the
+    // Philox counters of the strata of one epoch apart
+    int32_t blk_lo, blk_hi;
+    int64_t sample_base;
 };
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -354,6 +359,45 @@ __device__ __forceinline__ void bpr_draw(const SgdParams& p, int64_t s, int32_t&
     }
 }
 
+// first index in [b, e) with col >= x
+__device__ __forceinline__ int64_t row_lower_bound(const int32_t* __restrict__ col, int64_t b, int64_t e, int32_t x) {
+    while (b < e) {
+        const int64_t m = (b + e) >> 1;
+        if (__ldg(col + m) < x) b = m + 1; else e = m;
+    }
+    return b;
+}
+// Stratified BPR draw for DSGD: user uniform over local users that have at least one and not all
+// items of the held block [blk_lo, blk_hi) in their train row; positive uniform over the row's items in the
+// block; negative uniform over the block's items outside the row (rejection).  Same structure as
+// BPRRecommender.java:54-67 restricted to the stratum.
+__device__ __forceinline__ void bpr_draw_block(const SgdParams& p, int64_t s, int32_t& u, int32_t& pi, int32_t& nj) {
+    const uint2 key = make_uint2(p.seed_lo, p.seed_hi);
+    const uint32_t width = (uint32_t)(p.blk_hi - p.blk_lo);
+    const int64_t sc = s + p.sample_base;
+    uint32_t attempt = 0;
+    for (;;) {
+        uint4 x = philox4x32_10(make_uint4((uint32_t)sc, (uint32_t)(sc >> 32), p.epoch, attempt++), key);
+        u = (int32_t)__umulhi(x.x, (uint32_t)p.U);
+        const int64_t rb = __ldg(p.rowptr + u), re = __ldg(p.rowptr + u + 1);
+        const int64_t b = row_lower_bound(p.col, rb, re, p.blk_lo), e = row_lower_bound(p.col, b, re, p.blk_hi);
+        const int64_t len = e - b;
+        if (len == 0 || len == (int64_t)width) continue;
+        pi = __ldg(p.col + b + (int64_t)__umulhi(x.y, (uint32_t)len));
+        nj = p.blk_lo + (int32_t)__umulhi(x.z, width);
+        if (!row_contains(p.col, b, e, nj)) return;
+        nj = p.blk_lo + (int32_t)__umulhi(x.w, width);
+        if (!row_contains(p.col, b, e, nj)) return;
+        for (;;) {
+            x = philox4x32_10(make_uint4((uint32_t)sc, (uint32_t)(sc >> 32), p.epoch, attempt++), key);
+            nj = p.blk_lo + (int32_t)__umulhi(x.x, width); if (!row_contains(p.col, b, e, nj)) return;
+            nj = p.blk_lo + (int32_t)__umulhi(x.y, width); if (!row_contains(p.col, b, e, nj)) return;
+            nj = p.blk_lo + (int32_t)__umulhi(x.z, width); if (!row_contains(p.col, b, e, nj)) return;
+            nj = p.blk_lo + (int32_t)__umulhi(x.w, width); if (!row_contains(p.col, b, e, nj)) return;
+        }
+    }
+}
+
 __global__ void bpr_peek_kernel(SgdParams p, int64_t first, int64_t n, int32_t* out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -379,7 +423,10 @@ __global__ void __launch_bounds__(256) sgd_bpr_epoch_kernel(SgdParams p) {
         int32_t u_l = -1, i_l = 0, j_l = 0;
         {
             const int64_t s = (tile << 5) + lane;
-            if (s < p.n) bpr_draw(p, s, u_l, i_l, j_l);
+            if (s < p.n) {
+                if (p.blk_hi > 0) { bpr_draw_block(p, s, u_l, i_l, j_l); i_l -= p.blk_lo; j_l -= p.blk_lo; }
+                else bpr_draw(p, s, u_l, i_l, j_l);
+            }
         }
         float loss_f = 0.f;
         float4 pn[V], qin[V], qjn[V];
