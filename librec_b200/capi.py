@@ -56,6 +56,8 @@ SIGNATURES = {
     "lrk_eval_rating": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                   C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lrk_topn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, _f64p, _i32p]),
+    "lrk_eval_ranking": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_double)]),
     "lrk_topn_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "lrk_topn_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "lrk_sgd_safeguard_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
@@ -211,6 +213,20 @@ class Handle:
             counts = np.empty(nq, np.int32)
         _check(load().lrk_topn(self._h, _ptr(users), nq, topn, int(bool(exclude_train)), items, scores, counts), self._h)
         return items, scores, counts
+
+    def eval_ranking(self, topn, t_rowptr, t_col, t_val, want_lists=False):
+        """-> dict(AUC, AP, NDCG, Precision, Recall, RR) [, (items, scores, counts)]"""
+        t_rowptr = np.ascontiguousarray(t_rowptr, np.int64)
+        t_col = np.ascontiguousarray(t_col, np.int32)
+        t_val = np.ascontiguousarray(t_val, np.float64)
+        out = (C.c_double * 6)()
+        items = np.empty((self.U, topn), np.int32) if want_lists else None
+        scores = np.empty((self.U, topn), np.float64) if want_lists else None
+        counts = np.empty(self.U, np.int32) if want_lists else None
+        _check(load().lrk_eval_ranking(self._h, topn, _ptr(t_rowptr), _ptr(t_col), _ptr(t_val), _ptr(items), _ptr(scores),
+                                       _ptr(counts), out), self._h)
+        m = dict(zip(("AUC", "AP", "NDCG", "Precision", "Recall", "RR"), list(out)))
+        return (m, (items, scores, counts)) if want_lists else m
 
     def sgd_safeguard(self):
         d, r = C.c_int32(), C.c_int64()

@@ -428,13 +428,11 @@ int lrk_eval_rating(lrk_handle_t h, int32_t U, const int64_t* t_rowptr, const in
 }
 
 // -------------------------------------------------------------------------------------------
-int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int32_t exclude_train,
-             int32_t* out_items, double* out_scores, int32_t* out_counts) {
-    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+// top-N lists of the queried users into the handle's device buffers (tn_items / tn_scores / tn_counts)
+static int topn_to_device(lrk_handle_s* h, const int32_t* users, int32_t nq, int32_t topn, int32_t exclude_train) {
     LRK_REQUIRE(h, h->has_factors, "no factors set");
     LRK_REQUIRE(h, topn > 0, "rec.recommender.ranking.topn should be more than 0!");   // AbstractRecommender.java:115-117
     LRK_REQUIRE(h, topn <= LRK_MAX_TOPN, "topn above LRK_MAX_TOPN (512)");
-    LRK_REQUIRE(h, nq >= 0 && (nq == 0 || (out_items && out_scores && out_counts)), "bad arguments");
     LRK_REQUIRE(h, !exclude_train || h->has_train, "exclude_train needs the train CSR");
     LRK_REQUIRE(h, h->world == 1, "gather the factors with lrk_get_factors in DSGD mode; top-N shards by user block");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -444,44 +442,82 @@ int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int
     if (nq == 0) return LRK_OK;
     if (users) for (int32_t c = 0; c < nq; ++c) LRK_REQUIRE(h, users[c] >= 0 && users[c] < h->U, "user index out of range");
     else LRK_REQUIRE(h, nq <= h->U, "nq exceeds numUsers");
-    static const bool trace = getenv("LRK_TOPN_TRACE") && atoi(getenv("LRK_TOPN_TRACE"));
-    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_a = now();
     int rc = refresh_masters(h);
     if (rc) return rc;
     cudaStream_t st = h->stream;
-    int32_t *d_users = nullptr, *d_items = nullptr, *d_counts = nullptr; double* d_scores = nullptr;
-    cudaError_t e = cudaSuccess;
+    int32_t* d_users = nullptr;
     if (users) {
         if ((rc = lrk_dev_alloc(h, &h->tn_users, (size_t)nq))) return rc;
         d_users = h->tn_users;
-        e = cudaMemcpyAsync(d_users, users, sizeof(int32_t) * (size_t)nq, cudaMemcpyHostToDevice, st);
+        LRK_CUDA(h, cudaMemcpyAsync(d_users, users, sizeof(int32_t) * (size_t)nq, cudaMemcpyHostToDevice, st));
     }
     if ((rc = lrk_dev_alloc(h, &h->tn_items, (size_t)nq * topn))) return rc;
     if ((rc = lrk_dev_alloc(h, &h->tn_scores, (size_t)nq * topn))) return rc;
     if ((rc = lrk_dev_alloc(h, &h->tn_counts, (size_t)nq))) return rc;
-    d_items = h->tn_items; d_scores = h->tn_scores; d_counts = h->tn_counts;
-    const double t_b = now();
-    if (e == cudaSuccess) {
-        cudaEventRecord(h->ev0, st);
-        const bool want_tc = h->cfg.topn_path == 2 || (h->cfg.topn_path == 0 && topn_tc_profitable(h, nq, topn));
-        if (want_tc) rc = topn_tc_run(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts);
-        else if (d_users && h->cfg.topn_path != 1 && nq <= 4 * h->sm_count && h->I >= 32768) {
-            rc = topn_exact_parallel_launch(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts);
-            h->topn_fallback_users = nq;
-        } else { rc = topn_exact_launch(h, d_users, nq, topn, exclude_train, d_items, d_scores, d_counts); h->topn_fallback_users = nq; }
-        cudaEventRecord(h->ev1, st);
-    }
-    const double t_c = now();
-    if (rc == LRK_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_items, d_items, sizeof(int32_t) * (size_t)nq * topn, cudaMemcpyDeviceToHost, st);
-    if (rc == LRK_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_scores, sizeof(double) * (size_t)nq * topn, cudaMemcpyDeviceToHost, st);
-    if (rc == LRK_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_counts, d_counts, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess && rc == LRK_OK) cudaEventElapsedTime(&h->topn_ms, h->ev0, h->ev1);
-    const double t_d = now();
-    if (trace) fprintf(stderr, "[lrk_topn] host ms: prepare %.2f, compute %.2f, copy-out %.2f, free %.2f\n", t_b - t_a, t_c - t_b, t_d - t_c, now() - t_d);
+    cudaEventRecord(h->ev0, st);
+    const bool want_tc = h->cfg.topn_path == 2 || (h->cfg.topn_path == 0 && topn_tc_profitable(h, nq, topn));
+    if (want_tc) rc = topn_tc_run(h, d_users, nq, topn, exclude_train, h->tn_items, h->tn_scores, h->tn_counts);
+    else if (d_users && h->cfg.topn_path != 1 && nq <= 4 * h->sm_count && h->I >= 32768) {
+        rc = topn_exact_parallel_launch(h, d_users, nq, topn, exclude_train, h->tn_items, h->tn_scores, h->tn_counts);
+        h->topn_fallback_users = nq;
+    } else { rc = topn_exact_launch(h, d_users, nq, topn, exclude_train, h->tn_items, h->tn_scores, h->tn_counts); h->topn_fallback_users = nq; }
+    cudaEventRecord(h->ev1, st);
+    return rc;
+}
+static int topn_lists_to_host(lrk_handle_s* h, int32_t nq, int32_t topn, int32_t* out_items, double* out_scores, int32_t* out_counts) {
+    cudaStream_t st = h->stream;
+    if (out_items) LRK_CUDA(h, cudaMemcpyAsync(out_items, h->tn_items, sizeof(int32_t) * (size_t)nq * topn, cudaMemcpyDeviceToHost, st));
+    if (out_scores) LRK_CUDA(h, cudaMemcpyAsync(out_scores, h->tn_scores, sizeof(double) * (size_t)nq * topn, cudaMemcpyDeviceToHost, st));
+    if (out_counts) LRK_CUDA(h, cudaMemcpyAsync(out_counts, h->tn_counts, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&h->topn_ms, h->ev0, h->ev1);
+    return LRK_OK;
+}
+
+int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int32_t exclude_train,
+             int32_t* out_items, double* out_scores, int32_t* out_counts) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, nq >= 0 && (nq == 0 || (out_items && out_scores && out_counts)), "bad arguments");
+    int rc = topn_to_device(h, users, nq, topn, exclude_train);
+    if (rc || nq == 0) return rc;
+    return topn_lists_to_host(h, nq, topn, out_items, out_scores, out_counts);
+}
+
+int lrk_eval_ranking(lrk_handle_t h, int32_t topn, const int64_t* t_rowptr, const int32_t* t_col, const double* t_val,
+                     int32_t* out_items, double* out_scores, int32_t* out_counts, double out_measures[6]) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, t_rowptr && out_measures, "NULL argument");
+    LRK_REQUIRE(h, h->has_train && h->has_factors, "set the train CSR and the factors first");
+    LRK_REQUIRE(h, topn >= 1 && topn <= LRK_EVAL_MAX_TOPN, "lrk_eval_ranking supports 1 <= topn <= 64");
+    const int32_t U = h->U;
+    const int64_t nnz = t_rowptr[U];
+    LRK_REQUIRE(h, nnz == 0 || (t_col && t_val), "NULL test arrays");
+    int rc = topn_to_device(h, nullptr, U, topn, /*exclude_train=*/1);      // MatrixRecommender.java:153-201
     if (rc) return rc;
-    LRK_CUDA(h, e);
+    cudaStream_t st = h->stream;
+    LrkScratch sc;
+    const int nb = lrk_ceil_div(U, 128);
+    if ((rc = lrk_scratch_begin(h, sizeof(int64_t) * ((size_t)U + 1) + (size_t)nnz * 12 + sizeof(double) * (7 * (size_t)U + 16) + 16 * 256, &sc))) return rc;
+    int64_t* d_rp = sc.take<int64_t>((size_t)U + 1);
+    int32_t* d_c = sc.take<int32_t>((size_t)std::max<int64_t>(nnz, 1));
+    double* d_v = sc.take<double>((size_t)std::max<int64_t>(nnz, 1));
+    double* d_part = sc.take<double>(7 * (size_t)U);
+    double* d_out = sc.take<double>(8);
+    if (!d_rp || !d_c || !d_v || !d_part || !d_out) return lrk_fail(h, LRK_ERR_NOMEM, "lrk_eval_ranking", "scratch arena too small", __FILE__, __LINE__);
+    LRK_CUDA(h, cudaMemcpyAsync(d_rp, t_rowptr, sizeof(int64_t) * ((size_t)U + 1), cudaMemcpyHostToDevice, st));
+    if (nnz > 0) {
+        LRK_CUDA(h, cudaMemcpyAsync(d_c, t_col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        LRK_CUDA(h, cudaMemcpyAsync(d_v, t_val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    }
+    eval_ranking_kernel<<<nb, 128, 0, st>>>(U, h->I, topn, h->tn_items, h->tn_counts, d_rp, d_c, d_v, h->d_rowptr, d_part);
+    LRK_LAUNCH_CHECK(h);
+    eval_ranking_final_kernel<<<7, 256, 0, st>>>(d_part, U, d_out);
+    LRK_LAUNCH_CHECK(h);
+    double res[8];
+    LRK_CUDA(h, cudaMemcpyAsync(res, d_out, sizeof(double) * 7, cudaMemcpyDeviceToHost, st));
+    if ((rc = topn_lists_to_host(h, U, topn, out_items, out_scores, out_counts))) return rc;
+    // res[6] = users that count, res[1] carries AP's own denominator in the kernel (see eval_ranking_final_kernel)
+    for (int m = 0; m < 6; ++m) out_measures[m] = res[m];
     return LRK_OK;
 }
 

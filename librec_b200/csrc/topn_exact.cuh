@@ -462,3 +462,101 @@ static int topn_exact_parallel_launch(lrk_handle_s* h, const int32_t* d_users, i
     LRK_CUDA(h, e);
     return LRK_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Ranking evaluators over the top-N lists while they are still on the device:
+// eval/ranking/{AUC,AveragePrecision,NormalizedDCG,Precision,Recall,ReciprocalRank}Evaluator.java.
+// One thread per user; per-user terms to part[7][U] (6 measures + "user counts" flags: bit0 test row not empty,
+// bit1 AP's extra condition topK != 0), reduced in a fixed order by eval_ranking_final_kernel.
+// Java behaviour kept: Precision / topN; AP / min(|test|, topK);
+// "NDCG" with the ideal DCG of the hit entries only; AUC's pair count in java.util.HashSet<Integer> iteration
+// order of the test items (bucket (h ^ h>>>16) & (cap-1) ascending, insertion order inside a bucket).
+// ---------------------------------------------------------------------------------------------
+#define LRK_EVAL_MAX_TOPN 64
+__device__ __forceinline__ int64_t er_find(const int32_t* __restrict__ col, int64_t b, int64_t e, int32_t key) {
+    int64_t lo = b, hi = e;
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (col[m] < key) lo = m + 1; else hi = m; }
+    return (lo < e && col[lo] == key) ? lo : -1;
+}
+__global__ void eval_ranking_kernel(int32_t U, int32_t I, int topn, const int32_t* __restrict__ rec_items, const int32_t* __restrict__ rec_counts,
+                                    const int64_t* __restrict__ t_rowptr, const int32_t* __restrict__ t_col, const double* __restrict__ t_val,
+                                    const int64_t* __restrict__ train_rowptr, double* __restrict__ part) {
+    const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    double auc = 0, ap = 0, ndcg = 0, prec = 0, rec = 0, rr = 0, flags = 0;
+    const int64_t tb = t_rowptr[u], te = t_rowptr[u + 1], nt = te - tb;
+    if (nt > 0) {
+        flags = 1;
+        const int32_t* r = rec_items + (int64_t)u * topn;
+        const int topk = topn <= rec_counts[u] ? topn : rec_counts[u];
+        int hits = 0, miss = 0; double tmp = 0.0, dcg = 0.0; bool first = true;
+        double hv[LRK_EVAL_MAX_TOPN];                      // ratings of the hit entries, kept in descending order
+        for (int i = 0; i < topk; ++i) {
+            const int64_t pos = er_find(t_col, tb, te, r[i]);
+            if (pos >= 0) {
+                const double v = t_val[pos];
+                int j = hits;
+                while (j > 0 && hv[j - 1] < v) { hv[j] = hv[j - 1]; --j; }
+                hv[j] = v;
+                ++hits;
+                tmp += 1.0 * hits / (i + 1);
+                if (first) { rr = 1.0 / (i + 1.0); first = false; }
+                dcg += v / (log((double)(i + 2)) / log(2.0));
+            } else ++miss;
+        }
+        prec = hits / (topn + 0.0);
+        rec = hits / (nt + 0.0);
+        if (topk != 0) { ap = tmp / (double)(nt < topk ? nt : topk); flags = 3; }
+        if (hits > 0 && dcg != 0.0) {
+            double idcg = 0.0;
+            for (int j = 0; j < hits; ++j) idcg += hv[j] / (log((double)(j + 2)) / log(2.0));
+            if (idcg != 0.0) ndcg = dcg / idcg;
+        }
+        // AUC
+        const int num_dropped = (int)(I - (train_rowptr[u + 1] - train_rowptr[u])) - topk;
+        const long long n_pairs = ((long long)num_dropped + topk - hits) * hits;
+        if (n_pairs == 0) auc = 0.5;
+        else {
+            uint32_t cap = 16;
+            while ((double)nt > 0.75 * (double)cap) cap <<= 1;
+            long long correct = 0;
+            for (int64_t e = tb; e < te; ++e) {
+                const int32_t b = t_col[e];
+                bool in_rec = false;
+                for (int i = 0; i < topk; ++i) if (r[i] == b) { in_rec = true; break; }
+                if (in_rec) continue;
+                const uint32_t hb = (((uint32_t)b) ^ (((uint32_t)b) >> 16)) & (cap - 1);
+                // hits that the HashSet iteration meets before b
+                for (int i = 0; i < topk; ++i) {
+                    const int64_t pos = er_find(t_col, tb, te, r[i]);
+                    if (pos < 0) continue;
+                    const uint32_t ha = (((uint32_t)r[i]) ^ (((uint32_t)r[i]) >> 16)) & (cap - 1);
+                    if (ha < hb || (ha == hb && pos < e)) ++correct;
+                }
+            }
+            correct += (long long)hits * (num_dropped - miss);
+            auc = (correct + 0.0) / (double)n_pairs;
+        }
+    }
+    part[0 * (size_t)U + u] = auc; part[1 * (size_t)U + u] = ap; part[2 * (size_t)U + u] = ndcg;
+    part[3 * (size_t)U + u] = prec; part[4 * (size_t)U + u] = rec; part[5 * (size_t)U + u] = rr; part[6 * (size_t)U + u] = flags;
+}
+// block m sums measure m over the users (fixed order); the mean is over the users that count
+__global__ void eval_ranking_final_kernel(const double* __restrict__ part, int32_t U, double* __restrict__ out) {
+    __shared__ double s_sum[256], s_cnt[256];
+    const int m = blockIdx.x;
+    double sum = 0.0, cnt = 0.0;
+    for (int32_t u = threadIdx.x; u < U; u += blockDim.x) {
+        const int f = (int)part[6 * (size_t)U + u];
+        if (m < 6) { sum += part[(size_t)m * U + u]; cnt += (m == 1) ? ((f & 2) ? 1.0 : 0.0) : ((f & 1) ? 1.0 : 0.0); }
+        else cnt += (f & 1) ? 1.0 : 0.0;
+    }
+    s_sum[threadIdx.x] = sum; s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int st = 128; st >= 1; st >>= 1) {
+        if ((int)threadIdx.x < st) { s_sum[threadIdx.x] += s_sum[threadIdx.x + st]; s_cnt[threadIdx.x] += s_cnt[threadIdx.x + st]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[m] = m < 6 ? (s_cnt[0] > 0.0 ? s_sum[0] / s_cnt[0] : 0.0) : s_cnt[0];
+}

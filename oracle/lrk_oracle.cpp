@@ -521,6 +521,101 @@ LRO_API void lro_eval_rating(int32_t model, int32_t U, const int64_t* t_rowptr, 
     *mae = n > 0 ? ae / (double)n : 0.0;
 }
 
+// -------------------------------------------------------------------------------------
+// Ranking evaluators over top-N lists:
+//   eval/ranking/AUCEvaluator.java:45-106, AveragePrecisionEvaluator.java:43-72,
+//   NormalizedDCGEvaluator.java:44-103 (+ getValueByKey :105-113), PrecisionEvaluator.java:24-47,
+//   RecallEvaluator.java:44-66, ReciprocalRankEvaluator.java:43-64.
+// Ground truth of a user = its test row in CSR order (eval/EvalContext.java:75-88); a user counts only if that
+// row is not empty.  numDropped[u] = numItems - |train row u| (recommender/MatrixRecommender.java:110-113).
+// JDK behaviour the reference leans on (not vendored): the AUC pair count iterates a java.util.HashSet<Integer>
+// built by adding the test items in ascending order -- iteration order = ascending bucket
+// ((h ^ h>>>16) & (cap-1), cap = 16 doubled while size > 0.75 cap), insertion order inside a bucket.
+// Java quirks kept: Precision divides by topN, not by the list length; AP divides by min(|test|, topK);
+// "NDCG" takes its ideal DCG only from the ground-truth entries that were hit.
+// out[6] = {AUC, AP, NDCG, Precision, Recall, RR}, each the mean over the users that count.
+// -------------------------------------------------------------------------------------
+static inline uint32_t jhash_bucket(int32_t key, uint32_t cap) {
+    const uint32_t h = (uint32_t)key;
+    return (h ^ (h >> 16)) & (cap - 1);
+}
+static inline uint32_t jhashset_capacity(int64_t n) {          // HashMap.putVal / resize with the default load factor
+    uint32_t cap = 16;
+    while ((double)n > 0.75 * (double)cap) cap <<= 1;
+    return cap;
+}
+LRO_API void lro_eval_ranking(int32_t U, int32_t topn, const int32_t* rec_items, const int32_t* rec_counts,
+                              const int64_t* t_rowptr, const int32_t* t_col, const double* t_val,
+                              const int32_t* num_dropped, double* out) {
+    double auc = 0, ap = 0, ndcg = 0, prec = 0, rec = 0, rr = 0;
+    int64_t nz = 0, nz_ap = 0;
+    std::vector<std::pair<uint64_t, int32_t>> order;
+    std::vector<double> hitvals;
+    for (int32_t u = 0; u < U; ++u) {
+        const int64_t tb = t_rowptr[u], te = t_rowptr[u + 1];
+        const int64_t nt = te - tb;
+        if (nt <= 0) continue;
+        ++nz;
+        const int32_t* r = rec_items + (int64_t)u * topn;
+        const int topk = topn <= rec_counts[u] ? topn : rec_counts[u];
+        auto in_test = [&](int32_t key, double* val) {
+            const int32_t* p = std::lower_bound(t_col + tb, t_col + te, key);
+            if (p != t_col + te && *p == key) { if (val) *val = t_val[p - t_col]; return true; }
+            return false;
+        };
+        // Precision / Recall / AP / RR / DCG in list order
+        int hits = 0; double tmp_prec = 0.0, dcg = 0.0; bool first = true, has_dcg = false;
+        hitvals.clear();
+        for (int i = 0; i < topk; ++i) {
+            double v = 0.0;
+            if (in_test(r[i], &v)) {
+                ++hits;
+                tmp_prec += 1.0 * hits / (i + 1);
+                if (first) { rr += 1.0 / (i + 1.0); first = false; }
+                has_dcg = true;
+                dcg += v / (log((double)(i + 2)) / log(2.0));           // Maths.log(n, 2) = Math.log(n) / Math.log(2)
+                hitvals.push_back(v);
+            }
+        }
+        prec += hits / (topn + 0.0);
+        rec += hits / (nt + 0.0);
+        if (topk != 0) { ap += tmp_prec / (double)(nt < topk ? nt : topk); ++nz_ap; }
+        if (has_dcg && dcg != 0.0) {
+            std::sort(hitvals.begin(), hitvals.end(), [](double a, double b) { return a > b; });
+            double idcg = 0.0;
+            for (size_t i = 0; i < hitvals.size(); ++i) idcg += hitvals[i] / (log((double)(i + 2)) / log(2.0));
+            if (idcg != 0.0) ndcg += dcg / idcg;
+        }
+        // AUC
+        {
+            const int num_dropped_items = num_dropped[u] - topk;
+            int rel = 0, miss = 0;
+            for (int i = 0; i < topk; ++i) { if (in_test(r[i], nullptr)) ++rel; else ++miss; }    // list keys are distinct
+            const int64_t n_items = (int64_t)num_dropped_items + topk;
+            const int64_t n_pairs = (n_items - rel) * rel;
+            if (n_pairs == 0) { auc += 0.5; continue; }
+            const uint32_t cap = jhashset_capacity(nt);
+            order.clear();
+            for (int64_t e = tb; e < te; ++e) order.push_back({((uint64_t)jhash_bucket(t_col[e], cap) << 32) | (uint32_t)(e - tb), t_col[e]});
+            std::sort(order.begin(), order.end());
+            int64_t correct = 0; int h2 = 0;
+            for (auto& o : order) {
+                bool in_rec = false;
+                for (int i = 0; i < topk; ++i) if (r[i] == o.second) { in_rec = true; break; }
+                if (!in_rec) correct += h2; else ++h2;
+            }
+            correct += (int64_t)h2 * (num_dropped_items - miss);
+            auc += (correct + 0.0) / (double)n_pairs;
+        }
+    }
+    out[0] = nz > 0 ? auc / nz : 0.0;
+    out[1] = nz_ap > 0 ? ap / nz_ap : 0.0;
+    out[2] = nz > 0 ? ndcg / nz : 0.0;
+    out[3] = nz > 0 ? prec / nz : 0.0;
+    out[4] = nz > 0 ? rec / nz : 0.0;
+    out[5] = nz > 0 ? rr / nz : 0.0;
+}
+
 LRO_API void lro_predict_pairs(int32_t model, int32_t k, const double* P, const double* Q, const double* bu,
                                const double* bi, double mu, const int32_t* us, const int32_t* is, int64_t n, double* out) {
     for (int64_t t = 0; t < n; ++t) out[t] = predict_raw(model, k, P, Q, bu, bi, mu, us[t], is[t]);

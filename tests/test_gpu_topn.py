@@ -237,3 +237,32 @@ def test_topn_tensor_core_nonfinite_items_use_exact_kernel(O, capi):
     assert np.array_equal(counts, oc) and np.array_equal(items, oi)
     assert np.array_equal(scores.view(np.int64), os_.view(np.int64))
     assert stats["fallback_users"] == U and stats["fast_users"] == 0
+
+
+# ---- ranking evaluators on the device: lists never leave the GPU between recommendRank and the measures ----
+@pytest.mark.parametrize("U,I,k,N,path", [(700, 9000, 32, 10, 2), (300, 70000, 16, 5, 2), (120, 400, 8, 10, 1), (64, 3000, 8, 64, 1)])
+def test_eval_ranking_matches_oracle(O, capi, U, I, k, N, path):
+    rng = np.random.default_rng(U + I)
+    P = rng.normal(0, 0.1, (U, k)); Q = rng.normal(0, 0.1, (I, k))
+    tr = rng_csr(O, U, I, min(0.02, 40.0 / I), 3)
+    # test rows: disjoint from train, some users without any test item, ratings 1..5
+    rowptr, col, val = [0], [], []
+    for u in range(U):
+        n = 0 if u % 7 == 0 else int(rng.integers(1, 30))
+        cand = np.setdiff1d(rng.choice(I, size=min(I, 3 * n + 5), replace=False), tr.col[tr.rowptr[u]:tr.rowptr[u + 1]])[:n]
+        cand.sort()
+        col += cand.tolist(); val += rng.integers(1, 6, cand.shape[0]).astype(float).tolist()
+        rowptr.append(len(col))
+    te = O.Csr(U, I, np.asarray(rowptr, np.int64), np.asarray(col, np.int32), np.asarray(val, np.float64))
+    with capi.Handle(capi.MODEL_PMF, k, topn_path=path) as h:
+        h.set_train_csr(U, I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q)
+        got, (items, scores, counts) = h.eval_ranking(N, te.rowptr, te.col, te.val, want_lists=True)
+        only = h.eval_ranking(N, te.rowptr, te.col, te.val)
+    oi, os_, oc = O.recommend_rank(O.PMF, U, I, k, P, Q, None, None, 0.0, tr, N)
+    assert np.array_equal(items, oi) and np.array_equal(counts, oc) and np.array_equal(scores.view(np.int64), os_.view(np.int64))
+    exp = O.eval_ranking(te, tr, N, oi, oc)
+    for name in O.RANKING_MEASURES:
+        assert abs(got[name] - exp[name]) <= 1e-12, (name, got[name], exp[name])
+        assert got[name] == only[name]
+    assert exp["Precision"] > 0 or exp["AUC"] > 0
