@@ -327,6 +327,27 @@ RecommendedList MatrixFactorizationCudaRecommender::recommendRank(const std::vec
     info("end recommend");
     return list;
 }
+RecommendedList MatrixFactorizationCudaRecommender::recommendRankAndEvaluate(const SequentialAccessSparseMatrix& test,
+                                                                             std::map<std::string, double>* measures) {
+    info("begin recommend");
+    const int n = numUsers;
+    std::vector<int32_t> items((size_t)n * topN), counts((size_t)n);
+    std::vector<double> scores((size_t)n * topN);
+    double m[6] = {0, 0, 0, 0, 0, 0};
+    check(lrk_eval_ranking(handle, topN, test.rowptr.data(), test.col.data(), test.val.data(), items.data(), scores.data(),
+                           counts.data(), m));
+    RecommendedList list;
+    for (int c = 0; c < n; ++c) {
+        list.addList();
+        for (int t = 0; t < counts[(size_t)c]; ++t) list.add(c, items[(size_t)c * topN + t], scores[(size_t)c * topN + t]);
+    }
+    if (list.size() == 0)
+        throw std::out_of_range("No item is recommended, there is something error in the recommendation algorithm! Please check it!");
+    info("end recommend");
+    static const char* names[6] = {"AUC", "AP", "NDCG", "PRECISION", "RECALL", "RR"};        // eval/Measure.java
+    if (measures) for (int i = 0; i < 6; ++i) (*measures)[std::string(names[i]) + " top " + std::to_string(topN)] = m[i];
+    return list;
+}
 RecommendedList MatrixFactorizationCudaRecommender::recommendRating(const SequentialAccessSparseMatrix& pm) {
     std::vector<double> pred((size_t)pm.size());
     double rmse = 0, mae = 0;
@@ -397,7 +418,8 @@ void RecommenderJob::runJob() {
     recommender->train(conf, train, test);
     const bool ranking = conf.getBoolean("rec.recommender.isranking");
     if (conf.getBoolean("rec.eval.enable", true)) {                                          // :205-271
-        recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
+        if (ranking && recommender->rankingTopN() <= 64) recommendedList = recommender->recommendRankAndEvaluate(test, &evaluatedMap);
+        else recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
         if (!ranking) {
             evaluatedMap["RMSE"] = evaluateRMSE(test, recommendedList);
             evaluatedMap["MAE"] = evaluateMAE(test, recommendedList);

@@ -150,6 +150,10 @@ public:
     ~MatrixFactorizationCudaRecommender() override;
     RecommendedList recommendRank() override;                                               // MatrixRecommender.java:137-201
     RecommendedList recommendRank(const std::vector<int>& userIds);
+    // recommendRank() for every user + the ranking evaluators of job/RecommenderJob.java:229-250 in one native call:
+    // measures[] = AUC, AP, NDCG, PRECISION, RECALL, RR (eval/Measure.java names) at rec.recommender.ranking.topn
+    int rankingTopN() const { return topN; }
+    RecommendedList recommendRankAndEvaluate(const SequentialAccessSparseMatrix& test, std::map<std::string, double>* measures);
     RecommendedList recommendRating(const SequentialAccessSparseMatrix& predictMatrix) override;   // :211-248
     const DenseMatrix& getUserFactors() const { return userFactors; }
     const DenseMatrix& getItemFactors() const { return itemFactors; }
