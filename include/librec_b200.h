@@ -155,12 +155,13 @@ LRK_API int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t t
              int32_t* out_items, double* out_scores, int32_t* out_counts);
 /* replaces RecommenderJob's ranking evaluation (job/RecommenderJob.java:205-271 with rec.recommender.isranking=true):
  * recommendRank() for EVERY user with the train items excluded, then
- * eval/ranking/{AUC,AveragePrecision,NormalizedDCG,Precision,Recall,ReciprocalRank}Evaluator.java against the test
+ * eval/ranking/{AUC,AveragePrecision,NormalizedDCG,Precision,Recall,ReciprocalRank,Novelty,Entropy}Evaluator.java against the test
  * CSR (ground truth = test rows in CSR order, eval/EvalContext.java:75-88; numDropped = numItems - |train row|,
  * recommender/MatrixRecommender.java:110-113) while the lists are still on the device.
- * out_measures[6] = {AUC, AP, NDCG, Precision, Recall, RR}; the three list outputs may be NULL.  1 <= topn <= 64. */
+ * out_measures[8] = {AUC, AP, NDCG, Precision, Recall, RR, Novelty, Entropy} -- the default ranking measures of
+ * eval/Measure.java:71-97; the three list outputs may be NULL.  1 <= topn <= 64. */
 LRK_API int lrk_eval_ranking(lrk_handle_t h, int32_t topn, const int64_t* t_rowptr, const int32_t* t_col, const double* t_val,
-                     int32_t* out_items, double* out_scores, int32_t* out_counts, double out_measures[6]);
+                     int32_t* out_items, double* out_scores, int32_t* out_counts, double out_measures[8]);
 /* statistics of the last lrk_topn call: users served by the tensor-core candidate path, users
  * that failed the exactness certificate and were re-done by the exact fp64 kernel, device ms */
 LRK_API int lrk_topn_stats(lrk_handle_t h, int64_t* fast_users, int64_t* fallback_users, float* ms_out);

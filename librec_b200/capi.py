@@ -215,17 +215,17 @@ class Handle:
         return items, scores, counts
 
     def eval_ranking(self, topn, t_rowptr, t_col, t_val, want_lists=False):
-        """-> dict(AUC, AP, NDCG, Precision, Recall, RR) [, (items, scores, counts)]"""
+        """-> dict(AUC, AP, NDCG, Precision, Recall, RR, Novelty, Entropy) [, (items, scores, counts)]"""
         t_rowptr = np.ascontiguousarray(t_rowptr, np.int64)
         t_col = np.ascontiguousarray(t_col, np.int32)
         t_val = np.ascontiguousarray(t_val, np.float64)
-        out = (C.c_double * 6)()
+        out = (C.c_double * 8)()
         items = np.empty((self.U, topn), np.int32) if want_lists else None
         scores = np.empty((self.U, topn), np.float64) if want_lists else None
         counts = np.empty(self.U, np.int32) if want_lists else None
         _check(load().lrk_eval_ranking(self._h, topn, _ptr(t_rowptr), _ptr(t_col), _ptr(t_val), _ptr(items), _ptr(scores),
                                        _ptr(counts), out), self._h)
-        m = dict(zip(("AUC", "AP", "NDCG", "Precision", "Recall", "RR"), list(out)))
+        m = dict(zip(("AUC", "AP", "NDCG", "Precision", "Recall", "RR", "Novelty", "Entropy"), list(out)))
         return (m, (items, scores, counts)) if want_lists else m
 
     def sgd_safeguard(self):

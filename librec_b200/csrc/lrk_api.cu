@@ -484,7 +484,7 @@ int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int
 }
 
 int lrk_eval_ranking(lrk_handle_t h, int32_t topn, const int64_t* t_rowptr, const int32_t* t_col, const double* t_val,
-                     int32_t* out_items, double* out_scores, int32_t* out_counts, double out_measures[6]) {
+                     int32_t* out_items, double* out_scores, int32_t* out_counts, double out_measures[8]) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
     LRK_REQUIRE(h, t_rowptr && out_measures, "NULL argument");
     LRK_REQUIRE(h, h->has_train && h->has_factors, "set the train CSR and the factors first");
@@ -497,27 +497,34 @@ int lrk_eval_ranking(lrk_handle_t h, int32_t topn, const int64_t* t_rowptr, cons
     cudaStream_t st = h->stream;
     LrkScratch sc;
     const int nb = lrk_ceil_div(U, 128);
-    if ((rc = lrk_scratch_begin(h, sizeof(int64_t) * ((size_t)U + 1) + (size_t)nnz * 12 + sizeof(double) * (7 * (size_t)U + 16) + 16 * 256, &sc))) return rc;
+    if ((rc = lrk_scratch_begin(h, sizeof(int64_t) * ((size_t)U + 1) + (size_t)nnz * 12 + sizeof(double) * (8 * (size_t)U + 16) +
+                                       sizeof(int32_t) * 2 * (size_t)h->I + 16 * 256, &sc))) return rc;
     int64_t* d_rp = sc.take<int64_t>((size_t)U + 1);
     int32_t* d_c = sc.take<int32_t>((size_t)std::max<int64_t>(nnz, 1));
     double* d_v = sc.take<double>((size_t)std::max<int64_t>(nnz, 1));
-    double* d_part = sc.take<double>(7 * (size_t)U);
+    double* d_part = sc.take<double>(8 * (size_t)U);
     double* d_out = sc.take<double>(8);
-    if (!d_rp || !d_c || !d_v || !d_part || !d_out) return lrk_fail(h, LRK_ERR_NOMEM, "lrk_eval_ranking", "scratch arena too small", __FILE__, __LINE__);
+    int32_t* d_purch = sc.take<int32_t>((size_t)h->I);
+    int32_t* d_reco = sc.take<int32_t>((size_t)h->I);
+    if (!d_rp || !d_c || !d_v || !d_part || !d_out || !d_purch || !d_reco) return lrk_fail(h, LRK_ERR_NOMEM, "lrk_eval_ranking", "scratch arena too small", __FILE__, __LINE__);
     LRK_CUDA(h, cudaMemcpyAsync(d_rp, t_rowptr, sizeof(int64_t) * ((size_t)U + 1), cudaMemcpyHostToDevice, st));
     if (nnz > 0) {
         LRK_CUDA(h, cudaMemcpyAsync(d_c, t_col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
         LRK_CUDA(h, cudaMemcpyAsync(d_v, t_val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
     }
-    eval_ranking_kernel<<<nb, 128, 0, st>>>(U, h->I, topn, h->tn_items, h->tn_counts, d_rp, d_c, d_v, h->d_rowptr, d_part);
+    // rec.eval.item.purchase.num = train + test column counts (MatrixRecommender.java:118-122)
+    LRK_CUDA(h, cudaMemsetAsync(d_purch, 0, sizeof(int32_t) * (size_t)h->I, st));
+    LRK_CUDA(h, cudaMemsetAsync(d_reco, 0, sizeof(int32_t) * (size_t)h->I, st));
+    if (h->nnz > 0) { item_count_add_kernel<<<lrk_ceil_div(h->nnz, 256), 256, 0, st>>>(h->d_col, h->nnz, d_purch); LRK_LAUNCH_CHECK(h); }
+    if (nnz > 0) { item_count_add_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(d_c, nnz, d_purch); LRK_LAUNCH_CHECK(h); }
+    eval_ranking_kernel<<<nb, 128, 0, st>>>(U, h->I, topn, h->tn_items, h->tn_counts, d_rp, d_c, d_v, h->d_rowptr, d_purch, d_reco, d_part);
     LRK_LAUNCH_CHECK(h);
-    eval_ranking_final_kernel<<<7, 256, 0, st>>>(d_part, U, d_out);
+    eval_ranking_final_kernel<<<8, 256, 0, st>>>(d_part, U, d_reco, h->I, d_out);
     LRK_LAUNCH_CHECK(h);
     double res[8];
-    LRK_CUDA(h, cudaMemcpyAsync(res, d_out, sizeof(double) * 7, cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaMemcpyAsync(res, d_out, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
     if ((rc = topn_lists_to_host(h, U, topn, out_items, out_scores, out_counts))) return rc;
-    // res[6] = users that count, res[1] carries AP's own denominator in the kernel (see eval_ranking_final_kernel)
-    for (int m = 0; m < 6; ++m) out_measures[m] = res[m];
+    for (int m = 0; m < 8; ++m) out_measures[m] = res[m];
     return LRK_OK;
 }
 

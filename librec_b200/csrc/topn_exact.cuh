@@ -481,10 +481,20 @@ __device__ __forceinline__ int64_t er_find(const int32_t* __restrict__ col, int6
 }
 __global__ void eval_ranking_kernel(int32_t U, int32_t I, int topn, const int32_t* __restrict__ rec_items, const int32_t* __restrict__ rec_counts,
                                     const int64_t* __restrict__ t_rowptr, const int32_t* __restrict__ t_col, const double* __restrict__ t_val,
-                                    const int64_t* __restrict__ train_rowptr, double* __restrict__ part) {
+                                    const int64_t* __restrict__ train_rowptr, const int32_t* __restrict__ purchased,
+                                    int32_t* __restrict__ reco_cnt, double* __restrict__ part) {
     const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= U) return;
-    double auc = 0, ap = 0, ndcg = 0, prec = 0, rec = 0, rr = 0, flags = 0;
+    double auc = 0, ap = 0, ndcg = 0, prec = 0, rec = 0, rr = 0, flags = 0, info = 0;
+    {   // Novelty / Entropy terms: every user's list counts (NoveltyEvaluator.java:70-82, EntropyEvaluator.java:68-76)
+        const int topk_all = topn <= rec_counts[u] ? topn : rec_counts[u];
+        for (int i = 0; i < topk_all; ++i) {
+            const int32_t it = rec_items[(int64_t)u * topn + i];
+            atomicAdd(reco_cnt + it, 1);
+            const int32_t c = purchased[it];
+            if (c > 0) info += -log(((double)c) / U);
+        }
+    }
     const int64_t tb = t_rowptr[u], te = t_rowptr[u + 1], nt = te - tb;
     if (nt > 0) {
         flags = 1;
@@ -541,16 +551,28 @@ __global__ void eval_ranking_kernel(int32_t U, int32_t I, int topn, const int32_
     }
     part[0 * (size_t)U + u] = auc; part[1 * (size_t)U + u] = ap; part[2 * (size_t)U + u] = ndcg;
     part[3 * (size_t)U + u] = prec; part[4 * (size_t)U + u] = rec; part[5 * (size_t)U + u] = rr; part[6 * (size_t)U + u] = flags;
+    part[7 * (size_t)U + u] = info;
 }
-// block m sums measure m over the users (fixed order); the mean is over the users that count
-__global__ void eval_ranking_final_kernel(const double* __restrict__ part, int32_t U, double* __restrict__ out) {
+__global__ void item_count_add_kernel(const int32_t* __restrict__ col, int64_t n, int32_t* __restrict__ cnt) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) atomicAdd(cnt + col[t], 1);
+}
+// block m sums measure m over the users (fixed order); the mean is over the users that count.
+// m = 6: Novelty = sum of self-information / (U ln 2); m = 7: Entropy over the items' list frequencies.
+__global__ void eval_ranking_final_kernel(const double* __restrict__ part, int32_t U, const int32_t* __restrict__ reco_cnt, int32_t I,
+                                          double* __restrict__ out) {
     __shared__ double s_sum[256], s_cnt[256];
     const int m = blockIdx.x;
     double sum = 0.0, cnt = 0.0;
-    for (int32_t u = threadIdx.x; u < U; u += blockDim.x) {
+    if (m == 7) {
+        for (int32_t i = threadIdx.x; i < I; i += blockDim.x) {
+            const int32_t c = reco_cnt[i];
+            if (c > 0) { const double p = ((double)c) / U; sum += p * (-log(p)); }
+        }
+    } else for (int32_t u = threadIdx.x; u < U; u += blockDim.x) {
         const int f = (int)part[6 * (size_t)U + u];
         if (m < 6) { sum += part[(size_t)m * U + u]; cnt += (m == 1) ? ((f & 2) ? 1.0 : 0.0) : ((f & 1) ? 1.0 : 0.0); }
-        else cnt += (f & 1) ? 1.0 : 0.0;
+        else sum += part[7 * (size_t)U + u];
     }
     s_sum[threadIdx.x] = sum; s_cnt[threadIdx.x] = cnt;
     __syncthreads();
@@ -558,5 +580,6 @@ __global__ void eval_ranking_final_kernel(const double* __restrict__ part, int32
         if ((int)threadIdx.x < st) { s_sum[threadIdx.x] += s_sum[threadIdx.x + st]; s_cnt[threadIdx.x] += s_cnt[threadIdx.x + st]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[m] = m < 6 ? (s_cnt[0] > 0.0 ? s_sum[0] / s_cnt[0] : 0.0) : s_cnt[0];
+    if (threadIdx.x == 0)
+        out[m] = m < 6 ? (s_cnt[0] > 0.0 ? s_sum[0] / s_cnt[0] : 0.0) : (m == 6 ? s_sum[0] / (U * log(2.0)) : s_sum[0] / log(2.0));
 }

@@ -333,7 +333,7 @@ RecommendedList MatrixFactorizationCudaRecommender::recommendRankAndEvaluate(con
     const int n = numUsers;
     std::vector<int32_t> items((size_t)n * topN), counts((size_t)n);
     std::vector<double> scores((size_t)n * topN);
-    double m[6] = {0, 0, 0, 0, 0, 0};
+    double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     check(lrk_eval_ranking(handle, topN, test.rowptr.data(), test.col.data(), test.val.data(), items.data(), scores.data(),
                            counts.data(), m));
     RecommendedList list;
@@ -344,8 +344,8 @@ RecommendedList MatrixFactorizationCudaRecommender::recommendRankAndEvaluate(con
     if (list.size() == 0)
         throw std::out_of_range("No item is recommended, there is something error in the recommendation algorithm! Please check it!");
     info("end recommend");
-    static const char* names[6] = {"AUC", "AP", "NDCG", "PRECISION", "RECALL", "RR"};        // eval/Measure.java
-    if (measures) for (int i = 0; i < 6; ++i) (*measures)[std::string(names[i]) + " top " + std::to_string(topN)] = m[i];
+    static const char* names[8] = {"AUC", "AP", "NDCG", "PRECISION", "RECALL", "RR", "Novelty", "Entropy"};   // eval/Measure.java
+    if (measures) for (int i = 0; i < 8; ++i) (*measures)[std::string(names[i]) + " top " + std::to_string(topN)] = m[i];
     return list;
 }
 RecommendedList MatrixFactorizationCudaRecommender::recommendRating(const SequentialAccessSparseMatrix& pm) {

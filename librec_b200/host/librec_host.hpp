@@ -151,7 +151,7 @@ public:
     RecommendedList recommendRank() override;                                               // MatrixRecommender.java:137-201
     RecommendedList recommendRank(const std::vector<int>& userIds);
     // recommendRank() for every user + the ranking evaluators of job/RecommenderJob.java:229-250 in one native call:
-    // measures[] = AUC, AP, NDCG, PRECISION, RECALL, RR (eval/Measure.java names) at rec.recommender.ranking.topn
+    // measures[] = AUC, AP, NDCG, PRECISION, RECALL, RR, Novelty, Entropy (eval/Measure.java names) at rec.recommender.ranking.topn
     int rankingTopN() const { return topN; }
     RecommendedList recommendRankAndEvaluate(const SequentialAccessSparseMatrix& test, std::map<std::string, double>* measures);
     RecommendedList recommendRating(const SequentialAccessSparseMatrix& predictMatrix) override;   // :211-248

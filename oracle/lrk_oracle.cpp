@@ -533,7 +533,10 @@ LRO_API void lro_eval_rating(int32_t model, int32_t U, const int64_t* t_rowptr, 
 // ((h ^ h>>>16) & (cap-1), cap = 16 doubled while size > 0.75 cap), insertion order inside a bucket.
 // Java quirks kept: Precision divides by topN, not by the list length; AP divides by min(|test|, topK);
 // "NDCG" takes its ideal DCG only from the ground-truth entries that were hit.
-// out[6] = {AUC, AP, NDCG, Precision, Recall, RR}, each the mean over the users that count.
+// out[8] = {AUC, AP, NDCG, Precision, Recall, RR, Novelty, Entropy}; the first six are means over the users that count.
+// Novelty (NoveltyEvaluator.java:62-84): self-information of the recommended items under the purchase probability
+// count_i / numUsers, count_i = train + test column counts (MatrixRecommender.java:118-122), summed over ALL users'
+// lists, / (numUsers ln 2).  Entropy (EntropyEvaluator.java:60-90): entropy in bits of the items' frequency in the lists.
 // -------------------------------------------------------------------------------------
 static inline uint32_t jhash_bucket(int32_t key, uint32_t cap) {
     const uint32_t h = (uint32_t)key;
@@ -546,8 +549,25 @@ static inline uint32_t jhashset_capacity(int64_t n) {          // HashMap.putVal
 }
 LRO_API void lro_eval_ranking(int32_t U, int32_t topn, const int32_t* rec_items, const int32_t* rec_counts,
                               const int64_t* t_rowptr, const int32_t* t_col, const double* t_val,
-                              const int32_t* num_dropped, double* out) {
+                              const int32_t* num_dropped, const int32_t* item_purchase_num, int32_t I, double* out) {
     double auc = 0, ap = 0, ndcg = 0, prec = 0, rec = 0, rr = 0;
+    {
+        double sum_info = 0.0;
+        std::vector<int32_t> reco_cnt((size_t)I, 0);
+        for (int32_t u = 0; u < U; ++u) {
+            const int topk = topn <= rec_counts[u] ? topn : rec_counts[u];
+            for (int i = 0; i < topk; ++i) {
+                const int32_t it = rec_items[(int64_t)u * topn + i];
+                reco_cnt[(size_t)it]++;
+                const int32_t c = item_purchase_num[it];
+                if (c > 0) sum_info += -log(((double)c) / U);
+            }
+        }
+        out[6] = sum_info / (U * log(2.0));
+        double sum_ent = 0.0;
+        for (int32_t i = 0; i < I; ++i) if (reco_cnt[(size_t)i] > 0) { const double p = ((double)reco_cnt[(size_t)i]) / U; sum_ent += p * (-log(p)); }
+        out[7] = sum_ent / log(2.0);
+    }
     int64_t nz = 0, nz_ap = 0;
     std::vector<std::pair<uint64_t, int32_t>> order;
     std::vector<double> hitvals;

@@ -87,7 +87,7 @@ def lib():
                             C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
     L.lro_eval_rating.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _f64p, C.c_int32, _f64p, _f64p, C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
-    L.lro_eval_ranking.argtypes = [C.c_int32, C.c_int32, _i32p, _i32p, _i64p, _i32p, _f64p, _i32p, _f64p]
+    L.lro_eval_ranking.argtypes = [C.c_int32, C.c_int32, _i32p, _i32p, _i64p, _i32p, _f64p, _i32p, _i32p, C.c_int32, _f64p]
     L.lro_predict_pairs.argtypes = [C.c_int32, C.c_int32, _f64p, _f64p, C.c_void_p, C.c_void_p, C.c_double,
                                     _i32p, _i32p, C.c_int64, _f64p]
     L.lro_recommend_rank.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f64p, _f64p, C.c_void_p, C.c_void_p,
@@ -182,15 +182,16 @@ def eval_rating(model, te, k, P, Q, bu, bi, mu, min_rate, max_rate, want_pred=Fa
     return (rmse.value, mae.value, pred) if want_pred else (rmse.value, mae.value)
 
 
-RANKING_MEASURES = ("AUC", "AP", "NDCG", "Precision", "Recall", "RR")
+RANKING_MEASURES = ("AUC", "AP", "NDCG", "Precision", "Recall", "RR", "Novelty", "Entropy")
 
 
 def eval_ranking(te, tr, topn, items, counts):
-    """ranking evaluators of the reference over top-N lists for ALL users -> dict(AUC, AP, NDCG, Precision, Recall, RR)"""
-    out = np.zeros(6, np.float64)
+    """ranking evaluators of the reference over top-N lists for ALL users -> dict over RANKING_MEASURES"""
+    out = np.zeros(8, np.float64)
     num_dropped = (te.I - np.diff(tr.rowptr)).astype(np.int32)
+    purchased = (np.bincount(tr.col, minlength=te.I) + np.bincount(te.col, minlength=te.I)).astype(np.int32)
     lib().lro_eval_ranking(te.U, topn, np.ascontiguousarray(items, np.int32), np.ascontiguousarray(counts, np.int32),
-                           te.rowptr, te.col, te.val, num_dropped, out)
+                           te.rowptr, te.col, te.val, num_dropped, purchased, te.I, out)
     return dict(zip(RANKING_MEASURES, out.tolist()))
 
 

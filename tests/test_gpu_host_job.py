@@ -135,7 +135,8 @@ rec.random.seed=1
     assert len(losses) == 20 and losses[-1] < losses[0]
     # the job's ranking measures (job/RecommenderJob.java:229-262) come from the device evaluators and equal the oracle's
     exp = O.eval_ranking(te, ones, 10, oi, oc)
-    for java_name, name in [("PRECISION", "Precision"), ("RECALL", "Recall"), ("AUC", "AUC"), ("AP", "AP"), ("NDCG", "NDCG"), ("RR", "RR")]:
+    for java_name, name in [("PRECISION", "Precision"), ("RECALL", "Recall"), ("AUC", "AUC"), ("AP", "AP"), ("NDCG", "NDCG"), ("RR", "RR"),
+                            ("Novelty", "Novelty"), ("Entropy", "Entropy")]:
         got = job.metric("%s top 10" % java_name)
         assert abs(got - exp[name]) <= 1e-12, (java_name, got, exp[name])
         assert any(l.startswith("Evaluator value:%s top 10 is " % java_name) for l in job.log())

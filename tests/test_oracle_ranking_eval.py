@@ -104,6 +104,23 @@ def java_eval(topn, rec_items, rec_counts, t_rowptr, t_col, t_val, num_dropped):
     return out
 
 
+def java_novelty_entropy(topn, rec_items, rec_counts, purchased, I):
+    U = len(rec_counts)
+    info, reco = 0.0, [0] * I
+    for u in range(U):
+        for key in rec_items[u][:min(topn, rec_counts[u])]:
+            reco[int(key)] += 1
+            c = int(purchased[int(key)])
+            if c > 0:
+                info += -math.log(c / U)
+    ent = 0.0
+    for c in reco:
+        if c > 0:
+            p = c / U
+            ent += p * (-math.log(p))
+    return info / (U * math.log(2)), ent / math.log(2)
+
+
 def _random_case(rng, U, I, topn, max_test):
     rowptr, col, val = [0], [], []
     for u in range(U):
@@ -125,19 +142,23 @@ def test_ranking_evaluators_match_java_replay(O):
     rng = np.random.default_rng(0)
     for U, I, topn, max_test in [(40, 300, 10, 30), (25, 200000, 5, 60), (10, 50, 10, 3), (30, 100000, 20, 120)]:
         rowptr, col, val, rec, counts, dropped = _random_case(rng, U, I, topn, max_test)
-        out = np.zeros(6)
-        O.lib().lro_eval_ranking(U, topn, rec, counts, rowptr, col, val, dropped, out)
+        out = np.zeros(8)
+        purchased = rng.integers(0, 2 * U, I).astype(np.int32)
+        safe = np.where(rec >= 0, rec, 0).astype(np.int32)
+        O.lib().lro_eval_ranking(U, topn, safe, counts, rowptr, col, val, dropped, purchased, I, out)
         exp = java_eval(topn, rec, counts, rowptr, col, val, dropped)
+        exp["Novelty"], exp["Entropy"] = java_novelty_entropy(topn, rec, counts, purchased, I)
         for name, got in zip(O.RANKING_MEASURES, out):
-            assert abs(got - exp[name]) <= 1e-14, (name, got, exp[name])
+            assert abs(got - exp[name]) <= 1e-12 * max(1.0, abs(exp[name])), (name, got, exp[name])
 
 
 def test_ranking_evaluators_hand_worked(O):
     # one user, test items {2:5.0, 7:3.0, 9:1.0}, list [7, 4, 2], topN 5, numDropped 20
     rowptr = np.array([0, 3, 3], np.int64); col = np.array([2, 7, 9], np.int32); val = np.array([5.0, 3.0, 1.0])
     rec = np.array([[7, 4, 2, -1, -1], [1, 2, 3, 4, 5]], np.int32); counts = np.array([3, 5], np.int32)
-    out = np.zeros(6)
-    O.lib().lro_eval_ranking(2, 5, rec, counts, rowptr, col, val, np.array([20, 20], np.int32), out)
+    out = np.zeros(8)
+    rec = np.where(rec >= 0, rec, 0).astype(np.int32)
+    O.lib().lro_eval_ranking(2, 5, rec, counts, rowptr, col, val, np.array([20, 20], np.int32), np.ones(12, np.int32), 12, out)
     m = dict(zip(O.RANKING_MEASURES, out))
     assert m["Precision"] == 2 / 5.0 and m["Recall"] == 2 / 3.0 and m["RR"] == 1.0          # user 1 has no test items
     assert abs(m["AP"] - (1.0 / 1 + 2.0 / 3) / 3) < 1e-15                                    # min(|test| = 3, topK = 3)
@@ -146,3 +167,6 @@ def test_ranking_evaluators_hand_worked(O):
     # AUC: iteration order of {2,7,9} in a 16-bucket table is 2,7,9; hits so far when 9 (not recommended) is met: 2;
     # numDroppedItems = 20 - 3 = 17, numMiss = 1 -> correct = 2 + 2 * 16 = 34, pairs = (17 + 3 - 2) * 2 = 36
     assert abs(m["AUC"] - 34 / 36) < 1e-15
+    # every item bought once, 2 users: 8 recommended entries x -ln(1/2) / (2 ln 2) = 4 bits; list frequencies
+    # {1:1, 2:2, 3:1, 4:2, 5:1, 7:1} of 2 lists -> 4 items at p = 1/2 -> 2 bits
+    assert abs(m["Novelty"] - 4.0) < 1e-14 and abs(m["Entropy"] - 2.0) < 1e-14
