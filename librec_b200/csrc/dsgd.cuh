@@ -259,6 +259,8 @@ static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64
         for (int b = 0; b < world; ++b) s->seg_off[(size_t)b + 1] = s->seg_off[(size_t)b] + local_cnt[(size_t)b];
         uint32_t md[64] = {0};
         if (e == cudaSuccess && rc_k == LRK_OK) e = cudaMemcpy(md, w.max_deg, sizeof(uint32_t) * 64, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && rc_k == LRK_OK) rc_k = lrk_dev_alloc(h, &h->d_item_deg, (size_t)I);
+        if (e == cudaSuccess && rc_k == LRK_OK) e = cudaMemcpy(h->d_item_deg, w.deg, sizeof(uint32_t) * (size_t)I, cudaMemcpyDeviceToDevice);
         s->seg_hot_share.assign((size_t)world, 0.0);
         for (int b = 0; b < world; ++b) if (local_cnt[(size_t)b] > 0) s->seg_hot_share[(size_t)b] = (double)md[b] / (double)local_cnt[(size_t)b];
         cudaFree(d_val); cudaFree(row_of); cudaFree(keys); cudaFree(keys2); cudaFree(idx); cudaFree(perm); cudaFree(tmp); cudaFree(w32);
@@ -363,6 +365,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
             }
             sp.hot_share = (h->cfg.model != LRK_MODEL_BPR && (size_t)b < s->seg_hot_share.size()) ? s->seg_hot_share[(size_t)b] : 0.0;
             sp.conc_div = h->conc_div;
+            sp.item_deg = (h->cfg.model != LRK_MODEL_BPR && h->d_item_deg) ? h->d_item_deg + s->bounds[(size_t)b] : nullptr;   // block-local item ids
             int rc = sgd_launch(h, sp);
             if (rc) return rc;
         }

@@ -31,6 +31,7 @@ struct lrk_handle_s {
     float* d_sr = nullptr;
     bool has_train = false;
     double hot_share = 0.0;   // largest share one item has of the train ratings (stability cap of the SGD grid)
+    uint32_t* d_item_deg = nullptr;   // ratings per item in this handle's shard (staleness-aware step of run tiles, sgd.cuh)
 
     // factors: fp32 working copies (padded rows) + fp64 masters (dense rows, what Java sees)
     float *P32 = nullptr, *Q32 = nullptr, *bu32 = nullptr, *bi32 = nullptr;

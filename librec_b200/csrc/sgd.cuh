@@ -24,9 +24,13 @@
 // 8 ratings, accumulates their item-side deltas in registers and issues ONE vector RED for them (an
 // 8-rating mini-batch for that item; the user side is untouched): 8x fewer row reads and REDs.
 //
-// Stability: B ratings of one item in flight at once act like one step of size lr*B on its bias
-// (e' = (1 - lr*B) e), so lr*B must stay well below 2.  With the hottest item holding a share s of the
-// launch, B = s * (ratings in flight): sgd_grid_for caps the grid at lr * s * in-flight <= 1.
+// Stability: B ratings of one item in flight at once act like ONE step of size lr*B on its bias
+// (e' = (1 - lr*B) e; unstable from lr*B = 2), whereas the reference's sequential walk over the same B ratings
+// contracts the error by (1 - lr)^B ~ exp(-lr*B) and never overshoots.  With x = lr * B_i,
+// B_i = deg_i * (ratings in flight) / n, the item-side delta of a run tile is therefore scaled by
+// (1 - exp(-x)) / x: identical to plain SGD for x -> 0, the sequential limit for popular items, stable at any
+// concurrency.  (Without it the grid had to be capped at lr * s * in-flight <= 1, s = share of the hottest item,
+// which left 142 of 592 CTAs at 8 DSGD strata; sgd_grid_for keeps that cap for launches without degrees.)
 #pragma once
 #include "lrk_common.cuh"
 
@@ -47,6 +51,10 @@ struct SgdParams {
     int64_t tile_mul;
     double hot_share;       // largest share one item has of this launch's ratings (0 = unknown): stability cap of the grid
     int conc_div;           // >= 1: divisor of the grid (rollback safeguard, lrk_common.cuh)
+    // staleness-aware step of item-run tiles: item_deg[i] = ratings of item i in this launch (NULL = off),
+    // inflight_frac = (ratings in flight) / n, filled in by the launcher
+    const uint32_t* item_deg;
+    float inflight_frac;
     // BPR only
     const int64_t* __restrict__ rowptr;
     const int32_t* __restrict__ col;
@@ -147,6 +155,11 @@ __global__ void __launch_bounds__(256) sgd_rating_epoch_kernel(SgdParams p) {
             constexpr int HOT_CHUNK = (STEPS >= 4) ? STEPS / 4 : 1;
             float4 pn[V];
             float bun = 0.f;
+            float damp = 1.f;
+            if (p.item_deg) {
+                const float x = lr * (float)__ldg(p.item_deg + i0) * p.inflight_frac;
+                if (x > 1e-3f) damp = (1.f - __expf(-x)) / x;
+            }
             int32_t un = __shfl_sync(0xffffffffu, u_l, grp);
             float rn = __shfl_sync(0xffffffffu, r_l, grp);
 #pragma unroll
@@ -218,8 +231,11 @@ __global__ void __launch_bounds__(256) sgd_rating_epoch_kernel(SgdParams p) {
                 }
                 if (grp == 0) {
 #pragma unroll
-                    for (int v = 0; v < V; ++v) apply4<ATOMIC>(p.Q + (int64_t)i0 * p.ld + (v * G + sub) * 4, q[v], dq[v]);
-                    if (BIASED && sub == 0) apply1<ATOMIC>(p.bi + i0, bi0, dbi);
+                    for (int v = 0; v < V; ++v) {
+                        dq[v].x *= damp; dq[v].y *= damp; dq[v].z *= damp; dq[v].w *= damp;
+                        apply4<ATOMIC>(p.Q + (int64_t)i0 * p.ld + (v * G + sub) * 4, q[v], dq[v]);
+                    }
+                    if (BIASED && sub == 0) apply1<ATOMIC>(p.bi + i0, bi0, dbi * damp);
                 }
             }
             loss_d += (double)loss_f;
@@ -515,7 +531,7 @@ static int sgd_grid_for(lrk_handle_s* h, K kernel, int64_t n, int rps, int* grid
     if (need < grid) grid = need;
     const int64_t stale_cap = (n / 16) / (8 * (int64_t)rps * 2);
     if (stale_cap < grid) grid = stale_cap;
-    if (lr > 0.0 && hot_share > 0.0) {
+    if (lr > 0.0 && hot_share > 0.0) {      // only for launches without per-item degrees (no staleness-aware step)
         // a warp keeps at most 8 ratings of one item in flight (run-tile chunk; 2 steps of the general path)
         const double in_flight_max = 1.0 / (lr * hot_share);
         const int64_t hot_cap = (int64_t)(in_flight_max / (8.0 * (double)(rps > 8 ? rps : 8)));
@@ -541,13 +557,16 @@ static int64_t sgd_tile_mul(int64_t n) {
 template <int G, int V>
 static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp_in) {
     SgdParams sp = sp_in;
+    static const bool no_damp = getenv("LRK_SGD_NODAMP") && atoi(getenv("LRK_SGD_NODAMP"));    // A/B probe: fall back to the grid cap
+    if (no_damp) sp.item_deg = nullptr;
     sp.tile_mul = sgd_tile_mul(sp.n);
     const bool atomic = h->cfg.update_mode == LRK_UPDATE_ATOMIC;
     int grid = 1;
 #define LRK_GO(KERN)                                                          \
     do {                                                                      \
-        int rc__ = sgd_grid_for(h, KERN, sp.n, 32 / G, &grid, (double)sp.lr, sp.hot_share, sp.conc_div); \
+        int rc__ = sgd_grid_for(h, KERN, sp.n, 32 / G, &grid, (double)sp.lr, sp.item_deg ? 0.0 : sp.hot_share, sp.conc_div); \
         if (rc__) return rc__;                                                \
+        sp.inflight_frac = (float)((double)grid * 8.0 * (double)(32 / G > 8 ? 32 / G : 8) / (double)(sp.n > 0 ? sp.n : 1)); \
         KERN<<<grid, 256, 0, h->stream>>>(sp);                                \
     } while (0)
     if (h->cfg.model == LRK_MODEL_BIASEDMF) {

@@ -214,6 +214,8 @@ static int stage_coo_from_csr(lrk_handle_s* h, const int64_t* d_rowptr, const in
         coo_gather_kernel<<<nb, 256, 0, st>>>(perm, row_of, d_col, d_val, nnz, su, si, sr);
         LRK_LAUNCH_CHECK(h);
         uint32_t max_deg = 0;
+        if ((rc = lrk_dev_alloc(h, &h->d_item_deg, (size_t)I))) return rc;
+        LRK_CUDA(h, cudaMemcpyAsync(h->d_item_deg, w.deg, sizeof(uint32_t) * (size_t)I, cudaMemcpyDeviceToDevice, st));
         LRK_CUDA(h, cudaMemcpyAsync(&max_deg, w.max_deg, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         LRK_CUDA(h, cudaStreamSynchronize(st));
         h->hot_share = (double)max_deg / (double)nnz;
