@@ -28,6 +28,15 @@ def load():
     L.lrh_job_list_size.restype = C.c_int64
     L.lrh_job_list_size.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
     L.lrh_job_list_copy.argtypes = [C.c_void_p] * 4
+    L.lrh_datamodel_build.restype = C.c_void_p
+    L.lrh_datamodel_build.argtypes = [C.c_char_p]
+    L.lrh_datamodel_destroy.argtypes = [C.c_void_p]
+    L.lrh_datamodel_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    L.lrh_datamodel_copy.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
+    L.lrh_datamodel_raw_id.restype = C.c_char_p
+    L.lrh_datamodel_raw_id.argtypes = [C.c_void_p, C.c_int, C.c_int32]
+    L.lrh_job_save_result.restype = C.c_char_p
+    L.lrh_job_save_result.argtypes = [C.c_void_p]
     L.lrh_randoms_seed.argtypes = [C.c_longlong]
     L.lrh_randoms_uniform_int.restype = C.c_int
     L.lrh_randoms_uniform_int.argtypes = [C.c_int]
@@ -44,6 +53,37 @@ def load():
 
 class LibrecException(Exception):
     pass
+
+
+class TextDataModel:
+    """data/model/TextDataModel.java: properties (dfs.data.dir, data.input.path, data.convert.binarize.threshold,
+    data.splitter.trainset.ratio, rec.random.seed) -> preference / train / test as flat CSR"""
+
+    def __init__(self, properties):
+        text = properties if isinstance(properties, str) else "\n".join("%s=%s" % kv for kv in properties.items())
+        self._L = load()
+        self._h = self._L.lrh_datamodel_build(text.encode())
+        if not self._h:
+            raise LibrecException(self._L.lrh_last_error().decode())
+
+    def matrix(self, which):
+        """which: 'preference' | 'train' | 'test' -> (U, I, rowptr, col, val)"""
+        w = {"preference": 0, "train": 1, "test": 2}[which]
+        U, I, n = C.c_int32(), C.c_int32(), C.c_int64()
+        self._L.lrh_datamodel_dims(self._h, w, C.byref(U), C.byref(I), C.byref(n))
+        rowptr = np.zeros(U.value + 1, np.int64); col = np.zeros(n.value, np.int32); val = np.zeros(n.value, np.float64)
+        self._L.lrh_datamodel_copy(self._h, w, rowptr.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p))
+        return U.value, I.value, rowptr, col, val
+
+    def raw_id(self, is_item, inner):
+        return self._L.lrh_datamodel_raw_id(self._h, int(is_item), inner).decode()
+
+    def close(self):
+        if self._h:
+            self._L.lrh_datamodel_destroy(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 class RecommenderJob:
@@ -73,6 +113,12 @@ class RecommenderJob:
             raise LibrecException(self._L.lrh_last_error().decode())
         if rc:
             raise IndexError(self._L.lrh_last_error().decode())
+
+    def save_result(self):
+        p = self._L.lrh_job_save_result(self._h)
+        if p is None:
+            raise LibrecException(self._L.lrh_last_error().decode())
+        return p.decode()
 
     def metric(self, name):
         return self._L.lrh_job_metric(self._h, name.encode())

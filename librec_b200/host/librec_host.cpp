@@ -1,5 +1,8 @@
 // Host-side mirror of the reference's recommender plugin interface; see librec_host.hpp.
 #include "librec_host.hpp"
+#include <sys/stat.h>
+#include <unordered_map>
+#include <string_view>
 
 #include <algorithm>
 #include <charconv>
@@ -409,11 +412,144 @@ double evaluateMAE(const SequentialAccessSparseMatrix& test, const RecommendedLi
     return n > 0 ? ae / (double)n : 0.0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// TextDataModel: text file -> flat CSR -> ratio split
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct SvHash { size_t operator()(const std::string_view& v) const { return std::hash<std::string_view>()(v); } };
+inline bool is_sep(char c) { return c == '\t' || c == ';' || c == ',' || c == ' '; }
+inline bool is_blank_line(const char* b, const char* e) {       // String.trim().isEmpty(): every char <= U+0020
+    for (; b < e; ++b) if ((unsigned char)*b > ' ') return false;
+    return true;
+}
+}  // namespace
+
+void TextDataModel::buildConvert() {
+    const std::string dir = conf.get("dfs.data.dir", "");
+    const std::string path = (dir.empty() ? std::string() : dir + "/") + conf.get("data.input.path", "");
+    const std::string fmt = conf.get("data.column.format", "UIR");
+    const double binThold = conf.getDouble("data.convert.binarize.threshold", -1.0);
+    const size_t nfields = (fmt == "UIRT" || fmt == "uirt") ? 4 : 3;
+    log.push_back("Dataset: [" + path + "]");
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) throw LibrecException("TextDataConvertor: cannot read " + path);
+    std::string buf;
+    {
+        char tmp[1 << 16];
+        size_t got;
+        while ((got = fread(tmp, 1, sizeof tmp, fp)) > 0) buf.append(tmp, got);
+        fclose(fp);
+    }
+    // pass 1: one (user, item, rating) per line, inner ids in first-seen order; ids are views into `buf`
+    std::unordered_map<std::string_view, int32_t, SvHash> umap, imap;
+    std::vector<std::string_view> uview, iview;
+    std::vector<uint64_t> keys;          // (user << 32 | item), line order
+    std::vector<double> rates;
+    const char* p = buf.data();
+    const char* const end = p + buf.size();
+    while (p < end) {
+        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = eol ? eol : end;
+        const char* lend = (le > p && le[-1] == '\r') ? le - 1 : le;
+        if (is_blank_line(p, lend)) break;                                                   // TextDataConvertor.java:176-178
+        // fields: split at every separator character, drop trailing empty fields
+        std::string_view f[4]; size_t nf = 0, total = 0;
+        const char* fb = p;
+        for (const char* c = p;; ++c) {
+            if (c == lend || is_sep(*c)) {
+                if (nf < 4) f[nf] = std::string_view(fb, (size_t)(c - fb));
+                if (c > fb) total = nf + 1;                                                  // index of the last non-empty field + 1
+                ++nf;
+                if (c == lend) break;
+                fb = c + 1;
+            }
+        }
+        if (total < nfields) throw std::out_of_range("TextDataConvertor: line with fewer than " + std::to_string(nfields) + " fields: " + std::string(p, (size_t)(lend - p)));
+        auto idOf = [](std::unordered_map<std::string_view, int32_t, SvHash>& m, std::vector<std::string_view>& views, std::string_view key) {
+            auto it = m.find(key);
+            if (it != m.end()) return it->second;
+            const int32_t id = (int32_t)m.size();                                            // DataFrame.java:370-379
+            m.emplace(key, id); views.push_back(key);
+            return id;
+        };
+        const int32_t u = idOf(umap, uview, f[0]), i = idOf(imap, iview, f[1]);
+        const std::string rs(f[2]);
+        char* pe = nullptr;
+        const double r = strtod(rs.c_str(), &pe);
+        if (rs.empty() || (pe && *pe != 0)) throw std::invalid_argument("NumberFormatException: For input string: \"" + rs + "\"");
+        keys.push_back(((uint64_t)(uint32_t)u << 32) | (uint32_t)i);
+        rates.push_back(r);
+        p = eol ? eol + 1 : end;
+    }
+    const int32_t U = (int32_t)umap.size(), I = (int32_t)imap.size();
+    // pass 2: order by (user, item, line); the first entry of every (user, item) run is the earliest line -> it wins
+    const size_t n = keys.size();
+    std::vector<uint32_t> ord(n);
+    for (size_t t = 0; t < n; ++t) ord[t] = (uint32_t)t;
+    std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return keys[a] != keys[b] ? keys[a] < keys[b] : a < b; });
+    preference = SequentialAccessSparseMatrix();
+    preference.numRows = U; preference.numCols = I;
+    preference.rowptr.assign((size_t)U + 1, 0);
+    preference.col.reserve(n); preference.val.reserve(n);
+    for (size_t t = 0; t < n; ++t) {
+        const uint32_t a = ord[t];
+        if (t > 0 && keys[ord[t - 1]] == keys[a]) continue;
+        double r = rates[a];
+        if (binThold >= 0) r = r > binThold ? 1.0 : -1.0;                                    // DataFrame.java:251-253
+        preference.col.push_back((int32_t)(keys[a] & 0xffffffffu));
+        preference.val.push_back(r);
+        preference.rowptr[(size_t)(keys[a] >> 32) + 1]++;
+    }
+    for (int32_t u = 0; u < U; ++u) preference.rowptr[(size_t)u + 1] += preference.rowptr[(size_t)u];
+    userIds.assign(uview.begin(), uview.end());
+    itemIds.assign(iview.begin(), iview.end());
+    log.push_back("user number: " + std::to_string(U) + ",\t item number is: " + std::to_string(I));
+}
+
+void TextDataModel::buildSplitter() {
+    const std::string splitter = conf.get("data.model.splitter", "ratio");
+    const std::string by = conf.get("data.splitter.ratio", "rating");
+    if (!(splitter == "ratio" || splitter == "net.librec.data.splitter.RatioDataSplitter") || by != "rating")
+        throw LibrecException("only data.model.splitter=ratio with data.splitter.ratio=rating is implemented");
+    const double ratio = conf.getDouble("data.splitter.trainset.ratio", 0.8);
+    auto start = [&](SequentialAccessSparseMatrix& m) {
+        m = SequentialAccessSparseMatrix();
+        m.numRows = preference.numRows; m.numCols = preference.numCols;
+        m.rowptr.assign((size_t)preference.numRows + 1, 0);
+    };
+    start(train); start(test);
+    for (int u = 0; u < preference.numRows; ++u) {
+        for (int64_t e = preference.rowptr[(size_t)u]; e < preference.rowptr[(size_t)u + 1]; ++e) {
+            const double rdm = Randoms::uniform();                                           // RatioDataSplitter.java:143-150
+            const double v = preference.val[(size_t)e];
+            if (v == 0.0) continue;                                                          // reshape() drops exact zeros
+            SequentialAccessSparseMatrix& dst = rdm < ratio ? train : test;
+            dst.col.push_back(preference.col[(size_t)e]); dst.val.push_back(v);
+            dst.rowptr[(size_t)u + 1]++;
+        }
+    }
+    for (int u = 0; u < preference.numRows; ++u) {
+        train.rowptr[(size_t)u + 1] += train.rowptr[(size_t)u];
+        test.rowptr[(size_t)u + 1] += test.rowptr[(size_t)u];
+    }
+}
+
+void TextDataModel::buildDataModel() {
+    buildConvert();
+    buildSplitter();
+    log.push_back("Transform data and split data set successfully!");                        // AbstractDataModel.java:110
+}
+
 RecommenderJob::RecommenderJob(const Configuration& c) : conf(c) {
     if (conf.has("rec.random.seed")) Randoms::seed(conf.getLong("rec.random.seed", 1));      // RecommenderJob.java:74-77
 }
 void RecommenderJob::setData(const SequentialAccessSparseMatrix& tr, const SequentialAccessSparseMatrix& te) { train = tr; test = te; }
 void RecommenderJob::runJob() {
+    if (train.numRows == 0 && conf.has("data.input.path")) {                                 // RecommenderJob.java:121-128
+        dataModel.reset(new TextDataModel(conf));
+        dataModel->buildDataModel();
+        train = dataModel->train; test = dataModel->test;
+    }
     recommender = newRecommender(conf.get("rec.recommender.class"));
     recommender->train(conf, train, test);
     const bool ranking = conf.getBoolean("rec.recommender.isranking");
@@ -428,7 +564,36 @@ void RecommenderJob::runJob() {
         recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
     }
     log = recommender->log();
+    if (dataModel) log.insert(log.begin(), dataModel->log.begin(), dataModel->log.end());
     for (const auto& kv : evaluatedMap) log.push_back("Evaluator value:" + kv.first + " is " + java_double_to_string(kv.second));   // :257-260
+}
+
+std::string RecommenderJob::saveResult() {
+    if (recommendedList.size() == 0) return "";
+    std::string algo = conf.get("rec.recommender.class");                                    // DriverClassUtil.getDriverName: the short name
+    const std::string outputPath = conf.get("dfs.result.dir", "result") + "/" + conf.get("data.input.path", "data") + "-" + algo + "-output/" + algo;
+    std::string out;
+    out.reserve((size_t)recommendedList.size() * 16);
+    for (size_t c = 0; c < recommendedList.lists.size(); ++c) {
+        for (const KeyValue& kv : recommendedList.lists[c]) {
+            // AbstractRecommender.java:213-235: raw ids through the inverse id maps; without a data model the inner ids are the ids
+            const std::string uid = dataModel ? dataModel->userIds[c] : std::to_string(c);
+            const std::string iid = dataModel ? dataModel->itemIds[(size_t)kv.key] : std::to_string(kv.key);
+            if (uid.find_first_not_of(" \t\r\n") == std::string::npos || iid.find_first_not_of(" \t\r\n") == std::string::npos) continue;   // StringUtils.isNotBlank
+            out += uid; out += ','; out += iid; out += ','; out += java_double_to_string(kv.value); out += '\n';
+        }
+    }
+    // util/FileUtil.java:314-326 creates the parent directories
+    for (size_t pos = outputPath.find('/', 1); pos != std::string::npos; pos = outputPath.find('/', pos + 1)) {
+        const std::string d = outputPath.substr(0, pos);
+        if (!d.empty()) mkdir(d.c_str(), 0777);
+    }
+    FILE* fp = fopen(outputPath.c_str(), "wb");
+    if (!fp) throw LibrecException("saveResult: cannot write " + outputPath);
+    fwrite(out.data(), 1, out.size(), fp);
+    fclose(fp);
+    log.push_back("Result path is " + outputPath);
+    return outputPath;
 }
 
 }  // namespace librec

@@ -199,12 +199,34 @@ std::unique_ptr<MatrixFactorizationCudaRecommender> newRecommender(const std::st
 double evaluateRMSE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended);
 double evaluateMAE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended);
 
-// job/RecommenderJob.java:72-79,121-143,205-271 : seed -> instantiate -> train -> evaluate -> log lines
+// data/model/TextDataModel.java + data/convertor/TextDataConvertor.java:136-200 + math/structure/DataFrame.java:237-261,370-379
+// + data/splitter/RatioDataSplitter.java:136-156, straight into flat CSR arrays: no per-line String[],
+// no HashBasedTable<Integer,Integer,Double>, no per-row objects.  Semantics kept: fields split at every one of "\t;, " (empty
+// interior fields survive, like Pattern.split), the first blank line ends a file, inner ids in first-seen order, on a duplicate
+// (user,item) the EARLIEST line wins (the reference scans the frame backwards into a table), binThold >= 0 maps the rating to
+// +1 / -1, rows sorted by item; the ratio splitter draws one Randoms.uniform() per entry in CSR order (< ratio -> train) and
+// entries whose value is exactly 0.0 vanish from both sides (OrderedIntDoubleMapping.java:342-359).
+struct TextDataModel {
+    explicit TextDataModel(const Configuration& conf) : conf(conf) {}
+    void buildDataModel();                           // AbstractDataModel.java:92-117: convert, then split
+    void buildConvert();                             // reads dfs.data.dir + "/" + data.input.path (a file)
+    void buildSplitter();                            // data.model.splitter=ratio, data.splitter.ratio=rating
+    Configuration conf;
+    SequentialAccessSparseMatrix preference, train, test;
+    std::vector<std::string> userIds, itemIds;       // inner id -> raw id (the BiMap inverses of DataFrame)
+    std::vector<std::string> log;
+};
+
+// job/RecommenderJob.java:72-79,121-143,205-271 : seed -> [data model] -> instantiate -> train -> evaluate -> log lines -> save
 struct RecommenderJob {
     explicit RecommenderJob(const Configuration& conf);
     void setData(const SequentialAccessSparseMatrix& train, const SequentialAccessSparseMatrix& test);
-    void runJob();
+    void runJob();                                   // builds the TextDataModel first when no data was set and data.input.path is
+    // job/RecommenderJob.java:281-306 + AbstractRecommender.java:213-235: "user,item,value\n" with raw ids,
+    // values printed like String.valueOf(double); returns the path written ("" when there is nothing to write)
+    std::string saveResult();
     Configuration conf;
+    std::unique_ptr<TextDataModel> dataModel;
     SequentialAccessSparseMatrix train, test;
     std::unique_ptr<MatrixFactorizationCudaRecommender> recommender;
     std::map<std::string, double> evaluatedMap;     // "RMSE", "MAE", ...

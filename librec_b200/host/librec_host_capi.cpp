@@ -100,6 +100,47 @@ LRH_API void lrh_job_list_copy(void* h, int32_t* counts, int32_t* keys, double* 
     }
 }
 // host-logic probes used by the CPU tests (no GPU needed)
+// ---- data model alone (no GPU needed): properties -> TextDataModel.buildDataModel() -> flat CSR arrays
+struct DataModelBox { std::unique_ptr<TextDataModel> dm; std::string tmp; };
+LRH_API void* lrh_datamodel_build(const char* properties_text) {
+    try {
+        Configuration conf;
+        conf.load_properties(properties_text ? properties_text : "");
+        if (conf.has("rec.random.seed")) Randoms::seed(conf.getLong("rec.random.seed", 1));      // RecommenderJob.java:74-77
+        DataModelBox* b = new DataModelBox();
+        b->dm.reset(new TextDataModel(conf));
+        b->dm->buildDataModel();
+        return b;
+    } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+LRH_API void lrh_datamodel_destroy(void* h) { delete (DataModelBox*)h; }
+static const SequentialAccessSparseMatrix& dm_matrix(void* h, int which) {
+    TextDataModel* d = ((DataModelBox*)h)->dm.get();
+    return which == 0 ? d->preference : (which == 1 ? d->train : d->test);
+}
+LRH_API void lrh_datamodel_dims(void* h, int which, int32_t* U, int32_t* I, int64_t* nnz) {
+    const SequentialAccessSparseMatrix& m = dm_matrix(h, which);
+    *U = m.numRows; *I = m.numCols; *nnz = m.size();
+}
+LRH_API void lrh_datamodel_copy(void* h, int which, int64_t* rowptr, int32_t* col, double* val) {
+    const SequentialAccessSparseMatrix& m = dm_matrix(h, which);
+    memcpy(rowptr, m.rowptr.data(), m.rowptr.size() * sizeof(int64_t));
+    memcpy(col, m.col.data(), m.col.size() * sizeof(int32_t));
+    memcpy(val, m.val.data(), m.val.size() * sizeof(double));
+}
+LRH_API const char* lrh_datamodel_raw_id(void* h, int is_item, int32_t inner) {
+    DataModelBox* b = (DataModelBox*)h;
+    const auto& ids = is_item ? b->dm->itemIds : b->dm->userIds;
+    b->tmp = (inner >= 0 && (size_t)inner < ids.size()) ? ids[(size_t)inner] : std::string();
+    return b->tmp.c_str();
+}
+// job/RecommenderJob.java:281-306; returns the path written ("" when the list is empty), NULL on error
+LRH_API const char* lrh_job_save_result(void* h) {
+    Job* j = (Job*)h;
+    try { j->log_text = j->job->saveResult(); return j->log_text.c_str(); }
+    catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
 LRH_API void lrh_randoms_seed(long long s) { Randoms::seed(s); }
 LRH_API int lrh_randoms_uniform_int(int range) { return Randoms::uniform(range); }
 LRH_API double lrh_randoms_uniform() { return Randoms::uniform(); }

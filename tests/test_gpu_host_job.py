@@ -141,3 +141,39 @@ rec.random.seed=1
         assert abs(got - exp[name]) <= 1e-12, (java_name, got, exp[name])
         assert any(l.startswith("Evaluator value:%s top 10 is " % java_name) for l in job.log())
     assert abs(exp["Precision"] - precision * tr.U / np.count_nonzero(np.diff(te.rowptr))) < 1e-12
+
+
+def test_job_from_a_ratings_file_end_to_end(O, capi, c1, tmp_path):
+    """`librec rec -exec` shape of a run: properties name a ratings file; the native TextDataModel loads and splits it
+    (SURVEY.md 8f N2), the CUDA recommender trains and evaluates, saveResult writes `user,item,value` lines with raw ids
+    (N4).  Checked against the oracle run on the SAME file with the SAME java.util.Random stream
+    (seed -> split draws -> factor init, job/RecommenderJob.java:74-77)."""
+    import os
+    from librec_b200.host.binding import RecommenderJob
+    full = c1["full"]
+    rows = full.rows()
+    path = os.path.join(str(tmp_path), "ratings.txt")
+    with open(path, "w") as f:                                             # raw ids: user 1000+u, item 5000+i, tab separated
+        for u, i, r in zip(rows.tolist(), full.col.tolist(), full.val.tolist()):
+            f.write("%d\t%d\t%s\n" % (1000 + u, 5000 + i, repr(float(r))))
+    props = BIASEDMF_PROPS + "\ndfs.data.dir=%s\ndata.input.path=ratings.txt\ndfs.result.dir=%s\ndata.splitter.trainset.ratio=0.8\n" % (
+        str(tmp_path), os.path.join(str(tmp_path), "result"))
+    job = RecommenderJob(props)
+    job.run_job()
+    # oracle on the same file, same RNG stream
+    O.lib().lro_seed(1)
+    ofull = O.load_text(path)
+    otr, ote = O.split_ratio(ofull, 0.8)
+    mu, mn, mx = O.matrix_setup(otr)
+    P, Q, bu, bi = O.mf_setup(otr.U, otr.I, 20, True)
+    O.train(O.BIASEDMF, otr, 20, P, Q, bu, bi, mu, 0.002, 0.01, 0.01, 0.01, 0.01, 100)
+    ormse, omae = O.eval_rating(O.BIASEDMF, ote, 20, P, Q, bu, bi, mu, mn, mx)
+    assert abs(job.metric("RMSE") - ormse) < 1e-3 and abs(job.metric("MAE") - omae) < 1e-3
+    assert any(l.startswith("Dataset: [") for l in job.log()) and any("user number: 943" in l for l in job.log())
+    # result sink: one line per test entry, raw ids, Java's Double.toString for the value
+    out = job.save_result()
+    assert out.endswith("ratings.txt-biasedmf-output/biasedmf") and os.path.exists(out)
+    lines = open(out).read().splitlines()
+    assert len(lines) == ote.nnz
+    u0, i0, v0 = lines[0].split(",")
+    assert 1000 <= int(u0) < 1000 + full.U and 5000 <= int(i0) < 5000 + full.I and 1.0 <= float(v0) <= 5.0

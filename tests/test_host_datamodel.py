@@ -1,0 +1,89 @@
+"""CPU: the native TextDataModel (loader + ratio splitter straight into flat CSR) against the oracle's
+restatement of TextDataConvertor / DataFrame / RatioDataSplitter on the same files and the same java.util.Random stream."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _write(path, lines):
+    with open(path, "w") as f:
+        f.write("".join(lines))
+
+
+def _check(O, tmp_path, lines, seed=1, thold=-1.0, ratio=0.8):
+    from librec_b200.host.binding import TextDataModel
+    path = os.path.join(str(tmp_path), "ratings.txt")
+    _write(path, lines)
+    props = {"dfs.data.dir": str(tmp_path), "data.input.path": "ratings.txt", "rec.random.seed": seed,
+             "data.convert.binarize.threshold": thold, "data.splitter.trainset.ratio": ratio}
+    dm = TextDataModel(props)
+    full = O.load_text(path, thold)
+    U, I, rowptr, col, val = dm.matrix("preference")
+    assert (U, I) == (full.U, full.I)
+    assert np.array_equal(rowptr, full.rowptr) and np.array_equal(col, full.col) and np.array_equal(val, full.val)
+    O.lib().lro_seed(seed)
+    exp_train, exp_test = O.split_ratio(full, ratio)
+    for which, exp in (("train", exp_train), ("test", exp_test)):
+        gU, gI, grp, gc, gv = dm.matrix(which)
+        assert (gU, gI) == (exp.U, exp.I)
+        assert np.array_equal(grp, exp.rowptr) and np.array_equal(gc, exp.col) and np.array_equal(gv, exp.val)
+    return dm, full
+
+
+def test_loader_matches_reference_fixture(O, tmp_path):
+    # the reference's own loader fixture (TextDataModelTestCase.java:66 expects 13 entries from matrix4by4.txt)
+    lines = open(os.path.join(ROOT, "tests", "golden", "matrix4by4.txt")).readlines()
+    dm, full = _check(O, tmp_path, lines)
+    assert full.nnz == 13
+
+
+def test_loader_quirks(O, tmp_path):
+    lines = [
+        "u9 i7 4.0\n",            # raw string ids, first-seen order
+        "u1,i7,3.5\n",            # every one of tab ; , space separates
+        "u9;i2;5\n",
+        "u1\ti2\t0\n",            # exact zero: present in the preference matrix, dropped by the splitter's reshape
+        "u9 i7 1.0\n",            # duplicate (u9, i7): the EARLIEST line (4.0) wins
+        "u3 i5 2.5 881250949\n",  # extra column ignored in UIR
+        "u1 i9 1e0\r\n",          # CRLF, Double.parseDouble syntax
+        "   \n",                  # first blank line ends the file
+        "u7 i1 5.0\n",
+    ]
+    dm, full = _check(O, tmp_path, lines, seed=7)
+    assert (full.U, full.I, full.nnz) == (3, 4, 6)
+    assert [dm.raw_id(0, u) for u in range(3)] == ["u9", "u1", "u3"]
+    assert [dm.raw_id(1, i) for i in range(4)] == ["i7", "i2", "i5", "i9"]
+    U, I, rowptr, col, val = dm.matrix("preference")
+    assert val[rowptr[0]:rowptr[1]].tolist() == [4.0, 5.0]          # u9: i7 (earliest line), i2
+    # binarisation: rating > 3 -> +1 else -1 (DataFrame.java:251-253)
+    _check(O, tmp_path, lines, seed=7, thold=3.0)
+
+
+@pytest.mark.parametrize("seed", [1, 42])
+def test_loader_and_splitter_on_a_bigger_file(O, tmp_path, seed):
+    rng = np.random.default_rng(seed)
+    n = 60000
+    u = rng.integers(1, 900, n); i = rng.integers(1, 1500, n); r = rng.integers(0, 11, n) / 2.0
+    seps = np.array(["\t", " ", ",", ";"])[rng.integers(0, 4, n)]
+    lines = ["%d%s%d%s%s\n" % (a, s, b, s, repr(float(c))) for a, b, c, s in zip(u, i, r, seps)]
+    dm, full = _check(O, tmp_path, lines, seed=seed)
+    assert full.nnz < n                                              # duplicates were folded
+    tr = dm.matrix("train"); te = dm.matrix("test")
+    kept = tr[4].shape[0] + te[4].shape[0]
+    assert kept == np.count_nonzero(full.val != 0.0) and abs(tr[4].shape[0] / kept - 0.8) < 0.01     # RatioDataSplitterTestCase.java:74
+
+
+def test_loader_errors(O, tmp_path):
+    from librec_b200.host.binding import TextDataModel, LibrecException
+    with pytest.raises(LibrecException):
+        TextDataModel({"dfs.data.dir": str(tmp_path), "data.input.path": "missing.txt"})
+    _write(os.path.join(str(tmp_path), "bad.txt"), ["1 2 x\n"])
+    with pytest.raises(LibrecException) as e:
+        TextDataModel({"dfs.data.dir": str(tmp_path), "data.input.path": "bad.txt"})
+    assert "NumberFormatException" in str(e.value)
+    _write(os.path.join(str(tmp_path), "short.txt"), ["1 2\n"])
+    with pytest.raises(LibrecException):
+        TextDataModel({"dfs.data.dir": str(tmp_path), "data.input.path": "short.txt"})
