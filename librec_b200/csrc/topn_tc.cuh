@@ -7,14 +7,14 @@
 //      scaling (per user row / per item matrix), K padded to 64; BiasedMF folds the item bias into two extra
 //      K columns (hi/lo fp16 split against the row's scale in A).
 //   2. topn_tc_kernel (persistent, warp-specialised, 1 CTA/SM, 320 threads):
-//        warp 0  TMA producer   item tiles, cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier ring (7 stages at k=128)
+//        warp 0  TMA producer   item tiles, cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier ring (3 stages at k=128)
 //        warp 1  MMA issuer     tcgen05.mma.cta_group::1.kind::f16 with the A operand in TENSOR MEMORY (.ts form),
 //                               M=128 N=128 K=16; two user sub-tiles (256 users) share every item tile; the loop is
 //                               warp-uniform with elect.sync around the issue (8 back-to-back UTCHMMA per sub-tile);
 //                               accumulators in a ring of three 128-column TMEM slots
 //        warps 2-9 epilogue     stage their user rows into TMEM (tcgen05.st), then per tile tcgen05.ld 32x32b.x32:
 //                               one thread owns one user row; a score is appended to the row's candidate list
-//                               (global memory, L2-resident) only if it beats the row's running threshold tau --
+//                               (shared memory, 64 slots) only if it beats the row's running threshold tau --
 //                               common case 15 FMNMX3/FMNMX + 1 compare + 1 warp vote per 32 scores; full lists are
 //                               compacted warp-cooperatively to the best K' (train items masked there, tau rises).
 //      Invariant: every item that is NOT in a row's candidate list has sweep score <= tau_row
@@ -239,14 +239,27 @@ __device__ __forceinline__ T* tc_shfl_ptr(T* ptr, int src) {
 //   3. rank by (score desc, slot asc), keep the best K', tau := score of rank K'-1.
 // Everything dropped here has approximate score <= the new tau (or is a train item), which is the invariant the
 // exactness certificate of topn_tc_rescore_kernel rests on.
-__device__ __noinline__ int4 tc_compact(uint2* lp, int cnt, int kept, float tau, const int32_t* col_row, int tlen, int tp, int32_t nt,
+// Candidate lists live in shared memory: TC_ROWS rows x TC_CAP slots of {score bits, item}; entry e of row r sits in
+// slot (e & 32) | ((e ^ r) & 31) of the row's 512-byte line, which keeps both access patterns conflict-free: the lanes
+// of a warp (32 consecutive rows) appending at equal counts, and the 32 lanes of a compaction reading one row.
+__device__ __forceinline__ uint32_t tc_slot(uint32_t row_base, int sw, int e) { return row_base + (uint32_t)(((e & 32) | ((e ^ sw) & 31)) << 3); }
+__device__ __forceinline__ void tc_sts2(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 tc_lds2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __noinline__ int4 tc_compact(uint32_t lp, int sw, int cnt, int kept, float tau, const int32_t* col_row, int tlen, int tp, int32_t nt,
                                         int trig, int keep, int32_t n_items) {
     const int lane = threadIdx.x & 31;
     unsigned flagged = __ballot_sync(0xffffffffu, cnt > trig);
     while (flagged) {
         const int r = __ffs(flagged) - 1;
         flagged &= flagged - 1;
-        uint2* L = tc_shfl_ptr(lp, r);
+        const uint32_t L = __shfl_sync(0xffffffffu, lp, r);
+        const int rsw = __shfl_sync(0xffffffffu, sw, r);
         const int32_t* cr = tc_shfl_ptr(col_row, r);
         const int n = __shfl_sync(0xffffffffu, cnt, r), kp = __shfl_sync(0xffffffffu, kept, r);
         const int tl = __shfl_sync(0xffffffffu, tlen, r);
@@ -256,8 +269,8 @@ __device__ __noinline__ int4 tc_compact(uint2* lp, int cnt, int kept, float tau,
         __syncwarp();
         bool al0 = lane < n, al1 = lane + 32 < n;
         uint2 e0 = make_uint2(0u, 0u), e1 = make_uint2(0u, 0u);
-        if (al0) e0 = __ldcg(L + lane);
-        if (al1) e1 = __ldcg(L + 32 + lane);
+        if (al0) e0 = tc_lds2(tc_slot(L, rsw, lane));
+        if (al1) e1 = tc_lds2(tc_slot(L, rsw, lane + 32));
         // columns past the catalogue end (zero-filled by TMA) are appended unchecked by the sweep; drop them here
         if ((int32_t)e0.y >= n_items) al0 = false;
         if ((int32_t)e1.y >= n_items) al1 = false;
@@ -297,8 +310,8 @@ __device__ __noinline__ int4 tc_compact(uint2* lp, int cnt, int kept, float tau,
         const int alive = __popc(__ballot_sync(0xffffffffu, al0)) + __popc(__ballot_sync(0xffffffffu, al1));
         const int keep_n = min(alive, keep);
         __syncwarp();
-        if (al0 && rk0 < keep_n) __stcg(L + rk0, e0);
-        if (al1 && rk1 < keep_n) __stcg(L + rk1, e1);
+        if (al0 && rk0 < keep_n) tc_sts2(tc_slot(L, rsw, rk0), e0.x, e0.y);
+        if (al1 && rk1 < keep_n) tc_sts2(tc_slot(L, rsw, rk1), e1.x, e1.y);
         if (alive >= keep) {
             const unsigned b0 = __ballot_sync(0xffffffffu, al0 && rk0 == keep - 1);
             const unsigned b1 = __ballot_sync(0xffffffffu, al1 && rk1 == keep - 1);
@@ -312,7 +325,7 @@ __device__ __noinline__ int4 tc_compact(uint2* lp, int cnt, int kept, float tau,
 }
 #define TC_COMPACT(TRIG)                                                                  \
     do {                                                                                  \
-        const int4 r_ = tc_compact(lp, cnt, kept, tau, col_row, tlen, tp, nt, (TRIG), p.keep, p.I); \
+        const int4 r_ = tc_compact(lp, sw, cnt, kept, tau, col_row, tlen, tp, nt, (TRIG), p.keep, p.I); \
         cnt = r_.x; kept = r_.y; tau = __int_as_float(r_.z);                              \
         if (r_.w != tp) { tp = r_.w; nt = tp < tlen ? __ldg(col_row + tp) : 0x7fffffff; }  \
     } while (0)
@@ -384,7 +397,8 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __half* __restrict
     unsigned char* base = (unsigned char*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t tile_bytes = TC_TILE_N * TC_KB * 2;               // 16 KB: 128 rows x 128 B
     unsigned char* smB = base;                                       // [stages][num_kb] tiles
-    uint64_t* bars = (uint64_t*)(smB + (size_t)p.stages * p.num_kb * tile_bytes);
+    unsigned char* lists = smB + (size_t)p.stages * p.num_kb * tile_bytes;            // [TC_ROWS][TC_CAP] {score bits, item}
+    uint64_t* bars = (uint64_t*)(lists + (size_t)TC_ROWS * TC_CAP * 8);
     const int S = p.stages;
     uint32_t* tmem_slot = (uint32_t*)(bars + TC_NBARS(S));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -495,7 +509,8 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __half* __restrict
             const bool valid = c < p.nq;
             const int t0 = ch * p.tiles_per_chunk;
             const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-            uint2* lp = p.cand + ((size_t)c * p.n_chunks + ch) * TC_CAP;          // this row's candidate list (global, L2-resident)
+            const uint32_t lp = smem_u32(lists) + (uint32_t)row_in_cta * (TC_CAP * 8);     // this row's candidate list (shared memory)
+            const int sw = row_in_cta & 31;
             const int32_t* col_row = p.col;
             int tlen = 0, tp = 0;
             int32_t nt = 0x7fffffff;               // next train item at / after the cursor (lets a compaction skip the mask)
@@ -519,7 +534,7 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __half* __restrict
 #define TC_APPEND(R, J)                                                                                            \
             do {                                                                                                   \
                 if (__uint_as_float(R[J]) > tau) {                                                                 \
-                    __stcg(lp + cnt, make_uint2(R[J], (uint32_t)(item0 + (J))));                                   \
+                    tc_sts2(tc_slot(lp, sw, cnt), R[J], (uint32_t)(item0 + (J)));                                  \
                     ++cnt;                                                                                         \
                 }                                                                                                  \
             } while (0)
@@ -588,6 +603,8 @@ topn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __half* __restrict
             // final pass: masks over the entries appended since the last compaction, trim to K'
             TC_COMPACT(kept);
             if (valid) {
+                uint2* out = p.cand + ((size_t)c * p.n_chunks + ch) * TC_CAP;
+                for (int e = 0; e < cnt; ++e) out[e] = tc_lds2(tc_slot(lp, sw, e));
                 p.cand_cnt[(size_t)c * p.n_chunks + ch] = cnt;
                 p.cand_tau[(size_t)c * p.n_chunks + ch] = tau;
             }
@@ -765,10 +782,11 @@ static int tc_pass(lrk_handle_s* h, TcState* s, const int32_t* d_users, int32_t 
     const int64_t nq_pad = (int64_t)m_tiles * TC_ROWS;
     const size_t tile_bytes = (size_t)TC_TILE_N * TC_KB * 2;
     const size_t b_stage = (size_t)num_kb * tile_bytes;
-    int stages = (int)((227 * 1024 - 1024 - 256) / b_stage);
+    const size_t list_bytes = (size_t)TC_ROWS * TC_CAP * 8;
+    int stages = (int)((227 * 1024 - 1024 - 256 - list_bytes) / b_stage);
     stages = std::max(2, std::min(stages, 8));
     { const char* es = getenv("LRK_TC_STAGES"); if (es && atoi(es) >= 2) stages = std::min(stages, atoi(es)); }   // profiling probe
-    const size_t smem = 1024 + (size_t)stages * b_stage + TC_NBARS(stages) * 8 + 16;
+    const size_t smem = 1024 + (size_t)stages * b_stage + list_bytes + TC_NBARS(stages) * 8 + 16;
     // ---- scratch
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_aq = up(sizeof(__half) * (size_t)nq_pad * Kp), b_pn = up(sizeof(double2) * (size_t)nq_pad);
