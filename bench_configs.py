@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Secondary measurements on one B200 for the BASELINE.json configs that bench.py does not headline:
   C3: BPR k=128 SGD epoch (samples/s) on the synthetic ML-20M shape (implicit feedback, device-side sampling)
-  C4: PMF k=128 SGD epoch (updates/s) on the synthetic Netflix shape (480 189 x 17 770, 100 480 507 ratings), one GPU's view
+  C4: PMF k=128 SGD epoch (updates/s) on the synthetic Netflix shape (480 189 x 17 770, 100 480 507 ratings); under torchrun
+      (N ranks) the users are split into N contiguous blocks and the epoch runs as DSGD (strong scaling of the one data set)
 One JSON line per config: device-resident epochs timed with CUDA events (lrk_last_epoch_ms), L2 flushed between
 epochs, algorithmic-byte roofline per SURVEY.md 8(d)."""
 import argparse
@@ -13,6 +14,58 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def run_dsgd(name, model_name, shape, k, lr, reg, steps, warmup):
+    """strong scaling: the one data set, users split into WORLD_SIZE contiguous blocks"""
+    import torch
+    import torch.distributed as dist
+    from librec_b200 import capi, synth
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    d = synth.make_ratings(shape)
+    U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
+    lo, hi = rank * U // world, (rank + 1) * U // world
+    a, b = int(d["rowptr"][lo]), int(d["rowptr"][hi])
+    rowptr = np.ascontiguousarray(d["rowptr"][lo:hi + 1] - a)
+    col, val = np.ascontiguousarray(d["col"][a:b]), np.ascontiguousarray(d["val"][a:b])
+    P, Q, _, _ = synth.init_factors(U, I, k, 11, False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    h = capi.Handle(capi.MODEL_PMF, k, device=local, seed=1)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    h.comm_init(rank, world, uid[0])
+    h.set_train_csr(hi - lo, I, rowptr, col, val)
+    h.set_factors(P[lo:hi], Q)
+    ms, losses = [], []
+    for s in range(warmup + steps):
+        flush.zero_(); torch.cuda.synchronize(); dist.barrier()
+        losses.append(h.sgd_epoch(lr, reg, reg, 0.0, s + 1))
+        if s >= warmup:
+            ms.append(h.last_epoch_ms())
+    guard = h.sgd_safeguard()
+    h.close()
+    t = torch.tensor([float(np.mean(ms))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kms = float(t.item())
+    if rank == 0:
+        bytes_per = 12 + 4 * k * 4
+        achieved = bytes_per * nnz / world / (kms * 1e-3) / 1e9
+        print(json.dumps({"config": name, "metric": "MF SGD rating-updates/s", "value": nnz / (kms * 1e-3), "unit": "updates/s", "n_gpus": world,
+                          "scaling": "strong", "steps": steps, "warmup": warmup, "ms_per_step": kms,
+                          "workload": "%s k=%d, synthetic %s shape (%d x %d, %d ratings), DSGD over %d user blocks, lr %g reg %g" % (
+                              model_name, k, shape, U, I, nnz, world, lr, reg),
+                          "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s (per GPU)",
+                                       "frac": achieved / peaks["hbm_gbs"], "algorithmic_bytes_per_unit": bytes_per},
+                          "losses": losses, "safeguard": guard}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def run(name, model_name, shape, k, lr, reg, steps, warmup):
@@ -52,6 +105,9 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--only", default="")
     a = ap.parse_args()
+    if dist_env()[1] > 1:
+        run_dsgd("C4", "pmf", "netflix", 128, 0.01, 0.08, a.steps, a.warmup)    # pmf-test.properties, DSGD
+        sys.exit(0)
     if a.only in ("", "c3"):
         run("C3", "bpr", "ml-20m", 128, 0.01, 0.01, a.steps, a.warmup)          # bpr-test.properties
     if a.only in ("", "c4"):

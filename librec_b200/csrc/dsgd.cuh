@@ -312,6 +312,7 @@ static int dsgd_set_factors(lrk_handle_s* h, const double* P, const double* Q, c
         LRK_LAUNCH_CHECK(h);
     }
     s->cur = 0; s->cur_block = b;
+    if (h->cfg.model != LRK_MODEL_BPR) { int rc_n = refresh_user_norm2(h, false); if (rc_n) return rc_n; }
     LRK_CUDA(h, cudaStreamSynchronize(st));
     h->prev_loss = -1.0; h->conc_div = 1; h->good_epochs = 0;
     h->mu = mu; h->has_factors = true; h->f64_valid = false;
@@ -336,6 +337,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     LRK_CUDA(h, cudaMemcpyAsync(h->bk_P, h->P32, sizeof(float) * np_, cudaMemcpyDeviceToDevice, st));
     LRK_CUDA(h, cudaMemcpyAsync(h->bk_Q, s->qbuf[s->cur], sizeof(float) * s->buf_floats, cudaMemcpyDeviceToDevice, st));
     if (biased_) LRK_CUDA(h, cudaMemcpyAsync(h->bk_bu, h->bu32, sizeof(float) * (size_t)h->U, cudaMemcpyDeviceToDevice, st));
+    if (h->h_pnorm2) h->pnorm2_host = *h->h_pnorm2;
     for (int attempt = 0;; ++attempt) {
     LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
     LRK_CUDA(h, cudaEventRecord(h->ev0, st));
@@ -366,6 +368,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
             sp.hot_share = (h->cfg.model != LRK_MODEL_BPR && (size_t)b < s->seg_hot_share.size()) ? s->seg_hot_share[(size_t)b] : 0.0;
             sp.conc_div = h->conc_div;
             sp.item_deg = (h->cfg.model != LRK_MODEL_BPR && h->d_item_deg) ? h->d_item_deg + s->bounds[(size_t)b] : nullptr;   // block-local item ids
+            sp.pnorm2 = sp.item_deg ? h->d_pnorm2 : nullptr;
             int rc = sgd_launch(h, sp);
             if (rc) return rc;
         }
@@ -383,6 +386,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     }
     LRK_NCCL(h, n->AllReduce(h->d_loss, h->d_loss, 1, ncclFloat64, ncclSum, (ncclComm_t)h->comm, st));
     LRK_CUDA(h, cudaEventRecord(h->ev1, st));
+    if (h->cfg.model != LRK_MODEL_BPR && h->d_item_deg) { int rc_n = refresh_user_norm2(h, false); if (rc_n) return rc_n; }
     h->f64_valid = false;
     LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
     LRK_CUDA(h, cudaStreamSynchronize(st));
@@ -395,6 +399,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
         LRK_CUDA(h, cudaMemcpyAsync(s->qbuf[s->cur], h->bk_Q, sizeof(float) * s->buf_floats, cudaMemcpyDeviceToDevice, st));
         if (biased_) LRK_CUDA(h, cudaMemcpyAsync(h->bu32, h->bk_bu, sizeof(float) * (size_t)h->U, cudaMemcpyDeviceToDevice, st));
         h->conc_div *= 4; h->good_epochs = 0; h->rollbacks++;
+        if (h->cfg.model != LRK_MODEL_BPR && h->d_item_deg) { int rc_n = refresh_user_norm2(h, false); if (rc_n) return rc_n; }
     }
     }
     if (s->trace) {

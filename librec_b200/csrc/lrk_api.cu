@@ -100,11 +100,12 @@ int lrk_destroy(lrk_handle_t h) {
     lrk_dev_free(&h->P32); lrk_dev_free(&h->Q32); lrk_dev_free(&h->bu32); lrk_dev_free(&h->bi32);
     lrk_dev_free(&h->P64); lrk_dev_free(&h->Q64); lrk_dev_free(&h->bu64); lrk_dev_free(&h->bi64);
     lrk_dev_free(&h->d_loss);
-    lrk_dev_free(&h->d_item_deg);
+    lrk_dev_free(&h->d_item_deg); lrk_dev_free(&h->d_pnorm2);
     lrk_dev_free(&h->bk_P); lrk_dev_free(&h->bk_Q); lrk_dev_free(&h->bk_bu); lrk_dev_free(&h->bk_bi);
     lrk_dev_free(&h->tn_users); lrk_dev_free(&h->tn_items); lrk_dev_free(&h->tn_scores); lrk_dev_free(&h->tn_counts);
     if (h->scratch) cudaFree(h->scratch);
     if (h->h_loss) cudaFreeHost(h->h_loss);
+    if (h->h_pnorm2) cudaFreeHost(h->h_pnorm2);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -192,6 +193,7 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I * ld, 256), 256, 0, st>>>(h->Q64, h->Q32, I, k, ld); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu64, h->bu32, U, 1, 1); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi64, h->bi32, I, 1, 1); LRK_LAUNCH_CHECK(h);
+    if (h->cfg.model != LRK_MODEL_BPR && (rc = refresh_user_norm2(h, false))) return rc;
     LRK_CUDA(h, cudaStreamSynchronize(st));   // host buffers may be reused by the caller on return
     h->mu = mu;
     h->has_factors = true;
@@ -241,6 +243,7 @@ static void fill_sgd_params(lrk_handle_s* h, SgdParams& sp, float lr, float reg_
     sp.loss = h->d_loss; sp.ld = h->ld;
     sp.hot_share = h->cfg.model == LRK_MODEL_BPR ? 0.0 : h->hot_share;
     sp.item_deg = h->cfg.model == LRK_MODEL_BPR ? nullptr : h->d_item_deg;
+    if (h->h_pnorm2) h->pnorm2_host = *h->h_pnorm2;
     sp.rowptr = h->d_rowptr; sp.col = h->d_col; sp.U = h->U; sp.I = h->I;
     sp.seed_lo = (uint32_t)h->cfg.seed; sp.seed_hi = (uint32_t)(h->cfg.seed >> 32); sp.epoch = (uint32_t)epoch_idx;
 }
@@ -286,6 +289,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
         LRK_CUDA(h, cudaMemcpyAsync(h->bk_bu, h->bu32, sizeof(float) * (size_t)h->U, cudaMemcpyDeviceToDevice, st));
         LRK_CUDA(h, cudaMemcpyAsync(h->bk_bi, h->bi32, sizeof(float) * (size_t)h->I, cudaMemcpyDeviceToDevice, st));
     }
+    if (sp.item_deg) sp.pnorm2 = h->d_pnorm2;          // refreshed by refresh_user_norm2 at set_factors and after every epoch
     double loss = 0.0;
     for (int attempt = 0;; ++attempt) {
         sp.conc_div = h->conc_div;
@@ -293,6 +297,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
         LRK_CUDA(h, cudaEventRecord(h->ev0, st));
         if (h->nnz > 0 && (rc = sgd_launch(h, sp))) return rc;
         LRK_CUDA(h, cudaEventRecord(h->ev1, st));
+        if (sp.item_deg && (rc = refresh_user_norm2(h, false))) return rc;
         LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
         LRK_CUDA(h, cudaStreamSynchronize(st));
         loss = h->h_loss[0];
@@ -307,6 +312,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
             LRK_CUDA(h, cudaMemcpyAsync(h->bi32, h->bk_bi, sizeof(float) * (size_t)h->I, cudaMemcpyDeviceToDevice, st));
         }
         h->conc_div *= 4; h->good_epochs = 0; h->rollbacks++;
+        if (sp.item_deg && (rc = refresh_user_norm2(h, false))) return rc;
     }
     h->f64_valid = false;
     topn_tc_invalidate(h);

@@ -31,6 +31,8 @@ struct lrk_handle_s {
     float* d_sr = nullptr;
     bool has_train = false;
     double hot_share = 0.0;   // largest share one item has of the train ratings (stability cap of the SGD grid)
+    float* d_pnorm2 = nullptr;        // mean |p_u|^2 at the start of the epoch (curvature term of that step)
+    float pnorm2_host = 0.f;          // its host copy, refreshed with every loss read-back (picks the kernel variant)
     uint32_t* d_item_deg = nullptr;   // ratings per item in this handle's shard (staleness-aware step of run tiles, sgd.cuh)
 
     // factors: fp32 working copies (padded rows) + fp64 masters (dense rows, what Java sees)
@@ -49,6 +51,7 @@ struct lrk_handle_s {
     int64_t rollbacks = 0;
     double* d_loss = nullptr;   // device accumulator
     double* h_loss = nullptr;   // pinned
+    float* h_pnorm2 = nullptr;  // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_epoch_ms = 0.f;
     uint64_t launches = 0;

@@ -29,7 +29,11 @@
 // contracts the error by (1 - lr)^B ~ exp(-lr*B) and never overshoots.  With x = lr * B_i,
 // B_i = deg_i * (ratings in flight) / n, the item-side delta of a run tile is therefore scaled by
 // (1 - exp(-x)) / x: identical to plain SGD for x -> 0, the sequential limit for popular items, stable at any
-// concurrency.  (Without it the grid had to be capped at lr * s * in-flight <= 1, s = share of the hottest item,
+// concurrency.  The item row has curvature |p_u|^2 along p_u (PMF on un-centred ratings aligns all user vectors,
+// |p|^2 grows to ~8 at k=128), so x is multiplied by max(1, mean |p_u|^2): the value at the start of the epoch
+// (user_norm2_kernel, read from device memory) for a warp's first run tile, then the mean over the 32 users of
+// the warp's previous run tile (the factors grow fast in the first epochs; 5 shuffles per tile).  Config C4 (PMF k=128, lr 0.01, Netflix
+// shape) ran at 1.2 G updates/s behind the rollback safeguard (grid / 8) before this, at 7.2 G without a rollback after.  (Without it the grid had to be capped at lr * s * in-flight <= 1, s = share of the hottest item,
 // which left 142 of 592 CTAs at 8 DSGD strata; sgd_grid_for keeps that cap for launches without degrees.)
 #pragma once
 #include "lrk_common.cuh"
@@ -55,6 +59,7 @@ struct SgdParams {
     // inflight_frac = (ratings in flight) / n, filled in by the launcher
     const uint32_t* item_deg;
     float inflight_frac;
+    const float* pnorm2;    // device scalar: mean |p_u|^2 of the rank's user factors at the start of the epoch (NULL = 1)
     // BPR only
     const int64_t* __restrict__ rowptr;
     const int32_t* __restrict__ col;
@@ -116,8 +121,10 @@ __device__ __forceinline__ void block_loss_commit(double v, double* out) {
 // ---------------------------------------------------------------------------------------------
 // BiasedMF / PMF.  G lanes per rating, V float4 per lane (row length ld = 4*G*V floats).
 // ---------------------------------------------------------------------------------------------
-template <int G, int V, bool BIASED, bool ATOMIC>
-__global__ void __launch_bounds__(256) sgd_rating_epoch_kernel(SgdParams p) {
+// TRACK: refresh the curvature estimate max(1, mean |p_u|^2) from every run tile (a few registers and 5 shuffles per
+// tile; chosen by the launcher when the user factors are no longer small, see sgd_launch_gv)
+template <int G, int V, bool BIASED, bool ATOMIC, bool TRACK = false>
+__global__ void __launch_bounds__(256, (G * V <= 16 && !TRACK) ? 4 : 1) sgd_rating_epoch_kernel(SgdParams p) {
     constexpr int RPS = 32 / G;  // ratings per warp step
     constexpr int STEPS = G;     // steps per 32-rating tile
     const int lane = threadIdx.x & 31;
@@ -127,6 +134,9 @@ __global__ void __launch_bounds__(256) sgd_rating_epoch_kernel(SgdParams p) {
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t ntiles = (p.n + 31) >> 5;
     const float lr = p.lr, reg_u = p.reg_u, reg_i = p.reg_i, reg_b = p.reg_b, mu = p.mu;
+    // running max(1, mean |p_u|^2): the epoch-start value, then the warp's last run tile.  The launcher picks the
+    // TRACK variant only when that mean exceeds 0.25; below, the factor is 1 and costs no register
+    float pn2 = (TRACK && p.pnorm2) ? fmaxf(1.f, __ldg(p.pnorm2)) : 1.f;
     double loss_d = 0.0;
 
     int64_t tile = gwarp;
@@ -155,9 +165,11 @@ __global__ void __launch_bounds__(256) sgd_rating_epoch_kernel(SgdParams p) {
             constexpr int HOT_CHUNK = (STEPS >= 4) ? STEPS / 4 : 1;
             float4 pn[V];
             float bun = 0.f;
-            float damp = 1.f;
+            // x = lr * (ratings of this item in flight) * max(1, mean |p_u|^2): curvature 1 for the bias, |p_u|^2 along
+            // p_u for the row; the item-side step of the tile is scaled by (1 - exp(-x)) / x
+            float damp = 1.f, psq = 0.f;
             if (p.item_deg) {
-                const float x = lr * (float)__ldg(p.item_deg + i0) * p.inflight_frac;
+                const float x = lr * (float)__ldg(p.item_deg + i0) * p.inflight_frac * pn2;
                 if (x > 1e-3f) damp = (1.f - __expf(-x)) / x;
             }
             int32_t un = __shfl_sync(0xffffffffu, u_l, grp);
@@ -207,7 +219,9 @@ __global__ void __launch_bounds__(256) sgd_rating_epoch_kernel(SgdParams p) {
                         dp.z = lr * (err * b.z - reg_u * a.z); dq[v].z += lr * (err * a.z - reg_i * b.z);
                         dp.w = lr * (err * b.w - reg_u * a.w); dq[v].w += lr * (err * a.w - reg_i * b.w);
                         apply4<ATOMIC>(p.P + (int64_t)uc * p.ld + (v * G + sub) * 4, a, dp);
-                        reg_acc += reg_u * dot4(a, a) + reg_i * dot4(b, b);
+                        const float aa = dot4(a, a);
+                        if (TRACK) psq += aa;
+                        reg_acc += reg_u * aa + reg_i * dot4(b, b);
                     }
                     if (sub == 0) {
                         reg_acc += err * err;
@@ -237,6 +251,11 @@ __global__ void __launch_bounds__(256) sgd_rating_epoch_kernel(SgdParams p) {
                     }
                     if (BIASED && sub == 0) apply1<ATOMIC>(p.bi + i0, bi0, dbi * damp);
                 }
+            }
+            if (TRACK && p.item_deg) {       // |p_u|^2 of the 32 users just seen -> curvature estimate for this warp's next run tile
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) psq += __shfl_xor_sync(0xffffffffu, psq, m);
+                pn2 = fmaxf(1.f, psq * (1.f / 32.f));
             }
             loss_d += (double)loss_f;
             continue;
@@ -422,7 +441,9 @@ __global__ void bpr_peek_kernel(SgdParams p, int64_t first, int64_t n, int32_t* 
     out[3 * t] = u; out[3 * t + 1] = pi; out[3 * t + 2] = nj;
 }
 
-template <int G, int V, bool ATOMIC>
+// BLOCKED: DSGD stratum (positives and negatives inside the held item block); a separate instantiation so that the
+// single-GPU kernel does not carry the second sampler (it cost 32 % of its throughput as a run-time branch)
+template <int G, int V, bool ATOMIC, bool BLOCKED = false>
 __global__ void __launch_bounds__(256) sgd_bpr_epoch_kernel(SgdParams p) {
     constexpr int RPS = 32 / G;
     constexpr int STEPS = G;
@@ -440,7 +461,7 @@ __global__ void __launch_bounds__(256) sgd_bpr_epoch_kernel(SgdParams p) {
         {
             const int64_t s = (tile << 5) + lane;
             if (s < p.n) {
-                if (p.blk_hi > 0) { bpr_draw_block(p, s, u_l, i_l, j_l); i_l -= p.blk_lo; j_l -= p.blk_lo; }
+                if (BLOCKED) { bpr_draw_block(p, s, u_l, i_l, j_l); i_l -= p.blk_lo; j_l -= p.blk_lo; }
                 else bpr_draw(p, s, u_l, i_l, j_l);
             }
         }
@@ -543,6 +564,31 @@ static int sgd_grid_for(lrk_handle_s* h, K kernel, int64_t n, int rps, int* grid
     return LRK_OK;
 }
 
+// mean |p_u|^2 over the rank's users -> out[0] (float); out must be zeroed before
+__global__ void user_norm2_kernel(const float* __restrict__ P, int64_t U, int ld, float* __restrict__ out) {
+    float acc = 0.f;
+    const int64_t n = U * ld;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) { const float v = __ldg(P + t); acc += v * v; }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc / (float)U);
+}
+
+// mean |p_u|^2 of the working user factors -> d_pnorm2 (device, read by the SGD kernel) and pnorm2_host (after the next
+// stream synchronisation; pinned)
+static int refresh_user_norm2(lrk_handle_s* h, bool sync) {
+    cudaStream_t st = h->stream;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_pnorm2, 1))) return rc;
+    if (!h->h_pnorm2) LRK_CUDA(h, cudaMallocHost((void**)&h->h_pnorm2, sizeof(float)));
+    LRK_CUDA(h, cudaMemsetAsync(h->d_pnorm2, 0, sizeof(float), st));
+    user_norm2_kernel<<<2 * h->sm_count, 256, 0, st>>>(h->P32, h->U, h->ld, h->d_pnorm2);
+    LRK_LAUNCH_CHECK(h);
+    LRK_CUDA(h, cudaMemcpyAsync(h->h_pnorm2, h->d_pnorm2, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (sync) LRK_CUDA(h, cudaStreamSynchronize(st));
+    return LRK_OK;
+}
+
 // multiplier of the tile walk: close to the golden-ratio fraction of the tile count and coprime with it
 static int64_t sgd_tile_mul(int64_t n) {
     const int64_t T = (n + 31) / 32;
@@ -569,12 +615,18 @@ static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp_in) {
         sp.inflight_frac = (float)((double)grid * 8.0 * (double)(32 / G > 8 ? 32 / G : 8) / (double)(sp.n > 0 ? sp.n : 1)); \
         KERN<<<grid, 256, 0, h->stream>>>(sp);                                \
     } while (0)
+    // user factors no longer small -> the curvature-tracking variant (lrk_common.cuh, pnorm2_host)
+    bool track = atomic && sp.item_deg && h->pnorm2_host > 0.25f;
+    { static const char* env = getenv("LRK_SGD_TRACK"); if (env && atomic && sp.item_deg) track = atoi(env) != 0; }    // A/B probe
     if (h->cfg.model == LRK_MODEL_BIASEDMF) {
-        if (atomic) LRK_GO((sgd_rating_epoch_kernel<G, V, true, true>)); else LRK_GO((sgd_rating_epoch_kernel<G, V, true, false>));
+        if (track) LRK_GO((sgd_rating_epoch_kernel<G, V, true, true, true>));
+        else if (atomic) LRK_GO((sgd_rating_epoch_kernel<G, V, true, true>)); else LRK_GO((sgd_rating_epoch_kernel<G, V, true, false>));
     } else if (h->cfg.model == LRK_MODEL_PMF) {
-        if (atomic) LRK_GO((sgd_rating_epoch_kernel<G, V, false, true>)); else LRK_GO((sgd_rating_epoch_kernel<G, V, false, false>));
+        if (track) LRK_GO((sgd_rating_epoch_kernel<G, V, false, true, true>));
+        else if (atomic) LRK_GO((sgd_rating_epoch_kernel<G, V, false, true>)); else LRK_GO((sgd_rating_epoch_kernel<G, V, false, false>));
     } else {
-        if (atomic) LRK_GO((sgd_bpr_epoch_kernel<G, V, true>)); else LRK_GO((sgd_bpr_epoch_kernel<G, V, false>));
+        if (sp.blk_hi > 0) { if (atomic) LRK_GO((sgd_bpr_epoch_kernel<G, V, true, true>)); else LRK_GO((sgd_bpr_epoch_kernel<G, V, false, true>)); }
+        else if (atomic) LRK_GO((sgd_bpr_epoch_kernel<G, V, true>)); else LRK_GO((sgd_bpr_epoch_kernel<G, V, false>));
     }
 #undef LRK_GO
     LRK_LAUNCH_CHECK(h);
