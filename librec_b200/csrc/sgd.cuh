@@ -124,7 +124,7 @@ __device__ __forceinline__ void block_loss_commit(double v, double* out) {
 // TRACK: refresh the curvature estimate max(1, mean |p_u|^2) from every run tile (a few registers and 5 shuffles per
 // tile; chosen by the launcher when the user factors are no longer small, see sgd_launch_gv)
 template <int G, int V, bool BIASED, bool ATOMIC, bool TRACK = false>
-__global__ void __launch_bounds__(256, (G * V <= 16 && !TRACK) ? 4 : 1) sgd_rating_epoch_kernel(SgdParams p) {
+__global__ void __launch_bounds__(256, (G * V <= 16 && !TRACK) ? 4 : ((G * V <= 32) ? 3 : 1)) sgd_rating_epoch_kernel(SgdParams p) {
     constexpr int RPS = 32 / G;  // ratings per warp step
     constexpr int STEPS = G;     // steps per 32-rating tile
     const int lane = threadIdx.x & 31;
