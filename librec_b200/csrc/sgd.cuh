@@ -19,10 +19,14 @@
 // Item-run tiles: popular items receive most of the updates (Zipf), and the L2 atomic units serialise
 // REDs to one address, so hot item rows bound the epoch long before HBM does -- and the more so under
 // DSGD, where a sub-epoch concentrates every SM on 1/G of the catalogue (measured: 5.8 G -> 3.3 G
-// updates/s per GPU at 4 strata).  Staging therefore groups the ratings of items with >= 64 ratings into
-// runs of 32 (staging.cuh); a warp that finds all 32 items of its tile equal reads the item row once per
-// 8 ratings, accumulates their item-side deltas in registers and issues ONE vector RED for them (an
-// 8-rating mini-batch for that item; the user side is untouched): 8x fewer row reads and REDs.
+// updates/s per GPU at 4 strata).  Staging therefore groups the ratings of items with >= LRK_RUN_MIN_DEGREE
+// ratings into runs of 32 (staging.cuh); a warp that finds all 32 items of its tile equal reads the item row once
+// per flush period, accumulates the item-side deltas in registers and issues ONE vector RED for them (a
+// mini-batch for that item; the user side is untouched).  The period is 8 ratings, 16 from hot_flush_deg
+// ratings per item and the whole tile from twice that (default 512 / 1024: <= 1/32 of the item's ratings).
+// Every flush of a hot item is 16 REDs to the same two lines, and same-line REDs serialise in L2: on one of 8
+// DSGD item blocks of the ML-20M shape the epoch kernel took 0.32 ms with 8-rating flushes, 0.24 ms with these
+// (tools/probe_block_shape.py); the whole matrix 1.74 -> 1.64 ms.
 //
 // Stability: B ratings of one item in flight at once act like ONE step of size lr*B on its bias
 // (e' = (1 - lr*B) e; unstable from lr*B = 2), whereas the reference's sequential walk over the same B ratings
@@ -33,7 +37,7 @@
 // |p|^2 grows to ~8 at k=128), so x is multiplied by max(1, mean |p_u|^2): the value at the start of the epoch
 // (user_norm2_kernel, read from device memory) for a warp's first run tile, then the mean over the 32 users of
 // the warp's previous run tile (the factors grow fast in the first epochs; 5 shuffles per tile).  Config C4 (PMF k=128, lr 0.01, Netflix
-// shape) ran at 1.2 G updates/s behind the rollback safeguard (grid / 8) before this, at 7.2 G without a rollback after.  (Without it the grid had to be capped at lr * s * in-flight <= 1, s = share of the hottest item,
+// shape) ran at 1.2 G updates/s behind the rollback safeguard (grid / 8) before this, at 6.6 G without a rollback after.  (Without it the grid had to be capped at lr * s * in-flight <= 1, s = share of the hottest item,
 // which left 142 of 592 CTAs at 8 DSGD strata; sgd_grid_for keeps that cap for launches without degrees.)
 #pragma once
 #include "lrk_common.cuh"
@@ -59,6 +63,8 @@ struct SgdParams {
     // inflight_frac = (ratings in flight) / n, filled in by the launcher
     const uint32_t* item_deg;
     float inflight_frac;
+    // run tiles of items with at least this many ratings flush every 16 ratings, from twice this on once per tile
+    uint32_t hot_flush_deg;
     const float* pnorm2;    // device scalar: mean |p_u|^2 of the rank's user factors at the start of the epoch (NULL = 1)
     // BPR only
     const int64_t* __restrict__ rowptr;
@@ -168,8 +174,22 @@ __global__ void __launch_bounds__(256, (G * V <= 16 && !TRACK) ? 4 : ((G * V <= 
             // x = lr * (ratings of this item in flight) * max(1, mean |p_u|^2): curvature 1 for the bias, |p_u|^2 along
             // p_u for the row; the item-side step of the tile is scaled by (1 - exp(-x)) / x
             float damp = 1.f, psq = 0.f;
+            // flush period in steps: 8 ratings by default; 16 / the whole tile for items whose degree makes that an
+            // equally small share (<= 1/128) -- every flush of a hot item is 16 same-line REDs that serialise in L2
+            int flush_steps = HOT_CHUNK;
             if (p.item_deg) {
-                const float x = lr * (float)__ldg(p.item_deg + i0) * p.inflight_frac * pn2;
+                const uint32_t deg = __ldg(p.item_deg + i0);
+                // a flush is a mini-batch of its own: lengthen it only while lr * curvature * (ratings per flush) <= 1/8,
+                // which leaves room for |p_u|^2 growing inside the epoch (PMF on un-centred ratings: 1e-4 -> 8 within the
+                // first two epochs; config C4 rolled back twice with 32-rating flushes at lr 0.01)
+                const float lrc = lr * pn2;
+                if (deg >= p.hot_flush_deg) {
+                    if (deg >= 2u * p.hot_flush_deg && lrc * 32.f <= 0.125f) flush_steps = STEPS;
+                    else if (STEPS >= 2 * HOT_CHUNK && lrc * (float)(2 * HOT_CHUNK * RPS) <= 0.125f) flush_steps = 2 * HOT_CHUNK;
+                }
+                // inflight_frac counts HOT_CHUNK steps per warp; a longer flush period keeps that many more in flight,
+                // and the warp's own flush period is in flight whatever the grid
+                const float x = lrc * fmaxf((float)deg * p.inflight_frac * (float)(flush_steps / HOT_CHUNK), (float)(flush_steps * RPS));
                 if (x > 1e-3f) damp = (1.f - __expf(-x)) / x;
             }
             int32_t un = __shfl_sync(0xffffffffu, u_l, grp);
@@ -178,7 +198,7 @@ __global__ void __launch_bounds__(256, (G * V <= 16 && !TRACK) ? 4 : ((G * V <= 
             for (int v = 0; v < V; ++v) pn[v] = ldcg4(p.P + (int64_t)un * p.ld + (v * G + sub) * 4);
             if (BIASED && sub == 0) bun = __ldcg(p.bu + un);
 #pragma unroll 1
-            for (int c0 = 0; c0 < STEPS; c0 += HOT_CHUNK) {
+            for (int c0 = 0; c0 < STEPS; c0 += flush_steps) {
                 float4 q[V], dq[V];
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
@@ -187,9 +207,11 @@ __global__ void __launch_bounds__(256, (G * V <= 16 && !TRACK) ? 4 : ((G * V <= 
                 }
                 const float bi0 = BIASED ? __ldcg(p.bi + i0) : 0.f;
                 float dbi = 0.f;
+#pragma unroll 1
+                for (int c1 = c0; c1 < c0 + flush_steps; c1 += HOT_CHUNK) {
 #pragma unroll
                 for (int sc = 0; sc < HOT_CHUNK; ++sc) {
-                    const int s = c0 + sc;
+                    const int s = c1 + sc;
                     float4 pc[V];
 #pragma unroll
                     for (int v = 0; v < V; ++v) pc[v] = pn[v];
@@ -233,7 +255,8 @@ __global__ void __launch_bounds__(256, (G * V <= 16 && !TRACK) ? 4 : ((G * V <= 
                     }
                     loss_f += reg_acc;
                 }
-                // one update of the item row for the chunk
+                }
+                // one update of the item row per flush period
 #pragma unroll
                 for (int m = G; m < 32; m <<= 1) {
 #pragma unroll
@@ -606,6 +629,10 @@ static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp_in) {
     static const bool no_damp = getenv("LRK_SGD_NODAMP") && atoi(getenv("LRK_SGD_NODAMP"));    // A/B probe: fall back to the grid cap
     if (no_damp) sp.item_deg = nullptr;
     sp.tile_mul = sgd_tile_mul(sp.n);
+    {   // LRK_SGD_HOT_FLUSH: A/B probe of the degree from which run tiles flush every 16 ratings (0 = always every 8)
+        static const char* env = getenv("LRK_SGD_HOT_FLUSH");
+        sp.hot_flush_deg = env ? (atoi(env) > 0 ? (uint32_t)atoi(env) : 0xffffffffu) : 512u;
+    }
     const bool atomic = h->cfg.update_mode == LRK_UPDATE_ATOMIC;
     int grid = 1;
 #define LRK_GO(KERN)                                                          \

@@ -55,7 +55,7 @@ def test_conflict_free_epoch_matches_oracle(O, capi, model_name, k, mode):
 @pytest.mark.parametrize("model_name,k", [("biasedmf", 64), ("pmf", 128), ("biasedmf", 20), ("pmf", 3)])
 def test_item_run_tiles_are_minibatches_for_the_item(O, capi, model_name, k):
     """Items with >= 512 ratings are staged as runs of 32 ratings (staging.cuh) and the kernel applies one item-row
-    update per 8 ratings of a run (sgd.cuh): for users that rate a single item this is a mini-batch step on q_i / b_i.
+    update per flush period (8, 16 or 32 ratings of a run, sgd.cuh): for users that rate a single item this is a mini-batch step on q_i / b_i.
     To first order in lr the epoch equals one step with every gradient taken at the initial q_i; which chunks see
     which earlier updates depends on scheduling and moves the result by O(lr^2 * degree) -- hence the tolerances."""
     n_items, per_item = 6, 512
