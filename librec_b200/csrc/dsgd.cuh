@@ -337,7 +337,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     LRK_CUDA(h, cudaMemcpyAsync(h->bk_P, h->P32, sizeof(float) * np_, cudaMemcpyDeviceToDevice, st));
     LRK_CUDA(h, cudaMemcpyAsync(h->bk_Q, s->qbuf[s->cur], sizeof(float) * s->buf_floats, cudaMemcpyDeviceToDevice, st));
     if (biased_) LRK_CUDA(h, cudaMemcpyAsync(h->bk_bu, h->bu32, sizeof(float) * (size_t)h->U, cudaMemcpyDeviceToDevice, st));
-    if (h->h_pnorm2) h->pnorm2_host = *h->h_pnorm2;
+    if (h->h_pnorm2) { h->pnorm2_prev = h->pnorm2_host; h->pnorm2_host = *h->h_pnorm2; }
     for (int attempt = 0;; ++attempt) {
     LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
     LRK_CUDA(h, cudaEventRecord(h->ev0, st));

@@ -243,7 +243,7 @@ static void fill_sgd_params(lrk_handle_s* h, SgdParams& sp, float lr, float reg_
     sp.loss = h->d_loss; sp.ld = h->ld;
     sp.hot_share = h->cfg.model == LRK_MODEL_BPR ? 0.0 : h->hot_share;
     sp.item_deg = h->cfg.model == LRK_MODEL_BPR ? nullptr : h->d_item_deg;
-    if (h->h_pnorm2) h->pnorm2_host = *h->h_pnorm2;
+    if (h->h_pnorm2) { h->pnorm2_prev = h->pnorm2_host; h->pnorm2_host = *h->h_pnorm2; }
     sp.rowptr = h->d_rowptr; sp.col = h->d_col; sp.U = h->U; sp.I = h->I;
     sp.seed_lo = (uint32_t)h->cfg.seed; sp.seed_hi = (uint32_t)(h->cfg.seed >> 32); sp.epoch = (uint32_t)epoch_idx;
 }

@@ -33,6 +33,7 @@ struct lrk_handle_s {
     double hot_share = 0.0;   // largest share one item has of the train ratings (stability cap of the SGD grid)
     float* d_pnorm2 = nullptr;        // mean |p_u|^2 at the start of the epoch (curvature term of that step)
     float pnorm2_host = 0.f;          // its host copy, refreshed with every loss read-back (picks the kernel variant)
+    float pnorm2_prev = 0.f;          // the value one epoch earlier (growth of the user factors, sgd_launch_gv)
     uint32_t* d_item_deg = nullptr;   // ratings per item in this handle's shard (staleness-aware step of run tiles, sgd.cuh)
 
     // factors: fp32 working copies (padded rows) + fp64 masters (dense rows, what Java sees)

@@ -643,7 +643,11 @@ static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp_in) {
         KERN<<<grid, 256, 0, h->stream>>>(sp);                                \
     } while (0)
     // user factors no longer small -> the curvature-tracking variant (lrk_common.cuh, pnorm2_host)
-    bool track = atomic && sp.item_deg && h->pnorm2_host > 0.25f;
+    // ... or growing fast: PMF on un-centred ratings takes mean |p_u|^2 from 1e-4 to ~8 within the first two epochs, and an
+    // epoch that starts below the threshold can end far above it (config C4 then needed the rollback in 1 run of 3)
+    bool track = atomic && sp.item_deg && (h->pnorm2_host > 0.25f || (h->pnorm2_host > 0.02f && h->pnorm2_host > 4.f * h->pnorm2_prev));
+    { static const bool trace = getenv("LRK_SGD_TRACE") && atoi(getenv("LRK_SGD_TRACE"));
+      if (trace) fprintf(stderr, "[sgd] epoch %u n %lld mean|p|^2 %.5f (prev %.5f) track %d conc_div %d\n", sp.epoch, (long long)sp.n, h->pnorm2_host, h->pnorm2_prev, (int)track, sp.conc_div); }
     { static const char* env = getenv("LRK_SGD_TRACK"); if (env && atomic && sp.item_deg) track = atoi(env) != 0; }    // A/B probe
     if (h->cfg.model == LRK_MODEL_BIASEDMF) {
         if (track) LRK_GO((sgd_rating_epoch_kernel<G, V, true, true, true>));

@@ -69,15 +69,19 @@ __global__ void f32_to_f64_rows_kernel(const float* __restrict__ src, double* __
 // Stream order.  The COO stream of an epoch is, per item block (one block on a single GPU, `world`
 // blocks under DSGD): [item-run tiles] [everything else, shuffled].  An item-run tile is 32 ratings
 // of ONE item (items with >= LRK_RUN_MIN_DEGREE ratings in the block's shard give floor(deg/32) of
-// them, the CSR-order remainder joins the shuffled part); tiles are shuffled among themselves.  A run
-// is a 32-rating mini-batch for its item, so only items for which that is a small step qualify: at
-// 512 ratings a run is 1/16 of the item's ratings, the same share the staleness cap of sgd_grid_for
-// allows in flight (with runs from 64 ratings up, PMF at lr 0.01 diverged on ml-100k).  The
+// them, the CSR-order remainder joins the shuffled part); tiles are shuffled among themselves.  The
+// kernel flushes the item-side delta of a run every 8 ratings (16 / 32 for hot items, sgd.cuh), so a flush of
+// a 128-rating item is a mini-batch of 1/16 of its ratings -- the share the staleness cap of sgd_grid_for
+// allows in flight -- and its step is damped by the staleness-aware factor.  (Before that factor existed,
+// runs from 64 ratings up made PMF at lr 0.01 diverge on ml-100k and the threshold was 512; 512 -> 128 moves
+// half of the remaining ratings into run tiles: C2 epoch 1.65 -> 1.50 ms.)  The
 // SGD kernel turns a run tile into a single update of the item row (sgd.cuh) and walks the tiles with
 // a multiplicative stride so that the two parts interleave in time.  All of it is one radix sort on
 //   key = block : 6 | is_rest : 1 | hash : 32 | tile or entry id : 25
 // ---------------------------------------------------------------------------------------------
-#define LRK_RUN_MIN_DEGREE 512
+#ifndef LRK_RUN_MIN_DEGREE
+#define LRK_RUN_MIN_DEGREE 128
+#endif
 
 __global__ void item_degree_kernel(const int32_t* __restrict__ col, int64_t nnz, uint32_t* __restrict__ deg) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

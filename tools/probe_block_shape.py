@@ -33,6 +33,7 @@ def main():
     from librec_b200 import capi, synth
     capi.load()
     striped = "--striped" in sys.argv
+    only = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--block=")]
     Gs = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [8, 4]
     d = synth.make_ratings("ml-20m", shard=0)
     U, I = d["U"], d["I"]
@@ -59,6 +60,8 @@ def main():
         for name, plist in parts.items():
             times, sizes, guard, loss = [], [], [], []
             for b, items in enumerate(plist):
+                if only and b not in only:
+                    continue
                 keep = np.full(I, -1, np.int64)
                 keep[items] = np.arange(items.shape[0])
                 rowptr, col, val = sub_csr(d, rows, keep)
@@ -74,8 +77,8 @@ def main():
                     loss.append(ls[-1])
                 times.append(float(np.median(ms[3:])))
                 sizes.append(int(col.shape[0]))
-            line = {"G": G, "partition": name, "ratings": sizes, "items": [int(p.shape[0]) for p in plist], "kernel_ms": times, "rollbacks": guard, "loss_8": loss,
-                    "sum_ms": float(np.sum(times)), "G_x_max_ms": float(G * np.max(times)), "whole_matrix_updates_per_s_if_bound_by_max": nnz / (G * np.max(times) * 1e-3)}
+            line = {"G": G, "partition": name, "ratings": sizes, "items": [int(p.shape[0]) for p in plist], "blocks": only or list(range(G)), "kernel_ms": times, "rollbacks": guard, "loss_8": loss,
+                    "sum_ms": float(np.sum(times)), "G_x_max_ms": float(G * np.max(times))}
             print(json.dumps(line), flush=True)
             out.append(line)
     return 0
