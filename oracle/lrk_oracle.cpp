@@ -323,7 +323,7 @@ static inline double dot_lr(const double* a, const double* b, int k) {
     return r;
 }
 
-enum { LRO_BIASEDMF = 0, LRO_PMF = 1, LRO_BPR = 2 };
+enum { LRO_BIASEDMF = 0, LRO_PMF = 1, LRO_BPR = 2, LRO_RANKSGD = 3 };
 
 // predict(): BiasedMFRecommender.java:118-120 ; MatrixFactorizationRecommender.java:104-106
 static inline double predict_raw(int model, int k, const double* P, const double* Q, const double* bu,
@@ -449,6 +449,97 @@ LRO_API double lro_bpr_epoch(int32_t U, int32_t I, const int64_t* rowptr, const 
     return loss;  // no *0.5 for BPR
 }
 
+// -------------------------------------------------------------------------------------
+// RankSGD: recommender/cf/ranking/RankSGDRecommender.java:42-108.
+// setup (:42-58): itemProbs = the items with at least one train rating, prob = users(j) / numRates, put into a
+// java.util.HashMap<Integer, Double> in ascending item order and sorted ASCENDING by prob with the stable
+// Collections.sort (util/Lists.java:266-308) -- so ties keep the HashMap's iteration order (ascending bucket
+// (h ^ h>>>16) & (cap-1); the JDK helpers further down restate it; forward-declared here).
+// -------------------------------------------------------------------------------------
+static inline uint32_t jhash_bucket(int32_t key, uint32_t cap);
+static inline uint32_t jhashset_capacity(int64_t n);
+
+// out_items / out_probs: capacity I; returns the list length m
+LRO_API int32_t lro_ranksgd_item_probs(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col,
+                                       int32_t* out_items, double* out_probs) {
+    const int64_t nnz = rowptr[U];
+    std::vector<int64_t> users((size_t)I, 0);
+    for (int64_t e = 0; e < nnz; ++e) users[(size_t)col[e]]++;
+    struct Ent { int32_t item; double prob; uint64_t pos; };
+    std::vector<Ent> ents;
+    int64_t m = 0;
+    for (int32_t j = 0; j < I; ++j) if (users[(size_t)j] > 0) ++m;
+    const uint32_t cap = jhashset_capacity(m);
+    uint64_t seq = 0;
+    for (int32_t j = 0; j < I; ++j) {
+        const double prob = ((double)users[(size_t)j] + 0.0) / (double)nnz;      // (users + 0.0) / numRates
+        if (prob > 0) ents.push_back({j, prob, ((uint64_t)jhash_bucket(j, cap) << 32) | (seq++)});
+    }
+    std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.pos < b.pos; });       // entrySet() order
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.prob < b.prob; });
+    for (size_t t = 0; t < ents.size(); ++t) { out_items[t] = ents[t].item; out_probs[t] = ents[t].prob; }
+    return (int32_t)ents.size();
+}
+
+// One RankSGD epoch (:62-108): every train entry in CSR order; the negative is drawn by walking the cumulative sum of
+// the ascending list until sum >= rand (Randoms.random() = nextDouble), redrawn while the user has rated it; if the
+// walk ends without a hit (sum of probs < rand by rounding) negItemIdx keeps its previous value, -1 at the first try
+// of an entry -- the reference would then index itemFactors with -1 and throw; restated as "return NaN".
+// error = (pos - neg) - (r - 0); loss += error^2; NO regularisation; old user factor feeds both item updates; loss *= 0.5.
+// trip (3*n int32 (u, i, j)) replaces the CSR walk and the RNG -- NOT reference behaviour, used to run the GPU kernel's own
+// samples through this arithmetic; the rating of (u, i) is looked up in the CSR.  trip_out records what was drawn.
+LRO_API double lro_ranksgd_epoch(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val, int32_t k,
+                                 double* P, double* Q, float lr_f, int64_t n, const int32_t* trip, int32_t* trip_out) {
+    const double learnRate = (double)lr_f;
+    std::vector<int32_t> items((size_t)I);
+    std::vector<double> probs((size_t)I);
+    int32_t m = 0;
+    if (!trip) m = lro_ranksgd_item_probs(U, I, rowptr, col, items.data(), probs.data());
+    double loss = 0.0;
+    int32_t u = 0;
+    const int64_t total = trip ? n : rowptr[U];
+    for (int64_t t = 0; t < total; ++t) {
+        int32_t pi, nj;
+        double r;
+        if (trip) {
+            u = trip[3 * t]; pi = trip[3 * t + 1]; nj = trip[3 * t + 2];
+            const int32_t* b = col + rowptr[u];
+            const int32_t* e = col + rowptr[u + 1];
+            const int32_t* f = std::lower_bound(b, e, pi);
+            if (f == e || *f != pi) return std::nan("");
+            r = val[f - col];
+        } else {
+            while (rowptr[u + 1] <= t) ++u;
+            pi = col[t]; r = val[t];
+            nj = -1;
+            for (;;) {
+                double sum = 0;
+                const double rand = lro_uniform();
+                for (int32_t c = 0; c < m; ++c) {
+                    sum += probs[(size_t)c];
+                    if (sum >= rand) { nj = items[(size_t)c]; break; }
+                }
+                if (nj < 0 || !std::binary_search(col + rowptr[u], col + rowptr[u + 1], nj)) break;
+            }
+            if (nj < 0) return std::nan("");
+        }
+        if (trip_out) { trip_out[3 * t] = u; trip_out[3 * t + 1] = pi; trip_out[3 * t + 2] = nj; }
+        double* pu = P + (int64_t)u * k;
+        double* qi = Q + (int64_t)pi * k;
+        double* qj = Q + (int64_t)nj * k;
+        const double error = (dot_lr(pu, qi, k) - dot_lr(pu, qj, k)) - (r - 0.0);
+        loss += error * error;
+        const double sgd = learnRate * error;
+        for (int f = 0; f < k; ++f) {
+            const double uf = pu[f], pf = qi[f], nf = qj[f];
+            pu[f] += -sgd * (pf - nf);
+            qi[f] += -sgd * uf;
+            qj[f] += sgd * uf;
+        }
+    }
+    return 0.5 * loss;
+}
+
 // AbstractRecommender.isConverged: recommender/AbstractRecommender.java:249-267.
 // returns 1 converged, 0 not, -1 = would throw LibrecException (NaN / Inf loss)
 LRO_API int32_t lro_is_converged(double last_loss, double loss, float* delta_out) {
@@ -486,6 +577,7 @@ LRO_API int32_t lro_train(int32_t model, int32_t U, int32_t I, const int64_t* ro
         double loss;
         if (model == LRO_BIASEDMF) loss = lro_biasedmf_epoch(U, rowptr, col, val, k, P, Q, bu, bi, mu, learnRate, regU, regI, regB, nullptr, nullptr);
         else if (model == LRO_PMF) loss = lro_pmf_epoch(U, rowptr, col, val, k, P, Q, learnRate, regU, regI, nullptr, nullptr);
+        else if (model == LRO_RANKSGD) loss = lro_ranksgd_epoch(U, I, rowptr, col, val, k, P, Q, learnRate, 0, nullptr, nullptr);
         else loss = lro_bpr_epoch(U, I, rowptr, col, k, P, Q, learnRate, regU, regI, rowptr[U], nullptr, nullptr);
         if (losses_out) losses_out[iter - 1] = loss;
         done = iter;

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liblrk_oracle.so")
 
-BIASEDMF, PMF, BPR = 0, 1, 2
+BIASEDMF, PMF, BPR, RANKSGD = 0, 1, 2, 3
 
 
 def build(force=False):
@@ -85,6 +85,11 @@ def lib():
     L.lro_train.argtypes = [C.c_int32, C.c_int32, C.c_int32, _i64p, _i32p, _f64p, C.c_int32, _f64p, _f64p,
                             C.c_void_p, C.c_void_p, C.c_double, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double,
                             C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+    L.lro_ranksgd_item_probs.restype = C.c_int32
+    L.lro_ranksgd_item_probs.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _i32p, _f64p]
+    L.lro_ranksgd_epoch.restype = C.c_double
+    L.lro_ranksgd_epoch.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _f64p, C.c_int32, _f64p, _f64p, C.c_float,
+                                    C.c_int64, C.c_void_p, C.c_void_p]
     L.lro_eval_rating.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _f64p, C.c_int32, _f64p, _f64p, C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
     L.lro_eval_ranking.argtypes = [C.c_int32, C.c_int32, _i32p, _i32p, _i64p, _i32p, _f64p, _i32p, _i32p, C.c_int32, _f64p]

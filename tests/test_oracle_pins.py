@@ -189,6 +189,62 @@ def test_bpr_sampler_respects_rows(O):
         assert i in row and j not in row
 
 
+# ---- RankSGD: recommender/cf/ranking/RankSGDRecommender.java ---------------------------
+def test_ranksgd_single_update_by_hand(O):
+    """:86-103 worked by hand: error = (pos - neg) - (r - 0); no regularisation; the OLD user factor feeds both item updates"""
+    L = O.lib()
+    tr = O.Csr(1, 2, [0, 1], [0], [4.0])
+    P = np.array([[0.2, -0.1]]); Q = np.array([[0.4, 0.3], [-0.5, 0.6]])
+    trip = np.array([0, 0, 1], np.int32)
+    lr = _f32(0.01)
+    pos = (0.0 + 0.2 * 0.4) + -0.1 * 0.3
+    neg = (0.0 + 0.2 * -0.5) + -0.1 * 0.6
+    err = (pos - neg) - (4.0 - 0.0)
+    sgd = lr * err
+    nP, nQ = P.copy(), Q.copy()
+    for f in range(2):
+        uf, pf, nf = P[0, f], Q[0, f], Q[1, f]
+        nP[0, f] = uf + -sgd * (pf - nf)
+        nQ[0, f] = pf + -sgd * uf
+        nQ[1, f] = nf + sgd * uf
+    got = L.lro_ranksgd_epoch(1, 2, tr.rowptr, tr.col, tr.val, 2, P, Q, 0.01, 1, trip.ctypes.data, None)
+    assert got == 0.5 * err * err
+    assert P.tolist() == nP.tolist() and Q.tolist() == nQ.tolist()
+
+
+def test_ranksgd_item_probs_ascending_with_hashmap_tie_order(O):
+    """:47-57: prob = users(j) / numRates, zero-probability items dropped, ascending by prob, ties in HashMap order
+    (= ascending item id while ids stay below the table size)"""
+    #            item: 0  1  2  3  4     users: 2, 0, 1, 2, 1
+    tr = O.Csr(3, 5, [0, 3, 5, 6], [0, 2, 3, 0, 3, 4], np.ones(6))
+    items = np.zeros(5, np.int32); probs = np.zeros(5)
+    m = O.lib().lro_ranksgd_item_probs(3, 5, tr.rowptr, tr.col, items, probs)
+    assert m == 4
+    assert items[:m].tolist() == [2, 4, 0, 3]
+    assert probs[:m].tolist() == [1 / 6, 1 / 6, 2 / 6, 2 / 6]
+
+
+def test_ranksgd_reference_sampler_draws_unrated_items_by_popularity(O):
+    tr = rng_csr(O, 200, 40, 0.2, 7)
+    k = 4
+    P = np.zeros((tr.U, k)); Q = np.zeros((tr.I, k))
+    out = np.zeros(3 * tr.nnz, np.int32)
+    O.lib().lro_seed(11)
+    loss = O.lib().lro_ranksgd_epoch(tr.U, tr.I, tr.rowptr, tr.col, tr.val, k, P, Q, 0.0, 0, None, out.ctypes.data)
+    t = out.reshape(-1, 3)
+    assert np.array_equal(t[:, 0], tr.rows()) and np.array_equal(t[:, 1], tr.col)        # every train entry, CSR order
+    for u, i, j in t[:800]:
+        assert j not in tr.col[tr.rowptr[u]:tr.rowptr[u + 1]]
+    assert loss == 0.5 * float(np.sum(tr.val ** 2))                                       # zero factors: error = -r
+    # negatives follow item popularity (before the per-user rejection): the most popular quarter of the catalogue is
+    # drawn more often than the least popular quarter
+    pop = np.bincount(tr.col, minlength=tr.I)
+    order = np.argsort(pop)
+    drawn = np.bincount(t[:, 2], minlength=tr.I)
+    assert drawn[order[-10:]].sum() > 1.3 * drawn[order[:10]].sum()
+    assert drawn[pop == 0].sum() == 0
+
+
 # ---- learning-rate schedule / convergence (host logic the shim keeps in Java) -----------------------
 def test_update_lrate_and_is_converged(O):
     L = O.lib()
