@@ -49,7 +49,14 @@ typedef enum {
  * biasedmf -> recommender/cf/rating/BiasedMFRecommender.java
  * pmf      -> vanilla PMF loop, recommender/cf/rating/PMFSimilarityRecommender.java:59-90
  * bpr      -> recommender/cf/ranking/BPRRecommender.java */
-typedef enum { LRK_MODEL_BIASEDMF = 0, LRK_MODEL_PMF = 1, LRK_MODEL_BPR = 2 } lrk_model;
+typedef enum {
+    LRK_MODEL_BIASEDMF = 0,
+    LRK_MODEL_PMF = 1,
+    LRK_MODEL_BPR = 2,
+    /* ranksgd -> recommender/cf/ranking/RankSGDRecommender.java:62-108: one update per train entry
+     * against a negative drawn by item popularity; single GPU; lrk_sgd_epoch ignores the regularisation arguments */
+    LRK_MODEL_RANKSGD = 3
+} lrk_model;
 
 /* how concurrent updates to one factor row are combined */
 typedef enum {

@@ -50,12 +50,12 @@ int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out) {
     *out = nullptr;
     if (cfg->num_factors < 1 || cfg->num_factors > LRK_MAX_FACTORS)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "num_factors must be in 1..256", __FILE__, __LINE__);
-    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_BPR)
+    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_RANKSGD)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown model", __FILE__, __LINE__);
     if (cfg->update_mode < LRK_UPDATE_ATOMIC || cfg->update_mode > LRK_UPDATE_REFERENCE_ORDER)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown update_mode", __FILE__, __LINE__);
-    if (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER && cfg->model == LRK_MODEL_BPR)
-        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "reference-order mode covers BiasedMF and PMF (BPR draws from a sequential RNG)", __FILE__, __LINE__);
+    if (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER && (cfg->model == LRK_MODEL_BPR || cfg->model == LRK_MODEL_RANKSGD))
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "reference-order mode covers BiasedMF and PMF (BPR and RankSGD draw from a sequential RNG)", __FILE__, __LINE__);
     int ndev = 0;
     LRK_CUDA(nullptr, cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev)
@@ -100,7 +100,7 @@ int lrk_destroy(lrk_handle_t h) {
     lrk_dev_free(&h->P32); lrk_dev_free(&h->Q32); lrk_dev_free(&h->bu32); lrk_dev_free(&h->bi32);
     lrk_dev_free(&h->P64); lrk_dev_free(&h->Q64); lrk_dev_free(&h->bu64); lrk_dev_free(&h->bi64);
     lrk_dev_free(&h->d_loss);
-    lrk_dev_free(&h->d_item_deg); lrk_dev_free(&h->d_pnorm2);
+    lrk_dev_free(&h->d_item_deg); lrk_dev_free(&h->d_item_cum); lrk_dev_free(&h->d_pnorm2);
     lrk_dev_free(&h->bk_P); lrk_dev_free(&h->bk_Q); lrk_dev_free(&h->bk_bu); lrk_dev_free(&h->bk_bi);
     lrk_dev_free(&h->tn_users); lrk_dev_free(&h->tn_items); lrk_dev_free(&h->tn_scores); lrk_dev_free(&h->tn_counts);
     if (h->scratch) cudaFree(h->scratch);
@@ -148,6 +148,19 @@ int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowpt
     h->U = U; h->I = I; h->nnz = nnz;
     rc = stage_coo_from_csr(h, h->d_rowptr, h->d_col, val, U, I, nnz, h->d_su, h->d_si, h->d_sr, /*validate=*/true);
     if (rc) return rc;
+    if (h->cfg.model == LRK_MODEL_RANKSGD && nnz > 0) {
+        // sampling table of the negatives: inclusive prefix sums of the item degrees (RankSGDRecommender.java:47-57)
+        if ((rc = lrk_dev_alloc(h, &h->d_item_cum, (size_t)I))) return rc;
+        size_t tb = 0;
+        LRK_CUDA(h, cub::DeviceScan::InclusiveSum(nullptr, tb, h->d_item_deg, h->d_item_cum, (int)I, st));
+        void* tmp = nullptr;
+        LRK_CUDA(h, cudaMalloc(&tmp, tb + 16));
+        cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, tb, h->d_item_deg, h->d_item_cum, (int)I, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(tmp);
+        LRK_CUDA(h, e);
+        h->launches++;
+    }
     if (h->cfg.update_mode == LRK_UPDATE_REFERENCE_ORDER) {
         exact_release((ExactSchedule*)h->exact);
         h->exact = nullptr;
@@ -193,7 +206,8 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I * ld, 256), 256, 0, st>>>(h->Q64, h->Q32, I, k, ld); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu64, h->bu32, U, 1, 1); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi64, h->bi32, I, 1, 1); LRK_LAUNCH_CHECK(h);
-    if (h->cfg.model != LRK_MODEL_BPR && (rc = refresh_user_norm2(h, false))) return rc;
+    if (h->cfg.model != LRK_MODEL_BPR && (rc = refresh_user_norm2(h, true))) return rc;
+    if (h->h_pnorm2) { h->pnorm2_prev = 0.f; h->pnorm2_host = *h->h_pnorm2; }
     LRK_CUDA(h, cudaStreamSynchronize(st));   // host buffers may be reused by the caller on return
     h->mu = mu;
     h->has_factors = true;
@@ -241,9 +255,16 @@ static void fill_sgd_params(lrk_handle_s* h, SgdParams& sp, float lr, float reg_
     sp.P = h->P32; sp.Q = h->Q32; sp.bu = h->bu32; sp.bi = h->bi32;
     sp.mu = (float)h->mu; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i; sp.reg_b = (float)reg_b;
     sp.loss = h->d_loss; sp.ld = h->ld;
-    sp.hot_share = h->cfg.model == LRK_MODEL_BPR ? 0.0 : h->hot_share;
-    sp.item_deg = h->cfg.model == LRK_MODEL_BPR ? nullptr : h->d_item_deg;
+    sp.hot_share = lrk_is_rating_model(h) ? h->hot_share : 0.0;
+    sp.item_deg = lrk_is_rating_model(h) ? h->d_item_deg : nullptr;
+    sp.item_cum = h->cfg.model == LRK_MODEL_RANKSGD ? h->d_item_cum : nullptr;
     if (h->h_pnorm2) { h->pnorm2_prev = h->pnorm2_host; h->pnorm2_host = *h->h_pnorm2; }
+    // RankSGD: squared loss without regularisation -- B concurrent updates of one item act like ONE step lr * B * |p_u|^2
+    // where the sequential walk contracts by exp(-lr * B * |p_u|^2).  Popular items are hit as positives and, by
+    // construction of the sampler, as negatives (2 x share), and the two only agree while that product is small: the grid
+    // is capped at lr * 2 share * |p|^2 * (ratings in flight) <= 1/4 (sgd_grid_for's hot-item cap).  With <= 1 instead, C1
+    // reached the oracle's loss but Precision@10 0.140 against 0.176 (sequential) / 0.214 (sequential, shuffled order).
+    if (h->cfg.model == LRK_MODEL_RANKSGD) sp.hot_share = 8.0 * h->hot_share * (double)std::max(1.f, h->pnorm2_host);
     sp.rowptr = h->d_rowptr; sp.col = h->d_col; sp.U = h->U; sp.I = h->I;
     sp.seed_lo = (uint32_t)h->cfg.seed; sp.seed_hi = (uint32_t)(h->cfg.seed >> 32); sp.epoch = (uint32_t)epoch_idx;
 }
@@ -290,6 +311,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
         LRK_CUDA(h, cudaMemcpyAsync(h->bk_bi, h->bi32, sizeof(float) * (size_t)h->I, cudaMemcpyDeviceToDevice, st));
     }
     if (sp.item_deg) sp.pnorm2 = h->d_pnorm2;          // refreshed by refresh_user_norm2 at set_factors and after every epoch
+    const bool track_norm = sp.item_deg != nullptr || h->cfg.model == LRK_MODEL_RANKSGD;
     double loss = 0.0;
     for (int attempt = 0;; ++attempt) {
         sp.conc_div = h->conc_div;
@@ -297,7 +319,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
         LRK_CUDA(h, cudaEventRecord(h->ev0, st));
         if (h->nnz > 0 && (rc = sgd_launch(h, sp))) return rc;
         LRK_CUDA(h, cudaEventRecord(h->ev1, st));
-        if (sp.item_deg && (rc = refresh_user_norm2(h, false))) return rc;
+        if (track_norm && (rc = refresh_user_norm2(h, false))) return rc;
         LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
         LRK_CUDA(h, cudaStreamSynchronize(st));
         loss = h->h_loss[0];
@@ -312,7 +334,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
             LRK_CUDA(h, cudaMemcpyAsync(h->bi32, h->bk_bi, sizeof(float) * (size_t)h->I, cudaMemcpyDeviceToDevice, st));
         }
         h->conc_div *= 4; h->good_epochs = 0; h->rollbacks++;
-        if (sp.item_deg && (rc = refresh_user_norm2(h, false))) return rc;
+        if (track_norm && (rc = refresh_user_norm2(h, false))) return rc;
     }
     h->f64_valid = false;
     topn_tc_invalidate(h);
@@ -352,6 +374,10 @@ int lrk_bpr_peek_samples(lrk_handle_t h, int32_t epoch_idx, int64_t first, int64
     fill_sgd_params(h, sp, 0.f, 0.f, 0.f, 0.0, epoch_idx);
     int32_t* d_out = nullptr;
     LRK_CUDA(h, cudaMalloc((void**)&d_out, sizeof(int32_t) * 3 * (size_t)n));
+    if (h->cfg.model == LRK_MODEL_RANKSGD) {
+        if (first + n > h->nnz) { cudaFree(d_out); return lrk_fail(h, LRK_ERR_INVALID, "lrk_bpr_peek_samples", "RankSGD has one sample per train entry: first + n exceeds nnz", __FILE__, __LINE__); }
+        ranksgd_peek_kernel<<<lrk_ceil_div(n, 256), 256, 0, h->stream>>>(sp, first, n, d_out);
+    } else
     bpr_peek_kernel<<<lrk_ceil_div(n, 256), 256, 0, h->stream>>>(sp, first, n, d_out);
     h->launches++;
     cudaError_t e = cudaGetLastError();
@@ -556,6 +582,7 @@ int lrk_comm_unique_id(uint8_t out[128]) { return dsgd_unique_id(out); }
 int lrk_comm_init(lrk_handle_t h, int32_t rank, int32_t world, const uint8_t unique_id[128]) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
     LRK_REQUIRE(h, h->cfg.update_mode != LRK_UPDATE_REFERENCE_ORDER, "reference-order mode is single-GPU");
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_RANKSGD, "RankSGD is single-GPU in this build");
     return dsgd_comm_init(h, rank, world, unique_id);
 }
 

@@ -35,6 +35,7 @@ struct lrk_handle_s {
     float pnorm2_host = 0.f;          // its host copy, refreshed with every loss read-back (picks the kernel variant)
     float pnorm2_prev = 0.f;          // the value one epoch earlier (growth of the user factors, sgd_launch_gv)
     uint32_t* d_item_deg = nullptr;   // ratings per item in this handle's shard (staleness-aware step of run tiles, sgd.cuh)
+    uint32_t* d_item_cum = nullptr;   // RankSGD: inclusive prefix sums of d_item_deg (negative sampling table)
 
     // factors: fp32 working copies (padded rows) + fp64 masters (dense rows, what Java sees)
     float *P32 = nullptr, *Q32 = nullptr, *bu32 = nullptr, *bi32 = nullptr;
@@ -157,3 +158,5 @@ static inline int lrk_scratch_begin(lrk_handle_s* h, size_t bytes, LrkScratch* o
 }
 
 static inline int lrk_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+// BiasedMF / PMF: one update per train rating with the rating as target (item-run tiles, staleness-aware step)
+static inline bool lrk_is_rating_model(const lrk_handle_s* h) { return h->cfg.model == LRK_MODEL_BIASEDMF || h->cfg.model == LRK_MODEL_PMF; }

@@ -382,6 +382,7 @@ std::unique_ptr<MatrixFactorizationCudaRecommender> newRecommender(const std::st
     if (n == "biasedmf" || n == "net.librec.recommender.cuda.biasedmfcudarecommender") return std::make_unique<BiasedMFCudaRecommender>();
     if (n == "pmf" || n == "net.librec.recommender.cuda.pmfcudarecommender") return std::make_unique<PMFCudaRecommender>();
     if (n == "bpr" || n == "net.librec.recommender.cuda.bprcudarecommender") return std::make_unique<BPRCudaRecommender>();
+    if (n == "ranksgd" || n == "net.librec.recommender.cuda.ranksgdcudarecommender") return std::make_unique<RankSGDCudaRecommender>();
     throw LibrecException("ClassNotFoundException: " + name);
 }
 

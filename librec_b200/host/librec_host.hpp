@@ -192,6 +192,13 @@ protected:
     int model() const override { return LRK_MODEL_BPR; }
 };
 
+class RankSGDCudaRecommender : public MatrixFactorizationCudaRecommender {      // cf/ranking/RankSGDRecommender.java:37
+public:
+    std::string simpleName() const override { return "RankSGDCudaRecommender"; }
+protected:
+    int model() const override { return LRK_MODEL_RANKSGD; }
+};
+
 // util/DriverClassUtil.java:79-88 : short name or fully-qualified class name -> recommender
 std::unique_ptr<MatrixFactorizationCudaRecommender> newRecommender(const std::string& className);
 

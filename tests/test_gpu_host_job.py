@@ -177,3 +177,38 @@ def test_job_from_a_ratings_file_end_to_end(O, capi, c1, tmp_path):
     assert len(lines) == ote.nnz
     u0, i0, v0 = lines[0].split(",")
     assert 1000 <= int(u0) < 1000 + full.U and 5000 <= int(i0) < 5000 + full.I and 1.0 <= float(v0) <= 5.0
+
+
+def test_ranksgd_ranking_job(O, capi, c1):
+    """ranksgd-test.properties on the C1 split: the job trains on the device, its lists are the reference's
+    lists for the factors it learned, and the ranking measures come out of the device evaluators"""
+    props = """
+rec.recommender.class=ranksgd
+rec.iterator.learnrate=0.01
+rec.iterator.learnrate.maximum=0.01
+rec.iterator.maximum=30
+rec.user.regularization=0.01
+rec.item.regularization=0.01
+rec.factor.number=10
+rec.learnrate.bolddriver=false
+rec.learnrate.decay=1.0
+rec.recommender.isranking=true
+rec.recommender.ranking.topn=10
+rec.random.seed=1
+"""
+    tr, te = c1["train"], c1["test"]
+    from librec_b200.host.binding import RecommenderJob
+    job = RecommenderJob(props)
+    job.set_data(tr.U, tr.I, tr, te)
+    job.run_job()
+    counts, keys, vals = job.recommended_list()
+    P, Q, _, _, _ = job.factors(10, False)
+    oi, os_, oc = O.recommend_rank(O.BPR, tr.U, tr.I, 10, P, Q, None, None, 0.0, tr, 10)
+    assert np.array_equal(counts, oc)
+    assert np.array_equal(keys, oi[oi >= 0]) and np.array_equal(vals.view(np.int64), os_[oi >= 0].view(np.int64))
+    losses = [float(re.search(r"loss = ([0-9.E-]+)", l).group(1)) for l in job.log() if " iter " in l]
+    assert len(losses) == 30 and losses[-1] < 0.75 * losses[0]
+    assert any(l.startswith("RankSGDCudaRecommender iter 1: loss = ") for l in job.log())
+    exp = O.eval_ranking(te, tr, 10, oi, oc)
+    assert abs(job.metric("PRECISION top 10") - exp["Precision"]) <= 1e-12 and exp["Precision"] > 0.10
+    assert abs(job.metric("NDCG top 10") - exp["NDCG"]) <= 1e-12
