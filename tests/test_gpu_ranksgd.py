@@ -78,8 +78,9 @@ def test_ranksgd_epoch_tracks_oracle_on_its_own_samples(O, capi):
 
 def test_ranksgd_c1_learns_like_the_oracle(O, capi, c1):
     """ranksgd-test.properties (lr 0.01, 30 iterations, 10 factors) on the C1 split.  The oracle's sequential run reaches
-    loss 548.6 k -> 286.3 k and Precision@10 0.176; the RNG streams and the visiting order differ, so the comparison is
-    at the level of the loss curve and the ranking quality."""
+    loss 548.6 k -> 286.3 k and Precision@10 0.176 in CSR order (0.209-0.214 when the same arithmetic visits the entries in
+    a shuffled order); the RNG streams and the visiting order differ, so the comparison is at the level of the loss curve
+    and the ranking quality.  r01 on a B200: loss_30 286.3 k, Precision@10 0.2115."""
     tr, te = c1["train"], c1["test"]
     O.lib().lro_rng_set_state(*c1["rng_state"])
     P, Q, _, _ = O.mf_setup(tr.U, tr.I, 10, False)
@@ -102,7 +103,7 @@ def test_ranksgd_c1_learns_like_the_oracle(O, capi, c1):
     print("RankSGD C1: loss_1 %.1f (oracle %.1f) loss_30 %.1f (oracle %.1f)  P@10 %.4f (oracle %.4f)" % (
         losses[0], olosses[0], losses[-1], olosses[29], p_gpu, p_ora))
     assert abs(losses[0] - olosses[0]) < 0.01 * olosses[0]              # first epoch: factors still ~0, error = -r
-    assert losses[-1] < 0.75 * losses[0] and abs(losses[-1] - olosses[29]) < 0.15 * olosses[29]
+    assert losses[-1] < 0.75 * losses[0] and abs(losses[-1] - olosses[29]) < 0.05 * olosses[29]
     assert p_gpu > 0.10 and p_gpu > 0.7 * p_ora
     # the lists the device returns are the reference's lists for the factors it learned
     ei, es, ec = O.recommend_rank(O.BPR, tr.U, tr.I, 10, gP, gQ, None, None, 0.0, tr, 10, users=users)
