@@ -8,7 +8,7 @@ import java.nio.ByteBuffer;
 final class LibrecB200 {
     static { System.loadLibrary("librec_b200_jni"); }   // ~150-line C file, INTEGRATION.md section 3
 
-    static final int MODEL_BIASEDMF = 0, MODEL_PMF = 1, MODEL_BPR = 2;
+    static final int MODEL_BIASEDMF = 0, MODEL_PMF = 1, MODEL_BPR = 2, MODEL_RANKSGD = 3;
     static final int UPDATE_ATOMIC = 0, UPDATE_HOGWILD = 1, UPDATE_REFERENCE_ORDER = 2;
 
     // every native returns the lrk_status; 0 == LRK_OK
