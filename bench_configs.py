@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Secondary measurements on one B200 for the BASELINE.json configs that bench.py does not headline:
   C3: BPR k=128 SGD epoch (samples/s) on the synthetic ML-20M shape (implicit feedback, device-side sampling)
+  N3 (--only n3): RankSGD k=10 (ranksgd-test.properties) on the ML-20M shape, one update per train entry
   C4: PMF k=128 SGD epoch (updates/s) on the synthetic Netflix shape (480 189 x 17 770, 100 480 507 ratings); under torchrun
       (N ranks) the users are split into N contiguous blocks and the epoch runs as DSGD (strong scaling of the one data set)
 One JSON line per config: device-resident epochs timed with CUDA events (lrk_last_epoch_ms), L2 flushed between
@@ -73,10 +74,11 @@ def run(name, model_name, shape, k, lr, reg, steps, warmup):
     from librec_b200 import capi, synth
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
     bpr = model_name == "bpr"
+    ranksgd = model_name == "ranksgd"
     d = synth.make_ratings(shape, binary=bpr)
     U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
     P, Q, _, _ = synth.init_factors(U, I, k, 11, False)
-    model = capi.MODEL_BPR if bpr else capi.MODEL_PMF
+    model = capi.MODEL_BPR if bpr else (capi.MODEL_RANKSGD if ranksgd else capi.MODEL_PMF)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     with capi.Handle(model, k, seed=1) as h:
         h.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
@@ -89,9 +91,9 @@ def run(name, model_name, shape, k, lr, reg, steps, warmup):
                 ms.append(h.last_epoch_ms())
         guard = h.sgd_safeguard()
     kms = float(np.mean(ms))
-    bytes_per = 6 * k * 4 if bpr else 12 + 4 * k * 4
+    bytes_per = 6 * k * 4 if bpr else (12 + 6 * k * 4 if ranksgd else 12 + 4 * k * 4)     # RankSGD: triple + r/w of p_u, q_i, q_j
     achieved = bytes_per * nnz / (kms * 1e-3) / 1e9
-    print(json.dumps({"config": name, "metric": "BPR samples/s" if bpr else "MF SGD rating-updates/s", "value": nnz / (kms * 1e-3),
+    print(json.dumps({"config": name, "metric": "BPR samples/s" if bpr else ("RankSGD updates/s" if ranksgd else "MF SGD rating-updates/s"), "value": nnz / (kms * 1e-3),
                       "unit": "samples/s" if bpr else "updates/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": kms,
                       "workload": "%s k=%d, synthetic %s shape (%d x %d, %d ratings), lr %g reg %g" % (model_name, k, shape, U, I, nnz, lr, reg),
                       "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
@@ -112,3 +114,5 @@ if __name__ == "__main__":
         run("C3", "bpr", "ml-20m", 128, 0.01, 0.01, a.steps, a.warmup)          # bpr-test.properties
     if a.only in ("", "c4"):
         run("C4", "pmf", "netflix", 128, 0.01, 0.08, a.steps, a.warmup)         # pmf-test.properties
+    if a.only == "n3":
+        run("N3", "ranksgd", "ml-20m", 10, 0.01, 0.0, a.steps, a.warmup)        # ranksgd-test.properties
