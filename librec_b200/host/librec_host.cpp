@@ -1,6 +1,8 @@
 // Host-side mirror of the reference's recommender plugin interface; see librec_host.hpp.
 #include "librec_host.hpp"
 #include <sys/stat.h>
+#include <dirent.h>
+#include <deque>
 #include <unordered_map>
 #include <string_view>
 
@@ -425,27 +427,68 @@ inline bool is_blank_line(const char* b, const char* e) {       // String.trim()
 }
 }  // namespace
 
+// Files.walkFileTree (TextDataConvertor.java:157-169): a path that is a directory contributes every regular file below it.
+// The JDK visits a directory in the order the file system lists it; here the listing is sorted by name so that inner ids
+// (first-seen order) do not depend on the file system.
+static void collect_files(const std::string& path, std::vector<std::string>& out) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0) throw LibrecException("TextDataConvertor: cannot read " + path);
+    if (!S_ISDIR(st.st_mode)) { out.push_back(path); return; }
+    DIR* d = opendir(path.c_str());
+    if (!d) throw LibrecException("TextDataConvertor: cannot list " + path);
+    std::vector<std::string> names;
+    while (struct dirent* e = readdir(d)) {
+        const std::string n = e->d_name;
+        if (n != "." && n != "..") names.push_back(n);
+    }
+    closedir(d);
+    std::sort(names.begin(), names.end());
+    for (const std::string& n : names) collect_files(path + "/" + n, out);
+}
+
 void TextDataModel::buildConvert() {
     const std::string dir = conf.get("dfs.data.dir", "");
-    const std::string path = (dir.empty() ? std::string() : dir + "/") + conf.get("data.input.path", "");
     const std::string fmt = conf.get("data.column.format", "UIR");
     const double binThold = conf.getDouble("data.convert.binarize.threshold", -1.0);
     const size_t nfields = (fmt == "UIRT" || fmt == "uirt") ? 4 : 3;
-    log.push_back("Dataset: [" + path + "]");
+    // data.input.path: ':'-separated, each entry relative to dfs.data.dir, file or directory (TextDataModel.java:58-64)
+    std::vector<std::string> files;
+    std::string shown;
+    {
+        std::string all = conf.get("data.input.path", "");
+        size_t b = all.find_first_not_of(" \t\r\n"), e = all.find_last_not_of(" \t\r\n");
+        all = b == std::string::npos ? std::string() : all.substr(b, e - b + 1);
+        size_t from = 0;
+        for (;;) {
+            const size_t c = all.find(':', from);
+            std::string one = all.substr(from, c == std::string::npos ? std::string::npos : c - from);
+            const size_t ob = one.find_first_not_of(" \t");
+            one = ob == std::string::npos ? std::string() : one.substr(ob, one.find_last_not_of(" \t") - ob + 1);
+            const std::string full = (dir.empty() ? std::string() : dir + "/") + one;
+            shown += (shown.empty() ? "" : ", ") + full;
+            collect_files(full, files);
+            if (c == std::string::npos) break;
+            from = c + 1;
+        }
+    }
+    log.push_back("Dataset: [" + shown + "]");
+    std::deque<std::string> bufs;                  // ids are views into these buffers
+    std::unordered_map<std::string_view, int32_t, SvHash> umap, imap;
+    std::vector<std::string_view> uview, iview;
+    std::vector<uint64_t> keys;          // (user << 32 | item), line order
+    std::vector<double> rates;
+    for (const std::string& path : files) {
     FILE* fp = fopen(path.c_str(), "rb");
     if (!fp) throw LibrecException("TextDataConvertor: cannot read " + path);
-    std::string buf;
+    bufs.emplace_back();
+    std::string& buf = bufs.back();
     {
         char tmp[1 << 16];
         size_t got;
         while ((got = fread(tmp, 1, sizeof tmp, fp)) > 0) buf.append(tmp, got);
         fclose(fp);
     }
-    // pass 1: one (user, item, rating) per line, inner ids in first-seen order; ids are views into `buf`
-    std::unordered_map<std::string_view, int32_t, SvHash> umap, imap;
-    std::vector<std::string_view> uview, iview;
-    std::vector<uint64_t> keys;          // (user << 32 | item), line order
-    std::vector<double> rates;
+    // pass 1: one (user, item, rating) per line, inner ids in first-seen order; the first blank line ends THIS file
     const char* p = buf.data();
     const char* const end = p + buf.size();
     while (p < end) {
@@ -482,6 +525,7 @@ void TextDataModel::buildConvert() {
         rates.push_back(r);
         p = eol ? eol + 1 : end;
     }
+    }   // files
     const int32_t U = (int32_t)umap.size(), I = (int32_t)imap.size();
     // pass 2: order by (user, item, line); the first entry of every (user, item) run is the earliest line -> it wins
     const size_t n = keys.size();

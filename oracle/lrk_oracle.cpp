@@ -25,6 +25,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <dirent.h>
+#include <sys/stat.h>
 #include <string>
 #include <vector>
 #include <unordered_map>
@@ -208,33 +210,68 @@ static bool is_blank(const std::string& s) {
     return true;
 }
 
-LRO_API void* lro_csr_load_text(const char* path, double bin_thold) {
-    FILE* fp = fopen(path, "rb");
-    if (!fp) return nullptr;
+// data/convertor/TextDataConvertor.java:142-200 with data/model/TextDataModel.java:58-64: `paths` is the ':'-separated
+// data.input.path (already prefixed with dfs.data.dir); a directory contributes every file below it (Files.walkFileTree;
+// the listing is sorted by name here, the JDK takes the file system's order); `fmt` "UIRT" requires a 4th (date) column,
+// which the preference matrix ignores; the first blank line ends the CURRENT file only.
+static void lro_collect_files(const std::string& path, std::vector<std::string>& out) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0) return;
+    if (!S_ISDIR(st.st_mode)) { out.push_back(path); return; }
+    DIR* d = opendir(path.c_str());
+    if (!d) return;
+    std::vector<std::string> names;
+    while (struct dirent* e = readdir(d)) {
+        const std::string n = e->d_name;
+        if (n != "." && n != "..") names.push_back(n);
+    }
+    closedir(d);
+    std::sort(names.begin(), names.end());
+    for (const std::string& n : names) lro_collect_files(path + "/" + n, out);
+}
+
+LRO_API void* lro_csr_load_paths(const char* paths, const char* fmt, double bin_thold) {
+    std::vector<std::string> files;
+    {
+        const std::string all(paths);
+        size_t from = 0;
+        for (;;) {
+            const size_t c = all.find(':', from);
+            lro_collect_files(all.substr(from, c == std::string::npos ? std::string::npos : c - from), files);
+            if (c == std::string::npos) break;
+            from = c + 1;
+        }
+    }
+    if (files.empty()) return nullptr;
+    const size_t need = (fmt && (strcmp(fmt, "UIRT") == 0 || strcmp(fmt, "uirt") == 0)) ? 4 : 3;
     std::unordered_map<std::string, int32_t> umap, imap;
     std::vector<int32_t> us, is;
     std::vector<double> rs;
     LroCsr* m = new LroCsr();
     std::vector<std::string> f;
     std::string line;
-    char buf[1 << 16];
-    while (fgets(buf, sizeof buf, fp)) {
-        line.assign(buf);
-        while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
-        if (is_blank(line)) break;
-        split_fields(line, "\t;, ", f);
-        if (f.size() < 3) continue;
-        auto iu = umap.find(f[0]);
-        int32_t u;
-        if (iu == umap.end()) { u = (int32_t)umap.size(); umap.emplace(f[0], u); m->user_ids.push_back(f[0]); }
-        else u = iu->second;
-        auto ii = imap.find(f[1]);
-        int32_t i;
-        if (ii == imap.end()) { i = (int32_t)imap.size(); imap.emplace(f[1], i); m->item_ids.push_back(f[1]); }
-        else i = ii->second;
-        us.push_back(u); is.push_back(i); rs.push_back(strtod(f[2].c_str(), nullptr));
+    static char buf[1 << 16];
+    for (const std::string& path : files) {
+        FILE* fp = fopen(path.c_str(), "rb");
+        if (!fp) { delete m; return nullptr; }
+        while (fgets(buf, sizeof buf, fp)) {
+            line.assign(buf);
+            while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
+            if (is_blank(line)) break;
+            split_fields(line, "\t;, ", f);
+            if (f.size() < need) continue;
+            auto iu = umap.find(f[0]);
+            int32_t u;
+            if (iu == umap.end()) { u = (int32_t)umap.size(); umap.emplace(f[0], u); m->user_ids.push_back(f[0]); }
+            else u = iu->second;
+            auto ii = imap.find(f[1]);
+            int32_t i;
+            if (ii == imap.end()) { i = (int32_t)imap.size(); imap.emplace(f[1], i); m->item_ids.push_back(f[1]); }
+            else i = ii->second;
+            us.push_back(u); is.push_back(i); rs.push_back(strtod(f[2].c_str(), nullptr));
+        }
+        fclose(fp);
     }
-    fclose(fp);
     m->U = (int32_t)umap.size(); m->I = (int32_t)imap.size();
     // earliest line wins: stable sort by (u,i), keep first of each run
     const size_t n = us.size();
@@ -256,6 +293,7 @@ LRO_API void* lro_csr_load_text(const char* path, double bin_thold) {
     for (int32_t u = 0; u < m->U; ++u) m->rowptr[u + 1] += m->rowptr[u];
     return m;
 }
+LRO_API void* lro_csr_load_text(const char* path, double bin_thold) { return lro_csr_load_paths(path, "UIR", bin_thold); }
 LRO_API void lro_csr_dims(void* h, int32_t* U, int32_t* I, int64_t* nnz) {
     LroCsr* m = (LroCsr*)h; *U = m->U; *I = m->I; *nnz = (int64_t)m->col.size();
 }

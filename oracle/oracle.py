@@ -60,6 +60,8 @@ def lib():
     L.lro_float_promote.argtypes = [C.c_char_p]
     L.lro_csr_load_text.restype = C.c_void_p
     L.lro_csr_load_text.argtypes = [C.c_char_p, C.c_double]
+    L.lro_csr_load_paths.restype = C.c_void_p
+    L.lro_csr_load_paths.argtypes = [C.c_char_p, C.c_char_p, C.c_double]
     L.lro_csr_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     L.lro_csr_copy.argtypes = [C.c_void_p, _i64p, _i32p, _f64p]
     L.lro_csr_outer_id.restype = C.c_int64
@@ -133,9 +135,10 @@ class Csr:
         return Csr(self.U, self.I, np.cumsum(rowptr), self.col[mask], self.val[mask])
 
 
-def load_text(path, bin_thold=-1.0):
+def load_text(path, bin_thold=-1.0, column_format="UIR"):
+    """path: file, directory, or ':'-separated list of them (data.input.path, already prefixed with dfs.data.dir)"""
     L = lib()
-    h = L.lro_csr_load_text(path.encode(), float(bin_thold))
+    h = L.lro_csr_load_paths(path.encode(), column_format.encode(), float(bin_thold))
     if not h:
         raise FileNotFoundError(path)
     U, I, n = C.c_int32(), C.c_int32(), C.c_int64()

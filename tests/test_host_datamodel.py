@@ -40,6 +40,26 @@ def test_loader_matches_reference_fixture(O, tmp_path):
     assert full.nnz == 13
 
 
+def test_loader_reference_fixtures_uirt_csv_and_directory(O):
+    """TextDataModelTestCase.java:84,101,118 through the native loader: UIRT column format, a directory with
+    sub-directories (Files.walkFileTree), mixed separators, ':'-separated data.input.path -- same matrices as the oracle"""
+    from librec_b200.host.binding import TextDataModel
+    g = os.path.join(ROOT, "tests", "golden", "datamodeltest")
+    cases = [("matrix4by4-date.txt", "UIRT", 13), ("testCSV.txt", "UIR", 13), ("test-convert-dir", "UIR", 26),
+             ("testCSV.txt:test-convert-dir/subdir1", "UIR", 26)]
+    for rel, fmt, n in cases:
+        dm = TextDataModel({"dfs.data.dir": g, "data.input.path": rel, "data.column.format": fmt, "rec.random.seed": 1})
+        full = O.load_text(":".join(os.path.join(g, r) for r in rel.split(":")), column_format=fmt)
+        U, I, rowptr, col, val = dm.matrix("preference")
+        assert full.nnz == n and (U, I) == (full.U, full.I)
+        assert np.array_equal(rowptr, full.rowptr) and np.array_equal(col, full.col) and np.array_equal(val, full.val)
+        tU, tI, trp, tc, tv = dm.matrix("train")
+        eU, eI, erp, ec, ev = dm.matrix("test")
+        assert trp[-1] + erp[-1] == n                                      # getDataSize(dataModel) of the reference test
+    with pytest.raises(Exception):
+        TextDataModel({"dfs.data.dir": g, "data.input.path": "no-such-file.txt"})
+
+
 def test_loader_quirks(O, tmp_path):
     lines = [
         "u9 i7 4.0\n",            # raw string ids, first-seen order

@@ -72,6 +72,20 @@ def test_loader_matrix4by4_has_13_entries(O):
     assert m.val.tolist() == [float(v) for v in range(1, 14)]
 
 
+def test_loader_reference_fixtures_uirt_csv_and_directory(O):
+    """the other expectations of the reference's loader test, on its own fixture files (copied under tests/golden/):
+    data/model/TextDataModelTestCase.java:84 (UIRT, 13), :101 (directory with sub-directories, 26), :118 (CSV, 13)"""
+    g = os.path.join(GOLDEN, "datamodeltest")
+    m = O.load_text(os.path.join(g, "matrix4by4-date.txt"), column_format="UIRT")
+    assert (m.U, m.I, m.nnz) == (4, 4, 13)
+    c = O.load_text(os.path.join(g, "testCSV.txt"))                       # ',', ' ' and tab mixed in one file
+    assert (c.U, c.I, c.nnz) == (4, 4, 13)
+    d = O.load_text(os.path.join(g, "test-convert-dir"))                  # 3 files, one of them twice -> duplicates collapse
+    assert d.nnz == 26
+    two = O.load_text(os.path.join(g, "testCSV.txt") + ":" + os.path.join(g, "test-convert-dir", "subdir1"))
+    assert two.nnz == 26                                                  # data.input.path is ':'-separated (TextDataModel.java:60)
+
+
 def test_loader_duplicate_keeps_earliest_and_blank_line_stops(O, tmp_path):
     p = tmp_path / "r.txt"
     p.write_text("a x 1\nb y 2\na x 5\nb,x;3\n\nc z 9\n")
