@@ -31,6 +31,10 @@ def load():
     L.lrh_datamodel_build.restype = C.c_void_p
     L.lrh_datamodel_build.argtypes = [C.c_char_p]
     L.lrh_datamodel_destroy.argtypes = [C.c_void_p]
+    L.lrh_datamodel_next_fold.argtypes = [C.c_void_p]
+    L.lrh_datamodel_next_fold.restype = C.c_int
+    L.lrh_datamodel_num_folds.argtypes = [C.c_void_p]
+    L.lrh_datamodel_num_folds.restype = C.c_int
     L.lrh_datamodel_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     L.lrh_datamodel_copy.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
     L.lrh_datamodel_raw_id.restype = C.c_char_p
@@ -56,8 +60,9 @@ class LibrecException(Exception):
 
 
 class TextDataModel:
-    """data/model/TextDataModel.java: properties (dfs.data.dir, data.input.path, data.convert.binarize.threshold,
-    data.splitter.trainset.ratio, rec.random.seed) -> preference / train / test as flat CSR"""
+    """data/model/TextDataModel.java: properties (dfs.data.dir, data.input.path, data.column.format,
+    data.convert.binarize.threshold, data.model.splitter = ratio | kcv | loocv | givenn with their keys, rec.random.seed)
+    -> preference / train / test as flat CSR; next_fold() walks the folds (one for everything but kcv)"""
 
     def __init__(self, properties):
         text = properties if isinstance(properties, str) else "\n".join("%s=%s" % kv for kv in properties.items())
@@ -74,6 +79,17 @@ class TextDataModel:
         rowptr = np.zeros(U.value + 1, np.int64); col = np.zeros(n.value, np.int32); val = np.zeros(n.value, np.float64)
         self._L.lrh_datamodel_copy(self._h, w, rowptr.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p))
         return U.value, I.value, rowptr, col, val
+
+    def next_fold(self):
+        """AbstractDataModel.hasNextFold(): True = matrix('train') / matrix('test') now hold the next fold"""
+        r = self._L.lrh_datamodel_next_fold(self._h)
+        if r < 0:
+            raise LibrecException(self._L.lrh_last_error().decode())
+        return bool(r)
+
+    @property
+    def num_folds(self):
+        return self._L.lrh_datamodel_num_folds(self._h)
 
     def raw_id(self, is_item, inner):
         return self._L.lrh_datamodel_raw_id(self._h, int(is_item), inner).decode()

@@ -551,32 +551,135 @@ void TextDataModel::buildConvert() {
     log.push_back("user number: " + std::to_string(U) + ",\t item number is: " + std::to_string(I));
 }
 
-void TextDataModel::buildSplitter() {
-    const std::string splitter = conf.get("data.model.splitter", "ratio");
-    const std::string by = conf.get("data.splitter.ratio", "rating");
-    if (!(splitter == "ratio" || splitter == "net.librec.data.splitter.RatioDataSplitter") || by != "rating")
-        throw LibrecException("only data.model.splitter=ratio with data.splitter.ratio=rating is implemented");
-    const double ratio = conf.getDouble("data.splitter.trainset.ratio", 0.8);
+// (train, test) from a per-entry flag; entries whose value is exactly 0.0 vanish from both (reshape())
+static void two_way(const SequentialAccessSparseMatrix& pref, const std::vector<uint8_t>& isTrain,
+                    SequentialAccessSparseMatrix& train, SequentialAccessSparseMatrix& test) {
     auto start = [&](SequentialAccessSparseMatrix& m) {
         m = SequentialAccessSparseMatrix();
-        m.numRows = preference.numRows; m.numCols = preference.numCols;
-        m.rowptr.assign((size_t)preference.numRows + 1, 0);
+        m.numRows = pref.numRows; m.numCols = pref.numCols;
+        m.rowptr.assign((size_t)pref.numRows + 1, 0);
     };
     start(train); start(test);
-    for (int u = 0; u < preference.numRows; ++u) {
-        for (int64_t e = preference.rowptr[(size_t)u]; e < preference.rowptr[(size_t)u + 1]; ++e) {
-            const double rdm = Randoms::uniform();                                           // RatioDataSplitter.java:143-150
-            const double v = preference.val[(size_t)e];
-            if (v == 0.0) continue;                                                          // reshape() drops exact zeros
-            SequentialAccessSparseMatrix& dst = rdm < ratio ? train : test;
-            dst.col.push_back(preference.col[(size_t)e]); dst.val.push_back(v);
+    for (int u = 0; u < pref.numRows; ++u) {
+        for (int64_t e = pref.rowptr[(size_t)u]; e < pref.rowptr[(size_t)u + 1]; ++e) {
+            const double v = pref.val[(size_t)e];
+            if (v == 0.0) continue;
+            SequentialAccessSparseMatrix& dst = isTrain[(size_t)e] ? train : test;
+            dst.col.push_back(pref.col[(size_t)e]); dst.val.push_back(v);
             dst.rowptr[(size_t)u + 1]++;
         }
     }
-    for (int u = 0; u < preference.numRows; ++u) {
+    for (int u = 0; u < pref.numRows; ++u) {
         train.rowptr[(size_t)u + 1] += train.rowptr[(size_t)u];
         test.rowptr[(size_t)u + 1] += test.rowptr[(size_t)u];
     }
+}
+// column walk of the CSR matrix (SequentialAccessSparseMatrix.column(j): rows ascending): csc[colptr[j] + t] = entry index
+static void csc_order(const SequentialAccessSparseMatrix& m, std::vector<int64_t>& colptr, std::vector<int64_t>& csc) {
+    const size_t nnz = m.col.size();
+    colptr.assign((size_t)m.numCols + 1, 0);
+    for (size_t e = 0; e < nnz; ++e) colptr[(size_t)m.col[e] + 1]++;
+    for (int j = 0; j < m.numCols; ++j) colptr[(size_t)j + 1] += colptr[(size_t)j];
+    csc.assign(nnz, 0);
+    std::vector<int64_t> fill(colptr.begin(), colptr.end() - 1);
+    for (int u = 0; u < m.numRows; ++u)
+        for (int64_t e = m.rowptr[(size_t)u]; e < m.rowptr[(size_t)u + 1]; ++e) csc[(size_t)fill[(size_t)m.col[(size_t)e]]++] = e;
+}
+// Randoms.nextIntArray(length, range): math/algorithm/Randoms.java:576-604 (nextInt :520-535)
+static void next_int_array(int length, int range, std::vector<int>& out) {
+    out.clear();
+    if (range == length) { for (int i = 0; i < length; ++i) out.push_back(i); return; }
+    while ((int)out.size() < length) {
+        const int next = Randoms::uniform(range);
+        if (std::find(out.begin(), out.end(), next) == out.end()) out.push_back(next);
+    }
+    std::sort(out.begin(), out.end());
+}
+
+void TextDataModel::buildSplitter() {
+    std::string splitter = conf.get("data.model.splitter", "ratio");
+    std::transform(splitter.begin(), splitter.end(), splitter.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    auto lower = [](std::string v) { std::transform(v.begin(), v.end(), v.begin(), [](unsigned char c) { return (char)std::tolower(c); }); return v; };
+    const size_t nnz = preference.col.size();
+    std::vector<uint8_t> isTrain(nnz, 1);
+    numFolds = 1; foldCursor = 0; assign.clear();
+    std::vector<int64_t> colptr, csc;
+    if (splitter == "ratio" || splitter == "net.librec.data.splitter.ratiodatasplitter") {
+        const std::string by = lower(conf.get("data.splitter.ratio", "rating"));
+        const double ratio = conf.getDouble("data.splitter.trainset.ratio", 0.8);
+        if (by == "rating" || by == "user") {                                                // RatioDataSplitter.java:136-156, 232-249
+            for (size_t e = 0; e < nnz; ++e) isTrain[e] = Randoms::uniform() < ratio;
+        } else if (by == "item") {                                                           // :315-334, column order
+            csc_order(preference, colptr, csc);
+            for (size_t t = 0; t < nnz; ++t) isTrain[(size_t)csc[t]] = Randoms::uniform() < ratio;
+        } else {
+            throw LibrecException("data.splitter.ratio=" + by + " is not implemented (rating, user, item are)");
+        }
+    } else if (splitter == "loocv" || splitter == "net.librec.data.splitter.loocvdatasplitter") {
+        const std::string by = lower(conf.get("data.splitter.loocv", "user"));
+        if (by == "user") {                                                                  // LOOCVDataSplitter.java:144-165
+            for (int u = 0; u < preference.numRows; ++u) {
+                const int64_t n = preference.rowptr[(size_t)u + 1] - preference.rowptr[(size_t)u];
+                if (n == 0) continue;
+                isTrain[(size_t)(preference.rowptr[(size_t)u] + (int64_t)((double)n * Randoms::uniform()))] = 0;
+            }
+        } else if (by == "item") {                                                           // :197-216
+            csc_order(preference, colptr, csc);
+            for (int j = 0; j < preference.numCols; ++j) {
+                const int64_t n = colptr[(size_t)j + 1] - colptr[(size_t)j];
+                if (n == 0) continue;
+                isTrain[(size_t)csc[(size_t)(colptr[(size_t)j] + (int64_t)((double)n * Randoms::uniform()))]] = 0;
+            }
+        } else {
+            throw LibrecException("data.splitter.loocv=" + by + " is not implemented (user, item are)");
+        }
+    } else if (splitter == "givenn" || splitter == "net.librec.data.splitter.givenndatasplitter") {
+        const std::string by = lower(conf.get("data.splitter.givenn", "user"));
+        const int given = (int)conf.getLong("data.splitter.givenn.n", 1);
+        if (by != "user" && by != "item") throw LibrecException("data.splitter.givenn=" + by + " is not implemented (user, item are)");
+        const bool byItem = by == "item";                                                    // GivenNDataSplitter.java:137-167, 217-245
+        if (byItem) csc_order(preference, colptr, csc);
+        std::vector<int> keep;
+        const int lines = byItem ? preference.numCols : preference.numRows;
+        for (int l = 0; given > 0 && l < lines; ++l) {
+            const int64_t b = byItem ? colptr[(size_t)l] : preference.rowptr[(size_t)l];
+            const int64_t n = (byItem ? colptr[(size_t)l + 1] : preference.rowptr[(size_t)l + 1]) - b;
+            if (n <= given) continue;
+            next_int_array(given, (int)n, keep);
+            size_t g = 0;
+            for (int64_t pos = 0; pos < n; ++pos) {
+                const int64_t e = byItem ? csc[(size_t)(b + pos)] : b + pos;
+                if (g < keep.size() && keep[g] == pos) ++g; else isTrain[(size_t)e] = 0;
+            }
+        }
+    } else if (splitter == "kcv" || splitter == "net.librec.data.splitter.kcvdatasplitter") {
+        const int64_t kFold = conf.getLong("data.splitter.cv.number", 5);                    // KCVDataSplitter.java:84-123,133-138
+        if (kFold <= 0 || nnz == 0) throw LibrecException("data.splitter.cv.number must be positive and the data non-empty");
+        const int64_t numFold = kFold > (int64_t)nnz ? (int64_t)nnz : kFold;
+        const double indv = ((double)nnz + 0.0) / (double)numFold;
+        std::vector<std::pair<int32_t, double>> rdm(nnz);
+        for (size_t i = 0; i < nnz; ++i) rdm[i] = {(int32_t)((double)i / indv) + 1, Randoms::uniform()};
+        std::stable_sort(rdm.begin(), rdm.end(), [](const std::pair<int32_t, double>& a, const std::pair<int32_t, double>& b) { return a.second > b.second; });
+        assign.resize(nnz);
+        for (size_t i = 0; i < nnz; ++i) assign[i] = rdm[i].first;
+        numFolds = (int)numFold;
+        train = SequentialAccessSparseMatrix(); test = SequentialAccessSparseMatrix();
+        return;                                                                              // the folds are cut by hasNextFold()
+    } else {
+        throw LibrecException("data.model.splitter=" + splitter + " is not implemented (ratio, kcv, loocv, givenn are)");
+    }
+    two_way(preference, isTrain, train, test);
+}
+
+bool TextDataModel::hasNextFold() {
+    if (foldCursor >= numFolds) return false;
+    ++foldCursor;
+    if (!assign.empty()) {
+        std::vector<uint8_t> isTrain(assign.size());
+        for (size_t e = 0; e < assign.size(); ++e) isTrain[e] = assign[e] != foldCursor;
+        two_way(preference, isTrain, train, test);
+    }
+    return true;
 }
 
 void TextDataModel::buildDataModel() {
@@ -589,10 +692,54 @@ RecommenderJob::RecommenderJob(const Configuration& c) : conf(c) {
     if (conf.has("rec.random.seed")) Randoms::seed(conf.getLong("rec.random.seed", 1));      // RecommenderJob.java:74-77
 }
 void RecommenderJob::setData(const SequentialAccessSparseMatrix& tr, const SequentialAccessSparseMatrix& te) { train = tr; test = te; }
+// RecommenderJob.java:121-133 with a k-fold splitter: `while (dataModel.hasNextFold())` trains and evaluates once per fold on
+// the SAME recommender instance, collects every evaluator value (collectCVResults :335-343) and prints the averages
+// (printCVAverageResult :311-326); the recommended list that is saved is the last fold's.
+void RecommenderJob::runCrossValidation() {
+    recommender = newRecommender(conf.get("rec.recommender.class"));
+    const bool ranking = conf.getBoolean("rec.recommender.isranking");
+    std::map<std::string, std::vector<double>> cv;
+    std::vector<std::string> lines(dataModel->log.begin(), dataModel->log.end());
+    size_t logSeen = 0;
+    while (dataModel->hasNextFold()) {
+        dataModel->nextFold();
+        train = dataModel->train; test = dataModel->test;
+        recommender->train(conf, train, test);
+        evaluatedMap.clear();
+        if (conf.getBoolean("rec.eval.enable", true)) {
+            if (ranking && recommender->rankingTopN() <= 64) recommendedList = recommender->recommendRankAndEvaluate(test, &evaluatedMap);
+            else recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
+            if (!ranking) {
+                evaluatedMap["RMSE"] = evaluateRMSE(test, recommendedList);
+                evaluatedMap["MAE"] = evaluateMAE(test, recommendedList);
+            }
+        } else {
+            recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
+        }
+        const std::vector<std::string>& rl = recommender->log();                              // grows over the folds: take the new lines
+        lines.insert(lines.end(), rl.begin() + (std::ptrdiff_t)logSeen, rl.end());
+        logSeen = rl.size();
+        for (const auto& kv : evaluatedMap) {
+            lines.push_back("Evaluator value:" + kv.first + " is " + java_double_to_string(kv.second));
+            cv[kv.first].push_back(kv.second);
+        }
+    }
+    lines.push_back("Average Evaluation Result of Cross Validation:");
+    for (const auto& kv : cv) {
+        double sum = 0.0;
+        for (double v : kv.second) sum += v;
+        const double avg = sum / (double)kv.second.size();
+        evaluatedMap[kv.first] = avg;                                                         // metric() then reports the average
+        lines.push_back("Evaluator value:" + kv.first + " is " + java_double_to_string(avg));
+    }
+    log = lines;
+}
+
 void RecommenderJob::runJob() {
     if (train.numRows == 0 && conf.has("data.input.path")) {                                 // RecommenderJob.java:121-128
         dataModel.reset(new TextDataModel(conf));
         dataModel->buildDataModel();
+        if (dataModel->numFolds > 1) { runCrossValidation(); return; }
         train = dataModel->train; test = dataModel->test;
     }
     recommender = newRecommender(conf.get("rec.recommender.class"));

@@ -217,9 +217,19 @@ struct TextDataModel {
     explicit TextDataModel(const Configuration& conf) : conf(conf) {}
     void buildDataModel();                           // AbstractDataModel.java:92-117: convert, then split
     void buildConvert();                             // reads dfs.data.dir + "/" + data.input.path (a file)
-    void buildSplitter();                            // data.model.splitter=ratio, data.splitter.ratio=rating
+    // data.model.splitter = ratio (data.splitter.ratio = rating | user | item), kcv (data.splitter.cv.number), loocv
+    // (data.splitter.loocv = user | item), givenn (data.splitter.givenn = user | item, data.splitter.givenn.n); the date
+    // variants, ratio "valid"/"userfixed" and testset are not implemented (LibrecException)
+    void buildSplitter();
+    // AbstractDataModel.hasNextFold / nextFold over AbstractDataSplitter.nextFold (AbstractDataSplitter.java:104-128): one
+    // fold for every splitter but kcv, which yields data.splitter.cv.number folds (fold k's test set = entries assigned k)
+    bool hasNextFold();
+    void nextFold() {}
+    int foldsDone() const { return foldCursor; }
     Configuration conf;
     SequentialAccessSparseMatrix preference, train, test;
+    std::vector<int32_t> assign;                     // kcv: fold id (1..K) per stored entry, CSR order
+    int numFolds = 1, foldCursor = 0;
     std::vector<std::string> userIds, itemIds;       // inner id -> raw id (the BiMap inverses of DataFrame)
     std::vector<std::string> log;
 };
@@ -229,6 +239,7 @@ struct RecommenderJob {
     explicit RecommenderJob(const Configuration& conf);
     void setData(const SequentialAccessSparseMatrix& train, const SequentialAccessSparseMatrix& test);
     void runJob();                                   // builds the TextDataModel first when no data was set and data.input.path is
+    void runCrossValidation();                       // the fold loop of RecommenderJob.java:125-133 for data.model.splitter=kcv
     // job/RecommenderJob.java:281-306 + AbstractRecommender.java:213-235: "user,item,value\n" with raw ids,
     // values printed like String.valueOf(double); returns the path written ("" when there is nothing to write)
     std::string saveResult();

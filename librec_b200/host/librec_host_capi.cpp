@@ -114,6 +114,11 @@ LRH_API void* lrh_datamodel_build(const char* properties_text) {
     } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
 LRH_API void lrh_datamodel_destroy(void* h) { delete (DataModelBox*)h; }
+// AbstractDataModel.hasNextFold(): 1 = the train / test matrices now hold the next fold, 0 = no fold left
+LRH_API int lrh_datamodel_next_fold(void* h) {
+    try { return ((DataModelBox*)h)->dm->hasNextFold() ? 1 : 0; } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+LRH_API int lrh_datamodel_num_folds(void* h) { return ((DataModelBox*)h)->dm->numFolds; }
 static const SequentialAccessSparseMatrix& dm_matrix(void* h, int which) {
     TextDataModel* d = ((DataModelBox*)h)->dm.get();
     return which == 0 ? d->preference : (which == 1 ? d->train : d->test);

@@ -328,6 +328,103 @@ LRO_API void lro_split_ratio(int64_t nnz, const double* val, double ratio, uint8
 }
 
 // -------------------------------------------------------------------------------------
+// The other splitters of data/splitter/ (SURVEY.md 8f, row N2 widened).  All work on the stored entries of the
+// preference matrix in CSR order and consume the global java.util.Random exactly like the reference; the outputs are
+// per-entry assignments (the caller drops exact zeros afterwards, like reshape()).  The *date variants need the
+// datetime matrix and the three-way "valid" split a validation set: not restated.
+// -------------------------------------------------------------------------------------
+// entry order of a column walk (SequentialAccessSparseMatrix.column(j): rows ascending): csc[t] = CSR entry index
+static void lro_csc_order(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, std::vector<int64_t>& colptr,
+                          std::vector<int64_t>& csc) {
+    const int64_t nnz = rowptr[U];
+    colptr.assign((size_t)I + 1, 0);
+    for (int64_t e = 0; e < nnz; ++e) colptr[(size_t)col[e] + 1]++;
+    for (int32_t j = 0; j < I; ++j) colptr[(size_t)j + 1] += colptr[(size_t)j];
+    csc.assign((size_t)nnz, 0);
+    std::vector<int64_t> fill(colptr.begin(), colptr.end() - 1);
+    for (int32_t u = 0; u < U; ++u)
+        for (int64_t e = rowptr[u]; e < rowptr[u + 1]; ++e) csc[(size_t)fill[(size_t)col[e]]++] = e;
+}
+
+// RatioDataSplitter.getRatioByItem (RatioDataSplitter.java:315-334): one Randoms.uniform() per entry in COLUMN order;
+// getRatioByUser (:232-249) draws in row order and is identical to getRatioByRating (lro_split_ratio).
+LRO_API void lro_split_ratio_item(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, double ratio, uint8_t* is_train) {
+    std::vector<int64_t> colptr, csc;
+    lro_csc_order(U, I, rowptr, col, colptr, csc);
+    for (size_t t = 0; t < csc.size(); ++t) is_train[csc[t]] = lro_uniform() < ratio ? 1 : 0;
+}
+
+// KCVDataSplitter.splitData(kFold) (KCVDataSplitter.java:84-123): entry index -> fold key (int)(index / (numRates / numFold)) + 1,
+// paired with one Randoms.uniform() each, sorted DESCENDING by the random value (Lists.sortList(.., true), stable); the
+// entries in CSR order receive the keys in that sorted order.  fold_out[e] in 1..numFold; fold k's test set = {fold == k}.
+LRO_API void lro_split_kcv(int64_t nnz, int32_t k_fold, int32_t* fold_out) {
+    const int64_t num_fold = k_fold > nnz ? nnz : k_fold;
+    const double indv = ((double)nnz + 0.0) / (double)num_fold;
+    std::vector<std::pair<int32_t, double>> rdm((size_t)nnz);
+    for (int64_t i = 0; i < nnz; ++i) rdm[(size_t)i] = {(int32_t)((double)i / indv) + 1, lro_uniform()};
+    std::stable_sort(rdm.begin(), rdm.end(), [](const std::pair<int32_t, double>& a, const std::pair<int32_t, double>& b) { return a.second > b.second; });
+    for (int64_t i = 0; i < nnz; ++i) fold_out[i] = rdm[(size_t)i].first;
+}
+
+// LOOCVDataSplitter.getLOOByUser / getLOOByItems (LOOCVDataSplitter.java:144-165, 197-216): one entry per non-empty row
+// (column) at position (int)(n * Randoms.uniform()) goes to the test set.
+LRO_API void lro_split_loocv(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, int32_t by_item, uint8_t* is_train) {
+    const int64_t nnz = rowptr[U];
+    for (int64_t e = 0; e < nnz; ++e) is_train[e] = 1;
+    if (!by_item) {
+        for (int32_t u = 0; u < U; ++u) {
+            const int64_t n = rowptr[u + 1] - rowptr[u];
+            if (n == 0) continue;
+            is_train[rowptr[u] + (int64_t)((double)n * lro_uniform())] = 0;
+        }
+    } else {
+        std::vector<int64_t> colptr, csc;
+        lro_csc_order(U, I, rowptr, col, colptr, csc);
+        for (int32_t j = 0; j < I; ++j) {
+            const int64_t n = colptr[(size_t)j + 1] - colptr[(size_t)j];
+            if (n == 0) continue;
+            is_train[csc[(size_t)(colptr[(size_t)j] + (int64_t)((double)n * lro_uniform()))]] = 0;
+        }
+    }
+}
+
+// Randoms.nextIntArray(length, range) (math/algorithm/Randoms.java:576-604, nextInt :520-535): `length` distinct draws of
+// r.nextInt(range), repeats rejected, sorted ascending; the identity when range == length.
+static void lro_next_int_array(int32_t length, int32_t range, std::vector<int32_t>& out) {
+    out.clear();
+    if (range == length) { for (int32_t i = 0; i < length; ++i) out.push_back(i); return; }
+    while ((int32_t)out.size() < length) {
+        const int32_t next = lro_uniform_int(range);
+        if (std::find(out.begin(), out.end(), next) == out.end()) out.push_back(next);
+    }
+    std::sort(out.begin(), out.end());
+}
+
+// GivenNDataSplitter.getGivenNByUser / getGivenNByItem (GivenNDataSplitter.java:137-167, 217-245): a row (column) with more
+// than N entries keeps N random positions for training and sends the rest to the test set; one with at most N keeps all.
+LRO_API void lro_split_givenn(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, int32_t by_item, int32_t n_given,
+                              uint8_t* is_train) {
+    const int64_t nnz = rowptr[U];
+    for (int64_t e = 0; e < nnz; ++e) is_train[e] = 1;
+    if (n_given <= 0) return;
+    std::vector<int32_t> given;
+    std::vector<int64_t> colptr, csc;
+    if (by_item) lro_csc_order(U, I, rowptr, col, colptr, csc);
+    const int32_t lines = by_item ? I : U;
+    for (int32_t l = 0; l < lines; ++l) {
+        const int64_t b = by_item ? colptr[(size_t)l] : rowptr[l];
+        const int64_t n = (by_item ? colptr[(size_t)l + 1] : rowptr[l + 1]) - b;
+        if (n <= n_given) continue;
+        lro_next_int_array(n_given, (int32_t)n, given);
+        size_t g = 0;
+        for (int64_t pos = 0; pos < n; ++pos) {
+            const int64_t e = by_item ? csc[(size_t)(b + pos)] : b + pos;
+            if (g < given.size() && given[g] == pos) ++g; else is_train[e] = 0;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------
 // MatrixRecommender.setup: recommender/MatrixRecommender.java:88-128
 // globalMean = sum in CSR order / nnz (math/structure/RowSequentialAccessSparseMatrix.java:161-167);
 // minRate/maxRate from the rating set, minRate=0 if equal (:103-107).

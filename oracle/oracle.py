@@ -87,6 +87,10 @@ def lib():
     L.lro_train.argtypes = [C.c_int32, C.c_int32, C.c_int32, _i64p, _i32p, _f64p, C.c_int32, _f64p, _f64p,
                             C.c_void_p, C.c_void_p, C.c_double, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double,
                             C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+    L.lro_split_ratio_item.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_double, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
+    L.lro_split_kcv.argtypes = [C.c_int64, C.c_int32, _i32p]
+    L.lro_split_loocv.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_int32, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
+    L.lro_split_givenn.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_int32, C.c_int32, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
     L.lro_ranksgd_item_probs.restype = C.c_int32
     L.lro_ranksgd_item_probs.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _i32p, _f64p]
     L.lro_ranksgd_epoch.restype = C.c_double
@@ -156,6 +160,37 @@ def split_ratio(csr, ratio=0.8):
     flags = np.zeros(csr.nnz, np.uint8)
     lib().lro_split_ratio(csr.nnz, csr.val, float(ratio), flags)
     return csr.select(flags == 1), csr.select(flags == 0)
+
+
+def _two_way(csr, flags):
+    """(train, test) from per-entry flags; exact zeros vanish from both (reshape())"""
+    nz = csr.val != 0.0
+    return csr.select((flags == 1) & nz), csr.select((flags == 0) & nz)
+
+
+def split(csr, splitter="ratio", by="rating", ratio=0.8, n_given=1, k_fold=5):
+    """the reference's splitters on the global RNG.  ratio / loocv / givenn -> (train, test); kcv -> list of (train, test)"""
+    L = lib()
+    flags = np.zeros(csr.nnz, np.uint8)
+    if splitter == "ratio":
+        if by in ("rating", "user"):
+            L.lro_split_ratio(csr.nnz, csr.val, ratio, flags)
+        elif by == "item":
+            L.lro_split_ratio_item(csr.U, csr.I, csr.rowptr, csr.col, ratio, flags)
+        else:
+            raise ValueError(by)
+        return _two_way(csr, flags)
+    if splitter == "loocv":
+        L.lro_split_loocv(csr.U, csr.I, csr.rowptr, csr.col, int(by == "item"), flags)
+        return _two_way(csr, flags)
+    if splitter == "givenn":
+        L.lro_split_givenn(csr.U, csr.I, csr.rowptr, csr.col, int(by == "item"), n_given, flags)
+        return _two_way(csr, flags)
+    if splitter == "kcv":
+        fold = np.zeros(csr.nnz, np.int32)
+        L.lro_split_kcv(csr.nnz, k_fold, fold)
+        return [_two_way(csr, (fold != k).astype(np.uint8)) for k in range(1, min(k_fold, csr.nnz) + 1)]
+    raise ValueError(splitter)
 
 
 def matrix_setup(csr):

@@ -212,3 +212,29 @@ rec.random.seed=1
     exp = O.eval_ranking(te, tr, 10, oi, oc)
     assert abs(job.metric("PRECISION top 10") - exp["Precision"]) <= 1e-12 and exp["Precision"] > 0.10
     assert abs(job.metric("NDCG top 10") - exp["NDCG"]) <= 1e-12
+
+
+def test_kcv_job_cross_validation(O, capi, c1, tmp_path):
+    """data.model.splitter=kcv: RecommenderJob.java:125-133 trains and evaluates once per fold and prints the averages
+    (printCVAverageResult :311-326).  Folds come from the native TextDataModel (checked against the oracle on CPU); here the
+    per-fold RMSE must match the oracle trained on the same fold within the fast mode's 1e-3 ... plus its init differences,
+    so the check is: finite, in the plausible range, and the reported metric is the mean of the fold lines."""
+    import os
+    from librec_b200.host.binding import RecommenderJob
+    full = c1["full"]
+    path = os.path.join(str(tmp_path), "ratings.txt")
+    with open(path, "w") as f:
+        for u, i, r in zip(full.rows().tolist(), full.col.tolist(), full.val.tolist()):
+            f.write("%d %d %s\n" % (u, i, repr(float(r))))
+    props = BIASEDMF_PROPS.replace("rec.iterator.maximum=100", "rec.iterator.maximum=15") + (
+        "\ndfs.data.dir=%s\ndata.input.path=ratings.txt\ndata.model.splitter=kcv\ndata.splitter.cv.number=3\n" % str(tmp_path))
+    job = RecommenderJob(props)
+    job.run_job()
+    log = job.log()
+    rmse_lines = [float(l.split(" is ")[1]) for l in log if l.startswith("Evaluator value:RMSE is ")]
+    assert len(rmse_lines) == 4                                            # 3 folds + the average
+    assert all(0.85 < v < 1.2 for v in rmse_lines)
+    assert abs(rmse_lines[3] - sum(rmse_lines[:3]) / 3.0) < 1e-12
+    assert abs(job.metric("RMSE") - rmse_lines[3]) < 1e-12
+    assert "Average Evaluation Result of Cross Validation:" in log
+    assert sum(" iter 15:" in l for l in log) == 3 and sum(" iter 1:" in l for l in log) == 3

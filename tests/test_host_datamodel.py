@@ -107,3 +107,85 @@ def test_loader_errors(O, tmp_path):
     _write(os.path.join(str(tmp_path), "short.txt"), ["1 2\n"])
     with pytest.raises(LibrecException):
         TextDataModel({"dfs.data.dir": str(tmp_path), "data.input.path": "short.txt"})
+
+
+def _same(got, exp):
+    U, I, rowptr, col, val = got
+    return (U, I) == (exp.U, exp.I) and np.array_equal(rowptr, exp.rowptr) and np.array_equal(col, exp.col) and np.array_equal(val, exp.val)
+
+
+@pytest.mark.parametrize("splitter,key,by,extra,train_n,test_n", [
+    ("givenn", "data.splitter.givenn", "user", {"data.splitter.givenn.n": 1}, 4, 9),     # GivenNDataSplitterTestCase.java:70-71
+    ("givenn", "data.splitter.givenn", "item", {"data.splitter.givenn.n": 1}, 4, 9),     # :90-91
+    ("loocv", "data.splitter.loocv", "user", {}, 9, 4),                                  # LOOCVDataSplitterTestCase.java:68-69
+    ("loocv", "data.splitter.loocv", "item", {}, 9, 4),                                  # :86-87
+])
+def test_splitters_meet_the_reference_test_expectations(O, splitter, key, by, extra, train_n, test_n):
+    """the sizes the reference's own splitter tests assert on matrix4by4.txt, and entry-for-entry the oracle's split on the
+    same java.util.Random stream"""
+    from librec_b200.host.binding import TextDataModel
+    g = os.path.join(ROOT, "tests", "golden")
+    for seed in (1, 2, 3):
+        props = {"dfs.data.dir": g, "data.input.path": "matrix4by4.txt", "rec.random.seed": seed, "data.model.splitter": splitter, key: by}
+        props.update(extra)
+        dm = TextDataModel(props)
+        full = O.load_text(os.path.join(g, "matrix4by4.txt"))
+        O.lib().lro_seed(seed)
+        etr, ete = O.split(full, splitter, by, n_given=extra.get("data.splitter.givenn.n", 1))
+        assert (etr.nnz, ete.nnz) == (train_n, test_n)
+        assert dm.num_folds == 1 and _same(dm.matrix("train"), etr) and _same(dm.matrix("test"), ete)
+        assert dm.next_fold() and not dm.next_fold()
+
+
+def test_kcv_folds_meet_the_reference_test_expectation(O):
+    """KCVDataSplitterTestCase.java:63-70: matrix4by4A.txt, 6 folds -> every fold 10 train / 2 test entries"""
+    from librec_b200.host.binding import TextDataModel
+    g = os.path.join(ROOT, "tests", "golden", "datamodeltest")
+    dm = TextDataModel({"dfs.data.dir": g, "data.input.path": "matrix4by4A.txt", "rec.random.seed": 1,
+                        "data.model.splitter": "kcv", "data.splitter.cv.number": 6})
+    full = O.load_text(os.path.join(g, "matrix4by4A.txt"))
+    O.lib().lro_seed(1)
+    folds = O.split(full, "kcv", k_fold=6)
+    assert dm.num_folds == 6 and len(folds) == 6
+    seen = np.zeros(full.nnz, np.int64)
+    for etr, ete in folds:
+        assert dm.next_fold()
+        assert (etr.nnz, ete.nnz) == (10, 2)
+        assert _same(dm.matrix("train"), etr) and _same(dm.matrix("test"), ete)
+        U, I, rp, col, val = dm.matrix("test")
+        rows = np.repeat(np.arange(U), np.diff(rp))
+        for r, c in zip(rows, col):
+            seen[np.flatnonzero((full.rows() == r) & (full.col == c))[0]] += 1
+    assert not dm.next_fold()
+    assert np.array_equal(seen, np.ones(full.nnz, np.int64))            # every entry is tested exactly once
+
+
+@pytest.mark.parametrize("by", ["user", "item"])
+def test_ratio_by_user_and_item_on_a_large_matrix(O, c1, tmp_path, by):
+    """RatioDataSplitterTestCase.java:93,153: |actual train ratio - 0.8| <= 0.01; and the oracle's split entry for entry"""
+    from librec_b200.host.binding import TextDataModel
+    full = c1["full"]
+    path = os.path.join(str(tmp_path), "r.txt")
+    with open(path, "w") as f:
+        for u, i, r in zip(full.rows().tolist(), full.col.tolist(), full.val.tolist()):
+            f.write("%d %d %s\n" % (u, i, repr(float(r))))
+    dm = TextDataModel({"dfs.data.dir": str(tmp_path), "data.input.path": "r.txt", "rec.random.seed": 5,
+                        "data.model.splitter": "ratio", "data.splitter.ratio": by, "data.splitter.trainset.ratio": 0.8})
+    loaded = O.load_text(path)
+    O.lib().lro_seed(5)
+    etr, ete = O.split(loaded, "ratio", by, ratio=0.8)
+    assert _same(dm.matrix("train"), etr) and _same(dm.matrix("test"), ete)
+    assert abs(etr.nnz / float(loaded.nnz) - 0.8) <= 0.01
+
+
+def test_unimplemented_splitters_fail_loudly(tmp_path):
+    from librec_b200.host.binding import TextDataModel, LibrecException
+    p = tmp_path / "r.txt"
+    p.write_text("a x 1\nb y 2\n")
+    for extra in ({"data.model.splitter": "testset"}, {"data.model.splitter": "ratio", "data.splitter.ratio": "ratingdate"},
+                  {"data.model.splitter": "loocv", "data.splitter.loocv": "userdate"}):
+        props = {"dfs.data.dir": str(tmp_path), "data.input.path": "r.txt"}
+        props.update(extra)
+        with pytest.raises(LibrecException) as e:
+            TextDataModel(props)
+        assert "not implemented" in str(e.value)

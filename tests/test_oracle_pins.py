@@ -110,6 +110,35 @@ def test_splitter_ratio_bound(O, c1):
     assert int((flags == 1).sum()) == tr.nnz
 
 
+def test_other_splitters_meet_the_reference_test_expectations(O, c1):
+    """sizes asserted by the reference's splitter tests on its 4x4 fixtures: GivenNDataSplitterTestCase.java:70-71,90-91
+    (N=1: 4 train / 9 test), LOOCVDataSplitterTestCase.java:68-69,86-87 (9 / 4), KCVDataSplitterTestCase.java:68-69
+    (matrix4by4A.txt, 6 folds: 10 / 2 each), RatioDataSplitterTestCase.java:93,153 (user / item ratio within 0.01 of 0.8)"""
+    m = O.load_text(os.path.join(GOLDEN, "matrix4by4.txt"))
+    for seed in range(1, 6):
+        for by in ("user", "item"):
+            O.lib().lro_seed(seed)
+            tr, te = O.split(m, "givenn", by, n_given=1)
+            assert (tr.nnz, te.nnz) == (4, 9)
+            if by == "user":
+                assert np.diff(tr.rowptr).tolist() == [1, 1, 1, 1]           # exactly N given entries per user
+            O.lib().lro_seed(seed)
+            tr, te = O.split(m, "loocv", by)
+            assert (tr.nnz, te.nnz) == (9, 4)
+    a = O.load_text(os.path.join(GOLDEN, "datamodeltest", "matrix4by4A.txt"))
+    O.lib().lro_seed(1)
+    folds = O.split(a, "kcv", k_fold=6)
+    assert [(x.nnz, y.nnz) for x, y in folds] == [(10, 2)] * 6
+    full = c1["full"]
+    for by in ("user", "item"):
+        O.lib().lro_seed(1)
+        tr, te = O.split(full, "ratio", by, ratio=0.8)
+        assert abs(tr.nnz / float(full.nnz) - 0.8) <= 0.01 and tr.nnz + te.nnz == full.nnz
+    O.lib().lro_seed(1)
+    tr_u, _ = O.split(full, "ratio", "user", ratio=0.8)
+    assert np.array_equal(tr_u.col, c1["train"].col)                           # getRatioByUser == getRatioByRating draw for draw
+
+
 def test_matrix_setup(O, c1):
     mu, mn, mx = O.matrix_setup(c1["train"])
     assert mu == c1["pins"]["global_mean"] and (mn, mx) == (1.0, 5.0)
