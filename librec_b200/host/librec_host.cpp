@@ -477,6 +477,7 @@ void TextDataModel::buildConvert() {
     std::vector<std::string_view> uview, iview;
     std::vector<uint64_t> keys;          // (user << 32 | item), line order
     std::vector<double> rates;
+    std::vector<int64_t> dates;
     for (const std::string& path : files) {
     FILE* fp = fopen(path.c_str(), "rb");
     if (!fp) throw LibrecException("TextDataConvertor: cannot read " + path);
@@ -523,6 +524,13 @@ void TextDataModel::buildConvert() {
         if (rs.empty() || (pe && *pe != 0)) throw std::invalid_argument("NumberFormatException: For input string: \"" + rs + "\"");
         keys.push_back(((uint64_t)(uint32_t)u << 32) | (uint32_t)i);
         rates.push_back(r);
+        if (nfields == 4) {                                                                  // DataFrame.java:112-113 Long.parseLong
+            const std::string ds(f[3]);
+            char* de = nullptr;
+            const long long d = strtoll(ds.c_str(), &de, 10);
+            if (ds.empty() || (de && *de != 0)) throw std::invalid_argument("NumberFormatException: For input string: \"" + ds + "\"");
+            dates.push_back((int64_t)d);
+        }
         p = eol ? eol + 1 : end;
     }
     }   // files
@@ -533,6 +541,7 @@ void TextDataModel::buildConvert() {
     for (size_t t = 0; t < n; ++t) ord[t] = (uint32_t)t;
     std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return keys[a] != keys[b] ? keys[a] < keys[b] : a < b; });
     preference = SequentialAccessSparseMatrix();
+    datetime.clear();
     preference.numRows = U; preference.numCols = I;
     preference.rowptr.assign((size_t)U + 1, 0);
     preference.col.reserve(n); preference.val.reserve(n);
@@ -543,6 +552,7 @@ void TextDataModel::buildConvert() {
         if (binThold >= 0) r = r > binThold ? 1.0 : -1.0;                                    // DataFrame.java:251-253
         preference.col.push_back((int32_t)(keys[a] & 0xffffffffu));
         preference.val.push_back(r);
+        if (nfields == 4) datetime.push_back(dates[a]);
         preference.rowptr[(size_t)(keys[a] >> 32) + 1]++;
     }
     for (int32_t u = 0; u < U; ++u) preference.rowptr[(size_t)u + 1] += preference.rowptr[(size_t)u];
@@ -596,6 +606,39 @@ static void next_int_array(int length, int range, std::vector<int>& out) {
     std::sort(out.begin(), out.end());
 }
 
+// date-ordered cuts (util/RatingContext.java:35-44, stable Collections.sort): mode 0 ratio ratingdate, 1 ratio userdate,
+// 2 ratio itemdate, 3 loocv userdate, 4 loocv itemdate, 5 givenn userdate, 6 givenn itemdate.  QUIRK kept from the
+// reference: modes 1 and 5 walk preferenceMatrix.row(u) and use (long) RATING as the timestamp (RatioDataSplitter.java:297,
+// GivenNDataSplitter.java:189), the others read the datetime matrix.
+static void split_by_date(const SequentialAccessSparseMatrix& pref, const std::vector<int64_t>& date, int mode, double ratio, int given,
+                          std::vector<uint8_t>& isTrain) {
+    const bool byCol = mode == 2 || mode == 4 || mode == 6;
+    const bool needDate = !(mode == 1 || mode == 5);
+    if (needDate && date.size() != pref.col.size()) throw LibrecException("this splitter needs data.column.format=UIRT (a date column)");
+    std::vector<int64_t> colptr, csc;
+    if (byCol) csc_order(pref, colptr, csc);
+    std::vector<std::pair<int64_t, int64_t>> ctx;
+    auto cut = [&](const int64_t* entries, size_t n, bool identity, int64_t first) {
+        if (n == 0) return;
+        ctx.resize(n);
+        for (size_t t = 0; t < n; ++t) {
+            const int64_t e = identity ? first + (int64_t)t : entries[t];
+            ctx[t] = {needDate ? date[(size_t)e] : (int64_t)pref.val[(size_t)e], e};
+        }
+        std::stable_sort(ctx.begin(), ctx.end(), [](const std::pair<int64_t, int64_t>& a, const std::pair<int64_t, int64_t>& b) {
+            return (double)a.first - (double)b.first < 0;
+        });
+        size_t nTrain;
+        if (mode <= 2) nTrain = (size_t)(int)((double)n * ratio);
+        else if (mode <= 4) nTrain = n - 1;
+        else nTrain = (size_t)std::min<int64_t>((int64_t)n, given);
+        for (size_t t = 0; t < n; ++t) isTrain[(size_t)ctx[t].second] = t < nTrain;
+    };
+    if (mode == 0) cut(nullptr, pref.col.size(), true, 0);
+    else if (!byCol) for (int u = 0; u < pref.numRows; ++u) cut(nullptr, (size_t)(pref.rowptr[(size_t)u + 1] - pref.rowptr[(size_t)u]), true, pref.rowptr[(size_t)u]);
+    else for (int j = 0; j < pref.numCols; ++j) cut(csc.data() + colptr[(size_t)j], (size_t)(colptr[(size_t)j + 1] - colptr[(size_t)j]), false, 0);
+}
+
 void TextDataModel::buildSplitter() {
     std::string splitter = conf.get("data.model.splitter", "ratio");
     std::transform(splitter.begin(), splitter.end(), splitter.begin(), [](unsigned char c) { return (char)std::tolower(c); });
@@ -612,8 +655,10 @@ void TextDataModel::buildSplitter() {
         } else if (by == "item") {                                                           // :315-334, column order
             csc_order(preference, colptr, csc);
             for (size_t t = 0; t < nnz; ++t) isTrain[(size_t)csc[t]] = Randoms::uniform() < ratio;
+        } else if (by == "ratingdate" || by == "userdate" || by == "itemdate") {             // :190-221, 283-313, 339-373
+            if (ratio > 0 && ratio < 1) split_by_date(preference, datetime, by == "ratingdate" ? 0 : (by == "userdate" ? 1 : 2), ratio, 0, isTrain);
         } else {
-            throw LibrecException("data.splitter.ratio=" + by + " is not implemented (rating, user, item are)");
+            throw LibrecException("data.splitter.ratio=" + by + " is not implemented (rating, user, item, ratingdate, userdate, itemdate are)");
         }
     } else if (splitter == "loocv" || splitter == "net.librec.data.splitter.loocvdatasplitter") {
         const std::string by = lower(conf.get("data.splitter.loocv", "user"));
@@ -630,13 +675,20 @@ void TextDataModel::buildSplitter() {
                 if (n == 0) continue;
                 isTrain[(size_t)csc[(size_t)(colptr[(size_t)j] + (int64_t)((double)n * Randoms::uniform()))]] = 0;
             }
+        } else if (by == "userdate" || by == "itemdate") {                                   // :171-191, 222-250
+            split_by_date(preference, datetime, by == "userdate" ? 3 : 4, 0.0, 0, isTrain);
         } else {
-            throw LibrecException("data.splitter.loocv=" + by + " is not implemented (user, item are)");
+            throw LibrecException("data.splitter.loocv=" + by + " is not implemented (user, item, userdate, itemdate are)");
         }
     } else if (splitter == "givenn" || splitter == "net.librec.data.splitter.givenndatasplitter") {
         const std::string by = lower(conf.get("data.splitter.givenn", "user"));
         const int given = (int)conf.getLong("data.splitter.givenn.n", 1);
-        if (by != "user" && by != "item") throw LibrecException("data.splitter.givenn=" + by + " is not implemented (user, item are)");
+        if (by == "userdate" || by == "itemdate") {                                          // GivenNDataSplitter.java:176-207, 254-284
+            if (given > 0) split_by_date(preference, datetime, by == "userdate" ? 5 : 6, 0.0, given, isTrain);
+            two_way(preference, isTrain, train, test);
+            return;
+        }
+        if (by != "user" && by != "item") throw LibrecException("data.splitter.givenn=" + by + " is not implemented (user, item, userdate, itemdate are)");
         const bool byItem = by == "item";                                                    // GivenNDataSplitter.java:137-167, 217-245
         if (byItem) csc_order(preference, colptr, csc);
         std::vector<int> keep;

@@ -192,6 +192,7 @@ struct LroCsr {
     std::vector<int64_t> rowptr;
     std::vector<int32_t> col;
     std::vector<double> val;
+    std::vector<int64_t> date;            // UIRT only: Long.parseLong of the 4th column of the line that won (DataFrame.java:112-113, 262-270)
     std::vector<std::string> user_ids, item_ids;
 };
 
@@ -247,6 +248,7 @@ LRO_API void* lro_csr_load_paths(const char* paths, const char* fmt, double bin_
     std::unordered_map<std::string, int32_t> umap, imap;
     std::vector<int32_t> us, is;
     std::vector<double> rs;
+    std::vector<int64_t> ds;
     LroCsr* m = new LroCsr();
     std::vector<std::string> f;
     std::string line;
@@ -269,6 +271,7 @@ LRO_API void* lro_csr_load_paths(const char* paths, const char* fmt, double bin_
             if (ii == imap.end()) { i = (int32_t)imap.size(); imap.emplace(f[1], i); m->item_ids.push_back(f[1]); }
             else i = ii->second;
             us.push_back(u); is.push_back(i); rs.push_back(strtod(f[2].c_str(), nullptr));
+            ds.push_back(need == 4 ? strtoll(f[3].c_str(), nullptr, 10) : 0);
         }
         fclose(fp);
     }
@@ -288,6 +291,7 @@ LRO_API void* lro_csr_load_paths(const char* paths, const char* fmt, double bin_
         double r = rs[a];
         if (bin_thold >= 0) r = r > bin_thold ? 1.0 : -1.0;
         m->col.push_back(is[a]); m->val.push_back(r);
+        if (need == 4) m->date.push_back(ds[a]);
         m->rowptr[(size_t)us[a] + 1]++;
     }
     for (int32_t u = 0; u < m->U; ++u) m->rowptr[u + 1] += m->rowptr[u];
@@ -302,6 +306,13 @@ LRO_API void lro_csr_copy(void* h, int64_t* rowptr, int32_t* col, double* val) {
     memcpy(rowptr, m->rowptr.data(), m->rowptr.size() * 8);
     memcpy(col, m->col.data(), m->col.size() * 4);
     memcpy(val, m->val.data(), m->val.size() * 8);
+}
+// datetime matrix values aligned with the entries (UIRT loads only); returns 0 when the load had no date column
+LRO_API int32_t lro_csr_copy_dates(void* h, int64_t* out) {
+    LroCsr* m = (LroCsr*)h;
+    if (m->date.size() != m->col.size()) return 0;
+    memcpy(out, m->date.data(), m->date.size() * 8);
+    return 1;
 }
 // outer (raw string) id of an inner user/item index, parsed as integer (-1 when not numeric)
 LRO_API int64_t lro_csr_outer_id(void* h, int32_t is_item, int32_t inner) {
@@ -420,6 +431,57 @@ LRO_API void lro_split_givenn(int32_t U, int32_t I, const int64_t* rowptr, const
         for (int64_t pos = 0; pos < n; ++pos) {
             const int64_t e = by_item ? csc[(size_t)(b + pos)] : b + pos;
             if (g < given.size() && given[g] == pos) ++g; else is_train[e] = 0;
+        }
+    }
+}
+
+// Date-ordered variants (util/RatingContext.java:35-44 orders by timestamp, Collections.sort is stable).  mode:
+//   0 ratio ratingdate (RatioDataSplitter.java:190-221)  all entries by date, first (int)(n * ratio) -> train
+//   1 ratio userdate   (:283-313)   per user, first (int)(n_u * ratio) -> train.  QUIRK kept: the timestamp is
+//                                    (long) RATING of the entry, not its date (the loop walks preferenceMatrix.row(u))
+//   2 ratio itemdate   (:339-373)   per item by date
+//   3 loocv userdate   (LOOCVDataSplitter.java:171-191)  per user, the latest entry -> test
+//   4 loocv itemdate   (:222-250)
+//   5 givenn userdate  (GivenNDataSplitter.java:176-207) per user, first N -> train; same (long) rating QUIRK as mode 1
+//   6 givenn itemdate  (:254-284)   per item by date
+LRO_API void lro_split_by_date(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val,
+                               const int64_t* date, int32_t mode, double ratio, int32_t n_given, uint8_t* is_train) {
+    const int64_t nnz = rowptr[U];
+    std::vector<int64_t> colptr, csc;
+    const bool by_col = mode == 2 || mode == 4 || mode == 6;
+    if (by_col) lro_csc_order(U, I, rowptr, col, colptr, csc);
+    auto cut = [&](const std::vector<int64_t>& entries) {
+        const size_t n = entries.size();
+        if (n == 0) return;
+        std::vector<std::pair<int64_t, int64_t>> ctx(n);                 // (timestamp, entry)
+        for (size_t t = 0; t < n; ++t) {
+            const int64_t e = entries[t];
+            ctx[t] = {(mode == 1 || mode == 5) ? (int64_t)val[e] : date[e], e};
+        }
+        std::stable_sort(ctx.begin(), ctx.end(), [](const std::pair<int64_t, int64_t>& a, const std::pair<int64_t, int64_t>& b) {
+            return (double)a.first - (double)b.first < 0;                   // compareTo works on the double difference
+        });
+        size_t n_train;
+        if (mode <= 2) n_train = (size_t)(int32_t)((double)n * ratio);
+        else if (mode <= 4) n_train = n - 1;
+        else n_train = (size_t)std::min<int64_t>((int64_t)n, n_given);
+        for (size_t t = 0; t < n; ++t) is_train[ctx[t].second] = t < n_train ? 1 : 0;
+    };
+    std::vector<int64_t> line;
+    if (mode == 0) {
+        line.resize((size_t)nnz);
+        for (int64_t e = 0; e < nnz; ++e) line[(size_t)e] = e;
+        cut(line);
+    } else if (!by_col) {
+        for (int32_t u = 0; u < U; ++u) {
+            line.clear();
+            for (int64_t e = rowptr[u]; e < rowptr[u + 1]; ++e) line.push_back(e);
+            cut(line);
+        }
+    } else {
+        for (int32_t j = 0; j < I; ++j) {
+            line.assign(csc.begin() + colptr[(size_t)j], csc.begin() + colptr[(size_t)j + 1]);
+            cut(line);
         }
     }
 }

@@ -89,6 +89,10 @@ def lib():
                             C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
     L.lro_split_ratio_item.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_double, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
     L.lro_split_kcv.argtypes = [C.c_int64, C.c_int32, _i32p]
+    L.lro_csr_copy_dates.restype = C.c_int32
+    L.lro_csr_copy_dates.argtypes = [C.c_void_p, _i64p]
+    L.lro_split_by_date.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _f64p, _i64p, C.c_int32, C.c_double, C.c_int32,
+                                    np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
     L.lro_split_loocv.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_int32, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
     L.lro_split_givenn.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_int32, C.c_int32, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
     L.lro_ranksgd_item_probs.restype = C.c_int32
@@ -151,8 +155,12 @@ def load_text(path, bin_thold=-1.0, column_format="UIR"):
     col = np.zeros(n.value, np.int32)
     val = np.zeros(n.value, np.float64)
     L.lro_csr_copy(h, rowptr, col, val)
+    date = np.zeros(n.value, np.int64)
+    has_date = L.lro_csr_copy_dates(h, date)
     L.lro_csr_free(h)
-    return Csr(U.value, I.value, rowptr, col, val)
+    m = Csr(U.value, I.value, rowptr, col, val)
+    m.date = date if has_date else None            # datetime matrix values aligned with the entries (UIRT)
+    return m
 
 
 def split_ratio(csr, ratio=0.8):
@@ -172,6 +180,10 @@ def split(csr, splitter="ratio", by="rating", ratio=0.8, n_given=1, k_fold=5):
     """the reference's splitters on the global RNG.  ratio / loocv / givenn -> (train, test); kcv -> list of (train, test)"""
     L = lib()
     flags = np.zeros(csr.nnz, np.uint8)
+    if splitter == "ratio" and by.endswith("date"):
+        L.lro_split_by_date(csr.U, csr.I, csr.rowptr, csr.col, csr.val, csr.date, {"ratingdate": 0, "userdate": 1, "itemdate": 2}[by],
+                            ratio, n_given, flags)
+        return _two_way(csr, flags)
     if splitter == "ratio":
         if by in ("rating", "user"):
             L.lro_split_ratio(csr.nnz, csr.val, ratio, flags)
@@ -179,6 +191,11 @@ def split(csr, splitter="ratio", by="rating", ratio=0.8, n_given=1, k_fold=5):
             L.lro_split_ratio_item(csr.U, csr.I, csr.rowptr, csr.col, ratio, flags)
         else:
             raise ValueError(by)
+        return _two_way(csr, flags)
+    date_modes = {("ratio", "ratingdate"): 0, ("ratio", "userdate"): 1, ("ratio", "itemdate"): 2, ("loocv", "userdate"): 3,
+                  ("loocv", "itemdate"): 4, ("givenn", "userdate"): 5, ("givenn", "itemdate"): 6}
+    if (splitter, by) in date_modes:
+        L.lro_split_by_date(csr.U, csr.I, csr.rowptr, csr.col, csr.val, csr.date, date_modes[(splitter, by)], ratio, n_given, flags)
         return _two_way(csr, flags)
     if splitter == "loocv":
         L.lro_split_loocv(csr.U, csr.I, csr.rowptr, csr.col, int(by == "item"), flags)

@@ -178,12 +178,53 @@ def test_ratio_by_user_and_item_on_a_large_matrix(O, c1, tmp_path, by):
     assert abs(etr.nnz / float(loaded.nnz) - 0.8) <= 0.01
 
 
+@pytest.mark.parametrize("splitter,key,by,train_n,test_n", [
+    ("loocv", "data.splitter.loocv", "userdate", 9, 4),          # LOOCVDataSplitterTestCase.java:103-104
+    ("loocv", "data.splitter.loocv", "itemdate", 9, 4),          # :120-121
+    ("givenn", "data.splitter.givenn", "userdate", 4, 9),        # GivenNDataSplitterTestCase.java:109-110
+    ("givenn", "data.splitter.givenn", "itemdate", 4, 9),        # :128-129
+])
+def test_date_splitters_meet_the_reference_test_expectations(O, splitter, key, by, train_n, test_n):
+    from librec_b200.host.binding import TextDataModel
+    g = os.path.join(ROOT, "tests", "golden", "datamodeltest")
+    dm = TextDataModel({"dfs.data.dir": g, "data.input.path": "matrix4by4-date.txt", "data.column.format": "UIRT", "rec.random.seed": 1,
+                        "data.model.splitter": splitter, key: by, "data.splitter.givenn.n": 1})
+    full = O.load_text(os.path.join(g, "matrix4by4-date.txt"), column_format="UIRT")
+    etr, ete = O.split(full, splitter, by, n_given=1)
+    assert (etr.nnz, ete.nnz) == (train_n, test_n)
+    assert _same(dm.matrix("train"), etr) and _same(dm.matrix("test"), ete)
+
+
+@pytest.mark.parametrize("by,tol", [("ratingdate", 0.01), ("userdate", 0.02), ("itemdate", 0.04)])
+def test_ratio_date_splitters_on_the_reference_dataset(O, by, tol):
+    """RatioDataSplitterTestCase.java:153,171,189 on the reference's own ratings-date.txt (35 497 lines): the train ratio is
+    within the tolerance THAT test states for this variant (0.01 / 0.02 / 0.04 -- the per-user variant sorts by (long) rating,
+    a quirk of the reference kept here, and lands at 0.7835), and the native split equals the oracle's entry for entry"""
+    from librec_b200.host.binding import TextDataModel
+    g = os.path.join(ROOT, "tests", "golden", "datamodeltest")
+    dm = TextDataModel({"dfs.data.dir": g, "data.input.path": "ratings-date.txt", "data.column.format": "UIRT", "rec.random.seed": 1,
+                        "data.model.splitter": "ratio", "data.splitter.ratio": by, "data.splitter.trainset.ratio": 0.8})
+    full = O.load_text(os.path.join(g, "ratings-date.txt"), column_format="UIRT")
+    etr, ete = O.split(full, "ratio", by, ratio=0.8)
+    assert abs(etr.nnz / float(full.nnz) - 0.8) <= tol
+    assert _same(dm.matrix("train"), etr) and _same(dm.matrix("test"), ete)
+
+
+def test_date_splitter_without_a_date_column_fails(tmp_path):
+    from librec_b200.host.binding import TextDataModel, LibrecException
+    p = tmp_path / "r.txt"
+    p.write_text("a x 1\nb y 2\n")
+    with pytest.raises(LibrecException) as e:
+        TextDataModel({"dfs.data.dir": str(tmp_path), "data.input.path": "r.txt", "data.model.splitter": "loocv", "data.splitter.loocv": "userdate"})
+    assert "UIRT" in str(e.value)
+
+
 def test_unimplemented_splitters_fail_loudly(tmp_path):
     from librec_b200.host.binding import TextDataModel, LibrecException
     p = tmp_path / "r.txt"
     p.write_text("a x 1\nb y 2\n")
-    for extra in ({"data.model.splitter": "testset"}, {"data.model.splitter": "ratio", "data.splitter.ratio": "ratingdate"},
-                  {"data.model.splitter": "loocv", "data.splitter.loocv": "userdate"}):
+    for extra in ({"data.model.splitter": "testset"}, {"data.model.splitter": "ratio", "data.splitter.ratio": "valid"},
+                  {"data.model.splitter": "ratio", "data.splitter.ratio": "userfixed"}):
         props = {"dfs.data.dir": str(tmp_path), "data.input.path": "r.txt"}
         props.update(extra)
         with pytest.raises(LibrecException) as e:

@@ -139,6 +139,24 @@ def test_other_splitters_meet_the_reference_test_expectations(O, c1):
     assert np.array_equal(tr_u.col, c1["train"].col)                           # getRatioByUser == getRatioByRating draw for draw
 
 
+def test_date_splitters_meet_the_reference_test_expectations(O):
+    """LOOCVDataSplitterTestCase.java:103-104,120-121 (9 / 4), GivenNDataSplitterTestCase.java:109-110,128-129 (4 / 9) on
+    matrix4by4-date.txt; RatioDataSplitterTestCase.java:153,171,189 on ratings-date.txt with that test's tolerances"""
+    g = os.path.join(GOLDEN, "datamodeltest")
+    m = O.load_text(os.path.join(g, "matrix4by4-date.txt"), column_format="UIRT")
+    assert m.date.tolist() == list(range(1, 14))
+    for by in ("userdate", "itemdate"):
+        tr, te = O.split(m, "loocv", by)
+        assert (tr.nnz, te.nnz) == (9, 4)
+        tr, te = O.split(m, "givenn", by, n_given=1)
+        assert (tr.nnz, te.nnz) == (4, 9)
+    r = O.load_text(os.path.join(g, "ratings-date.txt"), column_format="UIRT")
+    assert (r.U, r.I, r.nnz) == (1508, 2071, 35492)                          # 5 of the 35 497 lines repeat a (user, item) pair
+    for by, tol in (("ratingdate", 0.01), ("userdate", 0.02), ("itemdate", 0.04)):
+        tr, te = O.split(r, "ratio", by, ratio=0.8)
+        assert abs(tr.nnz / float(r.nnz) - 0.8) <= tol and tr.nnz + te.nnz == r.nnz
+
+
 def test_matrix_setup(O, c1):
     mu, mn, mx = O.matrix_setup(c1["train"])
     assert mu == c1["pins"]["global_mean"] and (mn, mx) == (1.0, 5.0)
