@@ -72,8 +72,8 @@ class TextDataModel:
             raise LibrecException(self._L.lrh_last_error().decode())
 
     def matrix(self, which):
-        """which: 'preference' | 'train' | 'test' -> (U, I, rowptr, col, val)"""
-        w = {"preference": 0, "train": 1, "test": 2}[which]
+        """which: 'preference' | 'train' | 'test' | 'valid' -> (U, I, rowptr, col, val)"""
+        w = {"preference": 0, "train": 1, "test": 2, "valid": 3}[which]
         U, I, n = C.c_int32(), C.c_int32(), C.c_int64()
         self._L.lrh_datamodel_dims(self._h, w, C.byref(U), C.byref(I), C.byref(n))
         rowptr = np.zeros(U.value + 1, np.int64); col = np.zeros(n.value, np.int32); val = np.zeros(n.value, np.float64)

@@ -646,6 +646,7 @@ void TextDataModel::buildSplitter() {
     const size_t nnz = preference.col.size();
     std::vector<uint8_t> isTrain(nnz, 1);
     numFolds = 1; foldCursor = 0; assign.clear();
+    valid = SequentialAccessSparseMatrix();
     std::vector<int64_t> colptr, csc;
     if (splitter == "ratio" || splitter == "net.librec.data.splitter.ratiodatasplitter") {
         const std::string by = lower(conf.get("data.splitter.ratio", "rating"));
@@ -655,10 +656,26 @@ void TextDataModel::buildSplitter() {
         } else if (by == "item") {                                                           // :315-334, column order
             csc_order(preference, colptr, csc);
             for (size_t t = 0; t < nnz; ++t) isTrain[(size_t)csc[t]] = Randoms::uniform() < ratio;
+        } else if (by == "valid") {                                                          // getRatio :382-412, three-way
+            const double validRatio = conf.getDouble("data.splitter.validset.ratio", 0.0);
+            if (!((ratio > 0 && validRatio > 0) && (ratio + validRatio) < 1))
+                throw LibrecException("data.splitter.ratio=valid needs positive trainset / validset ratios with a sum below 1");
+            std::vector<uint8_t> isValid(nnz, 0), inTrainOrValid(nnz, 0);
+            for (size_t e = 0; e < nnz; ++e) {
+                const double rdm = Randoms::uniform();
+                isTrain[e] = rdm < ratio;
+                isValid[e] = !isTrain[e] && rdm < ratio + validRatio;
+                inTrainOrValid[e] = isTrain[e] || isValid[e];
+            }
+            SequentialAccessSparseMatrix rest;
+            two_way(preference, inTrainOrValid, rest, test);                                 // test = neither
+            two_way(preference, isValid, valid, rest);                                       // valid
+            two_way(preference, isTrain, train, rest);                                       // train
+            return;
         } else if (by == "ratingdate" || by == "userdate" || by == "itemdate") {             // :190-221, 283-313, 339-373
             if (ratio > 0 && ratio < 1) split_by_date(preference, datetime, by == "ratingdate" ? 0 : (by == "userdate" ? 1 : 2), ratio, 0, isTrain);
         } else {
-            throw LibrecException("data.splitter.ratio=" + by + " is not implemented (rating, user, item, ratingdate, userdate, itemdate are)");
+            throw LibrecException("data.splitter.ratio=" + by + " is not implemented (rating, user, item, valid, ratingdate, userdate, itemdate are; userfixed is broken in the reference: its train and test sets overlap)");
         }
     } else if (splitter == "loocv" || splitter == "net.librec.data.splitter.loocvdatasplitter") {
         const std::string by = lower(conf.get("data.splitter.loocv", "user"));

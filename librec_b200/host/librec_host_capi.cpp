@@ -121,7 +121,7 @@ LRH_API int lrh_datamodel_next_fold(void* h) {
 LRH_API int lrh_datamodel_num_folds(void* h) { return ((DataModelBox*)h)->dm->numFolds; }
 static const SequentialAccessSparseMatrix& dm_matrix(void* h, int which) {
     TextDataModel* d = ((DataModelBox*)h)->dm.get();
-    return which == 0 ? d->preference : (which == 1 ? d->train : d->test);
+    return which == 0 ? d->preference : (which == 1 ? d->train : (which == 2 ? d->test : d->valid));
 }
 LRH_API void lrh_datamodel_dims(void* h, int which, int32_t* U, int32_t* I, int64_t* nnz) {
     const SequentialAccessSparseMatrix& m = dm_matrix(h, which);

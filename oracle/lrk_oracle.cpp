@@ -365,6 +365,19 @@ LRO_API void lro_split_ratio_item(int32_t U, int32_t I, const int64_t* rowptr, c
     for (size_t t = 0; t < csc.size(); ++t) is_train[csc[t]] = lro_uniform() < ratio ? 1 : 0;
 }
 
+// RatioDataSplitter.getRatio(trainRatio, validationRatio) (RatioDataSplitter.java:382-412): one Randoms.uniform() per entry in
+// CSR order; < trainRatio -> train (0), < trainRatio + validationRatio -> validation (1), else test (2).  Nothing is split
+// unless both ratios are positive and their sum is below 1 (assign stays 0 = everything "train"; the reference then leaves
+// all three matrices null).
+LRO_API void lro_split_ratio_valid(int64_t nnz, double train_ratio, double valid_ratio, uint8_t* assign) {
+    for (int64_t e = 0; e < nnz; ++e) assign[e] = 0;
+    if (!((train_ratio > 0 && valid_ratio > 0) && (train_ratio + valid_ratio) < 1)) return;
+    for (int64_t e = 0; e < nnz; ++e) {
+        const double rdm = lro_uniform();
+        assign[e] = rdm < train_ratio ? 0 : (rdm < train_ratio + valid_ratio ? 1 : 2);
+    }
+}
+
 // KCVDataSplitter.splitData(kFold) (KCVDataSplitter.java:84-123): entry index -> fold key (int)(index / (numRates / numFold)) + 1,
 // paired with one Randoms.uniform() each, sorted DESCENDING by the random value (Lists.sortList(.., true), stable); the
 // entries in CSR order receive the keys in that sorted order.  fold_out[e] in 1..numFold; fold k's test set = {fold == k}.

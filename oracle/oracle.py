@@ -88,6 +88,7 @@ def lib():
                             C.c_void_p, C.c_void_p, C.c_double, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double,
                             C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
     L.lro_split_ratio_item.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_double, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
+    L.lro_split_ratio_valid.argtypes = [C.c_int64, C.c_double, C.c_double, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
     L.lro_split_kcv.argtypes = [C.c_int64, C.c_int32, _i32p]
     L.lro_csr_copy_dates.restype = C.c_int32
     L.lro_csr_copy_dates.argtypes = [C.c_void_p, _i64p]
@@ -176,7 +177,7 @@ def _two_way(csr, flags):
     return csr.select((flags == 1) & nz), csr.select((flags == 0) & nz)
 
 
-def split(csr, splitter="ratio", by="rating", ratio=0.8, n_given=1, k_fold=5):
+def split(csr, splitter="ratio", by="rating", ratio=0.8, n_given=1, k_fold=5, valid_ratio=0.0):
     """the reference's splitters on the global RNG.  ratio / loocv / givenn -> (train, test); kcv -> list of (train, test)"""
     L = lib()
     flags = np.zeros(csr.nnz, np.uint8)
@@ -184,6 +185,10 @@ def split(csr, splitter="ratio", by="rating", ratio=0.8, n_given=1, k_fold=5):
         L.lro_split_by_date(csr.U, csr.I, csr.rowptr, csr.col, csr.val, csr.date, {"ratingdate": 0, "userdate": 1, "itemdate": 2}[by],
                             ratio, n_given, flags)
         return _two_way(csr, flags)
+    if splitter == "ratio" and by == "valid":            # -> (train, valid, test)
+        L.lro_split_ratio_valid(csr.nnz, ratio, valid_ratio, flags)
+        nz = csr.val != 0.0
+        return tuple(csr.select((flags == w) & nz) for w in (0, 1, 2))
     if splitter == "ratio":
         if by in ("rating", "user"):
             L.lro_split_ratio(csr.nnz, csr.val, ratio, flags)

@@ -210,6 +210,20 @@ def test_ratio_date_splitters_on_the_reference_dataset(O, by, tol):
     assert _same(dm.matrix("train"), etr) and _same(dm.matrix("test"), ete)
 
 
+def test_three_way_ratio_split_on_the_reference_dataset(O):
+    """RatioDataSplitterTestCase.java:118-136: trainset 0.5 / validset 0.3 -> actual ratios within 0.01"""
+    from librec_b200.host.binding import TextDataModel
+    g = os.path.join(ROOT, "tests", "golden", "datamodeltest")
+    dm = TextDataModel({"dfs.data.dir": g, "data.input.path": "ratings-date.txt", "rec.random.seed": 3, "data.model.splitter": "ratio",
+                        "data.splitter.ratio": "valid", "data.splitter.trainset.ratio": 0.5, "data.splitter.validset.ratio": 0.3})
+    full = O.load_text(os.path.join(g, "ratings-date.txt"))
+    O.lib().lro_seed(3)
+    etr, eva, ete = O.split(full, "ratio", "valid", ratio=0.5, valid_ratio=0.3)
+    assert abs(etr.nnz / float(full.nnz) - 0.5) <= 0.01 and abs(eva.nnz / float(full.nnz) - 0.3) <= 0.01
+    assert etr.nnz + eva.nnz + ete.nnz == full.nnz
+    assert _same(dm.matrix("train"), etr) and _same(dm.matrix("valid"), eva) and _same(dm.matrix("test"), ete)
+
+
 def test_date_splitter_without_a_date_column_fails(tmp_path):
     from librec_b200.host.binding import TextDataModel, LibrecException
     p = tmp_path / "r.txt"
@@ -223,8 +237,7 @@ def test_unimplemented_splitters_fail_loudly(tmp_path):
     from librec_b200.host.binding import TextDataModel, LibrecException
     p = tmp_path / "r.txt"
     p.write_text("a x 1\nb y 2\n")
-    for extra in ({"data.model.splitter": "testset"}, {"data.model.splitter": "ratio", "data.splitter.ratio": "valid"},
-                  {"data.model.splitter": "ratio", "data.splitter.ratio": "userfixed"}):
+    for extra in ({"data.model.splitter": "testset"}, {"data.model.splitter": "ratio", "data.splitter.ratio": "userfixed"}):
         props = {"dfs.data.dir": str(tmp_path), "data.input.path": "r.txt"}
         props.update(extra)
         with pytest.raises(LibrecException) as e:
