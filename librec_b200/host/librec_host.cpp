@@ -451,11 +451,15 @@ void TextDataModel::buildConvert() {
     const std::string fmt = conf.get("data.column.format", "UIR");
     const double binThold = conf.getDouble("data.convert.binarize.threshold", -1.0);
     const size_t nfields = (fmt == "UIRT" || fmt == "uirt") ? 4 : 3;
-    // data.input.path: ':'-separated, each entry relative to dfs.data.dir, file or directory (TextDataModel.java:58-64)
-    std::vector<std::string> files;
-    std::string shown;
-    {
-        std::string all = conf.get("data.input.path", "");
+    std::deque<std::string> bufs;                  // ids are views into these buffers
+    std::unordered_map<std::string_view, int32_t, SvHash> umap, imap;      // DataFrame's static id maps: shared by the test-set load
+    std::vector<std::string_view> uview, iview;
+    struct Lines { std::vector<uint64_t> keys; std::vector<double> rates; std::vector<int64_t> dates; };   // key = user << 32 | item, line order
+
+    // a ':'-separated path list, each entry relative to dfs.data.dir, file or directory (TextDataModel.java:58-64)
+    auto collect = [&](const std::string& spec, std::string& shown) {
+        std::vector<std::string> files;
+        std::string all = spec;
         size_t b = all.find_first_not_of(" \t\r\n"), e = all.find_last_not_of(" \t\r\n");
         all = b == std::string::npos ? std::string() : all.substr(b, e - b + 1);
         size_t from = 0;
@@ -470,92 +474,109 @@ void TextDataModel::buildConvert() {
             if (c == std::string::npos) break;
             from = c + 1;
         }
-    }
-    log.push_back("Dataset: [" + shown + "]");
-    std::deque<std::string> bufs;                  // ids are views into these buffers
-    std::unordered_map<std::string_view, int32_t, SvHash> umap, imap;
-    std::vector<std::string_view> uview, iview;
-    std::vector<uint64_t> keys;          // (user << 32 | item), line order
-    std::vector<double> rates;
-    std::vector<int64_t> dates;
-    for (const std::string& path : files) {
-    FILE* fp = fopen(path.c_str(), "rb");
-    if (!fp) throw LibrecException("TextDataConvertor: cannot read " + path);
-    bufs.emplace_back();
-    std::string& buf = bufs.back();
-    {
-        char tmp[1 << 16];
-        size_t got;
-        while ((got = fread(tmp, 1, sizeof tmp, fp)) > 0) buf.append(tmp, got);
-        fclose(fp);
-    }
-    // pass 1: one (user, item, rating) per line, inner ids in first-seen order; the first blank line ends THIS file
-    const char* p = buf.data();
-    const char* const end = p + buf.size();
-    while (p < end) {
-        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
-        const char* le = eol ? eol : end;
-        const char* lend = (le > p && le[-1] == '\r') ? le - 1 : le;
-        if (is_blank_line(p, lend)) break;                                                   // TextDataConvertor.java:176-178
-        // fields: split at every separator character, drop trailing empty fields
-        std::string_view f[4]; size_t nf = 0, total = 0;
-        const char* fb = p;
-        for (const char* c = p;; ++c) {
-            if (c == lend || is_sep(*c)) {
-                if (nf < 4) f[nf] = std::string_view(fb, (size_t)(c - fb));
-                if (c > fb) total = nf + 1;                                                  // index of the last non-empty field + 1
-                ++nf;
-                if (c == lend) break;
-                fb = c + 1;
+        return files;
+    };
+    // pass 1: one (user, item, rating[, date]) per line, inner ids in first-seen order; the first blank line ends THAT file
+    auto parse = [&](const std::vector<std::string>& files, Lines& L) {
+        for (const std::string& path : files) {
+            FILE* fp = fopen(path.c_str(), "rb");
+            if (!fp) throw LibrecException("TextDataConvertor: cannot read " + path);
+            bufs.emplace_back();
+            std::string& buf = bufs.back();
+            {
+                char tmp[1 << 16];
+                size_t got;
+                while ((got = fread(tmp, 1, sizeof tmp, fp)) > 0) buf.append(tmp, got);
+                fclose(fp);
+            }
+            const char* p = buf.data();
+            const char* const end = p + buf.size();
+            while (p < end) {
+                const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+                const char* le = eol ? eol : end;
+                const char* lend = (le > p && le[-1] == '\r') ? le - 1 : le;
+                if (is_blank_line(p, lend)) break;                                           // TextDataConvertor.java:176-178
+                // fields: split at every separator character, drop trailing empty fields
+                std::string_view f[4]; size_t nf = 0, total = 0;
+                const char* fb = p;
+                for (const char* c = p;; ++c) {
+                    if (c == lend || is_sep(*c)) {
+                        if (nf < 4) f[nf] = std::string_view(fb, (size_t)(c - fb));
+                        if (c > fb) total = nf + 1;                                          // index of the last non-empty field + 1
+                        ++nf;
+                        if (c == lend) break;
+                        fb = c + 1;
+                    }
+                }
+                if (total < nfields) throw std::out_of_range("TextDataConvertor: line with fewer than " + std::to_string(nfields) + " fields: " + std::string(p, (size_t)(lend - p)));
+                auto idOf = [](std::unordered_map<std::string_view, int32_t, SvHash>& m, std::vector<std::string_view>& views, std::string_view key) {
+                    auto it = m.find(key);
+                    if (it != m.end()) return it->second;
+                    const int32_t id = (int32_t)m.size();                                    // DataFrame.java:370-379
+                    m.emplace(key, id); views.push_back(key);
+                    return id;
+                };
+                const int32_t u = idOf(umap, uview, f[0]), i = idOf(imap, iview, f[1]);
+                const std::string rs(f[2]);
+                char* pe = nullptr;
+                const double r = strtod(rs.c_str(), &pe);
+                if (rs.empty() || (pe && *pe != 0)) throw std::invalid_argument("NumberFormatException: For input string: \"" + rs + "\"");
+                L.keys.push_back(((uint64_t)(uint32_t)u << 32) | (uint32_t)i);
+                L.rates.push_back(r);
+                if (nfields == 4) {                                                          // DataFrame.java:112-113 Long.parseLong
+                    const std::string ds(f[3]);
+                    char* de = nullptr;
+                    const long long d = strtoll(ds.c_str(), &de, 10);
+                    if (ds.empty() || (de && *de != 0)) throw std::invalid_argument("NumberFormatException: For input string: \"" + ds + "\"");
+                    L.dates.push_back((int64_t)d);
+                }
+                p = eol ? eol + 1 : end;
             }
         }
-        if (total < nfields) throw std::out_of_range("TextDataConvertor: line with fewer than " + std::to_string(nfields) + " fields: " + std::string(p, (size_t)(lend - p)));
-        auto idOf = [](std::unordered_map<std::string_view, int32_t, SvHash>& m, std::vector<std::string_view>& views, std::string_view key) {
-            auto it = m.find(key);
-            if (it != m.end()) return it->second;
-            const int32_t id = (int32_t)m.size();                                            // DataFrame.java:370-379
-            m.emplace(key, id); views.push_back(key);
-            return id;
-        };
-        const int32_t u = idOf(umap, uview, f[0]), i = idOf(imap, iview, f[1]);
-        const std::string rs(f[2]);
-        char* pe = nullptr;
-        const double r = strtod(rs.c_str(), &pe);
-        if (rs.empty() || (pe && *pe != 0)) throw std::invalid_argument("NumberFormatException: For input string: \"" + rs + "\"");
-        keys.push_back(((uint64_t)(uint32_t)u << 32) | (uint32_t)i);
-        rates.push_back(r);
-        if (nfields == 4) {                                                                  // DataFrame.java:112-113 Long.parseLong
-            const std::string ds(f[3]);
-            char* de = nullptr;
-            const long long d = strtoll(ds.c_str(), &de, 10);
-            if (ds.empty() || (de && *de != 0)) throw std::invalid_argument("NumberFormatException: For input string: \"" + ds + "\"");
-            dates.push_back((int64_t)d);
-        }
-        p = eol ? eol + 1 : end;
-    }
-    }   // files
-    const int32_t U = (int32_t)umap.size(), I = (int32_t)imap.size();
+    };
     // pass 2: order by (user, item, line); the first entry of every (user, item) run is the earliest line -> it wins
-    const size_t n = keys.size();
-    std::vector<uint32_t> ord(n);
-    for (size_t t = 0; t < n; ++t) ord[t] = (uint32_t)t;
-    std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return keys[a] != keys[b] ? keys[a] < keys[b] : a < b; });
-    preference = SequentialAccessSparseMatrix();
-    datetime.clear();
-    preference.numRows = U; preference.numCols = I;
-    preference.rowptr.assign((size_t)U + 1, 0);
-    preference.col.reserve(n); preference.val.reserve(n);
-    for (size_t t = 0; t < n; ++t) {
-        const uint32_t a = ord[t];
-        if (t > 0 && keys[ord[t - 1]] == keys[a]) continue;
-        double r = rates[a];
-        if (binThold >= 0) r = r > binThold ? 1.0 : -1.0;                                    // DataFrame.java:251-253
-        preference.col.push_back((int32_t)(keys[a] & 0xffffffffu));
-        preference.val.push_back(r);
-        if (nfields == 4) datetime.push_back(dates[a]);
-        preference.rowptr[(size_t)(keys[a] >> 32) + 1]++;
+    auto build = [&](const Lines& L, int32_t U, int32_t I, SequentialAccessSparseMatrix& out, std::vector<int64_t>* outDates) {
+        const size_t n = L.keys.size();
+        std::vector<uint32_t> ord(n);
+        for (size_t t = 0; t < n; ++t) ord[t] = (uint32_t)t;
+        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return L.keys[a] != L.keys[b] ? L.keys[a] < L.keys[b] : a < b; });
+        out = SequentialAccessSparseMatrix();
+        if (outDates) outDates->clear();
+        out.numRows = U; out.numCols = I;
+        out.rowptr.assign((size_t)U + 1, 0);
+        out.col.reserve(n); out.val.reserve(n);
+        for (size_t t = 0; t < n; ++t) {
+            const uint32_t a = ord[t];
+            if (t > 0 && L.keys[ord[t - 1]] == L.keys[a]) continue;
+            double r = L.rates[a];
+            if (binThold >= 0) r = r > binThold ? 1.0 : -1.0;                                // DataFrame.java:251-253
+            out.col.push_back((int32_t)(L.keys[a] & 0xffffffffu));
+            out.val.push_back(r);
+            if (outDates && nfields == 4) outDates->push_back(L.dates[a]);
+            out.rowptr[(size_t)(L.keys[a] >> 32) + 1]++;
+        }
+        for (int32_t u = 0; u < U; ++u) out.rowptr[(size_t)u + 1] += out.rowptr[(size_t)u];
+    };
+
+    std::string shown;
+    Lines mainLines, testLines;
+    parse(collect(conf.get("data.input.path", ""), shown), mainLines);
+    log.push_back("Dataset: [" + shown + "]");
+    std::string splitter = conf.get("data.model.splitter", "ratio");
+    std::transform(splitter.begin(), splitter.end(), splitter.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    const bool testset = splitter == "testset" || splitter == "net.librec.data.splitter.giventestsetdatasplitter";
+    if (testset) {
+        // GivenTestSetDataSplitter.java:64-84: the test file(s) (data.testset.path, same list syntax) go through a second
+        // convertor that continues the id maps; both matrices get the final dimensions
+        if (!conf.has("data.testset.path")) throw LibrecException("data.model.splitter=testset needs data.testset.path");
+        std::string shownTest;
+        parse(collect(conf.get("data.testset.path", ""), shownTest), testLines);
+        log.push_back("Dataset: [" + shownTest + "]");
     }
-    for (int32_t u = 0; u < U; ++u) preference.rowptr[(size_t)u + 1] += preference.rowptr[(size_t)u];
+    const int32_t U = (int32_t)umap.size(), I = (int32_t)imap.size();
+    build(mainLines, U, I, preference, &datetime);
+    givenTest = SequentialAccessSparseMatrix();
+    if (testset) build(testLines, U, I, givenTest, nullptr);
     userIds.assign(uview.begin(), uview.end());
     itemIds.assign(iview.begin(), iview.end());
     log.push_back("user number: " + std::to_string(U) + ",\t item number is: " + std::to_string(I));
@@ -734,8 +755,20 @@ void TextDataModel::buildSplitter() {
         numFolds = (int)numFold;
         train = SequentialAccessSparseMatrix(); test = SequentialAccessSparseMatrix();
         return;                                                                              // the folds are cut by hasNextFold()
+    } else if (splitter == "testset" || splitter == "net.librec.data.splitter.giventestsetdatasplitter") {
+        // GivenTestSetDataSplitter.java:86-93: every (user, item) of the test matrix is zeroed in the train matrix
+        for (int u = 0; u < preference.numRows; ++u) {
+            const int32_t* tb = givenTest.col.data() + givenTest.rowptr[(size_t)u];
+            const int32_t* te = givenTest.col.data() + givenTest.rowptr[(size_t)u + 1];
+            for (int64_t e = preference.rowptr[(size_t)u]; e < preference.rowptr[(size_t)u + 1]; ++e)
+                if (std::binary_search(tb, te, preference.col[(size_t)e])) isTrain[(size_t)e] = 0;
+        }
+        SequentialAccessSparseMatrix dropped;
+        two_way(preference, isTrain, train, dropped);
+        test = givenTest;
+        return;
     } else {
-        throw LibrecException("data.model.splitter=" + splitter + " is not implemented (ratio, kcv, loocv, givenn are)");
+        throw LibrecException("data.model.splitter=" + splitter + " is not implemented (ratio, kcv, loocv, givenn, testset are)");
     }
     two_way(preference, isTrain, train, test);
 }

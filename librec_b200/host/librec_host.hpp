@@ -220,7 +220,7 @@ struct TextDataModel {
     // data.model.splitter = ratio (data.splitter.ratio = rating | user | item), kcv (data.splitter.cv.number), loocv
     // (data.splitter.loocv = user | item | userdate | itemdate), givenn (data.splitter.givenn = user | item | userdate |
     // itemdate, data.splitter.givenn.n), ratio also ratingdate | userdate | itemdate (UIRT input) and valid
-    // (data.splitter.validset.ratio); ratio "userfixed" and testset are not implemented (LibrecException)
+    // (data.splitter.validset.ratio), testset (data.testset.path); ratio "userfixed" is not implemented (LibrecException)
     void buildSplitter();
     // AbstractDataModel.hasNextFold / nextFold over AbstractDataSplitter.nextFold (AbstractDataSplitter.java:104-128): one
     // fold for every splitter but kcv, which yields data.splitter.cv.number folds (fold k's test set = entries assigned k)
@@ -229,6 +229,7 @@ struct TextDataModel {
     int foldsDone() const { return foldCursor; }
     Configuration conf;
     SequentialAccessSparseMatrix preference, train, test, valid;   // valid: data.splitter.ratio=valid only
+    SequentialAccessSparseMatrix givenTest;          // data.model.splitter=testset: the matrix of data.testset.path
     std::vector<int64_t> datetime;                   // UIRT: Long.parseLong of the date column of the line that won, per stored entry
     std::vector<int32_t> assign;                     // kcv: fold id (1..K) per stored entry, CSR order
     int numFolds = 1, foldCursor = 0;

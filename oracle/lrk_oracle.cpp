@@ -231,7 +231,13 @@ static void lro_collect_files(const std::string& path, std::vector<std::string>&
     for (const std::string& n : names) lro_collect_files(path + "/" + n, out);
 }
 
-LRO_API void* lro_csr_load_paths(const char* paths, const char* fmt, double bin_thold) {
+struct LroIds {                       // DataFrame's STATIC id maps (DataFrame.java:48,370-379): shared by every convertor of a run
+    std::unordered_map<std::string, int32_t> umap, imap;
+    std::vector<std::string> user_ids, item_ids;
+};
+struct LroLines { std::vector<int32_t> us, is; std::vector<double> rs; std::vector<int64_t> ds; };
+
+static bool lro_read_lines(const char* paths, size_t need, LroIds& ids, LroLines& L) {
     std::vector<std::string> files;
     {
         const std::string all(paths);
@@ -243,59 +249,95 @@ LRO_API void* lro_csr_load_paths(const char* paths, const char* fmt, double bin_
             from = c + 1;
         }
     }
-    if (files.empty()) return nullptr;
-    const size_t need = (fmt && (strcmp(fmt, "UIRT") == 0 || strcmp(fmt, "uirt") == 0)) ? 4 : 3;
-    std::unordered_map<std::string, int32_t> umap, imap;
-    std::vector<int32_t> us, is;
-    std::vector<double> rs;
-    std::vector<int64_t> ds;
-    LroCsr* m = new LroCsr();
+    if (files.empty()) return false;
     std::vector<std::string> f;
     std::string line;
     static char buf[1 << 16];
     for (const std::string& path : files) {
         FILE* fp = fopen(path.c_str(), "rb");
-        if (!fp) { delete m; return nullptr; }
+        if (!fp) return false;
         while (fgets(buf, sizeof buf, fp)) {
             line.assign(buf);
             while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
             if (is_blank(line)) break;
             split_fields(line, "\t;, ", f);
             if (f.size() < need) continue;
-            auto iu = umap.find(f[0]);
+            auto iu = ids.umap.find(f[0]);
             int32_t u;
-            if (iu == umap.end()) { u = (int32_t)umap.size(); umap.emplace(f[0], u); m->user_ids.push_back(f[0]); }
+            if (iu == ids.umap.end()) { u = (int32_t)ids.umap.size(); ids.umap.emplace(f[0], u); ids.user_ids.push_back(f[0]); }
             else u = iu->second;
-            auto ii = imap.find(f[1]);
+            auto ii = ids.imap.find(f[1]);
             int32_t i;
-            if (ii == imap.end()) { i = (int32_t)imap.size(); imap.emplace(f[1], i); m->item_ids.push_back(f[1]); }
+            if (ii == ids.imap.end()) { i = (int32_t)ids.imap.size(); ids.imap.emplace(f[1], i); ids.item_ids.push_back(f[1]); }
             else i = ii->second;
-            us.push_back(u); is.push_back(i); rs.push_back(strtod(f[2].c_str(), nullptr));
-            ds.push_back(need == 4 ? strtoll(f[3].c_str(), nullptr, 10) : 0);
+            L.us.push_back(u); L.is.push_back(i); L.rs.push_back(strtod(f[2].c_str(), nullptr));
+            L.ds.push_back(need == 4 ? strtoll(f[3].c_str(), nullptr, 10) : 0);
         }
         fclose(fp);
     }
-    m->U = (int32_t)umap.size(); m->I = (int32_t)imap.size();
-    // earliest line wins: stable sort by (u,i), keep first of each run
-    const size_t n = us.size();
+    return true;
+}
+
+// DataFrame.toSparseMatrix (DataFrame.java:237-261): earliest line wins, rows sorted by item, optional binarisation
+static LroCsr* lro_build_csr(const LroIds& ids, const LroLines& L, size_t need, double bin_thold) {
+    LroCsr* m = new LroCsr();
+    m->U = (int32_t)ids.umap.size(); m->I = (int32_t)ids.imap.size();
+    m->user_ids = ids.user_ids; m->item_ids = ids.item_ids;
+    const size_t n = L.us.size();
     std::vector<size_t> ord(n);
     for (size_t t = 0; t < n; ++t) ord[t] = t;
     std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
-        if (us[a] != us[b]) return us[a] < us[b];
-        return is[a] < is[b];
+        if (L.us[a] != L.us[b]) return L.us[a] < L.us[b];
+        return L.is[a] < L.is[b];
     });
     m->rowptr.assign((size_t)m->U + 1, 0);
     for (size_t t = 0; t < n; ++t) {
         size_t a = ord[t];
-        if (t > 0 && us[ord[t - 1]] == us[a] && is[ord[t - 1]] == is[a]) continue;
-        double r = rs[a];
+        if (t > 0 && L.us[ord[t - 1]] == L.us[a] && L.is[ord[t - 1]] == L.is[a]) continue;
+        double r = L.rs[a];
         if (bin_thold >= 0) r = r > bin_thold ? 1.0 : -1.0;
-        m->col.push_back(is[a]); m->val.push_back(r);
-        if (need == 4) m->date.push_back(ds[a]);
-        m->rowptr[(size_t)us[a] + 1]++;
+        m->col.push_back(L.is[a]); m->val.push_back(r);
+        if (need == 4) m->date.push_back(L.ds[a]);
+        m->rowptr[(size_t)L.us[a] + 1]++;
     }
     for (int32_t u = 0; u < m->U; ++u) m->rowptr[u + 1] += m->rowptr[u];
     return m;
+}
+
+LRO_API void* lro_csr_load_paths(const char* paths, const char* fmt, double bin_thold) {
+    const size_t need = (fmt && (strcmp(fmt, "UIRT") == 0 || strcmp(fmt, "uirt") == 0)) ? 4 : 3;
+    LroIds ids; LroLines L;
+    if (!lro_read_lines(paths, need, ids, L)) return nullptr;
+    return lro_build_csr(ids, L, need, bin_thold);
+}
+
+// data/splitter/GivenTestSetDataSplitter.java:64-97 (data.model.splitter=testset): the test file(s) go through a second
+// TextDataConvertor that CONTINUES the static id maps, both matrices are then built with the final dimensions, and the train
+// matrix is the preference matrix with every (user, item) of the test matrix set to zero and reshaped away.
+// *pref_out (optional), *train_out, *test_out are LroCsr handles to free with lro_csr_free.  returns 0 on an unreadable path.
+LRO_API int32_t lro_csr_load_testset(const char* paths, const char* test_paths, const char* fmt, double bin_thold,
+                                     void** pref_out, void** train_out, void** test_out) {
+    const size_t need = (fmt && (strcmp(fmt, "UIRT") == 0 || strcmp(fmt, "uirt") == 0)) ? 4 : 3;
+    LroIds ids; LroLines L, T;
+    if (!lro_read_lines(paths, need, ids, L) || !lro_read_lines(test_paths, need, ids, T)) return 0;
+    LroCsr* pref = lro_build_csr(ids, L, need, bin_thold);
+    LroCsr* test = lro_build_csr(ids, T, need, bin_thold);
+    LroCsr* train = new LroCsr();
+    train->U = pref->U; train->I = pref->I; train->user_ids = pref->user_ids; train->item_ids = pref->item_ids;
+    train->rowptr.assign((size_t)pref->U + 1, 0);
+    for (int32_t u = 0; u < pref->U; ++u) {
+        const int32_t* tb = test->col.data() + test->rowptr[u];
+        const int32_t* te = test->col.data() + test->rowptr[u + 1];
+        for (int64_t e = pref->rowptr[u]; e < pref->rowptr[u + 1]; ++e) {
+            if (std::binary_search(tb, te, pref->col[(size_t)e]) || pref->val[(size_t)e] == 0.0) continue;
+            train->col.push_back(pref->col[(size_t)e]); train->val.push_back(pref->val[(size_t)e]);
+            if (need == 4) train->date.push_back(pref->date[(size_t)e]);
+        }
+        train->rowptr[(size_t)u + 1] = (int64_t)train->col.size();
+    }
+    if (pref_out) *pref_out = pref; else delete pref;
+    *train_out = train; *test_out = test;
+    return 1;
 }
 LRO_API void* lro_csr_load_text(const char* path, double bin_thold) { return lro_csr_load_paths(path, "UIR", bin_thold); }
 LRO_API void lro_csr_dims(void* h, int32_t* U, int32_t* I, int64_t* nnz) {

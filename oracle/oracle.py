@@ -60,6 +60,8 @@ def lib():
     L.lro_float_promote.argtypes = [C.c_char_p]
     L.lro_csr_load_text.restype = C.c_void_p
     L.lro_csr_load_text.argtypes = [C.c_char_p, C.c_double]
+    L.lro_csr_load_testset.restype = C.c_int32
+    L.lro_csr_load_testset.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.lro_csr_load_paths.restype = C.c_void_p
     L.lro_csr_load_paths.argtypes = [C.c_char_p, C.c_char_p, C.c_double]
     L.lro_csr_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
@@ -162,6 +164,26 @@ def load_text(path, bin_thold=-1.0, column_format="UIR"):
     m = Csr(U.value, I.value, rowptr, col, val)
     m.date = date if has_date else None            # datetime matrix values aligned with the entries (UIRT)
     return m
+
+
+def _take(h):
+    L = lib()
+    U, I, n = C.c_int32(), C.c_int32(), C.c_int64()
+    L.lro_csr_dims(h, C.byref(U), C.byref(I), C.byref(n))
+    rowptr = np.zeros(U.value + 1, np.int64); col = np.zeros(n.value, np.int32); val = np.zeros(n.value, np.float64)
+    L.lro_csr_copy(h, rowptr, col, val)
+    L.lro_csr_free(h)
+    return Csr(U.value, I.value, rowptr, col, val)
+
+
+def load_testset(path, test_path, bin_thold=-1.0, column_format="UIR"):
+    """data.model.splitter=testset (GivenTestSetDataSplitter): -> (preference, train, test), all with the final dimensions"""
+    p, tr, te = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    ok = lib().lro_csr_load_testset(path.encode(), test_path.encode(), column_format.encode(), float(bin_thold),
+                                    C.byref(p), C.byref(tr), C.byref(te))
+    if not ok:
+        raise FileNotFoundError(path + " / " + test_path)
+    return _take(p), _take(tr), _take(te)
 
 
 def split_ratio(csr, ratio=0.8):

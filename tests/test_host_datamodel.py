@@ -224,6 +224,30 @@ def test_three_way_ratio_split_on_the_reference_dataset(O):
     assert _same(dm.matrix("train"), etr) and _same(dm.matrix("valid"), eva) and _same(dm.matrix("test"), ete)
 
 
+def test_given_test_set_splitter(O, tmp_path):
+    """data.model.splitter=testset (GivenTestSetDataSplitter.java:64-97): the test file continues the id maps (a user and an
+    item that only occur there get the next inner ids), train = all ratings minus the test pairs, dimensions agree"""
+    from librec_b200.host.binding import TextDataModel
+    (tmp_path / "all.txt").write_text("u1 i1 5\nu1 i2 3\nu2 i1 4\nu2 i3 2\nu3 i2 1\nu3 i3 0\n")
+    (tmp_path / "test.txt").write_text("u2 i1 4\nu3 i2 1\nu9 i1 3\nu1 i7 2\n")            # u9 and i7 are new; (u1, i7) is not in all.txt
+    dm = TextDataModel({"dfs.data.dir": str(tmp_path), "data.input.path": "all.txt", "data.model.splitter": "testset",
+                        "data.testset.path": "test.txt"})
+    pref, etr, ete = O.load_testset(str(tmp_path / "all.txt"), str(tmp_path / "test.txt"))
+    assert (pref.U, pref.I) == (4, 4) and (etr.U, etr.I) == (4, 4) and (ete.U, ete.I) == (4, 4)
+    assert etr.nnz == 3 and ete.nnz == 4                                   # (u3, i3) has rating 0.0: reshape() drops it from train
+    assert _same(dm.matrix("preference"), pref) and _same(dm.matrix("train"), etr) and _same(dm.matrix("test"), ete)
+    assert [dm.raw_id(0, u) for u in range(4)] == ["u1", "u2", "u3", "u9"] and dm.raw_id(1, 3) == "i7"
+    assert dm.next_fold() and not dm.next_fold()
+    # the reference's fixtures through the same path: 4x4 matrix as data, the 4x4A file as test set
+    g = os.path.join(ROOT, "tests", "golden")
+    dm2 = TextDataModel({"dfs.data.dir": g, "data.input.path": "matrix4by4.txt:datamodeltest/matrix4by4A.txt",
+                         "data.model.splitter": "testset", "data.testset.path": "datamodeltest/matrix4by4A.txt"})
+    p2, tr2, te2 = O.load_testset(os.path.join(g, "matrix4by4.txt") + ":" + os.path.join(g, "datamodeltest", "matrix4by4A.txt"),
+                                  os.path.join(g, "datamodeltest", "matrix4by4A.txt"))
+    assert (p2.nnz, tr2.nnz, te2.nnz) == (25, 13, 12)
+    assert _same(dm2.matrix("train"), tr2) and _same(dm2.matrix("test"), te2)
+
+
 def test_date_splitter_without_a_date_column_fails(tmp_path):
     from librec_b200.host.binding import TextDataModel, LibrecException
     p = tmp_path / "r.txt"
@@ -237,7 +261,7 @@ def test_unimplemented_splitters_fail_loudly(tmp_path):
     from librec_b200.host.binding import TextDataModel, LibrecException
     p = tmp_path / "r.txt"
     p.write_text("a x 1\nb y 2\n")
-    for extra in ({"data.model.splitter": "testset"}, {"data.model.splitter": "ratio", "data.splitter.ratio": "userfixed"}):
+    for extra in ({"data.model.splitter": "nosuchsplitter"}, {"data.model.splitter": "ratio", "data.splitter.ratio": "userfixed"}):
         props = {"dfs.data.dir": str(tmp_path), "data.input.path": "r.txt"}
         props.update(extra)
         with pytest.raises(LibrecException) as e:
