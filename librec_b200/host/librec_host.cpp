@@ -414,6 +414,26 @@ double evaluateMAE(const SequentialAccessSparseMatrix& test, const RecommendedLi
     double se, ae; int64_t n; zip_eval(test, rec, &se, &ae, &n);
     return n > 0 ? ae / (double)n : 0.0;
 }
+double evaluateMSE(const SequentialAccessSparseMatrix& test, const RecommendedList& rec) {        // eval/rating/MSEEvaluator.java:33-66
+    if (test.size() == 0) return 0.0;
+    double se, ae; int64_t n; zip_eval(test, rec, &se, &ae, &n);
+    return n > 0 ? se / (double)n : 0.0;
+}
+double evaluateMPE(const SequentialAccessSparseMatrix& test, const RecommendedList& rec, double mpe) {   // eval/rating/MPEEvaluator.java:33-73
+    if (test.size() == 0) return 0.0;
+    int64_t n = 0, over = 0;
+    for (int u = 0; u < test.numRows; ++u) {
+        const auto& lst = rec.lists[(size_t)u];
+        size_t t = 0;
+        for (int64_t e = test.rowptr[(size_t)u]; e < test.rowptr[(size_t)u + 1]; ++e, ++t) {
+            if (t >= lst.size()) throw std::out_of_range("index cardinality of recommendedList does not equal testMatrix index cardinality");
+            if (lst[t].key != test.col[(size_t)e]) throw std::out_of_range("index of recommendedList does not equal testMatrix index");
+            if (std::fabs(test.val[(size_t)e] - lst[t].value) > mpe) ++over;
+            ++n;
+        }
+    }
+    return n > 0 ? ((double)over + 0.0) / (double)n : 0.0;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // TextDataModel: text file -> flat CSR -> ratio split
@@ -814,6 +834,8 @@ void RecommenderJob::runCrossValidation() {
             if (!ranking) {
                 evaluatedMap["RMSE"] = evaluateRMSE(test, recommendedList);
                 evaluatedMap["MAE"] = evaluateMAE(test, recommendedList);
+                evaluatedMap["MSE"] = evaluateMSE(test, recommendedList);
+                evaluatedMap["MPE"] = evaluateMPE(test, recommendedList, conf.getDouble("rec.measure.mpe", 0.01));
             }
         } else {
             recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
@@ -851,8 +873,10 @@ void RecommenderJob::runJob() {
         if (ranking && recommender->rankingTopN() <= 64) recommendedList = recommender->recommendRankAndEvaluate(test, &evaluatedMap);
         else recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
         if (!ranking) {
-            evaluatedMap["RMSE"] = evaluateRMSE(test, recommendedList);
+            evaluatedMap["RMSE"] = evaluateRMSE(test, recommendedList);             // eval/Measure.java:100-107: RMSE, MSE, MAE, MPE
             evaluatedMap["MAE"] = evaluateMAE(test, recommendedList);
+            evaluatedMap["MSE"] = evaluateMSE(test, recommendedList);
+            evaluatedMap["MPE"] = evaluateMPE(test, recommendedList, conf.getDouble("rec.measure.mpe", 0.01));
         }
     } else {
         recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);

@@ -205,6 +205,9 @@ std::unique_ptr<MatrixFactorizationCudaRecommender> newRecommender(const std::st
 // eval/rating/RMSEEvaluator.java:33-69, MAEEvaluator.java:34-70 : zip ground truth and predictions
 double evaluateRMSE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended);
 double evaluateMAE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended);
+// eval/rating/MSEEvaluator.java:33-66, MPEEvaluator.java:33-73 (share of entries with |error| > rec.measure.mpe, default 0.01)
+double evaluateMSE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended);
+double evaluateMPE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended, double mpe);
 
 // data/model/TextDataModel.java + data/convertor/TextDataConvertor.java:136-200 + math/structure/DataFrame.java:237-261,370-379
 // + data/splitter/RatioDataSplitter.java:136-156, straight into flat CSR arrays: no per-line String[],

@@ -100,6 +100,24 @@ LRH_API void lrh_job_list_copy(void* h, int32_t* counts, int32_t* keys, double* 
     }
 }
 // host-logic probes used by the CPU tests (no GPU needed)
+// the four default rating measures (eval/Measure.java:100-107) over a flat test CSR and the predictions in the same order:
+// out = RMSE, MSE, MAE, MPE
+LRH_API int lrh_probe_rating_measures(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val,
+                                      const double* pred, double mpe, double* out) {
+    try {
+        SequentialAccessSparseMatrix t;
+        t.numRows = U; t.numCols = I;
+        t.rowptr.assign(rowptr, rowptr + U + 1);
+        t.col.assign(col, col + rowptr[U]); t.val.assign(val, val + rowptr[U]);
+        RecommendedList rec;
+        for (int u = 0; u < U; ++u) {
+            rec.addList();
+            for (int64_t e = rowptr[u]; e < rowptr[u + 1]; ++e) rec.add(u, col[e], pred[e]);
+        }
+        out[0] = evaluateRMSE(t, rec); out[1] = evaluateMSE(t, rec); out[2] = evaluateMAE(t, rec); out[3] = evaluateMPE(t, rec, mpe);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 // ---- data model alone (no GPU needed): properties -> TextDataModel.buildDataModel() -> flat CSR arrays
 struct DataModelBox { std::unique_ptr<TextDataModel> dm; std::string tmp; };
 LRH_API void* lrh_datamodel_build(const char* properties_text) {

@@ -56,3 +56,28 @@ def test_unknown_recommender_class_is_reported(H):
     with pytest.raises(LibrecException) as e:
         job.run_job()
     assert "ClassNotFoundException" in str(e.value)
+
+
+def test_default_rating_measures(H, O):
+    """eval/Measure.java:100-107: a rating job reports RMSE, MSE, MAE and MPE (share of entries with |error| > rec.measure.mpe).
+    The host evaluators zip the test CSR with the predictions like eval/rating/*Evaluator.java; checked against numpy and, for
+    RMSE / MAE, the oracle's evaluator arithmetic."""
+    from conftest import rng_csr
+    te = rng_csr(O, 60, 40, 0.2, 9)
+    rng = np.random.default_rng(1)
+    pred = te.val + rng.normal(0, 0.5, te.nnz)
+    pred[::7] = te.val[::7]                                     # exact hits: never counted by MPE
+    pred[1::7] = te.val[1::7] + 0.005                           # below the default threshold 0.01
+    out = np.zeros(4)
+    H.lrh_probe_rating_measures.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    rc = H.lrh_probe_rating_measures(te.U, te.I, te.rowptr.ctypes.data, te.col.ctypes.data, te.val.ctypes.data, pred.ctypes.data, 0.01, out.ctypes.data)
+    assert rc == 0
+    d = te.val - pred
+    se = 0.0
+    for x in d:
+        se += x * x                                             # sequential sum like the evaluators
+    assert out[1] == se / te.nnz and out[0] == np.sqrt(se / te.nnz)
+    assert abs(out[2] - np.abs(d).sum() / te.nnz) < 1e-15
+    assert out[3] == np.count_nonzero(np.abs(d) > 0.01) / te.nnz and 0.5 < out[3] < 0.75
+    rc = H.lrh_probe_rating_measures(te.U, te.I, te.rowptr.ctypes.data, te.col.ctypes.data, te.val.ctypes.data, pred.ctypes.data, 0.75, out.ctypes.data)
+    assert rc == 0 and out[3] == np.count_nonzero(np.abs(d) > 0.75) / te.nnz
