@@ -655,6 +655,85 @@ LRO_API double lro_pmf_epoch(int32_t U, const int64_t* rowptr, const int32_t* co
     return loss;
 }
 
+// -------------------------------------------------------------------------------------
+// SVD++ (SURVEY.md 8f, row N3 -- groundwork: oracle only, no device kernel yet):
+// recommender/cf/rating/SVDPlusPlusRecommender.java:62-123 (extends BiasedMF; impItemFactors Y is I x k, Gaussian-initialised
+// AFTER the BiasedMF setup, regImpItem = rec.impItem.regularization, default 0.015).  Per user with a non-empty row:
+// fv = |N(u)|^-1/2 * sum_{j in N(u)} y_j, FIXED for the whole row; per rating in item order: predict =
+// (b_u + b_i + mu) + sum_f (fv_f + p_uf) q_if (:126-135), the bias and factor updates of BiasedMF except that the item
+// gradient uses (p_uf + fv_f) (:93) and steps_f += e * q_if(old) * scale (:96); after the row every y_j of the row moves by
+// lr * (steps_f - regImp * y_jf * n) and the loss takes regImp * y_jf^2 * n (:99-106).  loss *= 0.5.
+// -------------------------------------------------------------------------------------
+LRO_API double lro_svdpp_epoch(int32_t U, const int64_t* rowptr, const int32_t* col, const double* val, int32_t k,
+                               double* P, double* Q, double* Y, double* bu, double* bi, double mu,
+                               float lr_f, float regU_f, float regI_f, double regB, double regImp) {
+    const double learnRate = (double)lr_f, regUser = (double)regU_f, regItem = (double)regI_f;
+    double loss = 0.0;
+    std::vector<double> fv((size_t)k), steps((size_t)k);
+    for (int32_t u = 0; u < U; ++u) {
+        const int64_t b = rowptr[u], e = rowptr[u + 1];
+        const int64_t n = e - b;
+        if (n == 0) continue;
+        std::fill(steps.begin(), steps.end(), 0.0);
+        std::fill(fv.begin(), fv.end(), 0.0);
+        for (int64_t t = b; t < e; ++t)
+            for (int f = 0; f < k; ++f) fv[(size_t)f] = Y[(int64_t)col[t] * k + f] + fv[(size_t)f];
+        const double scale = pow((double)n, -0.5);
+        for (int f = 0; f < k; ++f) fv[(size_t)f] = fv[(size_t)f] * scale;
+        double* pu = P + (int64_t)u * k;
+        for (int64_t t = b; t < e; ++t) {
+            const int32_t i = col[t];
+            double* qi = Q + (int64_t)i * k;
+            double pred = bu[u] + bi[i] + mu;
+            for (int f = 0; f < k; ++f) pred += (fv[(size_t)f] + pu[f]) * qi[f];
+            const double error = val[t] - pred;
+            loss += error * error;
+            const double ub = bu[u];
+            bu[u] += learnRate * (error - regB * ub);
+            loss += regB * ub * ub;
+            const double ib = bi[i];
+            bi[i] += learnRate * (error - regB * ib);
+            loss += regB * ib * ib;
+            for (int f = 0; f < k; ++f) {
+                const double uf = pu[f], itf = qi[f];
+                pu[f] += learnRate * (error * itf - regUser * uf);
+                qi[f] += learnRate * (error * (uf + fv[(size_t)f]) - regItem * itf);
+                loss += regUser * uf * uf + regItem * itf * itf;
+                steps[(size_t)f] += error * itf * scale;
+            }
+        }
+        const int32_t size = (int32_t)n;
+        for (int64_t t = b; t < e; ++t) {
+            double* yj = Y + (int64_t)col[t] * k;
+            for (int f = 0; f < k; ++f) {
+                const double factor = yj[f];
+                yj[f] += learnRate * (steps[(size_t)f] - regImp * factor * size);
+                loss += regImp * factor * factor * size;
+            }
+        }
+    }
+    return 0.5 * loss;
+}
+
+// SVDPlusPlusRecommender.predict(u, i) (:138-150): fv = sum y_j / Math.sqrt(n) (division, not the pow of training), then :126-135
+LRO_API void lro_svdpp_predict_pairs(int32_t k, const double* P, const double* Q, const double* Y, const double* bu, const double* bi,
+                                     double mu, const int64_t* tr_rowptr, const int32_t* tr_col, const int32_t* users,
+                                     const int32_t* items, int64_t n, double* out) {
+    std::vector<double> fv((size_t)k);
+    for (int64_t t = 0; t < n; ++t) {
+        const int32_t u = users[t], i = items[t];
+        std::fill(fv.begin(), fv.end(), 0.0);
+        const int64_t b = tr_rowptr[u], e = tr_rowptr[u + 1];
+        for (int64_t x = b; x < e; ++x)
+            for (int f = 0; f < k; ++f) fv[(size_t)f] = Y[(int64_t)tr_col[x] * k + f] + fv[(size_t)f];
+        const double scale = sqrt((double)(e - b));
+        if (scale > 0) for (int f = 0; f < k; ++f) fv[(size_t)f] = fv[(size_t)f] / scale;
+        double v = bu[u] + bi[i] + mu;
+        for (int f = 0; f < k; ++f) v += (fv[(size_t)f] + P[(int64_t)u * k + f]) * Q[(int64_t)i * k + f];
+        out[t] = v;
+    }
+}
+
 // Maths.logistic: math/algorithm/Maths.java:127-129  (1 / (1 + Math.exp(-x)))
 static inline double logistic(double x) { return 1.0 / (1.0 + exp(-x)); }
 

@@ -98,6 +98,11 @@ def lib():
                                     np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
     L.lro_split_loocv.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_int32, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
     L.lro_split_givenn.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_int32, C.c_int32, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
+    L.lro_svdpp_epoch.restype = C.c_double
+    L.lro_svdpp_epoch.argtypes = [C.c_int32, _i64p, _i32p, _f64p, C.c_int32, _f64p, _f64p, _f64p, _f64p, _f64p, C.c_double,
+                                  C.c_float, C.c_float, C.c_float, C.c_double, C.c_double]
+    L.lro_svdpp_predict_pairs.argtypes = [C.c_int32, _f64p, _f64p, _f64p, _f64p, _f64p, C.c_double, _i64p, _i32p, _i32p, _i32p,
+                                          C.c_int64, _f64p]
     L.lro_ranksgd_item_probs.restype = C.c_int32
     L.lro_ranksgd_item_probs.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _i32p, _f64p]
     L.lro_ranksgd_epoch.restype = C.c_double

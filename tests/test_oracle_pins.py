@@ -306,6 +306,77 @@ def test_ranksgd_reference_sampler_draws_unrated_items_by_popularity(O):
     assert drawn[pop == 0].sum() == 0
 
 
+# ---- SVD++ (oracle groundwork): recommender/cf/rating/SVDPlusPlusRecommender.java ------------
+def test_svdpp_epoch_by_hand(O):
+    """one user with two ratings, k = 2, worked by hand from :62-123: fv is fixed for the row, the second rating sees the
+    updated p_u / b_u, the item gradient uses (p + fv), steps accumulate e * q_old * scale, Y moves after the row"""
+    L = O.lib()
+    tr = O.Csr(1, 3, [0, 2], [0, 2], [4.0, 2.0])
+    P = np.array([[0.1, -0.2]]); Q = np.array([[0.3, 0.1], [0.9, 0.9], [-0.2, 0.4]])
+    Y = np.array([[0.05, 0.02], [0.7, 0.7], [-0.01, 0.03]])
+    bu = np.array([0.1]); bi = np.array([0.2, 0.5, -0.1]); mu = 3.0
+    lr, ru, ri = _f32(0.01), _f32(0.02), _f32(0.03)
+    rb, rimp = 0.04, 0.015
+    p, q, y, b_u, b_i = P.copy(), Q.copy(), Y.copy(), bu.copy(), bi.copy()
+    n = 2
+    scale = math.pow(n, -0.5)
+    fv = [(0.0 + y[0, f]) + y[2, f] for f in range(2)]          # value = row(j).get(f) + value, entries in item order
+    fv = [v * scale for v in fv]
+    steps = [0.0, 0.0]
+    loss = 0.0
+    for i, r in ((0, 4.0), (2, 2.0)):
+        pred = b_u[0] + b_i[i] + mu
+        for f in range(2):
+            pred += (fv[f] + p[0, f]) * q[i, f]
+        e = r - pred
+        loss += e * e
+        ub = b_u[0]; b_u[0] += lr * (e - rb * ub); loss += rb * ub * ub
+        ib = b_i[i]; b_i[i] += lr * (e - rb * ib); loss += rb * ib * ib
+        for f in range(2):
+            uf, qf = p[0, f], q[i, f]
+            p[0, f] += lr * (e * qf - ru * uf)
+            q[i, f] += lr * (e * (uf + fv[f]) - ri * qf)
+            loss += ru * uf * uf + ri * qf * qf
+            steps[f] += e * qf * scale
+    for j in (0, 2):
+        for f in range(2):
+            fac = y[j, f]
+            y[j, f] += lr * (steps[f] - rimp * fac * n)
+            loss += rimp * fac * fac * n
+    got = L.lro_svdpp_epoch(1, tr.rowptr, tr.col, tr.val, 2, P, Q, Y, bu, bi, mu, 0.01, 0.02, 0.03, rb, rimp)
+    assert got == 0.5 * loss
+    assert P.tolist() == p.tolist() and Q.tolist() == q.tolist() and Y.tolist() == y.tolist()
+    assert bu.tolist() == b_u.tolist() and bi.tolist() == b_i.tolist()
+    assert Q[1].tolist() == [0.9, 0.9] and Y[1].tolist() == [0.7, 0.7]      # the unrated item is untouched
+    # predict (:138-150) divides by Math.sqrt(n)
+    out = np.zeros(1)
+    L.lro_svdpp_predict_pairs(2, P, Q, Y, bu, bi, mu, tr.rowptr, tr.col, np.array([0], np.int32), np.array([1], np.int32), 1, out)
+    fvp = [((0.0 + Y[0, f]) + Y[2, f]) / math.sqrt(2.0) for f in range(2)]
+    exp = bu[0] + bi[1] + mu
+    for f in range(2):
+        exp += (fvp[f] + P[0, f]) * Q[1, f]
+    assert out[0] == exp
+
+
+def test_svdpp_learns_on_c1(O, c1):
+    """svdpp-test.properties-like run on the C1 split (lr 0.01, reg 0.1 / 0.015, 10 factors, 13 iterations): the restated loop
+    converges and beats the global-mean predictor clearly"""
+    tr, te = c1["train"], c1["test"]
+    k = 10
+    rng = np.random.default_rng(3)
+    P = rng.normal(0, 0.001, (tr.U, k)); Q = rng.normal(0, 0.001, (tr.I, k)); Y = rng.normal(0, 0.001, (tr.I, k))
+    bu = rng.normal(0, 0.001, tr.U); bi = rng.normal(0, 0.001, tr.I)
+    mu = c1["pins"]["global_mean"]
+    losses = [O.lib().lro_svdpp_epoch(tr.U, tr.rowptr, tr.col, tr.val, k, P, Q, Y, bu, bi, mu, 0.01, 0.1, 0.1, 0.1, 0.015) for _ in range(13)]
+    assert all(b < a for a, b in zip(losses, losses[1:]))
+    rows = te.rows().astype(np.int32)
+    out = np.zeros(te.nnz)
+    O.lib().lro_svdpp_predict_pairs(k, P, Q, Y, bu, bi, mu, tr.rowptr, tr.col, rows, te.col, te.nnz, out)
+    rmse = float(np.sqrt(np.mean((te.val - np.clip(out, 1.0, 5.0)) ** 2)))
+    base = float(np.sqrt(np.mean((te.val - mu) ** 2)))
+    assert rmse < 0.97 and rmse < base - 0.15, (rmse, base)
+
+
 # ---- learning-rate schedule / convergence (host logic the shim keeps in Java) -----------------------
 def test_update_lrate_and_is_converged(O):
     L = O.lib()
