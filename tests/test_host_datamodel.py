@@ -162,7 +162,7 @@ def test_kcv_folds_meet_the_reference_test_expectation(O):
 
 @pytest.mark.parametrize("by", ["user", "item"])
 def test_ratio_by_user_and_item_on_a_large_matrix(O, c1, tmp_path, by):
-    """RatioDataSplitterTestCase.java:93,153: |actual train ratio - 0.8| <= 0.01; and the oracle's split entry for entry"""
+    """RatioDataSplitterTestCase.java:93,112: |actual train ratio - 0.8| <= 0.01; and the oracle's split entry for entry"""
     from librec_b200.host.binding import TextDataModel
     full = c1["full"]
     path = os.path.join(str(tmp_path), "r.txt")

@@ -113,7 +113,7 @@ def test_splitter_ratio_bound(O, c1):
 def test_other_splitters_meet_the_reference_test_expectations(O, c1):
     """sizes asserted by the reference's splitter tests on its 4x4 fixtures: GivenNDataSplitterTestCase.java:70-71,90-91
     (N=1: 4 train / 9 test), LOOCVDataSplitterTestCase.java:68-69,86-87 (9 / 4), KCVDataSplitterTestCase.java:68-69
-    (matrix4by4A.txt, 6 folds: 10 / 2 each), RatioDataSplitterTestCase.java:93,153 (user / item ratio within 0.01 of 0.8)"""
+    (matrix4by4A.txt, 6 folds: 10 / 2 each), RatioDataSplitterTestCase.java:93,112 (user / item ratio within 0.01 of 0.8)"""
     m = O.load_text(os.path.join(GOLDEN, "matrix4by4.txt"))
     for seed in range(1, 6):
         for by in ("user", "item"):
