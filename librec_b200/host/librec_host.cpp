@@ -436,6 +436,109 @@ double evaluateMPE(const SequentialAccessSparseMatrix& test, const RecommendedLi
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Ranking measures on the host -- used when rec.recommender.ranking.topn exceeds what the device evaluator keeps per thread
+// (64).  One pass per user over its list and its test row; semantics of eval/ranking/*.java:
+//   PRECISION hits / topN (PrecisionEvaluator.java:41);  RECALL hits / |test row| (RecallEvaluator.java);
+//   AP  sum over hit positions of hits-so-far / position, divided by min(|test row|, list length), users with an empty list
+//       skipped (AveragePrecisionEvaluator.java);  RR 1 / position of the first hit (ReciprocalRankEvaluator.java);
+//   NDCG dcg / idcg with gains = TEST RATINGS of the hits, discount log2(position + 1), ideal = the same hits sorted by
+//       rating (NormalizedDCGEvaluator.java:84-120);
+//   AUC (AUCEvaluator.java:56-98) pair count with the dropped-items correction; the test items are walked in
+//       java.util.HashSet<Integer> order (ascending bucket of h ^ h>>>16 in a table of the set's capacity);
+//   Novelty (NoveltyEvaluator.java) sum over recommended items of -ln(purchases / numUsers), / (numUsers ln 2);
+//   Entropy (EntropyEvaluator.java:60-90) of the items' share of the lists, in bits.
+// Users without test entries do not count for the first six.
+// ---------------------------------------------------------------------------------------------------------------------
+void evaluateRanking(const SequentialAccessSparseMatrix& train, const SequentialAccessSparseMatrix& test, const RecommendedList& rec,
+                     int topN, std::map<std::string, double>* measures) {
+    const int numUsers = test.numRows, numItems = test.numCols;
+    std::vector<int> purchases((size_t)numItems, 0), listed((size_t)numItems, 0);
+    for (int32_t c : train.col) purchases[(size_t)c]++;
+    for (int32_t c : test.col) purchases[(size_t)c]++;
+    double novelty = 0.0;
+    double auc = 0, ap = 0, ndcg = 0, prec = 0, recall = 0, rr = 0;
+    int64_t usersWithTest = 0, usersWithList = 0;
+    std::vector<double> gains;
+    std::vector<std::pair<uint64_t, int32_t>> hashOrder;
+    for (int u = 0; u < numUsers; ++u) {
+        const auto& lst = rec.lists[(size_t)u];
+        const int len = (int)std::min<size_t>(lst.size(), (size_t)topN);
+        for (int t = 0; t < len; ++t) {
+            const int item = lst[(size_t)t].key;
+            listed[(size_t)item]++;
+            if (purchases[(size_t)item] > 0) novelty += -std::log((double)purchases[(size_t)item] / numUsers);
+        }
+        const int64_t tb = test.rowptr[(size_t)u], te = test.rowptr[(size_t)u + 1];
+        const int64_t nTest = te - tb;
+        if (nTest <= 0) continue;
+        ++usersWithTest;
+        auto testValue = [&](int item, double* v) {
+            const int32_t* b = test.col.data() + tb;
+            const int32_t* e = test.col.data() + te;
+            const int32_t* f = std::lower_bound(b, e, item);
+            if (f == e || *f != item) return false;
+            if (v) *v = test.val[(size_t)(f - test.col.data())];
+            return true;
+        };
+        int hits = 0, misses = 0;
+        double precSum = 0.0, dcg = 0.0;
+        bool firstHit = true;
+        gains.clear();
+        for (int t = 0; t < len; ++t) {
+            double v = 0.0;
+            if (!testValue(lst[(size_t)t].key, &v)) { ++misses; continue; }
+            ++hits;
+            precSum += 1.0 * hits / (t + 1);
+            if (firstHit) { rr += 1.0 / (t + 1.0); firstHit = false; }
+            dcg += v / (std::log((double)(t + 2)) / std::log(2.0));
+            gains.push_back(v);
+        }
+        prec += hits / (topN + 0.0);
+        recall += hits / (nTest + 0.0);
+        if (len != 0) { ap += precSum / (double)(nTest < len ? nTest : len); ++usersWithList; }
+        if (!gains.empty() && dcg != 0.0) {
+            std::sort(gains.begin(), gains.end(), std::greater<double>());
+            double idcg = 0.0;
+            for (size_t t = 0; t < gains.size(); ++t) idcg += gains[t] / (std::log((double)(t + 2)) / std::log(2.0));
+            if (idcg != 0.0) ndcg += dcg / idcg;
+        }
+        // AUC: items never scored (numItems - |train row| - list length) rank below every listed item
+        const int64_t dropped = (int64_t)numItems - (train.rowptr[(size_t)u + 1] - train.rowptr[(size_t)u]) - len;
+        const int64_t pairs = ((dropped + len) - hits) * (int64_t)hits;
+        if (pairs == 0) { auc += 0.5; continue; }
+        uint32_t cap = 16;
+        while ((double)nTest > 0.75 * (double)cap) cap <<= 1;
+        hashOrder.clear();
+        for (int64_t e = tb; e < te; ++e) {
+            const uint32_t h = (uint32_t)test.col[(size_t)e];
+            hashOrder.push_back({((uint64_t)((h ^ (h >> 16)) & (cap - 1)) << 32) | (uint32_t)(e - tb), test.col[(size_t)e]});
+        }
+        std::sort(hashOrder.begin(), hashOrder.end());
+        int64_t correct = 0;
+        int seenHits = 0;
+        for (const auto& o : hashOrder) {
+            bool inList = false;
+            for (int t = 0; t < len; ++t) if (lst[(size_t)t].key == o.second) { inList = true; break; }
+            if (inList) ++seenHits; else correct += seenHits;
+        }
+        correct += (int64_t)seenHits * (dropped - misses);
+        auc += (correct + 0.0) / (double)pairs;
+    }
+    double entropy = 0.0;
+    for (int i = 0; i < numItems; ++i)
+        if (listed[(size_t)i] > 0) { const double p = (double)listed[(size_t)i] / numUsers; entropy += p * (-std::log(p)); }
+    const std::string suffix = " top " + std::to_string(topN);
+    (*measures)["AUC" + suffix] = usersWithTest ? auc / usersWithTest : 0.0;
+    (*measures)["AP" + suffix] = usersWithList ? ap / usersWithList : 0.0;
+    (*measures)["NDCG" + suffix] = usersWithTest ? ndcg / usersWithTest : 0.0;
+    (*measures)["PRECISION" + suffix] = usersWithTest ? prec / usersWithTest : 0.0;
+    (*measures)["RECALL" + suffix] = usersWithTest ? recall / usersWithTest : 0.0;
+    (*measures)["RR" + suffix] = usersWithTest ? rr / usersWithTest : 0.0;
+    (*measures)["Novelty" + suffix] = novelty / (numUsers * std::log(2.0));
+    (*measures)["Entropy" + suffix] = entropy / std::log(2.0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // TextDataModel: text file -> flat CSR -> ratio split
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
@@ -831,6 +934,7 @@ void RecommenderJob::runCrossValidation() {
         if (conf.getBoolean("rec.eval.enable", true)) {
             if (ranking && recommender->rankingTopN() <= 64) recommendedList = recommender->recommendRankAndEvaluate(test, &evaluatedMap);
             else recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
+            if (ranking && evaluatedMap.empty()) evaluateRanking(train, test, recommendedList, recommender->rankingTopN(), &evaluatedMap);
             if (!ranking) {
                 evaluatedMap["RMSE"] = evaluateRMSE(test, recommendedList);
                 evaluatedMap["MAE"] = evaluateMAE(test, recommendedList);
@@ -872,6 +976,7 @@ void RecommenderJob::runJob() {
     if (conf.getBoolean("rec.eval.enable", true)) {                                          // :205-271
         if (ranking && recommender->rankingTopN() <= 64) recommendedList = recommender->recommendRankAndEvaluate(test, &evaluatedMap);
         else recommendedList = ranking ? recommender->recommendRank() : recommender->recommendRating(test);
+        if (ranking && evaluatedMap.empty()) evaluateRanking(train, test, recommendedList, recommender->rankingTopN(), &evaluatedMap);   // topN > 64
         if (!ranking) {
             evaluatedMap["RMSE"] = evaluateRMSE(test, recommendedList);             // eval/Measure.java:100-107: RMSE, MSE, MAE, MPE
             evaluatedMap["MAE"] = evaluateMAE(test, recommendedList);

@@ -207,6 +207,9 @@ double evaluateRMSE(const SequentialAccessSparseMatrix& test, const RecommendedL
 double evaluateMAE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended);
 // eval/rating/MSEEvaluator.java:33-66, MPEEvaluator.java:33-73 (share of entries with |error| > rec.measure.mpe, default 0.01)
 double evaluateMSE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended);
+// the eight default ranking measures (eval/Measure.java:76-93) on the host; keys "<MEASURE> top <N>" like the job's log lines
+void evaluateRanking(const SequentialAccessSparseMatrix& train, const SequentialAccessSparseMatrix& test, const RecommendedList& recommended,
+                     int topN, std::map<std::string, double>* measures);
 double evaluateMPE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended, double mpe);
 
 // data/model/TextDataModel.java + data/convertor/TextDataConvertor.java:136-200 + math/structure/DataFrame.java:237-261,370-379

@@ -118,6 +118,28 @@ LRH_API int lrh_probe_rating_measures(int32_t U, int32_t I, const int64_t* rowpt
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
+// the eight default ranking measures over flat CSR train / test and padded lists [U x topn] (counts[u] valid entries):
+// out = AUC, AP, NDCG, PRECISION, RECALL, RR, Novelty, Entropy
+LRH_API int lrh_probe_ranking_measures(int32_t U, int32_t I, const int64_t* tr_rowptr, const int32_t* tr_col, const int64_t* te_rowptr,
+                                       const int32_t* te_col, const double* te_val, int32_t topn, const int32_t* items,
+                                       const int32_t* counts, double* out) {
+    try {
+        SequentialAccessSparseMatrix tr, te;
+        tr.numRows = te.numRows = U; tr.numCols = te.numCols = I;
+        tr.rowptr.assign(tr_rowptr, tr_rowptr + U + 1); tr.col.assign(tr_col, tr_col + tr_rowptr[U]); tr.val.assign((size_t)tr_rowptr[U], 1.0);
+        te.rowptr.assign(te_rowptr, te_rowptr + U + 1); te.col.assign(te_col, te_col + te_rowptr[U]); te.val.assign(te_val, te_val + te_rowptr[U]);
+        RecommendedList rec;
+        for (int u = 0; u < U; ++u) {
+            rec.addList();
+            for (int t = 0; t < counts[u]; ++t) rec.add(u, items[(int64_t)u * topn + t], 0.0);
+        }
+        std::map<std::string, double> m;
+        evaluateRanking(tr, te, rec, topn, &m);
+        static const char* names[8] = {"AUC", "AP", "NDCG", "PRECISION", "RECALL", "RR", "Novelty", "Entropy"};
+        for (int i = 0; i < 8; ++i) out[i] = m[std::string(names[i]) + " top " + std::to_string(topn)];
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 // ---- data model alone (no GPU needed): properties -> TextDataModel.buildDataModel() -> flat CSR arrays
 struct DataModelBox { std::unique_ptr<TextDataModel> dm; std::string tmp; };
 LRH_API void* lrh_datamodel_build(const char* properties_text) {

@@ -81,3 +81,37 @@ def test_default_rating_measures(H, O):
     assert out[3] == np.count_nonzero(np.abs(d) > 0.01) / te.nnz and 0.5 < out[3] < 0.75
     rc = H.lrh_probe_rating_measures(te.U, te.I, te.rowptr.ctypes.data, te.col.ctypes.data, te.val.ctypes.data, pred.ctypes.data, 0.75, out.ctypes.data)
     assert rc == 0 and out[3] == np.count_nonzero(np.abs(d) > 0.75) / te.nnz
+
+
+def test_host_ranking_measures_match_the_oracle(H, O):
+    """the host evaluators that take over when rec.recommender.ranking.topn > 64 (the device evaluator keeps 64 entries per
+    thread): all eight measures equal the oracle's on random train / test splits and random lists, topN 5 ... 100"""
+    from conftest import rng_csr
+    H.lrh_probe_ranking_measures.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(4)
+    for U, I, dens, topn in [(60, 300, 0.08, 10), (40, 500, 0.1, 100), (25, 70000, 0.001, 5), (30, 200, 0.3, 80)]:
+        full = rng_csr(O, U, I, dens, int(rng.integers(1, 1000)))
+        flags = rng.random(full.nnz) < 0.7
+        tr, te = full.select(flags), full.select(~flags)
+        items = np.zeros((U, topn), np.int32)
+        counts = np.zeros(U, np.int32)
+        for u in range(U):
+            cand = np.setdiff1d(np.arange(I), tr.col[tr.rowptr[u]:tr.rowptr[u + 1]])
+            n = int(min(topn, cand.shape[0], rng.integers(0, topn + 1)))
+            # half of the picks come from the test row so that hits occur
+            trow = te.col[te.rowptr[u]:te.rowptr[u + 1]]
+            pick = list(rng.permutation(trow)[:n // 2])
+            rest = np.setdiff1d(cand, pick)
+            pick += list(rng.permutation(rest)[:n - len(pick)])
+            pick = rng.permutation(pick)
+            items[u, :len(pick)] = pick
+            counts[u] = len(pick)
+        exp = O.eval_ranking(te, tr, topn, items, counts)
+        out = np.zeros(8)
+        rc = H.lrh_probe_ranking_measures(U, I, tr.rowptr.ctypes.data, tr.col.ctypes.data, te.rowptr.ctypes.data, te.col.ctypes.data,
+                                          te.val.ctypes.data, topn, items.ctypes.data, counts.ctypes.data, out.ctypes.data)
+        assert rc == 0
+        got = dict(zip(("AUC", "AP", "NDCG", "Precision", "Recall", "RR", "Novelty", "Entropy"), out.tolist()))
+        for name in O.RANKING_MEASURES:
+            assert abs(got[name] - exp[name]) <= 1e-12 * max(1.0, abs(exp[name])), (name, got[name], exp[name], U, I, topn)
+        assert got["Precision"] > 0 and got["AUC"] > 0
