@@ -289,7 +289,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_epoch_per_gpu": BYTES_PER_UPDATE * nnz,
                          "note": "algorithmic bytes = SURVEY 8(d): 1052 B per update, no cache credit. frac > 1 means the kernel "
                                  "moves less than that model: the 42 MB factor set is resident in the 126 MB L2 and item-run tiles "
-                                 "read/update a popular item's row once per 8 ratings; DRAM bytes per launch (ncu) are in `traffic`, "
+                                 "read/update a popular item's row once per 8-32 ratings; DRAM bytes per launch (ncu) are in `traffic`, "
                                  "the binding unit is L2 (profiles/r01_sgd_kernel_ncu_summary.md)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
