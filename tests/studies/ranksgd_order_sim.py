@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """CPU study behind DESIGN.md 4.4b2 (i): RankSGD on config C1 with the ORACLE's sequential arithmetic, varying only the order in
 which the train entries are visited (negatives drawn by popularity with numpy; 30 epochs, lr 0.01, k = 10).
-    python tools/ranksgd_order_sim.py        -> one line per order: final loss, Precision@10 on the C1 test split
+    python tests/studies/ranksgd_order_sim.py        -> one line per order: final loss, Precision@10 on the C1 test split
 Orders: csr (the reference), shuffled (fresh permutation per epoch), fixedshuffle (one permutation), hotfirst (the device
 stream walked front to back: entries of items with >= 128 ratings first, then the rest)."""
 import os
@@ -9,7 +9,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 
