@@ -8,6 +8,8 @@ Outputs
         on java.util.Random(seed=1), plus the RNG state right after the split (so the Gaussian
         factor init of MatrixFactorizationRecommender.setup can be replayed anywhere).
   matrix4by4.txt         : copy of the reference's 13-line loader fixture data/test/datamodeltest/matrix4by4.txt
+  datamodeltest/         : the other DATA files of the reference's loader / splitter tests (UIRT, CSV, 4x4A, ratings-date.txt,
+        the test-convert-dir tree), byte for byte
   oracle_c1.json         : the oracle's own results on C1 (regression pins; NOT reference outputs --
         the Java reference cannot run here, parity is unpinned).
 """
@@ -40,6 +42,18 @@ def main():
                         val=full.val.astype(np.int8), flags=flags,
                         rng_seed=np.uint64(seed.value), rng_have=np.int32(have.value), rng_nextg=np.float64(nextg.value))
     shutil.copyfile(REF + "/data/test/datamodeltest/matrix4by4.txt", os.path.join(HERE, "matrix4by4.txt"))
+    # the other data files the reference's loader / splitter tests run on (TextDataModelTestCase, *DataSplitterTestCase)
+    dm = os.path.join(HERE, "datamodeltest")
+    for rel in ("matrix4by4-date.txt", "matrix4by4A.txt", "testCSV.txt", "ratings-date.txt"):
+        os.makedirs(dm, exist_ok=True)
+        shutil.copyfile(REF + "/data/test/datamodeltest/" + rel, os.path.join(dm, rel))
+    for rel in ("sytTest4by4.txt", "subdir1/sytTest4by4A.txt", "subdir2/sytTest4by4.txt"):
+        dst = os.path.join(dm, "test-convert-dir", rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(REF + "/data/test/test-convert-dir/" + rel, dst)
+    for root, _, files in os.walk(dm):
+        for f in files:
+            os.chmod(os.path.join(root, f), 0o644)
 
     tr, te = full.select(flags == 1), full.select(flags == 0)
     mu, mn, mx = O.matrix_setup(tr)
@@ -57,6 +71,14 @@ def main():
     done, losses = O.train(O.PMF, tr, 6, P, Q, None, None, mu, 0.01, 0.01, 0.08, 0.08, 0.0, 70)
     rmse, mae = O.eval_rating(O.PMF, te, 6, P, Q, None, None, mu, mn, mx)
     out["pmf"] = {"iters": done, "loss_1": losses[0], "loss_70": losses[-1], "rmse": rmse, "mae": mae}
+    # RankSGD on the same split (ranksgd-test.properties: k=10, 30 iters, lr 0.01f), sequential reference order + RNG
+    L.lro_rng_set_state(seed.value, have.value, nextg.value)
+    P, Q, _, _ = O.mf_setup(tr.U, tr.I, 10, False)
+    done, losses = O.train(O.RANKSGD, tr, 10, P, Q, None, None, 0.0, 0.01, 0.01, 0.01, 0.01, 0.0, 30)
+    users = np.flatnonzero(np.diff(te.rowptr) > 0).astype(np.int32)
+    items, _, counts = O.recommend_rank(O.BPR, tr.U, tr.I, 10, P, Q, None, None, 0.0, tr, 10, users=users)
+    hits = sum(np.intersect1d(items[r, :counts[r]], te.col[te.rowptr[u]:te.rowptr[u + 1]]).shape[0] for r, u in enumerate(users))
+    out["ranksgd"] = {"iters": done, "loss_1": losses[0], "loss_30": losses[-1], "precision_at_10": hits / (10.0 * users.shape[0])}
     with open(os.path.join(HERE, "oracle_c1.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out, indent=1))

@@ -497,3 +497,17 @@ def test_c1_regression_pins(O, c1):
     assert abs(losses[0] - pins["biasedmf"]["loss_1"]) < 1e-6 and abs(losses[-1] - pins["biasedmf"]["loss_100"]) < 1e-6
     assert abs(rmse - pins["biasedmf"]["rmse"]) < 1e-12 and abs(mae - pins["biasedmf"]["mae"]) < 1e-12
     assert 0.90 < rmse < 0.96 and 0.71 < mae < 0.76     # sanity: the range LibRec documents for BiasedMF on ml-100k
+
+
+def test_c1_ranksgd_regression_pins(O, c1):
+    """ranksgd-test.properties on C1 through the oracle (reference order, java.util.Random negatives) == the committed pins"""
+    pins = c1["pins"]["ranksgd"]; tr, te = c1["train"], c1["test"]
+    O.lib().lro_rng_set_state(*c1["rng_state"])
+    P, Q, _, _ = O.mf_setup(tr.U, tr.I, 10, False)
+    done, losses = O.train(O.RANKSGD, tr, 10, P, Q, None, None, 0.0, 0.01, 0.01, 0.01, 0.01, 0.0, 30)
+    assert done == pins["iters"] == 30
+    assert abs(losses[0] - pins["loss_1"]) < 1e-6 and abs(losses[-1] - pins["loss_30"]) < 1e-6
+    users = np.flatnonzero(np.diff(te.rowptr) > 0).astype(np.int32)
+    items, _, counts = O.recommend_rank(O.BPR, tr.U, tr.I, 10, P, Q, None, None, 0.0, tr, 10, users=users)
+    hits = sum(np.intersect1d(items[r, :counts[r]], te.col[te.rowptr[u]:te.rowptr[u + 1]]).shape[0] for r, u in enumerate(users))
+    assert abs(hits / (10.0 * users.shape[0]) - pins["precision_at_10"]) < 1e-12
