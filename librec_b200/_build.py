@@ -23,7 +23,7 @@ def _nvcc():
 
 
 def _sources():
-    return sorted(os.path.join(_SRC_DIR, f) for f in os.listdir(_SRC_DIR) if f.endswith((".cu", ".cuh")))
+    return sorted(os.path.join(_SRC_DIR, f) for f in os.listdir(_SRC_DIR) if f.endswith((".cu", ".cuh", ".inc")))
 
 
 def is_stale():

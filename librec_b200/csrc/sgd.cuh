@@ -134,237 +134,7 @@ __device__ __forceinline__ void block_loss_commit(double v, double* out) {
 // tile; chosen by the launcher when the user factors are no longer small, see sgd_launch_gv)
 template <int G, int V, bool BIASED, bool ATOMIC, bool TRACK = false>
 __global__ void __launch_bounds__(256, (G * V <= 16 && !TRACK) ? 4 : ((G * V <= 32) ? 3 : 1)) sgd_rating_epoch_kernel(SgdParams p) {
-    constexpr int RPS = 32 / G;  // ratings per warp step
-    constexpr int STEPS = G;     // steps per 32-rating tile
-    const int lane = threadIdx.x & 31;
-    const int sub = lane % G;
-    const int grp = lane / G;
-    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t ntiles = (p.n + 31) >> 5;
-    const float lr = p.lr, reg_u = p.reg_u, reg_i = p.reg_i, reg_b = p.reg_b, mu = p.mu;
-    // running max(1, mean |p_u|^2): the epoch-start value, then the warp's last run tile.  The launcher picks the
-    // TRACK variant only when that mean exceeds 0.25; below, the factor is 1 and costs no register
-    float pn2 = (TRACK && p.pnorm2) ? fmaxf(1.f, __ldg(p.pnorm2)) : 1.f;
-    double loss_d = 0.0;
-
-    int64_t tile = gwarp;
-    int32_t u_n = -1, i_n = 0;
-    float r_n = 0.f;
-    if (tile < ntiles) {
-        const int64_t e = ((int64_t)(((unsigned long long)tile * (unsigned long long)p.tile_mul) % (unsigned long long)ntiles) << 5) + lane;
-        if (e < p.n) { u_n = __ldcs(p.su + e); i_n = __ldcs(p.si + e); r_n = __ldcs(p.sr + e); }
-    }
-    for (; tile < ntiles; tile += nwarps) {
-        const int32_t u_l = u_n, i_l = i_n;
-        const float r_l = r_n;
-        {   // prefetch the next tile's triples
-            const int64_t tn = tile + nwarps;
-            u_n = -1; i_n = 0; r_n = 0.f;
-            if (tn < ntiles) {
-                const int64_t e = ((int64_t)(((unsigned long long)tn * (unsigned long long)p.tile_mul) % (unsigned long long)ntiles) << 5) + lane;
-                if (e < p.n) { u_n = __ldcs(p.su + e); i_n = __ldcs(p.si + e); r_n = __ldcs(p.sr + e); }
-            }
-        }
-        float loss_f = 0.f;
-        const int32_t i0 = __shfl_sync(0xffffffffu, i_l, 0);
-        if (__all_sync(0xffffffffu, u_l >= 0 && i_l == i0)) {
-            // ---- item-run tile: one item, 32 distinct users.  The item row is re-read and its accumulated delta
-            // flushed every HOT_CHUNK steps (8 ratings), which bounds the staleness a warp adds for its item.
-            constexpr int HOT_CHUNK = (STEPS >= 4) ? STEPS / 4 : 1;
-            float4 pn[V];
-            float bun = 0.f;
-            // x = lr * (ratings of this item in flight) * max(1, mean |p_u|^2): curvature 1 for the bias, |p_u|^2 along
-            // p_u for the row; the item-side step of the tile is scaled by (1 - exp(-x)) / x
-            float damp = 1.f, psq = 0.f;
-            // flush period in steps: 8 ratings by default; 16 / the whole tile for items whose degree makes that an
-            // equally small share (<= 1/128) -- every flush of a hot item is 16 same-line REDs that serialise in L2
-            int flush_steps = HOT_CHUNK;
-            if (p.item_deg) {
-                const uint32_t deg = __ldg(p.item_deg + i0);
-                // a flush is a mini-batch of its own: lengthen it only while lr * curvature * (ratings per flush) <= 1/8,
-                // which leaves room for |p_u|^2 growing inside the epoch (PMF on un-centred ratings: 1e-4 -> 8 within the
-                // first two epochs; config C4 rolled back twice with 32-rating flushes at lr 0.01)
-                const float lrc = lr * pn2;
-                if (deg >= p.hot_flush_deg) {
-                    if (deg >= 2u * p.hot_flush_deg && lrc * 32.f <= 0.125f) flush_steps = STEPS;
-                    else if (STEPS >= 2 * HOT_CHUNK && lrc * (float)(2 * HOT_CHUNK * RPS) <= 0.125f) flush_steps = 2 * HOT_CHUNK;
-                }
-                // inflight_frac counts HOT_CHUNK steps per warp; a longer flush period keeps that many more in flight,
-                // and the warp's own flush period is in flight whatever the grid
-                const float x = lrc * fmaxf((float)deg * p.inflight_frac * (float)(flush_steps / HOT_CHUNK), (float)(flush_steps * RPS));
-                if (x > 1e-3f) damp = (1.f - __expf(-x)) / x;
-            }
-            int32_t un = __shfl_sync(0xffffffffu, u_l, grp);
-            float rn = __shfl_sync(0xffffffffu, r_l, grp);
-#pragma unroll
-            for (int v = 0; v < V; ++v) pn[v] = ldcg4(p.P + (int64_t)un * p.ld + (v * G + sub) * 4);
-            if (BIASED && sub == 0) bun = __ldcg(p.bu + un);
-#pragma unroll 1
-            for (int c0 = 0; c0 < STEPS; c0 += flush_steps) {
-                float4 q[V], dq[V];
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    q[v] = ldcg4(p.Q + (int64_t)i0 * p.ld + (v * G + sub) * 4);
-                    dq[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                const float bi0 = BIASED ? __ldcg(p.bi + i0) : 0.f;
-                float dbi = 0.f;
-#pragma unroll 1
-                for (int c1 = c0; c1 < c0 + flush_steps; c1 += HOT_CHUNK) {
-#pragma unroll
-                for (int sc = 0; sc < HOT_CHUNK; ++sc) {
-                    const int s = c1 + sc;
-                    float4 pc[V];
-#pragma unroll
-                    for (int v = 0; v < V; ++v) pc[v] = pn[v];
-                    const float buc = bun, rc = rn;
-                    const int32_t uc = un;
-                    if (s + 1 < STEPS) {
-                        const int src = (s + 1) * RPS + grp;
-                        un = __shfl_sync(0xffffffffu, u_l, src);
-                        rn = __shfl_sync(0xffffffffu, r_l, src);
-#pragma unroll
-                        for (int v = 0; v < V; ++v) pn[v] = ldcg4(p.P + (int64_t)un * p.ld + (v * G + sub) * 4);
-                        if (BIASED && sub == 0) bun = __ldcg(p.bu + un);
-                    }
-                    float part = 0.f;
-#pragma unroll
-                    for (int v = 0; v < V; ++v) part += dot4(pc[v], q[v]);
-                    float pred = group_sum<G>(part);
-                    if (BIASED) pred += __shfl_sync(0xffffffffu, buc, grp * G) + bi0 + mu;
-                    const float err = rc - pred;
-                    float reg_acc = 0.f;
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const float4 a = pc[v], b = q[v];
-                        float4 dp;
-                        dp.x = lr * (err * b.x - reg_u * a.x); dq[v].x += lr * (err * a.x - reg_i * b.x);
-                        dp.y = lr * (err * b.y - reg_u * a.y); dq[v].y += lr * (err * a.y - reg_i * b.y);
-                        dp.z = lr * (err * b.z - reg_u * a.z); dq[v].z += lr * (err * a.z - reg_i * b.z);
-                        dp.w = lr * (err * b.w - reg_u * a.w); dq[v].w += lr * (err * a.w - reg_i * b.w);
-                        apply4<ATOMIC>(p.P + (int64_t)uc * p.ld + (v * G + sub) * 4, a, dp);
-                        const float aa = dot4(a, a);
-                        if (TRACK) psq += aa;
-                        reg_acc += reg_u * aa + reg_i * dot4(b, b);
-                    }
-                    if (sub == 0) {
-                        reg_acc += err * err;
-                        if (BIASED) {
-                            apply1<ATOMIC>(p.bu + uc, buc, lr * (err - reg_b * buc));
-                            dbi += lr * (err - reg_b * bi0);
-                            reg_acc += reg_b * (buc * buc + bi0 * bi0);
-                        }
-                    }
-                    loss_f += reg_acc;
-                }
-                }
-                // one update of the item row per flush period
-#pragma unroll
-                for (int m = G; m < 32; m <<= 1) {
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        dq[v].x += __shfl_xor_sync(0xffffffffu, dq[v].x, m); dq[v].y += __shfl_xor_sync(0xffffffffu, dq[v].y, m);
-                        dq[v].z += __shfl_xor_sync(0xffffffffu, dq[v].z, m); dq[v].w += __shfl_xor_sync(0xffffffffu, dq[v].w, m);
-                    }
-                    dbi += __shfl_xor_sync(0xffffffffu, dbi, m);
-                }
-                if (grp == 0) {
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        dq[v].x *= damp; dq[v].y *= damp; dq[v].z *= damp; dq[v].w *= damp;
-                        apply4<ATOMIC>(p.Q + (int64_t)i0 * p.ld + (v * G + sub) * 4, q[v], dq[v]);
-                    }
-                    if (BIASED && sub == 0) apply1<ATOMIC>(p.bi + i0, bi0, dbi * damp);
-                }
-            }
-            if (TRACK && p.item_deg) {       // |p_u|^2 of the 32 users just seen -> curvature estimate for this warp's next run tile
-#pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) psq += __shfl_xor_sync(0xffffffffu, psq, m);
-                pn2 = fmaxf(1.f, psq * (1.f / 32.f));
-            }
-            loss_d += (double)loss_f;
-            continue;
-        }
-        float4 pn[V], qn[V];
-        float bun = 0.f, bin = 0.f;
-        int32_t un, in_;
-        float rn;
-        // rows of step 0
-        un = __shfl_sync(0xffffffffu, u_l, grp);
-        in_ = __shfl_sync(0xffffffffu, i_l, grp);
-        rn = __shfl_sync(0xffffffffu, r_l, grp);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            pn[v] = make_float4(0.f, 0.f, 0.f, 0.f); qn[v] = pn[v];
-            if (un >= 0) {
-                pn[v] = ldcg4(p.P + (int64_t)un * p.ld + (v * G + sub) * 4);
-                qn[v] = ldcg4(p.Q + (int64_t)in_ * p.ld + (v * G + sub) * 4);
-            }
-        }
-        if (BIASED && un >= 0 && sub == 0) { bun = __ldcg(p.bu + un); bin = __ldcg(p.bi + in_); }
-
-#pragma unroll
-        for (int s = 0; s < STEPS; ++s) {
-            float4 pc[V], qc[V];
-#pragma unroll
-            for (int v = 0; v < V; ++v) { pc[v] = pn[v]; qc[v] = qn[v]; }
-            const float buc = bun, bic = bin;
-            const int32_t uc = un, ic = in_;
-            const float rc = rn;
-            if (s + 1 < STEPS) {
-                const int src = (s + 1) * RPS + grp;
-                un = __shfl_sync(0xffffffffu, u_l, src);
-                in_ = __shfl_sync(0xffffffffu, i_l, src);
-                rn = __shfl_sync(0xffffffffu, r_l, src);
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    pn[v] = make_float4(0.f, 0.f, 0.f, 0.f); qn[v] = pn[v];
-                    if (un >= 0) {
-                        pn[v] = ldcg4(p.P + (int64_t)un * p.ld + (v * G + sub) * 4);
-                        qn[v] = ldcg4(p.Q + (int64_t)in_ * p.ld + (v * G + sub) * 4);
-                    }
-                }
-                bun = 0.f; bin = 0.f;
-                if (BIASED && un >= 0 && sub == 0) { bun = __ldcg(p.bu + un); bin = __ldcg(p.bi + in_); }
-            }
-            float part = 0.f;
-#pragma unroll
-            for (int v = 0; v < V; ++v) part += dot4(pc[v], qc[v]);
-            float pred = group_sum<G>(part);
-            if (BIASED) {
-                // bias values live on sub-lane 0 of the group; broadcast inside the group
-                const float bsum = __shfl_sync(0xffffffffu, buc + bic, grp * G);
-                pred += bsum + mu;
-            }
-            const float err = rc - pred;
-            if (uc >= 0) {
-                float reg_acc = 0.f;
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const float4 a = pc[v], b = qc[v];
-                    float4 dp, dq;
-                    dp.x = lr * (err * b.x - reg_u * a.x); dq.x = lr * (err * a.x - reg_i * b.x);
-                    dp.y = lr * (err * b.y - reg_u * a.y); dq.y = lr * (err * a.y - reg_i * b.y);
-                    dp.z = lr * (err * b.z - reg_u * a.z); dq.z = lr * (err * a.z - reg_i * b.z);
-                    dp.w = lr * (err * b.w - reg_u * a.w); dq.w = lr * (err * a.w - reg_i * b.w);
-                    apply4<ATOMIC>(p.P + (int64_t)uc * p.ld + (v * G + sub) * 4, a, dp);
-                    apply4<ATOMIC>(p.Q + (int64_t)ic * p.ld + (v * G + sub) * 4, b, dq);
-                    reg_acc += reg_u * dot4(a, a) + reg_i * dot4(b, b);
-                }
-                if (sub == 0) {
-                    reg_acc += err * err;
-                    if (BIASED) {
-                        apply1<ATOMIC>(p.bu + uc, buc, lr * (err - reg_b * buc));
-                        apply1<ATOMIC>(p.bi + ic, bic, lr * (err - reg_b * bic));
-                        reg_acc += reg_b * (buc * buc + bic * bic);
-                    }
-                }
-                loss_f += reg_acc;
-            }
-        }
-        loss_d += (double)loss_f;
-    }
+#include "sgd_rating_body.inc"
     block_loss_commit(loss_d, p.loss);
 }
 

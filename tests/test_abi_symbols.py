@@ -51,7 +51,7 @@ def test_product_never_imports_oracle():
     bad = []
     for dp, _, fs in os.walk(os.path.join(ROOT, "librec_b200")):
         for f in fs:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".inc", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 if re.search(r"(from|import)\s+oracle|lrk_oracle|lro_", txt):
                     bad.append(f)
