@@ -15,6 +15,7 @@
 #include "lrk_common.cuh"
 #include "staging.cuh"
 #include "sgd.cuh"
+#include "dsgd_fused.cuh"
 #include <nccl.h>
 #include <dlfcn.h>
 #include <vector>
@@ -90,6 +91,7 @@ struct DsgdState {
     // LRK_DSGD_TRACE=1: events around every sub-epoch kernel / ring exchange of the last epoch
     std::vector<cudaEvent_t> trace_ev;
     int trace = -1;
+    DsgdFused fused;                    // experimental one-kernel epoch (dsgd_fused.cuh), LRK_DSGD_FUSED=1
 };
 
 __global__ void item_hist_kernel(const int32_t* __restrict__ col, int64_t nnz, unsigned long long* __restrict__ cnt) {
@@ -139,6 +141,7 @@ __global__ void dsgd_unpack_block_kernel(float* __restrict__ Q, float* __restric
 static void dsgd_release(lrk_handle_s* h) {
     DsgdState* s = (DsgdState*)h->dsgd;
     if (s) {
+        dsgd_fused_release(&s->fused);
         cudaFree(s->qbuf[0]); cudaFree(s->qbuf[1]); cudaFree(s->d_bounds);
         delete s;
         h->dsgd = nullptr;
@@ -319,6 +322,147 @@ static int dsgd_set_factors(lrk_handle_s* h, const double* P, const double* Q, c
     return LRK_OK;
 }
 
+// ---- experimental fused epoch (dsgd_fused.cuh): IPC mapping of the ring neighbours, then one cooperative launch per epoch
+static int dsgd_fused_map(lrk_handle_s* h, DsgdState* s) {
+    NcclApi* n = nccl_api();
+    DsgdFused* f = &s->fused;
+    cudaStream_t st = h->stream;
+    const int world = h->world, rank = h->rank;
+    if (f->mapped && f->my_qbuf[0] == s->qbuf[0] && f->my_qbuf[1] == s->qbuf[1]) return LRK_OK;
+    dsgd_fused_release(f);
+    LRK_CUDA(h, cudaMalloc((void**)&f->d_flags, sizeof(unsigned long long) * 4));
+    LRK_CUDA(h, cudaMalloc((void**)&f->d_abort, sizeof(int)));
+    LRK_CUDA(h, cudaMemsetAsync(f->d_flags, 0, sizeof(unsigned long long) * 4, st));
+    LRK_CUDA(h, cudaMemsetAsync(f->d_abort, 0, sizeof(int), st));
+    // handles of (qbuf[0], qbuf[1], flags) of every rank
+    cudaIpcMemHandle_t mine[3];
+    LRK_CUDA(h, cudaIpcGetMemHandle(&mine[0], s->qbuf[0]));
+    LRK_CUDA(h, cudaIpcGetMemHandle(&mine[1], s->qbuf[1]));
+    LRK_CUDA(h, cudaIpcGetMemHandle(&mine[2], f->d_flags));
+    const size_t hb = sizeof(cudaIpcMemHandle_t) * 3;
+    uint8_t *d_mine = nullptr, *d_all = nullptr;
+    LRK_CUDA(h, cudaMalloc((void**)&d_mine, hb));
+    LRK_CUDA(h, cudaMalloc((void**)&d_all, hb * (size_t)world));
+    std::vector<uint8_t> all(hb * (size_t)world);
+    cudaError_t e = cudaMemcpyAsync(d_mine, mine, hb, cudaMemcpyHostToDevice, st);
+    ncclResult_t nr = ncclSuccess;
+    if (e == cudaSuccess) nr = n->AllGather(d_mine, d_all, hb, ncclUint8, (ncclComm_t)h->comm, st);
+    if (e == cudaSuccess && nr == ncclSuccess) e = cudaMemcpyAsync(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && nr == ncclSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_mine); cudaFree(d_all);
+    LRK_NCCL(h, nr);
+    LRK_CUDA(h, e);
+    auto handle_of = [&](int r, int which) {
+        cudaIpcMemHandle_t v;
+        memcpy(&v, all.data() + hb * (size_t)r + sizeof(cudaIpcMemHandle_t) * (size_t)which, sizeof v);
+        return v;
+    };
+    auto open = [&](int r, int which, void** out) -> cudaError_t {
+        cudaError_t oe = cudaIpcOpenMemHandle(out, handle_of(r, which), cudaIpcMemLazyEnablePeerAccess);
+        if (oe == cudaSuccess) f->opened[f->n_opened++] = *out;
+        return oe;
+    };
+    const int prev = dsgd_send_peer(rank, world), next = dsgd_recv_peer(rank, world);
+    void *q0 = nullptr, *q1 = nullptr, *pf = nullptr, *nf = nullptr;
+    LRK_CUDA(h, open(prev, 0, &q0));
+    LRK_CUDA(h, open(prev, 1, &q1));
+    LRK_CUDA(h, open(prev, 2, &pf));
+    if (next == prev) nf = pf; else LRK_CUDA(h, open(next, 2, &nf));
+    f->peer_qbuf[0] = (float*)q0; f->peer_qbuf[1] = (float*)q1;
+    f->prev_flags = (unsigned long long*)pf; f->next_flags = (unsigned long long*)nf;
+    f->my_qbuf[0] = s->qbuf[0]; f->my_qbuf[1] = s->qbuf[1];
+    f->seq = 0;
+    f->mapped = true;
+    // nobody may push before every rank has zeroed its flags: one more collective as a barrier
+    LRK_NCCL(h, n->AllReduce(h->d_loss, h->d_loss, 1, ncclFloat64, ncclSum, (ncclComm_t)h->comm, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    return LRK_OK;
+}
+
+template <int G, int V>
+static int dsgd_fused_launch_gv(lrk_handle_s* h, DsgdState* s, DsgdFusedParams& fp, bool track) {
+    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    void* kern = nullptr;
+    if (biased) kern = track ? (void*)dsgd_fused_epoch_kernel<G, V, true, true> : (void*)dsgd_fused_epoch_kernel<G, V, true, false>;
+    else kern = track ? (void*)dsgd_fused_epoch_kernel<G, V, false, true> : (void*)dsgd_fused_epoch_kernel<G, V, false, false>;
+    int per_sm = 0;
+    LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)h->sm_count * per_sm;
+    for (int t = 0; t < h->world; ++t) {                       // staleness cap of the smallest non-empty segment (sgd_grid_for)
+        const int64_t n = fp.seg[t].n;
+        if (n <= 0) continue;
+        const int64_t stale_cap = (n / 16) / (8 * (int64_t)(32 / G) * 2);
+        if (stale_cap < grid) grid = stale_cap;
+    }
+    if (h->conc_div > 1) grid /= h->conc_div;
+    if (grid < 1) grid = 1;
+    for (int t = 0; t < h->world; ++t) {
+        const int64_t n = fp.seg[t].n > 0 ? fp.seg[t].n : 1;
+        fp.seg[t].inflight_frac = (float)((double)grid * 8.0 * (double)(32 / G > 8 ? 32 / G : 8) / (double)n);
+    }
+    void* args[] = {(void*)&fp};
+    LRK_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(256), args, 0, h->stream));
+    h->launches++;
+    (void)s;
+    return LRK_OK;
+}
+
+// true: the epoch's strata were run by the fused kernel (s->cur advanced like the loop would have); false: not applicable here
+static int dsgd_fused_epoch(lrk_handle_s* h, DsgdState* s, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, bool* done) {
+    *done = false;
+    DsgdFused* f = &s->fused;
+    if (f->enabled < 0) { const char* e = getenv("LRK_DSGD_FUSED"); f->enabled = e && atoi(e) ? 1 : 0; }
+    const int world = h->world;
+    if (!f->enabled || world < 2 || world > LRK_FUSED_MAX_WORLD || h->cfg.model == LRK_MODEL_BPR ||
+        h->cfg.update_mode != LRK_UPDATE_ATOMIC || h->V != 1 || h->G < 4)
+        return LRK_OK;
+    int coop = 0;
+    LRK_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->cfg.device));
+    if (!coop) return LRK_OK;
+    int rc = dsgd_fused_map(h, s);
+    if (rc) return rc;
+    DsgdFusedParams fp;
+    memset(&fp, 0, sizeof fp);
+    static const char* hf = getenv("LRK_SGD_HOT_FLUSH");
+    for (int t = 0; t < world; ++t) {
+        const int b = dsgd_block_at(h->rank, world, t);
+        const int64_t off = s->seg_off[(size_t)b], cnt = s->seg_off[(size_t)b + 1] - off;
+        SgdParams& sp = fp.seg[t];
+        sp.su = h->d_su + off; sp.si = h->d_si + off; sp.sr = h->d_sr + off; sp.n = cnt;
+        sp.P = h->P32; sp.bu = h->bu32;
+        sp.mu = (float)h->mu; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i; sp.reg_b = (float)reg_b;
+        sp.loss = h->d_loss; sp.ld = h->ld; sp.epoch = (uint32_t)epoch_idx;
+        sp.tile_mul = sgd_tile_mul(cnt);
+        sp.conc_div = h->conc_div;
+        sp.item_deg = h->d_item_deg ? h->d_item_deg + s->bounds[(size_t)b] : nullptr;
+        sp.pnorm2 = sp.item_deg ? h->d_pnorm2 : nullptr;
+        sp.hot_flush_deg = hf ? (atoi(hf) > 0 ? (uint32_t)atoi(hf) : 0xffffffffu) : 512u;
+    }
+    fp.qbuf[0] = s->qbuf[0]; fp.qbuf[1] = s->qbuf[1];
+    fp.peer_qbuf[0] = f->peer_qbuf[0]; fp.peer_qbuf[1] = f->peer_qbuf[1];
+    fp.ready = f->d_flags; fp.peer_free = f->d_flags + 2;
+    fp.prev_ready = f->prev_flags; fp.next_peer_free = f->next_flags + 2;
+    fp.seq0 = f->seq; fp.cur0 = s->cur; fp.world = world;
+    fp.buf_floats = (long long)s->buf_floats; fp.bi_off = (long long)s->max_blk * h->ld;
+    fp.abort = f->d_abort;
+    fp.spin_limit = 4000000000LL;                               // ~2 s at 2 GHz
+    const bool track = fp.seg[0].item_deg && (h->pnorm2_host > 0.25f || (h->pnorm2_host > 0.02f && h->pnorm2_host > 4.f * h->pnorm2_prev));
+    switch (h->G) {
+        case 4: rc = dsgd_fused_launch_gv<4, 1>(h, s, fp, track); break;
+        case 8: rc = dsgd_fused_launch_gv<8, 1>(h, s, fp, track); break;
+        case 16: rc = dsgd_fused_launch_gv<16, 1>(h, s, fp, track); break;
+        case 32: rc = dsgd_fused_launch_gv<32, 1>(h, s, fp, track); break;
+        default: return LRK_OK;
+    }
+    if (rc) return rc;
+    f->seq += (unsigned long long)world;
+    s->cur = (s->cur + world) & 1;
+    s->cur_block = dsgd_block_at(h->rank, world, world);
+    *done = true;
+    return LRK_OK;
+}
+
 static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, double* loss_out) {
     NcclApi* n = nccl_api();
     DsgdState* s = (DsgdState*)h->dsgd;
@@ -347,7 +491,9 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
         for (auto& ev : s->trace_ev) LRK_CUDA(h, cudaEventCreate(&ev));
     }
     if (s->trace) LRK_CUDA(h, cudaEventRecord(s->trace_ev[0], st));
-    for (int sub = 0; sub < world; ++sub) {
+    bool fused_done = false;
+    { int rc_f = dsgd_fused_epoch(h, s, lr, reg_u, reg_i, reg_b, epoch_idx, &fused_done); if (rc_f) return rc_f; }
+    for (int sub = 0; !fused_done && sub < world; ++sub) {
         const int b = dsgd_block_at(rank, world, sub);
         float* buf = s->qbuf[s->cur];
         const int64_t off = s->seg_off[(size_t)b], cnt = s->seg_off[(size_t)b + 1] - off;
@@ -390,6 +536,11 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     h->f64_valid = false;
     LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
     LRK_CUDA(h, cudaStreamSynchronize(st));
+    if (fused_done) {
+        int aborted = 0;
+        LRK_CUDA(h, cudaMemcpy(&aborted, s->fused.d_abort, sizeof(int), cudaMemcpyDeviceToHost));
+        if (aborted) return lrk_fail(h, LRK_ERR_NCCL, "lrk_sgd_epoch", "fused DSGD epoch: a ring neighbour did not answer within the spin limit", __FILE__, __LINE__);
+    }
     LRK_CUDA(h, cudaEventElapsedTime(&h->last_epoch_ms, h->ev0, h->ev1));
     {
         const double l_ = (h->cfg.model == LRK_MODEL_BPR ? 1.0 : 0.5) * h->h_loss[0];

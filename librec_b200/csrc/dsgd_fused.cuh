@@ -1,0 +1,123 @@
+// EXPERIMENTAL, OFF BY DEFAULT (LRK_DSGD_FUSED=1 turns it on): one persistent kernel per DSGD epoch with the ring exchange
+// inside it.  Written at the end of r01 from the measurements in DESIGN.md 5 / 8; it compiles, but it has NOT run on a GPU yet --
+// the default path is the sub-epoch loop of dsgd.cuh (SGD kernel + grouped ncclSend/ncclRecv per stratum).
+//
+// Why: after r01 a DSGD stratum runs at the whole-matrix rate, so what separates N GPUs from N x one GPU is per sub-epoch the
+// NCCL send/recv pair (0.026-0.03 ms when both ranks are in step), launch gaps and the wait for the slower neighbour.  NCCL's
+// copy kernels cannot overlap with the epoch kernel (it occupies every SM), so a second stream does not help.
+//
+// How: every rank maps its ring neighbours' block buffers and flag words with CUDA IPC (handles exchanged once through the NCCL
+// communicator).  The epoch kernel is launched cooperatively and loops over the G strata:
+//   wait   until the block for this stratum has arrived in my buffer b        (ready[b]     >= seq, written by rank+1)
+//   train  the stratum's COO segment against buffer b                          (sgd_rating_body.inc, the same tile code)
+//   grid.sync
+//   wait   until rank-1 no longer needs its buffer 1-b                         (peer_free[1-b] >= seq, written by rank-1)
+//   push   buffer b into rank-1's buffer 1-b with coalesced peer stores over NVLink; __threadfence_system; grid.sync
+//   signal rank-1: ready[1-b] = seq + 1 (st.release.sys);  rank+1: its buffer b here is free again (peer_free[b] = seq + 1)
+// and finally waits for the block of the NEXT epoch's first stratum, so that the buffer is complete when the kernel ends
+// (snapshot, all-gather in lrk_get_factors and the next launch read it).  seq = seq0 + stratum increases monotonically over the
+// epochs, so no flag is ever reset.  A spin that exceeds spin_limit cycles raises `abort` in every rank's own memory and the
+// remaining strata fall through (all grid.sync calls are still executed), the host then reports LRK_ERR_NCCL.
+#pragma once
+#include "lrk_common.cuh"
+#include "sgd.cuh"
+#include <cooperative_groups.h>
+
+#define LRK_FUSED_MAX_WORLD 8
+
+struct DsgdFusedParams {
+    SgdParams seg[LRK_FUSED_MAX_WORLD];     // per stratum: COO segment, n, tile_mul, degrees, in-flight share; Q / bi filled in-kernel
+    float* qbuf[2];                         // my rotating block buffers
+    float* peer_qbuf[2];                    // rank-1's buffers (push target)
+    unsigned long long* ready;              // mine [2]: written by rank+1
+    unsigned long long* peer_free;          // mine [2]: written by rank-1
+    unsigned long long* prev_ready;         // rank-1's ready[2]
+    unsigned long long* next_peer_free;     // rank+1's peer_free[2]
+    unsigned long long seq0;
+    int cur0, world;
+    long long buf_floats, bi_off;           // floats per buffer; offset of the bias slice (max_blk * ld)
+    int* abort;
+    long long spin_limit;                   // clock64 cycles
+};
+
+__device__ __forceinline__ unsigned long long lrk_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lrk_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// thread 0 of every CTA spins; returns false once any wait of this rank has timed out
+__device__ __forceinline__ bool lrk_fused_wait(const unsigned long long* flag, unsigned long long want, int* abort_flag, long long spin_limit) {
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (lrk_ld_acquire_sys(flag) < want) {
+            if (*(volatile int*)abort_flag) break;
+            if (clock64() - t0 > spin_limit) { atomicExch(abort_flag, 1); break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    return *(volatile int*)abort_flag == 0;
+}
+
+template <int G, int V, bool BIASED, bool TRACK>
+__global__ void __launch_bounds__(256, (G * V <= 16 && !TRACK) ? 4 : ((G * V <= 32) ? 3 : 1)) dsgd_fused_epoch_kernel(DsgdFusedParams fp) {
+    constexpr bool ATOMIC = true;
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gthreads = (long long)gridDim.x * blockDim.x;
+    for (int t = 0; t < fp.world; ++t) {
+        const int b = (fp.cur0 + t) & 1;
+        const unsigned long long seq = fp.seq0 + (unsigned long long)t;
+        bool ok = lrk_fused_wait(fp.ready + b, seq, fp.abort, fp.spin_limit);
+        if (ok) {
+            SgdParams p = fp.seg[t];
+            p.Q = fp.qbuf[b];
+            p.bi = fp.qbuf[b] + fp.bi_off;
+#include "sgd_rating_body.inc"
+            block_loss_commit(loss_d, p.loss);
+        }
+        __threadfence();
+        grid.sync();
+        ok = lrk_fused_wait(fp.peer_free + (b ^ 1), seq, fp.abort, fp.spin_limit);
+        if (ok) {
+            const float4* src = reinterpret_cast<const float4*>(fp.qbuf[b]);
+            float4* dst = reinterpret_cast<float4*>(fp.peer_qbuf[b ^ 1]);
+            const long long n4 = fp.buf_floats >> 2;
+            for (long long i = gtid; i < n4; i += gthreads) dst[i] = __ldcg(src + i);
+            for (long long i = (n4 << 2) + gtid; i < fp.buf_floats; i += gthreads) fp.peer_qbuf[b ^ 1][i] = __ldcg(fp.qbuf[b] + i);
+        }
+        __threadfence_system();
+        grid.sync();
+        if (gtid == 0 && *(volatile int*)fp.abort == 0) {
+            lrk_st_release_sys(fp.prev_ready + (b ^ 1), seq + 1ull);
+            lrk_st_release_sys(fp.next_peer_free + b, seq + 1ull);
+        }
+    }
+    // the block of the next epoch's first stratum must be complete before the kernel ends
+    lrk_fused_wait(fp.ready + ((fp.cur0 + fp.world) & 1), fp.seq0 + (unsigned long long)fp.world, fp.abort, fp.spin_limit);
+}
+
+struct DsgdFused {
+    int enabled = -1;                        // -1: environment not read yet
+    bool mapped = false;
+    float* my_qbuf[2] = {nullptr, nullptr};  // the buffers the mappings were made for
+    unsigned long long* d_flags = nullptr;   // [0,1] ready, [2,3] peer_free
+    int* d_abort = nullptr;
+    float* peer_qbuf[2] = {nullptr, nullptr};
+    unsigned long long* prev_flags = nullptr;
+    unsigned long long* next_flags = nullptr;
+    void* opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n_opened = 0;
+    unsigned long long seq = 0;
+};
+
+static void dsgd_fused_release(DsgdFused* f) {
+    for (int i = 0; i < f->n_opened; ++i) if (f->opened[i]) cudaIpcCloseMemHandle(f->opened[i]);
+    f->n_opened = 0;
+    cudaFree(f->d_flags); cudaFree(f->d_abort);
+    f->d_flags = nullptr; f->d_abort = nullptr; f->mapped = false;
+}
