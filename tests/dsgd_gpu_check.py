@@ -5,7 +5,7 @@
 (3) BPR with stratified sampling: it must learn a ranking (Precision@10 on the binarised C1 split well
     above chance and at least 60 % of the single-GPU BPR of the same library).  Stratified BPR only ever compares
     items of the same block, so it is NOT on a par with the reference's sampling (r01, 2 ranks: 0.225 vs 0.325).
-Prints "DSGD-CHECK OK" on rank 0.
+Prints "DSGD-CHECK OK" on rank 0.  `--fused` runs the same checks through the experimental fused epoch kernel.
 """
 import json
 import os
@@ -47,6 +47,8 @@ def run_dsgd(capi, dist, torch, O, model, full, k, P, Q, bu, bi, mu, hyper, iter
 
 
 def main():
+    if "--fused" in sys.argv:                      # opt-in: the experimental one-kernel epoch (csrc/dsgd_fused.cuh)
+        os.environ["LRK_DSGD_FUSED"] = "1"
     import torch
     import torch.distributed as dist
     from librec_b200 import capi
