@@ -48,3 +48,68 @@ def segments(col, bounds):
     col = np.asarray(col)
     blk = np.searchsorted(np.asarray(bounds[1:-1]), col, side="right")
     return [np.nonzero(blk == b)[0] for b in range(len(bounds) - 1)]
+
+
+# ---- flag protocol of the experimental fused epoch kernel (csrc/dsgd_fused.cuh), restated as a step function so that the
+# sequencing (who may read / overwrite which buffer when) can be exercised on the CPU under arbitrary interleavings.
+class FusedRank:
+    """One rank's view: two block buffers, ready[2] (written by rank+1), peer_free[2] (written by rank-1).  `step()` advances
+    the rank by one protocol action if its wait condition holds and returns what it did (None = blocked)."""
+
+    def __init__(self, rank, world, start_block):
+        self.rank, self.world = rank, world
+        self.buf = [start_block, None]          # block id held in each buffer (None = stale / free)
+        self.ready = [0, 0]
+        self.peer_free = [0, 0]
+        self.cur0, self.seq0 = 0, 0
+        self.t, self.phase = 0, "wait_ready"    # phases per stratum: wait_ready -> compute -> wait_free -> push
+        self.trained = []                       # (seq, block) in the order the rank trained them
+        self.final_wait_done = False
+
+    def begin_epoch(self):
+        self.t, self.phase, self.final_wait_done = 0, "wait_ready", False
+
+    def finished(self):
+        return self.t == self.world and self.final_wait_done
+
+    def step(self, ranks):
+        G = self.world
+        prev, nxt = ranks[(self.rank - 1) % G], ranks[(self.rank + 1) % G]
+        if self.t == G:                                        # the block of the next epoch's first stratum must have arrived
+            b = (self.cur0 + G) & 1
+            if self.ready[b] >= self.seq0 + G:
+                self.final_wait_done = True
+                self.cur0, self.seq0 = b, self.seq0 + G
+                return "final"
+            return None
+        b, seq = (self.cur0 + self.t) & 1, self.seq0 + self.t
+        if self.phase == "wait_ready":
+            if self.ready[b] < seq:
+                return None
+            self.phase = "compute"
+            return "ready"
+        if self.phase == "compute":
+            assert self.buf[b] is not None, "trained on a buffer that was never filled"
+            self.trained.append((seq, self.buf[b]))
+            self.phase = "wait_free"
+            return "compute"
+        if self.phase == "wait_free":
+            if self.peer_free[b ^ 1] < seq:
+                return None
+            self.phase = "push"
+            return "free"
+        # push: copy my buffer b into prev's buffer b^1, then signal
+        assert prev.phase_reads() != (b ^ 1), "pushed into a buffer its owner is still reading"
+        prev.buf[b ^ 1] = self.buf[b]
+        prev.ready[b ^ 1] = seq + 1
+        nxt.peer_free[b] = seq + 1                             # my buffer b may be overwritten by rank+1 again
+        self.buf[b] = None
+        self.t += 1
+        self.phase = "wait_ready"
+        return "push"
+
+    def phase_reads(self):
+        """index of the buffer this rank is reading right now (computing on it or pushing from it), else -1"""
+        if self.t < self.world and self.phase in ("compute", "wait_free", "push"):
+            return (self.cur0 + self.t) & 1
+        return -1
