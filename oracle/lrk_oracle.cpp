@@ -871,6 +871,106 @@ LRO_API double lro_ranksgd_epoch(int32_t U, int32_t I, const int64_t* rowptr, co
     return 0.5 * loss;
 }
 
+// -------------------------------------------------------------------------------------
+// AoBPR (SURVEY.md 8f, row N3 -- groundwork: oracle only): recommender/cf/ranking/AoBPRRecommender.java:51-216.
+// BPR whose negative item is drawn by RANK: setup (:51-73) lambdaItem = (int)(rec.item.distribution.parameter * numItems),
+// loopNumber = (int)(numItems * ln numItems), RankingPro[i] = exp(-((i + 1) / lambdaItem)) with INTEGER division (a step
+// function -- kept), normalised.  Every loopNumber samples (counter carried over the epochs, :88-92) each factor's items are
+// re-sorted by value, descending and stable (:186-203), and var[f] is the population variance of that column.  A sample
+// (:95-130): train entry uniform(numRates) -> (u, i); rank r = discrete(RankingPro); factor f = discrete(|p_uf| var[f] / sum);
+// j = factorRanking[f][r] if p_uf > 0 else factorRanking[f][numItems - r - 1]; redraw (r and f) while u has rated j.
+// Randoms.discrete (math/algorithm/Randoms.java:468-489): one uniform per attempt, first i with cumulative sum > r.
+// The update is BPR's (:133-148), no 0.5 on the loss.  losses_out[iter]; trip_out (3 * nnz, optional) records iteration 1.
+// returns 0, or -1 when discrete() would throw (probabilities not summing to one, e.g. all-zero user factors).
+// -------------------------------------------------------------------------------------
+static int32_t lro_discrete(const double* a, int32_t n) {
+    double sum = 0.0;
+    for (int32_t i = 0; i < n; ++i) { if (a[i] < 0.0) return -1; sum = sum + a[i]; }
+    if (!(sum <= 1.0 + 1E-6 && sum >= 1.0 - 1E-6)) return -1;
+    for (;;) {
+        const double r = lro_uniform();
+        sum = 0.0;
+        for (int32_t i = 0; i < n; ++i) { sum = sum + a[i]; if (sum > r) return i; }
+    }
+}
+LRO_API int32_t lro_aobpr_train(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, int32_t k, double* P, double* Q,
+                                float lr_f, float regU_f, float regI_f, float dist_param, int32_t num_iter, double* losses_out,
+                                int32_t* trip_out) {
+    const double learnRate = (double)lr_f, regUser = (double)regU_f, regItem = (double)regI_f;
+    const int64_t nnz = rowptr[U];
+    const int32_t lambdaItem = (int32_t)(dist_param * (float)I);
+    const int32_t loopNumber = (int32_t)((double)I * log((double)I));
+    if (lambdaItem == 0 || loopNumber == 0) return -1;                       // ArithmeticException in the reference
+    std::vector<double> rankingPro((size_t)I), var((size_t)k), pfc((size_t)k), values((size_t)I);
+    {
+        double sum = 0;
+        for (int32_t i = 0; i < I; ++i) { rankingPro[(size_t)i] = exp((double)(-((i + 1) / lambdaItem))); sum += rankingPro[(size_t)i]; }
+        for (int32_t i = 0; i < I; ++i) rankingPro[(size_t)i] /= sum;
+    }
+    std::vector<int32_t> ranking((size_t)k * I), user_of((size_t)nnz);
+    for (int32_t u = 0; u < U; ++u) for (int64_t e = rowptr[u]; e < rowptr[u + 1]; ++e) user_of[(size_t)e] = u;
+    int64_t countIter = 0;
+    for (int32_t iter = 1; iter <= num_iter; ++iter) {
+        double loss = 0.0;
+        for (int64_t s = 0; s < nnz; ++s) {
+            if (countIter % loopNumber == 0) {
+                for (int32_t f = 0; f < k; ++f) {
+                    int32_t* rk = ranking.data() + (size_t)f * I;
+                    for (int32_t i = 0; i < I; ++i) rk[i] = i;
+                    std::stable_sort(rk, rk + I, [&](int32_t a, int32_t b) { return Q[(int64_t)a * k + f] > Q[(int64_t)b * k + f]; });
+                    double m = 0.0;
+                    for (int32_t i = 0; i < I; ++i) { values[(size_t)i] = Q[(int64_t)rk[i] * k + f]; m += values[(size_t)i]; }
+                    m = m / I;
+                    double v = 0.0;
+                    for (int32_t i = 0; i < I; ++i) v += (values[(size_t)i] - m) * (values[(size_t)i] - m);
+                    var[(size_t)f] = v / (I - 0);
+                }
+                countIter = 0;
+            }
+            countIter++;
+            int32_t u, pi, nj;
+            for (;;) {
+                const int32_t dataIdx = lro_uniform_int((int32_t)nnz);
+                u = user_of[(size_t)dataIdx];
+                const int64_t b = rowptr[u], e = rowptr[u + 1];
+                if (e - b == 0 || e - b == I) continue;
+                pi = col[dataIdx];
+                do {
+                    int32_t r;
+                    do { r = lro_discrete(rankingPro.data(), I); if (r < 0) return -1; } while (r > I);
+                    double sumfc = 0;
+                    for (int32_t f = 0; f < k; ++f) {
+                        const double t = fabs(P[(int64_t)u * k + f]);
+                        sumfc += t * var[(size_t)f];
+                        pfc[(size_t)f] = t * var[(size_t)f];
+                    }
+                    for (int32_t f = 0; f < k; ++f) pfc[(size_t)f] /= sumfc;
+                    const int32_t f = lro_discrete(pfc.data(), k);
+                    if (f < 0) return -1;
+                    nj = P[(int64_t)u * k + f] > 0 ? ranking[(size_t)f * I + r] : ranking[(size_t)f * I + (I - r - 1)];
+                } while (std::binary_search(col + b, col + e, nj));
+                break;
+            }
+            if (trip_out && iter == 1) { trip_out[3 * s] = u; trip_out[3 * s + 1] = pi; trip_out[3 * s + 2] = nj; }
+            double* pu = P + (int64_t)u * k;
+            double* qi = Q + (int64_t)pi * k;
+            double* qj = Q + (int64_t)nj * k;
+            const double diff = dot_lr(pu, qi, k) - dot_lr(pu, qj, k);
+            loss += -log(logistic(diff));
+            const double deri = logistic(-diff);
+            for (int f = 0; f < k; ++f) {
+                const double uf = pu[f], pf = qi[f], nf = qj[f];
+                pu[f] += learnRate * (deri * (pf - nf) - regUser * uf);
+                qi[f] += learnRate * (deri * uf - regItem * pf);
+                qj[f] += learnRate * (deri * (-uf) - regItem * nf);
+                loss += regUser * uf * uf + regItem * pf * pf + regItem * nf * nf;
+            }
+        }
+        if (losses_out) losses_out[iter - 1] = loss;
+    }
+    return 0;
+}
+
 // AbstractRecommender.isConverged: recommender/AbstractRecommender.java:249-267.
 // returns 1 converged, 0 not, -1 = would throw LibrecException (NaN / Inf loss)
 LRO_API int32_t lro_is_converged(double last_loss, double loss, float* delta_out) {
