@@ -48,8 +48,10 @@ __device__ __forceinline__ unsigned long long lrk_ld_acquire_sys(const unsigned 
 __device__ __forceinline__ void lrk_st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// thread 0 of every CTA spins; returns false once any wait of this rank has timed out
+// thread 0 of every CTA spins; returns false once any wait of this rank has timed out.  The verdict is CTA-uniform (it gates
+// code that contains __syncthreads): thread 0 samples the abort flag once and hands it to the others through shared memory.
 __device__ __forceinline__ bool lrk_fused_wait(const unsigned long long* flag, unsigned long long want, int* abort_flag, long long spin_limit) {
+    __shared__ int s_ok;
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         while (lrk_ld_acquire_sys(flag) < want) {
@@ -57,9 +59,12 @@ __device__ __forceinline__ bool lrk_fused_wait(const unsigned long long* flag, u
             if (clock64() - t0 > spin_limit) { atomicExch(abort_flag, 1); break; }
             __nanosleep(100);
         }
+        s_ok = *(volatile int*)abort_flag == 0;
     }
     __syncthreads();
-    return *(volatile int*)abort_flag == 0;
+    const bool ok = s_ok != 0;
+    __syncthreads();                       // s_ok is reused by the next wait
+    return ok;
 }
 
 template <int G, int V, bool BIASED, bool TRACK>
