@@ -6,6 +6,7 @@ package net.librec.recommender.cuda;
 
 import java.nio.ByteBuffer;
 import java.nio.ByteOrder;
+import java.nio.DoubleBuffer;
 import java.util.ArrayList;
 
 import net.librec.common.LibrecException;
@@ -56,12 +57,14 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
 
     private ByteBuffer flatten(DenseMatrix m) {
         ByteBuffer b = LibrecB200.hostAlloc(8L * m.rowSize() * m.columnSize()).order(ByteOrder.nativeOrder());
-        for (int r = 0; r < m.rowSize(); r++) b.asDoubleBuffer().position(r * m.columnSize()).put(m.getValues()[r]);
+        DoubleBuffer d = b.asDoubleBuffer();               // JDK 8: Buffer.position(int) returns Buffer, so no call chaining
+        for (int r = 0; r < m.rowSize(); r++) { d.position(r * m.columnSize()); d.put(m.getValues()[r]); }
         return b;
     }
 
     private void unflatten(ByteBuffer b, DenseMatrix m) {
-        for (int r = 0; r < m.rowSize(); r++) b.asDoubleBuffer().position(r * m.columnSize()).get(m.getValues()[r]);
+        DoubleBuffer d = b.asDoubleBuffer();
+        for (int r = 0; r < m.rowSize(); r++) { d.position(r * m.columnSize()); d.get(m.getValues()[r]); }
     }
 
     /** trainModel(): the iteration loop, isConverged and updateLRate stay in Java (BiasedMFRecommender.java:101-105). */
