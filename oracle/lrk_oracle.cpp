@@ -971,6 +971,103 @@ LRO_API int32_t lro_aobpr_train(int32_t U, int32_t I, const int64_t* rowptr, con
     return 0;
 }
 
+// -------------------------------------------------------------------------------------
+// GBPR (SURVEY.md 8f, row N3 -- groundwork: oracle only): recommender/cf/ranking/GBPRRecommender.java:56-196.
+// Group preference: a sample is (u, i, G, j) -- u uniform over users with ratings, i uniform in u's row, G a java.util.HashSet
+// of gLen users who rated i (all of them when at most gLen did; otherwise u plus uniform draws from the column until the set
+// is full, :95-105), j uniform over the items u has not rated.  Prediction of (u, i, G) = rho * (mean_g p_g.q_i + b_i) +
+// (1 - rho) * (b_i + p_u.q_i) (:185-192); loss and derivative as BPR.  The item biases move immediately (:121-126); the
+// FACTOR updates are accumulated in temporaries and applied at the END of the epoch (:68-69,160-161) -- within an epoch every
+// sample sees the epoch-start factors.  The group is walked in HashSet iteration order (sumGroup and the loss are sums in
+// that order).  rho is a float (default 1.5f): (1 - rho) is float arithmetic.  No 0.5 on the loss.
+// group_out (optional, n * gLen int32, -1 padded) / trip_out (3 * n) record what was drawn.
+// -------------------------------------------------------------------------------------
+LRO_API double lro_gbpr_epoch(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, int32_t k, double* P, double* Q, double* bi,
+                              float lr_f, float regU_f, float regI_f, double regB, float rho, int32_t g_len,
+                              int32_t* trip_out, int32_t* group_out) {
+    const double learnRate = (double)lr_f, regUser = (double)regU_f, regItem = (double)regI_f;
+    const int64_t nnz = rowptr[U];
+    std::vector<int64_t> colptr, csc;
+    lro_csc_order(U, I, rowptr, col, colptr, csc);
+    std::vector<int32_t> user_of((size_t)nnz);
+    for (int32_t u = 0; u < U; ++u) for (int64_t e = rowptr[u]; e < rowptr[u + 1]; ++e) user_of[(size_t)e] = u;
+    std::vector<double> tP((size_t)U * k, 0.0), tQ((size_t)I * k, 0.0), sumGroup((size_t)k);
+    std::vector<int32_t> group, order;
+    const double one_minus_rho = (double)(1 - rho);                        // float subtraction, then promotion
+    double loss = 0.0;
+    for (int64_t s = 0; s < nnz; ++s) {
+        int32_t u;
+        int64_t b, e;
+        do { u = lro_uniform_int(U); b = rowptr[u]; e = rowptr[u + 1]; } while (e - b == 0);
+        const int32_t pi = col[b + lro_uniform_int((int32_t)(e - b))];
+        // users group: insertion order first, then HashSet iteration order
+        const int64_t cb = colptr[(size_t)pi], ce = colptr[(size_t)pi + 1];
+        group.clear();
+        if (ce - cb <= g_len) {
+            for (int64_t x = cb; x < ce; ++x) group.push_back(user_of[(size_t)csc[(size_t)x]]);
+        } else {
+            group.push_back(u);
+            while ((int32_t)group.size() < g_len) {
+                const int32_t t = user_of[(size_t)csc[(size_t)(cb + lro_uniform_int((int32_t)(ce - cb)))]];
+                if (std::find(group.begin(), group.end(), t) == group.end()) group.push_back(t);
+            }
+        }
+        {
+            const uint32_t cap = jhashset_capacity((int64_t)group.size());
+            std::vector<std::pair<uint64_t, int32_t>> ord;
+            for (size_t x = 0; x < group.size(); ++x) ord.push_back({((uint64_t)jhash_bucket(group[x], cap) << 32) | (uint32_t)x, group[x]});
+            std::sort(ord.begin(), ord.end());
+            order.clear();
+            for (auto& o : ord) order.push_back(o.second);
+        }
+        const double* qi = Q + (int64_t)pi * k;
+        const double predictRating = bi[pi] + dot_lr(P + (int64_t)u * k, qi, k);
+        double sum = 0;
+        for (int32_t g : order) sum += dot_lr(P + (int64_t)g * k, qi, k);
+        const double groupRating = sum / (double)order.size() + bi[pi];
+        const double posPredict = rho * groupRating + one_minus_rho * predictRating;
+        int32_t nj;
+        do { nj = lro_uniform_int(I); } while (std::binary_search(col + b, col + e, nj));
+        const double* qj = Q + (int64_t)nj * k;
+        const double negPredict = bi[nj] + dot_lr(P + (int64_t)u * k, qj, k);
+        if (trip_out) { trip_out[3 * s] = u; trip_out[3 * s + 1] = pi; trip_out[3 * s + 2] = nj; }
+        if (group_out) for (int32_t x = 0; x < g_len; ++x) group_out[s * g_len + x] = x < (int32_t)order.size() ? order[(size_t)x] : -1;
+        const double diff = posPredict - negPredict;
+        loss += -log(logistic(diff));
+        const double deri = logistic(-diff);
+        const double pb = bi[pi];
+        bi[pi] += learnRate * (deri - regB * pb);
+        loss += regB * pb * pb;
+        const double nb = bi[nj];
+        bi[nj] += learnRate * (-deri - regB * nb);
+        loss += regB * nb * nb;
+        const double avgW = 1.0 / (double)order.size();
+        std::fill(sumGroup.begin(), sumGroup.end(), 0.0);
+        for (int32_t g : order) {
+            const double delta = g == u ? 1 : 0;
+            for (int f = 0; f < k; ++f) {
+                const double gf = P[(int64_t)g * k + f], pf = qi[f], nf = qj[f];
+                const double deltaGroup = rho * avgW * pf + one_minus_rho * delta * pf - delta * nf;
+                tP[(size_t)g * k + f] += learnRate * (deri * deltaGroup - regUser * gf);
+                loss += regUser * gf * gf;
+                sumGroup[(size_t)f] += gf;
+            }
+        }
+        for (int f = 0; f < k; ++f) {
+            const double uf = P[(int64_t)u * k + f], pf = qi[f], nf = qj[f];
+            const double posDelta = rho * avgW * sumGroup[(size_t)f] + one_minus_rho * uf;
+            tQ[(size_t)pi * k + f] += learnRate * (deri * posDelta - regItem * pf);
+            loss += regItem * pf * pf;
+            loss += regItem * nf * nf;
+            const double negDelta = -uf;
+            tQ[(size_t)nj * k + f] += learnRate * (deri * negDelta - regItem * nf);
+        }
+    }
+    for (size_t t = 0; t < tP.size(); ++t) P[t] = P[t] + tP[t];
+    for (size_t t = 0; t < tQ.size(); ++t) Q[t] = Q[t] + tQ[t];
+    return loss;
+}
+
 // AbstractRecommender.isConverged: recommender/AbstractRecommender.java:249-267.
 // returns 1 converged, 0 not, -1 = would throw LibrecException (NaN / Inf loss)
 LRO_API int32_t lro_is_converged(double last_loss, double loss, float* delta_out) {
