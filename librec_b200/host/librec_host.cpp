@@ -538,6 +538,32 @@ void evaluateRanking(const SequentialAccessSparseMatrix& train, const Sequential
     (*measures)["Entropy" + suffix] = entropy / std::log(2.0);
 }
 
+// The ranking evaluators outside the default list (rec.eval.classes = hitrate, arhr, idcg): HitRateEvaluator.java:33-62 (leave-one-out
+// only: throws when a user has more than one test item), AverageReciprocalHitRankEvaluator.java:33-56 (the user's FIRST test item),
+// IdealDCGEvaluator.java:34-52.  Keys "HitRate" / "ARHR" / "IDCG" + " top <N>".
+void evaluateRankingExtra(const SequentialAccessSparseMatrix& test, const RecommendedList& rec, int topN, bool wantHitRate,
+                          std::map<std::string, double>* measures) {
+    int64_t hits = 0, usersWithTest = 0;
+    double arhr = 0.0, idcgSum = 0.0;
+    for (int u = 0; u < test.numRows; ++u) {
+        const int64_t tb = test.rowptr[(size_t)u], nTest = test.rowptr[(size_t)u + 1] - tb;
+        if (nTest <= 0) continue;
+        if (wantHitRate && nTest > 1)
+            throw std::out_of_range("It is not a leave-one-out validation method! Please use leave-one-out validation method");
+        ++usersWithTest;
+        const auto& lst = rec.lists[(size_t)u];
+        const int len = (int)std::min<size_t>(lst.size(), (size_t)topN);
+        const int first = test.col[(size_t)tb];
+        for (int t = 0; t < len; ++t)
+            if (lst[(size_t)t].key == first) { ++hits; arhr += 1.0 / (t + 1.0); break; }
+        for (int64_t i = 0; i < nTest; ++i) idcgSum += 1 / (std::log((double)i + 2.0) / std::log(2.0));
+    }
+    const std::string suffix = " top " + std::to_string(topN);
+    if (wantHitRate) (*measures)["HitRate" + suffix] = usersWithTest ? 1.0 * hits / usersWithTest : 0.0;
+    (*measures)["ARHR" + suffix] = usersWithTest ? arhr / usersWithTest : 0.0;
+    (*measures)["IDCG" + suffix] = usersWithTest ? idcgSum / usersWithTest : 0.0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // TextDataModel: text file -> flat CSR -> ratio split
 // ---------------------------------------------------------------------------------------------------------------------
@@ -988,6 +1014,35 @@ void RecommenderJob::runJob() {
     }
     log = recommender->log();
     if (dataModel) log.insert(log.begin(), dataModel->log.begin(), dataModel->log.end());
+    if (conf.has("rec.eval.classes") && conf.getBoolean("rec.eval.enable", true)) {
+        // RecommenderJob.java:219-231: only the designated evaluators, logged as "Evaluator info:<SimpleName> is <value>"
+        static const std::map<std::string, std::pair<const char*, const char*>> known = {
+            {"auc", {"AUC", "AUCEvaluator"}}, {"ap", {"AP", "AveragePrecisionEvaluator"}}, {"ndcg", {"NDCG", "NormalizedDCGEvaluator"}},
+            {"precision", {"PRECISION", "PrecisionEvaluator"}}, {"recall", {"RECALL", "RecallEvaluator"}}, {"rr", {"RR", "ReciprocalRankEvaluator"}},
+            {"novelty", {"Novelty", "NoveltyEvaluator"}}, {"entropy", {"Entropy", "EntropyEvaluator"}}, {"hitrate", {"HitRate", "HitRateEvaluator"}},
+            {"arhr", {"ARHR", "AverageReciprocalHitRankEvaluator"}}, {"idcg", {"IDCG", "IdealDCGEvaluator"}},
+            {"rmse", {"RMSE", "RMSEEvaluator"}}, {"mse", {"MSE", "MSEEvaluator"}}, {"mae", {"MAE", "MAEEvaluator"}}, {"mpe", {"MPE", "MPEEvaluator"}}};
+        std::string spec = conf.get("rec.eval.classes", "");
+        for (char& c : spec) { if (c == ',') c = ' '; c = (char)std::tolower((unsigned char)c); }
+        std::istringstream in(spec);
+        std::vector<std::string> keys;
+        for (std::string k; in >> k;) keys.push_back(k);
+        const bool wantHitRate = std::find(keys.begin(), keys.end(), "hitrate") != keys.end();
+        if (ranking) evaluateRankingExtra(test, recommendedList, recommender->rankingTopN(), wantHitRate, &evaluatedMap);
+        std::map<std::string, double> designated;
+        for (const std::string& k : keys) {
+            auto it = known.find(k);
+            if (it == known.end()) throw LibrecException("ClassNotFoundException: rec.eval.classes=" + k + " (diversity needs a similarity matrix and is not on this path)");
+            const std::string name = ranking && k != "rmse" && k != "mse" && k != "mae" && k != "mpe"
+                                         ? std::string(it->second.first) + " top " + std::to_string(recommender->rankingTopN()) : std::string(it->second.first);
+            auto v = evaluatedMap.find(name);
+            if (v == evaluatedMap.end()) throw LibrecException(std::string(it->second.second) + " does not apply to this kind of recommender (rec.recommender.isranking)");
+            designated[it->second.second] = v->second;
+        }
+        evaluatedMap = designated;
+        for (const auto& kv : evaluatedMap) log.push_back("Evaluator info:" + kv.first + " is " + java_double_to_string(kv.second));
+        return;
+    }
     for (const auto& kv : evaluatedMap) log.push_back("Evaluator value:" + kv.first + " is " + java_double_to_string(kv.second));   // :257-260
 }
 

@@ -208,6 +208,8 @@ double evaluateMAE(const SequentialAccessSparseMatrix& test, const RecommendedLi
 // eval/rating/MSEEvaluator.java:33-66, MPEEvaluator.java:33-73 (share of entries with |error| > rec.measure.mpe, default 0.01)
 double evaluateMSE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended);
 // the eight default ranking measures (eval/Measure.java:76-93) on the host; keys "<MEASURE> top <N>" like the job's log lines
+void evaluateRankingExtra(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended, int topN, bool wantHitRate,
+                          std::map<std::string, double>* measures);   // HitRate (leave-one-out only), ARHR, IDCG
 void evaluateRanking(const SequentialAccessSparseMatrix& train, const SequentialAccessSparseMatrix& test, const RecommendedList& recommended,
                      int topN, std::map<std::string, double>* measures);
 double evaluateMPE(const SequentialAccessSparseMatrix& test, const RecommendedList& recommended, double mpe);

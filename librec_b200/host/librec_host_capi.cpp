@@ -140,6 +140,26 @@ LRH_API int lrh_probe_ranking_measures(int32_t U, int32_t I, const int64_t* tr_r
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
+// HitRate / ARHR / IDCG over a flat test CSR and padded lists: out[3]; returns -1 (message in lrh_last_error) when HitRate is asked
+// for data that is not leave-one-out
+LRH_API int lrh_probe_ranking_extra(int32_t U, int32_t I, const int64_t* te_rowptr, const int32_t* te_col, int32_t topn,
+                                    const int32_t* items, const int32_t* counts, int want_hitrate, double* out) {
+    try {
+        SequentialAccessSparseMatrix te;
+        te.numRows = U; te.numCols = I;
+        te.rowptr.assign(te_rowptr, te_rowptr + U + 1); te.col.assign(te_col, te_col + te_rowptr[U]); te.val.assign((size_t)te_rowptr[U], 1.0);
+        RecommendedList rec;
+        for (int u = 0; u < U; ++u) {
+            rec.addList();
+            for (int t = 0; t < counts[u]; ++t) rec.add(u, items[(int64_t)u * topn + t], 0.0);
+        }
+        std::map<std::string, double> m;
+        evaluateRankingExtra(te, rec, topn, want_hitrate != 0, &m);
+        const std::string sfx = " top " + std::to_string(topn);
+        out[0] = want_hitrate ? m["HitRate" + sfx] : 0.0; out[1] = m["ARHR" + sfx]; out[2] = m["IDCG" + sfx];
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 // ---- data model alone (no GPU needed): properties -> TextDataModel.buildDataModel() -> flat CSR arrays
 struct DataModelBox { std::unique_ptr<TextDataModel> dm; std::string tmp; };
 LRH_API void* lrh_datamodel_build(const char* properties_text) {

@@ -1256,6 +1256,35 @@ LRO_API void lro_eval_ranking(int32_t U, int32_t topn, const int32_t* rec_items,
     out[5] = nz > 0 ? rr / nz : 0.0;
 }
 
+// The three ranking evaluators outside the default list (reachable through rec.eval.classes): out[0] HitRate
+// (eval/ranking/HitRateEvaluator.java:33-62; leave-one-out only -- NaN here when a user has more than one test item, where the
+// reference throws), out[1] ARHR (AverageReciprocalHitRankEvaluator.java:33-56: reciprocal rank of the FIRST test item of the
+// user, i.e. its lowest item id), out[2] IDCG (IdealDCGEvaluator.java:34-52: sum_{i < |test|} 1 / log2(i + 2), averaged).
+LRO_API void lro_eval_ranking_extra(int32_t U, int32_t topn, const int32_t* rec_items, const int32_t* rec_counts,
+                                    const int64_t* t_rowptr, const int32_t* t_col, double* out) {
+    int64_t hits = 0, nz_hit = 0, nz = 0;
+    bool loo = true;
+    double arhr = 0.0, idcg_sum = 0.0;
+    for (int32_t u = 0; u < U; ++u) {
+        const int64_t tb = t_rowptr[u], nt = t_rowptr[u + 1] - tb;
+        if (nt <= 0) continue;
+        ++nz;
+        const int32_t* r = rec_items + (int64_t)u * topn;
+        const int topk = topn <= rec_counts[u] ? topn : rec_counts[u];
+        if (nt == 1) {
+            for (int i = 0; i < topk; ++i) if (r[i] == t_col[tb]) { ++hits; break; }
+            ++nz_hit;
+        } else loo = false;
+        for (int i = 0; i < topk; ++i) if (r[i] == t_col[tb]) { arhr += 1.0 / (i + 1.0); break; }
+        double idcg = 0.0;
+        for (int64_t i = 0; i < nt; ++i) idcg += 1 / (log((double)i + 2.0) / log(2.0));
+        idcg_sum += idcg;
+    }
+    out[0] = !loo ? std::nan("") : (nz_hit > 0 ? 1.0 * hits / nz_hit : 0.0);
+    out[1] = nz > 0 ? arhr / nz : 0.0;
+    out[2] = nz > 0 ? idcg_sum / nz : 0.0;
+}
+
 LRO_API void lro_predict_pairs(int32_t model, int32_t k, const double* P, const double* Q, const double* bu,
                                const double* bi, double mu, const int32_t* us, const int32_t* is, int64_t n, double* out) {
     for (int64_t t = 0; t < n; ++t) out[t] = predict_raw(model, k, P, Q, bu, bi, mu, us[t], is[t]);

@@ -117,6 +117,7 @@ def lib():
     L.lro_eval_rating.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _f64p, C.c_int32, _f64p, _f64p, C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
     L.lro_eval_ranking.argtypes = [C.c_int32, C.c_int32, _i32p, _i32p, _i64p, _i32p, _f64p, _i32p, _i32p, C.c_int32, _f64p]
+    L.lro_eval_ranking_extra.argtypes = [C.c_int32, C.c_int32, _i32p, _i32p, _i64p, _i32p, _f64p]
     L.lro_predict_pairs.argtypes = [C.c_int32, C.c_int32, _f64p, _f64p, C.c_void_p, C.c_void_p, C.c_double,
                                     _i32p, _i32p, C.c_int64, _f64p]
     L.lro_recommend_rank.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f64p, _f64p, C.c_void_p, C.c_void_p,
@@ -291,6 +292,14 @@ def eval_ranking(te, tr, topn, items, counts):
     lib().lro_eval_ranking(te.U, topn, np.ascontiguousarray(items, np.int32), np.ascontiguousarray(counts, np.int32),
                            te.rowptr, te.col, te.val, num_dropped, purchased, te.I, out)
     return dict(zip(RANKING_MEASURES, out.tolist()))
+
+
+def eval_ranking_extra(te, topn, items, counts):
+    """HitRate (NaN unless leave-one-out), ARHR, IDCG -- the ranking evaluators outside the default list"""
+    out = np.zeros(3, np.float64)
+    lib().lro_eval_ranking_extra(te.U, topn, np.ascontiguousarray(items, np.int32), np.ascontiguousarray(counts, np.int32),
+                                 te.rowptr, te.col, out)
+    return dict(zip(("HitRate", "ARHR", "IDCG"), out.tolist()))
 
 
 def recommend_rank(model, U, I, k, P, Q, bu, bi, mu, tr, topn, users=None, nthreads=None):

@@ -115,3 +115,31 @@ def test_host_ranking_measures_match_the_oracle(H, O):
         for name in O.RANKING_MEASURES:
             assert abs(got[name] - exp[name]) <= 1e-12 * max(1.0, abs(exp[name])), (name, got[name], exp[name], U, I, topn)
         assert got["Precision"] > 0 and got["AUC"] > 0
+
+
+def test_hitrate_arhr_idcg_match_the_oracle_and_a_hand_worked_case(H, O):
+    """the three ranking evaluators outside the default list (rec.eval.classes = hitrate, arhr, idcg)"""
+    H.lrh_probe_ranking_extra.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    # hand-worked, leave-one-out: user 0 test {7} found at rank 3; user 1 test {2} missed; user 2 no test item; user 3 test {5} at rank 1
+    rowptr = np.array([0, 1, 2, 2, 3], np.int64); col = np.array([7, 2, 5], np.int32)
+    items = np.array([[4, 9, 7, 1], [1, 3, 4, 5], [1, 2, 3, 4], [5, 6, 7, 8]], np.int32); counts = np.array([4, 4, 4, 4], np.int32)
+    out = np.zeros(3)
+    assert H.lrh_probe_ranking_extra(4, 10, rowptr.ctypes.data, col.ctypes.data, 4, items.ctypes.data, counts.ctypes.data, 1, out.ctypes.data) == 0
+    assert out[0] == 2 / 3.0 and abs(out[1] - (1 / 3.0 + 0.0 + 1.0) / 3) < 1e-15 and out[2] == 1.0      # IDCG of one item = 1 / log2(2)
+    te = O.Csr(4, 10, rowptr, col, np.ones(3))
+    exp = O.eval_ranking_extra(te, 4, items, counts)
+    assert [exp["HitRate"], exp["ARHR"], exp["IDCG"]] == out.tolist()
+    # with top-2 lists the rank-3 hit is gone
+    assert H.lrh_probe_ranking_extra(4, 10, rowptr.ctypes.data, col.ctypes.data, 2, np.ascontiguousarray(items[:, :2]).ctypes.data,
+                                     np.array([2, 2, 2, 2], np.int32).ctypes.data, 1, out.ctypes.data) == 0
+    assert out[0] == 1 / 3.0 and abs(out[1] - 1.0 / 3) < 1e-15
+    # not leave-one-out: HitRate throws like the reference, the other two still work and equal the oracle
+    from conftest import rng_csr
+    te = rng_csr(O, 50, 80, 0.1, 3)
+    rng = np.random.default_rng(0)
+    items = np.stack([rng.permutation(80)[:10] for _ in range(50)]).astype(np.int32); counts = np.full(50, 10, np.int32)
+    assert H.lrh_probe_ranking_extra(50, 80, te.rowptr.ctypes.data, te.col.ctypes.data, 10, items.ctypes.data, counts.ctypes.data, 1, out.ctypes.data) == -1
+    assert b"leave-one-out" in H.lrh_last_error()
+    assert H.lrh_probe_ranking_extra(50, 80, te.rowptr.ctypes.data, te.col.ctypes.data, 10, items.ctypes.data, counts.ctypes.data, 0, out.ctypes.data) == 0
+    exp = O.eval_ranking_extra(te, 10, items, counts)
+    assert np.isnan(exp["HitRate"]) and abs(out[1] - exp["ARHR"]) < 1e-15 and abs(out[2] - exp["IDCG"]) < 1e-12
