@@ -215,10 +215,10 @@ rec.random.seed=1
 
 
 def test_kcv_job_cross_validation(O, capi, c1, tmp_path):
-    """data.model.splitter=kcv: RecommenderJob.java:125-133 trains and evaluates once per fold and prints the averages
-    (printCVAverageResult :311-326).  Folds come from the native TextDataModel (checked against the oracle on CPU); here the
-    per-fold RMSE must match the oracle trained on the same fold within the fast mode's 1e-3 ... plus its init differences,
-    so the check is: finite, in the plausible range, and the reported metric is the mean of the fold lines."""
+    """data.model.splitter=kcv: RecommenderJob.java:125-133 trains and evaluates once per fold on one recommender instance and
+    prints the averages (printCVAverageResult :311-326).  The folds themselves are checked entry for entry against the oracle on
+    the CPU (tests/test_host_datamodel.py); here: three folds run, every fold's RMSE is in the plausible range for 15 iterations,
+    and the reported metric is the mean of the fold lines."""
     import os
     from librec_b200.host.binding import RecommenderJob
     full = c1["full"]
