@@ -21,9 +21,11 @@ collective), measured through lrk_topn with pinned host result buffers (D2H insi
 with the tensor-pipe roofline of topn_tc_kernel from CUDA events on its stream.
 """
 import argparse
+import csv
 import ctypes
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -37,9 +39,12 @@ sys.path.insert(0, ROOT)
 METRIC = "MF SGD rating-updates/s"
 UNIT = "updates/s"
 K_FACTORS = 64
-LR, REG, REG_B = 0.002, 0.01, 0.01           # biasedmf-test.properties
+LR, REG, REG_B = 0.002, 0.01, 0.01           # biasedmf-test.properties (config C2)
 BYTES_PER_UPDATE = 12 + 4 * K_FACTORS * 4 + 16   # 1052 B for k=64 fp32
 E2E_EPOCHS = 10                               # epochs per trainModel() call in the e2e leg
+# config C4 (BASELINE configs[3]): PMF k=128 on the Netflix shape, pmf-test.properties, DSGD at 2/4/8 GPUs (strong scaling)
+C4_K, C4_LR, C4_REG = 128, 0.01, 0.08
+C4_BYTES_PER_UPDATE = 12 + 4 * C4_K * 4      # 2060 B for k=128 fp32
 
 
 def log(*a):
@@ -124,13 +129,18 @@ def dist_env():
     return rank, world, local
 
 
-def workload_desc(d):
+def workload_c2(U, I, nnz):
     return "BiasedMF k=%d SGD epoch, synthetic ML-20M shape (%d users x %d items, %d ratings), lr %g reg %g" % (
-        K_FACTORS, d["U"], d["I"], d["rowptr"][-1], LR, REG)
+        K_FACTORS, U, I, nnz, LR, REG)
+
+
+def workload_c4(U, I, nnz, world):
+    return ("PMF k=%d SGD epoch, synthetic Netflix shape (%d users x %d items, %d ratings), lr %g reg %g, DSGD over %d GPUs "
+            "(users in %d contiguous blocks, strong scaling)" % (C4_K, U, I, nnz, C4_LR, C4_REG, world, world))
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(d, sample_ratings, steps, warmup, nthreads=1):
+def cpu_reference_rate(d, sample_ratings, steps, warmup, model="biasedmf"):
     """time the oracle's faithful restatement (1 thread, CSR order, fp64) on a CSR prefix"""
     from oracle import oracle as O
     from librec_b200 import synth
@@ -142,11 +152,16 @@ def cpu_reference_rate(d, sample_ratings, steps, warmup, nthreads=1):
     u_end = max(1, min(U, u_end))
     n = int(d["rowptr"][u_end])
     rowptr = np.ascontiguousarray(d["rowptr"][:u_end + 1])
-    P, Q, bu, bi = synth.init_factors(U, I, K_FACTORS, 7, True)
+    biased = model == "biasedmf"
+    k = K_FACTORS if biased else C4_K
+    P, Q, bu, bi = synth.init_factors(U, I, k, 7, biased)
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        L.lro_biasedmf_epoch(u_end, rowptr, d["col"], d["val"], K_FACTORS, P, Q, bu, bi, 3.5, LR, REG, REG, REG_B, None, None)
+        if biased:
+            L.lro_biasedmf_epoch(u_end, rowptr, d["col"], d["val"], k, P, Q, bu, bi, 3.5, LR, REG, REG, REG_B, None, None)
+        else:
+            L.lro_pmf_epoch(u_end, rowptr, d["col"], d["val"], k, P, Q, C4_LR, C4_REG, C4_REG, None, None)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
@@ -155,22 +170,28 @@ def cpu_reference_rate(d, sample_ratings, steps, warmup, nthreads=1):
 
 
 def run_reference(args):
+    """the reference's CPU path on this box's host cores: the oracle port (the Java reference cannot run: no JVM), one thread
+    because the reference's trainModel is single-threaded; same workload as our arm at this --gpus"""
     rank, world, _ = dist_env()
     if rank != 0:
         return
     from librec_b200 import synth
-    d = synth.make_ratings("ml-20m")
+    c4 = args.gpus > 1
+    d = synth.make_ratings("netflix" if c4 else "ml-20m")
     nnz = int(d["rowptr"][-1])
+    model = "pmf" if c4 else "biasedmf"
     # probe 1M ratings to size the per-step sample so K+W steps end within ~2.5 minutes
-    rate, _, _ = cpu_reference_rate(d, 1_000_000, 1, 0)
+    rate, _, _ = cpu_reference_rate(d, 1_000_000, 1, 0, model)
     budget_s = 150.0 / max(1, args.steps + args.warmup)
     sample = int(min(nnz, max(1_000_000, rate * budget_s)))
-    rate, n, sec = cpu_reference_rate(d, sample, args.steps, args.warmup)
+    rate, n, sec = cpu_reference_rate(d, sample, args.steps, args.warmup, model)
+    what = "PMFSimilarityRecommender.trainModel" if c4 else "BiasedMFRecommender.trainModel"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if c4 else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(d), "reference": "oracle port of BiasedMFRecommender.trainModel (Java reference cannot run: no JVM)"},
+        "config": {"workload": workload_c4(d["U"], d["I"], nnz, args.gpus) if c4 else workload_c2(d["U"], d["I"], nnz)},
+        "reference": "oracle port of %s (Java reference cannot run: no JVM)" % what,
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": "one epoch over the first %d ratings in CSR order per step (of %d); the reference's trainModel is single-threaded" % (n, nnz)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -184,12 +205,85 @@ def pinned_array(capi, shape, dtype):
     """numpy view over a cudaMallocHost buffer from the C ABI (what the Java shim's direct buffers are)"""
     nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = ctypes.c_void_p()
-    rc = capi.load().lrk_host_alloc(ctypes.byref(p), nbytes)
+    rc = capi.load().lrk_host_alloc(ctypes.byref(p), max(nbytes, 1))
     if rc != 0:
         raise RuntimeError("lrk_host_alloc failed")
-    buf = (ctypes.c_char * nbytes).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     return arr, p
+
+
+def ncu_dram_bytes(probe, kernel_regex, skip, count=1):
+    """DRAM bytes (read + write) of ONE launch of `kernel_regex`, measured by running this script's --traffic-probe mode under
+    ncu (two counters, --clock-control none) -- outside the timed region, in the same bench run.  None when ncu cannot profile here."""
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
+           "-k", "regex:" + kernel_regex, "-s", str(skip), "-c", str(count), "--csv", sys.executable, os.path.abspath(__file__),
+           "--traffic-probe", probe]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0"))
+    except Exception as e:  # pragma: no cover
+        return None, "ncu failed: %s" % e
+    per_launch, header = {}, None
+    for row in csv.reader(r.stdout.splitlines()):
+        if header is None:
+            if "Metric Name" in row and "Metric Value" in row:
+                header = {name: i for i, name in enumerate(row)}
+            continue
+        try:
+            if row[header["Metric Name"]].startswith("dram__bytes_"):
+                per_launch.setdefault(row[header["ID"]], []).append(float(row[header["Metric Value"]].replace(",", "")))
+        except (IndexError, ValueError, KeyError):
+            pass
+    full = [sum(v) for v in per_launch.values() if len(v) >= 2]
+    if not full:
+        return None, "ncu gave no dram counters (rc %d): %s" % (r.returncode, (r.stdout + r.stderr)[-300:].replace("\n", " "))
+    return max(full), ("ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:%s -s %d -c %d, largest launch (this run)"
+                       % (kernel_regex, skip, count))
+
+
+def traffic_probe(which):
+    """child of ncu_dram_bytes: launches the kernel in question a few times on the benchmark shape and exits"""
+    from librec_b200 import capi, synth
+    if which == "sgd":
+        d = synth.make_ratings("ml-20m")
+        P0, Q0, bu0, bi0 = synth.init_factors(d["U"], d["I"], K_FACTORS, 100, True)
+        with capi.Handle(capi.MODEL_BIASEDMF, K_FACTORS, seed=1) as h:
+            h.set_train_csr(d["U"], d["I"], d["rowptr"], d["col"], d["val"])
+            h.set_factors(P0, Q0, bu0, bi0, float(d["val"].mean()))
+            for it in range(5):
+                h.sgd_epoch(LR, REG, REG, REG_B, it + 1)
+    elif which == "topn":
+        nu, rowptr, col, val, P, Q = topn_inputs(0, 1)
+        with capi.Handle(capi.MODEL_BPR, TOPN_K) as h:
+            h.set_train_csr(nu, TOPN_ITEMS, rowptr, col, val)
+            h.set_factors(P, Q)
+            h.topn(TOPN_N, nq=4096)
+            h.topn(TOPN_N)
+
+
+def sgd_roofline(h, kernel, kms, nnz_launch, bytes_per_update, row_floats, working_set_bytes, peaks, which, traffic, traffic_how):
+    """roofline object of an SGD epoch kernel.  The kernel gathers and RED-updates factor rows that live in L2, so its bound is
+    the L2's gather+RED rate, measured HERE by lrk_probe_l2 with the same instruction mix on a working set of the same size;
+    `achieved` = SURVEY 8(d)'s algorithmic bytes per update x updates per launch / kernel time.  HBM figures ride along."""
+    l2 = h.probe_l2(working_set_bytes, row_floats)
+    achieved = bytes_per_update * nnz_launch / (kms * 1e-3) / 1e9
+    out = {"bound": "l2", "achieved": achieved, "peak": l2["mix"], "unit": "GB/s", "frac": achieved / l2["mix"], "traffic": traffic,
+           "peak_source": "lrk_probe_l2 in this run: random %d B row gathers (ld.global.cg.v4) + red.global.add.v4.f32 1:1 on a %.0f MB "
+                          "working set; gathers alone %.0f GB/s, REDs alone %.0f GB/s" % (row_floats * 4, working_set_bytes / 1e6, l2["gather"], l2["red"]),
+           "kernel": kernel, "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_per_update * nnz_launch,
+           "traffic_source": traffic_how,
+           "hbm": {"peak": peaks["hbm_gbs"], "peak_source": which,
+                   "achieved_algorithmic": achieved, "frac_algorithmic": achieved / peaks["hbm_gbs"],
+                   "achieved_dram": None if traffic is None else traffic / (kms * 1e-3) / 1e9,
+                   "frac_dram": None if traffic is None else traffic / (kms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+           "note": "algorithmic bytes = SURVEY 8(d), no cache credit; the factor set is L2-resident, so the bytes are L2 traffic and the bound is "
+                   "the L2 gather+RED rate (frac), not HBM (hbm.frac_algorithmic may exceed 1; hbm.frac_dram is what DRAM really moved). "
+                   "Item-run tiles keep a popular item's row in registers for 8-32 ratings, which is traffic the model counts and the kernel "
+                   "does not issue."}
+    return out
 
 
 def run_ours(args):
@@ -205,108 +299,101 @@ def run_ours(args):
     if not os.path.exists(_build.LIB_PATH):
         _build.build()
     capi.load()
-
-    # N=1: the ML-20M-shaped matrix.  N>1 (weak scaling): every rank owns one ML-20M-shaped user shard
-    # over the same item catalogue -> N x 138 493 users, N x 20 000 263 ratings in total.
-    d = synth.make_ratings("ml-20m", shard=rank)
-    U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
-    P0, _, bu0, _ = synth.init_factors(U, I, K_FACTORS, 100 + rank, True)
-    _, Q0, _, bi0 = synth.init_factors(U, I, K_FACTORS, 1, True)          # item side identical on every rank
-    mu = float(d["val"].mean())
     if world > 1:
-        m = torch.tensor([mu], dtype=torch.float64, device=dev)
-        dist.all_reduce(m)
-        mu = float(m.item()) / world
-
-    h = capi.Handle(capi.MODEL_BIASEDMF, K_FACTORS, device=local, seed=1)
-    stream = torch.cuda.current_stream()
-    h.set_stream(stream.cuda_stream)
+        line = run_c4_dsgd(args, torch, dist, capi, synth, rank, world, local, dev)
+    else:
+        line = run_c2_single(args, torch, capi, synth, local, dev)
+    if not args.no_topn:
+        tn = topn_leg(args, capi, torch, dist, rank, world, local, dev)
+        if rank == 0:
+            line["topn"] = tn
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
-        uid = [capi.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        h.comm_init(rank, world, uid[0])
-    h.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
-    h.set_factors(P0, Q0, bu0, bi0, mu)
+        dist.barrier()
+        dist.destroy_process_group()
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+def timed_epochs(torch, dist, h, world, stream, flush, steps, warmup, hyper, first_epoch=1):
+    """W untimed + K timed epochs; barrier + synchronize on both sides; CUDA events per step on `stream`; -> (total ms max over
+    ranks, mean device ms of the epoch's kernels on this rank, losses)"""
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    for w in range(args.warmup):
-        h.sgd_epoch(LR, REG, REG, REG_B, w + 1)
-    sampler = ClockSampler(index=local)
-    launches0 = h.launch_count()
+    losses = []
+    for w in range(warmup):
+        losses.append(h.sgd_epoch(*hyper, first_epoch + w))
     barrier()
-    sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms, losses = [], []
-    for s in range(args.steps):
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    kernel_ms = []
+    for s in range(steps):
         flush.zero_()                                   # evict L2 between timed steps (not timed)
         evs[s][0].record(stream)
-        losses.append(h.sgd_epoch(LR, REG, REG, REG_B, args.warmup + s + 1))
+        losses.append(h.sgd_epoch(*hyper, first_epoch + warmup + s))
         evs[s][1].record(stream)
         kernel_ms.append(h.last_epoch_ms())
     barrier()
+    total_ms = float(np.sum([a.elapsed_time(b) for a, b in evs]))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    return total_ms, float(np.mean(kernel_ms)), losses
+
+
+def run_c2_single(args, torch, capi, synth, local, dev):
+    d = synth.make_ratings("ml-20m")
+    U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
+    P0, _, bu0, _ = synth.init_factors(U, I, K_FACTORS, 100, True)
+    _, Q0, _, bi0 = synth.init_factors(U, I, K_FACTORS, 1, True)
+    mu = float(d["val"].mean())
+    h = capi.Handle(capi.MODEL_BIASEDMF, K_FACTORS, device=local, seed=1)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    h.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
+    h.set_factors(P0, Q0, bu0, bi0, mu)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    sampler = ClockSampler(index=local)
+    for w in range(args.warmup):                                    # warm-up outside the sampler
+        h.sgd_epoch(LR, REG, REG, REG_B, w + 1)
+    launches0 = h.launch_count()
+    sampler.start()
+    total_ms, kms, losses = timed_epochs(torch, None, h, 1, stream, flush, args.steps, 0, (LR, REG, REG, REG_B), args.warmup + 1)
     clocks = sampler.stop()
     launches = h.launch_count() - launches0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = float(np.sum(step_ms))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = nnz * world * args.steps / (total_ms * 1e-3)
-    kms = float(np.mean(kernel_ms))
-
-    line = None
-    if rank == 0:
-        peaks, which = measured_peaks()
-        achieved = BYTES_PER_UPDATE * nnz / (kms * 1e-3) / 1e9        # per GPU (rank 0's kernels)
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("sgd_rating_epoch_kernel_bytes_per_launch")
-            except Exception:
-                traffic = None
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_desc(d) if world == 1 else
-                       "BiasedMF k=%d SGD epoch, %d ML-20M-shaped user shards (%d users x %d items, %d ratings in total), "
-                       "lr %g reg %g" % (K_FACTORS, world, U * world, I, nnz * world, LR, REG),
-                       "update_mode": "atomic (REDG.E.ADD.F32x4)",
-                       "l2": "L2 flushed between timed steps (256 MiB memset, untimed); COO stream 240 MB > L2",
-                       "parallelism": "single GPU" if world == 1 else "DSGD %d strata, NCCL ring rotation of item blocks" % world,
-                       "final_loss": losses[-1]},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
-                         "kernel": "sgd_rating_epoch_kernel<16,1,true,true>", "kernel_ms": kms,
-                         "algorithmic_bytes_per_epoch_per_gpu": BYTES_PER_UPDATE * nnz,
-                         "note": "algorithmic bytes = SURVEY 8(d): 1052 B per update, no cache credit. frac > 1 means the kernel "
-                                 "moves less than that model: the 42 MB factor set is resident in the 126 MB L2 and item-run tiles "
-                                 "read/update a popular item's row once per 8-32 ratings; DRAM bytes per launch (ncu) are in `traffic`, "
-                                 "the binding unit is L2 (profiles/r01_sgd_kernel_ncu_summary.md)"},
-            "gpu_launches": int(launches), "clocks": clocks,
-        }
+    value = nnz * args.steps / (total_ms * 1e-3)
+    peaks, which = measured_peaks()
+    traffic, traffic_how = (None, "skipped (--no-traffic)") if args.no_traffic else ncu_dram_bytes("sgd", "sgd_rating_epoch_kernel", 4)
+    ws = (U + I) * (K_FACTORS + 1) * 4
+    stage = h.stage_stats()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_c2(U, I, nnz)},
+        "run": {"update_mode": "atomic (REDG.E.ADD.F32x4)",
+                "l2": "L2 flushed between timed steps (256 MiB memset, untimed); COO stream 240 MB > L2",
+                "parallelism": "single GPU", "final_loss": losses[-1],
+                "item_popularity": "Zipf(1.0) over %d items (the survey's generator); share of ratings staged as item-run tiles: %.3f"
+                                   % (I, stage["run_tile_share"]),
+                "run_tile_share": stage["run_tile_share"]},
+        "roofline": sgd_roofline(h, "sgd_rating_epoch_kernel<16,1,true,true>", kms, nnz, BYTES_PER_UPDATE, K_FACTORS, ws, peaks, which,
+                                 traffic, traffic_how),
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
 
     # ---- e2e: one trainModel() call of the shim per step, host buffers, copies inside the timed region
-    if world == 1 and not args.no_e2e:
-        bufs = []
+    if not args.no_e2e:
         rp, p1 = pinned_array(capi, (U + 1,), np.int64); rp[:] = d["rowptr"]
         cl, p2 = pinned_array(capi, (nnz,), np.int32); cl[:] = d["col"]
         vl, p3 = pinned_array(capi, (nnz,), np.float64); vl[:] = d["val"]
         hP, p4 = pinned_array(capi, (U, K_FACTORS), np.float64); hQ, p5 = pinned_array(capi, (I, K_FACTORS), np.float64)
         hbu, p6 = pinned_array(capi, (U,), np.float64); hbi, p7 = pinned_array(capi, (I,), np.float64)
-        bufs = [p1, p2, p3, p4, p5, p6, p7]
+        hloss, p8 = pinned_array(capi, (E2E_EPOCHS,), np.float64)
+        bufs = [p1, p2, p3, p4, p5, p6, p7, p8]
         L = capi.load()
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-        loss = ctypes.c_double()
-
         breakdown = {"set_train_csr": [], "set_factors": [], "epochs": [], "get_factors": []}
 
         def train_model_call(record=True):
@@ -316,8 +403,8 @@ def run_ours(args):
             t1 = time.perf_counter()
             rc |= L.lrk_set_factors(h._h, vp(hP), vp(hQ), vp(hbu), vp(hbi), mu)
             t2 = time.perf_counter()
-            for it in range(E2E_EPOCHS):
-                rc |= L.lrk_sgd_epoch(h._h, LR, REG, REG, REG_B, it + 1, ctypes.byref(loss))
+            # rec.learnrate.bolddriver=false, decay=1, no early stop (biasedmf-test.properties): the shim batches the iterations
+            rc |= L.lrk_sgd_epochs(h._h, E2E_EPOCHS, LR, 1.0, LR, REG, REG, REG_B, 1, vp(hloss))
             t3 = time.perf_counter()
             rc |= L.lrk_get_factors(h._h, vp(hP), vp(hQ), vp(hbu), vp(hbi))
             torch.cuda.synchronize()
@@ -337,16 +424,30 @@ def run_ours(args):
         line["e2e"] = {"value": nnz * E2E_EPOCHS * e2e_steps / float(np.sum(tt)), "unit": UNIT,
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "step": "one trainModel() call through the C ABI from pinned host buffers: lrk_set_train_csr + "
-                               "lrk_set_factors + %d x lrk_sgd_epoch + lrk_get_factors" % E2E_EPOCHS,
+                               "lrk_set_factors + lrk_sgd_epochs(%d) + lrk_get_factors" % E2E_EPOCHS,
                        "ms_per_call": float(np.mean(tt)) * 1e3, "calls": e2e_steps,
                        "breakdown_ms": {k_: float(np.mean(v)) for k_, v in breakdown.items()}}
         for p in bufs:
             L.lrk_host_free(p)
-    elif rank == 0:
+    else:
         line["e2e"] = None
+    h.close()
 
-    # ---- cpu baseline: oracle port on this box's host cores (rank 0, N=1 only)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # ---- parity at scale, same run: the fast kernel at full concurrency vs the oracle's sequential loop, held-out RMSE / MAE
+    if not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import parity_scale
+        from oracle import oracle as O
+        r = parity_scale.rating_parity(capi, O, "c2", epochs=10, device=local)
+        line["parity"] = {"what": "BiasedMF k=64, 10 epochs from identical factors on a seeded 80/20 split of the benchmark matrix: held-out "
+                                  "RMSE / MAE of the fast kernel vs the oracle's sequential fp64 loop", **r}
+        if not r["ok"]:
+            log("PARITY FAILED:", r)
+            print(json.dumps(line), flush=True)
+            sys.exit(3)
+
+    # ---- cpu baseline: oracle port on this box's host cores
+    if not args.no_cpu_baseline:
         rate, n, sec = cpu_reference_rate(d, nnz, 1, 0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": "one full epoch (%d ratings) of the oracle's restatement of BiasedMFRecommender.trainModel, "
@@ -366,27 +467,192 @@ def run_ours(args):
                                        "what": "OpenMP Hogwild fp32 epoch over shuffled triples (NOT the reference's algorithm)"}
         except Exception as e:  # pragma: no cover
             log("best-effort cpu leg failed:", e)
+    return line
 
-    h.close()
-    if not args.no_topn:
-        tn = topn_leg(args, capi, torch, dist, rank, world, local, dev)
+
+def run_c4_dsgd(args, torch, dist, capi, synth, rank, world, local, dev):
+    """N > 1: BASELINE configs[3] -- PMF k=128 on the Netflix shape, ONE data set split into N user blocks (strong scaling), DSGD
+    strata with the item blocks rotating over NVLink.  Parity is checked inside the run, before the timed region."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import dsgd_checks
+    from oracle import oracle as O
+    stream = torch.cuda.current_stream()
+
+    # ---- parity first: a run whose DSGD does not reproduce the oracle is not measured
+    par_cf = dsgd_checks.conflict_free(capi, dist, O, rank, world, local)
+    par_c1 = dsgd_checks.c1(capi, dist, O, rank, world, local)
+    parity = {"conflict_free_epoch_vs_oracle": par_cf, "c1_biasedmf_100_epochs_vs_oracle": par_c1,
+              "ok": bool(par_cf["ok"] and par_c1["ok"])}
+    if not parity["ok"]:
         if rank == 0:
-            line["topn"] = tn
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
+            log("DSGD PARITY FAILED:", parity)
+            print(json.dumps({"metric": METRIC, "value": None, "n_gpus": world, "parity": parity}), flush=True)
         dist.barrier()
-        dist.destroy_process_group()
+        sys.exit(3)
+
+    d = synth.make_ratings("netflix")
+    U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
+    lo, hi = rank * U // world, (rank + 1) * U // world
+    a, b = int(d["rowptr"][lo]), int(d["rowptr"][hi])
+    rowptr = np.ascontiguousarray(d["rowptr"][lo:hi + 1] - a)
+    col, val = np.ascontiguousarray(d["col"][a:b]), np.ascontiguousarray(d["val"][a:b])
+    P0, Q0, _, _ = synth.init_factors(U, I, C4_K, 11, False)
+    hyper = (C4_LR, C4_REG, C4_REG, 0.0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    h = capi.Handle(capi.MODEL_PMF, C4_K, device=local, seed=1)
+    h.set_stream(stream.cuda_stream)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    h.comm_init(rank, world, uid[0])
+    h.set_train_csr(hi - lo, I, rowptr, col, val)
+    h.set_factors(P0[lo:hi], Q0)
+    sampler = ClockSampler(index=local)
+    wl = []
+    for w in range(args.warmup):
+        wl.append(h.sgd_epoch(*hyper, w + 1))
+    launches0 = h.launch_count()
+    sampler.start()
+    total_ms, kms, losses = timed_epochs(torch, dist, h, world, stream, flush, args.steps, 0, hyper, args.warmup + 1)
+    clocks = sampler.stop()
+    launches = h.launch_count() - launches0
+    guard = h.sgd_safeguard()
+    losses = wl + losses
+    value = nnz * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e at N GPUs: every rank stages its shard from pinned host buffers, trains E epochs, reads its factors back
+    e2e = None
+    if not args.no_e2e:
+        nl = int(rowptr[-1])
+        rp, p1 = pinned_array(capi, rowptr.shape, np.int64); rp[:] = rowptr
+        cl, p2 = pinned_array(capi, (nl,), np.int32); cl[:] = col
+        vl, p3 = pinned_array(capi, (nl,), np.float64); vl[:] = val
+        hP, p4 = pinned_array(capi, (hi - lo, C4_K), np.float64); hQ, p5 = pinned_array(capi, (I, C4_K), np.float64)
+        hloss, p6 = pinned_array(capi, (E2E_EPOCHS,), np.float64)
+        L = capi.load()
+        vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+
+        def call():
+            hP[:] = P0[lo:hi]; hQ[:] = Q0
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rc = L.lrk_set_train_csr(h._h, hi - lo, I, vp(rp), vp(cl), vp(vl))
+            rc |= L.lrk_set_factors(h._h, vp(hP), vp(hQ), None, None, 0.0)
+            rc |= L.lrk_sgd_epochs(h._h, E2E_EPOCHS, C4_LR, 1.0, C4_LR, C4_REG, C4_REG, 0.0, 1, vp(hloss))
+            rc |= L.lrk_get_factors(h._h, vp(hP), vp(hQ), None, None)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if rc != 0:
+                raise RuntimeError("e2e call failed: %s" % L.lrk_last_error(h._h))
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        call()
+        calls = 2
+        tt = [call() for _ in range(calls)]
+        byt = torch.tensor([rp.nbytes + cl.nbytes + vl.nbytes + hP.nbytes + hQ.nbytes, hP.nbytes + hQ.nbytes + 8 * E2E_EPOCHS],
+                           dtype=torch.float64, device="cuda")
+        dist.all_reduce(byt)
+        e2e = {"value": nnz * E2E_EPOCHS * calls / float(np.sum(tt)), "unit": UNIT, "h2d_bytes_per_step": int(byt[0].item()),
+               "d2h_bytes_per_step": int(byt[1].item()),
+               "step": "one trainModel() per rank through the C ABI from pinned host buffers: lrk_set_train_csr(shard) + lrk_set_factors + "
+                       "lrk_sgd_epochs(%d) + lrk_get_factors (ring gather of the item factors); wall clock between barriers, max over ranks; "
+                       "bytes summed over ranks" % E2E_EPOCHS,
+               "ms_per_call": float(np.mean(tt)) * 1e3, "calls": calls}
+        for p in (p1, p2, p3, p4, p5, p6):
+            L.lrk_host_free(p)
+    peaks, which = measured_peaks()
+    roof = None
+    if rank == 0:
+        ws = ((hi - lo) + I) * C4_K * 4
+        roof = sgd_roofline(h, "sgd_rating_epoch_kernel<32,1,false,true,true> (one launch per DSGD stratum)", kms, int(rowptr[-1]),
+                            C4_BYTES_PER_UPDATE, C4_K, ws, peaks, which, None, "not measured under DSGD (ncu runs one GPU)")
+        roof["kernel_ms"] = kms
+        roof["note"] = "per GPU (rank 0): kernel_ms is the epoch on the stream = N stratum kernels + N ring exchanges + loss all-reduce; " + roof["note"]
+    h.close()
+
+    # ---- the same data set on ONE GPU of this box (rank 0, the others wait): the base of the strong-scaling claim and of the loss check
+    base = None
+    if not args.no_base:
+        if rank == 0:
+            h1 = capi.Handle(capi.MODEL_PMF, C4_K, device=local, seed=1)
+            h1.set_stream(stream.cuda_stream)
+            h1.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
+            h1.set_factors(P0, Q0)
+            t1_ms, k1_ms, l1 = timed_epochs(torch, None, h1, 1, stream, flush, args.steps, args.warmup, hyper, 1)
+            g1 = h1.sgd_safeguard()
+            h1.close()
+            v1 = nnz * args.steps / (t1_ms * 1e-3)
+            base = {"workload": workload_c4(U, I, nnz, 1), "n_gpus": 1, "value": v1, "unit": UNIT, "ms_per_step": t1_ms / args.steps,
+                    "final_loss": l1[-1], "rollbacks": g1["rollbacks"],
+                    "loss_ratio_dsgd_over_1gpu": losses[-1] / l1[-1], "speedup": value / v1}
+        dist.barrier()
+
+    # ---- r01's weak-scaling line (N ML-20M-shaped user shards), kept as an extra key
+    weak = None
+    if not args.no_weak:
+        weak = weak_ml20m(args, torch, dist, capi, synth, rank, world, local, dev, stream, flush)
+
+    if rank != 0:
+        return None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_c4(U, I, nnz, world)},
+        "run": {"update_mode": "atomic (REDG.E.ADD.F32x4)", "l2": "L2 flushed between timed steps (256 MiB memset, untimed)",
+                "parallelism": "DSGD %d strata per epoch, item blocks rotate over NVLink (%s)" % (world, h_exchange_desc()),
+                "losses": losses, "final_loss": losses[-1], "rollbacks": guard["rollbacks"], "conc_div": guard["conc_div"],
+                "note": "N=1 of this bench is BASELINE configs[1] (BiasedMF k=64, ML-20M shape), N>1 is configs[3] (this line): the two "
+                        "values are different workloads; the strong-scaling base of THIS workload is in strong_scaling_base"},
+        "parity": parity,
+        "strong_scaling_base": base,
+        "roofline": roof, "e2e": e2e, "weak_ml20m": weak,
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if guard["rollbacks"]:
+        log("WARNING: %d rollbacks" % guard["rollbacks"])
+    return line
+
+
+def h_exchange_desc():
+    if os.environ.get("LRK_DSGD_FUSED", "") == "1":
+        return "LRK_DSGD_FUSED=1: one cooperative kernel per epoch, peer stores + system-scope flags"
+    return "grouped ncclSend/ncclRecv after every stratum kernel"
+
+
+def weak_ml20m(args, torch, dist, capi, synth, rank, world, local, dev, stream, flush):
+    """every rank owns one ML-20M-shaped user shard over the same item catalogue (N x 20 000 263 ratings), BiasedMF k=64"""
+    d = synth.make_ratings("ml-20m", shard=rank)
+    U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
+    P0, _, bu0, _ = synth.init_factors(U, I, K_FACTORS, 100 + rank, True)
+    _, Q0, _, bi0 = synth.init_factors(U, I, K_FACTORS, 1, True)          # item side identical on every rank
+    m = torch.tensor([float(d["val"].mean())], dtype=torch.float64, device=dev)
+    dist.all_reduce(m)
+    mu = float(m.item()) / world
+    h = capi.Handle(capi.MODEL_BIASEDMF, K_FACTORS, device=local, seed=1)
+    h.set_stream(stream.cuda_stream)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    h.comm_init(rank, world, uid[0])
+    h.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
+    h.set_factors(P0, Q0, bu0, bi0, mu)
+    total_ms, kms, losses = timed_epochs(torch, dist, h, world, stream, flush, args.steps, args.warmup, (LR, REG, REG, REG_B), 1)
+    guard = h.sgd_safeguard()
+    h.close()
+    return {"metric": METRIC, "scaling": "weak", "value": nnz * world * args.steps / (total_ms * 1e-3), "unit": UNIT,
+            "ms_per_step": total_ms / args.steps, "kernel_ms": kms, "final_loss": losses[-1], "rollbacks": guard["rollbacks"],
+            "workload": "BiasedMF k=%d SGD epoch, %d ML-20M-shaped user shards (%d users x %d items, %d ratings in total), lr %g reg %g"
+                        % (K_FACTORS, world, U * world, I, nnz * world, LR, REG)}
 
 
 # ------------------------------------------------------------------------------------------------
 TOPN_USERS, TOPN_ITEMS, TOPN_K, TOPN_N, TOPN_TRAIN = 1 << 20, 1 << 20, 128, 10, 32
 
 
-def topn_leg(args, capi, torch, dist, rank, world, local, dev):
-    """top-10 users scored/s on configs[4]; users are sharded by contiguous block over the ranks (strong scaling,
-    no collective: every rank holds the full item matrix).  Returns the "topn" object (rank 0) or None."""
-    U, I, k, N = TOPN_USERS, TOPN_ITEMS, TOPN_K, TOPN_N
+def topn_inputs(rank, world):
+    """this rank's user block of configs[4]: factors N(0, 0.1^2) rounded through fp32, a 32-item train mask per user"""
+    U, I, k = TOPN_USERS, TOPN_ITEMS, TOPN_K
     lo, hi = rank * U // world, (rank + 1) * U // world
     nu = hi - lo
     rng_q = np.random.default_rng(0x4C520005)                       # item side identical on every rank
@@ -399,6 +665,14 @@ def topn_leg(args, capi, torch, dist, rank, world, local, dev):
     rowptr = np.arange(nu + 1, dtype=np.int64) * TOPN_TRAIN
     col = np.ascontiguousarray(cols.reshape(-1))
     val = np.ones(col.shape[0], np.float64)
+    return nu, rowptr, col, val, P, Q
+
+
+def topn_leg(args, capi, torch, dist, rank, world, local, dev):
+    """top-10 users scored/s on configs[4]; users are sharded by contiguous block over the ranks (strong scaling,
+    no collective: every rank holds the full item matrix).  Returns the "topn" object (rank 0) or None."""
+    U, I, k, N = TOPN_USERS, TOPN_ITEMS, TOPN_K, TOPN_N
+    nu, rowptr, col, val, P, Q = topn_inputs(rank, world)
     h = capi.Handle(capi.MODEL_BPR, k, device=local)
     h.set_train_csr(nu, I, rowptr, col, val)
     h.set_factors(P, Q)
@@ -425,6 +699,9 @@ def topn_leg(args, capi, torch, dist, rank, world, local, dev):
     out = None
     if rank == 0:
         peaks, which = measured_peaks()
+        tn_traffic, tn_traffic_how = None, "skipped"
+        if world == 1 and not args.no_traffic:
+            tn_traffic, tn_traffic_how = ncu_dram_bytes("topn", "topn_tc_kernel", 0, 6)
         kms = float(np.mean(sweep))
         flop = 2.0 * nu * I * k                                     # this rank's launch
         tf = flop / (kms * 1e-3) / 1e12
@@ -450,7 +727,7 @@ def topn_leg(args, capi, torch, dist, rank, world, local, dev):
                "roofline": {"bound": "tensor", "kernel": "topn_tc_kernel", "kernel_ms": kms, "achieved": tf, "peak": peaks["bf16_tflops"],
                             "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
                             "frac_of_sustained": tf / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
-                            "peak_source": which, "flop_per_launch": flop, "traffic": None},
+                            "peak_source": which, "flop_per_launch": flop, "traffic": tn_traffic, "traffic_source": tn_traffic_how},
                "parity": {"users_checked": 64, "bit_identical": ok},
                "cpu_baseline": {"value": 64 / cpu_dt, "unit": "users/s", "cores": int(O.lib().lro_max_threads()), "kind": "port",
                                 "sample": "64 users against the full catalogue, oracle restatement of recommendRank, OpenMP over users"}}
@@ -470,7 +747,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-topn", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the at-scale parity leg (N=1)")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu DRAM-traffic probes (N=1)")
+    ap.add_argument("--no-base", action="store_true", help="skip the 1-GPU base of the strong-scaling workload (N>1)")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling ML-20M extra line (N>1)")
+    ap.add_argument("--traffic-probe", default="", help="internal: child mode of the ncu traffic probe (sgd | topn)")
     args = ap.parse_args()
+    if args.traffic_probe:
+        traffic_probe(args.traffic_probe)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

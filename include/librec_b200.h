@@ -125,6 +125,16 @@ LRK_API int lrk_get_factors(lrk_handle_t h, double* P, double* Q, double* bu, do
  * writes *loss_out) when the loss is NaN/Inf. */
 LRK_API int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg_b,
                   int32_t epoch_idx, double* loss_out);
+/* replaces n_epochs iterations of trainModel() in one call, for the configurations in which the Java loop takes no decision between
+ * iterations: rec.recommender.earlystop=false and rec.learnrate.bolddriver=false (the shipped *-test.properties).  The learning
+ * rate follows updateLRate's decay branch (MatrixFactorizationRecommender.java:131-138): lr *= decay when 0 < decay < 1, clamped to
+ * max_lr when max_lr > 0, in float arithmetic.  losses_out[n_epochs] receives every epoch's loss (for the shim's log lines and its
+ * NaN check); stops at the first epoch that fails and returns its status. */
+LRK_API int lrk_sgd_epochs(lrk_handle_t h, int32_t n_epochs, float lr, float decay, float max_lr, float reg_u, float reg_i, double reg_b,
+                   int32_t first_epoch_idx, double* losses_out);
+/* staging statistics of the last lrk_set_train_csr: out[0] ratings staged, out[1] ratings staged as item-run tiles (32 ratings of
+ * one item, csrc/staging.cuh), out[2] largest item degree, out[3] smallest item degree that forms runs */
+LRK_API int lrk_stage_stats(lrk_handle_t h, int64_t out[4]);
 /* device time of the last lrk_sgd_epoch kernel in milliseconds (CUDA events on its stream) */
 LRK_API int lrk_last_epoch_ms(lrk_handle_t h, float* ms_out);
 /* Safeguard of the fast (parallel) SGD modes.  The reference applies one rating at a time; here thousands are in
@@ -181,11 +191,21 @@ LRK_API int lrk_topn_stats(lrk_handle_t h, int64_t* fast_users, int64_t* fallbac
  * Zeros if the exact path ran. */
 LRK_API int lrk_topn_phase_ms(lrk_handle_t h, float out[6]);
 
+/* ---- measurement aid ------------------------------------------------------------------ */
+/* L2 roofline probe of the SGD epoch kernels (no reference counterpart; bench.py's roofline.bound = "l2"): the epoch kernels gather
+ * factor rows through L2 and apply vector reductions (red.global.add.v4.f32) to them on an L2-resident factor set, so what bounds
+ * them is the L2's rate for exactly those two operations.  Runs them alone -- same instruction widths, rows of `row_floats` floats
+ * (64 or 128), uniformly random rows of a working set of `working_set_bytes` -- and reports GB/s of row bytes through L2:
+ * out_gbps[0] gathers only, [1] REDs only, [2] one RED per gather (the epoch kernel's mix). */
+LRK_API int lrk_probe_l2(lrk_handle_t h, uint64_t working_set_bytes, int32_t row_floats, double out_gbps[3]);
+
 /* ---- multi-GPU DSGD (one process per GPU) ----------------------------- */
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the host (torch.distributed / MPI / JVM) */
 LRK_API int lrk_comm_unique_id(uint8_t out[128]);
-/* joins the handle to a world of `world` ranks.  After this, lrk_set_train_csr expects the FULL
- * matrix on every rank and keeps only the rank's user block; lrk_set_factors likewise. */
+/* joins the handle to a world of `world` ranks.  After this, lrk_set_train_csr expects the
+ * rank's OWN user block (a CSR with the rank's users as rows 0..U_local-1 and GLOBAL item ids; every rank passes the same
+ * num_items) and lrk_set_factors the rank's rows of P / userBiases together with the FULL Q / itemBiases (identical on every
+ * rank).  lrk_get_factors returns the rank's user rows and the full item side gathered from the ring. */
 LRK_API int lrk_comm_init(lrk_handle_t h, int32_t rank, int32_t world, const uint8_t unique_id[128]);
 
 #ifdef __cplusplus

@@ -49,6 +49,9 @@ SIGNATURES = {
     "lrk_set_factors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "lrk_get_factors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lrk_sgd_epoch": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_double, C.c_int32, C.POINTER(C.c_double)]),
+    "lrk_sgd_epochs": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double, C.c_int32,
+                                 C.c_void_p]),
+    "lrk_stage_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "lrk_last_epoch_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "lrk_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "lrk_bpr_peek_samples": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, _i32p]),
@@ -61,6 +64,7 @@ SIGNATURES = {
     "lrk_topn_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "lrk_topn_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "lrk_sgd_safeguard_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "lrk_probe_l2": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
     "lrk_comm_unique_id": (C.c_int, [C.c_void_p]),
     "lrk_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }
@@ -164,6 +168,17 @@ class Handle:
         _check(rc, self._h)
         return loss.value
 
+    def sgd_epochs(self, n, lr, reg_u, reg_i, reg_b=0.0, first_epoch_idx=1, decay=1.0, max_lr=0.0):
+        losses = np.zeros(n, np.float64)
+        _check(load().lrk_sgd_epochs(self._h, n, lr, decay, max_lr, reg_u, reg_i, float(reg_b), first_epoch_idx, _ptr(losses)), self._h)
+        return losses
+
+    def stage_stats(self):
+        out = (C.c_int64 * 4)()
+        _check(load().lrk_stage_stats(self._h, out), self._h)
+        return {"ratings": out[0], "run_tile_ratings": out[1], "run_tile_share": (out[1] / out[0]) if out[0] else 0.0,
+                "max_item_degree": out[2], "run_min_degree": out[3]}
+
     def last_epoch_ms(self):
         ms = C.c_float()
         _check(load().lrk_last_epoch_ms(self._h, C.byref(ms)), self._h)
@@ -241,6 +256,12 @@ class Handle:
         return {"fast_users": a.value, "fallback_users": b.value, "ms": ms.value,
                 "phase_ms": {"operands": ph[0], "sweep": ph[1], "rescore": ph[2], "fallback": ph[3]},
                 "sweep_error_over_bound": ph[4], "resweep_users": int(ph[5])}
+
+    def probe_l2(self, working_set_bytes, row_floats):
+        """-> dict(gather, red, mix) GB/s of row bytes through L2 (measurement aid, include/librec_b200.h)"""
+        out = (C.c_double * 3)()
+        _check(load().lrk_probe_l2(self._h, int(working_set_bytes), int(row_floats), out), self._h)
+        return {"gather": out[0], "red": out[1], "mix": out[2]}
 
     # -- DSGD
     def comm_init(self, rank, world, unique_id):

@@ -82,6 +82,7 @@ struct DsgdState {
     std::vector<int32_t> bounds;        // world+1 item block bounds
     std::vector<int64_t> seg_off;       // world+1 offsets of the COO segments
     std::vector<double> seg_hot_share;  // per segment: largest share one item has of its ratings
+    std::vector<int64_t> bpr_qualify;   // per block: local users with 0 < |row in block| < width (population of bpr_draw_block)
     int32_t max_blk = 0;                // rows of the largest item block
     size_t buf_floats = 0;              // floats per rotating buffer: max_blk*ld + max_blk
     float* qbuf[2] = {nullptr, nullptr};
@@ -94,24 +95,8 @@ struct DsgdState {
     DsgdFused fused;                    // experimental one-kernel epoch (dsgd_fused.cuh), LRK_DSGD_FUSED=1
 };
 
-__global__ void item_hist_kernel(const int32_t* __restrict__ col, int64_t nnz, unsigned long long* __restrict__ cnt) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nnz) atomicAdd(cnt + col[t], 1ULL);
-}
-// key = (item block << 32) | hash  -> a radix sort groups by block and shuffles inside the block
-__global__ void dsgd_keys_kernel(const int64_t* __restrict__ rowptr, int32_t U, const int32_t* __restrict__ col, int64_t nnz,
-                                 const int32_t* __restrict__ bounds, int world, uint64_t seed,
-                                 int32_t* __restrict__ row_of, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nnz) return;
-    int32_t lo = 0, hi = U;
-    while (hi - lo > 1) { const int32_t m = (lo + hi) >> 1; if (rowptr[m] <= e) lo = m; else hi = m; }
-    row_of[e] = lo;
-    const int32_t c = col[e];
-    int b = 0;
-    while (b + 1 < world && c >= bounds[b + 1]) ++b;
-    keys[e] = ((uint64_t)b << 32) | lrk_hash32((uint64_t)e ^ (seed * 0xD6E8FEB86659FD93ull));
-    idx[e] = (uint32_t)e;
+__global__ void flag_bits_kernel(const int* __restrict__ flags, int* __restrict__ bits) {
+    if (threadIdx.x < 3) bits[threadIdx.x] = (flags[0] >> threadIdx.x) & 1;
 }
 __global__ void dsgd_gather_kernel(const uint32_t* __restrict__ perm, const uint64_t* __restrict__ keys_sorted,
                                    const int32_t* __restrict__ row_of, const int32_t* __restrict__ col,
@@ -175,7 +160,35 @@ static int dsgd_comm_init(lrk_handle_s* h, int rank, int world, const uint8_t* u
     return LRK_OK;
 }
 
-// rank-local user block: CSR with U_local rows and GLOBAL item ids
+// per (user, block): does the user have at least one and not all items of the block in the train row?  -> qualify[b] = number of
+// such users (the population bpr_draw_block samples from; 0 means the stratum has nobody to draw and must be skipped)
+__global__ void dsgd_bpr_qualify_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int32_t U,
+                                        const int32_t* __restrict__ bounds, int world, unsigned long long* __restrict__ qualify) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)U * world) return;
+    const int32_t u = (int32_t)(t / world);
+    const int b = (int)(t - (int64_t)u * world);
+    const int64_t rb = rowptr[u], re = rowptr[u + 1];
+    const int64_t lo = row_lower_bound(col, rb, re, bounds[b]), hi = row_lower_bound(col, lo, re, bounds[b + 1]);
+    const int64_t len = hi - lo;
+    if (len > 0 && len < (int64_t)(bounds[b + 1] - bounds[b])) atomicAdd(qualify + b, 1ULL);
+}
+// local ratings per item block from the local item degrees (one thread per item)
+__global__ void dsgd_block_counts_kernel(const uint32_t* __restrict__ deg, int32_t I, const int32_t* __restrict__ bounds, int world,
+                                         unsigned long long* __restrict__ cnt) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= I || deg[i] == 0) return;
+    int b = 0;
+    while (b + 1 < world && i >= bounds[b + 1]) ++b;
+    atomicAdd(cnt + b, (unsigned long long)deg[i]);
+}
+__global__ void u32_to_u64_kernel(const uint32_t* __restrict__ in, int32_t n, unsigned long long* __restrict__ out) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+// rank-local user block: CSR with U_local rows and GLOBAL item ids.  Everything that walks the nnz entries runs on the device and
+// takes its temporaries from the handle's staging arena (the host only sees O(numItems) and O(world) arrays).
 static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val) {
     NcclApi* n = nccl_api();
     cudaStream_t st = h->stream;
@@ -191,23 +204,68 @@ static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64
     if ((rc = lrk_dev_alloc(h, &h->d_si, (size_t)nnz))) return rc;
     if ((rc = lrk_dev_alloc(h, &h->d_sr, (size_t)nnz))) return rc;
     if ((rc = lrk_dev_alloc(h, &s->d_bounds, (size_t)world + 1))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_item_deg, (size_t)I))) return rc;
     LRK_CUDA(h, cudaMemcpyAsync(h->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)U + 1), cudaMemcpyHostToDevice, st));
-    LRK_CUDA(h, cudaMemcpyAsync(h->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    if (nnz > 0) LRK_CUDA(h, cudaMemcpyAsync(h->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
     h->U = U; h->I = I; h->nnz = nnz;
 
-    // global item popularity -> identical block bounds on every rank
-    unsigned long long* d_cnt = nullptr;
-    LRK_CUDA(h, cudaMalloc((void**)&d_cnt, sizeof(unsigned long long) * (size_t)I));
+    size_t tmp64 = 0;
+    LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp64, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
+                                                (uint32_t*)nullptr, (int)std::max<int64_t>(nnz, 1), 0, 64, st));
+    const size_t tmp_bytes = std::max(tmp64, stage_tile_keys_tmp_bytes(I, std::max<int64_t>(nnz, 1)));
+    const size_t nn = (size_t)std::max<int64_t>(nnz, 1);
+    LrkScratch sc;
+    if ((rc = lrk_scratch_begin(h, nn * (8 + 4 + 8 + 8 + 4 * 6) + (size_t)I * (16 + 8) + tmp_bytes + 64 * 256, &sc))) return rc;
+    double* d_val = sc.take<double>(nn);
+    int32_t* row_of = sc.take<int32_t>(nn);
+    uint64_t *keys = sc.take<uint64_t>(nn), *keys2 = sc.take<uint64_t>(nn);
+    uint32_t *idx = sc.take<uint32_t>(nn), *perm = sc.take<uint32_t>(nn);
+    TileKeyWork w;
+    w.k32 = sc.take<uint32_t>(nn); w.v32 = sc.take<uint32_t>(nn); w.k32_out = sc.take<uint32_t>(nn); w.sorted_e = sc.take<uint32_t>(nn);
+    w.deg = sc.take<uint32_t>((size_t)I); w.item_start = sc.take<uint32_t>((size_t)I);
+    w.runs = sc.take<uint32_t>((size_t)I); w.run_base = sc.take<uint32_t>((size_t)I);
+    w.max_deg = sc.take<uint32_t>(64);
+    w.tmp = sc.take<char>(tmp_bytes); w.tmp_bytes = tmp_bytes;
+    unsigned long long* d_cnt = sc.take<unsigned long long>((size_t)I);
+    unsigned long long* d_small = sc.take<unsigned long long>(192);        // [0,64) block counts, [64,128) BPR qualify counts, [128] flags
+    if (!d_val || !row_of || !keys || !keys2 || !idx || !perm || !w.k32 || !w.v32 || !w.k32_out || !w.sorted_e || !w.deg || !w.item_start ||
+        !w.runs || !w.run_base || !w.max_deg || !w.tmp || !d_cnt || !d_small)
+        return lrk_fail(h, LRK_ERR_NOMEM, "dsgd_set_train_csr", "scratch arena too small", __FILE__, __LINE__);
+    int* d_flags = reinterpret_cast<int*>(d_small + 128);
+    const int nb = lrk_ceil_div(nn, 256), ib = lrk_ceil_div(I, 256);
+
+    // validate the shard BEFORE anything indexes by column (same checks and messages as the single-GPU path); the flag is
+    // all-reduced so that every rank fails together and nobody is left waiting in a collective
+    LRK_CUDA(h, cudaMemsetAsync(d_small, 0, sizeof(unsigned long long) * 192, st));
+    if (nnz > 0) {
+        LRK_CUDA(h, cudaMemcpyAsync(d_val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        coo_rows_kernel<<<nb, 256, 0, st>>>(h->d_rowptr, U, nnz, row_of); LRK_LAUNCH_CHECK(h);
+    }
+    {
+        const int64_t m = nnz > U ? nnz : U;
+        csr_validate_kernel<<<lrk_ceil_div(m, 256), 256, 0, st>>>(h->d_rowptr, h->d_col, U, I, nnz, d_flags); LRK_LAUNCH_CHECK(h);
+        if (nnz > 0) { csr_validate_rows_kernel<<<nb, 256, 0, st>>>(h->d_rowptr, h->d_col, row_of, nnz, d_flags); LRK_LAUNCH_CHECK(h); }
+    }
+    int flags[4] = {0, 0, 0, 0};
+    {   // bit-wise OR across ranks: three counters (one per bit) summed
+        int* d_bits = d_flags + 4;
+        flag_bits_kernel<<<1, 32, 0, st>>>(d_flags, d_bits); LRK_LAUNCH_CHECK(h);
+        LRK_NCCL(h, n->AllReduce(d_bits, d_bits, 3, ncclInt32, ncclSum, (ncclComm_t)h->comm, st));
+        LRK_CUDA(h, cudaMemcpyAsync(flags, d_bits, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
+        LRK_CUDA(h, cudaStreamSynchronize(st));
+    }
+    if (flags[0]) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "rowptr is not a monotone prefix sum ending at nnz", __FILE__, __LINE__);
+    if (flags[1]) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "column index out of range", __FILE__, __LINE__);
+    if (flags[2]) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "columns must be strictly ascending inside a row", __FILE__, __LINE__);
+
+    // global item popularity -> identical block bounds on every rank (host work is O(numItems))
+    LRK_CUDA(h, cudaMemsetAsync(h->d_item_deg, 0, sizeof(uint32_t) * (size_t)I, st));
+    if (nnz > 0) { item_degree_kernel<<<nb, 256, 0, st>>>(h->d_col, nnz, h->d_item_deg); LRK_LAUNCH_CHECK(h); }
+    u32_to_u64_kernel<<<ib, 256, 0, st>>>(h->d_item_deg, I, d_cnt); LRK_LAUNCH_CHECK(h);
+    LRK_NCCL(h, n->AllReduce(d_cnt, d_cnt, (size_t)I, ncclUint64, ncclSum, (ncclComm_t)h->comm, st));
     std::vector<int64_t> cnt((size_t)I);
-    cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * (size_t)I, st);
-    if (e == cudaSuccess && nnz > 0) { item_hist_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(h->d_col, nnz, d_cnt); h->launches++; e = cudaGetLastError(); }
-    if (e != cudaSuccess) { cudaFree(d_cnt); LRK_CUDA(h, e); }
-    ncclResult_t nr = n->AllReduce(d_cnt, d_cnt, (size_t)I, ncclUint64, ncclSum, (ncclComm_t)h->comm, st);
-    if (nr == ncclSuccess) e = cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int64_t) * (size_t)I, cudaMemcpyDeviceToHost, st);
-    if (nr == ncclSuccess && e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_cnt);
-    LRK_NCCL(h, nr);
-    LRK_CUDA(h, e);
+    LRK_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int64_t) * (size_t)I, cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
     dsgd_item_bounds(cnt.data(), I, world, s->bounds);
     s->max_blk = 0;
     for (int b = 0; b < world; ++b) s->max_blk = std::max(s->max_blk, s->bounds[b + 1] - s->bounds[b]);
@@ -215,62 +273,39 @@ static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64
 
     // bucket by item block; inside a block: item-run tiles, then the shuffled rest (staging.cuh, stage_tile_keys)
     s->seg_off.assign((size_t)world + 1, 0);
+    s->seg_hot_share.assign((size_t)world, 0.0);
+    s->bpr_qualify.assign((size_t)world, 0);
+    dsgd_block_counts_kernel<<<ib, 256, 0, st>>>(h->d_item_deg, I, s->d_bounds, world, d_small); LRK_LAUNCH_CHECK(h);
+    if (h->cfg.model == LRK_MODEL_BPR && U > 0) {
+        dsgd_bpr_qualify_kernel<<<lrk_ceil_div((int64_t)U * world, 256), 256, 0, st>>>(h->d_rowptr, h->d_col, U, s->d_bounds, world, d_small + 64);
+        LRK_LAUNCH_CHECK(h);
+    }
     if (nnz > 0) {
-        double* d_val = nullptr; int32_t* row_of = nullptr; uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *idx = nullptr, *perm = nullptr;
-        void* tmp = nullptr; size_t tmp_bytes = 0;
-        uint32_t* w32 = nullptr;
-        TileKeyWork w;
-        memset(&w, 0, sizeof w);
-        e = cudaMalloc((void**)&d_val, sizeof(double) * (size_t)nnz);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&row_of, sizeof(int32_t) * (size_t)nnz);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&keys, sizeof(uint64_t) * (size_t)nnz);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&keys2, sizeof(uint64_t) * (size_t)nnz);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&idx, sizeof(uint32_t) * (size_t)nnz);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&perm, sizeof(uint32_t) * (size_t)nnz);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&w32, sizeof(uint32_t) * (4 * (size_t)nnz + 4 * (size_t)I + 64));
-        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, perm, (int)nnz, 0, 64, st);
-        tmp_bytes = std::max(tmp_bytes, stage_tile_keys_tmp_bytes(I, nnz));
-        if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) {
-            w.k32 = w32; w.v32 = w32 + nnz; w.k32_out = w32 + 2 * (size_t)nnz; w.sorted_e = w32 + 3 * (size_t)nnz;
-            w.deg = w32 + 4 * (size_t)nnz; w.item_start = w.deg + I; w.runs = w.item_start + I; w.run_base = w.runs + I;
-            w.max_deg = w.run_base + I;
-            w.tmp = tmp; w.tmp_bytes = tmp_bytes;
-            coo_rows_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(h->d_rowptr, U, nnz, row_of);
-            h->launches++;
-            e = cudaGetLastError();
-        }
-        int rc_k = LRK_OK;
-        if (e == cudaSuccess) rc_k = stage_tile_keys(h, h->d_col, I, nnz, s->d_bounds, world, h->cfg.seed + 977u * h->rank, w, keys, idx);
+        if ((rc = stage_tile_keys(h, h->d_col, I, nnz, s->d_bounds, world, h->cfg.seed + 977u * h->rank, w, keys, idx))) return rc;
         size_t tb = tmp_bytes;
-        if (e == cudaSuccess && rc_k == LRK_OK) e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, idx, perm, (int)nnz, 0, 64, st);
-        if (e == cudaSuccess && rc_k == LRK_OK) {
-            dsgd_gather_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(perm, keys2, row_of, h->d_col, d_val, s->d_bounds, nnz, h->d_su, h->d_si, h->d_sr);
-            h->launches++;
-            e = cudaGetLastError();
-        }
-        // segment offsets: per-block counts from the (host) item counts of THIS rank
-        std::vector<int64_t> local_cnt((size_t)world, 0);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        for (int64_t t = 0; t < nnz; ++t) {
-            const int32_t c = col[t];
-            int b = (int)(std::upper_bound(s->bounds.begin(), s->bounds.end(), c) - s->bounds.begin()) - 1;
-            if (b >= world) b = world - 1;
-            local_cnt[(size_t)b]++;
-        }
-        for (int b = 0; b < world; ++b) s->seg_off[(size_t)b + 1] = s->seg_off[(size_t)b] + local_cnt[(size_t)b];
-        uint32_t md[64] = {0};
-        if (e == cudaSuccess && rc_k == LRK_OK) e = cudaMemcpy(md, w.max_deg, sizeof(uint32_t) * 64, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && rc_k == LRK_OK) rc_k = lrk_dev_alloc(h, &h->d_item_deg, (size_t)I);
-        if (e == cudaSuccess && rc_k == LRK_OK) e = cudaMemcpy(h->d_item_deg, w.deg, sizeof(uint32_t) * (size_t)I, cudaMemcpyDeviceToDevice);
-        s->seg_hot_share.assign((size_t)world, 0.0);
-        for (int b = 0; b < world; ++b) if (local_cnt[(size_t)b] > 0) s->seg_hot_share[(size_t)b] = (double)md[b] / (double)local_cnt[(size_t)b];
-        cudaFree(d_val); cudaFree(row_of); cudaFree(keys); cudaFree(keys2); cudaFree(idx); cudaFree(perm); cudaFree(tmp); cudaFree(w32);
-        if (rc_k) return rc_k;
-        LRK_CUDA(h, e);
+        LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(w.tmp, tb, keys, keys2, idx, perm, (int)nnz, 0, 64, st));
+        dsgd_gather_kernel<<<nb, 256, 0, st>>>(perm, keys2, row_of, h->d_col, d_val, s->d_bounds, nnz, h->d_su, h->d_si, h->d_sr);
+        LRK_LAUNCH_CHECK(h);
+    }
+    unsigned long long small[128];
+    uint32_t md[64] = {0}, last_base = 0, last_runs = 0;
+    if (nnz > 0) {
+        LRK_CUDA(h, cudaMemcpyAsync(&last_base, w.run_base + (I - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        LRK_CUDA(h, cudaMemcpyAsync(&last_runs, w.runs + (I - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    LRK_CUDA(h, cudaMemcpyAsync(small, d_small, sizeof small, cudaMemcpyDeviceToHost, st));
+    if (nnz > 0) LRK_CUDA(h, cudaMemcpyAsync(md, w.max_deg, sizeof md, cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    h->run_tiles = (int64_t)last_base + (int64_t)last_runs;
+    h->max_item_deg = 0;
+    for (int b = 0; b < world; ++b) h->max_item_deg = std::max(h->max_item_deg, md[b]);
+    for (int b = 0; b < world; ++b) {
+        s->seg_off[(size_t)b + 1] = s->seg_off[(size_t)b] + (int64_t)small[b];
+        if (small[b] > 0) s->seg_hot_share[(size_t)b] = (double)md[b] / (double)small[b];
+        s->bpr_qualify[(size_t)b] = (int64_t)small[64 + b];
     }
     s->buf_floats = (size_t)s->max_blk * h->ld + (size_t)s->max_blk;
+    s->buf_floats = (s->buf_floats + 3) & ~(size_t)3;                       // float4-copyable
     for (int j = 0; j < 2; ++j) if ((rc = lrk_dev_alloc(h, &s->qbuf[j], s->buf_floats))) return rc;
     h->has_train = true;
     return LRK_OK;
@@ -317,7 +352,7 @@ static int dsgd_set_factors(lrk_handle_s* h, const double* P, const double* Q, c
     s->cur = 0; s->cur_block = b;
     if (h->cfg.model != LRK_MODEL_BPR) { int rc_n = refresh_user_norm2(h, false); if (rc_n) return rc_n; }
     LRK_CUDA(h, cudaStreamSynchronize(st));
-    h->prev_loss = -1.0; h->conc_div = 1; h->good_epochs = 0;
+    h->prev_loss = -1.0; h->conc_div = 1; h->good_epochs = 0; h->epochs_done = 0;
     h->mu = mu; h->has_factors = true; h->f64_valid = false;
     return LRK_OK;
 }
@@ -447,7 +482,8 @@ static int dsgd_fused_epoch(lrk_handle_s* h, DsgdState* s, float lr, float reg_u
     fp.buf_floats = (long long)s->buf_floats; fp.bi_off = (long long)s->max_blk * h->ld;
     fp.abort = f->d_abort;
     fp.spin_limit = 4000000000LL;                               // ~2 s at 2 GHz
-    const bool track = fp.seg[0].item_deg && (h->pnorm2_host > 0.25f || (h->pnorm2_host > 0.02f && h->pnorm2_host > 4.f * h->pnorm2_prev));
+    LRK_CUDA(h, cudaMemsetAsync(f->d_abort, 0, sizeof(int), h->stream));      // a timeout of an earlier epoch must not silence this one
+    const bool track = fp.seg[0].item_deg && sgd_want_track(h, h->G * h->V);
     switch (h->G) {
         case 16: rc = dsgd_fused_launch_gv<16, 1>(h, s, fp, track); break;          // k in 33..64 and 65..128: the benchmark shapes;
         case 32: rc = dsgd_fused_launch_gv<32, 1>(h, s, fp, track); break;          // smaller k stays on the sub-epoch loop
@@ -495,7 +531,8 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
         const int b = dsgd_block_at(rank, world, sub);
         float* buf = s->qbuf[s->cur];
         const int64_t off = s->seg_off[(size_t)b], cnt = s->seg_off[(size_t)b + 1] - off;
-        if (cnt > 0) {
+        const bool nobody = h->cfg.model == LRK_MODEL_BPR && (size_t)b < s->bpr_qualify.size() && s->bpr_qualify[(size_t)b] == 0;
+        if (cnt > 0 && !nobody) {
             SgdParams sp;
             memset(&sp, 0, sizeof sp);
             sp.su = h->d_su + off; sp.si = h->d_si + off; sp.sr = h->d_sr + off; sp.n = cnt;
@@ -569,6 +606,7 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     if (std::isnan(loss) || std::isinf(loss))
         return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);
     h->prev_loss = loss;
+    h->epochs_done++;
     if (h->conc_div > 1 && ++h->good_epochs >= 8) { h->conc_div /= 2; h->good_epochs = 0; }
     return LRK_OK;
 }

@@ -8,6 +8,7 @@
 #include "topn_exact.cuh"
 #include "topn_tc.cuh"
 #include "dsgd.cuh"
+#include "l2_probe.cuh"
 
 #include <cmath>
 #include <new>
@@ -212,7 +213,7 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     h->mu = mu;
     h->has_factors = true;
     h->f64_valid = true;
-    h->prev_loss = -1.0; h->conc_div = 1; h->good_epochs = 0;
+    h->prev_loss = -1.0; h->conc_div = 1; h->good_epochs = 0; h->epochs_done = 0;
     topn_tc_invalidate(h);
     return LRK_OK;
 }
@@ -249,7 +250,8 @@ int lrk_get_factors(lrk_handle_t h, double* P, double* Q, double* bu, double* bi
 }
 
 // -------------------------------------------------------------------------------------------
-static void fill_sgd_params(lrk_handle_s* h, SgdParams& sp, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx) {
+// read-only with respect to the handle (lrk_bpr_peek_samples uses it too)
+static void fill_sgd_params(const lrk_handle_s* h, SgdParams& sp, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx) {
     memset(&sp, 0, sizeof sp);
     sp.su = h->d_su; sp.si = h->d_si; sp.sr = h->d_sr; sp.n = h->nnz;
     sp.P = h->P32; sp.Q = h->Q32; sp.bu = h->bu32; sp.bi = h->bi32;
@@ -258,7 +260,6 @@ static void fill_sgd_params(lrk_handle_s* h, SgdParams& sp, float lr, float reg_
     sp.hot_share = lrk_is_rating_model(h) ? h->hot_share : 0.0;
     sp.item_deg = lrk_is_rating_model(h) ? h->d_item_deg : nullptr;
     sp.item_cum = h->cfg.model == LRK_MODEL_RANKSGD ? h->d_item_cum : nullptr;
-    if (h->h_pnorm2) { h->pnorm2_prev = h->pnorm2_host; h->pnorm2_host = *h->h_pnorm2; }
     // RankSGD: squared loss without regularisation -- B concurrent updates of one item act like ONE step lr * B * |p_u|^2
     // where the sequential walk contracts by exp(-lr * B * |p_u|^2).  Popular items are hit as positives and, by
     // construction of the sampler, as negatives (2 x share), and the two only agree while that product is small: the grid
@@ -281,7 +282,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
         if (rc) return rc;
         LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
         LRK_CUDA(h, cudaEventRecord(h->ev0, st));
-        if (h->nnz > 0 && (rc = exact_epoch(h, (ExactSchedule*)h->exact, lr, reg_u, reg_i, reg_b, &h->bar_generation))) return rc;
+        if (h->nnz > 0 && (rc = exact_epoch(h, (ExactSchedule*)h->exact, lr, reg_u, reg_i, reg_b))) return rc;
         LRK_CUDA(h, cudaEventRecord(h->ev1, st));
         topn_tc_invalidate(h);
         LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -293,6 +294,9 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
             return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);
         return LRK_OK;
     }
+    // curvature estimate of the epoch: the value the last norm refresh left in pinned memory (once per epoch call, so that a
+    // lrk_bpr_peek_samples between two epochs cannot change which kernel variant the next epoch picks)
+    if (h->h_pnorm2) { h->pnorm2_prev = h->pnorm2_host; h->pnorm2_host = *h->h_pnorm2; }
     SgdParams sp;
     fill_sgd_params(h, sp, lr, reg_u, reg_i, reg_b, epoch_idx);
     const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
@@ -334,7 +338,11 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
             LRK_CUDA(h, cudaMemcpyAsync(h->bi32, h->bk_bi, sizeof(float) * (size_t)h->I, cudaMemcpyDeviceToDevice, st));
         }
         h->conc_div *= 4; h->good_epochs = 0; h->rollbacks++;
-        if (track_norm && (rc = refresh_user_norm2(h, false))) return rc;
+        if (track_norm) {
+            if ((rc = refresh_user_norm2(h, true))) return rc;          // the restored factors' norm, visible to the host now
+            h->pnorm2_host = *h->h_pnorm2;
+            if (h->cfg.model == LRK_MODEL_RANKSGD) sp.hot_share = 8.0 * h->hot_share * (double)std::max(1.f, h->pnorm2_host);
+        }
     }
     h->f64_valid = false;
     topn_tc_invalidate(h);
@@ -343,7 +351,30 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
     if (std::isnan(loss) || std::isinf(loss))
         return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);
     h->prev_loss = loss;
+    h->epochs_done++;
     if (h->conc_div > 1 && ++h->good_epochs >= 8) { h->conc_div /= 2; h->good_epochs = 0; }
+    return LRK_OK;
+}
+
+int lrk_sgd_epochs(lrk_handle_t h, int32_t n_epochs, float lr, float decay, float max_lr, float reg_u, float reg_i, double reg_b,
+                   int32_t first_epoch_idx, double* losses_out) {
+    LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_REQUIRE(h, n_epochs >= 0 && (n_epochs == 0 || losses_out != nullptr), "bad arguments");
+    float rate = lr;
+    for (int32_t it = 0; it < n_epochs; ++it) {
+        const int rc = lrk_sgd_epoch(h, rate, reg_u, reg_i, reg_b, first_epoch_idx + it, losses_out + it);
+        if (rc) return rc;
+        // updateLRate without the bold driver (MatrixFactorizationRecommender.java:131-138): float arithmetic like the reference
+        if (decay > 0.f && decay < 1.f) rate *= decay;
+        if (max_lr > 0.f && rate > max_lr) rate = max_lr;
+    }
+    return LRK_OK;
+}
+
+int lrk_stage_stats(lrk_handle_t h, int64_t out[4]) {
+    LRK_REQUIRE(h, h != nullptr && out != nullptr, "NULL argument");
+    LRK_REQUIRE(h, h->has_train, "no train CSR");
+    out[0] = h->nnz; out[1] = 32 * h->run_tiles; out[2] = (int64_t)h->max_item_deg; out[3] = LRK_RUN_MIN_DEGREE;
     return LRK_OK;
 }
 
@@ -576,6 +607,12 @@ int lrk_topn_stats(lrk_handle_t h, int64_t* fast_users, int64_t* fallback_users,
     if (fallback_users) *fallback_users = h->topn_fallback_users;
     if (ms_out) *ms_out = h->topn_ms;
     return LRK_OK;
+}
+
+int lrk_probe_l2(lrk_handle_t h, uint64_t working_set_bytes, int32_t row_floats, double out_gbps[3]) {
+    LRK_REQUIRE(h, h != nullptr && out_gbps != nullptr, "NULL argument");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    return l2_probe_run(h, (size_t)working_set_bytes, row_floats, out_gbps);
 }
 
 int lrk_comm_unique_id(uint8_t out[128]) { return dsgd_unique_id(out); }

@@ -30,6 +30,8 @@ struct lrk_handle_s {
     int32_t* d_si = nullptr;
     float* d_sr = nullptr;
     bool has_train = false;
+    int64_t run_tiles = 0;    // 32-rating item-run tiles in the staged stream (lrk_stage_stats)
+    uint32_t max_item_deg = 0;
     double hot_share = 0.0;   // largest share one item has of the train ratings (stability cap of the SGD grid)
     float* d_pnorm2 = nullptr;        // mean |p_u|^2 at the start of the epoch (curvature term of that step)
     float pnorm2_host = 0.f;          // its host copy, refreshed with every loss read-back (picks the kernel variant)
@@ -51,6 +53,7 @@ struct lrk_handle_s {
     int good_epochs = 0;
     double prev_loss = -1.0;    // loss of the last accepted epoch (< 0: none yet)
     int64_t rollbacks = 0;
+    int epochs_done = 0;        // accepted epochs since lrk_set_factors (picks the kernel variant of the first epochs)
     double* d_loss = nullptr;   // device accumulator
     double* h_loss = nullptr;   // pinned
     float* h_pnorm2 = nullptr;  // pinned
@@ -71,7 +74,6 @@ struct lrk_handle_s {
 
     // reference-order (wavefront) schedule, see sgd_exact.cuh
     void* exact = nullptr;
-    unsigned long long bar_generation = 0;
 
     // DSGD
     void* comm = nullptr;   // ncclComm_t

@@ -166,10 +166,13 @@ __device__ __forceinline__ bool row_contains(const int32_t* __restrict__ col, in
 // BPRRecommender.java:54-67 restated with a counter-based generator: user uniform over users that
 // have at least one and fewer than numItems train items; positive uniform over the user's row;
 // negative uniform over items NOT in the row (rejection).  uniform(n) = mulhi(r32, n).
+// Both loops are bounded (LRK_BPR_MAX_ATTEMPTS Philox blocks each): the reference spins for ever when no user qualifies or a
+// user has rated (practically) everything; here such a sample is skipped (u = -1) instead of hanging the GPU.
+#define LRK_BPR_MAX_ATTEMPTS 256u
 __device__ __forceinline__ void bpr_draw(const SgdParams& p, int64_t s, int32_t& u, int32_t& pi, int32_t& nj) {
     const uint2 key = make_uint2(p.seed_lo, p.seed_hi);
     uint32_t attempt = 0;
-    for (;;) {
+    while (attempt < LRK_BPR_MAX_ATTEMPTS) {
         uint4 x = philox4x32_10(make_uint4((uint32_t)s, (uint32_t)(s >> 32), p.epoch, attempt++), key);
         u = (int32_t)__umulhi(x.x, (uint32_t)p.U);
         const int64_t b = __ldg(p.rowptr + u), e = __ldg(p.rowptr + u + 1);
@@ -180,14 +183,16 @@ __device__ __forceinline__ void bpr_draw(const SgdParams& p, int64_t s, int32_t&
         if (!row_contains(p.col, b, e, nj)) return;
         nj = (int32_t)__umulhi(x.w, (uint32_t)p.I);
         if (!row_contains(p.col, b, e, nj)) return;
-        for (;;) {
+        for (const uint32_t stop = attempt + LRK_BPR_MAX_ATTEMPTS; attempt < stop;) {
             x = philox4x32_10(make_uint4((uint32_t)s, (uint32_t)(s >> 32), p.epoch, attempt++), key);
             nj = (int32_t)__umulhi(x.x, (uint32_t)p.I); if (!row_contains(p.col, b, e, nj)) return;
             nj = (int32_t)__umulhi(x.y, (uint32_t)p.I); if (!row_contains(p.col, b, e, nj)) return;
             nj = (int32_t)__umulhi(x.z, (uint32_t)p.I); if (!row_contains(p.col, b, e, nj)) return;
             nj = (int32_t)__umulhi(x.w, (uint32_t)p.I); if (!row_contains(p.col, b, e, nj)) return;
         }
+        break;
     }
+    u = -1; pi = 0; nj = 0;
 }
 
 // first index in [b, e) with col >= x
@@ -207,7 +212,9 @@ __device__ __forceinline__ void bpr_draw_block(const SgdParams& p, int64_t s, in
     const uint32_t width = (uint32_t)(p.blk_hi - p.blk_lo);
     const int64_t sc = s + p.sample_base;
     uint32_t attempt = 0;
-    for (;;) {
+    // bounded like bpr_draw: a block in which no local user has both a positive and a free negative (width 1, or every user
+    // with ratings in the block has rated all of it) is skipped by the host (DsgdState::bpr_qualify); the cap covers the rest
+    while (attempt < LRK_BPR_MAX_ATTEMPTS) {
         uint4 x = philox4x32_10(make_uint4((uint32_t)sc, (uint32_t)(sc >> 32), p.epoch, attempt++), key);
         u = (int32_t)__umulhi(x.x, (uint32_t)p.U);
         const int64_t rb = __ldg(p.rowptr + u), re = __ldg(p.rowptr + u + 1);
@@ -219,14 +226,16 @@ __device__ __forceinline__ void bpr_draw_block(const SgdParams& p, int64_t s, in
         if (!row_contains(p.col, b, e, nj)) return;
         nj = p.blk_lo + (int32_t)__umulhi(x.w, width);
         if (!row_contains(p.col, b, e, nj)) return;
-        for (;;) {
+        for (const uint32_t stop = attempt + LRK_BPR_MAX_ATTEMPTS; attempt < stop;) {
             x = philox4x32_10(make_uint4((uint32_t)sc, (uint32_t)(sc >> 32), p.epoch, attempt++), key);
             nj = p.blk_lo + (int32_t)__umulhi(x.x, width); if (!row_contains(p.col, b, e, nj)) return;
             nj = p.blk_lo + (int32_t)__umulhi(x.y, width); if (!row_contains(p.col, b, e, nj)) return;
             nj = p.blk_lo + (int32_t)__umulhi(x.z, width); if (!row_contains(p.col, b, e, nj)) return;
             nj = p.blk_lo + (int32_t)__umulhi(x.w, width); if (!row_contains(p.col, b, e, nj)) return;
         }
+        break;
     }
+    u = -1; pi = p.blk_lo; nj = p.blk_lo;
 }
 
 __global__ void bpr_peek_kernel(SgdParams p, int64_t first, int64_t n, int32_t* out) {
@@ -507,6 +516,16 @@ static int64_t sgd_tile_mul(int64_t n) {
     return a % T ? a % T : 1;
 }
 
+// Which epoch kernel variant: TRACK follows mean |p_u|^2 of the rows in flight (curvature of the item-side step) instead of taking the
+// epoch-start value.  It is needed as soon as the user factors are no longer small, and whenever they may grow within the epoch:
+// PMF on un-centred ratings takes mean |p_u|^2 from 1e-4 to ~2 inside the FIRST epoch, so an epoch that starts far below any
+// threshold ends far above it (r01: config C4 under 2-GPU DSGD rolled back for exactly that reason).  Hence: always for the k > 64
+// layouts (3 CTAs/SM either way, the variant costs five shuffles per run tile), for the first two epochs after lrk_set_factors,
+// and from mean |p_u|^2 > 0.02 on.
+static bool sgd_want_track(const lrk_handle_s* h, int gv) {
+    return gv >= 32 || h->epochs_done < 2 || h->pnorm2_host > 0.02f;
+}
+
 template <int G, int V>
 static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp_in) {
     SgdParams sp = sp_in;
@@ -526,10 +545,7 @@ static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp_in) {
         sp.inflight_frac = (float)((double)grid * 8.0 * (double)(32 / G > 8 ? 32 / G : 8) / (double)(sp.n > 0 ? sp.n : 1)); \
         KERN<<<grid, 256, 0, h->stream>>>(sp);                                \
     } while (0)
-    // user factors no longer small -> the curvature-tracking variant (lrk_common.cuh, pnorm2_host)
-    // ... or growing fast: PMF on un-centred ratings takes mean |p_u|^2 from 1e-4 to ~8 within the first two epochs, and an
-    // epoch that starts below the threshold can end far above it (config C4 then needed the rollback in 1 run of 3)
-    bool track = atomic && sp.item_deg && (h->pnorm2_host > 0.25f || (h->pnorm2_host > 0.02f && h->pnorm2_host > 4.f * h->pnorm2_prev));
+    bool track = atomic && sp.item_deg && sgd_want_track(h, G * V);
     { static const bool trace = getenv("LRK_SGD_TRACE") && atoi(getenv("LRK_SGD_TRACE"));
       if (trace) fprintf(stderr, "[sgd] epoch %u n %lld mean|p|^2 %.5f (prev %.5f) track %d conc_div %d\n", sp.epoch, (long long)sp.n, h->pnorm2_host, h->pnorm2_prev, (int)track, sp.conc_div); }
     { static const char* env = getenv("LRK_SGD_TRACK"); if (env && atomic && sp.item_deg) track = atoi(env) != 0; }    // A/B probe

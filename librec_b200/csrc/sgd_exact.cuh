@@ -24,6 +24,7 @@ struct ExactSchedule {
     int32_t* d_i = nullptr;
     double* d_r = nullptr;
     unsigned long long* d_bar = nullptr;
+    unsigned long long generation = 0;   // arrivals counted by d_bar so far; lives and dies with d_bar (a re-staged schedule starts at 0)
 };
 
 struct ExactParams {
@@ -163,15 +164,14 @@ static int exact_build_schedule(lrk_handle_s* h, ExactSchedule** out, int32_t U,
     return LRK_OK;
 }
 
-static int exact_epoch(lrk_handle_s* h, ExactSchedule* s, float lr, float reg_u, float reg_i, double reg_b,
-                       unsigned long long* bar_generation) {
+static int exact_epoch(lrk_handle_s* h, ExactSchedule* s, float lr, float reg_u, float reg_i, double reg_b) {
     const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
     ExactParams p;
     memset(&p, 0, sizeof p);
     p.level_ptr = s->d_level_ptr; p.lu = s->d_u; p.li = s->d_i; p.lr_val = s->d_r; p.num_levels = s->num_levels;
     p.P = h->P64; p.Q = h->Q64; p.bu = h->bu64; p.bi = h->bi64;
     p.mu = h->mu; p.learn_rate = (double)lr; p.reg_u = (double)reg_u; p.reg_i = (double)reg_i; p.reg_b = reg_b;
-    p.k = h->k; p.loss = h->d_loss; p.bar = s->d_bar; p.bar_base = *bar_generation;
+    p.k = h->k; p.loss = h->d_loss; p.bar = s->d_bar; p.bar_base = s->generation;
     void* kern = biased ? (void*)sgd_reference_order_kernel<true> : (void*)sgd_reference_order_kernel<false>;
     int per_sm = 0;
     LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
@@ -183,6 +183,6 @@ static int exact_epoch(lrk_handle_s* h, ExactSchedule* s, float lr, float reg_u,
     void* args[] = {&p};
     LRK_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(256), args, 0, h->stream));
     h->launches++;
-    *bar_generation += (unsigned long long)s->num_levels * (unsigned long long)grid;
+    s->generation += (unsigned long long)s->num_levels * (unsigned long long)grid;
     return LRK_OK;
 }

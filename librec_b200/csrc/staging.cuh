@@ -217,12 +217,16 @@ static int stage_coo_from_csr(lrk_handle_s* h, const int64_t* d_rowptr, const in
         LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(w.tmp, tb, keys, keys2, idx, perm, (int)nnz, 0, 58, st));
         coo_gather_kernel<<<nb, 256, 0, st>>>(perm, row_of, d_col, d_val, nnz, su, si, sr);
         LRK_LAUNCH_CHECK(h);
-        uint32_t max_deg = 0;
+        uint32_t max_deg = 0, last_base = 0, last_runs = 0;
+        LRK_CUDA(h, cudaMemcpyAsync(&last_base, w.run_base + (I - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        LRK_CUDA(h, cudaMemcpyAsync(&last_runs, w.runs + (I - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if ((rc = lrk_dev_alloc(h, &h->d_item_deg, (size_t)I))) return rc;
         LRK_CUDA(h, cudaMemcpyAsync(h->d_item_deg, w.deg, sizeof(uint32_t) * (size_t)I, cudaMemcpyDeviceToDevice, st));
         LRK_CUDA(h, cudaMemcpyAsync(&max_deg, w.max_deg, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         LRK_CUDA(h, cudaStreamSynchronize(st));
         h->hot_share = (double)max_deg / (double)nnz;
+        h->run_tiles = (int64_t)last_base + (int64_t)last_runs;
+        h->max_item_deg = max_deg;
     }
     if (flags & 1) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "rowptr is not a monotone prefix sum ending at nnz", __FILE__, __LINE__);
     if (flags & 2) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "column index out of range", __FILE__, __LINE__);

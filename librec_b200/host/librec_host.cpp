@@ -556,7 +556,9 @@ void evaluateRankingExtra(const SequentialAccessSparseMatrix& test, const Recomm
         const int first = test.col[(size_t)tb];
         for (int t = 0; t < len; ++t)
             if (lst[(size_t)t].key == first) { ++hits; arhr += 1.0 / (t + 1.0); break; }
-        for (int64_t i = 0; i < nTest; ++i) idcgSum += 1 / (std::log((double)i + 2.0) / std::log(2.0));
+        double idcg = 0.0;                                   // IdealDCGEvaluator sums per user first, then adds
+        for (int64_t i = 0; i < nTest; ++i) idcg += 1 / (std::log((double)i + 2.0) / std::log(2.0));
+        idcgSum += idcg;
     }
     const std::string suffix = " top " + std::to_string(topN);
     if (wantHitRate) (*measures)["HitRate" + suffix] = usersWithTest ? 1.0 * hits / usersWithTest : 0.0;

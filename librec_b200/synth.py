@@ -14,7 +14,12 @@ SHAPES = {
     "ml-20m": (138493, 26744, 20000263, 0x4C520001),
     "netflix": (480189, 17770, 100480507, 0x4C520002),
     "ml-1m": (6040, 3706, 1000209, 0x4C520003),
+    # one tenth of the Netflix shape's users over the same 17 770-item catalogue and popularity law: the at-scale parity case
+    # the CPU oracle finishes in seconds per epoch (tests/parity_scale.py)
+    "netflix-10m": (48019, 17770, 10048050, 0x4C520002),
     "tiny": (2000, 1500, 60000, 0x4C520004),
+    # smallest shape whose top-N takes the tensor-core path (>= 512 users, >= 8192 items): __graft_entry__.smoke()
+    "small": (4096, 8192, 400000, 0x4C520006),
 }
 
 

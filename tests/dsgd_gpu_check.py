@@ -18,32 +18,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def shard_rows(U, world):
-    return [(r * U) // world for r in range(world + 1)]
-
-
-def local_csr(O, full, lo, hi):
-    a, b = full.rowptr[lo], full.rowptr[hi]
-    return O.Csr(hi - lo, full.I, full.rowptr[lo:hi + 1] - a, full.col[a:b], full.val[a:b])
+import dsgd_checks
+from dsgd_checks import run_dsgd as _run_dsgd
 
 
 def run_dsgd(capi, dist, torch, O, model, full, k, P, Q, bu, bi, mu, hyper, iters, rank, world, local):
-    sh = shard_rows(full.U, world)
-    mine = local_csr(O, full, sh[rank], sh[rank + 1])
-    h = capi.Handle(model, k, device=local, seed=1)
-    uid = [capi.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    h.comm_init(rank, world, uid[0])
-    h.set_train_csr(mine.U, mine.I, mine.rowptr, mine.col, mine.val)
-    h.set_factors(P[sh[rank]:sh[rank + 1]], Q, None if bu is None else bu[sh[rank]:sh[rank + 1]], bi, mu)
-    losses = [h.sgd_epoch(*hyper, it + 1) for it in range(iters)]
-    gP, gQ, gbu, gbi = h.get_factors()
-    h.close()
-    parts = [None] * world
-    dist.all_gather_object(parts, (gP, gbu))
-    allP = np.concatenate([p[0] for p in parts])
-    allbu = None if bu is None else np.concatenate([p[1] for p in parts])
-    return allP, gQ, allbu, gbi, losses
+    return _run_dsgd(capi, dist, O, model, full, k, P, Q, bu, bi, mu, hyper, iters, rank, world, local)[:5]
 
 
 def main():
@@ -58,35 +38,11 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.load()
 
-    # (1) conflict-free: every user and item exactly once
-    n, I, k = 4000, 5000, 64
-    rng = np.random.default_rng(3)
-    items = rng.permutation(I)[:n].astype(np.int32)
-    vals = rng.integers(1, 11, n).astype(np.float64) / 2.0
-    cf = O.Csr(n, I, np.arange(n + 1, dtype=np.int64), items, vals)
-    f32 = lambda a: a.astype(np.float32).astype(np.float64)
-    P, Q = f32(rng.normal(0, 0.1, (n, k))), f32(rng.normal(0, 0.1, (I, k)))
-    bu, bi = f32(rng.normal(0, 0.1, n)), f32(rng.normal(0, 0.1, I))
-    gP, gQ, gbu, gbi, losses = run_dsgd(capi, dist, torch, O, capi.MODEL_BIASEDMF, cf, k, P, Q, bu, bi, 3.0,
-                                        (0.01, 0.02, 0.03, 0.04), 1, rank, world, local)
-    oP, oQ, obu, obi = P.copy(), Q.copy(), bu.copy(), bi.copy()
-    oloss = O.lib().lro_biasedmf_epoch(cf.U, cf.rowptr, cf.col, cf.val, k, oP, oQ, obu, obi, 3.0, 0.01, 0.02, 0.03, 0.04, None, None)
-    ok1 = (np.allclose(gP, oP, rtol=0, atol=2e-6) and np.allclose(gQ, oQ, rtol=0, atol=2e-6) and
-           np.allclose(gbu, obu, rtol=0, atol=2e-6) and np.allclose(gbi, obi, rtol=0, atol=2e-6) and
-           abs(losses[0] - oloss) <= 2e-5 * abs(oloss))
-
-    # (2) C1
-    z = np.load(os.path.join(ROOT, "tests", "golden", "ml100k_seed1_split.npz"))
-    full = O.Csr(int(z["U"]), int(z["I"]), z["rowptr"].astype(np.int64), z["col"].astype(np.int32), z["val"].astype(np.float64))
-    tr, te = full.select(z["flags"] == 1), full.select(z["flags"] == 0)
-    pins = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_c1.json")))
-    O.lib().lro_rng_set_state(int(z["rng_seed"]), int(z["rng_have"]), float(z["rng_nextg"]))
-    P, Q, bu, bi = O.mf_setup(tr.U, tr.I, 20, True)
-    mu = pins["global_mean"]
-    gP, gQ, gbu, gbi, losses = run_dsgd(capi, dist, torch, O, capi.MODEL_BIASEDMF, tr, 20, P, Q, bu, bi, mu,
-                                        (0.002, 0.01, 0.01, 0.01), 100, rank, world, local)
-    rmse, mae = O.eval_rating(O.BIASEDMF, te, 20, gP, gQ, gbu, gbi, mu, 1.0, 5.0)
-    ok2 = abs(rmse - pins["biasedmf"]["rmse"]) < 1e-3 and abs(mae - pins["biasedmf"]["mae"]) < 1e-3
+    r1 = dsgd_checks.conflict_free(capi, dist, O, rank, world, local)
+    ok1 = r1["ok"]
+    r2 = dsgd_checks.c1(capi, dist, O, rank, world, local)
+    ok2 = r2["ok"]
+    z, tr, te, pins = dsgd_checks.load_c1(O)
     # (3) BPR: stratified DSGD vs one GPU, Precision@10 of the exact top-10 lists against the test split
     def precision_at_10(gP, gQ):
         users = np.flatnonzero(np.diff(te.rowptr) > 0).astype(np.int32)
@@ -111,10 +67,40 @@ def main():
         print("BPR DSGD world=%d: P@10 %.4f (one GPU %.4f)  loss_30 %.1f (one GPU %.1f)" % (world, prec_dsgd, prec_one, bl[-1], l1[-1]))
     ok3 = rank != 0 or (prec_dsgd > 0.1 and prec_dsgd >= 0.6 * prec_one)
     ok2 = ok2 and ok3
+    # (4) ADVICE r01: an invalid CSR on ONE rank must fail on EVERY rank with LRK_ERR_INVALID (no rank left waiting in NCCL)
+    sh = dsgd_checks.shard_rows(tr.U, world)
+    mine = dsgd_checks.local_csr(O, tr, sh[rank], sh[rank + 1])
+    bad_col = mine.col.copy()
+    if rank == world - 1 and bad_col.shape[0]:
+        bad_col[0] = tr.I + 7
+    h4 = capi.Handle(capi.MODEL_BIASEDMF, 8, device=local, seed=1)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    h4.comm_init(rank, world, uid[0])
+    try:
+        h4.set_train_csr(mine.U, mine.I, mine.rowptr, bad_col, mine.val)
+        ok4 = False
+    except capi.LibrecException as e:
+        ok4 = e.status == capi.ERR_INVALID and "column index out of range" in str(e)
+    h4.close()
+    # (5) ADVICE r01: a BPR stratum in which no local user has both a positive and a free negative must be skipped, not spin:
+    #     I == world -> every item block has width 1
+    n5 = 64
+    rng5 = np.random.default_rng(5)
+    dense = (rng5.random((n5, world)) < 0.6)
+    dense[:, 0] |= ~dense.any(axis=1)
+    r5, c5 = np.nonzero(dense)
+    rp5 = np.zeros(n5 + 1, np.int64); np.add.at(rp5, r5 + 1, 1)
+    tiny = O.Csr(n5, world, np.cumsum(rp5), c5.astype(np.int32), np.ones(r5.shape[0]))
+    P5, Q5 = rng5.normal(0, 0.1, (n5, 8)), rng5.normal(0, 0.1, (world, 8))
+    gP5, gQ5, _, _, l5 = run_dsgd(capi, dist, torch, O, capi.MODEL_BPR, tiny, 8, P5, Q5, None, None, 0.0, (0.05, 0.01, 0.01, 0.0), 2, rank, world, local)
+    ok5 = bool(np.isfinite(l5).all())
     if rank == 0:
-        print("conflict-free ok=%s  loss %.6f vs oracle %.6f" % (ok1, losses[0] if False else 0.0, oloss))
-        print("C1 DSGD world=%d: rmse %.6f (oracle %.6f)  mae %.6f (oracle %.6f)  loss_100 %.2f (oracle %.2f)" % (
-            world, rmse, pins["biasedmf"]["rmse"], mae, pins["biasedmf"]["mae"], losses[-1], pins["biasedmf"]["loss_100"]))
+        print("invalid shard fails everywhere: %s   width-1 BPR blocks are skipped: %s (losses %s)" % (ok4, ok5, l5))
+    ok2 = ok2 and ok4 and ok5
+    if rank == 0:
+        print("conflict-free:", r1)
+        print("C1 DSGD world=%d:" % world, r2)
         print("DSGD-CHECK OK" if (ok1 and ok2) else "DSGD-CHECK FAILED")
     dist.barrier()
     dist.destroy_process_group()

@@ -267,3 +267,71 @@ def test_empty_and_ragged_inputs(O, capi):
         h.set_train_csr(3, 3, empty.rowptr, empty.col, empty.val)
         h.set_factors(np.ones((3, 4)), np.ones((3, 4)))
         assert h.sgd_epoch(0.01, 0.01, 0.01) == 0.0
+
+
+@pytest.mark.timeout(120)
+def test_reference_order_mode_survives_restaging(O, capi):
+    """ADVICE r01: a second lrk_set_train_csr on a reference-order handle rebuilds the wavefront schedule and its barrier counter;
+    the epoch after it must not wait for arrivals counted on the old counter (it used to spin for ever -- e.g. cross-validation
+    folds reusing one handle).  Both stagings must also stay bit-identical to the oracle."""
+    k = 8
+    rng = np.random.default_rng(5)
+    with capi.Handle(capi.MODEL_PMF, k, update_mode=capi.UPDATE_REFERENCE_ORDER) as h:
+        for fold in range(2):
+            tr = rng_csr(O, 60, 50, 0.2, 100 + fold)
+            P, Q = rng.normal(0, 0.1, (60, k)), rng.normal(0, 0.1, (50, k))
+            h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+            h.set_factors(P, Q)
+            for it in range(3):
+                h.sgd_epoch(0.01, 0.05, 0.05, 0.0, it + 1)
+            gP, gQ, _, _ = h.get_factors()
+            oP, oQ = P.copy(), Q.copy()
+            for it in range(3):
+                O.lib().lro_pmf_epoch(tr.U, tr.rowptr, tr.col, tr.val, k, oP, oQ, 0.01, 0.05, 0.05, None, None)
+            assert np.array_equal(gP, oP) and np.array_equal(gQ, oQ)
+
+
+def test_peeking_samples_does_not_change_training(O, capi):
+    """lrk_bpr_peek_samples is read-only -- training with and without peeks in between gives the same factors"""
+    tr = rng_csr(O, 300, 200, 0.1, 9)
+    rng = np.random.default_rng(2)
+    P, Q = rng.normal(0, 0.1, (300, 16)), rng.normal(0, 0.1, (200, 16))
+    outs = []
+    for peek in (False, True):
+        with capi.Handle(capi.MODEL_RANKSGD, 16, seed=3) as h:
+            h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+            h.set_factors(P, Q)
+            losses = []
+            for it in range(4):
+                if peek:
+                    h.bpr_peek_samples(it + 1, 0, 64)
+                    h.bpr_peek_samples(it + 1, 0, 64)
+                losses.append(h.sgd_epoch(0.01, 0.0, 0.0, 0.0, it + 1))
+            outs.append(losses)
+    assert np.allclose(outs[0], outs[1], rtol=1e-3), outs    # atomics reorder fp32 sums; the kernel variant / grid must not change
+
+
+def test_sgd_epochs_batches_the_iterations(O, capi):
+    """lrk_sgd_epochs(n) == n x lrk_sgd_epoch with updateLRate's decay branch (MatrixFactorizationRecommender.java:131-138)"""
+    n, I, k = 2000, 3000, 16
+    tr = _conflict_free(O, n, I, 11)
+    rng = np.random.default_rng(4)
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    P, Q = f32(rng.normal(0, 0.1, (n, k))), f32(rng.normal(0, 0.1, (I, k)))
+    with capi.Handle(capi.MODEL_PMF, k) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        h.set_factors(P, Q)
+        la = h.sgd_epochs(3, 0.02, 0.05, 0.05, 0.0, 1, decay=0.5, max_lr=0.015)
+        A = h.get_factors()
+        h.set_factors(P, Q)
+        lb, lr = [], np.float32(0.02)
+        for it in range(3):
+            lb.append(h.sgd_epoch(float(lr), 0.05, 0.05, 0.0, it + 1))
+            lr = min(np.float32(lr * np.float32(0.5)), np.float32(0.015))
+        B = h.get_factors()
+    assert np.allclose(la, lb, rtol=1e-6) and np.allclose(A[0], B[0], atol=1e-6) and np.allclose(A[1], B[1], atol=1e-6)
+    st = None
+    with capi.Handle(capi.MODEL_PMF, k) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        st = h.stage_stats()
+    assert st["ratings"] == n and st["run_tile_ratings"] == 0
