@@ -76,10 +76,24 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
         if (bu != null) { bu.asDoubleBuffer().put(userBiases.getValues()); bi.asDoubleBuffer().put(itemBiases.getValues()); }
         check(LibrecB200.setFactors(handle, P, Q, bu, bi, globalMean));
         double[] lossOut = new double[1];
+        boolean boldDriver = conf.getBoolean("rec.learnrate.bolddriver", false);
+        if (!earlyStop && !boldDriver && !verbose) {
+            // no decision between iterations (the shipped *-test.properties): one native call for all of them; the decay branch of
+            // updateLRate runs natively (include/librec_b200.h, lrk_sgd_epochs), the NaN check of isConverged on every returned loss
+            double[] losses = new double[numIterations];
+            int st = LibrecB200.sgdEpochs(handle, numIterations, learnRate, decay, maxLearnRate, regUser, regItem, regBias, 1, losses);
+            for (int iter = 1; iter <= numIterations; iter++) {
+                loss = losses[iter - 1];
+                if (Double.isNaN(loss) || Double.isInfinite(loss))
+                    throw new LibrecException("Loss = NaN or Infinity: current settings does not fit the recommender! Change the settings and try again!");
+                lastLoss = loss;
+            }
+            if (st != 0 && st != LibrecB200.ERR_DIVERGED) check(st);
+        } else
         for (int iter = 1; iter <= numIterations; iter++) {
             int st = LibrecB200.sgdEpoch(handle, learnRate, regUser, regItem, regBias, iter, lossOut);
             loss = lossOut[0];
-            if (st != 0 && st != -5) check(st);            // -5 = LRK_ERR_DIVERGED: let isConverged throw the reference's exception
+            if (st != 0 && st != LibrecB200.ERR_DIVERGED) check(st);   // diverged: let isConverged throw the reference's exception
             if (isConverged(iter) && earlyStop) break;     // AbstractRecommender.java:249-267 (throws on NaN/Inf)
             updateLRate(iter);                             // MatrixFactorizationRecommender.java:121-139
         }
@@ -96,13 +110,18 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
         int n = dataList.size();
         int[] users = new int[n];
         for (int c = 0; c < n; c++) users[c] = ((BaseRankingDataEntry) dataList.getDataEntry(c)).getUserId();
-        int[] items = new int[n * topN]; double[] scores = new double[n * topN]; int[] counts = new int[n];
+        ByteBuffer items = LibrecB200.hostAlloc(4L * n * topN).order(ByteOrder.nativeOrder());
+        ByteBuffer scores = LibrecB200.hostAlloc(8L * n * topN).order(ByteOrder.nativeOrder());
+        ByteBuffer counts = LibrecB200.hostAlloc(4L * n).order(ByteOrder.nativeOrder());
         check(LibrecB200.topn(handle, users, n, topN, 1, items, scores, counts));
         RecommendedList list = new RecommendedList(numUsers);
         for (int c = 0; c < n; c++) {
             list.addList(new ArrayList<>());
-            for (int t = 0; t < counts[c]; t++) list.add(c, items[c * topN + t], scores[c * topN + t]);   // RecommendedList.java:134-151
+            int cnt = counts.getInt(4 * c);
+            for (int t = 0; t < cnt; t++)                                                             // RecommendedList.java:134-151
+                list.add(c, items.getInt(4 * (c * topN + t)), scores.getDouble(8 * (c * topN + t)));
         }
+        LibrecB200.hostFree(items); LibrecB200.hostFree(scores); LibrecB200.hostFree(counts);
         if (list.size() == 0) throw new IndexOutOfBoundsException("No item is recommended, there is something error in the recommendation algorithm! Please check it!");
         return list;
     }

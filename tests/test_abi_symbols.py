@@ -73,3 +73,24 @@ def test_enum_values_agree_across_header_binding_and_java_shim(capi):
     assert set(jconst) == {"MODEL_BIASEDMF", "MODEL_PMF", "MODEL_BPR", "MODEL_RANKSGD"}
     # the bad-model guard of test_bad_config_is_rejected relies on 7 being out of range
     assert max(v for k, v in header.items() if k.startswith("LRK_MODEL_")) < 7
+
+
+def test_jni_forwarder_compiles_and_covers_every_export():
+    """java/librec_b200_jni.c is the reference-side JNI binding of the C ABI.  No JDK in this image: it is compiled against a
+    minimal stand-in for jni.h (tests/stubs/jni.h) with -Wall -Werror, every lrk_* export must be forwarded by it, and every
+    JNI function must have a `static native` declaration of the same name in LibrecB200.java (and vice versa)."""
+    import shutil
+    import subprocess
+    src = os.path.join(ROOT, "java", "librec_b200_jni.c")
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc missing"
+    r = subprocess.run([gcc, "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "tests", "stubs"),
+                        "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(src).read(), flags=re.S)
+    called = set(re.findall(r"\b(lrk_[a-z0-9_]+)\s*\(", code))
+    assert sorted(called) == _declared()
+    jni_names = set(re.findall(r"LRK_JNI\((\w+)\)", code)) - {"name"}      # "name" is the macro parameter
+    java = open(os.path.join(ROOT, "java", "net", "librec", "recommender", "cuda", "LibrecB200.java")).read()
+    natives = set(re.findall(r"static native [\w\[\]]+ (\w+)\(", java))
+    assert jni_names == natives, (jni_names ^ natives)
