@@ -15,6 +15,7 @@
 #include "lrk_common.cuh"
 #include "staging.cuh"
 #include "sgd.cuh"
+#include "sgd_group.cuh"
 #include "dsgd_fused.cuh"
 #include <nccl.h>
 #include <dlfcn.h>
@@ -92,6 +93,9 @@ struct DsgdState {
     // LRK_DSGD_TRACE=1: events around every sub-epoch kernel / ring exchange of the last epoch
     std::vector<cudaEvent_t> trace_ev;
     int trace = -1;
+    float* q_ref = nullptr;             // BPR: the item factors at the start of the current window (delta all-reduce)
+    float* q_delta = nullptr;
+    int64_t bpr_samples = 0;            // BPR: samples this rank draws per epoch = numRates * (its users / all users)
     DsgdFused fused;                    // experimental one-kernel epoch (dsgd_fused.cuh), LRK_DSGD_FUSED=1
 };
 
@@ -107,6 +111,15 @@ __global__ void dsgd_gather_kernel(const uint32_t* __restrict__ perm, const uint
     const uint32_t e = perm[t];
     const int b = (int)(keys_sorted[t] >> 58);
     su[t] = row_of[e]; si[t] = col[e] - bounds[b]; sr[t] = (float)val[e];
+}
+// BPR windows: delta = Q - Qref ; after the all-reduce Q = Qref + sum of all ranks' deltas
+__global__ void dsgd_delta_kernel(const float* __restrict__ q, const float* __restrict__ ref, float* __restrict__ delta, int64_t n) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) delta[t] = q[t] - ref[t];
+}
+__global__ void dsgd_apply_delta_kernel(float* __restrict__ q, float* __restrict__ ref, const float* __restrict__ delta, int64_t n) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) { const float v = ref[t] + delta[t]; q[t] = v; ref[t] = v; }
 }
 __global__ void dsgd_pack_block_kernel(const float* __restrict__ Q, const float* __restrict__ bi, int32_t first, int32_t rows,
                                        int ld, int32_t max_blk, float* __restrict__ buf) {
@@ -127,7 +140,7 @@ static void dsgd_release(lrk_handle_s* h) {
     DsgdState* s = (DsgdState*)h->dsgd;
     if (s) {
         dsgd_fused_release(&s->fused);
-        cudaFree(s->qbuf[0]); cudaFree(s->qbuf[1]); cudaFree(s->d_bounds);
+        cudaFree(s->qbuf[0]); cudaFree(s->qbuf[1]); cudaFree(s->d_bounds); cudaFree(s->q_ref); cudaFree(s->q_delta);
         delete s;
         h->dsgd = nullptr;
     }
@@ -215,7 +228,7 @@ static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64
     const size_t tmp_bytes = std::max(tmp64, stage_tile_keys_tmp_bytes(I, std::max<int64_t>(nnz, 1)));
     const size_t nn = (size_t)std::max<int64_t>(nnz, 1);
     LrkScratch sc;
-    if ((rc = lrk_scratch_begin(h, nn * (8 + 4 + 8 + 8 + 4 * 6) + (size_t)I * (16 + 8) + tmp_bytes + 64 * 256, &sc))) return rc;
+    if ((rc = lrk_scratch_begin(h, nn * (8 + 4 + 8 + 8 + 4 * 6) + (size_t)I * (16 + 8) + (size_t)U * world * 20 + tmp_bytes + 80 * 256, &sc))) return rc;
     double* d_val = sc.take<double>(nn);
     int32_t* row_of = sc.take<int32_t>(nn);
     uint64_t *keys = sc.take<uint64_t>(nn), *keys2 = sc.take<uint64_t>(nn);
@@ -280,7 +293,16 @@ static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64
         dsgd_bpr_qualify_kernel<<<lrk_ceil_div((int64_t)U * world, 256), 256, 0, st>>>(h->d_rowptr, h->d_col, U, s->d_bounds, world, d_small + 64);
         LRK_LAUNCH_CHECK(h);
     }
-    if (nnz > 0) {
+    group_units_release((GroupUnits*)h->group);
+    h->group = nullptr;
+    const bool want_group = lrk_use_group_kernel(h) && group_order_supported(U, I, nnz, world);
+    if (nnz > 0 && want_group) {
+        GroupUnits* gu = nullptr;
+        LRK_CUDA(h, cudaMemsetAsync(w.max_deg, 0, sizeof(uint32_t) * 64, st));
+        if ((rc = stage_group_stream(h, h->d_rowptr, h->d_col, row_of, d_val, U, I, nnz, s->d_bounds, world, sgd_group_resident_workers(h, nullptr),
+                                     h->cfg.seed + 977u * h->rank, sc, w.tmp, tmp_bytes, keys, keys2, idx, perm, h->d_su, h->d_si, h->d_sr, &gu))) return rc;
+        h->group = gu;
+    } else if (nnz > 0) {
         if ((rc = stage_tile_keys(h, h->d_col, I, nnz, s->d_bounds, world, h->cfg.seed + 977u * h->rank, w, keys, idx))) return rc;
         size_t tb = tmp_bytes;
         LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(w.tmp, tb, keys, keys2, idx, perm, (int)nnz, 0, 64, st));
@@ -289,7 +311,7 @@ static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64
     }
     unsigned long long small[128];
     uint32_t md[64] = {0}, last_base = 0, last_runs = 0;
-    if (nnz > 0) {
+    if (nnz > 0 && !h->group) {
         LRK_CUDA(h, cudaMemcpyAsync(&last_base, w.run_base + (I - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         LRK_CUDA(h, cudaMemcpyAsync(&last_runs, w.runs + (I - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
@@ -303,6 +325,17 @@ static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64
         s->seg_off[(size_t)b + 1] = s->seg_off[(size_t)b] + (int64_t)small[b];
         if (small[b] > 0) s->seg_hot_share[(size_t)b] = (double)md[b] / (double)small[b];
         s->bpr_qualify[(size_t)b] = (int64_t)small[64 + b];
+    }
+    if (h->cfg.model == LRK_MODEL_BPR) {
+        // BPRRecommender.java:48-58 draws numRates samples per iteration, the user uniformly over ALL users: this rank's share is
+        // numRates * (its users / all users)
+        double tot[2] = {(double)nnz, (double)U};
+        double* d_tot = reinterpret_cast<double*>(d_cnt);
+        LRK_CUDA(h, cudaMemcpyAsync(d_tot, tot, sizeof tot, cudaMemcpyHostToDevice, st));
+        LRK_NCCL(h, n->AllReduce(d_tot, d_tot, 2, ncclFloat64, ncclSum, (ncclComm_t)h->comm, st));
+        LRK_CUDA(h, cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
+        LRK_CUDA(h, cudaStreamSynchronize(st));
+        s->bpr_samples = tot[1] > 0.0 ? (int64_t)(tot[0] * ((double)U / tot[1]) + 0.5) : 0;
     }
     s->buf_floats = (size_t)s->max_blk * h->ld + (size_t)s->max_blk;
     s->buf_floats = (s->buf_floats + 3) & ~(size_t)3;                       // float4-copyable
@@ -449,7 +482,7 @@ static int dsgd_fused_epoch(lrk_handle_s* h, DsgdState* s, float lr, float reg_u
     DsgdFused* f = &s->fused;
     if (f->enabled < 0) { const char* e = getenv("LRK_DSGD_FUSED"); f->enabled = e && atoi(e) ? 1 : 0; }
     const int world = h->world;
-    if (!f->enabled || world < 2 || world > LRK_FUSED_MAX_WORLD || h->cfg.model == LRK_MODEL_BPR ||
+    if (!f->enabled || h->group || world < 2 || world > LRK_FUSED_MAX_WORLD || h->cfg.model == LRK_MODEL_BPR ||
         h->cfg.update_mode != LRK_UPDATE_ATOMIC || h->V != 1 || h->G < 16)
         return LRK_OK;
     int coop = 0;
@@ -497,6 +530,44 @@ static int dsgd_fused_epoch(lrk_handle_s* h, DsgdState* s, float lr, float reg_u
     return LRK_OK;
 }
 
+// BPR across GPUs.  r01 sampled positives AND negatives inside the item block a rank holds (DSGD strata): items of different blocks
+// are then never compared and Precision@10 fell from 0.325 (one GPU) to 0.225 (2 GPUs) / 0.142 (8 GPUs).  The reference's sampler
+// (BPRRecommender.java:54-67) compares a positive with a negative from the WHOLE catalogue, so every rank keeps the full item
+// matrix (27 k x 128 floats = 14 MB on the ML-20M shape) and trains on its own users with exactly the reference's sampling
+// distribution; the epoch is cut into windows, and after each window the ranks all-reduce the CHANGE of the item matrix and
+// apply the sum -- the one real exchange step of this path.  Within a window a rank does not see the other ranks' item updates
+// (the same kind of staleness as ratings in flight on one GPU, one window long).
+#define LRK_BPR_WINDOWS 8
+static int dsgd_bpr_epoch(lrk_handle_s* h, DsgdState* s, float lr, float reg_u, float reg_i, int32_t epoch_idx) {
+    NcclApi* n = nccl_api();
+    cudaStream_t st = h->stream;
+    const int64_t nq = (int64_t)h->I * h->ld;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &s->q_ref, (size_t)nq))) return rc;
+    if ((rc = lrk_dev_alloc(h, &s->q_delta, (size_t)nq))) return rc;
+    LRK_CUDA(h, cudaMemcpyAsync(s->q_ref, h->Q32, sizeof(float) * (size_t)nq, cudaMemcpyDeviceToDevice, st));
+    const uint64_t seed = h->cfg.seed + 977u * (uint64_t)h->rank;
+    int64_t done = 0;
+    for (int w = 0; w < LRK_BPR_WINDOWS; ++w) {
+        const int64_t cnt = s->bpr_samples * (w + 1) / LRK_BPR_WINDOWS - done;
+        if (cnt > 0 && h->U > 0 && h->nnz > 0) {
+            SgdParams sp;
+            memset(&sp, 0, sizeof sp);
+            sp.n = cnt; sp.P = h->P32; sp.Q = h->Q32; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i;
+            sp.loss = h->d_loss; sp.ld = h->ld; sp.epoch = (uint32_t)epoch_idx;
+            sp.rowptr = h->d_rowptr; sp.col = h->d_col; sp.U = h->U; sp.I = h->I;
+            sp.seed_lo = (uint32_t)seed; sp.seed_hi = (uint32_t)(seed >> 32);
+            sp.sample_base = done; sp.conc_div = h->conc_div;
+            if ((rc = sgd_launch(h, sp))) return rc;
+        }
+        done += cnt;
+        dsgd_delta_kernel<<<lrk_ceil_div(nq, 256), 256, 0, st>>>(h->Q32, s->q_ref, s->q_delta, nq); LRK_LAUNCH_CHECK(h);
+        LRK_NCCL(h, n->AllReduce(s->q_delta, s->q_delta, (size_t)nq, ncclFloat32, ncclSum, (ncclComm_t)h->comm, st));
+        dsgd_apply_delta_kernel<<<lrk_ceil_div(nq, 256), 256, 0, st>>>(h->Q32, s->q_ref, s->q_delta, nq); LRK_LAUNCH_CHECK(h);
+    }
+    return LRK_OK;
+}
+
 static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, double* loss_out) {
     NcclApi* n = nccl_api();
     DsgdState* s = (DsgdState*)h->dsgd;
@@ -505,19 +576,23 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     // safeguard (lrk_common.cuh): snapshot of what this rank owns at the epoch boundary -- its user block and the
     // item block it holds; the loss is all-reduced, so every rank takes the same rollback decision
     const bool biased_ = h->cfg.model == LRK_MODEL_BIASEDMF;
+    const bool bpr_ = h->cfg.model == LRK_MODEL_BPR;
     const size_t np_ = (size_t)h->U * h->ld;
     {
         int rc_a;
         if ((rc_a = lrk_dev_alloc(h, &h->bk_P, np_))) return rc_a;
-        if ((rc_a = lrk_dev_alloc(h, &h->bk_Q, s->buf_floats))) return rc_a;
+        if ((rc_a = lrk_dev_alloc(h, &h->bk_Q, bpr_ ? (size_t)h->I * h->ld : s->buf_floats))) return rc_a;
         if (biased_ && (rc_a = lrk_dev_alloc(h, &h->bk_bu, (size_t)h->U))) return rc_a;
     }
     LRK_CUDA(h, cudaMemcpyAsync(h->bk_P, h->P32, sizeof(float) * np_, cudaMemcpyDeviceToDevice, st));
-    LRK_CUDA(h, cudaMemcpyAsync(h->bk_Q, s->qbuf[s->cur], sizeof(float) * s->buf_floats, cudaMemcpyDeviceToDevice, st));
+    if (bpr_) LRK_CUDA(h, cudaMemcpyAsync(h->bk_Q, h->Q32, sizeof(float) * (size_t)h->I * h->ld, cudaMemcpyDeviceToDevice, st));
+    else LRK_CUDA(h, cudaMemcpyAsync(h->bk_Q, s->qbuf[s->cur], sizeof(float) * s->buf_floats, cudaMemcpyDeviceToDevice, st));
     if (biased_) LRK_CUDA(h, cudaMemcpyAsync(h->bk_bu, h->bu32, sizeof(float) * (size_t)h->U, cudaMemcpyDeviceToDevice, st));
     if (h->h_pnorm2) { h->pnorm2_prev = h->pnorm2_host; h->pnorm2_host = *h->h_pnorm2; }
+    bool fused_done_last = false;
     for (int attempt = 0;; ++attempt) {
     LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
+    if (h->group) LRK_CUDA(h, cudaMemsetAsync(((GroupUnits*)h->group)->d_counter, 0, sizeof(unsigned int) * 64, st));
     LRK_CUDA(h, cudaEventRecord(h->ev0, st));
     if (s->trace < 0) { const char* t = getenv("LRK_DSGD_TRACE"); s->trace = t && atoi(t) ? 1 : 0; }
     if (s->trace && s->trace_ev.empty()) {
@@ -526,8 +601,10 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     }
     if (s->trace) LRK_CUDA(h, cudaEventRecord(s->trace_ev[0], st));
     bool fused_done = false;
-    { int rc_f = dsgd_fused_epoch(h, s, lr, reg_u, reg_i, reg_b, epoch_idx, &fused_done); if (rc_f) return rc_f; }
-    for (int sub = 0; !fused_done && sub < world; ++sub) {
+    fused_done_last = false;
+    if (bpr_) { int rc_b = dsgd_bpr_epoch(h, s, lr, reg_u, reg_i, epoch_idx); if (rc_b) return rc_b; }
+    else { int rc_f = dsgd_fused_epoch(h, s, lr, reg_u, reg_i, reg_b, epoch_idx, &fused_done); if (rc_f) return rc_f; }
+    for (int sub = 0; !bpr_ && !fused_done && sub < world; ++sub) {
         const int b = dsgd_block_at(rank, world, sub);
         float* buf = s->qbuf[s->cur];
         const int64_t off = s->seg_off[(size_t)b], cnt = s->seg_off[(size_t)b + 1] - off;
@@ -550,7 +627,19 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
             sp.conc_div = h->conc_div;
             sp.item_deg = (h->cfg.model != LRK_MODEL_BPR && h->d_item_deg) ? h->d_item_deg + s->bounds[(size_t)b] : nullptr;   // block-local item ids
             sp.pnorm2 = sp.item_deg ? h->d_pnorm2 : nullptr;
-            int rc = sgd_launch(h, sp);
+            int rc;
+            GroupUnits* gu = (GroupUnits*)h->group;
+            if (gu && h->cfg.model != LRK_MODEL_BPR) {
+                SgdGroupParams gp;
+                memset(&gp, 0, sizeof gp);
+                gp.su = h->d_su; gp.si = h->d_si; gp.sr = h->d_sr;                      // unit starts index the whole stream
+                gp.units = gu->d_units + gu->unit_base[(size_t)b];
+                gp.n_units = (int32_t)(gu->unit_base[(size_t)b + 1] - gu->unit_base[(size_t)b]);
+                gp.counter = gu->d_counter + b;
+                gp.P = sp.P; gp.Q = sp.Q; gp.bu = sp.bu; gp.bi = sp.bi; gp.mu = sp.mu; gp.lr = sp.lr; gp.reg_u = sp.reg_u; gp.reg_i = sp.reg_i;
+                gp.reg_b = sp.reg_b; gp.loss = sp.loss; gp.ld = sp.ld; gp.item_deg = sp.item_deg;
+                rc = sgd_group_launch(h, gp, cnt, h->conc_div);
+            } else rc = sgd_launch(h, sp);
             if (rc) return rc;
         }
         if (s->trace) LRK_CUDA(h, cudaEventRecord(s->trace_ev[(size_t)2 * sub + 1], st));
@@ -567,10 +656,11 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     }
     LRK_NCCL(h, n->AllReduce(h->d_loss, h->d_loss, 1, ncclFloat64, ncclSum, (ncclComm_t)h->comm, st));
     LRK_CUDA(h, cudaEventRecord(h->ev1, st));
-    if (h->cfg.model != LRK_MODEL_BPR && h->d_item_deg) { int rc_n = refresh_user_norm2(h, false); if (rc_n) return rc_n; }
+    if (h->cfg.model != LRK_MODEL_BPR && h->d_item_deg && !h->group) { int rc_n = refresh_user_norm2(h, false); if (rc_n) return rc_n; }
     h->f64_valid = false;
     LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
     LRK_CUDA(h, cudaStreamSynchronize(st));
+    fused_done_last = fused_done;
     if (fused_done) {
         int aborted = 0;
         LRK_CUDA(h, cudaMemcpy(&aborted, s->fused.d_abort, sizeof(int), cudaMemcpyDeviceToHost));
@@ -582,13 +672,14 @@ static int dsgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
         const bool bad = !std::isfinite(l_) || (h->prev_loss > 0.0 && l_ > 10.0 * h->prev_loss);
         if (!bad || attempt >= 6 || h->conc_div >= 4096) break;
         LRK_CUDA(h, cudaMemcpyAsync(h->P32, h->bk_P, sizeof(float) * np_, cudaMemcpyDeviceToDevice, st));
-        LRK_CUDA(h, cudaMemcpyAsync(s->qbuf[s->cur], h->bk_Q, sizeof(float) * s->buf_floats, cudaMemcpyDeviceToDevice, st));
+        if (bpr_) LRK_CUDA(h, cudaMemcpyAsync(h->Q32, h->bk_Q, sizeof(float) * (size_t)h->I * h->ld, cudaMemcpyDeviceToDevice, st));
+        else LRK_CUDA(h, cudaMemcpyAsync(s->qbuf[s->cur], h->bk_Q, sizeof(float) * s->buf_floats, cudaMemcpyDeviceToDevice, st));
         if (biased_) LRK_CUDA(h, cudaMemcpyAsync(h->bu32, h->bk_bu, sizeof(float) * (size_t)h->U, cudaMemcpyDeviceToDevice, st));
         h->conc_div *= 4; h->good_epochs = 0; h->rollbacks++;
-        if (h->cfg.model != LRK_MODEL_BPR && h->d_item_deg) { int rc_n = refresh_user_norm2(h, false); if (rc_n) return rc_n; }
+        if (h->cfg.model != LRK_MODEL_BPR && h->d_item_deg && !h->group) { int rc_n = refresh_user_norm2(h, false); if (rc_n) return rc_n; }
     }
     }
-    if (s->trace) {
+    if (s->trace && !fused_done_last && !bpr_) {
         std::string line = "[dsgd rank " + std::to_string(rank) + " epoch " + std::to_string(epoch_idx) + "]";
         for (int sub = 0; sub < world; ++sub) {
             float k_ms = 0.f, x_ms = 0.f;
@@ -620,11 +711,13 @@ static int dsgd_get_factors(lrk_handle_s* h, double* P, double* Q, double* bu, d
     const int64_t U = h->U, I = h->I;
     const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
     // all-gather the rotating buffers (every rank holds block `cur_block`), then unpack into Q32 / bi32
+    // (BPR keeps the full item matrix on every rank: nothing to gather)
     float* all = nullptr;
-    LRK_CUDA(h, cudaMalloc((void**)&all, sizeof(float) * s->buf_floats * (size_t)world));
-    ncclResult_t nr = n->AllGather(s->qbuf[s->cur], all, s->buf_floats, ncclFloat32, (ncclComm_t)h->comm, st);
+    const bool gather = h->cfg.model != LRK_MODEL_BPR;
+    if (gather) LRK_CUDA(h, cudaMalloc((void**)&all, sizeof(float) * s->buf_floats * (size_t)world));
+    ncclResult_t nr = gather ? n->AllGather(s->qbuf[s->cur], all, s->buf_floats, ncclFloat32, (ncclComm_t)h->comm, st) : ncclSuccess;
     cudaError_t e = cudaSuccess;
-    if (nr == ncclSuccess) {
+    if (nr == ncclSuccess && gather) {
         for (int r = 0; r < world && e == cudaSuccess; ++r) {
             const int b = dsgd_block_at(r, world, 0);     // between epochs rank r holds block r
             const int32_t first = s->bounds[b], rows = s->bounds[b + 1] - first;

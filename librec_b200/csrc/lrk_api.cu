@@ -3,6 +3,8 @@
 #include "lrk_common.cuh"
 #include "staging.cuh"
 #include "sgd.cuh"
+#include "staging_group.cuh"
+#include "sgd_group.cuh"
 #include "sgd_exact.cuh"
 #include <chrono>
 #include "topn_exact.cuh"
@@ -93,6 +95,7 @@ int lrk_destroy(lrk_handle_t h) {
     if (!h) return LRK_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    group_units_release((GroupUnits*)h->group);
     dsgd_release(h);
     topn_tc_release(h);
     exact_release((ExactSchedule*)h->exact);
@@ -147,8 +150,16 @@ int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowpt
     LRK_CUDA(h, cudaMemcpyAsync(h->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)U + 1), cudaMemcpyHostToDevice, st));
     LRK_CUDA(h, cudaMemcpyAsync(h->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
     h->U = U; h->I = I; h->nnz = nnz;
-    rc = stage_coo_from_csr(h, h->d_rowptr, h->d_col, val, U, I, nnz, h->d_su, h->d_si, h->d_sr, /*validate=*/true);
+    // BiasedMF / PMF in the default (atomic) mode train with the user-group kernel over a unit-ordered stream (sgd_group.cuh);
+    // Hogwild mode, the reference-order mode, BPR / RankSGD and layouts outside 32 < ld <= 128 keep the shuffled stream of sgd.cuh
+    group_units_release((GroupUnits*)h->group);
+    h->group = nullptr;
+    const bool want_group = lrk_use_group_kernel(h) && group_order_supported(U, I, nnz, 1);
+    GroupUnits* gu = nullptr;
+    rc = stage_coo_from_csr(h, h->d_rowptr, h->d_col, val, U, I, nnz, h->d_su, h->d_si, h->d_sr, /*validate=*/true,
+                            want_group ? sgd_group_resident_workers(h, nullptr) : 0, &gu);
     if (rc) return rc;
+    h->group = gu;
     if (h->cfg.model == LRK_MODEL_RANKSGD && nnz > 0) {
         // sampling table of the negatives: inclusive prefix sums of the item degrees (RankSGDRecommender.java:47-57)
         if ((rc = lrk_dev_alloc(h, &h->d_item_cum, (size_t)I))) return rc;
@@ -315,13 +326,23 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
         LRK_CUDA(h, cudaMemcpyAsync(h->bk_bi, h->bi32, sizeof(float) * (size_t)h->I, cudaMemcpyDeviceToDevice, st));
     }
     if (sp.item_deg) sp.pnorm2 = h->d_pnorm2;          // refreshed by refresh_user_norm2 at set_factors and after every epoch
-    const bool track_norm = sp.item_deg != nullptr || h->cfg.model == LRK_MODEL_RANKSGD;
+    // the group kernel takes the curvature from the rows it holds; the stream kernels need mean |p_u|^2 refreshed per epoch
+    const bool track_norm = !h->group && (sp.item_deg != nullptr || h->cfg.model == LRK_MODEL_RANKSGD);
     double loss = 0.0;
     for (int attempt = 0;; ++attempt) {
         sp.conc_div = h->conc_div;
         LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
         LRK_CUDA(h, cudaEventRecord(h->ev0, st));
-        if (h->nnz > 0 && (rc = sgd_launch(h, sp))) return rc;
+        if (h->nnz > 0 && h->group) {
+            GroupUnits* gu = (GroupUnits*)h->group;
+            SgdGroupParams gp;
+            memset(&gp, 0, sizeof gp);
+            gp.su = sp.su; gp.si = sp.si; gp.sr = sp.sr; gp.units = gu->d_units; gp.n_units = (int32_t)gu->n_units; gp.counter = gu->d_counter;
+            gp.P = sp.P; gp.Q = sp.Q; gp.bu = sp.bu; gp.bi = sp.bi; gp.mu = sp.mu; gp.lr = sp.lr; gp.reg_u = sp.reg_u; gp.reg_i = sp.reg_i;
+            gp.reg_b = sp.reg_b; gp.loss = sp.loss; gp.ld = sp.ld; gp.item_deg = sp.item_deg;
+            LRK_CUDA(h, cudaMemsetAsync(gu->d_counter, 0, sizeof(unsigned int), st));
+            if ((rc = sgd_group_launch(h, gp, h->nnz, h->conc_div))) return rc;
+        } else if (h->nnz > 0 && (rc = sgd_launch(h, sp))) return rc;
         LRK_CUDA(h, cudaEventRecord(h->ev1, st));
         if (track_norm && (rc = refresh_user_norm2(h, false))) return rc;
         LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));

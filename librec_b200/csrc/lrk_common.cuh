@@ -30,6 +30,7 @@ struct lrk_handle_s {
     int32_t* d_si = nullptr;
     float* d_sr = nullptr;
     bool has_train = false;
+    void* group = nullptr;    // GroupUnits*: the stream is unit-ordered (staging_group.cuh) and the epoch runs sgd_group_epoch_kernel
     int64_t run_tiles = 0;    // 32-rating item-run tiles in the staged stream (lrk_stage_stats)
     uint32_t max_item_deg = 0;
     double hot_share = 0.0;   // largest share one item has of the train ratings (stability cap of the SGD grid)

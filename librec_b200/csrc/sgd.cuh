@@ -169,8 +169,9 @@ __device__ __forceinline__ bool row_contains(const int32_t* __restrict__ col, in
 // Both loops are bounded (LRK_BPR_MAX_ATTEMPTS Philox blocks each): the reference spins for ever when no user qualifies or a
 // user has rated (practically) everything; here such a sample is skipped (u = -1) instead of hanging the GPU.
 #define LRK_BPR_MAX_ATTEMPTS 256u
-__device__ __forceinline__ void bpr_draw(const SgdParams& p, int64_t s, int32_t& u, int32_t& pi, int32_t& nj) {
+__device__ __forceinline__ void bpr_draw(const SgdParams& p, int64_t s_in, int32_t& u, int32_t& pi, int32_t& nj) {
     const uint2 key = make_uint2(p.seed_lo, p.seed_hi);
+    const int64_t s = s_in + p.sample_base;        // multi-GPU: the windows of one epoch draw from disjoint counter ranges
     uint32_t attempt = 0;
     while (attempt < LRK_BPR_MAX_ATTEMPTS) {
         uint4 x = philox4x32_10(make_uint4((uint32_t)s, (uint32_t)(s >> 32), p.epoch, attempt++), key);

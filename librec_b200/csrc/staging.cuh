@@ -169,8 +169,15 @@ __global__ void coo_rows_kernel(const int64_t* __restrict__ rowptr, int32_t U, i
     while (hi - lo > 1) { const int32_t m = (lo + hi) >> 1; if (rowptr[m] <= e) lo = m; else hi = m; }
     row_of[e] = lo;
 }
+struct GroupUnits;
+static int stage_group_stream(lrk_handle_s* h, const int64_t* d_rowptr, const int32_t* d_col, const int32_t* row_of, const double* d_val,
+                              int32_t U, int32_t I, int64_t nnz, const int32_t* d_bounds, int world, int workers, uint64_t seed,
+                              LrkScratch& sc, void* tmp, size_t tmp_bytes, uint64_t* keys, uint64_t* keys2, uint32_t* idx, uint32_t* perm,
+                              int32_t* su, int32_t* si, float* sr, GroupUnits** out);
+// group_workers > 0: stage the unit-ordered stream of the user-group kernel (staging_group.cuh) for that many resident workers
 static int stage_coo_from_csr(lrk_handle_s* h, const int64_t* d_rowptr, const int32_t* d_col, const double* h_val,
-                              int32_t U, int32_t I, int64_t nnz, int32_t* su, int32_t* si, float* sr, bool validate) {
+                              int32_t U, int32_t I, int64_t nnz, int32_t* su, int32_t* si, float* sr, bool validate,
+                              int group_workers = 0, GroupUnits** group_out = nullptr) {
     cudaStream_t st = h->stream;
     if (nnz == 0) { LRK_CUDA(h, cudaStreamSynchronize(st)); return LRK_OK; }
     size_t tmp64 = 0;
@@ -179,7 +186,7 @@ static int stage_coo_from_csr(lrk_handle_s* h, const int64_t* d_rowptr, const in
     const size_t tmp_bytes = std::max(tmp64, stage_tile_keys_tmp_bytes(I, nnz));
     const size_t n = (size_t)nnz;
     LrkScratch sc;
-    int rc = lrk_scratch_begin(h, n * (8 + 4 + 8 + 8 + 4 * 6) + (size_t)I * 16 + tmp_bytes + 32 * 256, &sc);
+    int rc = lrk_scratch_begin(h, n * (8 + 4 + 8 + 8 + 4 * 6) + (size_t)I * 16 + (size_t)U * 20 + tmp_bytes + 48 * 256, &sc);
     if (rc) return rc;
     double* d_val = sc.take<double>(n);
     int32_t* row_of = sc.take<int32_t>(n);
@@ -211,7 +218,17 @@ static int stage_coo_from_csr(lrk_handle_s* h, const int64_t* d_rowptr, const in
         LRK_CUDA(h, cudaStreamSynchronize(st));
     }
     (void)validate;
-    if (!flags) {
+    if (!flags && group_workers > 0) {
+        // item degrees (staleness-aware step), then the unit-ordered stream
+        LRK_CUDA(h, cudaMemsetAsync(w.deg, 0, sizeof(uint32_t) * (size_t)I, st));
+        item_degree_kernel<<<nb, 256, 0, st>>>(d_col, nnz, w.deg); LRK_LAUNCH_CHECK(h);
+        if ((rc = lrk_dev_alloc(h, &h->d_item_deg, (size_t)I))) return rc;
+        LRK_CUDA(h, cudaMemcpyAsync(h->d_item_deg, w.deg, sizeof(uint32_t) * (size_t)I, cudaMemcpyDeviceToDevice, st));
+        if ((rc = stage_group_stream(h, d_rowptr, d_col, row_of, d_val, U, I, nnz, nullptr, 1, group_workers, h->cfg.seed, sc, w.tmp, tmp_bytes,
+                                     keys, keys2, idx, perm, su, si, sr, group_out))) return rc;
+        LRK_CUDA(h, cudaStreamSynchronize(st));
+        h->hot_share = 0.0; h->run_tiles = 0; h->max_item_deg = 0;
+    } else if (!flags) {
         if ((rc = stage_tile_keys(h, d_col, I, nnz, nullptr, 1, h->cfg.seed, w, keys, idx))) return rc;
         size_t tb = tmp_bytes;
         LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(w.tmp, tb, keys, keys2, idx, perm, (int)nnz, 0, 58, st));
