@@ -135,6 +135,10 @@ LRK_API int lrk_sgd_epochs(lrk_handle_t h, int32_t n_epochs, float lr, float dec
 /* staging statistics of the last lrk_set_train_csr: out[0] ratings staged, out[1] ratings staged as item-run tiles (32 ratings of
  * one item, csrc/staging.cuh), out[2] largest item degree, out[3] smallest item degree that forms runs */
 LRK_API int lrk_stage_stats(lrk_handle_t h, int64_t out[4]);
+/* debug / test aid: the staged COO stream of the SGD epoch (su / si / sr, nnz entries each; any pointer may be NULL) and, when the
+ * stream is unit-ordered (csrc/staging_group.cuh), its unit table: units[4 * n] = {stream start, ratings, first user,
+ * users | slices << 16} for n = *n_units_out units (0 for the shuffled item-run-tile stream).  Single GPU: item ids are global. */
+LRK_API int lrk_debug_stream(lrk_handle_t h, int32_t* su, int32_t* si, float* sr, int32_t* units, int64_t max_units, int64_t* n_units_out);
 /* device time of the last lrk_sgd_epoch kernel in milliseconds (CUDA events on its stream) */
 LRK_API int lrk_last_epoch_ms(lrk_handle_t h, float* ms_out);
 /* Safeguard of the fast (parallel) SGD modes.  The reference applies one rating at a time; here thousands are in

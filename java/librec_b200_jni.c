@@ -116,6 +116,15 @@ jint LRK_JNI(bprPeekSamples)(JNIEnv* env, jclass c, jlong h, jint epochIdx, jlon
     return rc;
 }
 
+jint LRK_JNI(debugStream)(JNIEnv* env, jclass c, jlong h, jobject su, jobject si, jobject sr, jobject units, jlong maxUnits, jlongArray nUnitsOut1) {
+    int64_t n = 0; jlong v;
+    const int rc = lrk_debug_stream(H(h), (int32_t*)BUF(su), (int32_t*)BUF(si), (float*)BUF(sr), (int32_t*)BUF(units), maxUnits, &n);
+    (void)c;
+    v = (jlong)n;
+    (*env)->SetLongArrayRegion(env, nUnitsOut1, 0, 1, &v);
+    return rc;
+}
+
 /* ---- prediction --------------------------------------------------------------------- */
 jint LRK_JNI(predictPairs)(JNIEnv* env, jclass c, jlong h, jintArray users, jintArray items, jlong n, jdoubleArray out) {
     int32_t* u = (int32_t*)PIN(users); int32_t* i = (int32_t*)PIN(items); double* o = (double*)PIN(out);

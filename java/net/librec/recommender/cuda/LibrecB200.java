@@ -36,6 +36,7 @@ final class LibrecB200 {
     static native int sgdSafeguardState(long h, long[] concDivAndRollbacks);
     static native int launchCount(long h, long[] out1);
     static native int bprPeekSamples(long h, int epochIdx, long first, long n, int[] out3n);
+    static native int debugStream(long h, ByteBuffer su, ByteBuffer si, ByteBuffer sr, ByteBuffer units, long maxUnits, long[] nUnitsOut1);
     // prediction
     static native int predictPairs(long h, int[] users, int[] items, long n, double[] out);
     static native int evalRating(long h, int numUsers, ByteBuffer rowptr, ByteBuffer col, ByteBuffer val, double minRate,

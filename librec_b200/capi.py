@@ -52,6 +52,7 @@ SIGNATURES = {
     "lrk_sgd_epochs": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double, C.c_int32,
                                  C.c_void_p]),
     "lrk_stage_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "lrk_debug_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "lrk_last_epoch_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "lrk_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "lrk_bpr_peek_samples": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, _i32p]),
@@ -178,6 +179,15 @@ class Handle:
         _check(load().lrk_stage_stats(self._h, out), self._h)
         return {"ratings": out[0], "run_tile_ratings": out[1], "run_tile_share": (out[1] / out[0]) if out[0] else 0.0,
                 "max_item_degree": out[2], "run_min_degree": out[3]}
+
+    def debug_stream(self, nnz):
+        """-> (su, si, sr, units[n,4] or None): the staged stream and, for the unit-ordered stream, its unit table"""
+        su, si, sr = np.empty(nnz, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float32)
+        n = C.c_int64()
+        _check(load().lrk_debug_stream(self._h, None, None, None, None, 0, C.byref(n)), self._h)
+        units = np.empty((n.value, 4), np.int32) if n.value else None
+        _check(load().lrk_debug_stream(self._h, _ptr(su), _ptr(si), _ptr(sr), _ptr(units), n.value, C.byref(n)), self._h)
+        return su, si, sr, units
 
     def last_epoch_ms(self):
         ms = C.c_float()

@@ -476,20 +476,84 @@ static int dsgd_fused_launch_gv(lrk_handle_s* h, DsgdState* s, DsgdFusedParams& 
     return LRK_OK;
 }
 
+template <int G, int V>
+static int dsgd_fused_group_launch_gv(lrk_handle_s* h, DsgdFusedGroupParams& fp) {
+    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    void* kern = biased ? (void*)dsgd_fused_group_epoch_kernel<G, V, true> : (void*)dsgd_fused_group_epoch_kernel<G, V, false>;
+    const size_t smem = sgd_group_smem_bytes<G, V>();
+    LRK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    constexpr int WPC = 8 * (32 / G);
+    int64_t grid = (int64_t)h->sm_count * per_sm;
+    int64_t most = 1;
+    for (int t = 0; t < h->world; ++t) most = std::max<int64_t>(most, (fp.seg[t].n_units + WPC - 1) / WPC);
+    if (most < grid) grid = most;
+    if (h->conc_div > 1) grid /= h->conc_div;
+    if (grid < 1) grid = 1;
+    void* args[] = {(void*)&fp};
+    LRK_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(256), args, smem, h->stream));
+    h->launches++;
+    return (int)grid;
+}
+
 // true: the epoch's strata were run by the fused kernel (s->cur advanced like the loop would have); false: not applicable here
 static int dsgd_fused_epoch(lrk_handle_s* h, DsgdState* s, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, bool* done) {
     *done = false;
     DsgdFused* f = &s->fused;
     if (f->enabled < 0) { const char* e = getenv("LRK_DSGD_FUSED"); f->enabled = e && atoi(e) ? 1 : 0; }
     const int world = h->world;
-    if (!f->enabled || h->group || world < 2 || world > LRK_FUSED_MAX_WORLD || h->cfg.model == LRK_MODEL_BPR ||
-        h->cfg.update_mode != LRK_UPDATE_ATOMIC || h->V != 1 || h->G < 16)
+    if (!f->enabled || world < 2 || world > LRK_FUSED_MAX_WORLD || h->cfg.model == LRK_MODEL_BPR ||
+        h->cfg.update_mode != LRK_UPDATE_ATOMIC || h->V != 1 || (h->G < 16 && !h->group))
         return LRK_OK;
     int coop = 0;
     LRK_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->cfg.device));
     if (!coop) return LRK_OK;
     int rc = dsgd_fused_map(h, s);
     if (rc) return rc;
+    if (h->group) {
+        GroupUnits* gu = (GroupUnits*)h->group;
+        DsgdFusedGroupParams gp;
+        memset(&gp, 0, sizeof gp);
+        int ctas = 0;
+        const int workers = sgd_group_resident_workers(h, &ctas);
+        for (int t = 0; t < world; ++t) {
+            const int b = dsgd_block_at(h->rank, world, t);
+            const int64_t off = s->seg_off[(size_t)b], cnt = s->seg_off[(size_t)b + 1] - off;
+            SgdGroupParams& sp = gp.seg[t];
+            sp.su = h->d_su; sp.si = h->d_si; sp.sr = h->d_sr;
+            sp.units = gu->d_units + gu->unit_base[(size_t)b];
+            sp.n_units = cnt > 0 ? (int32_t)(gu->unit_base[(size_t)b + 1] - gu->unit_base[(size_t)b]) : 0;
+            sp.counter = gu->d_counter + b;
+            sp.P = h->P32; sp.bu = h->bu32;
+            sp.mu = (float)h->mu; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i; sp.reg_b = (float)reg_b;
+            sp.loss = h->d_loss; sp.ld = h->ld;
+            sp.item_deg = h->d_item_deg ? h->d_item_deg + s->bounds[(size_t)b] : nullptr;
+            const double w = (double)std::min<int64_t>((int64_t)workers / (h->conc_div > 1 ? h->conc_div : 1), std::max<int64_t>(sp.n_units, 1));
+            sp.inflight_frac = (float)(w / (double)(cnt > 0 ? cnt : 1));
+        }
+        gp.qbuf[0] = s->qbuf[0]; gp.qbuf[1] = s->qbuf[1];
+        gp.peer_qbuf[0] = f->peer_qbuf[0]; gp.peer_qbuf[1] = f->peer_qbuf[1];
+        gp.ready = f->d_flags; gp.peer_free = f->d_flags + 2;
+        gp.prev_ready = f->prev_flags; gp.next_peer_free = f->next_flags + 2;
+        gp.seq0 = f->seq; gp.cur0 = s->cur; gp.world = world;
+        gp.buf_floats = (long long)s->buf_floats; gp.bi_off = (long long)s->max_blk * h->ld;
+        gp.abort = f->d_abort;
+        gp.spin_limit = 4000000000LL;
+        LRK_CUDA(h, cudaMemsetAsync(f->d_abort, 0, sizeof(int), h->stream));
+        switch (h->G) {
+            case 8: rc = dsgd_fused_group_launch_gv<8, 1>(h, gp); break;
+            case 16: rc = dsgd_fused_group_launch_gv<16, 1>(h, gp); break;
+            default: rc = dsgd_fused_group_launch_gv<32, 1>(h, gp); break;
+        }
+        if (rc < 0) return rc;
+        f->seq += (unsigned long long)world;
+        s->cur = (s->cur + world) & 1;
+        s->cur_block = dsgd_block_at(h->rank, world, world);
+        *done = true;
+        return LRK_OK;
+    }
     DsgdFusedParams fp;
     memset(&fp, 0, sizeof fp);
     static const char* hf = getenv("LRK_SGD_HOT_FLUSH");

@@ -21,6 +21,7 @@
 #pragma once
 #include "lrk_common.cuh"
 #include "sgd.cuh"
+#include "sgd_group.cuh"
 #include <cooperative_groups.h>
 
 #define LRK_FUSED_MAX_WORLD 8
@@ -104,6 +105,61 @@ __global__ void __launch_bounds__(256, (G * V <= 16 && !TRACK) ? 4 : ((G * V <= 
     }
     // the block of the next epoch's first stratum must be complete before the kernel ends
     lrk_fused_wait(fp.ready + ((fp.cur0 + fp.world) & 1), fp.seq0 + (unsigned long long)fp.world, fp.abort, fp.spin_limit);
+}
+
+// the same epoch over the unit-ordered stream of the user-group kernel (sgd_group.cuh): per stratum the CTAs pull units from the
+// stratum's work counter (zeroed by the host before the launch), then the ring step as above
+struct DsgdFusedGroupParams {
+    SgdGroupParams seg[LRK_FUSED_MAX_WORLD];   // per stratum: units, counter, degrees, in-flight share; Q / bi filled in-kernel
+    float* qbuf[2];
+    float* peer_qbuf[2];
+    unsigned long long* ready;
+    unsigned long long* peer_free;
+    unsigned long long* prev_ready;
+    unsigned long long* next_peer_free;
+    unsigned long long seq0;
+    int cur0, world;
+    long long buf_floats, bi_off;
+    int* abort;
+    long long spin_limit;
+};
+
+template <int G, int V, bool BIASED>
+__global__ void __launch_bounds__(256, 3) dsgd_fused_group_epoch_kernel(DsgdFusedGroupParams fp) {
+    extern __shared__ float4 lrk_fused_group_smem4[];
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gthreads = (long long)gridDim.x * blockDim.x;
+    double loss_d = 0.0;
+    for (int t = 0; t < fp.world; ++t) {
+        const int b = (fp.cur0 + t) & 1;
+        const unsigned long long seq = fp.seq0 + (unsigned long long)t;
+        bool ok = lrk_fused_wait(fp.ready + b, seq, fp.abort, fp.spin_limit);
+        if (ok && fp.seg[t].n_units > 0) {
+            SgdGroupParams p = fp.seg[t];
+            p.Q = fp.qbuf[b];
+            p.bi = fp.qbuf[b] + fp.bi_off;
+            sgd_group_segment<G, V, BIASED>(p, reinterpret_cast<float*>(lrk_fused_group_smem4), loss_d);
+        }
+        __threadfence();
+        grid.sync();
+        ok = lrk_fused_wait(fp.peer_free + (b ^ 1), seq, fp.abort, fp.spin_limit);
+        if (ok) {
+            const float4* src = reinterpret_cast<const float4*>(fp.qbuf[b]);
+            float4* dst = reinterpret_cast<float4*>(fp.peer_qbuf[b ^ 1]);
+            const long long n4 = fp.buf_floats >> 2;
+            for (long long i = gtid; i < n4; i += gthreads) dst[i] = __ldcg(src + i);
+        }
+        __threadfence_system();
+        grid.sync();
+        if (gtid == 0 && *(volatile int*)fp.abort == 0) {
+            lrk_st_release_sys(fp.prev_ready + (b ^ 1), seq + 1ull);
+            lrk_st_release_sys(fp.next_peer_free + b, seq + 1ull);
+        }
+    }
+    lrk_fused_wait(fp.ready + ((fp.cur0 + fp.world) & 1), fp.seq0 + (unsigned long long)fp.world, fp.abort, fp.spin_limit);
+    block_loss_commit(loss_d, fp.seg[0].loss);
 }
 
 struct DsgdFused {

@@ -399,6 +399,25 @@ int lrk_stage_stats(lrk_handle_t h, int64_t out[4]) {
     return LRK_OK;
 }
 
+int lrk_debug_stream(lrk_handle_t h, int32_t* su, int32_t* si, float* sr, int32_t* units, int64_t max_units, int64_t* n_units_out) {
+    LRK_REQUIRE(h, h != nullptr && n_units_out != nullptr, "NULL argument");
+    LRK_REQUIRE(h, h->has_train, "no train CSR");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    GroupUnits* gu = (GroupUnits*)h->group;
+    *n_units_out = gu ? gu->n_units : 0;
+    const size_t n = (size_t)h->nnz;
+    if (su && n) LRK_CUDA(h, cudaMemcpyAsync(su, h->d_su, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (si && n) LRK_CUDA(h, cudaMemcpyAsync(si, h->d_si, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (sr && n) LRK_CUDA(h, cudaMemcpyAsync(sr, h->d_sr, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    if (units && gu) {
+        LRK_REQUIRE(h, max_units >= gu->n_units, "units buffer too small");
+        LRK_CUDA(h, cudaMemcpyAsync(units, gu->d_units, sizeof(int4) * (size_t)gu->n_units, cudaMemcpyDeviceToHost, st));
+    }
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    return LRK_OK;
+}
+
 int lrk_sgd_safeguard_state(lrk_handle_t h, int32_t* conc_div, int64_t* rollbacks) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
     if (conc_div) *conc_div = h->conc_div;

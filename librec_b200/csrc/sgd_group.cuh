@@ -16,11 +16,12 @@
 //
 // Concurrency of the item side: W workers hold an item row for the length of a pair (+ one rating of prefetch), so about
 // deg_i * (W * hold) / n ratings of item i are in flight at once.  As in sgd.cuh the RED of a pair is scaled by (1 - exp(-x)) / x,
-// x = lr * max(1, mean |p_u|^2 of the unit) * (deg_i - ratings of the pair) * inflight_frac: plain SGD for x -> 0, the sequential
+// x = lr * max(1, mean |p_u|^2 of the unit) * (deg_i - pair) * (W / n) * (pair + 1): plain SGD for x -> 0, the sequential
 // limit for the items everybody rates.  The curvature term comes from the unit's own rows (computed while they are loaded).
 //
-// Heavy users (more ratings in the block than a unit holds) are single-user units per slice; their slices run concurrently, so such a
-// unit adds (row - row as loaded) with a RED instead of storing the row.
+// Heavy users (more ratings in the block than a unit holds) are single-user units per slice; their slices run concurrently, each on a
+// private copy of the user's row, so such a unit merges every 16 / 32 ratings: it adds its change of the row with a RED (scaled for
+// the ratings the other slices have in flight, like an item row) and continues from the row as it then stands in global memory.
 #pragma once
 #include "lrk_common.cuh"
 #include "sgd.cuh"
@@ -38,17 +39,23 @@ struct SgdGroupParams {
     double* loss;
     int ld;
     const uint32_t* __restrict__ item_deg;   // ratings per item in this launch's shard (block-local ids); NULL: no damping
-    float inflight_frac;                // (resident workers * ratings a worker holds an item row for) / ratings of the launch
+    float inflight_frac;                // resident workers / ratings of the launch: share of the stream one rating-time covers
 };
-
-#define LRK_GROUP_HOLD 2.5f            // mean ratings a worker holds an item row for: pair length (~1.6) + one rating of prefetch
 
 template <int G, int V>
 __host__ __device__ constexpr int sgd_group_smem_floats_per_worker() { return LRK_GS * (4 * G * V) + LRK_GS; }
 
-// One worker = G lanes.  All G-lane workers of a warp run in lock-step: loops are warp-uniform, everything that depends on a
-// worker's own unit is predicated (the predicated blocks contain no warp-synchronous operation).  A lane only ever touches ITS four
-// columns of the unit's rows in shared memory, and only sub-lane 0 touches the biases, so no __syncwarp is needed inside a unit.
+template <int G>
+__device__ __forceinline__ float group_sum_masked(unsigned mask, float v) {
+#pragma unroll
+    for (int m = G / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(mask, v, m);
+    return v;
+}
+
+// One worker = G lanes; the 32/G workers of a warp share its instruction stream.  The chunk loop is warp-uniform (16 / 32 ratings
+// per worker and iteration, everything that depends on a worker's own data predicated); taking the next unit is a divergent block of
+// its own, entered by a worker whenever ITS unit is used up, so workers never wait for each other's units.  A lane only ever touches
+// its own four columns of the unit's rows in shared memory and only sub-lane 0 touches the biases: no __syncwarp inside a unit.
 template <int G, int V, bool BIASED>
 __device__ __forceinline__ void sgd_group_segment(const SgdGroupParams& p, float* smem_cta, double& loss_d) {
     constexpr int NWW = 32 / G;                    // workers per warp
@@ -57,179 +64,190 @@ __device__ __forceinline__ void sgd_group_segment(const SgdGroupParams& p, float
     const int lane = threadIdx.x & 31;
     const int sub = lane % G;
     const int grp = lane / G;
+    const unsigned wmask = G == 32 ? FULL : (((1u << (G & 31)) - 1u) << (grp * G));   // the lanes of this worker
     const int wk = (threadIdx.x >> 5) * NWW + grp;
     float* Ps = smem_cta + (size_t)wk * sgd_group_smem_floats_per_worker<G, V>();
     float* bus = Ps + LRK_GS * LDS;
     const float lr = p.lr, reg_u = p.reg_u, reg_i = p.reg_i, reg_b = p.reg_b, mu = p.mu;
-    bool alive = true;
 
-    for (;;) {
-        int unit = -1;
-        if (alive && sub == 0) unit = (int)atomicAdd(p.counter, 1u);
-        unit = __shfl_sync(FULL, unit, 0, G);
-        if (unit < 0 || unit >= p.n_units) alive = false;
-        if (!__any_sync(FULL, alive)) break;
-        int4 d = make_int4(0, 0, 0, 0);
-        if (alive) d = __ldg(p.units + unit);
-        const int64_t start = (int64_t)(uint32_t)d.x;
-        const int count = alive ? d.y : 0;
-        const int first = d.z;
-        const int nus = d.w & 0xffff;
-        const bool shared = (d.w >> 16) != 0;
-
-        // ---- the unit's user rows -> shared memory (each lane its own four columns of every row)
-        float4 p0[V];
-        float pn2 = 0.f;
+    bool alive = true, have = false;
+    int64_t start = 0;
+    int count = 0, first = 0, nus = 0, c = 0, slices = 1;
+    bool shared = false;
+    float curv = 1.f, bu0 = 0.f;
+    float4 p0[V], q[V], dq[V], qn[V];
+    int32_t cur = -1, qn_item = -1;               // item whose row is in q / prefetched in qn (block-local ids)
+    float bic = 0.f, dbi = 0.f, bin = 0.f;
+    int pair_len = 0;
 #pragma unroll
-        for (int v = 0; v < V; ++v) p0[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j = 0; j < nus; ++j) {
+    for (int v = 0; v < V; ++v) { p0[v] = make_float4(0.f, 0.f, 0.f, 0.f); q[v] = p0[v]; dq[v] = p0[v]; qn[v] = p0[v]; }
+
+    // the change of the current item row -> global memory, scaled for the ratings of that item other workers have in flight:
+    // while this worker held the row for pair_len (+1 of prefetch) ratings, the others applied about deg_i * (W / n) * (pair_len + 1)
+    auto flush = [&]() {
+        if (cur >= 0) {
+            float damp = 1.f;
+            if (p.item_deg) {
+                const float others = fmaxf((float)__ldg(p.item_deg + cur) - (float)pair_len, 0.f);
+                const float x = lr * curv * others * p.inflight_frac * (float)(pair_len + 1);
+                if (x > 1e-3f) damp = (1.f - __expf(-x)) / x;
+            }
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const float4 x = ldcg4(p.P + (int64_t)(first + j) * p.ld + (v * G + sub) * 4);
-                *reinterpret_cast<float4*>(Ps + j * LDS + (v * G + sub) * 4) = x;
-                pn2 += dot4(x, x);
-                if (j == 0) p0[v] = x;
+                const float4 t = make_float4(dq[v].x * damp, dq[v].y * damp, dq[v].z * damp, dq[v].w * damp);
+                apply4<true>(p.Q + (int64_t)cur * p.ld + (v * G + sub) * 4, t, t);
             }
-            if (BIASED && sub == 0) bus[j] = __ldcg(p.bu + first + j);
+            if (BIASED && sub == 0) apply1<true>(p.bi + cur, 0.f, dbi * damp);
         }
-        pn2 = group_sum<G>(pn2);
-        const float curv = fmaxf(1.f, nus > 0 ? pn2 / (float)nus : 0.f);
-        const float bu0 = (BIASED && sub == 0 && nus > 0) ? bus[0] : 0.f;
+        cur = -1; pair_len = 0;
+    };
+    // slice of a heavy user: its other slices run concurrently on other workers, each on a private copy of the user's row.  Merge:
+    // add this slice's change since the last merge (scaled like an item row: the other slices have (slices - 1) * ratings-per-merge
+    // ratings in flight) and continue from the row as it now stands in global memory
+    auto merge_shared_row = [&](int since) {
+        const float x = lr * curv * (float)((slices - 1) * since);
+        const float damp = x > 1e-3f ? (1.f - __expf(-x)) / x : 1.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            float* g = p.P + (int64_t)first * p.ld + (v * G + sub) * 4;
+            const float4 x4 = *reinterpret_cast<const float4*>(Ps + (v * G + sub) * 4);
+            const float4 t = make_float4((x4.x - p0[v].x) * damp, (x4.y - p0[v].y) * damp, (x4.z - p0[v].z) * damp, (x4.w - p0[v].w) * damp);
+            apply4<true>(g, t, t);
+            p0[v] = ldcg4(g);                     // same thread, same address: ordered after its own RED
+            *reinterpret_cast<float4*>(Ps + (v * G + sub) * 4) = p0[v];
+        }
+        if (BIASED && sub == 0) {
+            apply1<true>(p.bu + first, 0.f, (bus[0] - bu0) * damp);
+            bu0 = __ldcg(p.bu + first);
+            bus[0] = bu0;
+        }
+    };
 
-        // ---- walk the unit's ratings: chunks of G entries (lane `sub` loads entry c + sub), one rating per step and worker
-        int32_t cur = -1;                 // item whose row is in q (block-local id)
-        float4 q[V], dq[V], qn[V];
-        int32_t qn_item = -1;
-        float bic = 0.f, dbi = 0.f, bin = 0.f;
-        int pair_len = 0;
+    for (;;) {
+        if (alive && (!have || c >= count)) {
+            // ---- this worker's unit is used up: finish it, take the next one (divergent between the workers of a warp)
+            if (have) {
+                flush();
+                if (shared) merge_shared_row(count % G == 0 ? G : count % G);
+                else {
+                    for (int j = 0; j < nus; ++j) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v)
+                            __stcg(reinterpret_cast<float4*>(p.P + (int64_t)(first + j) * p.ld + (v * G + sub) * 4),
+                                   *reinterpret_cast<const float4*>(Ps + j * LDS + (v * G + sub) * 4));
+                        if (BIASED && sub == 0) __stcg(p.bu + first + j, bus[j]);
+                    }
+                }
+                have = false;
+            }
+            int unit = -1;
+            if (sub == 0) unit = (int)atomicAdd(p.counter, 1u);
+            unit = __shfl_sync(wmask, unit, grp * G);
+            if (unit >= p.n_units) alive = false;
+            else {
+                const int4 d = __ldg(p.units + unit);
+                start = (int64_t)(uint32_t)d.x; count = d.y; first = d.z; nus = d.w & 0xffff; shared = (d.w >> 16) != 0;
+                slices = shared ? (d.w >> 16) : 1;
+                c = 0; have = true; cur = -1; qn_item = -1; pair_len = 0;
+                float pn2 = 0.f;
+                for (int j = 0; j < nus; ++j) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const float4 x = ldcg4(p.P + (int64_t)(first + j) * p.ld + (v * G + sub) * 4);
+                        *reinterpret_cast<float4*>(Ps + j * LDS + (v * G + sub) * 4) = x;
+                        pn2 += dot4(x, x);
+                        if (j == 0) p0[v] = x;
+                    }
+                    if (BIASED && sub == 0) bus[j] = __ldcg(p.bu + first + j);
+                }
+                pn2 = group_sum_masked<G>(wmask, pn2);
+                curv = fmaxf(1.f, nus > 0 ? pn2 / (float)nus : 0.f);     // curvature of the item-side step: mean |p_u|^2 of the rows held
+                bu0 = (BIASED && sub == 0 && nus > 0) ? bus[0] : 0.f;
+            }
+        }
+        if (!__any_sync(FULL, alive)) break;
+        const bool on = alive && have;
+
+        // ---- one chunk: lane `sub` loads entry c + sub of its worker's unit, then G steps of one rating per worker
+        int32_t u_l = -1, i_l = -1;
+        float r_l = 0.f;
+        if (on && c + sub < count) {
+            const int64_t e = start + c + sub;
+            u_l = __ldcs(p.su + e) - first; i_l = __ldcs(p.si + e); r_l = __ldcs(p.sr + e);
+        }
+        int32_t un = __shfl_sync(FULL, u_l, 0, G), in_ = __shfl_sync(FULL, i_l, 0, G);
+        float rn = __shfl_sync(FULL, r_l, 0, G);
+        // first entry of the chunk: its item row unless it continues the current pair
+        if (un >= 0 && in_ != cur) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) qn[v] = ldcg4(p.Q + (int64_t)in_ * p.ld + (v * G + sub) * 4);
+            if (BIASED && sub == 0) bin = __ldcg(p.bi + in_);
+            qn_item = in_;
+        }
         float loss_f = 0.f;
 #pragma unroll
-        for (int v = 0; v < V; ++v) { q[v] = make_float4(0.f, 0.f, 0.f, 0.f); dq[v] = q[v]; qn[v] = q[v]; }
-
-        auto flush = [&]() {
-            if (cur >= 0) {
-                float damp = 1.f;
-                if (p.item_deg) {
-                    // ratings of this item in flight in OTHER workers (the pair itself was applied sequentially: nothing stale in it)
-                    const float others = fmaxf((float)__ldg(p.item_deg + cur) - (float)pair_len, 0.f);
-                    const float x = lr * curv * others * p.inflight_frac;
-                    if (x > 1e-3f) damp = (1.f - __expf(-x)) / x;
-                }
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const float4 t = make_float4(dq[v].x * damp, dq[v].y * damp, dq[v].z * damp, dq[v].w * damp);
-                    apply4<true>(p.Q + (int64_t)cur * p.ld + (v * G + sub) * 4, t, t);
-                }
-                if (BIASED && sub == 0) apply1<true>(p.bi + cur, 0.f, dbi * damp);
+        for (int s = 0; s < G; ++s) {
+            const int32_t uc = un, ic = in_;
+            const float rc = rn;
+            if (s + 1 < G) {
+                un = __shfl_sync(FULL, u_l, s + 1, G); in_ = __shfl_sync(FULL, i_l, s + 1, G); rn = __shfl_sync(FULL, r_l, s + 1, G);
             }
-        };
-
-        int warp_count = count;                      // the chunk loop is warp-uniform: longest unit among the warp's workers
+            const bool act = uc >= 0;
+            if (act && ic != cur) {          // new pair: flush the old one, take the prefetched row
+                flush();
 #pragma unroll
-        for (int m = G; m < 32; m <<= 1) warp_count = max(warp_count, __shfl_xor_sync(FULL, warp_count, m));
-        for (int c = 0; c < warp_count; c += G) {
-            int32_t u_l = -1, i_l = -1;
-            float r_l = 0.f;
-            if (c + sub < count) {
-                const int64_t e = start + c + sub;
-                u_l = __ldcs(p.su + e) - first; i_l = __ldcs(p.si + e); r_l = __ldcs(p.sr + e);
+                for (int v = 0; v < V; ++v) { q[v] = qn[v]; dq[v] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                bic = bin; dbi = 0.f; cur = ic; qn_item = -1;
             }
-            int32_t un = __shfl_sync(FULL, u_l, 0, G), in_ = __shfl_sync(FULL, i_l, 0, G);
-            float rn = __shfl_sync(FULL, r_l, 0, G);
-            // first entry of the chunk: its item row unless it continues the current pair or was prefetched
-            if (un >= 0 && in_ != cur && in_ != qn_item) {
+            // prefetch the next pair's item row while this rating is processed
+            if (s + 1 < G && un >= 0 && in_ != ic) {
 #pragma unroll
                 for (int v = 0; v < V; ++v) qn[v] = ldcg4(p.Q + (int64_t)in_ * p.ld + (v * G + sub) * 4);
                 if (BIASED && sub == 0) bin = __ldcg(p.bi + in_);
                 qn_item = in_;
             }
+            float4 pc[V];
+            float part = 0.f, buc = 0.f;
+            const int urow = act ? uc : 0;
 #pragma unroll
-            for (int s = 0; s < G; ++s) {
-                const int32_t uc = un, ic = in_;
-                const float rc = rn;
-                if (s + 1 < G) {
-                    un = __shfl_sync(FULL, u_l, s + 1, G); in_ = __shfl_sync(FULL, i_l, s + 1, G); rn = __shfl_sync(FULL, r_l, s + 1, G);
-                }
-                const bool act = uc >= 0;
-                if (act && ic != cur) {          // new pair: flush the old one, take the prefetched row
-                    flush();
-#pragma unroll
-                    for (int v = 0; v < V; ++v) { q[v] = qn[v]; dq[v] = make_float4(0.f, 0.f, 0.f, 0.f); }
-                    bic = bin; dbi = 0.f; cur = ic; pair_len = 0; qn_item = -1;
-                }
-                // prefetch the next pair's item row while this rating is processed
-                if (s + 1 < G && un >= 0 && in_ != ic) {
-                    {
-#pragma unroll
-                        for (int v = 0; v < V; ++v) qn[v] = ldcg4(p.Q + (int64_t)in_ * p.ld + (v * G + sub) * 4);
-                        if (BIASED && sub == 0) bin = __ldcg(p.bi + in_);
-                        qn_item = in_;
-                    }
-                }
-                float4 pc[V];
-                float part = 0.f, buc = 0.f;
-                const int urow = act ? uc : 0;
+            for (int v = 0; v < V; ++v) {
+                pc[v] = act ? *reinterpret_cast<const float4*>(Ps + urow * LDS + (v * G + sub) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                part += dot4(pc[v], q[v]);
+            }
+            if (BIASED && sub == 0 && act) { buc = bus[urow]; part += buc + bic + mu; }
+            const float pred = group_sum<G>(part);
+            const float err = rc - pred;
+            if (act) {
+                float reg_acc = 0.f;
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
-                    pc[v] = *reinterpret_cast<const float4*>(Ps + urow * LDS + (v * G + sub) * 4);
-                    part += dot4(pc[v], q[v]);
+                    const float4 a = pc[v], b = q[v];
+                    float4 np, dqs;
+                    np.x = a.x + lr * (err * b.x - reg_u * a.x); dqs.x = lr * (err * a.x - reg_i * b.x);
+                    np.y = a.y + lr * (err * b.y - reg_u * a.y); dqs.y = lr * (err * a.y - reg_i * b.y);
+                    np.z = a.z + lr * (err * b.z - reg_u * a.z); dqs.z = lr * (err * a.z - reg_i * b.z);
+                    np.w = a.w + lr * (err * b.w - reg_u * a.w); dqs.w = lr * (err * a.w - reg_i * b.w);
+                    *reinterpret_cast<float4*>(Ps + urow * LDS + (v * G + sub) * 4) = np;
+                    q[v].x += dqs.x; q[v].y += dqs.y; q[v].z += dqs.z; q[v].w += dqs.w;
+                    dq[v].x += dqs.x; dq[v].y += dqs.y; dq[v].z += dqs.z; dq[v].w += dqs.w;
+                    reg_acc += reg_u * dot4(a, a) + reg_i * dot4(b, b);
                 }
-                if (BIASED && sub == 0) { buc = bus[urow]; part += buc + bic + mu; }
-                const float pred = group_sum<G>(part);
-                const float err = rc - pred;
-                if (act) {
-                    float reg_acc = 0.f;
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const float4 a = pc[v], b = q[v];
-                        float4 np, dqs;
-                        np.x = a.x + lr * (err * b.x - reg_u * a.x); dqs.x = lr * (err * a.x - reg_i * b.x);
-                        np.y = a.y + lr * (err * b.y - reg_u * a.y); dqs.y = lr * (err * a.y - reg_i * b.y);
-                        np.z = a.z + lr * (err * b.z - reg_u * a.z); dqs.z = lr * (err * a.z - reg_i * b.z);
-                        np.w = a.w + lr * (err * b.w - reg_u * a.w); dqs.w = lr * (err * a.w - reg_i * b.w);
-                        *reinterpret_cast<float4*>(Ps + urow * LDS + (v * G + sub) * 4) = np;
-                        q[v].x += dqs.x; q[v].y += dqs.y; q[v].z += dqs.z; q[v].w += dqs.w;
-                        dq[v].x += dqs.x; dq[v].y += dqs.y; dq[v].z += dqs.z; dq[v].w += dqs.w;
-                        reg_acc += reg_u * dot4(a, a) + reg_i * dot4(b, b);
+                if (sub == 0) {
+                    reg_acc += err * err;
+                    if (BIASED) {
+                        bus[urow] = buc + lr * (err - reg_b * buc);
+                        const float dbs = lr * (err - reg_b * bic);
+                        reg_acc += reg_b * (buc * buc + bic * bic);
+                        bic += dbs; dbi += dbs;
                     }
-                    if (sub == 0) {
-                        reg_acc += err * err;
-                        if (BIASED) {
-                            bus[urow] = buc + lr * (err - reg_b * buc);
-                            const float dbs = lr * (err - reg_b * bic);
-                            reg_acc += reg_b * (buc * buc + bic * bic);
-                            bic += dbs; dbi += dbs;
-                        }
-                    }
-                    loss_f += reg_acc;
-                    ++pair_len;
                 }
+                loss_f += reg_acc;
+                ++pair_len;
             }
         }
-        flush();
-        cur = -1;
         loss_d += (double)loss_f;
-
-        // ---- write the unit's user rows back: exclusive owner -> plain stores; slice of a heavy user -> RED of the change
-        if (shared) {
-            if (nus > 0) {
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const float4 x = *reinterpret_cast<const float4*>(Ps + (v * G + sub) * 4);
-                    const float4 t = make_float4(x.x - p0[v].x, x.y - p0[v].y, x.z - p0[v].z, x.w - p0[v].w);
-                    apply4<true>(p.P + (int64_t)first * p.ld + (v * G + sub) * 4, t, t);
-                }
-                if (BIASED && sub == 0) apply1<true>(p.bu + first, 0.f, bus[0] - bu0);
-            }
-        } else {
-            for (int j = 0; j < nus; ++j) {
-#pragma unroll
-                for (int v = 0; v < V; ++v)
-                    __stcg(reinterpret_cast<float4*>(p.P + (int64_t)(first + j) * p.ld + (v * G + sub) * 4),
-                           *reinterpret_cast<const float4*>(Ps + j * LDS + (v * G + sub) * 4));
-                if (BIASED && sub == 0) __stcg(p.bu + first + j, bus[j]);
-            }
-        }
+        c += G;
+        if (on && shared && c < count) merge_shared_row(G);
     }
 }
 
@@ -285,7 +303,7 @@ static int sgd_group_launch_gv(lrk_handle_s* h, SgdGroupParams& gp, int64_t n_ra
     if (conc_div > 1) grid /= conc_div;                      // rollback safeguard: fewer units in flight
     if (grid < 1) grid = 1;
     const double workers = (double)std::min<int64_t>(grid * WPC, gp.n_units);
-    gp.inflight_frac = (float)(workers * (double)LRK_GROUP_HOLD / (double)(n_ratings > 0 ? n_ratings : 1));
+    gp.inflight_frac = (float)(workers / (double)(n_ratings > 0 ? n_ratings : 1));
     const size_t smem = sgd_group_smem_bytes<G, V>();
     if (h->cfg.model == LRK_MODEL_BIASEDMF) sgd_group_epoch_kernel<G, V, true><<<(unsigned)grid, 256, smem, h->stream>>>(gp);
     else sgd_group_epoch_kernel<G, V, false><<<(unsigned)grid, 256, smem, h->stream>>>(gp);

@@ -22,7 +22,7 @@
 #define LRK_GROUP_MAX_UNITS (1 << 27)
 
 struct GroupUnits {               // device unit table of a staged stream + host-side block ranges
-    int4* d_units = nullptr;      // {stream start, ratings, first user, users | shared << 16}
+    int4* d_units = nullptr;      // {stream start, ratings, first user, users | slices << 16 (0: the unit owns its users exclusively)}
     unsigned int* d_counter = nullptr;   // one work counter per item block (dynamic unit fetch)
     int64_t n_units = 0;
     uint32_t target = 0;
@@ -70,7 +70,7 @@ __global__ void group_unit_desc_kernel(const uint32_t* __restrict__ started, con
     const uint32_t st = started[v];
     if (st) {
         const uint32_t first = incl[v] - st;
-        for (uint32_t s = 0; s < st; ++s) { units[first + s].z = u; if (st > 1) atomicOr(&units[first + s].w, 1 << 16); }
+        for (uint32_t s = 0; s < st; ++s) { units[first + s].z = u; if (st > 1) atomicAdd(&units[first + s].w, (int)(st << 16)); }
         for (uint32_t s = 0; s < st; ++s) atomicAdd(&units[first + s].w, 1);
     } else {
         atomicAdd(&units[incl[v] - 1].w, 1);

@@ -335,3 +335,40 @@ def test_sgd_epochs_batches_the_iterations(O, capi):
         h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
         st = h.stage_stats()
     assert st["ratings"] == n and st["run_tile_ratings"] == 0
+
+
+@pytest.mark.parametrize("shape,k", [("tiny", 64), ("small", 128), ("ml-1m", 20)])
+def test_unit_ordered_stream_is_a_permutation_with_exclusive_units(O, capi, shape, k):
+    """staging_group.cuh: the unit-ordered stream holds every train entry exactly once; the units partition it; a unit's ratings
+    belong to its own users, users of units that store their rows (slices == 0) are disjoint, and inside a unit every item's
+    ratings are adjacent (one item-row read + one RED per (unit, item) pair)"""
+    from librec_b200 import synth
+    d = synth.make_ratings(shape, cache=False)
+    U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
+    with capi.Handle(capi.MODEL_PMF, k) as h:
+        h.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
+        su, si, sr, units = h.debug_stream(nnz)
+    assert units is not None and units.shape[0] > 0
+    rows = np.repeat(np.arange(U, dtype=np.int64), np.diff(d["rowptr"]))
+    want = np.sort(rows * I + d["col"])
+    got = su.astype(np.int64) * I + si
+    order = np.argsort(got, kind="stable")
+    assert np.array_equal(got[order], want)
+    ref_val = d["val"][np.argsort(rows * I + d["col"], kind="stable")].astype(np.float32)
+    assert np.array_equal(sr[order], ref_val)
+    start, count, first, w = units[:, 0].astype(np.int64) & 0xffffffff, units[:, 1], units[:, 2], units[:, 3]
+    nus, slices = w & 0xffff, w >> 16
+    assert count.sum() == nnz and np.array_equal(start, np.concatenate([[0], np.cumsum(count)[:-1]]))
+    assert nus.max() <= 16 and (nus[slices > 0] == 1).all()
+    owner = np.full(U, -1, np.int64)
+    for t in range(units.shape[0]):
+        a, b = start[t], start[t] + count[t]
+        uu, ii = su[a:b], si[a:b]
+        assert ((uu >= first[t]) & (uu < first[t] + nus[t])).all()
+        if count[t]:
+            change = np.flatnonzero(np.diff(ii) != 0)
+            heads = ii[np.concatenate([[0], change + 1])]
+            assert np.unique(heads).shape[0] == heads.shape[0], "an item's ratings are split inside a unit"
+        if slices[t] == 0:
+            assert (owner[first[t]:first[t] + nus[t]] == -1).all(), "two units store the same user's row"
+            owner[first[t]:first[t] + nus[t]] = t
