@@ -217,7 +217,7 @@ static int dsgd_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64
     if ((rc = lrk_dev_alloc(h, &h->d_si, (size_t)nnz))) return rc;
     if ((rc = lrk_dev_alloc(h, &h->d_sr, (size_t)nnz))) return rc;
     if ((rc = lrk_dev_alloc(h, &s->d_bounds, (size_t)world + 1))) return rc;
-    if ((rc = lrk_dev_alloc(h, &h->d_item_deg, (size_t)I))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->d_item_deg, (size_t)I + 4))) return rc;
     LRK_CUDA(h, cudaMemcpyAsync(h->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)U + 1), cudaMemcpyHostToDevice, st));
     if (nnz > 0) LRK_CUDA(h, cudaMemcpyAsync(h->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
     h->U = U; h->I = I; h->nnz = nnz;
@@ -359,7 +359,7 @@ static int dsgd_set_factors(lrk_handle_s* h, const double* P, const double* Q, c
     if ((rc = lrk_dev_alloc(h, &h->bu64, (size_t)U))) return rc;
     if ((rc = lrk_dev_alloc(h, &h->bi64, (size_t)I))) return rc;
     if ((rc = lrk_dev_alloc(h, &h->bu32, (size_t)U))) return rc;
-    if ((rc = lrk_dev_alloc(h, &h->bi32, (size_t)I))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bi32, (size_t)I + 4))) return rc;
     LRK_CUDA(h, cudaMemcpyAsync(h->P64, P, sizeof(double) * (size_t)U * k, cudaMemcpyHostToDevice, st));
     LRK_CUDA(h, cudaMemcpyAsync(h->Q64, Q, sizeof(double) * (size_t)I * k, cudaMemcpyHostToDevice, st));
     if (biased) {

@@ -125,7 +125,7 @@ struct DsgdFusedGroupParams {
 };
 
 template <int G, int V, bool BIASED>
-__global__ void __launch_bounds__(256, 3) dsgd_fused_group_epoch_kernel(DsgdFusedGroupParams fp) {
+__global__ void __launch_bounds__(256, 2) dsgd_fused_group_epoch_kernel(DsgdFusedGroupParams fp) {
     extern __shared__ float4 lrk_fused_group_smem4[];
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();

@@ -204,7 +204,7 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     if ((rc = lrk_dev_alloc(h, &h->bu64, (size_t)U))) return rc;
     if ((rc = lrk_dev_alloc(h, &h->bi64, (size_t)I))) return rc;
     if ((rc = lrk_dev_alloc(h, &h->bu32, (size_t)U))) return rc;
-    if ((rc = lrk_dev_alloc(h, &h->bi32, (size_t)I))) return rc;
+    if ((rc = lrk_dev_alloc(h, &h->bi32, (size_t)I + 4))) return rc;
     LRK_CUDA(h, cudaMemcpyAsync(h->P64, P, sizeof(double) * (size_t)U * k, cudaMemcpyHostToDevice, st));
     LRK_CUDA(h, cudaMemcpyAsync(h->Q64, Q, sizeof(double) * (size_t)I * k, cudaMemcpyHostToDevice, st));
     if (biased) {

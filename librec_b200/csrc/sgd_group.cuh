@@ -42,8 +42,14 @@ struct SgdGroupParams {
     float inflight_frac;                // resident workers / ratings of the launch: share of the stream one rating-time covers
 };
 
+#define LRK_GROUP_RING 8          // item rows a worker keeps in flight (cp.async ring in shared memory)
+#define LRK_GROUP_AHEAD 8         // entries of look-ahead: the row of entry s + 8 is requested while entry s is processed
+
+// per worker: LRK_GS user rows + LRK_GS user biases | ring of item rows | ring metadata (16 B chunk of item biases + 16 B chunk of degrees)
 template <int G, int V>
-__host__ __device__ constexpr int sgd_group_smem_floats_per_worker() { return LRK_GS * (4 * G * V) + LRK_GS; }
+__host__ __device__ constexpr int sgd_group_smem_floats_per_worker() {
+    return LRK_GS * (4 * G * V) + LRK_GS + LRK_GROUP_RING * (4 * G * V) + LRK_GROUP_RING * 8;
+}
 
 template <int G>
 __device__ __forceinline__ float group_sum_masked(unsigned mask, float v) {
@@ -51,15 +57,30 @@ __device__ __forceinline__ float group_sum_masked(unsigned mask, float v) {
     for (int m = G / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(mask, v, m);
     return v;
 }
+__device__ __forceinline__ void lrk_cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void lrk_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void lrk_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One worker = G lanes; the 32/G workers of a warp share its instruction stream.  The chunk loop is warp-uniform (16 / 32 ratings
-// per worker and iteration, everything that depends on a worker's own data predicated); taking the next unit is a divergent block of
+// One worker = G lanes; the 32/G workers of a warp share its instruction stream.  The chunk loop is warp-uniform (G ratings per
+// worker and iteration, everything that depends on a worker's own data predicated); taking the next unit is a divergent block of
 // its own, entered by a worker whenever ITS unit is used up, so workers never wait for each other's units.  A lane only ever touches
-// its own four columns of the unit's rows in shared memory and only sub-lane 0 touches the biases: no __syncwarp inside a unit.
+// its own four columns of the rows in shared memory and only sub-lane 0 touches the user biases: no __syncwarp inside a unit.
+//
+// Latency: a worker is a sequential chain (that is the point: Gauss-Seidel inside the unit), so the item rows must be there when
+// their pair starts.  The row (+ the 16 B chunks holding the item's bias and degree) of the pair that starts at entry s + 8 is
+// requested with cp.async.cg (L2 -> shared memory, no register staging, L1 bypassed: the rows are RED targets of other SMs) while
+// entry s is processed; one commit group per step, so `wait_group 7` at step s guarantees the row of entry s.  The next chunk's
+// triples are loaded one chunk ahead.
 template <int G, int V, bool BIASED>
 __device__ __forceinline__ void sgd_group_segment(const SgdGroupParams& p, float* smem_cta, double& loss_d) {
     constexpr int NWW = 32 / G;                    // workers per warp
     constexpr int LDS = 4 * G * V;                 // floats per row
+    constexpr int D = LRK_GROUP_AHEAD, R = LRK_GROUP_RING;
+    static_assert(G >= 8 && D <= G && D <= R, "look-ahead must fit the chunk and the ring");
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int sub = lane % G;
@@ -68,6 +89,8 @@ __device__ __forceinline__ void sgd_group_segment(const SgdGroupParams& p, float
     const int wk = (threadIdx.x >> 5) * NWW + grp;
     float* Ps = smem_cta + (size_t)wk * sgd_group_smem_floats_per_worker<G, V>();
     float* bus = Ps + LRK_GS * LDS;
+    float* Rq = bus + LRK_GS;                      // ring of item rows
+    float* Rm = Rq + R * LDS;                      // ring metadata: [slot][0..3] bias chunk, [slot][4..7] degree chunk
     const float lr = p.lr, reg_u = p.reg_u, reg_i = p.reg_i, reg_b = p.reg_b, mu = p.mu;
 
     bool alive = true, have = false;
@@ -75,21 +98,33 @@ __device__ __forceinline__ void sgd_group_segment(const SgdGroupParams& p, float
     int count = 0, first = 0, nus = 0, c = 0, slices = 1;
     bool shared = false;
     float curv = 1.f, bu0 = 0.f;
-    float4 p0[V], q[V], dq[V], qn[V];
-    int32_t cur = -1, qn_item = -1;               // item whose row is in q / prefetched in qn (block-local ids)
-    float bic = 0.f, dbi = 0.f, bin = 0.f;
+    float4 p0[V], q[V], dq[V];
+    int32_t cur = -1;                              // item whose row is in q (block-local id)
+    float bic = 0.f, dbi = 0.f, degc = 0.f;
     int pair_len = 0;
+    unsigned issued = 0, consumed = 0;             // pair heads requested / taken (ring slots are used in this order)
+    int32_t u_l = -1, i_l = -1, u_x = -1, i_x = -1;   // current / next chunk: entry `sub` of each
+    float r_l = 0.f, r_x = 0.f;
 #pragma unroll
-    for (int v = 0; v < V; ++v) { p0[v] = make_float4(0.f, 0.f, 0.f, 0.f); q[v] = p0[v]; dq[v] = p0[v]; qn[v] = p0[v]; }
+    for (int v = 0; v < V; ++v) { p0[v] = make_float4(0.f, 0.f, 0.f, 0.f); q[v] = p0[v]; dq[v] = p0[v]; }
 
+    // request the item row (and bias / degree chunks) of a pair head into the next ring slot
+    auto request = [&](int32_t item) {
+        const unsigned slot = issued % R;
+#pragma unroll
+        for (int v = 0; v < V; ++v) lrk_cp_async16(Rq + slot * LDS + (v * G + sub) * 4, p.Q + (int64_t)item * p.ld + (v * G + sub) * 4);
+        if (BIASED && sub == 0) lrk_cp_async16(Rm + slot * 8, (const void*)((uintptr_t)(p.bi + item) & ~(uintptr_t)15));
+        if (sub == 0 && p.item_deg) lrk_cp_async16(Rm + slot * 8 + 4, (const void*)((uintptr_t)(p.item_deg + item) & ~(uintptr_t)15));
+        ++issued;
+    };
     // the change of the current item row -> global memory, scaled for the ratings of that item other workers have in flight:
-    // while this worker held the row for pair_len (+1 of prefetch) ratings, the others applied about deg_i * (W / n) * (pair_len + 1)
+    // while this worker held the row for pair_len ratings (+ the look-ahead), the others applied about deg_i * (W / n) * that many
     auto flush = [&]() {
         if (cur >= 0) {
             float damp = 1.f;
             if (p.item_deg) {
-                const float others = fmaxf((float)__ldg(p.item_deg + cur) - (float)pair_len, 0.f);
-                const float x = lr * curv * others * p.inflight_frac * (float)(pair_len + 1);
+                const float others = fmaxf(degc - (float)pair_len, 0.f);
+                const float x = lr * curv * others * p.inflight_frac * (float)(pair_len + D);
                 if (x > 1e-3f) damp = (1.f - __expf(-x)) / x;
             }
 #pragma unroll
@@ -122,6 +157,13 @@ __device__ __forceinline__ void sgd_group_segment(const SgdGroupParams& p, float
             bus[0] = bu0;
         }
     };
+    auto load_chunk = [&](int at, int32_t& u, int32_t& i, float& r) {
+        u = -1; i = -1; r = 0.f;
+        if (at + sub < count) {
+            const int64_t e = start + at + sub;
+            u = __ldcs(p.su + e) - first; i = __ldcs(p.si + e); r = __ldcs(p.sr + e);
+        }
+    };
 
     for (;;) {
         if (alive && (!have || c >= count)) {
@@ -143,48 +185,57 @@ __device__ __forceinline__ void sgd_group_segment(const SgdGroupParams& p, float
             int unit = -1;
             if (sub == 0) unit = (int)atomicAdd(p.counter, 1u);
             unit = __shfl_sync(wmask, unit, grp * G);
-            if (unit >= p.n_units) alive = false;
+            if (unit >= p.n_units) { alive = false; u_l = -1; u_x = -1; i_l = -1; i_x = -1; count = 0; }
             else {
                 const int4 d = __ldg(p.units + unit);
                 start = (int64_t)(uint32_t)d.x; count = d.y; first = d.z; nus = d.w & 0xffff; shared = (d.w >> 16) != 0;
                 slices = shared ? (d.w >> 16) : 1;
-                c = 0; have = true; cur = -1; qn_item = -1; pair_len = 0;
+                c = 0; have = true; cur = -1; pair_len = 0;
+                load_chunk(0, u_l, i_l, r_l);
+                load_chunk(G, u_x, i_x, r_x);
+                // the unit's user rows -> shared memory, four rows in flight at a time
                 float pn2 = 0.f;
-                for (int j = 0; j < nus; ++j) {
+                for (int j0 = 0; j0 < nus; j0 += 4) {
+                    float4 x[4][V];
 #pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const float4 x = ldcg4(p.P + (int64_t)(first + j) * p.ld + (v * G + sub) * 4);
-                        *reinterpret_cast<float4*>(Ps + j * LDS + (v * G + sub) * 4) = x;
-                        pn2 += dot4(x, x);
-                        if (j == 0) p0[v] = x;
-                    }
-                    if (BIASED && sub == 0) bus[j] = __ldcg(p.bu + first + j);
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                        for (int v = 0; v < V; ++v)
+                            x[jj][v] = j0 + jj < nus ? ldcg4(p.P + (int64_t)(first + j0 + jj) * p.ld + (v * G + sub) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (j0 + jj < nus) {
+#pragma unroll
+                            for (int v = 0; v < V; ++v) {
+                                *reinterpret_cast<float4*>(Ps + (j0 + jj) * LDS + (v * G + sub) * 4) = x[jj][v];
+                                pn2 += dot4(x[jj][v], x[jj][v]);
+                                if (j0 + jj == 0) p0[v] = x[jj][v];
+                            }
+                        }
                 }
+                if (BIASED && sub == 0) for (int j = 0; j < nus; ++j) bus[j] = __ldcg(p.bu + first + j);
                 pn2 = group_sum_masked<G>(wmask, pn2);
                 curv = fmaxf(1.f, nus > 0 ? pn2 / (float)nus : 0.f);     // curvature of the item-side step: mean |p_u|^2 of the rows held
                 bu0 = (BIASED && sub == 0 && nus > 0) ? bus[0] : 0.f;
+                // prologue of the look-ahead: the pair heads among the first D entries (one commit group per entry, like a step)
+                int32_t prev = -1;
+#pragma unroll
+                for (int t = 0; t < D; ++t) {
+                    const int32_t it = __shfl_sync(wmask, i_l, grp * G + t);
+                    if (it >= 0 && it != prev) request(it);
+                    lrk_cp_async_commit();
+                    prev = it;
+                }
             }
         }
         if (!__any_sync(FULL, alive)) break;
         const bool on = alive && have;
 
-        // ---- one chunk: lane `sub` loads entry c + sub of its worker's unit, then G steps of one rating per worker
-        int32_t u_l = -1, i_l = -1;
-        float r_l = 0.f;
-        if (on && c + sub < count) {
-            const int64_t e = start + c + sub;
-            u_l = __ldcs(p.su + e) - first; i_l = __ldcs(p.si + e); r_l = __ldcs(p.sr + e);
-        }
+        // ---- one chunk: G steps of one rating per worker; entry s + D (this chunk or the next) is looked ahead at step s
+        float loss_f = 0.f;
         int32_t un = __shfl_sync(FULL, u_l, 0, G), in_ = __shfl_sync(FULL, i_l, 0, G);
         float rn = __shfl_sync(FULL, r_l, 0, G);
-        // first entry of the chunk: its item row unless it continues the current pair
-        if (un >= 0 && in_ != cur) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) qn[v] = ldcg4(p.Q + (int64_t)in_ * p.ld + (v * G + sub) * 4);
-            if (BIASED && sub == 0) bin = __ldcg(p.bi + in_);
-            qn_item = in_;
-        }
-        float loss_f = 0.f;
+        int32_t la_prev = __shfl_sync(FULL, i_l, D - 1, G);          // item of entry D - 1 (the last one already looked at)
 #pragma unroll
         for (int s = 0; s < G; ++s) {
             const int32_t uc = un, ic = in_;
@@ -192,20 +243,28 @@ __device__ __forceinline__ void sgd_group_segment(const SgdGroupParams& p, float
             if (s + 1 < G) {
                 un = __shfl_sync(FULL, u_l, s + 1, G); in_ = __shfl_sync(FULL, i_l, s + 1, G); rn = __shfl_sync(FULL, r_l, s + 1, G);
             }
+            // look-ahead: entry s + D
+            const int32_t la = (s + D < G) ? __shfl_sync(FULL, i_l, s + D, G) : __shfl_sync(FULL, i_x, s + D - G, G);
+            lrk_cp_async_wait<D - 1>();
             const bool act = uc >= 0;
-            if (act && ic != cur) {          // new pair: flush the old one, take the prefetched row
+            if (act && ic != cur) {          // new pair: flush the old one, take the row from the ring
                 flush();
+                const unsigned slot = consumed % R;
 #pragma unroll
-                for (int v = 0; v < V; ++v) { q[v] = qn[v]; dq[v] = make_float4(0.f, 0.f, 0.f, 0.f); }
-                bic = bin; dbi = 0.f; cur = ic; qn_item = -1;
+                for (int v = 0; v < V; ++v) {
+                    q[v] = *reinterpret_cast<const float4*>(Rq + slot * LDS + (v * G + sub) * 4);
+                    dq[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                // sub-lane 0 requested the two metadata chunks, so it is the lane that may read them
+                if (BIASED && sub == 0) bic = Rm[slot * 8 + (int)(((uintptr_t)(p.bi + ic) & 15) >> 2)];
+                degc = (p.item_deg && sub == 0) ? (float)reinterpret_cast<const uint32_t*>(Rm)[slot * 8 + 4 + (int)(((uintptr_t)(p.item_deg + ic) & 15) >> 2)] : 0.f;
+                degc = __shfl_sync(wmask, degc, grp * G);
+                dbi = 0.f; cur = ic;
+                ++consumed;
             }
-            // prefetch the next pair's item row while this rating is processed
-            if (s + 1 < G && un >= 0 && in_ != ic) {
-#pragma unroll
-                for (int v = 0; v < V; ++v) qn[v] = ldcg4(p.Q + (int64_t)in_ * p.ld + (v * G + sub) * 4);
-                if (BIASED && sub == 0) bin = __ldcg(p.bi + in_);
-                qn_item = in_;
-            }
+            if (on && la >= 0 && la != la_prev) request(la);
+            lrk_cp_async_commit();
+            la_prev = la;
             float4 pc[V];
             float part = 0.f, buc = 0.f;
             const int urow = act ? uc : 0;
@@ -247,12 +306,15 @@ __device__ __forceinline__ void sgd_group_segment(const SgdGroupParams& p, float
         }
         loss_d += (double)loss_f;
         c += G;
+        u_l = u_x; i_l = i_x; r_l = r_x;
+        if (on) load_chunk(c + G, u_x, i_x, r_x);
         if (on && shared && c < count) merge_shared_row(G);
     }
+    lrk_cp_async_wait<0>();
 }
 
 template <int G, int V, bool BIASED>
-__global__ void __launch_bounds__(256, 3) sgd_group_epoch_kernel(SgdGroupParams p) {
+__global__ void __launch_bounds__(256, 2) sgd_group_epoch_kernel(SgdGroupParams p) {
     extern __shared__ float4 lrk_group_smem4[];
     double loss_d = 0.0;
     sgd_group_segment<G, V, BIASED>(p, reinterpret_cast<float*>(lrk_group_smem4), loss_d);
