@@ -1,4 +1,5 @@
-// BiasedMF / PMF epoch over a unit-ordered stream (staging_group.cuh) -- the default fast kernel of the rating models.
+// BiasedMF / PMF epoch over a unit-ordered stream (staging_group.cuh) -- the order-faithful fast kernel of the rating models
+// (LRK_SGD_GROUP=1; the default is the item-run-tile kernel of sgd.cuh, see the measurement at lrk_use_group_kernel).
 //
 // Reference loop restated per rating (core/src/main/java/net/librec/): recommender/cf/rating/BiasedMFRecommender.java:72-98,
 // recommender/cf/rating/PMFSimilarityRecommender.java:64-82.  The reference walks users in CSR order, items ascending, one rating
@@ -339,18 +340,16 @@ static int sgd_group_resident_workers_gv(lrk_handle_s* h, int* ctas_out) {
     return per_sm * h->sm_count * 8 * (32 / G);
 }
 static bool sgd_group_layout_supported(const lrk_handle_s* h) { return h->V == 1 && (h->G == 8 || h->G == 16 || h->G == 32); }
-// LRK_SGD_GROUP=0 keeps the item-run-tile stream kernel of sgd.cuh (A/B probe)
+// Selected with LRK_SGD_GROUP=1 (read at every lrk_set_train_csr).  r02 measurement on one B200 (ML-20M shape, BiasedMF k=64): this
+// kernel is bit-for-bit the closer one to the reference (held-out RMSE within 1.3e-5 of the sequential oracle, first-epoch loss of
+// config C4 92.9 M vs the oracle's 94.6 M against 134 M for the item-run-tile kernel), but it is INSTRUCTION bound, not L2 bound:
+// 140 warp-instructions per rating (ncu, profiles/r02_group_kernel_ncu_summary.md) against 53 for the item-run-tile kernel -- the
+// sequential chain needs per-rating control flow (pair heads, look-ahead, ring slots) and the two workers of a warp diverge on it --
+// 4.0-4.8 ms per epoch against 1.5 ms.  So the item-run-tile kernel stays the default and this one is the order-faithful option.
 static bool lrk_use_group_kernel(const lrk_handle_s* h) {
-    static const char* env = getenv("LRK_SGD_GROUP");
-    if (env && atoi(env) == 0) return false;
+    const char* env = getenv("LRK_SGD_GROUP");
+    if (!env || atoi(env) == 0) return false;
     return lrk_is_rating_model(h) && h->cfg.update_mode == LRK_UPDATE_ATOMIC && sgd_group_layout_supported(h);
-}
-static int sgd_group_resident_workers(lrk_handle_s* h, int* ctas_out) {
-    switch (h->G) {
-        case 8: return sgd_group_resident_workers_gv<8, 1>(h, ctas_out);
-        case 16: return sgd_group_resident_workers_gv<16, 1>(h, ctas_out);
-        default: return sgd_group_resident_workers_gv<32, 1>(h, ctas_out);
-    }
 }
 
 template <int G, int V>

@@ -32,3 +32,13 @@ def test_bpr_c1_auc_and_precision_match_the_oracle_bpr(capi, O, c1):
     r = parity_scale.bpr_parity(capi, O, c1["train"], c1["test"], k=10, lr=0.01, reg=0.01, epochs=50)
     print("BPR C1 parity:", r)
     assert r["ok"], r
+
+
+@pytest.mark.timeout(600)
+def test_c2_group_kernel_heldout_rmse_matches_the_sequential_oracle(capi, O, monkeypatch):
+    """the order-faithful user-group kernel (LRK_SGD_GROUP=1) on the same case"""
+    monkeypatch.setenv("LRK_SGD_GROUP", "1")
+    r = parity_scale.rating_parity(capi, O, "c2", epochs=10)
+    print("C2 parity (group kernel):", r)
+    assert r["rollbacks"] == 0
+    assert abs(r["d_rmse"]) <= 1e-3 and abs(r["d_mae"]) <= 1e-3, r

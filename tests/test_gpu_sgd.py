@@ -338,7 +338,12 @@ def test_sgd_epochs_batches_the_iterations(O, capi):
 
 
 @pytest.mark.parametrize("shape,k", [("tiny", 64), ("small", 128), ("ml-1m", 20)])
-def test_unit_ordered_stream_is_a_permutation_with_exclusive_units(O, capi, shape, k):
+def test_unit_ordered_stream_is_a_permutation_with_exclusive_units(O, capi, shape, k, monkeypatch):
+    monkeypatch.setenv("LRK_SGD_GROUP", "1")
+    _unit_stream_checks(O, capi, shape, k)
+
+
+def _unit_stream_checks(O, capi, shape, k):
     """staging_group.cuh: the unit-ordered stream holds every train entry exactly once; the units partition it; a unit's ratings
     belong to its own users, users of units that store their rows (slices == 0) are disjoint, and inside a unit every item's
     ratings are adjacent (one item-row read + one RED per (unit, item) pair)"""
@@ -372,3 +377,51 @@ def test_unit_ordered_stream_is_a_permutation_with_exclusive_units(O, capi, shap
         if slices[t] == 0:
             assert (owner[first[t]:first[t] + nus[t]] == -1).all(), "two units store the same user's row"
             owner[first[t]:first[t] + nus[t]] = t
+
+
+@pytest.mark.parametrize("model_name,k", [("biasedmf", 64), ("pmf", 128), ("biasedmf", 20)])
+def test_group_kernel_conflict_free_epoch_matches_oracle(O, capi, model_name, k, monkeypatch):
+    """LRK_SGD_GROUP=1 (sgd_group.cuh): with every user and item rated once nothing is concurrent -- one epoch of the user-group
+    kernel equals the oracle's epoch up to fp32 rounding"""
+    monkeypatch.setenv("LRK_SGD_GROUP", "1")
+    n, I = 3000, 4000
+    tr = _conflict_free(O, n, I, 3)
+    rng = np.random.default_rng(1)
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    P, Q = f32(rng.normal(0, 0.1, (n, k))), f32(rng.normal(0, 0.1, (I, k)))
+    biased = model_name == "biasedmf"
+    bu = f32(rng.normal(0, 0.1, n)) if biased else None
+    bi = f32(rng.normal(0, 0.1, I)) if biased else None
+    with capi.Handle(capi.MODEL_BIASEDMF if biased else capi.MODEL_PMF, k) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        assert h.debug_stream(tr.nnz)[3] is not None          # the unit-ordered stream is in use
+        h.set_factors(P, Q, bu, bi, 3.0)
+        loss = h.sgd_epoch(0.01, 0.02, 0.03, 0.04)
+        gP, gQ, gbu, gbi = h.get_factors()
+    oP, oQ = P.copy(), Q.copy()
+    if biased:
+        obu, obi = bu.copy(), bi.copy()
+        oloss = O.lib().lro_biasedmf_epoch(tr.U, tr.rowptr, tr.col, tr.val, k, oP, oQ, obu, obi, 3.0, 0.01, 0.02, 0.03, 0.04, None, None)
+        assert np.allclose(gbu, obu, rtol=0, atol=2e-6) and np.allclose(gbi, obi, rtol=0, atol=2e-6)
+    else:
+        oloss = O.lib().lro_pmf_epoch(tr.U, tr.rowptr, tr.col, tr.val, k, oP, oQ, 0.01, 0.02, 0.03, None, None)
+    assert np.allclose(gP, oP, rtol=0, atol=2e-6) and np.allclose(gQ, oQ, rtol=0, atol=2e-6)
+    assert abs(loss - oloss) <= 2e-5 * abs(oloss)
+
+
+def test_group_kernel_c1_biasedmf_rmse_mae_within_1e3(O, capi, c1, monkeypatch):
+    """LRK_SGD_GROUP=1 on config C1 (k=20 -> the 8-lane layout): RMSE / MAE within 1e-3 of the oracle"""
+    monkeypatch.setenv("LRK_SGD_GROUP", "1")
+    tr, te, pins = c1["train"], c1["test"], c1["pins"]
+    O.lib().lro_rng_set_state(*c1["rng_state"])
+    P, Q, bu, bi = O.mf_setup(tr.U, tr.I, 20, True)
+    mu = pins["global_mean"]
+    with capi.Handle(capi.MODEL_BIASEDMF, 20) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        assert h.debug_stream(tr.nnz)[3] is not None
+        h.set_factors(P, Q, bu, bi, mu)
+        for it in range(100):
+            h.sgd_epoch(0.002, 0.01, 0.01, 0.01, it + 1)
+        rmse, mae = h.eval_rating(te.U, te.rowptr, te.col, te.val, 1.0, 5.0)
+    print("group kernel C1: rmse %.6f (oracle %.6f) mae %.6f (oracle %.6f)" % (rmse, pins["biasedmf"]["rmse"], mae, pins["biasedmf"]["mae"]))
+    assert abs(rmse - pins["biasedmf"]["rmse"]) < 1e-3 and abs(mae - pins["biasedmf"]["mae"]) < 1e-3
