@@ -352,6 +352,14 @@ static bool lrk_use_group_kernel(const lrk_handle_s* h) {
     return lrk_is_rating_model(h) && h->cfg.update_mode == LRK_UPDATE_ATOMIC && sgd_group_layout_supported(h);
 }
 
+static int sgd_group_resident_workers(lrk_handle_s* h, int* ctas_out) {
+    switch (h->G) {
+        case 8: return sgd_group_resident_workers_gv<8, 1>(h, ctas_out);
+        case 16: return sgd_group_resident_workers_gv<16, 1>(h, ctas_out);
+        default: return sgd_group_resident_workers_gv<32, 1>(h, ctas_out);
+    }
+}
+
 template <int G, int V>
 static int sgd_group_launch_gv(lrk_handle_s* h, SgdGroupParams& gp, int64_t n_ratings, int conc_div) {
     int ctas = 0;

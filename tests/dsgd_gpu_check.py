@@ -2,9 +2,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dsgd_gpu_check.py
 (1) conflict-free matrix: one DSGD epoch == the oracle's epoch up to fp32 rounding;
 (2) config C1 (seeded ml-100k split, biasedmf-test.properties): RMSE / MAE within 1e-3 of the oracle;
-(3) BPR with stratified sampling: it must learn a ranking (Precision@10 on the binarised C1 split well
-    above chance and at least 60 % of the single-GPU BPR of the same library).  Stratified BPR only ever compares
-    items of the same block, so it is NOT on a par with the reference's sampling (r01, 2 ranks: 0.225 vs 0.325).
+(3) BPR across ranks (every rank keeps the full item matrix and samples like the reference over the whole catalogue; the change
+    of the item matrix is all-reduced 8 times per epoch, csrc/dsgd.cuh dsgd_bpr_epoch): Precision@10 on the binarised C1 split at
+    least 90 % of the single-GPU BPR of the same library (r01's stratified sampler reached 0.225 / 0.142 on 2 / 8 ranks vs 0.325).
+(4) an invalid CSR shard on one rank fails on every rank; (5) BPR on a catalogue as small as the world size does not hang.
 Prints "DSGD-CHECK OK" on rank 0.  `--fused` runs the same checks through the experimental fused epoch kernel.
 """
 import json
@@ -65,7 +66,7 @@ def main():
             sP, sQ, _, _ = h1.get_factors()
         prec_dsgd, prec_one = precision_at_10(gP, gQ), precision_at_10(sP, sQ)
         print("BPR DSGD world=%d: P@10 %.4f (one GPU %.4f)  loss_30 %.1f (one GPU %.1f)" % (world, prec_dsgd, prec_one, bl[-1], l1[-1]))
-    ok3 = rank != 0 or (prec_dsgd > 0.1 and prec_dsgd >= 0.6 * prec_one)
+    ok3 = rank != 0 or (prec_dsgd > 0.1 and prec_dsgd >= 0.9 * prec_one)
     ok2 = ok2 and ok3
     # (4) ADVICE r01: an invalid CSR on ONE rank must fail on EVERY rank with LRK_ERR_INVALID (no rank left waiting in NCCL)
     sh = dsgd_checks.shard_rows(tr.U, world)
