@@ -86,6 +86,15 @@ LRK_API int32_t lrk_device_count(void);
 /* replaces: the no-arg constructor + setup() allocation of DenseMatrix factors
  * (recommender/MatrixFactorizationRecommender.java:67-94). */
 LRK_API int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out);
+/* replaces the same constructor for rec.cuda.devices=d0,d1,... (1 to 8 devices of one box): ONE handle, driven from the one thread
+ * job/RecommenderJob.java:121-143 runs, that trains on all listed GPUs.  It takes and returns the FULL matrices exactly like a
+ * single-device handle; inside, users are cut into contiguous blocks, one per device, each device runs a DSGD rank on its own host
+ * thread (NCCL communicator created inside this process; item blocks rotate over NVLink), and lrk_topn shards the queried users over
+ * the devices with the full item matrix on each (no collective).  cfg->device is ignored.  Supported on a multi handle:
+ * lrk_set_train_csr, lrk_set_factors, lrk_sgd_epoch(s), lrk_get_factors, lrk_topn, lrk_topn_stats, lrk_stage_stats, lrk_last_epoch_ms,
+ * lrk_sgd_safeguard_state, lrk_launch_count, lrk_synchronize, lrk_probe_l2, lrk_last_error, lrk_destroy; the remaining entry points
+ * return LRK_ERR_INVALID (gather the factors with lrk_get_factors and use a single-device handle for them). */
+LRK_API int lrk_create_multi(const lrk_config_t* cfg, const int32_t* devices, int32_t n_devices, lrk_handle_t* out);
 LRK_API int lrk_destroy(lrk_handle_t h);
 /* h may be NULL: returns the last error of the calling thread for calls that had no handle */
 LRK_API const char* lrk_last_error(lrk_handle_t h);

@@ -35,6 +35,19 @@ jlong LRK_JNI(create)(JNIEnv* env, jclass c, jint device, jint model, jint numFa
     cfg.seed = (uint64_t)seed; cfg.topn_path = topnPath;
     return lrk_create(&cfg, &h) == LRK_OK ? (jlong)(intptr_t)h : 0;     /* 0: lastError(0) has the text */
 }
+jlong LRK_JNI(createMulti)(JNIEnv* env, jclass c, jintArray devices, jint model, jint numFactors, jint updateMode, jlong seed, jint topnPath) {
+    lrk_config_t cfg;
+    lrk_handle_t h = NULL;
+    int32_t* d = (int32_t*)PIN(devices);
+    const jsize n = (*env)->GetArrayLength(env, devices);
+    int rc;
+    (void)c;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.model = model; cfg.num_factors = numFactors; cfg.update_mode = updateMode; cfg.seed = (uint64_t)seed; cfg.topn_path = topnPath;
+    rc = lrk_create_multi(&cfg, d, (int32_t)n, &h);
+    UNPIN(devices, d, JNI_ABORT);
+    return rc == LRK_OK ? (jlong)(intptr_t)h : 0;
+}
 jint LRK_JNI(destroy)(JNIEnv* env, jclass c, jlong h) { (void)env; (void)c; return lrk_destroy(H(h)); }
 jstring LRK_JNI(lastError)(JNIEnv* env, jclass c, jlong h) { (void)c; return (*env)->NewStringUTF(env, lrk_last_error(H(h))); }
 jint LRK_JNI(setStream)(JNIEnv* env, jclass c, jlong h, jlong cudaStream) { (void)env; (void)c; return lrk_set_stream(H(h), (void*)(intptr_t)cudaStream); }

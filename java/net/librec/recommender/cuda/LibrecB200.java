@@ -17,6 +17,7 @@ final class LibrecB200 {
     static native int abiVersion();
     static native int deviceCount();
     static native long create(int device, int model, int numFactors, int updateMode, long seed, int topnPath);   // 0 on failure
+    static native long createMulti(int[] devices, int model, int numFactors, int updateMode, long seed, int topnPath);   // rec.cuda.devices
     static native int destroy(long h);
     static native String lastError(long h);
     static native int setStream(long h, long cudaStream);

@@ -31,6 +31,13 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
         int device = conf.getInt("rec.cuda.device", 0);
         int mode = "reference".equals(conf.get("rec.cuda.order", "shuffled"))
                 ? LibrecB200.UPDATE_REFERENCE_ORDER : LibrecB200.UPDATE_ATOMIC;
+        String devs = conf.get("rec.cuda.devices");                    // e.g. 0,1,2,3,4,5,6,7: one handle, all listed GPUs of the box
+        if (devs != null && !devs.trim().isEmpty()) {
+            String[] parts = devs.trim().split("\\s*,\\s*");
+            int[] ids = new int[parts.length];
+            for (int d = 0; d < parts.length; d++) ids[d] = Integer.parseInt(parts[d]);
+            handle = LibrecB200.createMulti(ids, model(), numFactors, mode, conf.getLong("rec.cuda.seed", 1L), 0);
+        } else
         handle = LibrecB200.create(device, model(), numFactors, mode, conf.getLong("rec.cuda.seed", 1L), 0);
         if (handle == 0) throw new LibrecException(LibrecB200.lastError(0));
         // flatten SequentialAccessSparseMatrix (per-row int[]/double[]) into rowptr/col/val once

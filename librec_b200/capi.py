@@ -39,6 +39,7 @@ SIGNATURES = {
     "lrk_abi_version": (C.c_int32, []),
     "lrk_device_count": (C.c_int32, []),
     "lrk_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "lrk_create_multi": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
     "lrk_destroy": (C.c_int, [C.c_void_p]),
     "lrk_last_error": (C.c_char_p, [C.c_void_p]),
     "lrk_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -108,12 +109,17 @@ def _check(rc, h=None):
 class Handle:
     """one native handle == one recommender instance (not thread-safe)"""
 
-    def __init__(self, model, num_factors, device=0, update_mode=UPDATE_ATOMIC, seed=1, topn_path=0):
+    def __init__(self, model, num_factors, device=0, update_mode=UPDATE_ATOMIC, seed=1, topn_path=0, devices=None):
+        """devices=[d0, d1, ...]: a single-process multi-GPU handle (lrk_create_multi, rec.cuda.devices in the Java shim)"""
         L = load()
         cfg = Config(device=device, model=model, num_factors=num_factors, update_mode=update_mode,
                      seed=seed, topn_path=topn_path)
         h = C.c_void_p()
-        _check(L.lrk_create(C.byref(cfg), C.byref(h)))
+        if devices is not None:
+            dv = np.ascontiguousarray(devices, np.int32)
+            _check(L.lrk_create_multi(C.byref(cfg), _ptr(dv), dv.shape[0], C.byref(h)))
+        else:
+            _check(L.lrk_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self.k = num_factors
         self.model = model

@@ -504,7 +504,7 @@ static int dsgd_fused_epoch(lrk_handle_s* h, DsgdState* s, float lr, float reg_u
     DsgdFused* f = &s->fused;
     if (f->enabled < 0) { const char* e = getenv("LRK_DSGD_FUSED"); f->enabled = e && atoi(e) ? 1 : 0; }
     const int world = h->world;
-    if (!f->enabled || world < 2 || world > LRK_FUSED_MAX_WORLD || h->cfg.model == LRK_MODEL_BPR ||
+    if (!f->enabled || h->same_process || world < 2 || world > LRK_FUSED_MAX_WORLD || h->cfg.model == LRK_MODEL_BPR ||
         h->cfg.update_mode != LRK_UPDATE_ATOMIC || h->V != 1 || (h->G < 16 && !h->group))
         return LRK_OK;
     int coop = 0;

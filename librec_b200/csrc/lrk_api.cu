@@ -11,11 +11,21 @@
 #include "topn_tc.cuh"
 #include "dsgd.cuh"
 #include "l2_probe.cuh"
+#include "multi.cuh"
 
 #include <cmath>
 #include <new>
 
 thread_local std::string g_lrk_tls_error;
+
+static int multi_destroy(lrk_handle_s* h);
+static int multi_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val);
+static int multi_set_factors(lrk_handle_s* h, const double* P, const double* Q, const double* bu, const double* bi, double mu);
+static int multi_get_factors(lrk_handle_s* h, double* P, double* Q, double* bu, double* bi);
+static int multi_sgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, double* loss_out);
+static int multi_topn(lrk_handle_s* h, const int32_t* users, int32_t nq, int32_t topn, int32_t exclude_train, int32_t* out_items,
+                      double* out_scores, int32_t* out_counts);
+#define LRK_NOT_MULTI(h, what) LRK_REQUIRE(h, !(h)->multi, what " is not available on a multi-device handle: call lrk_get_factors and use a single-device handle")
 
 extern "C" {
 
@@ -93,6 +103,7 @@ int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out) {
 
 int lrk_destroy(lrk_handle_t h) {
     if (!h) return LRK_OK;
+    if (h->multi) return multi_destroy(h);
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     group_units_release((GroupUnits*)h->group);
@@ -119,12 +130,14 @@ int lrk_destroy(lrk_handle_t h) {
 
 int lrk_set_stream(lrk_handle_t h, void* cuda_stream) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_NOT_MULTI(h, "lrk_set_stream");
     LRK_CUDA(h, cudaStreamSynchronize(h->stream));
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
     return LRK_OK;
 }
 int lrk_synchronize(lrk_handle_t h) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    if (h->multi) { for (lrk_handle_s* c : ((MultiState*)h->multi)->child) { const int rc = lrk_synchronize(c); if (rc) return rc; } return LRK_OK; }
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     LRK_CUDA(h, cudaStreamSynchronize(h->stream));
     return LRK_OK;
@@ -133,7 +146,8 @@ int lrk_synchronize(lrk_handle_t h) {
 // -------------------------------------------------------------------------------------------
 int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
-    LRK_REQUIRE(h, U > 0 && I > 0 && rowptr && (col || rowptr[U] == 0) && (val || rowptr[U] == 0), "bad CSR arguments");
+    LRK_REQUIRE(h, U > 0 && I > 0 && rowptr && (col || rowptr[U] == 0) && (val || rowptr[U] == 0 || h->score_only), "bad CSR arguments");
+    if (h->multi) return multi_set_train_csr(h, U, I, rowptr, col, val);
     LRK_REQUIRE(h, !h->has_factors || (h->U == U && h->I == I), "CSR shape differs from the factors already set");
     const int64_t nnz = rowptr[U];
     LRK_REQUIRE(h, nnz >= 0 && nnz < (int64_t)0xffffffffLL, "nnz out of range");
@@ -144,12 +158,20 @@ int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowpt
     int rc;
     if ((rc = lrk_dev_alloc(h, &h->d_rowptr, (size_t)U + 1))) return rc;
     if ((rc = lrk_dev_alloc(h, &h->d_col, (size_t)nnz))) return rc;
-    if ((rc = lrk_dev_alloc(h, &h->d_su, (size_t)nnz))) return rc;
-    if ((rc = lrk_dev_alloc(h, &h->d_si, (size_t)nnz))) return rc;
-    if ((rc = lrk_dev_alloc(h, &h->d_sr, (size_t)nnz))) return rc;
+    if (!h->score_only) {
+        if ((rc = lrk_dev_alloc(h, &h->d_su, (size_t)nnz))) return rc;
+        if ((rc = lrk_dev_alloc(h, &h->d_si, (size_t)nnz))) return rc;
+        if ((rc = lrk_dev_alloc(h, &h->d_sr, (size_t)nnz))) return rc;
+    }
     LRK_CUDA(h, cudaMemcpyAsync(h->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)U + 1), cudaMemcpyHostToDevice, st));
     LRK_CUDA(h, cudaMemcpyAsync(h->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
     h->U = U; h->I = I; h->nnz = nnz;
+    if (h->score_only) {            // top-N mask only (scoring child of a multi handle; its DSGD sibling validated the shard)
+        LRK_CUDA(h, cudaStreamSynchronize(st));
+        h->has_train = true;
+        topn_tc_invalidate(h);
+        return LRK_OK;
+    }
     // BiasedMF / PMF in the default (atomic) mode train with the user-group kernel over a unit-ordered stream (sgd_group.cuh);
     // Hogwild mode, the reference-order mode, BPR / RankSGD and layouts outside 32 < ld <= 128 keep the shuffled stream of sgd.cuh
     group_units_release((GroupUnits*)h->group);
@@ -187,6 +209,7 @@ int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowpt
 
 int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const double* bu, const double* bi, double mu) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    if (h->multi) return multi_set_factors(h, P, Q, bu, bi, mu);
     LRK_REQUIRE(h, h->has_train, "call lrk_set_train_csr first (it fixes numUsers / numItems)");
     LRK_REQUIRE(h, P && Q, "P and Q are required");
     const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
@@ -246,6 +269,7 @@ static int refresh_masters(lrk_handle_s* h) {
 
 int lrk_get_factors(lrk_handle_t h, double* P, double* Q, double* bu, double* bi) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    if (h->multi) return multi_get_factors(h, P, Q, bu, bi);
     LRK_REQUIRE(h, h->has_factors, "no factors set");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->world > 1) return dsgd_get_factors(h, P, Q, bu, bi);
@@ -283,6 +307,7 @@ static void fill_sgd_params(const lrk_handle_s* h, SgdParams& sp, float lr, floa
 
 int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, double* loss_out) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    if (h->multi) return multi_sgd_epoch(h, lr, reg_u, reg_i, reg_b, epoch_idx, loss_out);
     LRK_REQUIRE(h, h->has_train && h->has_factors, "set the train CSR and the factors before training");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->world > 1) return dsgd_epoch(h, lr, reg_u, reg_i, reg_b, epoch_idx, loss_out);
@@ -394,6 +419,17 @@ int lrk_sgd_epochs(lrk_handle_t h, int32_t n_epochs, float lr, float decay, floa
 
 int lrk_stage_stats(lrk_handle_t h, int64_t out[4]) {
     LRK_REQUIRE(h, h != nullptr && out != nullptr, "NULL argument");
+    if (h->multi) {
+        int64_t acc[4] = {0, 0, 0, 0};
+        for (lrk_handle_s* c : ((MultiState*)h->multi)->child) {
+            int64_t v[4];
+            const int rc = lrk_stage_stats(c, v);
+            if (rc) { h->err = c->err; return rc; }
+            acc[0] += v[0]; acc[1] += v[1]; acc[2] = std::max(acc[2], v[2]); acc[3] = v[3];
+        }
+        for (int i = 0; i < 4; ++i) out[i] = acc[i];
+        return LRK_OK;
+    }
     LRK_REQUIRE(h, h->has_train, "no train CSR");
     out[0] = h->nnz; out[1] = 32 * h->run_tiles; out[2] = (int64_t)h->max_item_deg; out[3] = LRK_RUN_MIN_DEGREE;
     return LRK_OK;
@@ -401,6 +437,7 @@ int lrk_stage_stats(lrk_handle_t h, int64_t out[4]) {
 
 int lrk_debug_stream(lrk_handle_t h, int32_t* su, int32_t* si, float* sr, int32_t* units, int64_t max_units, int64_t* n_units_out) {
     LRK_REQUIRE(h, h != nullptr && n_units_out != nullptr, "NULL argument");
+    LRK_NOT_MULTI(h, "lrk_debug_stream");
     LRK_REQUIRE(h, h->has_train, "no train CSR");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = h->stream;
@@ -420,23 +457,33 @@ int lrk_debug_stream(lrk_handle_t h, int32_t* su, int32_t* si, float* sr, int32_
 
 int lrk_sgd_safeguard_state(lrk_handle_t h, int32_t* conc_div, int64_t* rollbacks) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    if (h->multi) return lrk_sgd_safeguard_state(((MultiState*)h->multi)->child[0], conc_div, rollbacks);   // the ranks decide alike
     if (conc_div) *conc_div = h->conc_div;
     if (rollbacks) *rollbacks = h->rollbacks;
     return LRK_OK;
 }
 int lrk_last_epoch_ms(lrk_handle_t h, float* ms_out) {
     LRK_REQUIRE(h, h != nullptr && ms_out != nullptr, "NULL argument");
+    if (h->multi) { *ms_out = 0.f; for (lrk_handle_s* c : ((MultiState*)h->multi)->child) *ms_out = std::max(*ms_out, c->last_epoch_ms); return LRK_OK; }
     *ms_out = h->last_epoch_ms;
     return LRK_OK;
 }
 int lrk_launch_count(lrk_handle_t h, uint64_t* out) {
     LRK_REQUIRE(h, h != nullptr && out != nullptr, "NULL argument");
+    if (h->multi) {
+        MultiState* ms = (MultiState*)h->multi;
+        *out = 0;
+        for (lrk_handle_s* c : ms->child) *out += c->launches;
+        for (lrk_handle_s* c : ms->scorer) if (c) *out += c->launches;
+        return LRK_OK;
+    }
     *out = h->launches;
     return LRK_OK;
 }
 
 int lrk_bpr_peek_samples(lrk_handle_t h, int32_t epoch_idx, int64_t first, int64_t n, int32_t* out) {
     LRK_REQUIRE(h, h != nullptr && out != nullptr && n >= 0 && first >= 0, "bad arguments");
+    LRK_NOT_MULTI(h, "lrk_bpr_peek_samples");
     LRK_REQUIRE(h, h->has_train, "no train CSR");
     LRK_REQUIRE(h, h->world == 1, "not available in DSGD mode");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -462,6 +509,7 @@ int lrk_bpr_peek_samples(lrk_handle_t h, int32_t epoch_idx, int64_t first, int64
 // -------------------------------------------------------------------------------------------
 int lrk_predict_pairs(lrk_handle_t h, const int32_t* users, const int32_t* items, int64_t n, double* out) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_NOT_MULTI(h, "lrk_predict_pairs");
     LRK_REQUIRE(h, h->has_factors, "no factors set");
     LRK_REQUIRE(h, n >= 0 && (n == 0 || (users && items && out)), "bad arguments");
     LRK_REQUIRE(h, h->world == 1, "gather the factors with lrk_get_factors in DSGD mode");
@@ -494,6 +542,7 @@ int lrk_predict_pairs(lrk_handle_t h, const int32_t* users, const int32_t* items
 int lrk_eval_rating(lrk_handle_t h, int32_t U, const int64_t* t_rowptr, const int32_t* t_col, const double* t_val,
                     double min_rate, double max_rate, double* pred_out, double* rmse_out, double* mae_out) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_NOT_MULTI(h, "lrk_eval_rating");
     LRK_REQUIRE(h, h->has_factors, "no factors set");
     LRK_REQUIRE(h, U == h->U && t_rowptr, "test matrix must have numUsers rows");
     LRK_REQUIRE(h, h->world == 1, "gather the factors with lrk_get_factors in DSGD mode");
@@ -583,6 +632,7 @@ int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int
              int32_t* out_items, double* out_scores, int32_t* out_counts) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
     LRK_REQUIRE(h, nq >= 0 && (nq == 0 || (out_items && out_scores && out_counts)), "bad arguments");
+    if (h->multi) return multi_topn(h, users, nq, topn, exclude_train, out_items, out_scores, out_counts);
     int rc = topn_to_device(h, users, nq, topn, exclude_train);
     if (rc || nq == 0) return rc;
     return topn_lists_to_host(h, nq, topn, out_items, out_scores, out_counts);
@@ -591,6 +641,7 @@ int lrk_topn(lrk_handle_t h, const int32_t* users, int32_t nq, int32_t topn, int
 int lrk_eval_ranking(lrk_handle_t h, int32_t topn, const int64_t* t_rowptr, const int32_t* t_col, const double* t_val,
                      int32_t* out_items, double* out_scores, int32_t* out_counts, double out_measures[8]) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_NOT_MULTI(h, "lrk_eval_ranking");
     LRK_REQUIRE(h, t_rowptr && out_measures, "NULL argument");
     LRK_REQUIRE(h, h->has_train && h->has_factors, "set the train CSR and the factors first");
     LRK_REQUIRE(h, topn >= 1 && topn <= LRK_EVAL_MAX_TOPN, "lrk_eval_ranking supports 1 <= topn <= 64");
@@ -635,6 +686,7 @@ int lrk_eval_ranking(lrk_handle_t h, int32_t topn, const int64_t* t_rowptr, cons
 
 int lrk_topn_phase_ms(lrk_handle_t h, float out[6]) {
     LRK_REQUIRE(h, h != nullptr && out != nullptr, "NULL argument");
+    LRK_NOT_MULTI(h, "lrk_topn_phase_ms");
     for (int i = 0; i < 4; ++i) out[i] = h->topn_phase_ms[i];
     out[4] = h->topn_err_ratio;
     out[5] = (float)h->topn_resweep_users;
@@ -643,6 +695,14 @@ int lrk_topn_phase_ms(lrk_handle_t h, float out[6]) {
 
 int lrk_topn_stats(lrk_handle_t h, int64_t* fast_users, int64_t* fallback_users, float* ms_out) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    if (h->multi) {
+        int64_t a = 0, b = 0; float ms = 0.f;
+        for (lrk_handle_s* c : ((MultiState*)h->multi)->scorer) if (c) { a += c->topn_fast_users; b += c->topn_fallback_users; ms = std::max(ms, c->topn_ms); }
+        if (fast_users) *fast_users = a;
+        if (fallback_users) *fallback_users = b;
+        if (ms_out) *ms_out = ms;
+        return LRK_OK;
+    }
     if (fast_users) *fast_users = h->topn_fast_users;
     if (fallback_users) *fallback_users = h->topn_fallback_users;
     if (ms_out) *ms_out = h->topn_ms;
@@ -651,6 +711,7 @@ int lrk_topn_stats(lrk_handle_t h, int64_t* fast_users, int64_t* fallback_users,
 
 int lrk_probe_l2(lrk_handle_t h, uint64_t working_set_bytes, int32_t row_floats, double out_gbps[3]) {
     LRK_REQUIRE(h, h != nullptr && out_gbps != nullptr, "NULL argument");
+    if (h->multi) h = ((MultiState*)h->multi)->child[0];
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     return l2_probe_run(h, (size_t)working_set_bytes, row_floats, out_gbps);
 }
@@ -658,9 +719,181 @@ int lrk_probe_l2(lrk_handle_t h, uint64_t working_set_bytes, int32_t row_floats,
 int lrk_comm_unique_id(uint8_t out[128]) { return dsgd_unique_id(out); }
 int lrk_comm_init(lrk_handle_t h, int32_t rank, int32_t world, const uint8_t unique_id[128]) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
+    LRK_NOT_MULTI(h, "lrk_comm_init");
     LRK_REQUIRE(h, h->cfg.update_mode != LRK_UPDATE_REFERENCE_ORDER, "reference-order mode is single-GPU");
     LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_RANKSGD, "RankSGD is single-GPU in this build");
     return dsgd_comm_init(h, rank, world, unique_id);
 }
 
+int lrk_create_multi(const lrk_config_t* cfg, const int32_t* devices, int32_t n_devices, lrk_handle_t* out) {
+    if (!cfg || !out || !devices) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "NULL argument", __FILE__, __LINE__);
+    *out = nullptr;
+    if (n_devices < 1 || n_devices > 8) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "1 to 8 devices", __FILE__, __LINE__);
+    for (int a = 0; a < n_devices; ++a) for (int b = a + 1; b < n_devices; ++b)
+        if (devices[a] == devices[b]) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "a device is listed twice", __FILE__, __LINE__);
+    if (n_devices > 1 && (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER || cfg->model == LRK_MODEL_RANKSGD))
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "reference-order mode and RankSGD are single-GPU", __FILE__, __LINE__);
+    lrk_handle_s* h = new (std::nothrow) lrk_handle_s();
+    MultiState* ms = new (std::nothrow) MultiState();
+    if (!h || !ms) { delete h; delete ms; return lrk_fail(nullptr, LRK_ERR_NOMEM, "lrk_create_multi", "host allocation failed", __FILE__, __LINE__); }
+    h->cfg = *cfg; h->cfg.device = devices[0]; h->k = cfg->num_factors; h->multi = ms;
+    ms->n = n_devices; ms->devices.assign(devices, devices + n_devices);
+    ms->child.assign((size_t)n_devices, nullptr); ms->scorer.assign((size_t)n_devices, nullptr);
+    int rc = LRK_OK;
+    for (int g = 0; g < n_devices && rc == LRK_OK; ++g) {
+        lrk_config_t c = *cfg;
+        c.device = devices[g];
+        rc = lrk_create(&c, &ms->child[(size_t)g]);
+        if (rc == LRK_OK) ms->child[(size_t)g]->same_process = true;    // no CUDA IPC between the ranks of one process
+    }
+    for (int g = 0; g < n_devices; ++g) {
+        LrkWorker* w = new LrkWorker();
+        w->th = std::thread([w] { w->loop(); });
+        ms->workers.push_back(w);
+    }
+    if (rc == LRK_OK && n_devices > 1) {
+        uint8_t uid[128];
+        rc = lrk_comm_unique_id(uid);
+        if (rc == LRK_OK) rc = multi_run(h, ms, [&](int g) { return lrk_comm_init(ms->child[(size_t)g], g, ms->n, uid); });
+    }
+    if (rc != LRK_OK) {
+        const std::string why = h->err.empty() ? g_lrk_tls_error : h->err;
+        multi_destroy(h);
+        return lrk_fail(nullptr, rc, "lrk_create_multi", why.c_str(), __FILE__, __LINE__);
+    }
+    *out = h;
+    return LRK_OK;
+}
+
 }  // extern "C"
+
+static int multi_destroy(lrk_handle_s* h) {
+    MultiState* ms = (MultiState*)h->multi;
+    // the children's communicators are destroyed together, each on its own thread
+    if (!ms->workers.empty() && (int)ms->workers.size() == ms->n)
+        multi_run(h, ms, [&](int g) -> int { return ms->child[(size_t)g] ? lrk_destroy(ms->child[(size_t)g]) : (int)LRK_OK; });
+    else for (lrk_handle_s* c : ms->child) if (c) lrk_destroy(c);
+    for (lrk_handle_s* c : ms->scorer) if (c) lrk_destroy(c);
+    for (LrkWorker* w : ms->workers) { w->stop(); delete w; }
+    delete ms;
+    h->multi = nullptr;
+    delete h;
+    return LRK_OK;
+}
+
+static int multi_set_train_csr(lrk_handle_s* h, int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val) {
+    MultiState* ms = (MultiState*)h->multi;
+    LRK_REQUIRE(h, U >= ms->n, "fewer users than devices");
+    ms->U = U; ms->I = I;
+    ms->ub.assign((size_t)ms->n + 1, 0);
+    for (int g = 0; g <= ms->n; ++g) ms->ub[(size_t)g] = (int64_t)g * U / ms->n;
+    const int64_t nnz = rowptr[U];
+    ms->rowptr.assign(rowptr, rowptr + U + 1);                 // kept for the scoring handles (top-N train mask)
+    ms->col.assign(col, col + nnz);
+    ms->scorer_csr = false; ms->scorer_factors = false;
+    const int rc = multi_run(h, ms, [&](int g) -> int {
+        const int64_t lo = ms->ub[(size_t)g], hi = ms->ub[(size_t)g + 1], off = rowptr[lo];
+        std::vector<int64_t> rp((size_t)(hi - lo) + 1);
+        for (int64_t u = lo; u <= hi; ++u) rp[(size_t)(u - lo)] = rowptr[u] - off;
+        return lrk_set_train_csr(ms->child[(size_t)g], (int32_t)(hi - lo), I, rp.data(), col + off, val + off);
+    });
+    if (rc == LRK_OK) { h->U = U; h->I = I; h->nnz = nnz; h->has_train = true; }
+    return rc;
+}
+
+static int multi_set_factors(lrk_handle_s* h, const double* P, const double* Q, const double* bu, const double* bi, double mu) {
+    MultiState* ms = (MultiState*)h->multi;
+    LRK_REQUIRE(h, h->has_train, "call lrk_set_train_csr first (it fixes numUsers / numItems)");
+    LRK_REQUIRE(h, P && Q, "P and Q are required");
+    ms->mu = mu; ms->scorer_factors = false;
+    const int k = h->k;
+    const int rc = multi_run(h, ms, [&](int g) {
+        const int64_t lo = ms->ub[(size_t)g];
+        return lrk_set_factors(ms->child[(size_t)g], P + lo * k, Q, bu ? bu + lo : nullptr, bi, mu);
+    });
+    if (rc == LRK_OK) { h->has_factors = true; h->mu = mu; }
+    return rc;
+}
+
+static int multi_get_factors(lrk_handle_s* h, double* P, double* Q, double* bu, double* bi) {
+    MultiState* ms = (MultiState*)h->multi;
+    LRK_REQUIRE(h, h->has_factors, "no factors set");
+    const int k = h->k;
+    return multi_run(h, ms, [&](int g) {       // every rank enters the ring gather; rank 0 delivers the item side
+        const int64_t lo = ms->ub[(size_t)g];
+        return lrk_get_factors(ms->child[(size_t)g], P ? P + lo * k : nullptr, g == 0 ? Q : nullptr, bu ? bu + lo : nullptr, g == 0 ? bi : nullptr);
+    });
+}
+
+static int multi_sgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, double* loss_out) {
+    MultiState* ms = (MultiState*)h->multi;
+    LRK_REQUIRE(h, h->has_train && h->has_factors, "set the train CSR and the factors before training");
+    std::vector<double> loss((size_t)ms->n, 0.0);
+    const int rc = multi_run(h, ms, [&](int g) { return lrk_sgd_epoch(ms->child[(size_t)g], lr, reg_u, reg_i, reg_b, epoch_idx, &loss[(size_t)g]); });
+    if (loss_out) *loss_out = loss[0];          // all-reduced: the same on every rank
+    ms->scorer_factors = false;
+    return rc;
+}
+
+// top-N: users shard by block, every device holds the full item matrix, no collective
+static int multi_topn(lrk_handle_s* h, const int32_t* users, int32_t nq, int32_t topn, int32_t exclude_train, int32_t* out_items,
+                      double* out_scores, int32_t* out_counts) {
+    MultiState* ms = (MultiState*)h->multi;
+    LRK_REQUIRE(h, h->has_factors, "no factors set");
+    LRK_REQUIRE(h, topn > 0 && topn <= LRK_MAX_TOPN, "rec.recommender.ranking.topn should be more than 0!");
+    if (nq == 0) return LRK_OK;
+    if (users) for (int32_t c = 0; c < nq; ++c) LRK_REQUIRE(h, users[c] >= 0 && users[c] < ms->U, "user index out of range");
+    else LRK_REQUIRE(h, nq <= ms->U, "nq exceeds numUsers");
+    const int k = h->k;
+    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    int rc;
+    if (!ms->scorer_factors) {
+        ms->P.resize((size_t)ms->U * k); ms->Q.resize((size_t)ms->I * k);
+        if (biased) { ms->bu.resize((size_t)ms->U); ms->bi.resize((size_t)ms->I); }
+        if ((rc = multi_get_factors(h, ms->P.data(), ms->Q.data(), biased ? ms->bu.data() : nullptr, biased ? ms->bi.data() : nullptr))) return rc;
+    }
+    // queries by shard
+    std::vector<std::vector<int32_t>> local((size_t)ms->n), pos((size_t)ms->n);
+    for (int32_t c = 0; c < nq; ++c) {
+        const int32_t u = users ? users[c] : c;
+        int g = (int)(((int64_t)u * ms->n) / ms->U);
+        while (g > 0 && u < ms->ub[(size_t)g]) --g;
+        while (g + 1 < ms->n && u >= ms->ub[(size_t)g + 1]) ++g;
+        local[(size_t)g].push_back((int32_t)(u - ms->ub[(size_t)g]));
+        pos[(size_t)g].push_back(c);
+    }
+    const bool stage_csr = !ms->scorer_csr, stage_fac = !ms->scorer_factors;
+    rc = multi_run(h, ms, [&](int g) -> int {
+        int r = LRK_OK;
+        lrk_handle_s*& sc = ms->scorer[(size_t)g];
+        if (!sc) {
+            lrk_config_t c = h->cfg;
+            c.device = ms->devices[(size_t)g];
+            if ((r = lrk_create(&c, &sc))) return r;
+            sc->score_only = true;
+        }
+        const int64_t lo = ms->ub[(size_t)g], hi = ms->ub[(size_t)g + 1];
+        if (stage_csr) {
+            const int64_t off = ms->rowptr[(size_t)lo];
+            std::vector<int64_t> rp((size_t)(hi - lo) + 1);
+            for (int64_t u = lo; u <= hi; ++u) rp[(size_t)(u - lo)] = ms->rowptr[(size_t)u] - off;
+            if ((r = lrk_set_train_csr(sc, (int32_t)(hi - lo), ms->I, rp.data(), ms->col.data() + off, nullptr))) return r;
+        }
+        if (stage_csr || stage_fac)
+            if ((r = lrk_set_factors(sc, ms->P.data() + lo * k, ms->Q.data(), biased ? ms->bu.data() + lo : nullptr, biased ? ms->bi.data() : nullptr, ms->mu))) return r;
+        const size_t m = local[(size_t)g].size();
+        if (m == 0) return LRK_OK;
+        std::vector<int32_t> it(m * (size_t)topn), cn(m);
+        std::vector<double> sc_(m * (size_t)topn);
+        if ((r = lrk_topn(sc, local[(size_t)g].data(), (int32_t)m, topn, exclude_train, it.data(), sc_.data(), cn.data()))) return r;
+        for (size_t t = 0; t < m; ++t) {
+            const size_t c = (size_t)pos[(size_t)g][t];
+            memcpy(out_items + c * topn, it.data() + t * topn, sizeof(int32_t) * (size_t)topn);
+            memcpy(out_scores + c * topn, sc_.data() + t * topn, sizeof(double) * (size_t)topn);
+            out_counts[c] = cn[t];
+        }
+        return LRK_OK;
+    }, &ms->scorer);
+    if (rc == LRK_OK) { ms->scorer_csr = true; ms->scorer_factors = true; }
+    return rc;
+}

@@ -76,6 +76,11 @@ struct lrk_handle_s {
     // reference-order (wavefront) schedule, see sgd_exact.cuh
     void* exact = nullptr;
 
+    // single-process multi-GPU parent (multi.cuh): no device state of its own, forwards to one child per device
+    void* multi = nullptr;
+    bool same_process = false; // DSGD child of a multi handle: its ring neighbours live in this process (CUDA IPC cannot map them)
+    bool score_only = false;   // scoring child of a multi handle: the train CSR is kept for the top-N mask only (no COO stream)
+
     // DSGD
     void* comm = nullptr;   // ncclComm_t
     int rank = 0, world = 1;
