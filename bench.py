@@ -264,25 +264,46 @@ def traffic_probe(which):
             h.topn(TOPN_N)
 
 
-def sgd_roofline(h, kernel, kms, nnz_launch, bytes_per_update, row_floats, working_set_bytes, peaks, which, traffic, traffic_how):
+def issued_l2_row_bytes(item_deg, k, biased):
+    """bytes of factor rows (and biases) one epoch of the item-run-tile kernel REQUESTS from L2, counted from the staged layout
+    (csrc/staging.cuh, csrc/sgd_rating_body.inc): a rating on the general path gathers and RED-updates both rows; a rating of an
+    item-run tile (items with >= 128 ratings, 32 ratings per tile) gathers and RED-updates only the user row, the item row once per
+    flush period (8 ratings; 16 from 512 ratings per item, 32 from 1024)."""
+    deg = np.asarray(item_deg, np.int64)
+    row, b = k * 4, (4 if biased else 0)
+    run = np.where(deg >= 128, (deg // 32) * 32, 0)
+    period = np.where(deg >= 1024, 32, np.where(deg >= 512, 16, 8))
+    general = deg - run
+    per_run_rating = 2 * (row + b) + 2.0 * (row + b) / period
+    return float((general * (4 * row + 4 * b)).sum() + (run * per_run_rating).sum()), float(run.sum()) / float(max(1, deg.sum()))
+
+
+def sgd_roofline(h, kernel, kms, nnz_launch, bytes_per_update, row_floats, working_set_bytes, peaks, which, traffic, traffic_how,
+                 issued_bytes=None):
     """roofline object of an SGD epoch kernel.  The kernel gathers and RED-updates factor rows that live in L2, so its bound is
-    the L2's gather+RED rate, measured HERE by lrk_probe_l2 with the same instruction mix on a working set of the same size;
-    `achieved` = SURVEY 8(d)'s algorithmic bytes per update x updates per launch / kernel time.  HBM figures ride along."""
+    the L2's gather+RED rate, measured HERE by lrk_probe_l2 with the same instructions and row length on a working set of the same
+    size.  `achieved` = the row bytes the kernel requests from L2 per launch (issued_l2_row_bytes) / kernel time; SURVEY 8(d)'s
+    algorithmic bytes (no cache or register credit) and the HBM figures ride along."""
     l2 = h.probe_l2(working_set_bytes, row_floats)
-    achieved = bytes_per_update * nnz_launch / (kms * 1e-3) / 1e9
+    algo = bytes_per_update * nnz_launch / (kms * 1e-3) / 1e9
+    issued = None if issued_bytes is None else issued_bytes / (kms * 1e-3) / 1e9
+    achieved = issued if issued is not None else algo
     out = {"bound": "l2", "achieved": achieved, "peak": l2["mix"], "unit": "GB/s", "frac": achieved / l2["mix"], "traffic": traffic,
+           "achieved_is": "row bytes requested from L2 (gathers + REDs, counted from the staged layout)" if issued is not None
+                          else "algorithmic bytes (SURVEY 8d)",
            "peak_source": "lrk_probe_l2 in this run: random %d B row gathers (ld.global.cg.v4) + red.global.add.v4.f32 1:1 on a %.0f MB "
                           "working set; gathers alone %.0f GB/s, REDs alone %.0f GB/s" % (row_floats * 4, working_set_bytes / 1e6, l2["gather"], l2["red"]),
-           "kernel": kernel, "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_per_update * nnz_launch,
+           "kernel": kernel, "kernel_ms": kms,
+           "algorithmic": {"bytes_per_launch": bytes_per_update * nnz_launch, "achieved": algo, "frac_of_l2_peak": algo / l2["mix"],
+                           "frac_of_hbm_peak": algo / peaks["hbm_gbs"],
+                           "note": "SURVEY 8(d): 12 + 4*k*4 (+16) B per update, no cache credit; exceeds 1 because item-run tiles keep a popular "
+                                   "item's row in registers for 8-32 ratings -- bytes the model counts and the kernel never requests"},
            "traffic_source": traffic_how,
            "hbm": {"peak": peaks["hbm_gbs"], "peak_source": which,
-                   "achieved_algorithmic": achieved, "frac_algorithmic": achieved / peaks["hbm_gbs"],
                    "achieved_dram": None if traffic is None else traffic / (kms * 1e-3) / 1e9,
                    "frac_dram": None if traffic is None else traffic / (kms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-           "note": "algorithmic bytes = SURVEY 8(d), no cache credit; the factor set is L2-resident, so the bytes are L2 traffic and the bound is "
-                   "the L2 gather+RED rate (frac), not HBM (hbm.frac_algorithmic may exceed 1; hbm.frac_dram is what DRAM really moved). "
-                   "Item-run tiles keep a popular item's row in registers for 8-32 ratings, which is traffic the model counts and the kernel "
-                   "does not issue."}
+           "note": "the factor set is L2-resident (DRAM moves the COO stream only, hbm.frac_dram), so the binding resource is the L2's rate for "
+                   "row gathers + vector REDs; the REDs are the scarce half (peak_source)"}
     return out
 
 
@@ -367,6 +388,7 @@ def run_c2_single(args, torch, capi, synth, local, dev):
     traffic, traffic_how = (None, "skipped (--no-traffic)") if args.no_traffic else ncu_dram_bytes("sgd", "sgd_rating_epoch_kernel", 4)
     ws = (U + I) * (K_FACTORS + 1) * 4
     stage = h.stage_stats()
+    issued, run_share = issued_l2_row_bytes(np.bincount(d["col"], minlength=I), K_FACTORS, True)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -379,9 +401,25 @@ def run_c2_single(args, torch, capi, synth, local, dev):
                                    % (I, stage["run_tile_share"]),
                 "run_tile_share": stage["run_tile_share"]},
         "roofline": sgd_roofline(h, "sgd_rating_epoch_kernel<16,1,true,true>", kms, nnz, BYTES_PER_UPDATE, K_FACTORS, ws, peaks, which,
-                                 traffic, traffic_how),
+                                 traffic, traffic_how, issued_bytes=issued),
         "gpu_launches": int(launches), "clocks": clocks,
     }
+
+    # ---- the same shape with a flatter item popularity (Zipf 0.5: the head of real MovieLens data is far flatter than the survey's
+    #      Zipf 1.0 generator), so that the headline is not a property of the generator's head
+    if not args.no_flat:
+        df = synth.make_ratings("ml-20m", zipf=0.5)
+        h.set_train_csr(U, I, df["rowptr"], df["col"], df["val"])
+        h.set_factors(P0, Q0, bu0, bi0, float(df["val"].mean()))
+        tf_ms, kf_ms, lf = timed_epochs(torch, None, h, 1, stream, flush, max(3, min(args.steps, 10)), 3, (LR, REG, REG, REG_B), 1)
+        fdeg = np.bincount(df["col"], minlength=I)
+        line["run"]["flat_popularity"] = {
+            "workload": "same shape and hyper-parameters, item popularity Zipf(0.5)", "value": nnz / (kf_ms * 1e-3), "unit": UNIT,
+            "kernel_ms": kf_ms, "run_tile_share": h.stage_stats()["run_tile_share"],
+            "top_item_share": float(fdeg.max()) / nnz, "top_item_share_headline": float(np.bincount(d["col"], minlength=I).max()) / nnz,
+            "final_loss": lf[-1]}
+        h.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
+        h.set_factors(P0, Q0, bu0, bi0, mu)
 
     # ---- e2e: one trainModel() call of the shim per step, host buffers, copies inside the timed region
     if not args.no_e2e:
@@ -565,8 +603,10 @@ def run_c4_dsgd(args, torch, dist, capi, synth, rank, world, local, dev):
     roof = None
     if rank == 0:
         ws = ((hi - lo) + I) * C4_K * 4
+        issued, _ = issued_l2_row_bytes(np.bincount(col, minlength=I), C4_K, False)
         roof = sgd_roofline(h, "sgd_rating_epoch_kernel<32,1,false,true,true> (one launch per DSGD stratum)", kms, int(rowptr[-1]),
-                            C4_BYTES_PER_UPDATE, C4_K, ws, peaks, which, None, "not measured under DSGD (ncu runs one GPU)")
+                            C4_BYTES_PER_UPDATE, C4_K, ws, peaks, which, None, "not measured under DSGD (ncu runs one GPU)",
+                            issued_bytes=issued)
         roof["kernel_ms"] = kms
         roof["note"] = "per GPU (rank 0): kernel_ms is the epoch on the stream = N stratum kernels + N ring exchanges + loss all-reduce; " + roof["note"]
     h.close()
@@ -749,6 +789,7 @@ def main():
     ap.add_argument("--no-topn", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the at-scale parity leg (N=1)")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu DRAM-traffic probes (N=1)")
+    ap.add_argument("--no-flat", action="store_true", help="skip the flatter-popularity extra line (N=1)")
     ap.add_argument("--no-base", action="store_true", help="skip the 1-GPU base of the strong-scaling workload (N>1)")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling ML-20M extra line (N>1)")
     ap.add_argument("--traffic-probe", default="", help="internal: child mode of the ncu traffic probe (sgd | topn)")

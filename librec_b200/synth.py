@@ -29,12 +29,14 @@ def _cache_dir():
     return d
 
 
-def make_ratings(shape="ml-20m", binary=False, cache=True, shard=0):
+def make_ratings(shape="ml-20m", binary=False, cache=True, shard=0, zipf=1.0):
     """-> dict(U, I, rowptr int64[U+1], col int32[nnz], val float64[nnz]) ; exactly SHAPES[shape] nnz.
     `shard` selects an independent block of users over the SAME item catalogue (same popularity and
-    planted item factors) -- the per-rank user shard of the weak-scaling DSGD runs."""
+    planted item factors) -- the per-rank user shard of the weak-scaling DSGD runs.  `zipf` is the exponent of the item
+    popularity law (1.0 = the survey's generator; 0.5 gives the flatter head of real MovieLens data)."""
     U, I, nnz, seed = SHAPES[shape]
-    path = os.path.join(_cache_dir(), "%s_%s_s%d.npz" % (shape, "bin" if binary else "rat", shard))
+    tag = "" if zipf == 1.0 else "_z%g" % zipf
+    path = os.path.join(_cache_dir(), "%s_%s_s%d%s.npz" % (shape, "bin" if binary else "rat", shard, tag))
     if cache and os.path.exists(path):
         z = np.load(path)
         return {"U": U, "I": I, "rowptr": z["rowptr"], "col": z["col"], "val": z["val"].astype(np.float64)}
@@ -46,7 +48,7 @@ def make_ratings(shape="ml-20m", binary=False, cache=True, shard=0):
     deg = np.clip(deg, min(20, nnz / U), I / 2)
     deg = deg / deg.sum() * nnz
     # item popularity: Zipf(1.0) over a random permutation of item ids
-    pop = 1.0 / np.arange(1, I + 1, dtype=np.float64)
+    pop = 1.0 / np.arange(1, I + 1, dtype=np.float64) ** zipf
     pop = pop[rng_items.permutation(I)]
     cdf = np.cumsum(pop / pop.sum())
     keys = np.zeros(0, np.int64)
