@@ -656,9 +656,9 @@ def run_c4_dsgd(args, torch, dist, capi, synth, rank, world, local, dev):
 
 
 def h_exchange_desc():
-    if os.environ.get("LRK_DSGD_FUSED", "") == "1":
-        return "LRK_DSGD_FUSED=1: one cooperative kernel per epoch, peer stores + system-scope flags"
-    return "grouped ncclSend/ncclRecv after every stratum kernel"
+    if os.environ.get("LRK_DSGD_FUSED", "") == "0":
+        return "LRK_DSGD_FUSED=0: grouped ncclSend/ncclRecv after every stratum kernel"
+    return "one cooperative kernel per epoch: peer stores into the ring neighbour's buffer + system-scope flags (csrc/dsgd_fused.cuh)"
 
 
 def weak_ml20m(args, torch, dist, capi, synth, rank, world, local, dev, stream, flush):

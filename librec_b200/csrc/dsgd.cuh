@@ -383,6 +383,7 @@ static int dsgd_set_factors(lrk_handle_s* h, const double* P, const double* Q, c
         LRK_LAUNCH_CHECK(h);
     }
     s->cur = 0; s->cur_block = b;
+    s->fused.needs_reset = s->fused.mapped;
     if (h->cfg.model != LRK_MODEL_BPR) { int rc_n = refresh_user_norm2(h, false); if (rc_n) return rc_n; }
     LRK_CUDA(h, cudaStreamSynchronize(st));
     h->prev_loss = -1.0; h->conc_div = 1; h->good_epochs = 0; h->epochs_done = 0;
@@ -402,11 +403,14 @@ static int dsgd_fused_map(lrk_handle_s* h, DsgdState* s) {
     LRK_CUDA(h, cudaMalloc((void**)&f->d_abort, sizeof(int)));
     LRK_CUDA(h, cudaMemsetAsync(f->d_flags, 0, sizeof(unsigned long long) * 4, st));
     LRK_CUDA(h, cudaMemsetAsync(f->d_abort, 0, sizeof(int), st));
-    // handles of (qbuf[0], qbuf[1], flags) of every rank
+    // handles of (qbuf[0], qbuf[1], flags) of every rank.  A rank on which CUDA IPC does not work (other container, allocator without
+    // IPC support) still takes part in every collective below, and the verdict is all-reduced: either every rank maps its neighbours
+    // or all of them keep the ncclSend / ncclRecv ring -- a split decision would leave a kernel spinning on a flag nobody writes.
     cudaIpcMemHandle_t mine[3];
-    LRK_CUDA(h, cudaIpcGetMemHandle(&mine[0], s->qbuf[0]));
-    LRK_CUDA(h, cudaIpcGetMemHandle(&mine[1], s->qbuf[1]));
-    LRK_CUDA(h, cudaIpcGetMemHandle(&mine[2], f->d_flags));
+    memset(mine, 0, sizeof mine);
+    bool ok = cudaIpcGetMemHandle(&mine[0], s->qbuf[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine[1], s->qbuf[1]) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine[2], f->d_flags) == cudaSuccess;
+    cudaGetLastError();
     const size_t hb = sizeof(cudaIpcMemHandle_t) * 3;
     uint8_t *d_mine = nullptr, *d_all = nullptr;
     LRK_CUDA(h, cudaMalloc((void**)&d_mine, hb));
@@ -425,25 +429,32 @@ static int dsgd_fused_map(lrk_handle_s* h, DsgdState* s) {
         memcpy(&v, all.data() + hb * (size_t)r + sizeof(cudaIpcMemHandle_t) * (size_t)which, sizeof v);
         return v;
     };
-    auto open = [&](int r, int which, void** out) -> cudaError_t {
-        cudaError_t oe = cudaIpcOpenMemHandle(out, handle_of(r, which), cudaIpcMemLazyEnablePeerAccess);
-        if (oe == cudaSuccess) f->opened[f->n_opened++] = *out;
-        return oe;
+    auto open = [&](int r, int which, void** out) -> bool {
+        if (cudaIpcOpenMemHandle(out, handle_of(r, which), cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); *out = nullptr; return false; }
+        f->opened[f->n_opened++] = *out;
+        return true;
     };
     const int prev = dsgd_send_peer(rank, world), next = dsgd_recv_peer(rank, world);
     void *q0 = nullptr, *q1 = nullptr, *pf = nullptr, *nf = nullptr;
-    LRK_CUDA(h, open(prev, 0, &q0));
-    LRK_CUDA(h, open(prev, 1, &q1));
-    LRK_CUDA(h, open(prev, 2, &pf));
-    if (next == prev) nf = pf; else LRK_CUDA(h, open(next, 2, &nf));
+    ok = ok && open(prev, 0, &q0) && open(prev, 1, &q1) && open(prev, 2, &pf);
+    if (ok) { if (next == prev) nf = pf; else ok = open(next, 2, &nf); }
+    // all-reduce the verdict (min); it doubles as the barrier after which every rank's flags are zeroed
+    int verdict = ok ? 1 : 0;
+    LRK_CUDA(h, cudaMemcpyAsync(f->d_abort, &verdict, sizeof(int), cudaMemcpyHostToDevice, st));
+    LRK_NCCL(h, n->AllReduce(f->d_abort, f->d_abort, 1, ncclInt32, ncclMin, (ncclComm_t)h->comm, st));
+    LRK_CUDA(h, cudaMemcpyAsync(&verdict, f->d_abort, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaMemsetAsync(f->d_abort, 0, sizeof(int), st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    if (!verdict) {
+        dsgd_fused_release(f);
+        f->enabled = 0;                  // this communicator keeps the NCCL ring
+        return LRK_OK;
+    }
     f->peer_qbuf[0] = (float*)q0; f->peer_qbuf[1] = (float*)q1;
     f->prev_flags = (unsigned long long*)pf; f->next_flags = (unsigned long long*)nf;
     f->my_qbuf[0] = s->qbuf[0]; f->my_qbuf[1] = s->qbuf[1];
     f->seq = 0;
     f->mapped = true;
-    // nobody may push before every rank has zeroed its flags: one more collective as a barrier
-    LRK_NCCL(h, n->AllReduce(h->d_loss, h->d_loss, 1, ncclFloat64, ncclSum, (ncclComm_t)h->comm, st));
-    LRK_CUDA(h, cudaStreamSynchronize(st));
     return LRK_OK;
 }
 
@@ -502,7 +513,7 @@ static int dsgd_fused_group_launch_gv(lrk_handle_s* h, DsgdFusedGroupParams& fp)
 static int dsgd_fused_epoch(lrk_handle_s* h, DsgdState* s, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, bool* done) {
     *done = false;
     DsgdFused* f = &s->fused;
-    if (f->enabled < 0) { const char* e = getenv("LRK_DSGD_FUSED"); f->enabled = e && atoi(e) ? 1 : 0; }
+    if (f->enabled < 0) { const char* e = getenv("LRK_DSGD_FUSED"); f->enabled = (e && atoi(e) == 0) ? 0 : 1; }     // default on
     const int world = h->world;
     if (!f->enabled || h->same_process || world < 2 || world > LRK_FUSED_MAX_WORLD || h->cfg.model == LRK_MODEL_BPR ||
         h->cfg.update_mode != LRK_UPDATE_ATOMIC || h->V != 1 || (h->G < 16 && !h->group))
@@ -512,6 +523,17 @@ static int dsgd_fused_epoch(lrk_handle_s* h, DsgdState* s, float lr, float reg_u
     if (!coop) return LRK_OK;
     int rc = dsgd_fused_map(h, s);
     if (rc) return rc;
+    if (!f->enabled || !f->mapped) return LRK_OK;      // the ranks agreed to keep the ncclSend / ncclRecv ring
+    if (f->needs_reset) {
+        // every rank re-packed its ring buffers in lrk_set_factors: zero the flags, restart the sequence, and let nobody push before
+        // all ranks have done so
+        LRK_CUDA(h, cudaMemsetAsync(f->d_flags, 0, sizeof(unsigned long long) * 4, h->stream));
+        LRK_NCCL(h, nccl_api()->AllReduce(f->d_abort, f->d_abort, 1, ncclInt32, ncclMin, (ncclComm_t)h->comm, h->stream));
+        LRK_CUDA(h, cudaMemsetAsync(f->d_abort, 0, sizeof(int), h->stream));
+        LRK_CUDA(h, cudaStreamSynchronize(h->stream));
+        f->seq = 0;
+        f->needs_reset = false;
+    }
     if (h->group) {
         GroupUnits* gu = (GroupUnits*)h->group;
         DsgdFusedGroupParams gp;

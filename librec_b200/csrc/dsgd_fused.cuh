@@ -1,6 +1,8 @@
-// EXPERIMENTAL, OFF BY DEFAULT (LRK_DSGD_FUSED=1 turns it on): one persistent kernel per DSGD epoch with the ring exchange
-// inside it.  Written at the end of r01 from the measurements in DESIGN.md 5 / 8; it compiles, but it has NOT run on a GPU yet --
-// the default path is the sub-epoch loop of dsgd.cuh (SGD kernel + grouped ncclSend/ncclRecv per stratum).
+// One persistent kernel per DSGD epoch with the ring exchange inside it -- the default of the rating models between processes
+// (LRK_DSGD_FUSED=0 selects the sub-epoch loop of dsgd.cuh: SGD kernel + grouped ncclSend/ncclRecv per stratum; that loop is also
+// what BPR, the single-process multi handle and communicators without working CUDA IPC use).  r02, 8 x B200, config C4 (PMF k=128,
+// Netflix shape, strong scaling): 2.04 ms per epoch = 49.3 G updates/s against 2.17 ms = 46.4 G with the NCCL ring, parity checks
+// (conflict-free epoch = oracle to 2e-8, C1 within 1e-3) green at 2 and 8 ranks (profiles/r02_*).
 //
 // Why: after r01 a DSGD stratum runs at the whole-matrix rate, so what separates N GPUs from N x one GPU is per sub-epoch the
 // NCCL send/recv pair (0.026-0.03 ms when both ranks are in step), launch gaps and the wait for the slower neighbour.  NCCL's
@@ -174,6 +176,7 @@ struct DsgdFused {
     void* opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n_opened = 0;
     unsigned long long seq = 0;
+    bool needs_reset = false;                // lrk_set_factors re-packed the ring (buffer 0 holds the block again): restart the flag sequence
 };
 
 static void dsgd_fused_release(DsgdFused* f) {

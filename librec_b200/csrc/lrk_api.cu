@@ -82,6 +82,10 @@ int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out) {
     h->cfg = *cfg;
     h->k = cfg->num_factors;
     layout_for_k(h->k, &h->ld, &h->G, &h->V);
+    {   // the user-group kernel (LRK_SGD_GROUP=1, sgd_group.cuh) needs at least 8 lanes per rating: small k are padded to 32 columns
+        const char* env = getenv("LRK_SGD_GROUP");
+        if (env && atoi(env) != 0 && lrk_is_rating_model(h) && cfg->update_mode == LRK_UPDATE_ATOMIC && h->ld < 32) { h->ld = 32; h->G = 8; h->V = 1; }
+    }
     h->sm_count = prop.multiProcessorCount;
     int rc = LRK_OK;
     do {
@@ -123,6 +127,9 @@ int lrk_destroy(lrk_handle_t h) {
     if (h->h_pnorm2) cudaFreeHost(h->h_pnorm2);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_copy0) cudaEventDestroy(h->ev_copy0);
+    if (h->ev_copy1) cudaEventDestroy(h->ev_copy1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return LRK_OK;

@@ -21,6 +21,8 @@ struct lrk_handle_s {
     int64_t nnz = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // second stream: the H2D copy of the rating values overlaps the sort of the staging
+    cudaEvent_t ev_copy0 = nullptr, ev_copy1 = nullptr;
 
     // train CSR (device): membership for BPR sampling and the top-N train mask
     int64_t* d_rowptr = nullptr;

@@ -203,7 +203,17 @@ static int stage_coo_from_csr(lrk_handle_s* h, const int64_t* d_rowptr, const in
         !w.item_start || !w.runs || !w.run_base || !w.max_deg || !w.tmp || !d_flags)
         return lrk_fail(h, LRK_ERR_NOMEM, "stage_coo_from_csr", "scratch arena too small", __FILE__, __LINE__);
     int flags = 0;
-    LRK_CUDA(h, cudaMemcpyAsync(d_val, h_val, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    // the values (8 B per rating, two thirds of the H2D bytes) are needed only by the final gather: copy them on a second stream
+    // while the keys are built and sorted
+    if (!h->copy_stream) {
+        LRK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        LRK_CUDA(h, cudaEventCreateWithFlags(&h->ev_copy0, cudaEventDisableTiming));
+        LRK_CUDA(h, cudaEventCreateWithFlags(&h->ev_copy1, cudaEventDisableTiming));
+    }
+    LRK_CUDA(h, cudaEventRecord(h->ev_copy0, st));                       // earlier users of the scratch arena are done
+    LRK_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy0, 0));
+    LRK_CUDA(h, cudaMemcpyAsync(d_val, h_val, sizeof(double) * n, cudaMemcpyHostToDevice, h->copy_stream));
+    LRK_CUDA(h, cudaEventRecord(h->ev_copy1, h->copy_stream));
     LRK_CUDA(h, cudaMemsetAsync(d_flags, 0, sizeof(int), st));
     const int nb = lrk_ceil_div(nnz, 256);
     coo_rows_kernel<<<nb, 256, 0, st>>>(d_rowptr, U, nnz, row_of);
@@ -224,6 +234,7 @@ static int stage_coo_from_csr(lrk_handle_s* h, const int64_t* d_rowptr, const in
         item_degree_kernel<<<nb, 256, 0, st>>>(d_col, nnz, w.deg); LRK_LAUNCH_CHECK(h);
         if ((rc = lrk_dev_alloc(h, &h->d_item_deg, (size_t)I + 4))) return rc;
         LRK_CUDA(h, cudaMemcpyAsync(h->d_item_deg, w.deg, sizeof(uint32_t) * (size_t)I, cudaMemcpyDeviceToDevice, st));
+        LRK_CUDA(h, cudaStreamWaitEvent(st, h->ev_copy1, 0));
         if ((rc = stage_group_stream(h, d_rowptr, d_col, row_of, d_val, U, I, nnz, nullptr, 1, group_workers, h->cfg.seed, sc, w.tmp, tmp_bytes,
                                      keys, keys2, idx, perm, su, si, sr, group_out))) return rc;
         LRK_CUDA(h, cudaStreamSynchronize(st));
@@ -232,6 +243,7 @@ static int stage_coo_from_csr(lrk_handle_s* h, const int64_t* d_rowptr, const in
         if ((rc = stage_tile_keys(h, d_col, I, nnz, nullptr, 1, h->cfg.seed, w, keys, idx))) return rc;
         size_t tb = tmp_bytes;
         LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(w.tmp, tb, keys, keys2, idx, perm, (int)nnz, 0, 58, st));
+        LRK_CUDA(h, cudaStreamWaitEvent(st, h->ev_copy1, 0));
         coo_gather_kernel<<<nb, 256, 0, st>>>(perm, row_of, d_col, d_val, nnz, su, si, sr);
         LRK_LAUNCH_CHECK(h);
         uint32_t max_deg = 0, last_base = 0, last_runs = 0;
@@ -245,6 +257,7 @@ static int stage_coo_from_csr(lrk_handle_s* h, const int64_t* d_rowptr, const in
         h->run_tiles = (int64_t)last_base + (int64_t)last_runs;
         h->max_item_deg = max_deg;
     }
+    if (flags) LRK_CUDA(h, cudaStreamSynchronize(h->copy_stream));      // the caller may reuse its buffers on return
     if (flags & 1) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "rowptr is not a monotone prefix sum ending at nnz", __FILE__, __LINE__);
     if (flags & 2) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "column index out of range", __FILE__, __LINE__);
     if (flags & 4) return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_train_csr", "columns must be strictly ascending inside a row", __FILE__, __LINE__);

@@ -80,7 +80,7 @@ __global__ void group_unit_desc_kernel(const uint32_t* __restrict__ started, con
 __global__ void group_keys_kernel(const int32_t* __restrict__ row_of, const int32_t* __restrict__ col, int64_t nnz, int32_t U, int32_t I,
                                   const int32_t* __restrict__ bounds, int world, const uint32_t* __restrict__ degv,
                                   const uint32_t* __restrict__ rowlo, const uint32_t* __restrict__ started, const uint32_t* __restrict__ incl,
-                                  uint32_t target, uint64_t seed, int4* __restrict__ units, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+                                  uint32_t target, uint64_t seed, int rotate, int4* __restrict__ units, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nnz) return;
     const int32_t u = row_of[e], i = col[e];
@@ -92,7 +92,7 @@ __global__ void group_keys_kernel(const int32_t* __restrict__ row_of, const int3
     if (st > 1) unit += ((uint32_t)e - rowlo[v]) / target;           // heavy user: slice by position in its (block) row
     const int32_t lo_i = bounds ? bounds[b] : 0, hi_i = bounds ? bounds[b + 1] : I;
     const uint32_t width = (uint32_t)(hi_i - lo_i);
-    const uint32_t rot = lrk_hash32((uint64_t)unit ^ (seed * 0xA24BAED4963EE407ull)) % width;
+    const uint32_t rot = rotate ? lrk_hash32((uint64_t)unit ^ (seed * 0xA24BAED4963EE407ull)) % width : 0u;
     uint32_t ritem = (uint32_t)(i - lo_i) + width - rot;
     if (ritem >= width) ritem -= width;
     const uint32_t first_user = (uint32_t)units[unit].z;
@@ -177,7 +177,11 @@ static int stage_group_stream(lrk_handle_s* h, const int64_t* d_rowptr, const in
     if (e == cudaSuccess) e = cudaMemsetAsync(g->d_counter, 0, sizeof(unsigned int) * 64, st);
     if (e != cudaSuccess) { group_units_release(g); LRK_CUDA(h, e); }
     group_unit_desc_kernel<<<vb, 256, 0, st>>>(started, incl, U, world, g->d_units); h->launches++;
-    group_keys_kernel<<<nb, 256, 0, st>>>(row_of, d_col, nnz, U, I, d_bounds, world, degv, rowlo, started, incl, g->target, seed, g->d_units, keys, idx);
+    // LRK_SGD_GROUP_ROTATE=0: every unit walks its items in plain ascending order, exactly like a row of the reference's CSR walk
+    // (all concurrently running units then start on the low item ids together; a probe for small matrices)
+    const char* rot_env = getenv("LRK_SGD_GROUP_ROTATE");
+    const int rotate = (rot_env && atoi(rot_env) == 0) ? 0 : 1;
+    group_keys_kernel<<<nb, 256, 0, st>>>(row_of, d_col, nnz, U, I, d_bounds, world, degv, rowlo, started, incl, g->target, seed, rotate, g->d_units, keys, idx);
     h->launches++;
     e = cudaGetLastError();
     tb = tmp_bytes;

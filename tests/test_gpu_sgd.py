@@ -425,3 +425,24 @@ def test_group_kernel_c1_biasedmf_rmse_mae_within_1e3(O, capi, c1, monkeypatch):
         rmse, mae = h.eval_rating(te.U, te.rowptr, te.col, te.val, 1.0, 5.0)
     print("group kernel C1: rmse %.6f (oracle %.6f) mae %.6f (oracle %.6f)" % (rmse, pins["biasedmf"]["rmse"], mae, pins["biasedmf"]["mae"]))
     assert abs(rmse - pins["biasedmf"]["rmse"]) < 1e-3 and abs(mae - pins["biasedmf"]["mae"]) < 1e-3
+
+
+@pytest.mark.parametrize("rotate", ["1", "0"])
+def test_group_kernel_c1_pmf_tracks_reference_order(O, capi, c1, monkeypatch, rotate):
+    """PMF at lr 0.01 is sensitive to the visiting order (the shuffled stream kernel is held to 1e-2 above).  The user-group kernel
+    walks user by user, items ascending, like the reference: how close does that get?  (k=6 is padded to the 8-lane layout.)"""
+    monkeypatch.setenv("LRK_SGD_GROUP", "1")
+    monkeypatch.setenv("LRK_SGD_GROUP_ROTATE", rotate)
+    tr, te, pins = c1["train"], c1["test"], c1["pins"]
+    O.lib().lro_rng_set_state(*c1["rng_state"])
+    P, Q, _, _ = O.mf_setup(tr.U, tr.I, 6, False)
+    with capi.Handle(capi.MODEL_PMF, 6) as h:
+        h.set_train_csr(tr.U, tr.I, tr.rowptr, tr.col, tr.val)
+        assert h.debug_stream(tr.nnz)[3] is not None
+        h.set_factors(P, Q)
+        losses = [h.sgd_epoch(0.01, 0.08, 0.08, 0.0, it + 1) for it in range(70)]
+        gP, gQ, _, _ = h.get_factors()
+    rmse, mae = O.eval_rating(O.PMF, te, 6, gP, gQ, None, None, pins["global_mean"], 1.0, 5.0)
+    print("group kernel PMF C1 (rotate=%s): rmse %.6f (oracle %.6f, d %+.2e)  mae %.6f (oracle %.6f, d %+.2e)  loss_70 %.2f (oracle %.2f)" % (
+        rotate, rmse, pins["pmf"]["rmse"], rmse - pins["pmf"]["rmse"], mae, pins["pmf"]["mae"], mae - pins["pmf"]["mae"], losses[-1], pins["pmf"]["loss_70"]))
+    assert abs(rmse - pins["pmf"]["rmse"]) < 1e-2 and abs(mae - pins["pmf"]["mae"]) < 1e-2
