@@ -10,6 +10,7 @@
 #include "lrk_common.cuh"
 #include <condition_variable>
 #include <functional>
+#include <new>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -69,7 +70,12 @@ struct MultiState {
 
 // run f(g) on every device's thread; first failing child wins, its message is copied to the parent
 static int multi_run(lrk_handle_s* h, MultiState* ms, const std::function<int(int)>& f, const std::vector<lrk_handle_s*>* who = nullptr) {
-    for (int g = 0; g < ms->n; ++g) ms->workers[(size_t)g]->submit([&f, g] { return f(g); });
+    for (int g = 0; g < ms->n; ++g)
+        ms->workers[(size_t)g]->submit([&f, g]() -> int {
+            try { return f(g); }
+            catch (const std::bad_alloc&) { return (int)LRK_ERR_NOMEM; }       // nothing may unwind through a worker thread
+            catch (...) { return (int)LRK_ERR_INVALID; }
+        });
     int rc = LRK_OK;
     for (int g = 0; g < ms->n; ++g) {
         const int r = ms->workers[(size_t)g]->wait();

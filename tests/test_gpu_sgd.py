@@ -427,12 +427,13 @@ def test_group_kernel_c1_biasedmf_rmse_mae_within_1e3(O, capi, c1, monkeypatch):
     assert abs(rmse - pins["biasedmf"]["rmse"]) < 1e-3 and abs(mae - pins["biasedmf"]["mae"]) < 1e-3
 
 
-@pytest.mark.parametrize("rotate", ["1", "0"])
-def test_group_kernel_c1_pmf_tracks_reference_order(O, capi, c1, monkeypatch, rotate):
+def test_group_kernel_c1_pmf_tracks_reference_order(O, capi, c1, monkeypatch):
     """PMF at lr 0.01 is sensitive to the visiting order (the shuffled stream kernel is held to 1e-2 above).  The user-group kernel
-    walks user by user, items ascending, like the reference: how close does that get?  (k=6 is padded to the 8-lane layout.)"""
+    walks user by user like the reference, every unit through its own rotation of the ascending item order (k=6 is padded to the
+    8-lane layout).  r02 on a B200: RMSE -3.2e-3 / MAE -1.7e-3 from the reference -- 2-3x closer than the shuffled stream, still not
+    the 1e-3 the reference-order mode delivers.  (Without the rotation, LRK_SGD_GROUP_ROTATE=0, all units start on the low item ids
+    together and this configuration diverges: the rotation is what spreads the units over the catalogue.)"""
     monkeypatch.setenv("LRK_SGD_GROUP", "1")
-    monkeypatch.setenv("LRK_SGD_GROUP_ROTATE", rotate)
     tr, te, pins = c1["train"], c1["test"], c1["pins"]
     O.lib().lro_rng_set_state(*c1["rng_state"])
     P, Q, _, _ = O.mf_setup(tr.U, tr.I, 6, False)
@@ -443,6 +444,6 @@ def test_group_kernel_c1_pmf_tracks_reference_order(O, capi, c1, monkeypatch, ro
         losses = [h.sgd_epoch(0.01, 0.08, 0.08, 0.0, it + 1) for it in range(70)]
         gP, gQ, _, _ = h.get_factors()
     rmse, mae = O.eval_rating(O.PMF, te, 6, gP, gQ, None, None, pins["global_mean"], 1.0, 5.0)
-    print("group kernel PMF C1 (rotate=%s): rmse %.6f (oracle %.6f, d %+.2e)  mae %.6f (oracle %.6f, d %+.2e)  loss_70 %.2f (oracle %.2f)" % (
-        rotate, rmse, pins["pmf"]["rmse"], rmse - pins["pmf"]["rmse"], mae, pins["pmf"]["mae"], mae - pins["pmf"]["mae"], losses[-1], pins["pmf"]["loss_70"]))
-    assert abs(rmse - pins["pmf"]["rmse"]) < 1e-2 and abs(mae - pins["pmf"]["mae"]) < 1e-2
+    print("group kernel PMF C1: rmse %.6f (oracle %.6f, d %+.2e)  mae %.6f (oracle %.6f, d %+.2e)  loss_70 %.2f (oracle %.2f)" % (
+        rmse, pins["pmf"]["rmse"], rmse - pins["pmf"]["rmse"], mae, pins["pmf"]["mae"], mae - pins["pmf"]["mae"], losses[-1], pins["pmf"]["loss_70"]))
+    assert abs(rmse - pins["pmf"]["rmse"]) < 5e-3 and abs(mae - pins["pmf"]["mae"]) < 5e-3
