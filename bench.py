@@ -570,23 +570,29 @@ def run_c4_dsgd(args, torch, dist, capi, synth, rank, world, local, dev):
         L = capi.load()
         vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
 
+        phases = []
+
         def call():
             hP[:] = P0[lo:hi]; hQ[:] = Q0
             dist.barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
             rc = L.lrk_set_train_csr(h._h, hi - lo, I, vp(rp), vp(cl), vp(vl))
+            t1 = time.perf_counter()
             rc |= L.lrk_set_factors(h._h, vp(hP), vp(hQ), None, None, 0.0)
+            t2 = time.perf_counter()
             rc |= L.lrk_sgd_epochs(h._h, E2E_EPOCHS, C4_LR, 1.0, C4_LR, C4_REG, C4_REG, 0.0, 1, vp(hloss))
+            t3 = time.perf_counter()
             rc |= L.lrk_get_factors(h._h, vp(hP), vp(hQ), None, None)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            phases.append([(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (time.perf_counter() - t3) * 1e3])
             if rc != 0:
                 raise RuntimeError("e2e call failed: %s" % L.lrk_last_error(h._h))
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
         call()
-        calls = 2
+        calls = 3
         tt = [call() for _ in range(calls)]
         byt = torch.tensor([rp.nbytes + cl.nbytes + vl.nbytes + hP.nbytes + hQ.nbytes, hP.nbytes + hQ.nbytes + 8 * E2E_EPOCHS],
                            dtype=torch.float64, device="cuda")
@@ -596,7 +602,8 @@ def run_c4_dsgd(args, torch, dist, capi, synth, rank, world, local, dev):
                "step": "one trainModel() per rank through the C ABI from pinned host buffers: lrk_set_train_csr(shard) + lrk_set_factors + "
                        "lrk_sgd_epochs(%d) + lrk_get_factors (ring gather of the item factors); wall clock between barriers, max over ranks; "
                        "bytes summed over ranks" % E2E_EPOCHS,
-               "ms_per_call": float(np.mean(tt)) * 1e3, "calls": calls}
+               "ms_per_call": float(np.mean(tt)) * 1e3, "calls": calls, "ms_calls": [x * 1e3 for x in tt],
+               "rank0_phases_ms": {"names": ["set_train_csr", "set_factors", "sgd_epochs(%d)" % E2E_EPOCHS, "get_factors"], "calls": phases[1:]}}
         for p in (p1, p2, p3, p4, p5, p6):
             L.lrk_host_free(p)
     peaks, which = measured_peaks()

@@ -55,7 +55,11 @@ typedef enum {
     LRK_MODEL_BPR = 2,
     /* ranksgd -> recommender/cf/ranking/RankSGDRecommender.java:62-108: one update per train entry
      * against a negative drawn by item popularity; single GPU; lrk_sgd_epoch ignores the regularisation arguments */
-    LRK_MODEL_RANKSGD = 3
+    LRK_MODEL_RANKSGD = 3,
+    /* gbpr -> recommender/cf/ranking/GBPRRecommender.java:82-172: group-preference BPR.  Item biases only
+     * (lrk_set_factors: bu may be NULL, bi is required); rec.gpbr.rho / rec.gpbr.gsize through lrk_set_param; single GPU;
+     * lrk_sgd_epoch's reg_b is rec.bias.regularization */
+    LRK_MODEL_GBPR = 4
 } lrk_model;
 
 /* how concurrent updates to one factor row are combined */
@@ -116,12 +120,18 @@ LRK_API int lrk_set_train_csr(lrk_handle_t h, int32_t num_users, int32_t num_ite
                       const int64_t* rowptr, const int32_t* col, const double* val);
 /* replaces: DenseMatrix userFactors/itemFactors (double[][], math/structure/DenseMatrix.java:20),
  * VectorBasedDenseVector userBiases/itemBiases (BiasedMFRecommender.java:40-45), globalMean
- * (MatrixRecommender.java:109).  P is U x k, Q is I x k; bu/bi may be NULL unless model is BIASEDMF. */
+ * (MatrixRecommender.java:109).  P is U x k, Q is I x k; bu/bi may be NULL unless model is BIASEDMF (GBPR: bi is required). */
 LRK_API int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const double* bu, const double* bi,
                     double global_mean);
 /* copies the current factors back (any pointer may be NULL to skip it) so the inherited Java
  * predict()/recommendRating()/evaluators keep working on DenseMatrix. */
 LRK_API int lrk_get_factors(lrk_handle_t h, double* P, double* Q, double* bu, double* bi);
+
+/* model hyper-parameters that are not arguments of lrk_sgd_epoch (read by the reference in setup()):
+ *   "gbpr.rho"   rec.gpbr.rho   (float, default 1.5; GBPRRecommender.java:71)
+ *   "gbpr.gsize" rec.gpbr.gsize (int 1..8, default 2; GBPRRecommender.java:72)
+ * Unknown names fail with LRK_ERR_INVALID. */
+LRK_API int lrk_set_param(lrk_handle_t h, const char* name, double value);
 
 /* ---- training ----------------------------------------------------------------------- */
 /* replaces ONE iteration of trainModel():
@@ -160,7 +170,7 @@ LRK_API int lrk_sgd_safeguard_state(lrk_handle_t h, int32_t* conc_div, int64_t* 
 /* number of kernels this handle has launched since creation */
 LRK_API int lrk_launch_count(lrk_handle_t h, uint64_t* out);
 /* debug / test aid: the (user, positive item, negative item) triples that BPR epoch `epoch_idx`
- * draws for samples [first, first+n) -- out is int32[3*n]. */
+ * draws for samples [first, first+n) -- out is int32[3*n]; GBPR: int32[11*n] = {u, i, j, the group's users (8 slots, -1 padded)}. */
 LRK_API int lrk_bpr_peek_samples(lrk_handle_t h, int32_t epoch_idx, int64_t first, int64_t n, int32_t* out);
 
 /* ---- prediction --------------------------------------------------------------------- */

@@ -82,6 +82,16 @@ jint LRK_JNI(stageStats)(JNIEnv* env, jclass c, jlong h, jlongArray out4) {
     return rc;
 }
 
+jint LRK_JNI(setParam)(JNIEnv* env, jclass c, jlong h, jbyteArray nameUtf8, jdouble value) {
+    char name[64];
+    jsize n = (*env)->GetArrayLength(env, nameUtf8);
+    (void)c;
+    if (n > (jsize)sizeof name - 1) n = (jsize)sizeof name - 1;
+    (*env)->GetByteArrayRegion(env, nameUtf8, 0, n, (jbyte*)name);
+    name[n] = 0;
+    return lrk_set_param(H(h), name, value);
+}
+
 /* ---- training ----------------------------------------------------------------------- */
 jint LRK_JNI(sgdEpoch)(JNIEnv* env, jclass c, jlong h, jfloat lr, jfloat regU, jfloat regI, jdouble regB, jint epochIdx, jdoubleArray lossOut) {
     double loss = 0.0;

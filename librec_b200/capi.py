@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _build
 
-MODEL_BIASEDMF, MODEL_PMF, MODEL_BPR, MODEL_RANKSGD = 0, 1, 2, 3
+MODEL_BIASEDMF, MODEL_PMF, MODEL_BPR, MODEL_RANKSGD, MODEL_GBPR = 0, 1, 2, 3, 4
 UPDATE_ATOMIC, UPDATE_HOGWILD, UPDATE_REFERENCE_ORDER = 0, 1, 2
 OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NOMEM, ERR_DIVERGED = 0, -1, -2, -3, -4, -5
 
@@ -49,6 +49,7 @@ SIGNATURES = {
     "lrk_set_train_csr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lrk_set_factors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "lrk_get_factors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lrk_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "lrk_sgd_epoch": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_double, C.c_int32, C.POINTER(C.c_double)]),
     "lrk_sgd_epochs": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double, C.c_int32,
                                  C.c_void_p]),
@@ -162,11 +163,14 @@ class Handle:
     def get_factors(self):
         P = np.empty((self.U, self.k), np.float64)
         Q = np.empty((self.I, self.k), np.float64)
-        biased = self.model == MODEL_BIASEDMF
+        biased = self.model in (MODEL_BIASEDMF, MODEL_GBPR)
         bu = np.empty(self.U, np.float64) if biased else None
         bi = np.empty(self.I, np.float64) if biased else None
         _check(load().lrk_get_factors(self._h, _ptr(P), _ptr(Q), _ptr(bu), _ptr(bi)), self._h)
         return P, Q, bu, bi
+
+    def set_param(self, name, value):
+        _check(load().lrk_set_param(self._h, name.encode(), float(value)), self._h)
 
     # -- training
     def sgd_epoch(self, lr, reg_u, reg_i, reg_b=0.0, epoch_idx=1):
@@ -206,7 +210,7 @@ class Handle:
         return n.value
 
     def bpr_peek_samples(self, epoch_idx, first, n):
-        out = np.empty((n, 3), np.int32)
+        out = np.empty((n, 11 if self.model == MODEL_GBPR else 3), np.int32)
         _check(load().lrk_bpr_peek_samples(self._h, epoch_idx, first, n, out), self._h)
         return out
 

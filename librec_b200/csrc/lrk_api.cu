@@ -6,6 +6,7 @@
 #include "staging_group.cuh"
 #include "sgd_group.cuh"
 #include "sgd_exact.cuh"
+#include "sgd_gbpr.cuh"
 #include <chrono>
 #include "topn_exact.cuh"
 #include "topn_tc.cuh"
@@ -26,6 +27,114 @@ static int multi_sgd_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, 
 static int multi_topn(lrk_handle_s* h, const int32_t* users, int32_t nq, int32_t topn, int32_t exclude_train, int32_t* out_items,
                       double* out_scores, int32_t* out_counts);
 #define LRK_NOT_MULTI(h, what) LRK_REQUIRE(h, !(h)->multi, what " is not available on a multi-device handle: call lrk_get_factors and use a single-device handle")
+
+// GBPR: train CSC (users of every item, ascending) next to the CSR -- the group draws of GBPRRecommender.java:104-116 walk an item's column
+static int gbpr_stage(lrk_handle_s* h) {
+    cudaStream_t st = h->stream;
+    GbprState* g = (GbprState*)h->gbpr;
+    if (!g) { g = new GbprState(); h->gbpr = g; }
+    const int64_t nnz = h->nnz;
+    const int32_t U = h->U, I = h->I;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &g->d_colptr, (size_t)I + 1))) return rc;
+    if ((rc = lrk_dev_alloc(h, &g->d_cusers, (size_t)nnz))) return rc;
+    if (nnz == 0) { LRK_CUDA(h, cudaMemsetAsync(g->d_colptr, 0, sizeof(int64_t) * ((size_t)I + 1), st)); return LRK_OK; }
+    size_t tb_sort = 0, tb_scan = 0;
+    int end_bit = 1;
+    while (end_bit < 32 && ((int64_t)1 << end_bit) < (int64_t)I) ++end_bit;
+    LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, (uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int)nnz, 0, end_bit, st));
+    LRK_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, tb_scan, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)I, st));
+    const size_t tb = std::max(tb_sort, tb_scan) + 256;
+    LrkScratch sc;
+    if ((rc = lrk_scratch_begin(h, (size_t)nnz * 16 + (size_t)I * 8 + tb + 16 * 256, &sc))) return rc;
+    uint32_t *k_in = sc.take<uint32_t>((size_t)nnz), *k_out = sc.take<uint32_t>((size_t)nnz);
+    int32_t* rows = sc.take<int32_t>((size_t)nnz);
+    uint32_t *deg = sc.take<uint32_t>((size_t)I), *deg_ex = sc.take<uint32_t>((size_t)I);
+    void* tmp = sc.take<char>(tb);
+    if (!k_in || !k_out || !rows || !deg || !deg_ex || !tmp) return lrk_fail(h, LRK_ERR_NOMEM, "gbpr_stage", "scratch arena too small", __FILE__, __LINE__);
+    const int nb = lrk_ceil_div(nnz, 256);
+    coo_rows_kernel<<<nb, 256, 0, st>>>(h->d_rowptr, U, nnz, rows); LRK_LAUNCH_CHECK(h);
+    LRK_CUDA(h, cudaMemcpyAsync(k_in, h->d_col, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
+    LRK_CUDA(h, cudaMemsetAsync(deg, 0, sizeof(uint32_t) * (size_t)I, st));
+    item_degree_kernel<<<nb, 256, 0, st>>>(h->d_col, nnz, deg); LRK_LAUNCH_CHECK(h);
+    size_t t1 = tb;
+    LRK_CUDA(h, cub::DeviceScan::ExclusiveSum(tmp, t1, deg, deg_ex, (int)I, st));
+    gbpr_colptr_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(deg_ex, deg, I, g->d_colptr); LRK_LAUNCH_CHECK(h);
+    t1 = tb;
+    LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(tmp, t1, k_in, k_out, rows, g->d_cusers, (int)nnz, 0, end_bit, st));   // stable: users ascending
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    return LRK_OK;
+}
+
+static int gbpr_fill(lrk_handle_s* h, GbprParams& p, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx) {
+    GbprState* g = (GbprState*)h->gbpr;
+    memset(&p, 0, sizeof p);
+    p.n = h->nnz; p.P = h->P32; p.Q = h->Q32; p.tP = g->tP; p.tQ = g->tQ; p.bi = h->bi32;
+    p.lr = lr; p.reg_u = reg_u; p.reg_i = reg_i; p.reg_b = (float)reg_b; p.rho = g->rho; p.glen = g->glen;
+    p.loss = h->d_loss; p.ld = h->ld; p.rowptr = h->d_rowptr; p.col = h->d_col; p.colptr = g->d_colptr; p.cusers = g->d_cusers;
+    p.U = h->U; p.I = h->I; p.seed_lo = (uint32_t)h->cfg.seed; p.seed_hi = (uint32_t)(h->cfg.seed >> 32); p.epoch = (uint32_t)epoch_idx;
+    return LRK_OK;
+}
+
+template <int G, int V>
+static int gbpr_launch_gv(lrk_handle_s* h, const GbprParams& p) {
+    int per_sm = 0;
+    LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgd_gbpr_epoch_kernel<G, V>, 256, 0));
+    int64_t grid = (int64_t)h->sm_count * (per_sm < 1 ? 1 : per_sm);
+    const int64_t need = ((p.n + 31) / 32 + 7) / 8;
+    if (need < grid) grid = need;
+    // the factor side is frozen inside an epoch; only the item biases race.  Small matrices: keep at most n/16 samples in flight
+    const int64_t cap = (p.n / 16) / (8 * (int64_t)(32 / G));
+    if (cap < grid) grid = cap;
+    if (grid < 1) grid = 1;
+    sgd_gbpr_epoch_kernel<G, V><<<(unsigned)grid, 256, 0, h->stream>>>(p);
+    LRK_LAUNCH_CHECK(h);
+    return LRK_OK;
+}
+
+// one GBPR iteration: GBPRRecommender.java:84-168
+static int gbpr_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, double reg_b, int32_t epoch_idx, double* loss_out) {
+    GbprState* g = (GbprState*)h->gbpr;
+    LRK_REQUIRE(h, g != nullptr, "GBPR state missing: call lrk_set_train_csr first");
+    cudaStream_t st = h->stream;
+    const size_t np_ = (size_t)h->U * h->ld, nq_ = (size_t)h->I * h->ld;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &g->tP, np_))) return rc;
+    if ((rc = lrk_dev_alloc(h, &g->tQ, nq_))) return rc;
+    LRK_CUDA(h, cudaMemsetAsync(g->tP, 0, sizeof(float) * np_, st));
+    LRK_CUDA(h, cudaMemsetAsync(g->tQ, 0, sizeof(float) * nq_, st));
+    LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
+    GbprParams p;
+    gbpr_fill(h, p, lr, reg_u, reg_i, reg_b, epoch_idx);
+    LRK_CUDA(h, cudaEventRecord(h->ev0, st));
+    if (h->nnz > 0) {
+        switch (h->G * 100 + h->V) {
+            case 101: rc = gbpr_launch_gv<1, 1>(h, p); break;
+            case 201: rc = gbpr_launch_gv<2, 1>(h, p); break;
+            case 401: rc = gbpr_launch_gv<4, 1>(h, p); break;
+            case 801: rc = gbpr_launch_gv<8, 1>(h, p); break;
+            case 1601: rc = gbpr_launch_gv<16, 1>(h, p); break;
+            case 3201: rc = gbpr_launch_gv<32, 1>(h, p); break;
+            case 3202: rc = gbpr_launch_gv<32, 2>(h, p); break;
+            default: rc = lrk_fail(h, LRK_ERR_INVALID, "gbpr_epoch", "unsupported factor layout", __FILE__, __LINE__);
+        }
+        if (rc) return rc;
+        gbpr_apply_kernel<<<lrk_ceil_div((int64_t)np_, 256), 256, 0, st>>>(h->P32, g->tP, (int64_t)np_); LRK_LAUNCH_CHECK(h);
+        gbpr_apply_kernel<<<lrk_ceil_div((int64_t)nq_, 256), 256, 0, st>>>(h->Q32, g->tQ, (int64_t)nq_); LRK_LAUNCH_CHECK(h);
+    }
+    LRK_CUDA(h, cudaEventRecord(h->ev1, st));
+    LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    LRK_CUDA(h, cudaEventElapsedTime(&h->last_epoch_ms, h->ev0, h->ev1));
+    h->f64_valid = false;
+    topn_tc_invalidate(h);
+    const double loss = h->h_loss[0];                 // no 0.5 (GBPRRecommender.java:130-165)
+    if (loss_out) *loss_out = loss;
+    if (std::isnan(loss) || std::isinf(loss))
+        return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);
+    h->epochs_done++;
+    return LRK_OK;
+}
 
 extern "C" {
 
@@ -63,12 +172,12 @@ int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out) {
     *out = nullptr;
     if (cfg->num_factors < 1 || cfg->num_factors > LRK_MAX_FACTORS)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "num_factors must be in 1..256", __FILE__, __LINE__);
-    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_RANKSGD)
+    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_GBPR)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown model", __FILE__, __LINE__);
     if (cfg->update_mode < LRK_UPDATE_ATOMIC || cfg->update_mode > LRK_UPDATE_REFERENCE_ORDER)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown update_mode", __FILE__, __LINE__);
-    if (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER && (cfg->model == LRK_MODEL_BPR || cfg->model == LRK_MODEL_RANKSGD))
-        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "reference-order mode covers BiasedMF and PMF (BPR and RankSGD draw from a sequential RNG)", __FILE__, __LINE__);
+    if (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER && !(cfg->model == LRK_MODEL_BIASEDMF || cfg->model == LRK_MODEL_PMF))
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "reference-order mode covers BiasedMF and PMF (BPR, RankSGD and GBPR draw from a sequential RNG)", __FILE__, __LINE__);
     int ndev = 0;
     LRK_CUDA(nullptr, cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev)
@@ -111,6 +220,7 @@ int lrk_destroy(lrk_handle_t h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     group_units_release((GroupUnits*)h->group);
+    gbpr_release((GbprState*)h->gbpr);
     dsgd_release(h);
     topn_tc_release(h);
     exact_release((ExactSchedule*)h->exact);
@@ -209,6 +319,7 @@ int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowpt
         if ((rc = exact_build_schedule(h, &es, U, I, rowptr, col, val))) return rc;
         h->exact = es;
     }
+    if (h->cfg.model == LRK_MODEL_GBPR && (rc = gbpr_stage(h))) return rc;
     h->has_train = true;
     topn_tc_invalidate(h);
     return LRK_OK;
@@ -219,8 +330,9 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     if (h->multi) return multi_set_factors(h, P, Q, bu, bi, mu);
     LRK_REQUIRE(h, h->has_train, "call lrk_set_train_csr first (it fixes numUsers / numItems)");
     LRK_REQUIRE(h, P && Q, "P and Q are required");
-    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
-    LRK_REQUIRE(h, !biased || (bu && bi), "BiasedMF needs userBiases and itemBiases");
+    const bool biased = lrk_has_bias(h);
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_BIASEDMF || (bu && bi), "BiasedMF needs userBiases and itemBiases");
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_GBPR || bi, "GBPR needs itemBiases");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->world > 1) return dsgd_set_factors(h, P, Q, bu, bi, mu);
     cudaStream_t st = h->stream;
@@ -237,18 +349,15 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     if ((rc = lrk_dev_alloc(h, &h->bi32, (size_t)I + 4))) return rc;
     LRK_CUDA(h, cudaMemcpyAsync(h->P64, P, sizeof(double) * (size_t)U * k, cudaMemcpyHostToDevice, st));
     LRK_CUDA(h, cudaMemcpyAsync(h->Q64, Q, sizeof(double) * (size_t)I * k, cudaMemcpyHostToDevice, st));
-    if (biased) {
-        LRK_CUDA(h, cudaMemcpyAsync(h->bu64, bu, sizeof(double) * (size_t)U, cudaMemcpyHostToDevice, st));
-        LRK_CUDA(h, cudaMemcpyAsync(h->bi64, bi, sizeof(double) * (size_t)I, cudaMemcpyHostToDevice, st));
-    } else {
-        LRK_CUDA(h, cudaMemsetAsync(h->bu64, 0, sizeof(double) * (size_t)U, st));
-        LRK_CUDA(h, cudaMemsetAsync(h->bi64, 0, sizeof(double) * (size_t)I, st));
-    }
+    if (biased && bu) LRK_CUDA(h, cudaMemcpyAsync(h->bu64, bu, sizeof(double) * (size_t)U, cudaMemcpyHostToDevice, st));
+    else LRK_CUDA(h, cudaMemsetAsync(h->bu64, 0, sizeof(double) * (size_t)U, st));
+    if (biased) LRK_CUDA(h, cudaMemcpyAsync(h->bi64, bi, sizeof(double) * (size_t)I, cudaMemcpyHostToDevice, st));
+    else LRK_CUDA(h, cudaMemsetAsync(h->bi64, 0, sizeof(double) * (size_t)I, st));
     f64_to_f32_rows_kernel<<<lrk_ceil_div(U * ld, 256), 256, 0, st>>>(h->P64, h->P32, U, k, ld); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I * ld, 256), 256, 0, st>>>(h->Q64, h->Q32, I, k, ld); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu64, h->bu32, U, 1, 1); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi64, h->bi32, I, 1, 1); LRK_LAUNCH_CHECK(h);
-    if (h->cfg.model != LRK_MODEL_BPR && (rc = refresh_user_norm2(h, true))) return rc;
+    if (h->cfg.model != LRK_MODEL_BPR && h->cfg.model != LRK_MODEL_GBPR && (rc = refresh_user_norm2(h, true))) return rc;
     if (h->h_pnorm2) { h->pnorm2_prev = 0.f; h->pnorm2_host = *h->h_pnorm2; }
     LRK_CUDA(h, cudaStreamSynchronize(st));   // host buffers may be reused by the caller on return
     h->mu = mu;
@@ -266,7 +375,7 @@ static int refresh_masters(lrk_handle_s* h) {
     const int64_t U = h->U, I = h->I;
     f32_to_f64_rows_kernel<<<lrk_ceil_div(U * h->k, 256), 256, 0, st>>>(h->P32, h->P64, U, h->k, h->ld); LRK_LAUNCH_CHECK(h);
     f32_to_f64_rows_kernel<<<lrk_ceil_div(I * h->k, 256), 256, 0, st>>>(h->Q32, h->Q64, I, h->k, h->ld); LRK_LAUNCH_CHECK(h);
-    if (h->cfg.model == LRK_MODEL_BIASEDMF) {
+    if (lrk_has_bias(h)) {
         f32_to_f64_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu32, h->bu64, U, 1, 1); LRK_LAUNCH_CHECK(h);
         f32_to_f64_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi32, h->bi64, I, 1, 1); LRK_LAUNCH_CHECK(h);
     }
@@ -318,6 +427,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
     LRK_REQUIRE(h, h->has_train && h->has_factors, "set the train CSR and the factors before training");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->world > 1) return dsgd_epoch(h, lr, reg_u, reg_i, reg_b, epoch_idx, loss_out);
+    if (h->cfg.model == LRK_MODEL_GBPR) return gbpr_epoch(h, lr, reg_u, reg_i, reg_b, epoch_idx, loss_out);
     cudaStream_t st = h->stream;
     if (h->cfg.update_mode == LRK_UPDATE_REFERENCE_ORDER) {
         // fp64 masters are the working set in this mode
@@ -407,6 +517,23 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
     h->epochs_done++;
     if (h->conc_div > 1 && ++h->good_epochs >= 8) { h->conc_div /= 2; h->good_epochs = 0; }
     return LRK_OK;
+}
+
+int lrk_set_param(lrk_handle_t h, const char* name, double value) {
+    LRK_REQUIRE(h, h != nullptr && name != nullptr, "NULL argument");
+    LRK_NOT_MULTI(h, "lrk_set_param");
+    if (!strcmp(name, "gbpr.rho") || !strcmp(name, "gbpr.gsize")) {
+        LRK_REQUIRE(h, h->cfg.model == LRK_MODEL_GBPR, "gbpr.* parameters need a GBPR handle");
+        GbprState* g = (GbprState*)h->gbpr;
+        if (!g) { g = new GbprState(); h->gbpr = g; }
+        if (!strcmp(name, "gbpr.rho")) g->rho = (float)value;
+        else {
+            LRK_REQUIRE(h, value >= 1.0 && value <= (double)LRK_GBPR_MAX_GROUP, "rec.gpbr.gsize must be in 1..8");
+            g->glen = (int)value;
+        }
+        return LRK_OK;
+    }
+    return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_param", "unknown parameter name", __FILE__, __LINE__);
 }
 
 int lrk_sgd_epochs(lrk_handle_t h, int32_t n_epochs, float lr, float decay, float max_lr, float reg_u, float reg_i, double reg_b,
@@ -499,6 +626,22 @@ int lrk_bpr_peek_samples(lrk_handle_t h, int32_t epoch_idx, int64_t first, int64
     fill_sgd_params(h, sp, 0.f, 0.f, 0.f, 0.0, epoch_idx);
     int32_t* d_out = nullptr;
     LRK_CUDA(h, cudaMalloc((void**)&d_out, sizeof(int32_t) * 3 * (size_t)n));
+    if (h->cfg.model == LRK_MODEL_GBPR) {
+        // 11 ints per sample: {u, i, j, group[8] padded with -1}
+        cudaFree(d_out);
+        LRK_REQUIRE(h, h->gbpr != nullptr, "GBPR state missing");
+        LRK_CUDA(h, cudaMalloc((void**)&d_out, sizeof(int32_t) * (3 + LRK_GBPR_MAX_GROUP) * (size_t)n));
+        GbprParams gp;
+        gbpr_fill(h, gp, 0.f, 0.f, 0.f, 0.0, epoch_idx);
+        gbpr_peek_kernel<<<lrk_ceil_div(n, 256), 256, 0, h->stream>>>(gp, first, n, d_out);
+        h->launches++;
+        cudaError_t ge = cudaGetLastError();
+        if (ge == cudaSuccess) ge = cudaMemcpyAsync(out, d_out, sizeof(int32_t) * (3 + LRK_GBPR_MAX_GROUP) * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+        if (ge == cudaSuccess) ge = cudaStreamSynchronize(h->stream);
+        cudaFree(d_out);
+        LRK_CUDA(h, ge);
+        return LRK_OK;
+    }
     if (h->cfg.model == LRK_MODEL_RANKSGD) {
         if (first + n > h->nnz) { cudaFree(d_out); return lrk_fail(h, LRK_ERR_INVALID, "lrk_bpr_peek_samples", "RankSGD has one sample per train entry: first + n exceeds nnz", __FILE__, __LINE__); }
         ranksgd_peek_kernel<<<lrk_ceil_div(n, 256), 256, 0, h->stream>>>(sp, first, n, d_out);
@@ -535,7 +678,7 @@ int lrk_predict_pairs(lrk_handle_t h, const int32_t* users, const int32_t* items
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, items, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         predict_pairs_kernel<<<lrk_ceil_div(n, 128), 128, 0, st>>>(h->P64, h->Q64, h->bu64, h->bi64, h->mu,
-                                                                   h->cfg.model == LRK_MODEL_BIASEDMF, h->k, d_u, d_i, n, d_o);
+                                                                   lrk_has_bias(h), h->k, d_u, d_i, n, d_o);
         h->launches++;
         e = cudaGetLastError();
     }
@@ -572,7 +715,7 @@ int lrk_eval_rating(lrk_handle_t h, int32_t U, const int64_t* t_rowptr, const in
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_c, t_col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, t_val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-        eval_rating_kernel<<<nb, 256, 0, st>>>(h->P64, h->Q64, h->bu64, h->bi64, h->mu, h->cfg.model == LRK_MODEL_BIASEDMF,
+        eval_rating_kernel<<<nb, 256, 0, st>>>(h->P64, h->Q64, h->bu64, h->bi64, h->mu, lrk_has_bias(h),
                                                h->k, U, d_rp, d_c, d_v, min_rate, max_rate, d_p, d_part, d_part + nb);
         eval_rating_final_kernel<<<1, 32, 0, st>>>(d_part, d_part + nb, nb, nnz, d_part + 2 * (size_t)nb);
         h->launches += 2;
@@ -728,7 +871,7 @@ int lrk_comm_init(lrk_handle_t h, int32_t rank, int32_t world, const uint8_t uni
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
     LRK_NOT_MULTI(h, "lrk_comm_init");
     LRK_REQUIRE(h, h->cfg.update_mode != LRK_UPDATE_REFERENCE_ORDER, "reference-order mode is single-GPU");
-    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_RANKSGD, "RankSGD is single-GPU in this build");
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_RANKSGD && h->cfg.model != LRK_MODEL_GBPR, "RankSGD and GBPR are single-GPU in this build");
     return dsgd_comm_init(h, rank, world, unique_id);
 }
 
@@ -738,8 +881,8 @@ int lrk_create_multi(const lrk_config_t* cfg, const int32_t* devices, int32_t n_
     if (n_devices < 1 || n_devices > 8) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "1 to 8 devices", __FILE__, __LINE__);
     for (int a = 0; a < n_devices; ++a) for (int b = a + 1; b < n_devices; ++b)
         if (devices[a] == devices[b]) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "a device is listed twice", __FILE__, __LINE__);
-    if (n_devices > 1 && (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER || cfg->model == LRK_MODEL_RANKSGD))
-        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "reference-order mode and RankSGD are single-GPU", __FILE__, __LINE__);
+    if (n_devices > 1 && (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER || cfg->model == LRK_MODEL_RANKSGD || cfg->model == LRK_MODEL_GBPR))
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "reference-order mode, RankSGD and GBPR are single-GPU", __FILE__, __LINE__);
     lrk_handle_s* h = new (std::nothrow) lrk_handle_s();
     MultiState* ms = new (std::nothrow) MultiState();
     if (!h || !ms) { delete h; delete ms; return lrk_fail(nullptr, LRK_ERR_NOMEM, "lrk_create_multi", "host allocation failed", __FILE__, __LINE__); }
@@ -852,7 +995,7 @@ static int multi_topn(lrk_handle_s* h, const int32_t* users, int32_t nq, int32_t
     if (users) for (int32_t c = 0; c < nq; ++c) LRK_REQUIRE(h, users[c] >= 0 && users[c] < ms->U, "user index out of range");
     else LRK_REQUIRE(h, nq <= ms->U, "nq exceeds numUsers");
     const int k = h->k;
-    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    const bool biased = lrk_has_bias(h);
     int rc;
     if (!ms->scorer_factors) {
         ms->P.resize((size_t)ms->U * k); ms->Q.resize((size_t)ms->I * k);

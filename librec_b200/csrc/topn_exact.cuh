@@ -263,7 +263,7 @@ static int topn_exact_launch(lrk_handle_s* h, const int32_t* d_users, int32_t nq
     LRK_CUDA(h, cudaFuncSetAttribute(topn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = lrk_ceil_div(nq, TOPN_UPB);
     topn_exact_kernel<<<grid, TOPN_WARPS * 32, smem, h->stream>>>(
-        h->P64, h->Q64, h->bu64, h->bi64, h->mu, h->cfg.model == LRK_MODEL_BIASEDMF, h->k, h->I,
+        h->P64, h->Q64, h->bu64, h->bi64, h->mu, lrk_has_bias(h), h->k, h->I,
         h->d_rowptr, h->d_col, exclude_train, d_users, nq, topn, d_items, d_scores, d_counts);
     LRK_LAUNCH_CHECK(h);
     return LRK_OK;
@@ -436,7 +436,7 @@ static int topn_exact_parallel_launch(lrk_handle_s* h, const int32_t* d_users, i
         const size_t smem = sizeof(double) * ((size_t)h->k + (size_t)T * TOPN_PAR_THREADS + 8) + sizeof(int32_t) * ((size_t)T * TOPN_PAR_THREADS + 16);
         if ((e = cudaFuncSetAttribute(topn_exact_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) break;
         topn_exact_parts_kernel<<<nq * n_parts, TOPN_PAR_THREADS, smem, st>>>(
-            h->P64, h->Q64, h->bu64, h->bi64, h->mu, h->cfg.model == LRK_MODEL_BIASEDMF, h->k, h->I, h->d_rowptr, h->d_col,
+            h->P64, h->Q64, h->bu64, h->bi64, h->mu, lrk_has_bias(h), h->k, h->I, h->d_rowptr, h->d_col,
             exclude_train, d_users, n_parts, part_items, T, pi, psc, pc);
         h->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) break;

@@ -76,7 +76,7 @@ static inline void topn_tc_invalidate(lrk_handle_s* h) {
     if (h->tc) ((TcState*)h->tc)->valid = false;
 }
 static inline int tc_kp(lrk_handle_s* h) {
-    const int kaug = h->k + (h->cfg.model == LRK_MODEL_BIASEDMF ? 2 : 0);
+    const int kaug = h->k + (lrk_has_bias(h) ? 2 : 0);
     return ((kaug + TC_KB - 1) / TC_KB) * TC_KB;
 }
 static inline bool topn_tc_profitable(lrk_handle_s* h, int32_t nq, int topn) {
@@ -769,7 +769,7 @@ static int tc_pass(lrk_handle_s* h, TcState* s, const int32_t* d_users, int32_t 
                    int32_t* rs_slots, int32_t* rs_users, float* rs_tau0, int* rs_count,
                    int32_t* ex_slots, int32_t* ex_users, int* ex_count, bool first_pass) {
     cudaStream_t st = h->stream;
-    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    const bool biased = lrk_has_bias(h);
     const int Kp = s->Kp;
     const int num_kb = Kp / TC_KB;
     // ---- work decomposition
@@ -843,7 +843,7 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
                        int32_t* d_items, double* d_scores, int32_t* d_counts) {
     TcState* s = tc_state(h);
     cudaStream_t st = h->stream;
-    const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
+    const bool biased = lrk_has_bias(h);
     const int Kp = tc_kp(h);
     const int num_kb = Kp / TC_KB;
     if (num_kb > 2 || topn > 16)
