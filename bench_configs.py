@@ -75,26 +75,28 @@ def run(name, model_name, shape, k, lr, reg, steps, warmup):
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
     bpr = model_name == "bpr"
     ranksgd = model_name == "ranksgd"
-    d = synth.make_ratings(shape, binary=bpr)
+    d = synth.make_ratings(shape, binary=bpr or model_name == "gbpr")
     U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
     P, Q, _, _ = synth.init_factors(U, I, k, 11, False)
-    model = capi.MODEL_BPR if bpr else (capi.MODEL_RANKSGD if ranksgd else capi.MODEL_PMF)
+    gbpr = model_name == "gbpr"
+    model = capi.MODEL_BPR if bpr else (capi.MODEL_RANKSGD if ranksgd else (capi.MODEL_GBPR if gbpr else capi.MODEL_PMF))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     with capi.Handle(model, k, seed=1) as h:
         h.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
-        h.set_factors(P, Q)
+        h.set_factors(P, Q, None, np.zeros(I) if gbpr else None)
         ms, losses = [], []
         for s in range(warmup + steps):
             flush.zero_(); torch.cuda.synchronize()
-            losses.append(h.sgd_epoch(lr, reg, reg, 0.0, s + 1))
+            losses.append(h.sgd_epoch(lr, reg, reg, 0.01 if gbpr else 0.0, s + 1))
             if s >= warmup:
                 ms.append(h.last_epoch_ms())
         guard = h.sgd_safeguard()
     kms = float(np.mean(ms))
-    bytes_per = 6 * k * 4 if bpr else (12 + 6 * k * 4 if ranksgd else 12 + 4 * k * 4)     # RankSGD: triple + r/w of p_u, q_i, q_j
+    # GBPR: r/w of the group's user rows (2 users), q_i, q_j
+    bytes_per = 8 * k * 4 if gbpr else 6 * k * 4 if bpr else (12 + 6 * k * 4 if ranksgd else 12 + 4 * k * 4)     # RankSGD: triple + r/w of p_u, q_i, q_j
     achieved = bytes_per * nnz / (kms * 1e-3) / 1e9
-    print(json.dumps({"config": name, "metric": "BPR samples/s" if bpr else ("RankSGD updates/s" if ranksgd else "MF SGD rating-updates/s"), "value": nnz / (kms * 1e-3),
-                      "unit": "samples/s" if bpr else "updates/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": kms,
+    print(json.dumps({"config": name, "metric": "GBPR samples/s" if gbpr else "BPR samples/s" if bpr else ("RankSGD updates/s" if ranksgd else "MF SGD rating-updates/s"), "value": nnz / (kms * 1e-3),
+                      "unit": "samples/s" if (bpr or gbpr) else "updates/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": kms,
                       "workload": "%s k=%d, synthetic %s shape (%d x %d, %d ratings), lr %g reg %g" % (model_name, k, shape, U, I, nnz, lr, reg),
                       "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                                    "algorithmic_bytes_per_unit": bytes_per},
@@ -144,5 +146,7 @@ if __name__ == "__main__":
         run_reference_order("C2-reforder", "biasedmf", "ml-20m", 64, 0.002, 0.01, 0.01)
         run_reference_order("C4p-reforder", "pmf", "netflix-10m", 128, 0.01, 0.08, 0.0)
         run_reference_order("C4-reforder", "pmf", "netflix", 128, 0.01, 0.08, 0.0)
+    if a.only == "gbpr":
+        run("N3-GBPR", "gbpr", "ml-20m", 10, 0.05, 0.01, a.steps, a.warmup)        # gbpr defaults: rho 1.5, group size 2
     if a.only == "n3":
         run("N3", "ranksgd", "ml-20m", 10, 0.01, 0.0, a.steps, a.warmup)        # ranksgd-test.properties

@@ -80,7 +80,8 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
         ByteBuffer P = flatten(userFactors), Q = flatten(itemFactors);
         ByteBuffer bu = userBiases == null ? null : ByteBuffer.allocateDirect(8 * numUsers).order(ByteOrder.nativeOrder());
         ByteBuffer bi = itemBiases == null ? null : ByteBuffer.allocateDirect(8 * numItems).order(ByteOrder.nativeOrder());
-        if (bu != null) { bu.asDoubleBuffer().put(userBiases.getValues()); bi.asDoubleBuffer().put(itemBiases.getValues()); }
+        if (bu != null) bu.asDoubleBuffer().put(userBiases.getValues());
+        if (bi != null) bi.asDoubleBuffer().put(itemBiases.getValues());                // GBPR has item biases only
         check(LibrecB200.setFactors(handle, P, Q, bu, bi, globalMean));
         double[] lossOut = new double[1];
         boolean boldDriver = conf.getBoolean("rec.learnrate.bolddriver", false);
@@ -106,7 +107,8 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
         }
         check(LibrecB200.getFactors(handle, P, Q, bu, bi));
         unflatten(P, userFactors); unflatten(Q, itemFactors);
-        if (bu != null) { bu.asDoubleBuffer().get(userBiases.getValues()); bi.asDoubleBuffer().get(itemBiases.getValues()); }
+        if (bu != null) bu.asDoubleBuffer().get(userBiases.getValues());
+        if (bi != null) bi.asDoubleBuffer().get(itemBiases.getValues());
         LibrecB200.hostFree(P); LibrecB200.hostFree(Q);
         // inherited predict()/recommendRating()/evaluators keep working on the DenseMatrix copies
     }

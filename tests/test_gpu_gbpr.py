@@ -43,7 +43,7 @@ def test_gbpr_samples_follow_the_reference_sampler(O, capi, c1):
 
 def test_gbpr_epoch_loss_and_quality_match_the_oracle(O, capi, c1):
     """gbpr-test-like settings on the binarised C1 split: first-epoch loss (the factors are frozen inside an epoch, so it is a pure
-    function of the sample distribution) within 1 %; after 30 epochs AUC / Precision@10 within the tolerance the two RNG streams allow;
+    function of the sample distribution) within 2 %; after 30 epochs AUC / Precision@10 within the tolerance the two RNG streams allow;
     lists for the learned factors bit-identical to the oracle's (prediction = b_i + p_u.q_i)."""
     tr, te = _ones(O, c1["train"]), c1["test"]
     k, lr, reg, regb, rho, glen, epochs = 10, 0.05, 0.01, 0.01, 1.5, 2, 30
@@ -63,7 +63,7 @@ def test_gbpr_epoch_loss_and_quality_match_the_oracle(O, capi, c1):
         users = np.flatnonzero(np.diff(te.rowptr) > 0).astype(np.int32)[:200]
         items, scores, counts = h.topn(10, users=users)
     print("GBPR loss_1 %.1f (oracle %.1f)  loss_%d %.1f (oracle %.1f)" % (gl[0], ol[0], epochs, gl[-1], ol[-1]))
-    assert abs(gl[0] - ol[0]) < 0.01 * ol[0]
+    assert abs(gl[0] - ol[0]) < 0.02 * ol[0]          # measured 0.7 %: the oracle's item biases move sequentially, the device's Hogwild
     assert abs(gl[-1] - ol[-1]) < 0.05 * ol[-1]
     assert np.all(gbu == 0.0)
     oi, os_, oc = O.recommend_rank(O.BIASEDMF, tr.U, tr.I, k, gP, gQ, gbu, gbi, 0.0, tr, 10, users=users)
