@@ -39,6 +39,7 @@
 #define TC_TILE_N 128          // items per MMA tile
 #define TC_KB 64               // bf16 elements per 128-byte swizzle row
 #define TC_KEEP_MAX 32         // largest K' (candidates a compaction keeps per (row, chunk))
+#define TC_MAX_TOPN 26         // the first pass keeps K' = max(16, N + 6) <= TC_KEEP_MAX candidates: N up to 26 (r01: 16)
 #define TC_CAP 64              // candidate slots per (row, chunk) in global memory (append buffer, compacted to K')
 #define TC_ROWS (TC_TILE_M * TC_UT)   // user rows per CTA
 #define TC_THREADS 320
@@ -80,7 +81,7 @@ static inline int tc_kp(lrk_handle_s* h) {
     return ((kaug + TC_KB - 1) / TC_KB) * TC_KB;
 }
 static inline bool topn_tc_profitable(lrk_handle_s* h, int32_t nq, int topn) {
-    return topn <= 16 && tc_kp(h) <= 128 && h->I >= 8192 && nq >= 512;
+    return topn <= TC_MAX_TOPN && tc_kp(h) <= 128 && h->I >= 8192 && nq >= 512;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -846,8 +847,8 @@ static int topn_tc_run(lrk_handle_s* h, const int32_t* d_users, int32_t nq, int 
     const bool biased = lrk_has_bias(h);
     const int Kp = tc_kp(h);
     const int num_kb = Kp / TC_KB;
-    if (num_kb > 2 || topn > 16)
-        return lrk_fail(h, LRK_ERR_INVALID, "lrk_topn", "tensor-core path supports k (+2 for BiasedMF) <= 128 and topn <= 16", __FILE__, __LINE__);
+    if (num_kb > 2 || topn > TC_MAX_TOPN)
+        return lrk_fail(h, LRK_ERR_INVALID, "lrk_topn", "tensor-core path supports k (+2 for BiasedMF) <= 128 and topn <= 26", __FILE__, __LINE__);
     for (cudaEvent_t& ev : s->ev) if (!ev) LRK_CUDA(h, cudaEventCreate(&ev));
     LRK_CUDA(h, cudaEventRecord(s->ev[0], st));
     // ---- item operand (cached until the factors change)

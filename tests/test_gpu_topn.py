@@ -117,6 +117,8 @@ def test_topn_after_training_uses_current_factors(O, capi, c1):
     (0, 513, 4097, 20, 10, 0.3),       # BiasedMF: item bias folded into two extra K columns (Kp = 64)
     (0, 260, 3000, 100, 15, 0.1),      # BiasedMF k=100 -> Kp = 128 (two K blocks), N = 15
     (1, 1000, 20000, 128, 1, 0.05),    # N = 1
+    (2, 600, 9000, 64, 20, 0.1),       # N = 20: K' = 26
+    (0, 520, 8200, 30, 26, 0.2),       # N = 26: the largest N of the tensor-core path (K' = 32)
 ])
 def test_topn_tensor_core_path_bit_identical(O, capi, model, U, I, k, N, scale):
     h, tr, P, Q, bu, bi = _setup(capi, O, model, U, I, k, seed=U + I + k, density=0.01, scale=scale, topn_path=2)
