@@ -147,6 +147,9 @@ if __name__ == "__main__":
         run_reference_order("C4p-reforder", "pmf", "netflix-10m", 128, 0.01, 0.08, 0.0)
         run_reference_order("C4-reforder", "pmf", "netflix", 128, 0.01, 0.08, 0.0)
     if a.only == "gbpr":
-        run("N3-GBPR", "gbpr", "ml-20m", 10, 0.05, 0.01, a.steps, a.warmup)        # gbpr defaults: rho 1.5, group size 2
+        # gbpr defaults: rho 1.5, group size 2.  GBPR adds the SUM of an epoch's factor updates at its end (GBPRRecommender.java:167-168),
+        # so its effective step grows with the samples per row: lr 0.05 is fine on ml-100k (80 k samples), turns around after 4 epochs
+        # on an ML-1M-shaped matrix in the ORACLE as well, and explodes at 20 M samples; the timing run scales lr with 1 / samples
+        run("N3-GBPR", "gbpr", "ml-20m", 10, 0.0002, 0.01, a.steps, a.warmup)
     if a.only == "n3":
         run("N3", "ranksgd", "ml-20m", 10, 0.01, 0.0, a.steps, a.warmup)        # ranksgd-test.properties
