@@ -409,13 +409,15 @@ static void fill_sgd_params(const lrk_handle_s* h, SgdParams& sp, float lr, floa
     sp.mu = (float)h->mu; sp.lr = lr; sp.reg_u = reg_u; sp.reg_i = reg_i; sp.reg_b = (float)reg_b;
     sp.loss = h->d_loss; sp.ld = h->ld;
     sp.hot_share = lrk_is_rating_model(h) ? h->hot_share : 0.0;
-    sp.item_deg = lrk_is_rating_model(h) ? h->d_item_deg : nullptr;
+    sp.item_deg = (lrk_is_rating_model(h) || h->cfg.model == LRK_MODEL_RANKSGD) ? h->d_item_deg : nullptr;
     sp.item_cum = h->cfg.model == LRK_MODEL_RANKSGD ? h->d_item_cum : nullptr;
     // RankSGD: squared loss without regularisation -- B concurrent updates of one item act like ONE step lr * B * |p_u|^2
     // where the sequential walk contracts by exp(-lr * B * |p_u|^2).  Popular items are hit as positives and, by
     // construction of the sampler, as negatives (2 x share), and the two only agree while that product is small: the grid
     // is capped at lr * 2 share * |p|^2 * (ratings in flight) <= 1/4 (sgd_grid_for's hot-item cap).  With <= 1 instead, C1
     // reached the oracle's loss but Precision@10 0.140 against 0.176 (sequential) / 0.214 (sequential, shuffled order).
+    // r02: the RankSGD kernel scales its item-side steps for the samples in flight (sgd.cuh), so the cap is only the fallback of
+    // LRK_SGD_NODAMP=1 (r01: it left a handful of CTAs on the ML-20M shape, 0.48 G updates/s)
     if (h->cfg.model == LRK_MODEL_RANKSGD) sp.hot_share = 8.0 * h->hot_share * (double)std::max(1.f, h->pnorm2_host);
     sp.rowptr = h->d_rowptr; sp.col = h->d_col; sp.U = h->U; sp.I = h->I;
     sp.seed_lo = (uint32_t)h->cfg.seed; sp.seed_hi = (uint32_t)(h->cfg.seed >> 32); sp.epoch = (uint32_t)epoch_idx;
@@ -504,7 +506,9 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
         if (track_norm) {
             if ((rc = refresh_user_norm2(h, true))) return rc;          // the restored factors' norm, visible to the host now
             h->pnorm2_host = *h->h_pnorm2;
-            if (h->cfg.model == LRK_MODEL_RANKSGD) sp.hot_share = 8.0 * h->hot_share * (double)std::max(1.f, h->pnorm2_host);
+            // r02: the RankSGD kernel scales its item-side steps for the samples in flight (sgd.cuh), so the cap is only the fallback of
+    // LRK_SGD_NODAMP=1 (r01: it left a handful of CTAs on the ML-20M shape, 0.48 G updates/s)
+    if (h->cfg.model == LRK_MODEL_RANKSGD) sp.hot_share = 8.0 * h->hot_share * (double)std::max(1.f, h->pnorm2_host);
         }
     }
     h->f64_valid = false;

@@ -431,14 +431,32 @@ __global__ void __launch_bounds__(256) sgd_ranksgd_epoch_kernel(SgdParams p) {
                 part += dot4(pc[v], df[v]);
             }
             const float err = group_sum<G>(part) - rc;      // (posPredict - negPredict) - (posRating - 0)
+            // staleness-aware step of the item side (r02; as in the rating kernel): about 2 * deg * inflight_frac samples touching the
+            // same item row are in flight at once (an item is drawn as positive and, by popularity, as negative equally often), the
+            // squared loss has curvature |p_u|^2 along p_u, and B concurrent steps act like one step of size lr * B * |p_u|^2 where the
+            // reference's sequential walk contracts by exp(-lr * B * |p_u|^2): scale the item deltas by (1 - exp(-x)) / x
+            float damp_i = 1.f, damp_j = 1.f;
+            if (p.item_deg) {
+                float pp = 0.f;
+#pragma unroll
+                for (int v = 0; v < V; ++v) pp += dot4(pc[v], pc[v]);
+                pp = group_sum<G>(pp);
+                if (uc >= 0) {
+                    const float c = 2.f * lr * pp * p.inflight_frac;
+                    const float xi = c * (float)__ldg(p.item_deg + ic), xj = c * (float)__ldg(p.item_deg + jc);
+                    if (xi > 1e-3f) damp_i = (1.f - __expf(-xi)) / xi;
+                    if (xj > 1e-3f) damp_j = (1.f - __expf(-xj)) / xj;
+                }
+            }
             if (uc >= 0) {
                 const float sgd = lr * err;
+                const float si_ = sgd * damp_i, sj_ = sgd * damp_j;
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const float4 a = pc[v], d = df[v];
                     const float4 dp = make_float4(-sgd * d.x, -sgd * d.y, -sgd * d.z, -sgd * d.w);
-                    const float4 di = make_float4(-sgd * a.x, -sgd * a.y, -sgd * a.z, -sgd * a.w);
-                    const float4 dj = make_float4(sgd * a.x, sgd * a.y, sgd * a.z, sgd * a.w);
+                    const float4 di = make_float4(-si_ * a.x, -si_ * a.y, -si_ * a.z, -si_ * a.w);
+                    const float4 dj = make_float4(sj_ * a.x, sj_ * a.y, sj_ * a.z, sj_ * a.w);
                     apply4<ATOMIC>(p.P + (int64_t)uc * p.ld + (v * G + sub) * 4, a, dp);
                     apply4<ATOMIC>(p.Q + (int64_t)ic * p.ld + (v * G + sub) * 4, qic[v], di);
                     apply4<ATOMIC>(p.Q + (int64_t)jc * p.ld + (v * G + sub) * 4, qjc[v], dj);
