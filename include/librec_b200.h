@@ -59,7 +59,13 @@ typedef enum {
     /* gbpr -> recommender/cf/ranking/GBPRRecommender.java:82-172: group-preference BPR.  Item biases only
      * (lrk_set_factors: bu may be NULL, bi is required); rec.gpbr.rho / rec.gpbr.gsize through lrk_set_param; single GPU;
      * lrk_sgd_epoch's reg_b is rec.bias.regularization */
-    LRK_MODEL_GBPR = 4
+    LRK_MODEL_GBPR = 4,
+    /* svdpp -> recommender/cf/rating/SVDPlusPlusRecommender.java:62-123: BiasedMF plus the implicit-feedback
+     * factors impItemFactors (I x k) -- handed over / read back with lrk_set_matrix / lrk_get_matrix("svdpp.y"),
+     * rec.impItem.regularization through lrk_set_param("svdpp.reg_imp").  Training only, single GPU: its predict() needs the
+     * per-user sum of the implicit factors, so the scoring entry points return LRK_ERR_INVALID for this model (the shim keeps
+     * the reference's predict() on the matrices it reads back). */
+    LRK_MODEL_SVDPP = 5
 } lrk_model;
 
 /* how concurrent updates to one factor row are combined */
@@ -130,8 +136,14 @@ LRK_API int lrk_get_factors(lrk_handle_t h, double* P, double* Q, double* bu, do
 /* model hyper-parameters that are not arguments of lrk_sgd_epoch (read by the reference in setup()):
  *   "gbpr.rho"   rec.gpbr.rho   (float, default 1.5; GBPRRecommender.java:71)
  *   "gbpr.gsize" rec.gpbr.gsize (int 1..8, default 2; GBPRRecommender.java:72)
+ *   "svdpp.reg_imp" rec.impItem.regularization (default 0.015; SVDPlusPlusRecommender.java:52)
  * Unknown names fail with LRK_ERR_INVALID. */
 LRK_API int lrk_set_param(lrk_handle_t h, const char* name, double value);
+
+/* model matrices beyond P / Q / biases, row-major doubles like lrk_set_factors (call after it):
+ *   "svdpp.y"  impItemFactors, numItems x numFactors (SVDPlusPlusRecommender.java:55-56) */
+LRK_API int lrk_set_matrix(lrk_handle_t h, const char* name, const double* values);
+LRK_API int lrk_get_matrix(lrk_handle_t h, const char* name, double* values);
 
 /* ---- training ----------------------------------------------------------------------- */
 /* replaces ONE iteration of trainModel():

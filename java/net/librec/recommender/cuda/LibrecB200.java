@@ -8,7 +8,7 @@ import java.nio.ByteBuffer;
 final class LibrecB200 {
     static { System.loadLibrary("librec_b200_jni"); }
 
-    static final int MODEL_BIASEDMF = 0, MODEL_PMF = 1, MODEL_BPR = 2, MODEL_RANKSGD = 3, MODEL_GBPR = 4;
+    static final int MODEL_BIASEDMF = 0, MODEL_PMF = 1, MODEL_BPR = 2, MODEL_RANKSGD = 3, MODEL_GBPR = 4, MODEL_SVDPP = 5;
     static final int UPDATE_ATOMIC = 0, UPDATE_HOGWILD = 1, UPDATE_REFERENCE_ORDER = 2;
     static final int ERR_DIVERGED = -5;
 
@@ -30,6 +30,8 @@ final class LibrecB200 {
     static native int getFactors(long h, ByteBuffer P, ByteBuffer Q, ByteBuffer bu, ByteBuffer bi);
     static native int stageStats(long h, long[] out4);
     static native int setParam(long h, byte[] nameUtf8, double value);      // "gbpr.rho", "gbpr.gsize"
+    static native int setMatrix(long h, byte[] nameUtf8, ByteBuffer values);   // "svdpp.y"
+    static native int getMatrix(long h, byte[] nameUtf8, ByteBuffer values);
     // training
     static native int sgdEpoch(long h, float lr, float regU, float regI, double regB, int epochIdx, double[] lossOut);
     static native int sgdEpochs(long h, int nEpochs, float lr, float decay, float maxLr, float regU, float regI, double regB,

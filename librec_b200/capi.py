@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _build
 
-MODEL_BIASEDMF, MODEL_PMF, MODEL_BPR, MODEL_RANKSGD, MODEL_GBPR = 0, 1, 2, 3, 4
+MODEL_BIASEDMF, MODEL_PMF, MODEL_BPR, MODEL_RANKSGD, MODEL_GBPR, MODEL_SVDPP = 0, 1, 2, 3, 4, 5
 UPDATE_ATOMIC, UPDATE_HOGWILD, UPDATE_REFERENCE_ORDER = 0, 1, 2
 OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NOMEM, ERR_DIVERGED = 0, -1, -2, -3, -4, -5
 
@@ -50,6 +50,8 @@ SIGNATURES = {
     "lrk_set_factors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "lrk_get_factors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lrk_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "lrk_set_matrix": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
+    "lrk_get_matrix": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
     "lrk_sgd_epoch": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_double, C.c_int32, C.POINTER(C.c_double)]),
     "lrk_sgd_epochs": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double, C.c_int32,
                                  C.c_void_p]),
@@ -163,7 +165,7 @@ class Handle:
     def get_factors(self):
         P = np.empty((self.U, self.k), np.float64)
         Q = np.empty((self.I, self.k), np.float64)
-        biased = self.model in (MODEL_BIASEDMF, MODEL_GBPR)
+        biased = self.model in (MODEL_BIASEDMF, MODEL_GBPR, MODEL_SVDPP)
         bu = np.empty(self.U, np.float64) if biased else None
         bi = np.empty(self.I, np.float64) if biased else None
         _check(load().lrk_get_factors(self._h, _ptr(P), _ptr(Q), _ptr(bu), _ptr(bi)), self._h)
@@ -171,6 +173,15 @@ class Handle:
 
     def set_param(self, name, value):
         _check(load().lrk_set_param(self._h, name.encode(), float(value)), self._h)
+
+    def set_matrix(self, name, values):
+        values = np.ascontiguousarray(values, np.float64)
+        _check(load().lrk_set_matrix(self._h, name.encode(), _ptr(values)), self._h)
+
+    def get_matrix(self, name, shape):
+        out = np.empty(shape, np.float64)
+        _check(load().lrk_get_matrix(self._h, name.encode(), _ptr(out)), self._h)
+        return out
 
     # -- training
     def sgd_epoch(self, lr, reg_u, reg_i, reg_b=0.0, epoch_idx=1):

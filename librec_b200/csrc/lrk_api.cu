@@ -7,6 +7,7 @@
 #include "sgd_group.cuh"
 #include "sgd_exact.cuh"
 #include "sgd_gbpr.cuh"
+#include "sgd_svdpp.cuh"
 #include <chrono>
 #include "topn_exact.cuh"
 #include "topn_tc.cuh"
@@ -136,6 +137,93 @@ static int gbpr_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doubl
     return LRK_OK;
 }
 
+// SVD++: train values in CSR order + users by descending degree
+static int svdpp_stage(lrk_handle_s* h, const double* h_val) {
+    cudaStream_t st = h->stream;
+    SvdppState* g = (SvdppState*)h->svdpp;
+    if (!g) { g = new SvdppState(); h->svdpp = g; }
+    const int64_t nnz = h->nnz;
+    const int32_t U = h->U;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &g->d_cval, (size_t)nnz))) return rc;
+    if ((rc = lrk_dev_alloc(h, &g->d_uorder, (size_t)U))) return rc;
+    if ((rc = lrk_dev_alloc(h, &g->d_counter, 1))) return rc;
+    size_t tb = 0;
+    LRK_CUDA(h, cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int)U, 0, 32, st));
+    LrkScratch sc;
+    if ((rc = lrk_scratch_begin(h, (size_t)nnz * 8 + (size_t)U * 12 + tb + 16 * 256, &sc))) return rc;
+    double* d_val = sc.take<double>((size_t)std::max<int64_t>(nnz, 1));
+    uint32_t *deg = sc.take<uint32_t>((size_t)U), *deg2 = sc.take<uint32_t>((size_t)U);
+    int32_t* ids = sc.take<int32_t>((size_t)U);
+    void* tmp = sc.take<char>(tb + 16);
+    if (!d_val || !deg || !deg2 || !ids || !tmp) return lrk_fail(h, LRK_ERR_NOMEM, "svdpp_stage", "scratch arena too small", __FILE__, __LINE__);
+    if (nnz > 0) {
+        LRK_CUDA(h, cudaMemcpyAsync(d_val, h_val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        f64_to_f32_kernel<<<lrk_ceil_div(nnz, 256), 256, 0, st>>>(d_val, g->d_cval, nnz); LRK_LAUNCH_CHECK(h);
+    }
+    svdpp_deg_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->d_rowptr, U, deg, ids); LRK_LAUNCH_CHECK(h);
+    LRK_CUDA(h, cub::DeviceRadixSort::SortPairsDescending(tmp, tb, deg, deg2, ids, g->d_uorder, (int)U, 0, 32, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    return LRK_OK;
+}
+
+template <int G, int V>
+static int svdpp_launch_gv(lrk_handle_s* h, const SvdppParams& p) {
+    int per_sm = 0;
+    LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgd_svdpp_epoch_kernel<G, V>, 256, 0));
+    int64_t grid = (int64_t)h->sm_count * (per_sm < 1 ? 1 : per_sm);
+    const int64_t need = ((int64_t)p.U + 8 * (32 / G) - 1) / (8 * (32 / G));
+    if (need < grid) grid = need;
+    // small matrices: at most ~1/16 of the users in flight (every worker holds one user's whole row)
+    const int64_t cap = ((int64_t)p.U / 16) / (8 * (32 / G));
+    if (cap >= 1 && cap < grid) grid = cap;
+    if (grid < 1) grid = 1;
+    sgd_svdpp_epoch_kernel<G, V><<<(unsigned)grid, 256, 0, h->stream>>>(p);
+    LRK_LAUNCH_CHECK(h);
+    return LRK_OK;
+}
+
+// one SVD++ iteration: SVDPlusPlusRecommender.java:63-109
+static int svdpp_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, double reg_b, double* loss_out) {
+    SvdppState* g = (SvdppState*)h->svdpp;
+    LRK_REQUIRE(h, g != nullptr && g->has_y, "SVD++ needs impItemFactors: lrk_set_matrix(h, \"svdpp.y\", Y) after lrk_set_factors");
+    cudaStream_t st = h->stream;
+    SvdppParams p;
+    memset(&p, 0, sizeof p);
+    p.rowptr = h->d_rowptr; p.col = h->d_col; p.cval = g->d_cval; p.uorder = g->d_uorder; p.U = h->U; p.counter = g->d_counter;
+    p.P = h->P32; p.Q = h->Q32; p.Y = g->Y32; p.bu = h->bu32; p.bi = h->bi32;
+    p.mu = (float)h->mu; p.lr = lr; p.reg_u = reg_u; p.reg_i = reg_i; p.reg_b = (float)reg_b; p.reg_imp = (float)g->reg_imp;
+    p.loss = h->d_loss; p.ld = h->ld;
+    LRK_CUDA(h, cudaMemsetAsync(h->d_loss, 0, sizeof(double), st));
+    LRK_CUDA(h, cudaMemsetAsync(g->d_counter, 0, sizeof(unsigned int), st));
+    LRK_CUDA(h, cudaEventRecord(h->ev0, st));
+    int rc = LRK_OK;
+    if (h->nnz > 0) {
+        switch (h->G * 100 + h->V) {
+            case 101: rc = svdpp_launch_gv<1, 1>(h, p); break;
+            case 201: rc = svdpp_launch_gv<2, 1>(h, p); break;
+            case 401: rc = svdpp_launch_gv<4, 1>(h, p); break;
+            case 801: rc = svdpp_launch_gv<8, 1>(h, p); break;
+            case 1601: rc = svdpp_launch_gv<16, 1>(h, p); break;
+            case 3201: rc = svdpp_launch_gv<32, 1>(h, p); break;
+            case 3202: rc = svdpp_launch_gv<32, 2>(h, p); break;
+            default: rc = lrk_fail(h, LRK_ERR_INVALID, "svdpp_epoch", "unsupported factor layout", __FILE__, __LINE__);
+        }
+        if (rc) return rc;
+    }
+    LRK_CUDA(h, cudaEventRecord(h->ev1, st));
+    LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    LRK_CUDA(h, cudaEventElapsedTime(&h->last_epoch_ms, h->ev0, h->ev1));
+    h->f64_valid = false;
+    const double loss = 0.5 * h->h_loss[0];            // SVDPlusPlusRecommender.java:109
+    if (loss_out) *loss_out = loss;
+    if (std::isnan(loss) || std::isinf(loss))
+        return lrk_fail(h, LRK_ERR_DIVERGED, "lrk_sgd_epoch", "Loss = NaN or Infinity: current settings does not fit the recommender!", __FILE__, __LINE__);
+    h->epochs_done++;
+    return LRK_OK;
+}
+
 extern "C" {
 
 const char* lrk_version(void) { return "librec_b200 0.1.0 (sm_100a; LibRec 3.0.0 MF path)"; }
@@ -172,12 +260,12 @@ int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out) {
     *out = nullptr;
     if (cfg->num_factors < 1 || cfg->num_factors > LRK_MAX_FACTORS)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "num_factors must be in 1..256", __FILE__, __LINE__);
-    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_GBPR)
+    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_SVDPP)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown model", __FILE__, __LINE__);
     if (cfg->update_mode < LRK_UPDATE_ATOMIC || cfg->update_mode > LRK_UPDATE_REFERENCE_ORDER)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown update_mode", __FILE__, __LINE__);
     if (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER && !(cfg->model == LRK_MODEL_BIASEDMF || cfg->model == LRK_MODEL_PMF))
-        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "reference-order mode covers BiasedMF and PMF (BPR, RankSGD and GBPR draw from a sequential RNG)", __FILE__, __LINE__);
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "reference-order mode covers BiasedMF and PMF", __FILE__, __LINE__);
     int ndev = 0;
     LRK_CUDA(nullptr, cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev)
@@ -221,6 +309,7 @@ int lrk_destroy(lrk_handle_t h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     group_units_release((GroupUnits*)h->group);
     gbpr_release((GbprState*)h->gbpr);
+    svdpp_release((SvdppState*)h->svdpp);
     dsgd_release(h);
     topn_tc_release(h);
     exact_release((ExactSchedule*)h->exact);
@@ -320,6 +409,7 @@ int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowpt
         h->exact = es;
     }
     if (h->cfg.model == LRK_MODEL_GBPR && (rc = gbpr_stage(h))) return rc;
+    if (h->cfg.model == LRK_MODEL_SVDPP && (rc = svdpp_stage(h, val))) return rc;
     h->has_train = true;
     topn_tc_invalidate(h);
     return LRK_OK;
@@ -331,7 +421,7 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     LRK_REQUIRE(h, h->has_train, "call lrk_set_train_csr first (it fixes numUsers / numItems)");
     LRK_REQUIRE(h, P && Q, "P and Q are required");
     const bool biased = lrk_has_bias(h);
-    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_BIASEDMF || (bu && bi), "BiasedMF needs userBiases and itemBiases");
+    LRK_REQUIRE(h, (h->cfg.model != LRK_MODEL_BIASEDMF && h->cfg.model != LRK_MODEL_SVDPP) || (bu && bi), "BiasedMF / SVD++ need userBiases and itemBiases");
     LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_GBPR || bi, "GBPR needs itemBiases");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->world > 1) return dsgd_set_factors(h, P, Q, bu, bi, mu);
@@ -357,7 +447,7 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I * ld, 256), 256, 0, st>>>(h->Q64, h->Q32, I, k, ld); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu64, h->bu32, U, 1, 1); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi64, h->bi32, I, 1, 1); LRK_LAUNCH_CHECK(h);
-    if (h->cfg.model != LRK_MODEL_BPR && h->cfg.model != LRK_MODEL_GBPR && (rc = refresh_user_norm2(h, true))) return rc;
+    if (h->cfg.model != LRK_MODEL_BPR && h->cfg.model != LRK_MODEL_GBPR && h->cfg.model != LRK_MODEL_SVDPP && (rc = refresh_user_norm2(h, true))) return rc;
     if (h->h_pnorm2) { h->pnorm2_prev = 0.f; h->pnorm2_host = *h->h_pnorm2; }
     LRK_CUDA(h, cudaStreamSynchronize(st));   // host buffers may be reused by the caller on return
     h->mu = mu;
@@ -430,6 +520,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->world > 1) return dsgd_epoch(h, lr, reg_u, reg_i, reg_b, epoch_idx, loss_out);
     if (h->cfg.model == LRK_MODEL_GBPR) return gbpr_epoch(h, lr, reg_u, reg_i, reg_b, epoch_idx, loss_out);
+    if (h->cfg.model == LRK_MODEL_SVDPP) return svdpp_epoch(h, lr, reg_u, reg_i, reg_b, loss_out);
     cudaStream_t st = h->stream;
     if (h->cfg.update_mode == LRK_UPDATE_REFERENCE_ORDER) {
         // fp64 masters are the working set in this mode
@@ -537,7 +628,49 @@ int lrk_set_param(lrk_handle_t h, const char* name, double value) {
         }
         return LRK_OK;
     }
+    if (!strcmp(name, "svdpp.reg_imp")) {
+        LRK_REQUIRE(h, h->cfg.model == LRK_MODEL_SVDPP, "svdpp.* parameters need an SVD++ handle");
+        SvdppState* g = (SvdppState*)h->svdpp;
+        if (!g) { g = new SvdppState(); h->svdpp = g; }
+        g->reg_imp = value;
+        return LRK_OK;
+    }
     return lrk_fail(h, LRK_ERR_INVALID, "lrk_set_param", "unknown parameter name", __FILE__, __LINE__);
+}
+
+int lrk_set_matrix(lrk_handle_t h, const char* name, const double* values) {
+    LRK_REQUIRE(h, h != nullptr && name != nullptr && values != nullptr, "NULL argument");
+    LRK_NOT_MULTI(h, "lrk_set_matrix");
+    LRK_REQUIRE(h, !strcmp(name, "svdpp.y") && h->cfg.model == LRK_MODEL_SVDPP, "unknown matrix name for this model");
+    LRK_REQUIRE(h, h->has_factors, "call lrk_set_factors first");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    SvdppState* g = (SvdppState*)h->svdpp;
+    if (!g) { g = new SvdppState(); h->svdpp = g; }
+    cudaStream_t st = h->stream;
+    const int64_t I = h->I;
+    int rc;
+    if ((rc = lrk_dev_alloc(h, &g->Y64, (size_t)I * h->k))) return rc;
+    if ((rc = lrk_dev_alloc(h, &g->Y32, (size_t)I * h->ld))) return rc;
+    LRK_CUDA(h, cudaMemcpyAsync(g->Y64, values, sizeof(double) * (size_t)I * h->k, cudaMemcpyHostToDevice, st));
+    f64_to_f32_rows_kernel<<<lrk_ceil_div(I * h->ld, 256), 256, 0, st>>>(g->Y64, g->Y32, I, h->k, h->ld); LRK_LAUNCH_CHECK(h);
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    g->has_y = true;
+    return LRK_OK;
+}
+
+int lrk_get_matrix(lrk_handle_t h, const char* name, double* values) {
+    LRK_REQUIRE(h, h != nullptr && name != nullptr && values != nullptr, "NULL argument");
+    LRK_NOT_MULTI(h, "lrk_get_matrix");
+    LRK_REQUIRE(h, !strcmp(name, "svdpp.y") && h->cfg.model == LRK_MODEL_SVDPP, "unknown matrix name for this model");
+    SvdppState* g = (SvdppState*)h->svdpp;
+    LRK_REQUIRE(h, g != nullptr && g->has_y, "matrix not set");
+    LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const int64_t I = h->I;
+    f32_to_f64_rows_kernel<<<lrk_ceil_div(I * h->k, 256), 256, 0, st>>>(g->Y32, g->Y64, I, h->k, h->ld); LRK_LAUNCH_CHECK(h);
+    LRK_CUDA(h, cudaMemcpyAsync(values, g->Y64, sizeof(double) * (size_t)I * h->k, cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    return LRK_OK;
 }
 
 int lrk_sgd_epochs(lrk_handle_t h, int32_t n_epochs, float lr, float decay, float max_lr, float reg_u, float reg_i, double reg_b,
@@ -664,6 +797,7 @@ int lrk_bpr_peek_samples(lrk_handle_t h, int32_t epoch_idx, int64_t first, int64
 int lrk_predict_pairs(lrk_handle_t h, const int32_t* users, const int32_t* items, int64_t n, double* out) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
     LRK_NOT_MULTI(h, "lrk_predict_pairs");
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_SVDPP, "SVD++ predictions need the per-user sum of the implicit factors: read the matrices back (lrk_get_factors, lrk_get_matrix) and use the reference predict()");
     LRK_REQUIRE(h, h->has_factors, "no factors set");
     LRK_REQUIRE(h, n >= 0 && (n == 0 || (users && items && out)), "bad arguments");
     LRK_REQUIRE(h, h->world == 1, "gather the factors with lrk_get_factors in DSGD mode");
@@ -697,6 +831,7 @@ int lrk_eval_rating(lrk_handle_t h, int32_t U, const int64_t* t_rowptr, const in
                     double min_rate, double max_rate, double* pred_out, double* rmse_out, double* mae_out) {
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
     LRK_NOT_MULTI(h, "lrk_eval_rating");
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_SVDPP, "SVD++ predictions need the per-user sum of the implicit factors: read the matrices back (lrk_get_factors, lrk_get_matrix) and use the reference predict()");
     LRK_REQUIRE(h, h->has_factors, "no factors set");
     LRK_REQUIRE(h, U == h->U && t_rowptr, "test matrix must have numUsers rows");
     LRK_REQUIRE(h, h->world == 1, "gather the factors with lrk_get_factors in DSGD mode");
@@ -739,6 +874,7 @@ int lrk_eval_rating(lrk_handle_t h, int32_t U, const int64_t* t_rowptr, const in
 // top-N lists of the queried users into the handle's device buffers (tn_items / tn_scores / tn_counts)
 static int topn_to_device(lrk_handle_s* h, const int32_t* users, int32_t nq, int32_t topn, int32_t exclude_train) {
     LRK_REQUIRE(h, h->has_factors, "no factors set");
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_SVDPP, "SVD++ predictions need the per-user sum of the implicit factors: read the matrices back (lrk_get_factors, lrk_get_matrix) and use the reference predict()");
     LRK_REQUIRE(h, topn > 0, "rec.recommender.ranking.topn should be more than 0!");   // AbstractRecommender.java:115-117
     LRK_REQUIRE(h, topn <= LRK_MAX_TOPN, "topn above LRK_MAX_TOPN (512)");
     LRK_REQUIRE(h, !exclude_train || h->has_train, "exclude_train needs the train CSR");
@@ -875,7 +1011,7 @@ int lrk_comm_init(lrk_handle_t h, int32_t rank, int32_t world, const uint8_t uni
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
     LRK_NOT_MULTI(h, "lrk_comm_init");
     LRK_REQUIRE(h, h->cfg.update_mode != LRK_UPDATE_REFERENCE_ORDER, "reference-order mode is single-GPU");
-    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_RANKSGD && h->cfg.model != LRK_MODEL_GBPR, "RankSGD and GBPR are single-GPU in this build");
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_RANKSGD && h->cfg.model != LRK_MODEL_GBPR && h->cfg.model != LRK_MODEL_SVDPP, "RankSGD, GBPR and SVD++ are single-GPU in this build");
     return dsgd_comm_init(h, rank, world, unique_id);
 }
 
@@ -885,8 +1021,8 @@ int lrk_create_multi(const lrk_config_t* cfg, const int32_t* devices, int32_t n_
     if (n_devices < 1 || n_devices > 8) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "1 to 8 devices", __FILE__, __LINE__);
     for (int a = 0; a < n_devices; ++a) for (int b = a + 1; b < n_devices; ++b)
         if (devices[a] == devices[b]) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "a device is listed twice", __FILE__, __LINE__);
-    if (n_devices > 1 && (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER || cfg->model == LRK_MODEL_RANKSGD || cfg->model == LRK_MODEL_GBPR))
-        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "reference-order mode, RankSGD and GBPR are single-GPU", __FILE__, __LINE__);
+    if (n_devices > 1 && (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER || cfg->model == LRK_MODEL_RANKSGD || cfg->model == LRK_MODEL_GBPR || cfg->model == LRK_MODEL_SVDPP))
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "reference-order mode, RankSGD, GBPR and SVD++ are single-GPU", __FILE__, __LINE__);
     lrk_handle_s* h = new (std::nothrow) lrk_handle_s();
     MultiState* ms = new (std::nothrow) MultiState();
     if (!h || !ms) { delete h; delete ms; return lrk_fail(nullptr, LRK_ERR_NOMEM, "lrk_create_multi", "host allocation failed", __FILE__, __LINE__); }
