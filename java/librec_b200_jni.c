@@ -92,7 +92,7 @@ jint LRK_JNI(setParam)(JNIEnv* env, jclass c, jlong h, jbyteArray nameUtf8, jdou
     return lrk_set_param(H(h), name, value);
 }
 
-static void lrk_jni_name(JNIEnv* env, jbyteArray nameUtf8, char* name, jsize cap) {
+static void jni_copy_name(JNIEnv* env, jbyteArray nameUtf8, char* name, jsize cap) {
     jsize n = (*env)->GetArrayLength(env, nameUtf8);
     if (n > cap - 1) n = cap - 1;
     (*env)->GetByteArrayRegion(env, nameUtf8, 0, n, (jbyte*)name);
@@ -101,13 +101,13 @@ static void lrk_jni_name(JNIEnv* env, jbyteArray nameUtf8, char* name, jsize cap
 jint LRK_JNI(setMatrix)(JNIEnv* env, jclass c, jlong h, jbyteArray nameUtf8, jobject values) {
     char name[64];
     (void)c;
-    lrk_jni_name(env, nameUtf8, name, (jsize)sizeof name);
+    jni_copy_name(env, nameUtf8, name, (jsize)sizeof name);
     return lrk_set_matrix(H(h), name, (const double*)BUF(values));
 }
 jint LRK_JNI(getMatrix)(JNIEnv* env, jclass c, jlong h, jbyteArray nameUtf8, jobject values) {
     char name[64];
     (void)c;
-    lrk_jni_name(env, nameUtf8, name, (jsize)sizeof name);
+    jni_copy_name(env, nameUtf8, name, (jsize)sizeof name);
     return lrk_get_matrix(H(h), name, (double*)BUF(values));
 }
 

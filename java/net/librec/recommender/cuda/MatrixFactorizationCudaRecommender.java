@@ -58,6 +58,15 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
         LibrecB200.hostFree(rowptr); LibrecB200.hostFree(col); LibrecB200.hostFree(val);
     }
 
+    /** hooks for models with matrices beyond P / Q / biases (SVD++: impItemFactors) */
+    protected void afterSetFactors() throws LibrecException { }
+    protected void afterGetFactors() throws LibrecException { }
+
+    /** the reference's own recommendRank (for models the native top-N does not cover) */
+    protected RecommendedList recommendRankReference(LibrecDataList<AbstractBaseDataEntry> dataList) throws LibrecException {
+        return super.recommendRank(dataList);
+    }
+
     protected void check(int status) throws LibrecException {
         if (status != 0) throw new LibrecException(LibrecB200.lastError(handle));
     }
@@ -83,6 +92,7 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
         if (bu != null) bu.asDoubleBuffer().put(userBiases.getValues());
         if (bi != null) bi.asDoubleBuffer().put(itemBiases.getValues());                // GBPR has item biases only
         check(LibrecB200.setFactors(handle, P, Q, bu, bi, globalMean));
+        afterSetFactors();
         double[] lossOut = new double[1];
         boolean boldDriver = conf.getBoolean("rec.learnrate.bolddriver", false);
         if (!earlyStop && !boldDriver && !verbose) {
@@ -106,6 +116,7 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
             updateLRate(iter);                             // MatrixFactorizationRecommender.java:121-139
         }
         check(LibrecB200.getFactors(handle, P, Q, bu, bi));
+        afterGetFactors();
         unflatten(P, userFactors); unflatten(Q, itemFactors);
         if (bu != null) bu.asDoubleBuffer().get(userBiases.getValues());
         if (bi != null) bi.asDoubleBuffer().get(itemBiases.getValues());
