@@ -129,6 +129,43 @@ def run_reference_order(name, model_name, shape, k, lr, reg, reg_b):
                       "schedule_build_s": t_stage, "max_item_degree": int(np.bincount(d["col"], minlength=I).max()), "losses": losses}), flush=True)
 
 
+def run_svdpp(steps, warmup, oracle_epochs=2):
+    """N3: SVD++ (svdpp-test.properties: k=20, lr 0.002, reg 0.01) on the ML-20M shape; the oracle's sequential loop runs the first
+    epochs beside it so that the loss curve at full concurrency is seen next to the reference's"""
+    import time
+    import torch
+    from librec_b200 import capi, synth
+    from oracle import oracle as O
+    d = synth.make_ratings("ml-20m")
+    U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
+    k, lr, reg = 20, 0.002, 0.01
+    P, Q, bu, bi = synth.init_factors(U, I, k, 11, True)
+    Y = np.random.default_rng(12).normal(0, 0.001, (I, k))
+    mu = float(d["val"].mean())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    with capi.Handle(capi.MODEL_SVDPP, k, seed=1) as h:
+        h.set_param("svdpp.reg_imp", reg)
+        h.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
+        h.set_factors(P, Q, bu, bi, mu)
+        h.set_matrix("svdpp.y", Y)
+        ms, losses = [], []
+        for s in range(warmup + steps):
+            flush.zero_(); torch.cuda.synchronize()
+            losses.append(h.sgd_epoch(lr, reg, reg, reg, s + 1))
+            if s >= warmup:
+                ms.append(h.last_epoch_ms())
+    oP, oQ, oY, obu, obi = P.copy(), Q.copy(), Y.copy(), bu.copy(), bi.copy()
+    t0 = time.perf_counter()
+    ol = [O.lib().lro_svdpp_epoch(U, d["rowptr"], d["col"], d["val"], k, oP, oQ, oY, obu, obi, mu, lr, reg, reg, reg, reg) for _ in range(oracle_epochs)]
+    t_or = (time.perf_counter() - t0) / max(1, oracle_epochs)
+    kms = float(np.mean(ms))
+    print(json.dumps({"config": "N3-SVD++", "metric": "MF SGD rating-updates/s", "value": nnz / (kms * 1e-3), "unit": "updates/s", "n_gpus": 1,
+                      "steps": steps, "warmup": warmup, "ms_per_step": kms,
+                      "workload": "svdpp k=%d, synthetic ml-20m shape (%d x %d, %d ratings), lr %g reg %g" % (k, U, I, nnz, lr, reg),
+                      "losses": losses, "oracle_losses_first_epochs": ol, "oracle_updates_per_s_one_core": nnz / t_or,
+                      "row_transfers_per_rating": "3 gathers (y_j, q_i, y_j) + 2 REDs (q_i, y_j); the user side is register-resident"}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
@@ -146,6 +183,8 @@ if __name__ == "__main__":
         run_reference_order("C2-reforder", "biasedmf", "ml-20m", 64, 0.002, 0.01, 0.01)
         run_reference_order("C4p-reforder", "pmf", "netflix-10m", 128, 0.01, 0.08, 0.0)
         run_reference_order("C4-reforder", "pmf", "netflix", 128, 0.01, 0.08, 0.0)
+    if a.only == "svdpp":
+        run_svdpp(a.steps, a.warmup)
     if a.only == "gbpr":
         # gbpr defaults: rho 1.5, group size 2.  GBPR adds the SUM of an epoch's factor updates at its end (GBPRRecommender.java:167-168),
         # so its effective step grows with the samples per row: lr 0.05 is fine on ml-100k (80 k samples), turns around after 4 epochs

@@ -224,6 +224,11 @@ static int svdpp_epoch(lrk_handle_s* h, float lr, float reg_u, float reg_i, doub
     return LRK_OK;
 }
 
+__global__ void pairs_validate_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ i, int64_t n, int32_t U, int32_t I, int* __restrict__ flag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && (u[t] < 0 || u[t] >= U || i[t] < 0 || i[t] >= I)) atomicOr(flag, 1);
+}
+
 extern "C" {
 
 const char* lrk_version(void) { return "librec_b200 0.1.0 (sm_100a; LibRec 3.0.0 MF path)"; }
@@ -803,27 +808,29 @@ int lrk_predict_pairs(lrk_handle_t h, const int32_t* users, const int32_t* items
     LRK_REQUIRE(h, h->world == 1, "gather the factors with lrk_get_factors in DSGD mode");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     if (n == 0) return LRK_OK;
-    for (int64_t t = 0; t < n; ++t)
-        LRK_REQUIRE(h, users[t] >= 0 && users[t] < h->U && items[t] >= 0 && items[t] < h->I, "user/item index out of range");
     int rc = refresh_masters(h);
     if (rc) return rc;
     cudaStream_t st = h->stream;
-    int32_t *d_u = nullptr, *d_i = nullptr; double* d_o = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d_u, sizeof(int32_t) * (size_t)n);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_i, sizeof(int32_t) * (size_t)n);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_o, sizeof(double) * (size_t)n);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, users, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, items, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) {
-        predict_pairs_kernel<<<lrk_ceil_div(n, 128), 128, 0, st>>>(h->P64, h->Q64, h->bu64, h->bi64, h->mu,
-                                                                   lrk_has_bias(h), h->k, d_u, d_i, n, d_o);
-        h->launches++;
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_u); cudaFree(d_i); cudaFree(d_o);
-    LRK_CUDA(h, e);
+    // inputs, output and the range-check flag live in the handle's staging arena (no per-call cudaMalloc); the indices are
+    // validated on the device before anything is indexed with them
+    LrkScratch sc;
+    if ((rc = lrk_scratch_begin(h, (size_t)n * 16 + 4 * 256, &sc))) return rc;
+    int32_t *d_u = sc.take<int32_t>((size_t)n), *d_i = sc.take<int32_t>((size_t)n);
+    double* d_o = sc.take<double>((size_t)n);
+    int* d_flag = sc.take<int>(1);
+    if (!d_u || !d_i || !d_o || !d_flag) return lrk_fail(h, LRK_ERR_NOMEM, "lrk_predict_pairs", "scratch arena too small", __FILE__, __LINE__);
+    int flag = 0;
+    LRK_CUDA(h, cudaMemcpyAsync(d_u, users, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    LRK_CUDA(h, cudaMemcpyAsync(d_i, items, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    LRK_CUDA(h, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    pairs_validate_kernel<<<lrk_ceil_div(n, 256), 256, 0, st>>>(d_u, d_i, n, h->U, h->I, d_flag); LRK_LAUNCH_CHECK(h);
+    LRK_CUDA(h, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
+    LRK_REQUIRE(h, flag == 0, "user/item index out of range");
+    predict_pairs_kernel<<<lrk_ceil_div(n, 128), 128, 0, st>>>(h->P64, h->Q64, h->bu64, h->bi64, h->mu, lrk_has_bias(h), h->k, d_u, d_i, n, d_o);
+    LRK_LAUNCH_CHECK(h);
+    LRK_CUDA(h, cudaMemcpyAsync(out, d_o, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    LRK_CUDA(h, cudaStreamSynchronize(st));
     return LRK_OK;
 }
 
