@@ -65,7 +65,11 @@ typedef enum {
      * rec.impItem.regularization through lrk_set_param("svdpp.reg_imp").  Training only, single GPU: its predict() needs the
      * per-user sum of the implicit factors, so the scoring entry points return LRK_ERR_INVALID for this model (the shim keeps
      * the reference's predict() on the matrices it reads back). */
-    LRK_MODEL_SVDPP = 5
+    LRK_MODEL_SVDPP = 5,
+    /* aobpr -> recommender/cf/ranking/AoBPRRecommender.java:60-200: BPR with adaptive oversampling of the
+     * negative item; rec.item.distribution.parameter through lrk_set_param("aobpr.lambda") (required, as in the reference);
+     * single GPU; scoring and lrk_bpr_peek_samples as for BPR */
+    LRK_MODEL_AOBPR = 6
 } lrk_model;
 
 /* how concurrent updates to one factor row are combined */
@@ -137,6 +141,7 @@ LRK_API int lrk_get_factors(lrk_handle_t h, double* P, double* Q, double* bu, do
  *   "gbpr.rho"   rec.gpbr.rho   (float, default 1.5; GBPRRecommender.java:71)
  *   "gbpr.gsize" rec.gpbr.gsize (int 1..8, default 2; GBPRRecommender.java:72)
  *   "svdpp.reg_imp" rec.impItem.regularization (default 0.015; SVDPlusPlusRecommender.java:52)
+ *   "aobpr.lambda" rec.item.distribution.parameter (no default; AoBPRRecommender.java:63)
  * Unknown names fail with LRK_ERR_INVALID. */
 LRK_API int lrk_set_param(lrk_handle_t h, const char* name, double value);
 

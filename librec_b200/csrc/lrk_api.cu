@@ -8,6 +8,7 @@
 #include "sgd_exact.cuh"
 #include "sgd_gbpr.cuh"
 #include "sgd_svdpp.cuh"
+#include "sgd_aobpr.cuh"
 #include <chrono>
 #include "topn_exact.cuh"
 #include "topn_tc.cuh"
@@ -265,7 +266,7 @@ int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out) {
     *out = nullptr;
     if (cfg->num_factors < 1 || cfg->num_factors > LRK_MAX_FACTORS)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "num_factors must be in 1..256", __FILE__, __LINE__);
-    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_SVDPP)
+    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_AOBPR)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown model", __FILE__, __LINE__);
     if (cfg->update_mode < LRK_UPDATE_ATOMIC || cfg->update_mode > LRK_UPDATE_REFERENCE_ORDER)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown update_mode", __FILE__, __LINE__);
@@ -315,6 +316,7 @@ int lrk_destroy(lrk_handle_t h) {
     group_units_release((GroupUnits*)h->group);
     gbpr_release((GbprState*)h->gbpr);
     svdpp_release((SvdppState*)h->svdpp);
+    aobpr_release((AobprState*)h->aobpr);
     dsgd_release(h);
     topn_tc_release(h);
     exact_release((ExactSchedule*)h->exact);
@@ -452,7 +454,8 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I * ld, 256), 256, 0, st>>>(h->Q64, h->Q32, I, k, ld); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu64, h->bu32, U, 1, 1); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi64, h->bi32, I, 1, 1); LRK_LAUNCH_CHECK(h);
-    if (h->cfg.model != LRK_MODEL_BPR && h->cfg.model != LRK_MODEL_GBPR && h->cfg.model != LRK_MODEL_SVDPP && (rc = refresh_user_norm2(h, true))) return rc;
+    if (h->cfg.model != LRK_MODEL_BPR && h->cfg.model != LRK_MODEL_GBPR && h->cfg.model != LRK_MODEL_SVDPP && h->cfg.model != LRK_MODEL_AOBPR && (rc = refresh_user_norm2(h, true))) return rc;
+    if (h->aobpr) ((AobprState*)h->aobpr)->count = 0;                 // a new trainModel(): countIter starts at 0 (AoBPRRecommender.java:88)
     if (h->h_pnorm2) { h->pnorm2_prev = 0.f; h->pnorm2_host = *h->h_pnorm2; }
     LRK_CUDA(h, cudaStreamSynchronize(st));   // host buffers may be reused by the caller on return
     h->mu = mu;
@@ -550,6 +553,14 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
     if (h->h_pnorm2) { h->pnorm2_prev = h->pnorm2_host; h->pnorm2_host = *h->h_pnorm2; }
     SgdParams sp;
     fill_sgd_params(h, sp, lr, reg_u, reg_i, reg_b, epoch_idx);
+    AobprState* ao = nullptr;
+    if (h->cfg.model == LRK_MODEL_AOBPR) {
+        ao = (AobprState*)h->aobpr;
+        LRK_REQUIRE(h, ao != nullptr, "AoBPR needs rec.item.distribution.parameter: lrk_set_param(h, \"aobpr.lambda\", value)");
+        int rc_a = aobpr_prepare(h, ao);
+        if (rc_a) return rc_a;
+        sp.ao_rank = ao->d_rank; sp.ao_var = ao->d_var; sp.ao_cum = ao->d_cum; sp.n_entries = h->nnz;
+    }
     const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
     const size_t np_ = (size_t)h->U * h->ld, nq_ = (size_t)h->I * h->ld;
     int rc;
@@ -582,6 +593,19 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
             gp.reg_b = sp.reg_b; gp.loss = sp.loss; gp.ld = sp.ld; gp.item_deg = sp.item_deg;
             LRK_CUDA(h, cudaMemsetAsync(gu->d_counter, 0, sizeof(unsigned int), st));
             if ((rc = sgd_group_launch(h, gp, h->nnz, h->conc_div))) return rc;
+        } else if (h->nnz > 0 && ao) {
+            // AoBPR: the epoch in windows of loopNumber samples, the factor rankings refreshed between them (countIter runs across
+            // iterations and restarts at every refresh, AoBPRRecommender.java:92-97)
+            int64_t count = ao->count, done = 0;
+            while (done < h->nnz) {
+                if (count % ao->loop == 0) { if ((rc = aobpr_refresh(h, ao))) return rc; count = 0; }
+                const int64_t w = std::min<int64_t>(h->nnz - done, (int64_t)ao->loop - count);
+                SgdParams wp = sp;
+                wp.n = w; wp.sample_base = done;
+                if ((rc = sgd_launch(h, wp))) return rc;
+                done += w; count += w;
+            }
+            if (attempt == 0) ao->count = count;          // a rolled-back attempt replays the same windows
         } else if (h->nnz > 0 && (rc = sgd_launch(h, sp))) return rc;
         LRK_CUDA(h, cudaEventRecord(h->ev1, st));
         if (track_norm && (rc = refresh_user_norm2(h, false))) return rc;
@@ -631,6 +655,14 @@ int lrk_set_param(lrk_handle_t h, const char* name, double value) {
             LRK_REQUIRE(h, value >= 1.0 && value <= (double)LRK_GBPR_MAX_GROUP, "rec.gpbr.gsize must be in 1..8");
             g->glen = (int)value;
         }
+        return LRK_OK;
+    }
+    if (!strcmp(name, "aobpr.lambda")) {
+        LRK_REQUIRE(h, h->cfg.model == LRK_MODEL_AOBPR, "aobpr.* parameters need an AoBPR handle");
+        AobprState* a = (AobprState*)h->aobpr;
+        if (!a) { a = new AobprState(); h->aobpr = a; }
+        a->dist_param = (float)value;
+        a->I = 0;                                 // the rank distribution is rebuilt at the next epoch
         return LRK_OK;
     }
     if (!strcmp(name, "svdpp.reg_imp")) {
@@ -766,6 +798,15 @@ int lrk_bpr_peek_samples(lrk_handle_t h, int32_t epoch_idx, int64_t first, int64
     if (n == 0) return LRK_OK;
     SgdParams sp;
     fill_sgd_params(h, sp, 0.f, 0.f, 0.f, 0.0, epoch_idx);
+    if (h->cfg.model == LRK_MODEL_AOBPR) {
+        // the draws depend on the factor rankings: those of the current item factors (what the first window of an epoch uses)
+        AobprState* ao = (AobprState*)h->aobpr;
+        LRK_REQUIRE(h, ao != nullptr && h->has_factors, "AoBPR: set the factors and rec.item.distribution.parameter first");
+        int rc_a = aobpr_prepare(h, ao);
+        if (rc_a == LRK_OK) rc_a = aobpr_refresh(h, ao);
+        if (rc_a) return rc_a;
+        sp.ao_rank = ao->d_rank; sp.ao_var = ao->d_var; sp.ao_cum = ao->d_cum; sp.n_entries = h->nnz;
+    }
     int32_t* d_out = nullptr;
     LRK_CUDA(h, cudaMalloc((void**)&d_out, sizeof(int32_t) * 3 * (size_t)n));
     if (h->cfg.model == LRK_MODEL_GBPR) {
@@ -1018,7 +1059,7 @@ int lrk_comm_init(lrk_handle_t h, int32_t rank, int32_t world, const uint8_t uni
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
     LRK_NOT_MULTI(h, "lrk_comm_init");
     LRK_REQUIRE(h, h->cfg.update_mode != LRK_UPDATE_REFERENCE_ORDER, "reference-order mode is single-GPU");
-    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_RANKSGD && h->cfg.model != LRK_MODEL_GBPR && h->cfg.model != LRK_MODEL_SVDPP, "RankSGD, GBPR and SVD++ are single-GPU in this build");
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_RANKSGD && h->cfg.model != LRK_MODEL_GBPR && h->cfg.model != LRK_MODEL_SVDPP && h->cfg.model != LRK_MODEL_AOBPR, "RankSGD, GBPR, SVD++ and AoBPR are single-GPU in this build");
     return dsgd_comm_init(h, rank, world, unique_id);
 }
 
@@ -1028,8 +1069,8 @@ int lrk_create_multi(const lrk_config_t* cfg, const int32_t* devices, int32_t n_
     if (n_devices < 1 || n_devices > 8) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "1 to 8 devices", __FILE__, __LINE__);
     for (int a = 0; a < n_devices; ++a) for (int b = a + 1; b < n_devices; ++b)
         if (devices[a] == devices[b]) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "a device is listed twice", __FILE__, __LINE__);
-    if (n_devices > 1 && (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER || cfg->model == LRK_MODEL_RANKSGD || cfg->model == LRK_MODEL_GBPR || cfg->model == LRK_MODEL_SVDPP))
-        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "reference-order mode, RankSGD, GBPR and SVD++ are single-GPU", __FILE__, __LINE__);
+    if (n_devices > 1 && (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER || cfg->model == LRK_MODEL_RANKSGD || cfg->model == LRK_MODEL_GBPR || cfg->model == LRK_MODEL_SVDPP || cfg->model == LRK_MODEL_AOBPR))
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "reference-order mode, RankSGD, GBPR, SVD++ and AoBPR are single-GPU", __FILE__, __LINE__);
     lrk_handle_s* h = new (std::nothrow) lrk_handle_s();
     MultiState* ms = new (std::nothrow) MultiState();
     if (!h || !ms) { delete h; delete ms; return lrk_fail(nullptr, LRK_ERR_NOMEM, "lrk_create_multi", "host allocation failed", __FILE__, __LINE__); }

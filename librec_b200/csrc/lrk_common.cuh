@@ -77,6 +77,7 @@ struct lrk_handle_s {
 
     void* gbpr = nullptr;     // GbprState* (sgd_gbpr.cuh)
     void* svdpp = nullptr;    // SvdppState* (sgd_svdpp.cuh)
+    void* aobpr = nullptr;    // AobprState* (sgd_aobpr.cuh)
 
     // reference-order (wavefront) schedule, see sgd_exact.cuh
     void* exact = nullptr;

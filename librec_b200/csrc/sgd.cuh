@@ -47,6 +47,7 @@ struct SgdParams {
     const int32_t* __restrict__ si;
     const float* __restrict__ sr;
     int64_t n;
+    int64_t n_entries;      // AoBPR: entries of the staged stream (su / si), the population of its (u, i) draw
     float* P;
     float* Q;
     float* bu;
@@ -79,6 +80,11 @@ struct SgdParams {
     // Philox counters of the strata of one epoch apart
     int32_t blk_lo, blk_hi;
     int64_t sample_base;
+    // AoBPR only (adaptive oversampling, AoBPRRecommender.java:100-138): per-factor item rankings, factor variances and the
+    // cumulative rank distribution, refreshed by the host every |I| ln |I| samples (sgd_aobpr.cuh)
+    const int32_t* __restrict__ ao_rank;   // [k][I]: ao_rank[f * I + r] = item of rank r in factor f (descending value)
+    const float* __restrict__ ao_var;      // [k]
+    const float* __restrict__ ao_cum;      // [I] inclusive cumulative of exp(-((r + 1) / lambda)) / sum
 };
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -239,17 +245,61 @@ __device__ __forceinline__ void bpr_draw_block(const SgdParams& p, int64_t s, in
     u = -1; pi = p.blk_lo; nj = p.blk_lo;
 }
 
+// AoBPR draw (AoBPRRecommender.java:100-138): a train ENTRY uniformly (u, i) -- the staged stream is a permutation of the entries, so
+// a uniform stream position is a uniform entry --, then the negative by adaptive oversampling: rank r from the geometric-like step
+// distribution exp(-((r + 1) / lambda)), factor f with probability |p_uf| var_f / sum, item = the r-th item of factor f's ranking
+// from the top if p_uf > 0, from the bottom otherwise; redrawn while the user has rated it.
+__device__ __forceinline__ void aobpr_draw(const SgdParams& p, int64_t s_in, int32_t& u, int32_t& pi, int32_t& nj) {
+    const uint2 key = make_uint2(p.seed_lo, p.seed_hi);
+    const int64_t s = s_in + p.sample_base;
+    const int k = p.ld;                                    // padded columns are zero: they never win a draw
+    uint32_t attempt = 0;
+    while (attempt < LRK_BPR_MAX_ATTEMPTS) {
+        uint4 x = philox4x32_10(make_uint4((uint32_t)s, (uint32_t)(s >> 32), p.epoch, attempt++), key);
+        const int64_t d = (int64_t)(((unsigned long long)x.x * (unsigned long long)p.n_entries) >> 32);
+        u = __ldg(p.su + d);
+        const int64_t b = __ldg(p.rowptr + u), e = __ldg(p.rowptr + u + 1);
+        if (e - b == 0 || e - b == p.I) continue;
+        pi = __ldg(p.si + d);
+        const float* pu = p.P + (int64_t)u * p.ld;
+        float tot = 0.f;
+        for (int f = 0; f < k; ++f) tot += fabsf(__ldcg(pu + f)) * __ldg(p.ao_var + f);
+        uint32_t w[3] = {x.y, x.z, x.w};
+        int have = 3;
+        for (const uint32_t stop = attempt + LRK_BPR_MAX_ATTEMPTS; attempt < stop;) {
+            if (have < 2) {
+                x = philox4x32_10(make_uint4((uint32_t)s, (uint32_t)(s >> 32), p.epoch, attempt++), key);
+                w[0] = x.x; w[1] = x.y; w[2] = x.z; have = 3;
+            }
+            // rank: first r with cum[r] > t
+            const float t = (float)w[--have] * 2.3283064e-10f;
+            int lo = 0, hi = p.I - 1;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (__ldg(p.ao_cum + m) > t) hi = m; else lo = m + 1; }
+            const int r = lo;
+            // factor: first f whose cumulative |p_uf| var_f exceeds t2 * total
+            const float t2 = (float)w[--have] * 2.3283064e-10f * tot;
+            float acc = 0.f;
+            int fsel = k - 1;
+            for (int f = 0; f < k; ++f) { acc += fabsf(__ldcg(pu + f)) * __ldg(p.ao_var + f); if (acc > t2) { fsel = f; break; } }
+            nj = __ldcg(pu + fsel) > 0.f ? __ldg(p.ao_rank + (int64_t)fsel * p.I + r) : __ldg(p.ao_rank + (int64_t)fsel * p.I + (p.I - r - 1));
+            if (!row_contains(p.col, b, e, nj)) return;
+        }
+        break;
+    }
+    u = -1; pi = 0; nj = 0;
+}
+
 __global__ void bpr_peek_kernel(SgdParams p, int64_t first, int64_t n, int32_t* out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     int32_t u, pi, nj;
-    bpr_draw(p, first + t, u, pi, nj);
+    if (p.ao_rank) aobpr_draw(p, first + t, u, pi, nj); else bpr_draw(p, first + t, u, pi, nj);
     out[3 * t] = u; out[3 * t + 1] = pi; out[3 * t + 2] = nj;
 }
 
 // BLOCKED: DSGD stratum (positives and negatives inside the held item block); a separate instantiation so that the
 // single-GPU kernel does not carry the second sampler (it cost 32 % of its throughput as a run-time branch)
-template <int G, int V, bool ATOMIC, bool BLOCKED = false>
+template <int G, int V, bool ATOMIC, bool BLOCKED = false, bool AOBPR = false>
 __global__ void __launch_bounds__(256) sgd_bpr_epoch_kernel(SgdParams p) {
     constexpr int RPS = 32 / G;
     constexpr int STEPS = G;
@@ -268,6 +318,7 @@ __global__ void __launch_bounds__(256) sgd_bpr_epoch_kernel(SgdParams p) {
             const int64_t s = (tile << 5) + lane;
             if (s < p.n) {
                 if (BLOCKED) { bpr_draw_block(p, s, u_l, i_l, j_l); i_l -= p.blk_lo; j_l -= p.blk_lo; }
+                else if (AOBPR) aobpr_draw(p, s, u_l, i_l, j_l);
                 else bpr_draw(p, s, u_l, i_l, j_l);
             }
         }
@@ -577,7 +628,8 @@ static int sgd_launch_gv(lrk_handle_s* h, const SgdParams& sp_in) {
     } else if (h->cfg.model == LRK_MODEL_RANKSGD) {
         if (atomic) LRK_GO((sgd_ranksgd_epoch_kernel<G, V, true>)); else LRK_GO((sgd_ranksgd_epoch_kernel<G, V, false>));
     } else {
-        if (sp.blk_hi > 0) { if (atomic) LRK_GO((sgd_bpr_epoch_kernel<G, V, true, true>)); else LRK_GO((sgd_bpr_epoch_kernel<G, V, false, true>)); }
+        if (sp.ao_rank) { if (atomic) LRK_GO((sgd_bpr_epoch_kernel<G, V, true, false, true>)); else LRK_GO((sgd_bpr_epoch_kernel<G, V, false, false, true>)); }
+        else if (sp.blk_hi > 0) { if (atomic) LRK_GO((sgd_bpr_epoch_kernel<G, V, true, true>)); else LRK_GO((sgd_bpr_epoch_kernel<G, V, false, true>)); }
         else if (atomic) LRK_GO((sgd_bpr_epoch_kernel<G, V, true>)); else LRK_GO((sgd_bpr_epoch_kernel<G, V, false>));
     }
 #undef LRK_GO

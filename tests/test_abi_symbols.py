@@ -63,14 +63,14 @@ def test_enum_values_agree_across_header_binding_and_java_shim(capi):
     src = open(os.path.join(ROOT, "include", "librec_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     header = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(LRK_[A-Z_]+)\s*=\s*(-?\d+)", src)}
-    for name in ("MODEL_BIASEDMF", "MODEL_PMF", "MODEL_BPR", "MODEL_RANKSGD", "MODEL_GBPR", "MODEL_SVDPP", "UPDATE_ATOMIC", "UPDATE_HOGWILD",
+    for name in ("MODEL_BIASEDMF", "MODEL_PMF", "MODEL_BPR", "MODEL_RANKSGD", "MODEL_GBPR", "MODEL_SVDPP", "MODEL_AOBPR", "UPDATE_ATOMIC", "UPDATE_HOGWILD",
                  "UPDATE_REFERENCE_ORDER", "OK", "ERR_INVALID", "ERR_CUDA", "ERR_NCCL", "ERR_NOMEM", "ERR_DIVERGED"):
         assert getattr(capi, name) == header["LRK_" + name], name
     java = open(os.path.join(ROOT, "java", "net", "librec", "recommender", "cuda", "LibrecB200.java")).read()
     jconst = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(MODEL_[A-Z]+)\s*=\s*(\d+)", java)}
     for name, value in jconst.items():
         assert header["LRK_" + name] == value, name
-    assert set(jconst) == {"MODEL_BIASEDMF", "MODEL_PMF", "MODEL_BPR", "MODEL_RANKSGD", "MODEL_GBPR", "MODEL_SVDPP"}
+    assert set(jconst) == {"MODEL_BIASEDMF", "MODEL_PMF", "MODEL_BPR", "MODEL_RANKSGD", "MODEL_GBPR", "MODEL_SVDPP", "MODEL_AOBPR"}
     # the bad-model guard of test_bad_config_is_rejected relies on 7 being out of range
     assert max(v for k, v in header.items() if k.startswith("LRK_MODEL_")) < 7
 
