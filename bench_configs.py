@@ -79,9 +79,13 @@ def run(name, model_name, shape, k, lr, reg, steps, warmup):
     U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
     P, Q, _, _ = synth.init_factors(U, I, k, 11, False)
     gbpr = model_name == "gbpr"
-    model = capi.MODEL_BPR if bpr else (capi.MODEL_RANKSGD if ranksgd else (capi.MODEL_GBPR if gbpr else capi.MODEL_PMF))
+    aobpr = model_name == "aobpr"
+    bpr = bpr or aobpr
+    model = capi.MODEL_AOBPR if aobpr else capi.MODEL_BPR if bpr else (capi.MODEL_RANKSGD if ranksgd else (capi.MODEL_GBPR if gbpr else capi.MODEL_PMF))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     with capi.Handle(model, k, seed=1) as h:
+        if aobpr:
+            h.set_param("aobpr.lambda", 0.05)
         h.set_train_csr(U, I, d["rowptr"], d["col"], d["val"])
         h.set_factors(P, Q, None, np.zeros(I) if gbpr else None)
         ms, losses = [], []
@@ -95,7 +99,7 @@ def run(name, model_name, shape, k, lr, reg, steps, warmup):
     # GBPR: r/w of the group's user rows (2 users), q_i, q_j
     bytes_per = 8 * k * 4 if gbpr else 6 * k * 4 if bpr else (12 + 6 * k * 4 if ranksgd else 12 + 4 * k * 4)     # RankSGD: triple + r/w of p_u, q_i, q_j
     achieved = bytes_per * nnz / (kms * 1e-3) / 1e9
-    print(json.dumps({"config": name, "metric": "GBPR samples/s" if gbpr else "BPR samples/s" if bpr else ("RankSGD updates/s" if ranksgd else "MF SGD rating-updates/s"), "value": nnz / (kms * 1e-3),
+    print(json.dumps({"config": name, "metric": "GBPR samples/s" if gbpr else "AoBPR samples/s" if aobpr else "BPR samples/s" if bpr else ("RankSGD updates/s" if ranksgd else "MF SGD rating-updates/s"), "value": nnz / (kms * 1e-3),
                       "unit": "samples/s" if (bpr or gbpr) else "updates/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": kms,
                       "workload": "%s k=%d, synthetic %s shape (%d x %d, %d ratings), lr %g reg %g" % (model_name, k, shape, U, I, nnz, lr, reg),
                       "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
@@ -183,6 +187,8 @@ if __name__ == "__main__":
         run_reference_order("C2-reforder", "biasedmf", "ml-20m", 64, 0.002, 0.01, 0.01)
         run_reference_order("C4p-reforder", "pmf", "netflix-10m", 128, 0.01, 0.08, 0.0)
         run_reference_order("C4-reforder", "pmf", "netflix", 128, 0.01, 0.08, 0.0)
+    if a.only == "aobpr":
+        run("N3-AoBPR", "aobpr", "ml-20m", 10, 0.01, 0.01, a.steps, a.warmup)       # aobpr-test-like: lambda 0.05 * numItems
     if a.only == "svdpp":
         run_svdpp(a.steps, a.warmup)
     if a.only == "gbpr":

@@ -612,7 +612,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
         LRK_CUDA(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
         LRK_CUDA(h, cudaStreamSynchronize(st));
         loss = h->h_loss[0];
-        if (h->cfg.model != LRK_MODEL_BPR) loss *= 0.5;   // BiasedMFRecommender.java:101 ; BPR has no 0.5
+        if (h->cfg.model != LRK_MODEL_BPR && h->cfg.model != LRK_MODEL_AOBPR) loss *= 0.5;   // BiasedMFRecommender.java:101 ; BPR / AoBPR have no 0.5
         const bool bad = !std::isfinite(loss) || (h->prev_loss > 0.0 && loss > 10.0 * h->prev_loss);
         if (!bad || attempt >= 6 || h->conc_div >= 4096) break;
         // roll the epoch back and retry with fewer ratings in flight
