@@ -95,6 +95,11 @@ def run(name, model_name, shape, k, lr, reg, steps, warmup):
             if s >= warmup:
                 ms.append(h.last_epoch_ms())
         guard = h.sgd_safeguard()
+        # the L2 gather + RED rate for this row length and working set (lrk_probe_l2): what bounds these kernels
+        ld = 4
+        while ld < k and ld < 128:
+            ld *= 2
+        l2 = h.probe_l2((U + I) * ld * 4, ld) if ld in (64, 128) else None
     kms = float(np.mean(ms))
     # GBPR: r/w of the group's user rows (2 users), q_i, q_j
     bytes_per = 8 * k * 4 if gbpr else 6 * k * 4 if bpr else (12 + 6 * k * 4 if ranksgd else 12 + 4 * k * 4)     # RankSGD: triple + r/w of p_u, q_i, q_j
@@ -102,8 +107,13 @@ def run(name, model_name, shape, k, lr, reg, steps, warmup):
     print(json.dumps({"config": name, "metric": "GBPR samples/s" if gbpr else "AoBPR samples/s" if aobpr else "BPR samples/s" if bpr else ("RankSGD updates/s" if ranksgd else "MF SGD rating-updates/s"), "value": nnz / (kms * 1e-3),
                       "unit": "samples/s" if (bpr or gbpr) else "updates/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": kms,
                       "workload": "%s k=%d, synthetic %s shape (%d x %d, %d ratings), lr %g reg %g" % (model_name, k, shape, U, I, nnz, lr, reg),
-                      "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                                   "algorithmic_bytes_per_unit": bytes_per},
+                      "roofline": ({"bound": "l2", "achieved": achieved, "peak": l2["mix"], "unit": "GB/s", "frac": achieved / l2["mix"],
+                                    "peak_source": "lrk_probe_l2 in this run (row gathers + vector REDs 1:1, %d B rows; gathers alone %.0f, REDs alone %.0f GB/s)" % (ld * 4, l2["gather"], l2["red"]),
+                                    "algorithmic_bytes_per_unit": bytes_per, "frac_of_hbm_peak": achieved / peaks["hbm_gbs"],
+                                    "note": "BPR-type samples gather and RED-update three full rows (no run tiles): the algorithmic bytes ARE the L2 row traffic"}
+                                   if (l2 and (bpr or gbpr)) else
+                                   {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                                    "algorithmic_bytes_per_unit": bytes_per}),
                       "loss_first_last": [losses[0], losses[-1]], "losses": losses, "safeguard": guard}), flush=True)
 
 
