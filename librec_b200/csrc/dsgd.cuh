@@ -93,6 +93,7 @@ struct DsgdState {
     // LRK_DSGD_TRACE=1: events around every sub-epoch kernel / ring exchange of the last epoch
     std::vector<cudaEvent_t> trace_ev;
     int trace = -1;
+    float* gather_buf = nullptr;        // lrk_get_factors: all ranks' ring buffers (world * buf_floats)
     float* q_ref = nullptr;             // BPR: the item factors at the start of the current window (delta all-reduce)
     float* q_delta = nullptr;
     int64_t bpr_samples = 0;            // BPR: samples this rank draws per epoch = numRates * (its users / all users)
@@ -140,7 +141,7 @@ static void dsgd_release(lrk_handle_s* h) {
     DsgdState* s = (DsgdState*)h->dsgd;
     if (s) {
         dsgd_fused_release(&s->fused);
-        cudaFree(s->qbuf[0]); cudaFree(s->qbuf[1]); cudaFree(s->d_bounds); cudaFree(s->q_ref); cudaFree(s->q_delta);
+        cudaFree(s->qbuf[0]); cudaFree(s->qbuf[1]); cudaFree(s->d_bounds); cudaFree(s->q_ref); cudaFree(s->q_delta); cudaFree(s->gather_buf);
         delete s;
         h->dsgd = nullptr;
     }
@@ -798,9 +799,11 @@ static int dsgd_get_factors(lrk_handle_s* h, double* P, double* Q, double* bu, d
     const bool biased = h->cfg.model == LRK_MODEL_BIASEDMF;
     // all-gather the rotating buffers (every rank holds block `cur_block`), then unpack into Q32 / bi32
     // (BPR keeps the full item matrix on every rank: nothing to gather)
-    float* all = nullptr;
+    // (the gather buffer stays with the handle: cudaMalloc / cudaFree per call synchronise the device, and with the ring buffers
+    // exported over CUDA IPC a cudaFree was seen to take 60-100 ms now and then at 8 ranks)
     const bool gather = h->cfg.model != LRK_MODEL_BPR;
-    if (gather) LRK_CUDA(h, cudaMalloc((void**)&all, sizeof(float) * s->buf_floats * (size_t)world));
+    if (gather) { int rc_g = lrk_dev_alloc(h, &s->gather_buf, s->buf_floats * (size_t)world); if (rc_g) return rc_g; }
+    float* all = s->gather_buf;
     ncclResult_t nr = gather ? n->AllGather(s->qbuf[s->cur], all, s->buf_floats, ncclFloat32, (ncclComm_t)h->comm, st) : ncclSuccess;
     cudaError_t e = cudaSuccess;
     if (nr == ncclSuccess && gather) {
@@ -816,7 +819,6 @@ static int dsgd_get_factors(lrk_handle_s* h, double* P, double* Q, double* bu, d
         }
     }
     if (nr == ncclSuccess && e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(all);
     LRK_NCCL(h, nr);
     LRK_CUDA(h, e);
     f32_to_f64_rows_kernel<<<lrk_ceil_div(U * h->k, 256), 256, 0, st>>>(h->P32, h->P64, U, h->k, h->ld); LRK_LAUNCH_CHECK(h);
