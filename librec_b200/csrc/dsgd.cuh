@@ -409,8 +409,9 @@ static int dsgd_fused_map(lrk_handle_s* h, DsgdState* s) {
     // or all of them keep the ncclSend / ncclRecv ring -- a split decision would leave a kernel spinning on a flag nobody writes.
     cudaIpcMemHandle_t mine[3];
     memset(mine, 0, sizeof mine);
-    bool ok = cudaIpcGetMemHandle(&mine[0], s->qbuf[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine[1], s->qbuf[1]) == cudaSuccess &&
-              cudaIpcGetMemHandle(&mine[2], f->d_flags) == cudaSuccess;
+    const bool local = h->same_process && h->siblings != nullptr;      // ranks of one process (multi handle): peer pointers, no IPC
+    bool ok = local || (cudaIpcGetMemHandle(&mine[0], s->qbuf[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine[1], s->qbuf[1]) == cudaSuccess &&
+                        cudaIpcGetMemHandle(&mine[2], f->d_flags) == cudaSuccess);
     cudaGetLastError();
     const size_t hb = sizeof(cudaIpcMemHandle_t) * 3;
     uint8_t *d_mine = nullptr, *d_all = nullptr;
@@ -437,8 +438,25 @@ static int dsgd_fused_map(lrk_handle_s* h, DsgdState* s) {
     };
     const int prev = dsgd_send_peer(rank, world), next = dsgd_recv_peer(rank, world);
     void *q0 = nullptr, *q1 = nullptr, *pf = nullptr, *nf = nullptr;
-    ok = ok && open(prev, 0, &q0) && open(prev, 1, &q1) && open(prev, 2, &pf);
-    if (ok) { if (next == prev) nf = pf; else ok = open(next, 2, &nf); }
+    if (local) {
+        // the all-gather above completed, so every rank of this process has allocated its flags (it enqueues after allocating)
+        auto peer = [&](int r) -> bool {
+            const int dev = h->siblings[r]->cfg.device;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, h->cfg.device, dev) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(dev, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return false; }
+            cudaGetLastError();
+            return true;
+        };
+        DsgdState* ps = (DsgdState*)h->siblings[prev]->dsgd;
+        DsgdState* ns = (DsgdState*)h->siblings[next]->dsgd;
+        ok = ps && ns && ps->fused.d_flags && ns->fused.d_flags && peer(prev) && peer(next);
+        if (ok) { q0 = ps->qbuf[0]; q1 = ps->qbuf[1]; pf = ps->fused.d_flags; nf = ns->fused.d_flags; }
+    } else {
+        ok = ok && open(prev, 0, &q0) && open(prev, 1, &q1) && open(prev, 2, &pf);
+        if (ok) { if (next == prev) nf = pf; else ok = open(next, 2, &nf); }
+    }
     // all-reduce the verdict (min); it doubles as the barrier after which every rank's flags are zeroed
     int verdict = ok ? 1 : 0;
     LRK_CUDA(h, cudaMemcpyAsync(f->d_abort, &verdict, sizeof(int), cudaMemcpyHostToDevice, st));
@@ -516,7 +534,7 @@ static int dsgd_fused_epoch(lrk_handle_s* h, DsgdState* s, float lr, float reg_u
     DsgdFused* f = &s->fused;
     if (f->enabled < 0) { const char* e = getenv("LRK_DSGD_FUSED"); f->enabled = (e && atoi(e) == 0) ? 0 : 1; }     // default on
     const int world = h->world;
-    if (!f->enabled || h->same_process || world < 2 || world > LRK_FUSED_MAX_WORLD || h->cfg.model == LRK_MODEL_BPR ||
+    if (!f->enabled || world < 2 || world > LRK_FUSED_MAX_WORLD || h->cfg.model == LRK_MODEL_BPR ||
         h->cfg.update_mode != LRK_UPDATE_ATOMIC || h->V != 1 || (h->G < 16 && !h->group))
         return LRK_OK;
     int coop = 0;

@@ -1082,7 +1082,7 @@ int lrk_create_multi(const lrk_config_t* cfg, const int32_t* devices, int32_t n_
         lrk_config_t c = *cfg;
         c.device = devices[g];
         rc = lrk_create(&c, &ms->child[(size_t)g]);
-        if (rc == LRK_OK) ms->child[(size_t)g]->same_process = true;    // no CUDA IPC between the ranks of one process
+        if (rc == LRK_OK) { ms->child[(size_t)g]->same_process = true; ms->child[(size_t)g]->siblings = ms->child.data(); }   // peer pointers instead of CUDA IPC
     }
     for (int g = 0; g < n_devices; ++g) {
         LrkWorker* w = new LrkWorker();

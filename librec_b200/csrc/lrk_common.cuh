@@ -84,7 +84,9 @@ struct lrk_handle_s {
 
     // single-process multi-GPU parent (multi.cuh): no device state of its own, forwards to one child per device
     void* multi = nullptr;
-    bool same_process = false; // DSGD child of a multi handle: its ring neighbours live in this process (CUDA IPC cannot map them)
+    bool same_process = false; // DSGD child of a multi handle: its ring neighbours live in this process (CUDA IPC cannot map them;
+                               // the in-kernel ring takes their buffers by plain peer pointers instead)
+    lrk_handle_s** siblings = nullptr;   // same_process: the handles of all ranks, indexed by rank
     bool score_only = false;   // scoring child of a multi handle: the train CSR is kept for the top-N mask only (no COO stream)
 
     // DSGD

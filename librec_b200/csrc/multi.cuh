@@ -4,7 +4,8 @@
 // be reached through its plugin API.  A multi handle takes and returns the FULL matrices exactly like a single-device handle and
 // does the sharding inside: users are cut into n contiguous blocks, one per device; every device gets a DSGD child handle (rank g
 // of an n-rank NCCL communicator created inside this process) driven by its own host thread, because the children's calls contain
-// collectives that all ranks must enter together.  Training = the children's DSGD epoch (csrc/dsgd.cuh); top-N = one scoring
+// collectives that all ranks must enter together.  Training = the children's DSGD epoch (csrc/dsgd.cuh; the in-kernel ring takes the
+// neighbours' buffers by peer pointers, CUDA IPC cannot map memory of the same process); top-N = one scoring
 // handle per device over its user block with the full item matrix, no collective.
 #pragma once
 #include "lrk_common.cuh"

@@ -82,6 +82,7 @@ static int aobpr_prepare(lrk_handle_s* h, AobprState* a) {
     LRK_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, a->tmp_bytes, a->d_keys, a->d_keys2, a->d_vals, a->d_rank, (int)n, 0, 40, st));
     LRK_CUDA(h, cudaMalloc(&a->d_tmp, a->tmp_bytes + 16));
     LRK_CUDA(h, cudaMemsetAsync(a->d_var, 0, sizeof(float) * (size_t)h->ld, st));
+    LRK_CUDA(h, cudaMemsetAsync(a->d_rank, 0, sizeof(int32_t) * (size_t)I * h->ld, st));   // padded factors (never drawn unless p_u is all zero) rank item 0
     // cumulative rank distribution in double on the host (I values), float on the device
     std::vector<double> pro((size_t)I);
     double sum = 0.0;
