@@ -1,6 +1,6 @@
 // One persistent kernel per DSGD epoch with the ring exchange inside it -- the default of the rating models between processes
 // (LRK_DSGD_FUSED=0 selects the sub-epoch loop of dsgd.cuh: SGD kernel + grouped ncclSend/ncclRecv per stratum; that loop is also
-// what BPR, the single-process multi handle and communicators without working CUDA IPC use).  r02, 8 x B200, config C4 (PMF k=128,
+// what BPR and communicators without working CUDA IPC / peer access use).  r02, 8 x B200, config C4 (PMF k=128,
 // Netflix shape, strong scaling): 2.04 ms per epoch = 49.3 G updates/s against 2.17 ms = 46.4 G with the NCCL ring, parity checks
 // (conflict-free epoch = oracle to 2e-8, C1 within 1e-3) green at 2 and 8 ranks (profiles/r02_*).
 //
@@ -9,7 +9,7 @@
 // copy kernels cannot overlap with the epoch kernel (it occupies every SM), so a second stream does not help.
 //
 // How: every rank maps its ring neighbours' block buffers and flag words with CUDA IPC (handles exchanged once through the NCCL
-// communicator).  The epoch kernel is launched cooperatively and loops over the G strata:
+// communicator; the ranks of a single-process multi handle take them as plain peer pointers, csrc/multi.cuh).  The epoch kernel is launched cooperatively and loops over the G strata:
 //   wait   until the block for this stratum has arrived in my buffer b        (ready[b]     >= seq, written by rank+1)
 //   train  the stratum's COO segment against buffer b                          (sgd_rating_body.inc, the same tile code)
 //   grid.sync
