@@ -180,6 +180,60 @@ def run_svdpp(steps, warmup, oracle_epochs=2):
                       "row_transfers_per_rating": "3 gathers (y_j, q_i, y_j) + 2 REDs (q_i, y_j); the user side is register-resident"}), flush=True)
 
 
+def run_als(model_name, k, steps, warmup, shape="ml-20m", oracle_parity=True):
+    """N3: WRMF (wrmf-test.properties: k=20, reg 0.01, coefficient 4) / eALS (eals-test.properties: k=200, reg 0.01, judge 1,
+    coefficient 1) on the ML-20M shape.  The first iteration runs beside the oracle's and the factors are compared BITWISE; then
+    `steps` timed iterations."""
+    import time
+    import torch
+    from librec_b200 import capi, synth
+    from oracle import oracle as O
+    d = synth.make_ratings(shape)
+    U, I, nnz = d["U"], d["I"], int(d["rowptr"][-1])
+    reg = 0.01
+    wrmf = model_name == "wrmf"
+    lut = {float(v): (O.lib().lro_wrmf_weight(float(v), 4.0) if wrmf else O.lib().lro_eals_weight(float(v), 1.0, 1)) for v in np.unique(d["val"])}
+    val = np.array([lut[float(v)] for v in d["val"]])
+    P, Q, _, _ = synth.init_factors(U, I, k, 11, False)
+    if not wrmf:
+        P = np.zeros_like(P)                                   # EALSRecommender.java:125
+    conf = np.ones(I)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    out = {"config": "N3-" + ("WRMF" if wrmf else "eALS"), "metric": "ALS train entries/s (one iteration = both sides)", "unit": "entries/s", "n_gpus": 1,
+           "workload": "%s k=%d, synthetic %s shape (%d x %d, %d ratings), reg %g" % (model_name, k, shape, U, I, nnz, reg)}
+    with capi.Handle(capi.MODEL_WRMF if wrmf else capi.MODEL_EALS, k, seed=1) as h:
+        h.set_train_csr(U, I, d["rowptr"], d["col"], val)
+        if not wrmf:
+            h.set_matrix("eals.confidences", conf)
+        h.set_factors(P, Q)
+        h.sgd_epoch(0.0, reg, reg, 0.0, 1)
+        first_ms = h.last_epoch_ms()
+        if oracle_parity:
+            gP, gQ, _, _ = h.get_factors()
+            oP, oQ = P.copy(), Q.copy()
+            t0 = time.perf_counter()
+            if wrmf:
+                O.lib().lro_wrmf_epoch(U, I, d["rowptr"], d["col"], val, k, oP, oQ, reg, reg)
+            else:
+                O.lib().lro_eals_epoch(U, I, d["rowptr"], d["col"], val, k, oP, oQ, conf, reg, reg)
+            t_or = time.perf_counter() - t0
+            out["parity"] = {"factors_bit_identical_after_1_iteration": bool(np.array_equal(gP, oP) and np.array_equal(gQ, oQ)),
+                             "max_abs_diff": float(max(np.abs(gP - oP).max(), np.abs(gQ - oQ).max()))}
+            out["oracle_entries_per_s_one_core"] = nnz / t_or
+            out["oracle_s_per_iteration"] = t_or
+        ms = []
+        for s in range(warmup + steps):
+            flush.zero_(); torch.cuda.synchronize()
+            h.sgd_epoch(0.0, reg, reg, 0.0, s + 2)
+            if s >= warmup:
+                ms.append(h.last_epoch_ms())
+        gP, gQ, _, _ = h.get_factors()
+    kms = float(np.mean(ms))
+    out.update({"value": nnz / (kms * 1e-3), "steps": steps, "warmup": warmup, "ms_per_step": kms, "first_iteration_ms": first_ms,
+                "finite": bool(np.isfinite(gP).all() and np.isfinite(gQ).all())})
+    print(json.dumps(out), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
@@ -201,6 +255,11 @@ if __name__ == "__main__":
         run("N3-AoBPR", "aobpr", "ml-20m", 10, 0.01, 0.01, a.steps, a.warmup)       # aobpr-test-like: lambda 0.05 * numItems
     if a.only == "svdpp":
         run_svdpp(a.steps, a.warmup)
+    if a.only in ("als", "wrmf"):
+        run_als("wrmf", 20, a.steps, a.warmup)
+    if a.only in ("als", "eals"):
+        run_als("eals", 32, a.steps, a.warmup)                              # bitwise parity at scale (the oracle needs 40 s at k=32, 4 min at k=200)
+        run_als("eals", 200, a.steps, a.warmup, oracle_parity=False)        # eals-test.properties' k, timing only
     if a.only == "gbpr":
         # gbpr defaults: rho 1.5, group size 2.  GBPR adds the SUM of an epoch's factor updates at its end (GBPRRecommender.java:167-168),
         # so its effective step grows with the samples per row: lr 0.05 is fine on ml-100k (80 k samples), turns around after 4 epochs

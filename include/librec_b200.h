@@ -69,7 +69,17 @@ typedef enum {
     /* aobpr -> recommender/cf/ranking/AoBPRRecommender.java:60-200: BPR with adaptive oversampling of the
      * negative item; rec.item.distribution.parameter through lrk_set_param("aobpr.lambda") (required, as in the reference);
      * single GPU; scoring and lrk_bpr_peek_samples as for BPR */
-    LRK_MODEL_AOBPR = 6
+    LRK_MODEL_AOBPR = 6,
+    /* wrmf -> recommender/cf/ranking/WRMFRecommender.java:74-166: alternating least squares with the
+     * reference's Gauss-Jordan inverse (math/structure/DenseMatrix.java:362-437).  lrk_set_train_csr takes the WEIGHTED values
+     * (weightMatrix() stays in the shim's setup()); lrk_sgd_epoch = one iteration (lr and reg_b ignored, loss 0 -- the class
+     * never assigns it); fp64 in the reference's operation order: factors BIT-identical to the reference's; rec.factor.number <= 112;
+     * single GPU; scoring as for PMF */
+    LRK_MODEL_WRMF = 7,
+    /* eals -> recommender/cf/ranking/EALSRecommender.java:114-214: element-wise ALS.  Weighted values as
+     * for WRMF; the item confidences (:65-83, computed in the shim's setup()) through lrk_set_matrix("eals.confidences");
+     * the caller hands over zero user factors (:125 replaces them).  Bit-identical like WRMF; single GPU */
+    LRK_MODEL_EALS = 8
 } lrk_model;
 
 /* how concurrent updates to one factor row are combined */
@@ -146,7 +156,8 @@ LRK_API int lrk_get_factors(lrk_handle_t h, double* P, double* Q, double* bu, do
 LRK_API int lrk_set_param(lrk_handle_t h, const char* name, double value);
 
 /* model matrices beyond P / Q / biases, row-major doubles like lrk_set_factors (call after it):
- *   "svdpp.y"  impItemFactors, numItems x numFactors (SVDPlusPlusRecommender.java:55-56) */
+ *   "svdpp.y"  impItemFactors, numItems x numFactors (SVDPlusPlusRecommender.java:55-56)
+ *   "eals.confidences"  confidences, numItems doubles (EALSRecommender.java:50,65-83); needs only lrk_set_train_csr before it */
 LRK_API int lrk_set_matrix(lrk_handle_t h, const char* name, const double* values);
 LRK_API int lrk_get_matrix(lrk_handle_t h, const char* name, double* values);
 

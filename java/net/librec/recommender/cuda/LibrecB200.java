@@ -8,7 +8,8 @@ import java.nio.ByteBuffer;
 final class LibrecB200 {
     static { System.loadLibrary("librec_b200_jni"); }
 
-    static final int MODEL_BIASEDMF = 0, MODEL_PMF = 1, MODEL_BPR = 2, MODEL_RANKSGD = 3, MODEL_GBPR = 4, MODEL_SVDPP = 5, MODEL_AOBPR = 6;
+    static final int MODEL_BIASEDMF = 0, MODEL_PMF = 1, MODEL_BPR = 2, MODEL_RANKSGD = 3, MODEL_GBPR = 4, MODEL_SVDPP = 5, MODEL_AOBPR = 6,
+            MODEL_WRMF = 7, MODEL_EALS = 8;
     static final int UPDATE_ATOMIC = 0, UPDATE_HOGWILD = 1, UPDATE_REFERENCE_ORDER = 2;
     static final int ERR_DIVERGED = -5;
 

@@ -28,6 +28,7 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
     @Override
     protected void setup() throws LibrecException {
         super.setup();                                     // MatrixFactorizationRecommender.java:67-94 (Gaussian init on the JVM RNG)
+        beforeStage();                                     // WRMF / eALS: weightMatrix() rewrites the train values first
         int device = conf.getInt("rec.cuda.device", 0);
         int mode = "reference".equals(conf.get("rec.cuda.order", "shuffled"))
                 ? LibrecB200.UPDATE_REFERENCE_ORDER : LibrecB200.UPDATE_ATOMIC;
@@ -56,7 +57,14 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
         rowptr.putLong(8 * numUsers, off);
         check(LibrecB200.setTrainCsr(handle, numUsers, numItems, rowptr, col, val));
         LibrecB200.hostFree(rowptr); LibrecB200.hostFree(col); LibrecB200.hostFree(val);
+        afterStage();
     }
+
+    /** hooks around the staging of the train matrix (WRMF / eALS: weights before it, item confidences after it) */
+    protected void beforeStage() throws LibrecException { }
+    protected void afterStage() throws LibrecException { }
+    /** runs first in trainModel() (eALS replaces userFactors by a zero matrix, EALSRecommender.java:125) */
+    protected void beforeTrainModel() throws LibrecException { }
 
     /** hooks for models with matrices beyond P / Q / biases (SVD++: impItemFactors) */
     protected void afterSetFactors() throws LibrecException { }
@@ -86,6 +94,7 @@ abstract class MatrixFactorizationCudaRecommender extends MatrixFactorizationRec
     /** trainModel(): the iteration loop, isConverged and updateLRate stay in Java (BiasedMFRecommender.java:101-105). */
     @Override
     protected void trainModel() throws LibrecException {
+        beforeTrainModel();
         ByteBuffer P = flatten(userFactors), Q = flatten(itemFactors);
         ByteBuffer bu = userBiases == null ? null : ByteBuffer.allocateDirect(8 * numUsers).order(ByteOrder.nativeOrder());
         ByteBuffer bi = itemBiases == null ? null : ByteBuffer.allocateDirect(8 * numItems).order(ByteOrder.nativeOrder());

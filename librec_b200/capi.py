@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _build
 
-MODEL_BIASEDMF, MODEL_PMF, MODEL_BPR, MODEL_RANKSGD, MODEL_GBPR, MODEL_SVDPP, MODEL_AOBPR = 0, 1, 2, 3, 4, 5, 6
+MODEL_BIASEDMF, MODEL_PMF, MODEL_BPR, MODEL_RANKSGD, MODEL_GBPR, MODEL_SVDPP, MODEL_AOBPR, MODEL_WRMF, MODEL_EALS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 UPDATE_ATOMIC, UPDATE_HOGWILD, UPDATE_REFERENCE_ORDER = 0, 1, 2
 OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NOMEM, ERR_DIVERGED = 0, -1, -2, -3, -4, -5
 

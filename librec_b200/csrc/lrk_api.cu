@@ -9,6 +9,7 @@
 #include "sgd_gbpr.cuh"
 #include "sgd_svdpp.cuh"
 #include "sgd_aobpr.cuh"
+#include "als.cuh"
 #include <chrono>
 #include "topn_exact.cuh"
 #include "topn_tc.cuh"
@@ -266,8 +267,10 @@ int lrk_create(const lrk_config_t* cfg, lrk_handle_t* out) {
     *out = nullptr;
     if (cfg->num_factors < 1 || cfg->num_factors > LRK_MAX_FACTORS)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "num_factors must be in 1..256", __FILE__, __LINE__);
-    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_AOBPR)
+    if (cfg->model < LRK_MODEL_BIASEDMF || cfg->model > LRK_MODEL_EALS)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown model", __FILE__, __LINE__);
+    if (cfg->model == LRK_MODEL_WRMF && cfg->num_factors > ALS_MAX_K)
+        return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "WRMF on the device needs rec.factor.number <= 112 (the Gauss-Jordan step lives in shared memory)", __FILE__, __LINE__);
     if (cfg->update_mode < LRK_UPDATE_ATOMIC || cfg->update_mode > LRK_UPDATE_REFERENCE_ORDER)
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create", "unknown update_mode", __FILE__, __LINE__);
     if (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER && !(cfg->model == LRK_MODEL_BIASEDMF || cfg->model == LRK_MODEL_PMF))
@@ -317,6 +320,7 @@ int lrk_destroy(lrk_handle_t h) {
     gbpr_release((GbprState*)h->gbpr);
     svdpp_release((SvdppState*)h->svdpp);
     aobpr_release((AobprState*)h->aobpr);
+    als_release((AlsState*)h->als);
     dsgd_release(h);
     topn_tc_release(h);
     exact_release((ExactSchedule*)h->exact);
@@ -417,6 +421,7 @@ int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowpt
     }
     if (h->cfg.model == LRK_MODEL_GBPR && (rc = gbpr_stage(h))) return rc;
     if (h->cfg.model == LRK_MODEL_SVDPP && (rc = svdpp_stage(h, val))) return rc;
+    if (lrk_is_als(h) && (rc = als_stage(h, val))) return rc;
     h->has_train = true;
     topn_tc_invalidate(h);
     return LRK_OK;
@@ -454,7 +459,7 @@ int lrk_set_factors(lrk_handle_t h, const double* P, const double* Q, const doub
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I * ld, 256), 256, 0, st>>>(h->Q64, h->Q32, I, k, ld); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(U, 256), 256, 0, st>>>(h->bu64, h->bu32, U, 1, 1); LRK_LAUNCH_CHECK(h);
     f64_to_f32_rows_kernel<<<lrk_ceil_div(I, 256), 256, 0, st>>>(h->bi64, h->bi32, I, 1, 1); LRK_LAUNCH_CHECK(h);
-    if (h->cfg.model != LRK_MODEL_BPR && h->cfg.model != LRK_MODEL_GBPR && h->cfg.model != LRK_MODEL_SVDPP && h->cfg.model != LRK_MODEL_AOBPR && (rc = refresh_user_norm2(h, true))) return rc;
+    if (h->cfg.model != LRK_MODEL_BPR && h->cfg.model != LRK_MODEL_GBPR && h->cfg.model != LRK_MODEL_SVDPP && h->cfg.model != LRK_MODEL_AOBPR && !lrk_is_als(h) && (rc = refresh_user_norm2(h, true))) return rc;
     if (h->aobpr) ((AobprState*)h->aobpr)->count = 0;                 // a new trainModel(): countIter starts at 0 (AoBPRRecommender.java:88)
     if (h->h_pnorm2) { h->pnorm2_prev = 0.f; h->pnorm2_host = *h->h_pnorm2; }
     LRK_CUDA(h, cudaStreamSynchronize(st));   // host buffers may be reused by the caller on return
@@ -529,6 +534,7 @@ int lrk_sgd_epoch(lrk_handle_t h, float lr, float reg_u, float reg_i, double reg
     if (h->world > 1) return dsgd_epoch(h, lr, reg_u, reg_i, reg_b, epoch_idx, loss_out);
     if (h->cfg.model == LRK_MODEL_GBPR) return gbpr_epoch(h, lr, reg_u, reg_i, reg_b, epoch_idx, loss_out);
     if (h->cfg.model == LRK_MODEL_SVDPP) return svdpp_epoch(h, lr, reg_u, reg_i, reg_b, loss_out);
+    if (lrk_is_als(h)) { topn_tc_invalidate(h); return als_epoch(h, reg_u, reg_i, loss_out); }
     cudaStream_t st = h->stream;
     if (h->cfg.update_mode == LRK_UPDATE_REFERENCE_ORDER) {
         // fp64 masters are the working set in this mode
@@ -678,6 +684,18 @@ int lrk_set_param(lrk_handle_t h, const char* name, double value) {
 int lrk_set_matrix(lrk_handle_t h, const char* name, const double* values) {
     LRK_REQUIRE(h, h != nullptr && name != nullptr && values != nullptr, "NULL argument");
     LRK_NOT_MULTI(h, "lrk_set_matrix");
+    if (!strcmp(name, "eals.confidences") && h->cfg.model == LRK_MODEL_EALS) {
+        LRK_REQUIRE(h, h->has_train, "call lrk_set_train_csr first (it fixes numItems)");
+        LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+        AlsState* a = (AlsState*)h->als;
+        LRK_REQUIRE(h, a != nullptr, "ALS state missing");
+        int rc_a;
+        if ((rc_a = lrk_dev_alloc(h, &a->d_conf, (size_t)h->I))) return rc_a;
+        LRK_CUDA(h, cudaMemcpyAsync(a->d_conf, values, sizeof(double) * (size_t)h->I, cudaMemcpyHostToDevice, h->stream));
+        LRK_CUDA(h, cudaStreamSynchronize(h->stream));
+        a->has_conf = true;
+        return LRK_OK;
+    }
     LRK_REQUIRE(h, !strcmp(name, "svdpp.y") && h->cfg.model == LRK_MODEL_SVDPP, "unknown matrix name for this model");
     LRK_REQUIRE(h, h->has_factors, "call lrk_set_factors first");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -698,6 +716,14 @@ int lrk_set_matrix(lrk_handle_t h, const char* name, const double* values) {
 int lrk_get_matrix(lrk_handle_t h, const char* name, double* values) {
     LRK_REQUIRE(h, h != nullptr && name != nullptr && values != nullptr, "NULL argument");
     LRK_NOT_MULTI(h, "lrk_get_matrix");
+    if (!strcmp(name, "eals.confidences") && h->cfg.model == LRK_MODEL_EALS) {
+        AlsState* a = (AlsState*)h->als;
+        LRK_REQUIRE(h, a != nullptr && a->has_conf, "matrix not set");
+        LRK_CUDA(h, cudaSetDevice(h->cfg.device));
+        LRK_CUDA(h, cudaMemcpyAsync(values, a->d_conf, sizeof(double) * (size_t)h->I, cudaMemcpyDeviceToHost, h->stream));
+        LRK_CUDA(h, cudaStreamSynchronize(h->stream));
+        return LRK_OK;
+    }
     LRK_REQUIRE(h, !strcmp(name, "svdpp.y") && h->cfg.model == LRK_MODEL_SVDPP, "unknown matrix name for this model");
     SvdppState* g = (SvdppState*)h->svdpp;
     LRK_REQUIRE(h, g != nullptr && g->has_y, "matrix not set");
@@ -1059,7 +1085,7 @@ int lrk_comm_init(lrk_handle_t h, int32_t rank, int32_t world, const uint8_t uni
     LRK_REQUIRE(h, h != nullptr, "handle is NULL");
     LRK_NOT_MULTI(h, "lrk_comm_init");
     LRK_REQUIRE(h, h->cfg.update_mode != LRK_UPDATE_REFERENCE_ORDER, "reference-order mode is single-GPU");
-    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_RANKSGD && h->cfg.model != LRK_MODEL_GBPR && h->cfg.model != LRK_MODEL_SVDPP && h->cfg.model != LRK_MODEL_AOBPR, "RankSGD, GBPR, SVD++ and AoBPR are single-GPU in this build");
+    LRK_REQUIRE(h, h->cfg.model != LRK_MODEL_RANKSGD && h->cfg.model != LRK_MODEL_GBPR && h->cfg.model != LRK_MODEL_SVDPP && h->cfg.model != LRK_MODEL_AOBPR && !lrk_is_als(h), "RankSGD, GBPR, SVD++, AoBPR, WRMF and eALS are single-GPU in this build");
     return dsgd_comm_init(h, rank, world, unique_id);
 }
 
@@ -1069,7 +1095,7 @@ int lrk_create_multi(const lrk_config_t* cfg, const int32_t* devices, int32_t n_
     if (n_devices < 1 || n_devices > 8) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "1 to 8 devices", __FILE__, __LINE__);
     for (int a = 0; a < n_devices; ++a) for (int b = a + 1; b < n_devices; ++b)
         if (devices[a] == devices[b]) return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "a device is listed twice", __FILE__, __LINE__);
-    if (n_devices > 1 && (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER || cfg->model == LRK_MODEL_RANKSGD || cfg->model == LRK_MODEL_GBPR || cfg->model == LRK_MODEL_SVDPP || cfg->model == LRK_MODEL_AOBPR))
+    if (n_devices > 1 && (cfg->update_mode == LRK_UPDATE_REFERENCE_ORDER || cfg->model == LRK_MODEL_RANKSGD || cfg->model == LRK_MODEL_GBPR || cfg->model == LRK_MODEL_SVDPP || cfg->model == LRK_MODEL_AOBPR || cfg->model == LRK_MODEL_WRMF || cfg->model == LRK_MODEL_EALS))
         return lrk_fail(nullptr, LRK_ERR_INVALID, "lrk_create_multi", "reference-order mode, RankSGD, GBPR, SVD++ and AoBPR are single-GPU", __FILE__, __LINE__);
     lrk_handle_s* h = new (std::nothrow) lrk_handle_s();
     MultiState* ms = new (std::nothrow) MultiState();

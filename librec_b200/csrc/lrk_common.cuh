@@ -78,6 +78,7 @@ struct lrk_handle_s {
     void* gbpr = nullptr;     // GbprState* (sgd_gbpr.cuh)
     void* svdpp = nullptr;    // SvdppState* (sgd_svdpp.cuh)
     void* aobpr = nullptr;    // AobprState* (sgd_aobpr.cuh)
+    void* als = nullptr;      // AlsState* (als.cuh): WRMF / eALS
 
     // reference-order (wavefront) schedule, see sgd_exact.cuh
     void* exact = nullptr;
@@ -176,5 +177,7 @@ static inline int lrk_scratch_begin(lrk_handle_s* h, size_t bytes, LrkScratch* o
 static inline int lrk_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // models whose prediction adds biases (GBPR: item biases only, its user biases stay zero): b_i + p_u.q_i (+ b_u + mu)
 static inline bool lrk_has_bias(const lrk_handle_s* h) { return h->cfg.model == LRK_MODEL_BIASEDMF || h->cfg.model == LRK_MODEL_GBPR || h->cfg.model == LRK_MODEL_SVDPP; }
+// WRMF / eALS: alternating least squares on the fp64 masters (als.cuh); lrk_sgd_epoch = one ALS iteration
+static inline bool lrk_is_als(const lrk_handle_s* h) { return h->cfg.model == LRK_MODEL_WRMF || h->cfg.model == LRK_MODEL_EALS; }
 // BiasedMF / PMF: one update per train rating with the rating as target (item-run tiles, staleness-aware step)
 static inline bool lrk_is_rating_model(const lrk_handle_s* h) { return h->cfg.model == LRK_MODEL_BIASEDMF || h->cfg.model == LRK_MODEL_PMF; }

@@ -1068,6 +1068,206 @@ LRO_API double lro_gbpr_epoch(int32_t U, int32_t I, const int64_t* rowptr, const
     return loss;
 }
 
+// -------------------------------------------------------------------------------------
+// ALS siblings: WRMF and eALS.  Both are deterministic (no RNG inside trainModel; every row's update
+// reads only the OTHER side's matrix, so the reference's parallelStream order does not matter), which makes them the two models
+// of the path whose device results can be held to BIT equality with this restatement.
+//
+// math/structure/DenseMatrix.java:362-437 -- inverse(): Gauss-Jordan with partial pivoting on a clone, the inverse built in a
+// second matrix.  Quirks kept: the pivot search takes the FIRST strictly-largest |a_jr| (NaN never wins); "no pivot" returns the
+// half-built inverse as it stands; a row swap exchanges only columns >= r of the clone; the pivot row is divided (not multiplied
+// by a reciprocal); the elimination factor is read before the row is touched.
+static void lro_dense_inverse(const double* a, int32_t n, double* inv) {
+    for (int32_t r = 0; r < n; ++r) for (int32_t c = 0; c < n; ++c) inv[(size_t)r * n + c] = r == c ? 1.0 : 0.0;
+    if (n == 1) { inv[0] = 1.0 / a[0]; return; }
+    std::vector<double> m(a, a + (size_t)n * n);
+    for (int32_t r = 0; r < n; ++r) {
+        double mag = 0.0;
+        int32_t pivot = -1;
+        for (int32_t j = r; j < n; ++j) {
+            const double mag2 = fabs(m[(size_t)j * n + r]);
+            if (mag2 > mag) { mag = mag2; pivot = j; }
+        }
+        if (pivot == -1 || mag == 0) return;
+        if (pivot != r) {
+            for (int32_t c = r; c < n; ++c) std::swap(m[(size_t)r * n + c], m[(size_t)pivot * n + c]);
+            for (int32_t c = 0; c < n; ++c) std::swap(inv[(size_t)r * n + c], inv[(size_t)pivot * n + c]);
+        }
+        mag = m[(size_t)r * n + r];
+        for (int32_t c = r; c < n; ++c) m[(size_t)r * n + c] = m[(size_t)r * n + c] / mag;
+        for (int32_t c = 0; c < n; ++c) inv[(size_t)r * n + c] = inv[(size_t)r * n + c] / mag;
+        for (int32_t r2 = 0; r2 < n; ++r2) {
+            if (r == r2) continue;
+            const double mag2 = m[(size_t)r2 * n + r];
+            for (int32_t c = r; c < n; ++c) m[(size_t)r2 * n + c] = m[(size_t)r2 * n + c] - mag2 * m[(size_t)r * n + c];
+            for (int32_t c = 0; c < n; ++c) inv[(size_t)r2 * n + c] = inv[(size_t)r2 * n + c] - mag2 * inv[(size_t)r * n + c];
+        }
+    }
+}
+LRO_API void lro_dense_inverse_export(const double* a, int32_t n, double* inv) { lro_dense_inverse(a, n, inv); }
+
+// M^T M through DenseMatrix.transpose().times(M) (DenseMatrix.java:229-249,276-286; DenseVector.java:104-111): entry (r, c) is
+// the dot of row r of M^T with column c of M, summed over the rows of M in order, starting from 0.0
+static void lro_gram(const double* M, int64_t n, int32_t k, double* out) {
+    for (int32_t r = 0; r < k; ++r)
+        for (int32_t c = 0; c < k; ++c) {
+            double v = 0.0;
+            for (int64_t i = 0; i < n; ++i) v += M[i * k + c] * M[i * k + r];
+            out[(size_t)r * k + c] = v;
+        }
+}
+
+// WRMFRecommender.weight (recommender/cf/ranking/WRMFRecommender.java:58-61): log(1 + 10^coef * value); coef is a float.
+// The reference calls Math.log / Math.pow (intrinsics, allowed to differ from StrictMath by an ulp); the device never computes it --
+// the weighting stays in the Java shim's setup(), like weightMatrix() (:63-72).
+LRO_API double lro_wrmf_weight(double value, float coef) { return fdlibm_log(1.0 + pow(10.0, (double)coef) * value); }
+
+// one half-iteration of WRMFRecommender.trainModel (:93-126 users, :129-163 items): for every row of `ptr/idx/w` (the weighted train
+// matrix by rows, or by columns for the item step) solve (F^T F + reg [EVERY entry, :110] + sum_e w_e f_e f_e^T) x = sum_e (w_e + 1) f_e
+static void lro_wrmf_side(int32_t n_rows, const int64_t* ptr, const int32_t* idx, const double* w, int32_t k, const double* F, int64_t n_other,
+                          double* X, double reg) {
+    std::vector<double> G((size_t)k * k), A((size_t)k * k), W((size_t)k * k), b((size_t)k);
+    lro_gram(F, n_other, k, G.data());
+    for (int32_t r = 0; r < n_rows; ++r) {
+        std::fill(b.begin(), b.end(), 0.0);
+        for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e) {
+            const double weight = w[e] + 1.0;
+            const double* f = F + (int64_t)idx[e] * k;
+            for (int32_t a = 0; a < k; ++a) b[(size_t)a] += f[a] * weight;
+        }
+        for (size_t t = 0; t < A.size(); ++t) A[t] = G[t] + reg;
+        for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e) {
+            const double weight = w[e];
+            const double* f = F + (int64_t)idx[e] * k;
+            for (int32_t a = 0; a < k; ++a) {
+                const double temp = f[a] * weight;
+                for (int32_t c = 0; c < k; ++c) A[(size_t)a * k + c] += temp * f[c];
+            }
+        }
+        lro_dense_inverse(A.data(), k, W.data());
+        for (int32_t a = 0; a < k; ++a) {                     // DenseMatrix.times(Vector): row(a).dot(b)
+            double v = 0.0;
+            for (int32_t c = 0; c < k; ++c) v += b[(size_t)c] * W[(size_t)a * k + c];
+            X[(int64_t)r * k + a] = v;
+        }
+    }
+}
+
+// one iteration of WRMFRecommender.trainModel; val = the WEIGHTED train values (weightMatrix has run); the model has no loss
+LRO_API void lro_wrmf_epoch(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val, int32_t k,
+                            double* P, double* Q, float regU_f, float regI_f) {
+    std::vector<int64_t> colptr, csc;
+    lro_csc_order(U, I, rowptr, col, colptr, csc);
+    const int64_t nnz = rowptr[U];
+    std::vector<int32_t> cusers((size_t)nnz);
+    std::vector<double> cval((size_t)nnz);
+    {
+        std::vector<int32_t> user_of((size_t)nnz);
+        for (int32_t u = 0; u < U; ++u) for (int64_t e = rowptr[u]; e < rowptr[u + 1]; ++e) user_of[(size_t)e] = u;
+        for (int64_t x = 0; x < nnz; ++x) { cusers[(size_t)x] = user_of[(size_t)csc[(size_t)x]]; cval[(size_t)x] = val[csc[(size_t)x]]; }
+    }
+    lro_wrmf_side(U, rowptr, col, val, k, Q, I, P, (double)regU_f);
+    lro_wrmf_side(I, colptr.data(), cusers.data(), cval.data(), k, P, U, Q, (double)regI_f);
+}
+
+// eALS (recommender/cf/ranking/EALSRecommender.java:53-112 setup, :114-214 trainModel).
+// confidences (:65-83): judge 0 or 2: c_i = overall * pop_i^ratio / sum_j pop_j^ratio with pop_i = |column i| / numRates; else 1.
+// weight(value) (:85-95): judge 1 or 2: 1 + coef * value (coef float); else 1.
+LRO_API void lro_eals_confidences(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, float ratio, float overall, int32_t judge,
+                                  double* conf) {
+    if (judge == 0 || judge == 2) {
+        std::vector<int64_t> cnt((size_t)I, 0);
+        const int64_t nnz = rowptr[U];
+        for (int64_t e = 0; e < nnz; ++e) cnt[(size_t)col[e]]++;
+        double sumPopularity = 0.0;
+        for (int32_t i = 0; i < I; ++i) {
+            const double alphaPopularity = pow((double)cnt[(size_t)i] * 1.0 / (double)nnz, (double)ratio);
+            conf[i] = (double)overall * alphaPopularity;
+            sumPopularity += alphaPopularity;
+        }
+        for (int32_t i = 0; i < I; ++i) conf[i] = conf[i] / sumPopularity;
+    } else
+        for (int32_t i = 0; i < I; ++i) conf[i] = 1;
+}
+LRO_API double lro_eals_weight(double value, float coef, int32_t judge) { return judge == 1 || judge == 2 ? 1.0 + (double)coef * value : 1.0; }
+
+// one iteration of EALSRecommender.trainModel (:127-211).  The caller zeroes P before the first one (:125 replaces userFactors by a
+// fresh zero matrix).  val = weighted train values; element-wise coordinate updates, every sum in the reference's order.
+LRO_API void lro_eals_epoch(int32_t U, int32_t I, const int64_t* rowptr, const int32_t* col, const double* val, int32_t k,
+                            double* P, double* Q, const double* conf, float regU_f, float regI_f) {
+    const double regUser = (double)regU_f, regItem = (double)regI_f;
+    const int64_t nnz = rowptr[U];
+    std::vector<int64_t> colptr, csc;
+    lro_csc_order(U, I, rowptr, col, colptr, csc);
+    std::vector<int32_t> user_of((size_t)nnz);
+    for (int32_t u = 0; u < U; ++u) for (int64_t e = rowptr[u]; e < rowptr[u + 1]; ++e) user_of[(size_t)e] = u;
+    std::vector<double> Sq((size_t)k * k), Sp((size_t)k * k), itemsPredictions((size_t)I, 0.0), usersPredictions((size_t)U, 0.0);
+    for (int32_t f1 = 0; f1 < k; ++f1)
+        for (int32_t f2 = 0; f2 <= f1; ++f2) {
+            double value = 0;
+            for (int32_t i = 0; i < I; ++i) value += conf[i] * Q[(int64_t)i * k + f1] * Q[(int64_t)i * k + f2];
+            Sq[(size_t)f1 * k + f2] = value;
+            Sq[(size_t)f2 * k + f1] = value;
+        }
+    for (int32_t u = 0; u < U; ++u) {
+        const int64_t b = rowptr[u], e = rowptr[u + 1];
+        double* pu = P + (int64_t)u * k;
+        for (int64_t x = b; x < e; ++x) {
+            const double* qi = Q + (int64_t)col[x] * k;
+            double d = 0.0;
+            for (int32_t f = 0; f < k; ++f) d += qi[f] * pu[f];
+            itemsPredictions[(size_t)col[x]] = d;
+        }
+        for (int32_t f = 0; f < k; ++f) {
+            double numer = 0, denom = regUser + Sq[(size_t)f * k + f];
+            for (int32_t f2 = 0; f2 < k; ++f2)
+                if (f != f2) numer -= pu[f2] * Sq[(size_t)f * k + f2];
+            for (int64_t x = b; x < e; ++x) {
+                const int32_t i = col[x];
+                const double weight = val[x], qf = Q[(int64_t)i * k + f];
+                itemsPredictions[(size_t)i] -= pu[f] * qf;
+                numer += (weight - (weight - conf[i]) * itemsPredictions[(size_t)i]) * qf;
+                denom += (weight - conf[i]) * qf * qf;
+            }
+            pu[f] = numer / denom;
+            for (int64_t x = b; x < e; ++x) {
+                const int32_t i = col[x];
+                itemsPredictions[(size_t)i] += pu[f] * Q[(int64_t)i * k + f];
+            }
+        }
+    }
+    lro_gram(P, U, k, Sp.data());
+    for (int32_t i = 0; i < I; ++i) {
+        const int64_t b = colptr[(size_t)i], e = colptr[(size_t)i + 1];
+        double* qi = Q + (int64_t)i * k;
+        for (int64_t x = b; x < e; ++x) {
+            const int32_t u = user_of[(size_t)csc[(size_t)x]];
+            const double* pu = P + (int64_t)u * k;
+            double d = 0.0;
+            for (int32_t f = 0; f < k; ++f) d += qi[f] * pu[f];
+            usersPredictions[(size_t)u] = d;
+        }
+        for (int32_t f = 0; f < k; ++f) {
+            double numer = 0, denom = conf[i] * Sp[(size_t)f * k + f] + regItem;
+            for (int32_t f2 = 0; f2 < k; ++f2)
+                if (f != f2) numer -= qi[f2] * Sp[(size_t)f2 * k + f];
+            numer *= conf[i];
+            for (int64_t x = b; x < e; ++x) {
+                const int32_t u = user_of[(size_t)csc[(size_t)x]];
+                const double weight = val[csc[(size_t)x]], pf = P[(int64_t)u * k + f];
+                usersPredictions[(size_t)u] -= pf * qi[f];
+                numer += (weight - (weight - conf[i]) * usersPredictions[(size_t)u]) * pf;
+                denom += (weight - conf[i]) * pf * pf;
+            }
+            qi[f] = numer / denom;
+            for (int64_t x = b; x < e; ++x) {
+                const int32_t u = user_of[(size_t)csc[(size_t)x]];
+                usersPredictions[(size_t)u] += P[(int64_t)u * k + f] * qi[f];
+            }
+        }
+    }
+}
+
 // AbstractRecommender.isConverged: recommender/AbstractRecommender.java:249-267.
 // returns 1 converged, 0 not, -1 = would throw LibrecException (NaN / Inf loss)
 LRO_API int32_t lro_is_converged(double last_loss, double loss, float* delta_out) {

@@ -109,6 +109,14 @@ def lib():
     L.lro_gbpr_epoch.restype = C.c_double
     L.lro_gbpr_epoch.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_int32, _f64p, _f64p, _f64p, C.c_float, C.c_float, C.c_float,
                                  C.c_double, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]
+    L.lro_dense_inverse_export.argtypes = [_f64p, C.c_int32, _f64p]
+    L.lro_wrmf_weight.restype = C.c_double
+    L.lro_wrmf_weight.argtypes = [C.c_double, C.c_float]
+    L.lro_wrmf_epoch.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _f64p, C.c_int32, _f64p, _f64p, C.c_float, C.c_float]
+    L.lro_eals_confidences.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, C.c_float, C.c_float, C.c_int32, _f64p]
+    L.lro_eals_weight.restype = C.c_double
+    L.lro_eals_weight.argtypes = [C.c_double, C.c_float, C.c_int32]
+    L.lro_eals_epoch.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _f64p, C.c_int32, _f64p, _f64p, _f64p, C.c_float, C.c_float]
     L.lro_ranksgd_item_probs.restype = C.c_int32
     L.lro_ranksgd_item_probs.argtypes = [C.c_int32, C.c_int32, _i64p, _i32p, _i32p, _f64p]
     L.lro_ranksgd_epoch.restype = C.c_double

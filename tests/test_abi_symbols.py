@@ -41,7 +41,7 @@ def test_no_cpu_fallback(capi):
 
 
 def test_bad_config_is_rejected(capi):
-    for kw in (dict(model=7, num_factors=8), dict(model=0, num_factors=0), dict(model=0, num_factors=257)):
+    for kw in (dict(model=9, num_factors=8), dict(model=0, num_factors=0), dict(model=0, num_factors=257)):
         with pytest.raises(capi.LibrecException):
             capi.Handle(kw["model"], kw["num_factors"])
 
@@ -63,16 +63,16 @@ def test_enum_values_agree_across_header_binding_and_java_shim(capi):
     src = open(os.path.join(ROOT, "include", "librec_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     header = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(LRK_[A-Z_]+)\s*=\s*(-?\d+)", src)}
-    for name in ("MODEL_BIASEDMF", "MODEL_PMF", "MODEL_BPR", "MODEL_RANKSGD", "MODEL_GBPR", "MODEL_SVDPP", "MODEL_AOBPR", "UPDATE_ATOMIC", "UPDATE_HOGWILD",
+    for name in ("MODEL_BIASEDMF", "MODEL_PMF", "MODEL_BPR", "MODEL_RANKSGD", "MODEL_GBPR", "MODEL_SVDPP", "MODEL_AOBPR", "MODEL_WRMF", "MODEL_EALS", "UPDATE_ATOMIC", "UPDATE_HOGWILD",
                  "UPDATE_REFERENCE_ORDER", "OK", "ERR_INVALID", "ERR_CUDA", "ERR_NCCL", "ERR_NOMEM", "ERR_DIVERGED"):
         assert getattr(capi, name) == header["LRK_" + name], name
     java = open(os.path.join(ROOT, "java", "net", "librec", "recommender", "cuda", "LibrecB200.java")).read()
     jconst = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(MODEL_[A-Z]+)\s*=\s*(\d+)", java)}
     for name, value in jconst.items():
         assert header["LRK_" + name] == value, name
-    assert set(jconst) == {"MODEL_BIASEDMF", "MODEL_PMF", "MODEL_BPR", "MODEL_RANKSGD", "MODEL_GBPR", "MODEL_SVDPP", "MODEL_AOBPR"}
-    # the bad-model guard of test_bad_config_is_rejected relies on 7 being out of range
-    assert max(v for k, v in header.items() if k.startswith("LRK_MODEL_")) < 7
+    assert set(jconst) == {"MODEL_BIASEDMF", "MODEL_PMF", "MODEL_BPR", "MODEL_RANKSGD", "MODEL_GBPR", "MODEL_SVDPP", "MODEL_AOBPR", "MODEL_WRMF", "MODEL_EALS"}
+    # the bad-model guard of test_bad_config_is_rejected relies on 9 being out of range
+    assert max(v for k, v in header.items() if k.startswith("LRK_MODEL_")) < 9
 
 
 def test_jni_forwarder_compiles_and_covers_every_export():
