@@ -30,12 +30,14 @@ struct AlsState {
     double* d_gram = nullptr;       // k x k
     double* d_conf = nullptr;       // eALS: confidences[numItems] (lrk_set_matrix "eals.confidences")
     double* d_pred = nullptr;       // eALS: per-entry predictions
+    double *d_tn = nullptr, *d_td = nullptr;   // eALS heavy rows: per-entry terms
+    unsigned int* d_counter = nullptr;
     bool has_conf = false;
 };
 
 static void als_release(AlsState* a) {
     if (!a) return;
-    cudaFree(a->d_val); cudaFree(a->d_colptr); cudaFree(a->d_cusers); cudaFree(a->d_cval); cudaFree(a->d_gram); cudaFree(a->d_conf); cudaFree(a->d_pred);
+    cudaFree(a->d_val); cudaFree(a->d_colptr); cudaFree(a->d_cusers); cudaFree(a->d_cval); cudaFree(a->d_gram); cudaFree(a->d_conf); cudaFree(a->d_pred); cudaFree(a->d_tn); cudaFree(a->d_td); cudaFree(a->d_counter);
     delete a;
 }
 
@@ -225,12 +227,17 @@ struct AlsEalsParams {
     const double* S;          // Sq (user step) or Sp (item step), k x k
     const double* conf;       // confidences[numItems]
     double* pred;             // per-entry scratch in the order of ptr / idx
+    double* tn;               // heavy rows: the per-entry terms of numer / denom (same order)
+    double* td;
+    unsigned int* counter;    // heavy rows: dynamic row scheduler
     double reg;
     int32_t n_rows;
     int k;
+    int heavy;                // rows with more entries take the CTA-per-row kernel
 };
 
-// EALSRecommender.java:139-171 (ITEM_STEP false) / :175-209 (true), one warp per row
+// EALSRecommender.java:139-171 (ITEM_STEP false) / :175-209 (true), one warp per row; rows with more than p.heavy entries are
+// left to als_eals_heavy_kernel (a lone warp walking 10^5 entries k times is latency bound: 112 cycles per entry and factor)
 template <bool ITEM_STEP>
 __global__ void __launch_bounds__(256) als_eals_side_kernel(AlsEalsParams p) {
     extern __shared__ double sm[];
@@ -239,6 +246,7 @@ __global__ void __launch_bounds__(256) als_eals_side_kernel(AlsEalsParams p) {
     const int64_t stride = (int64_t)gridDim.x * 8;
     for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < p.n_rows; row += stride) {
         const int64_t b = p.ptr[row], e = p.ptr[row + 1];
+        if (e - b > p.heavy) continue;
         __syncwarp();
         for (int f = lane; f < k; f += 32) own[f] = p.Fself[row * k + f];
         __syncwarp();
@@ -287,6 +295,88 @@ __global__ void __launch_bounds__(256) als_eals_side_kernel(AlsEalsParams p) {
     }
 }
 
+// the same update for one HEAVY row per CTA.  Per factor: all 256 threads compute the entries' terms in parallel (together with the
+// prediction update the previous factor left open), then warp 0 folds them in entry order -- the only sequential part, ~8 cycles per
+// entry and factor.  Rows are handed out by an atomic counter so that the few very long rows do not queue behind each other.
+template <bool ITEM_STEP>
+__global__ void __launch_bounds__(256) als_eals_heavy_kernel(AlsEalsParams p) {
+    __shared__ double own[LRK_MAX_FACTORS];
+    __shared__ double s_nf;
+    __shared__ unsigned int s_row;
+    const int k = p.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_row = atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const int64_t row = s_row;
+        if (row >= p.n_rows) break;
+        const int64_t b = p.ptr[row], e = p.ptr[row + 1];
+        if (e - b <= p.heavy) continue;
+        for (int f = tid; f < k; f += 256) own[f] = p.Fself[row * k + f];
+        __syncthreads();
+        for (int64_t x = b + tid; x < e; x += 256) {
+            const double* o = p.Fother + (int64_t)p.idx[x] * k;
+            double d = 0.0;
+            for (int f = 0; f < k; ++f) d = __dadd_rn(d, __dmul_rn(o[f], own[f]));
+            p.pred[x] = d;
+        }
+        const double c_row = ITEM_STEP ? p.conf[row] : 0.0;
+        double nf_prev = 0.0;
+        for (int f = 0; f < k; ++f) {
+            __syncthreads();
+            const double of = own[f];
+            for (int64_t x = b + tid; x < e; x += 256) {
+                const int32_t o = p.idx[x];
+                const double* orow = p.Fother + (int64_t)o * k;
+                const double qf = orow[f];
+                double pr = p.pred[x];
+                if (f > 0) pr = __dadd_rn(pr, __dmul_rn(nf_prev, orow[f - 1]));        // the previous factor's "+= new * q" (:165-168)
+                const double pm = __dsub_rn(pr, __dmul_rn(of, qf));
+                p.pred[x] = pm;
+                const double wv = p.w[x];
+                const double c = ITEM_STEP ? c_row : p.conf[o];
+                const double wc = __dsub_rn(wv, c);
+                p.tn[x] = __dmul_rn(__dsub_rn(wv, __dmul_rn(wc, pm)), qf);
+                p.td[x] = __dmul_rn(__dmul_rn(wc, qf), qf);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double numer = 0.0;
+                for (int f2 = 0; f2 < k; ++f2)
+                    if (f2 != f) numer = __dsub_rn(numer, __dmul_rn(own[f2], ITEM_STEP ? p.S[f2 * k + f] : p.S[f * k + f2]));
+                double denom;
+                if (ITEM_STEP) { numer = __dmul_rn(numer, c_row); denom = __dadd_rn(__dmul_rn(c_row, p.S[f * k + f]), p.reg); }
+                else denom = __dadd_rn(p.reg, p.S[f * k + f]);
+                for (int64_t base = b; base < e; base += 128) {                         // four batches of loads in flight per fold
+                    double t1[4], t2[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int64_t x = base + 32 * j + lane;
+                        t1[j] = x < e ? p.tn[x] : 0.0;
+                        t2[j] = x < e ? p.td[x] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int64_t left = e - (base + 32 * j);
+                        const int cnt = left < 0 ? 0 : (left < 32 ? (int)left : 32);
+                        for (int l = 0; l < cnt; ++l) {
+                            numer = __dadd_rn(numer, __shfl_sync(0xffffffffu, t1[j], l));
+                            denom = __dadd_rn(denom, __shfl_sync(0xffffffffu, t2[j], l));
+                        }
+                    }
+                }
+                const double nf = numer / denom;
+                if (lane == 0) { own[f] = nf; s_nf = nf; }
+            }
+            __syncthreads();
+            nf_prev = s_nf;
+        }
+        // (the last factor's prediction update is not needed: predictions are re-initialised per row, :141-145)
+        __syncthreads();
+        for (int f = tid; f < k; f += 256) p.Fself[row * k + f] = own[f];
+    }
+}
+
 // the train matrix by columns + the fp64 values (lrk_set_train_csr tail for WRMF / eALS)
 static int als_stage(lrk_handle_s* h, const double* h_val) {
     cudaStream_t st = h->stream;
@@ -301,7 +391,12 @@ static int als_stage(lrk_handle_s* h, const double* h_val) {
     if ((rc = lrk_dev_alloc(h, &a->d_cusers, (size_t)nnz))) return rc;
     if ((rc = lrk_dev_alloc(h, &a->d_cval, (size_t)nnz))) return rc;
     if ((rc = lrk_dev_alloc(h, &a->d_gram, (size_t)h->k * h->k))) return rc;
-    if ((rc = lrk_dev_alloc(h, &a->d_pred, (size_t)nnz))) return rc;
+    if (h->cfg.model == LRK_MODEL_EALS) {
+        if ((rc = lrk_dev_alloc(h, &a->d_pred, (size_t)nnz))) return rc;
+        if ((rc = lrk_dev_alloc(h, &a->d_tn, (size_t)nnz))) return rc;
+        if ((rc = lrk_dev_alloc(h, &a->d_td, (size_t)nnz))) return rc;
+        if ((rc = lrk_dev_alloc(h, &a->d_counter, 1))) return rc;
+    }
     if (nnz == 0) { LRK_CUDA(h, cudaMemsetAsync(a->d_colptr, 0, sizeof(int64_t) * ((size_t)I + 1), st)); return LRK_OK; }
     LRK_CUDA(h, cudaMemcpyAsync(a->d_val, h_val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
     size_t tb_sort = 0, tb_scan = 0;
@@ -386,6 +481,14 @@ static int als_eals_side(lrk_handle_s* h, const AlsEalsParams& p) {
     als_eals_side_kernel<ITEM_STEP><<<(unsigned)grid, 256, smem, h->stream>>>(p);
     LRK_LAUNCH_CHECK(h);
     h->launches++;
+    // rows above the threshold: one CTA each
+    LRK_CUDA(h, cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), h->stream));
+    LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_eals_heavy_kernel<ITEM_STEP>, 256, 0));
+    grid = (int64_t)h->sm_count * (per_sm < 1 ? 1 : per_sm);
+    if (grid > p.n_rows) grid = p.n_rows;
+    als_eals_heavy_kernel<ITEM_STEP><<<(unsigned)grid, 256, 0, h->stream>>>(p);
+    LRK_LAUNCH_CHECK(h);
+    h->launches++;
     return LRK_OK;
 }
 
@@ -413,7 +516,11 @@ static int als_epoch(lrk_handle_s* h, float reg_u, float reg_i, double* loss_out
     } else {
         AlsEalsParams p;
         memset(&p, 0, sizeof p);
-        p.k = k; p.S = a->d_gram; p.conf = a->d_conf; p.pred = a->d_pred;
+        p.k = k; p.S = a->d_gram; p.conf = a->d_conf; p.pred = a->d_pred; p.tn = a->d_tn; p.td = a->d_td; p.counter = a->d_counter;
+        {
+            const char* env = getenv("LRK_EALS_HEAVY");          // test hook: a small value sends the rows of small matrices down the CTA-per-row path
+            p.heavy = env && atoi(env) > 0 ? atoi(env) : 512;
+        }
         if ((rc = als_gram(h, h->Q64, h->I, a->d_conf, a->d_gram))) return rc;
         p.ptr = h->d_rowptr; p.idx = h->d_col; p.w = a->d_val; p.Fself = h->P64; p.Fother = h->Q64; p.reg = (double)reg_u; p.n_rows = h->U;
         if ((rc = als_eals_side<false>(h, p))) return rc;

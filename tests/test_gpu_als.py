@@ -95,9 +95,13 @@ def test_wrmf_c1_factors_and_lists_bit_identical(O, capi, c1):
     assert S[seen].mean() > S[~seen].mean() + 0.3
 
 
+@pytest.mark.parametrize("heavy", [0, 8])
 @pytest.mark.parametrize("judge", [0, 1, 2])
 @pytest.mark.parametrize("k", [4, 40])
-def test_eals_factors_bit_identical_small(O, capi, judge, k):
+def test_eals_factors_bit_identical_small(O, capi, monkeypatch, judge, k, heavy):
+    """heavy = 8 sends every row with more than 8 entries down the CTA-per-row kernel (default threshold 512)"""
+    if heavy:
+        monkeypatch.setenv("LRK_EALS_HEAVY", str(heavy))
     tr = _csr_with_gaps(O, 61, 37, 0.3, 10 * judge + k)
     conf = np.zeros(tr.I)
     O.lib().lro_eals_confidences(tr.U, tr.I, tr.rowptr, tr.col, 0.4, 128.0, judge, conf)
@@ -122,8 +126,12 @@ def test_eals_factors_bit_identical_small(O, capi, judge, k):
     assert np.isfinite(gP).all() and np.abs(gP).max() > 0
 
 
-def test_eals_c1_k200_bit_identical(O, capi, c1):
-    """eals-test.properties: k=200, reg 0.01, judge 1, coefficient 1 -- one iteration on the C1 train split, then the lists"""
+@pytest.mark.parametrize("heavy", [0, 100])
+def test_eals_c1_k200_bit_identical(O, capi, c1, monkeypatch, heavy):
+    """eals-test.properties: k=200, reg 0.01, judge 1, coefficient 1 -- one iteration on the C1 train split, then the lists
+    (heavy = 100: a third of the users and the popular items take the CTA-per-row kernel)"""
+    if heavy:
+        monkeypatch.setenv("LRK_EALS_HEAVY", str(heavy))
     tr = c1["train"]
     k = 200
     conf = np.ones(tr.I)
