@@ -256,7 +256,8 @@ if __name__ == "__main__":
     if a.only == "svdpp":
         run_svdpp(a.steps, a.warmup)
     if a.only in ("als", "wrmf"):
-        run_als("wrmf", 20, a.steps, a.warmup)
+        run_als("wrmf", 20, a.steps, a.warmup)                              # wrmf-test.properties, bitwise parity at scale
+        run_als("wrmf", 64, a.steps, a.warmup, oracle_parity=False)         # a larger k, timing only (the oracle needs minutes)
     if a.only in ("als", "eals"):
         run_als("eals", 32, a.steps, a.warmup)                              # bitwise parity at scale (the oracle needs 40 s at k=32, 4 min at k=200)
         run_als("eals", 200, a.steps, a.warmup, oracle_parity=False)        # eals-test.properties' k, timing only

@@ -42,7 +42,6 @@ static void als_release(AlsState* a) {
 }
 
 #define ALS_MAX_K 112          // [A | I] of the Gauss-Jordan step must fit the 227 KB of shared memory: k (2k + 2) doubles
-#define ALS_CHUNK 8            // entries of a row staged per step of the WRMF accumulation
 
 __global__ void als_csc_gather_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ rows, const double* __restrict__ val, int64_t nnz,
                                       int32_t* __restrict__ cusers, double* __restrict__ cval) {
@@ -95,18 +94,20 @@ struct AlsSolveParams {
     int k;
 };
 
+// entries of a row staged per step of the WRMF accumulation (shared memory next to the k x (2k + 2) Gauss-Jordan tableau)
+__host__ __device__ constexpr int als_chunk(int tile) { return tile <= 4 ? 32 : (tile <= 6 ? 16 : 8); }
+
 // WRMFRecommender.java:93-126 (users) / :129-163 (items), one CTA per row
 template <int TILE>
 __global__ void __launch_bounds__(256) als_wrmf_solve_kernel(AlsSolveParams p) {
     extern __shared__ double sm[];
-    const int k = p.k, S = 2 * k + 2, KP = 16 * TILE;
+    constexpr int KP = 16 * TILE, CH = als_chunk(TILE), NPT = (CH * KP + 255) / 256;
+    const int k = p.k, S = 2 * k + 2;
     double* Mx = sm;                               // k x S: A in columns [0, k), the inverse in [k, 2k)
-    double* ys = Mx + (size_t)k * S;               // ALS_CHUNK x KP, zero padded
-    double* wsh = ys + ALS_CHUNK * KP;             // ALS_CHUNK
-    double* bs = wsh + ALS_CHUNK;                  // k
+    double* ys = Mx + (size_t)k * S;               // CH x KP, zero padded
+    double* wsh = ys + CH * KP;                    // CH
+    double* bs = wsh + CH;                         // k
     double* colp = bs + k;                         // k
-    __shared__ int s_pivot;
-    __shared__ double s_mag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tr = tid >> 4, tc = tid & 15;
     for (int32_t row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
@@ -120,15 +121,27 @@ __global__ void __launch_bounds__(256) als_wrmf_solve_kernel(AlsSolveParams p) {
                 acc[a][c] = (rr < k && cc < k) ? __dadd_rn(p.G[rr * k + cc], p.reg) : 0.0;         // :110, the regulariser lands on EVERY entry
             }
         double bacc = 0.0;
-        for (int64_t base = b0; base < e0; base += ALS_CHUNK) {
-            const int cnt = (int)((e0 - base) < ALS_CHUNK ? (e0 - base) : ALS_CHUNK);
-            __syncthreads();
-            for (int t = tid; t < ALS_CHUNK * KP; t += 256) {
-                const int e = t / KP, f = t - e * KP;
-                ys[t] = (e < cnt && f < k) ? p.F[(int64_t)p.idx[base + e] * k + f] : 0.0;
+        // the next chunk's factor rows travel in registers while the current one is consumed (a long row is a chain of dependent
+        // gathers otherwise: 2 us per 8 entries)
+        double pre[NPT], prew = 0.0;
+        auto fetch = [&](int64_t base) {
+            const int cnt = (int)((e0 - base) < CH ? (e0 - base) : CH);
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                const int t = tid + 256 * j, e = t / KP, f = t - e * KP;
+                pre[j] = (t < CH * KP && e < cnt && f < k) ? p.F[(int64_t)p.idx[base + e] * k + f] : 0.0;
             }
-            if (tid < cnt) wsh[tid] = p.w[base + tid];
+            prew = tid < cnt ? p.w[base + tid] : 0.0;
+        };
+        if (b0 < e0) fetch(b0);
+        for (int64_t base = b0; base < e0; base += CH) {
+            const int cnt = (int)((e0 - base) < CH ? (e0 - base) : CH);
             __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) { const int t = tid + 256 * j; if (t < CH * KP) ys[t] = pre[j]; }
+            if (tid < CH) wsh[tid] = prew;
+            __syncthreads();
+            if (base + CH < e0) fetch(base + CH);
             for (int e = 0; e < cnt; ++e) {
                 const double wv = wsh[e];
                 const double* y = ys + e * KP;
@@ -155,44 +168,36 @@ __global__ void __launch_bounds__(256) als_wrmf_solve_kernel(AlsSolveParams p) {
         for (int t = tid; t < k * k; t += 256) { const int rr = t / k, cc = t - rr * k; Mx[rr * S + k + cc] = rr == cc ? 1.0 : 0.0; }
         if (tid < k) bs[tid] = bacc;
         __syncthreads();
-        // DenseMatrix.inverse(): :362-437
+        // DenseMatrix.inverse(): :362-437.  Three barriers per pivot: every warp runs the pivot search itself (same tableau, same
+        // answer), the row swap and the division of the pivot row are one pass over the columns, the elimination another.
         if (k == 1) {
             if (tid == 0) Mx[k] = 1.0 / Mx[0];
-            __syncthreads();
         } else {
             for (int pv = 0; pv < k; ++pv) {
-                if (warp == 0) {
-                    double mag = 0.0;
-                    int best = -1;
-                    for (int j = pv + lane; j < k; j += 32) {
-                        const double m2 = fabs(Mx[j * S + pv]);
-                        if (m2 > mag) { mag = m2; best = j; }
-                    }
+                double mag = 0.0;
+                int best = -1;
+                for (int j = pv + lane; j < k; j += 32) {
+                    const double m2 = fabs(Mx[j * S + pv]);
+                    if (m2 > mag) { mag = m2; best = j; }
+                }
 #pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const double om = __shfl_xor_sync(0xffffffffu, mag, off);
-                        const int oj = __shfl_xor_sync(0xffffffffu, best, off);
-                        if (om > mag || (om == mag && om > 0.0 && oj < best)) { mag = om; best = oj; }   // first strictly-largest in row order
-                    }
-                    if (lane == 0) { s_pivot = best; s_mag = mag; }
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const double om = __shfl_xor_sync(0xffffffffu, mag, off);
+                    const int oj = __shfl_xor_sync(0xffffffffu, best, off);
+                    if (om > mag || (om == mag && om > 0.0 && oj < best)) { mag = om; best = oj; }       // first strictly-largest in row order
+                }
+                if (best == -1 || mag == 0.0) break;                                               // :393-394: the inverse as it stands
+                const int piv = best;
+                const double pm = Mx[piv * S + pv];                                                // :412, read after the swap in the reference
+                // elimination factors of the rows as they stand AFTER the swap (:421); colp[pv] is not used
+                for (int r2 = tid; r2 < k; r2 += 256) colp[r2] = Mx[(r2 == piv ? pv : r2) * S + pv];
+                __syncthreads();
+                for (int c = pv + tid; c < 2 * k; c += 256) {                                       // :397-410 swap, :412-417 normalise
+                    const double a = Mx[piv * S + c];
+                    if (piv != pv) Mx[piv * S + c] = Mx[pv * S + c];
+                    Mx[pv * S + c] = a / pm;
                 }
                 __syncthreads();
-                const int piv = s_pivot;
-                if (piv == -1 || s_mag == 0.0) break;                                              // :393-394: the inverse as it stands
-                if (piv != pv) {
-                    for (int c = pv + tid; c < 2 * k; c += 256) {
-                        const double t0 = Mx[pv * S + c];
-                        Mx[pv * S + c] = Mx[piv * S + c];
-                        Mx[piv * S + c] = t0;
-                    }
-                    __syncthreads();
-                }
-                const double mag = Mx[pv * S + pv];
-                __syncthreads();
-                for (int c = pv + tid; c < 2 * k; c += 256) Mx[pv * S + c] = Mx[pv * S + c] / mag;
-                for (int r2 = tid; r2 < k; r2 += 256) colp[r2] = Mx[r2 * S + pv];
-                __syncthreads();
-                // (colp[pv] races with the division of Mx[pv][pv] in the same interval; it is never used: r2 == pv is skipped)
                 double prow[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { const int c = pv + lane + 32 * j; prow[j] = c < 2 * k ? Mx[pv * S + c] : 0.0; }
@@ -207,8 +212,8 @@ __global__ void __launch_bounds__(256) als_wrmf_solve_kernel(AlsSolveParams p) {
                 }
                 __syncthreads();
             }
-            __syncthreads();
         }
+        __syncthreads();
         if (tid < k) {                                                                              // Wu.times(YtCuPu): row(a).dot(b)
             double v = 0.0;
             for (int c = 0; c < k; ++c) v = __dadd_rn(v, __dmul_rn(bs[c], Mx[tid * S + k + c]));
@@ -243,6 +248,8 @@ __global__ void __launch_bounds__(256) als_eals_side_kernel(AlsEalsParams p) {
     extern __shared__ double sm[];
     const int k = p.k, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* own = sm + warp * k;
+    double* f1 = sm + 8 * k + warp * 64;           // the 32 numer / denom terms of a batch
+    double* f2s = f1 + 32;
     const int64_t stride = (int64_t)gridDim.x * 8;
     for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < p.n_rows; row += stride) {
         const int64_t b = p.ptr[row], e = p.ptr[row + 1];
@@ -279,9 +286,12 @@ __global__ void __launch_bounds__(256) als_eals_side_kernel(AlsEalsParams p) {
                     td = __dmul_rn(__dmul_rn(wc, qf), qf);
                 }
                 const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
+                __syncwarp();
+                f1[lane] = tn; f2s[lane] = td;                     // fold in entry order: broadcast reads, the adds are the only chain
+                __syncwarp();
                 for (int l = 0; l < cnt; ++l) {
-                    numer = __dadd_rn(numer, __shfl_sync(0xffffffffu, tn, l));
-                    denom = __dadd_rn(denom, __shfl_sync(0xffffffffu, td, l));
+                    numer = __dadd_rn(numer, f1[l]);
+                    denom = __dadd_rn(denom, f2s[l]);
                 }
             }
             const double nf = numer / denom;
@@ -301,6 +311,7 @@ __global__ void __launch_bounds__(256) als_eals_side_kernel(AlsEalsParams p) {
 template <bool ITEM_STEP>
 __global__ void __launch_bounds__(256) als_eals_heavy_kernel(AlsEalsParams p) {
     __shared__ double own[LRK_MAX_FACTORS];
+    __shared__ double s_t1[128], s_t2[128];
     __shared__ double s_nf;
     __shared__ unsigned int s_row;
     const int k = p.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -347,22 +358,30 @@ __global__ void __launch_bounds__(256) als_eals_heavy_kernel(AlsEalsParams p) {
                 double denom;
                 if (ITEM_STEP) { numer = __dmul_rn(numer, c_row); denom = __dadd_rn(__dmul_rn(c_row, p.S[f * k + f]), p.reg); }
                 else denom = __dadd_rn(p.reg, p.S[f * k + f]);
-                for (int64_t base = b; base < e; base += 128) {                         // four batches of loads in flight per fold
-                    double t1[4], t2[4];
+                // ordered fold: 128 terms at a time go through shared memory (broadcast reads; the two add chains are the only
+                // dependency), the next 128 are already in flight in registers
+                double t1[4], t2[4];
+                auto fetch = [&](int64_t base) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int64_t x = base + 32 * j + lane;
                         t1[j] = x < e ? p.tn[x] : 0.0;
                         t2[j] = x < e ? p.td[x] : 0.0;
                     }
+                };
+                fetch(b);
+                for (int64_t base = b; base < e; base += 128) {
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int64_t left = e - (base + 32 * j);
-                        const int cnt = left < 0 ? 0 : (left < 32 ? (int)left : 32);
-                        for (int l = 0; l < cnt; ++l) {
-                            numer = __dadd_rn(numer, __shfl_sync(0xffffffffu, t1[j], l));
-                            denom = __dadd_rn(denom, __shfl_sync(0xffffffffu, t2[j], l));
-                        }
+                    for (int j = 0; j < 4; ++j) { s_t1[32 * j + lane] = t1[j]; s_t2[32 * j + lane] = t2[j]; }
+                    __syncwarp();
+                    if (base + 128 < e) fetch(base + 128);
+                    const int cnt = (int)((e - base) < 128 ? (e - base) : 128);
+                    if (cnt == 128) {
+#pragma unroll 16
+                        for (int j = 0; j < 128; ++j) { numer = __dadd_rn(numer, s_t1[j]); denom = __dadd_rn(denom, s_t2[j]); }
+                    } else {
+                        for (int j = 0; j < cnt; ++j) { numer = __dadd_rn(numer, s_t1[j]); denom = __dadd_rn(denom, s_t2[j]); }
                     }
                 }
                 const double nf = numer / denom;
@@ -442,7 +461,7 @@ static int als_gram(lrk_handle_s* h, const double* M, int64_t n, const double* w
 template <int TILE>
 static int als_wrmf_launch(lrk_handle_s* h, const AlsSolveParams& p) {
     const int k = p.k;
-    const size_t smem = sizeof(double) * ((size_t)k * (2 * k + 2) + (size_t)ALS_CHUNK * 16 * TILE + ALS_CHUNK + 2 * (size_t)k);
+    const size_t smem = sizeof(double) * ((size_t)k * (2 * k + 2) + (size_t)als_chunk(TILE) * 16 * TILE + als_chunk(TILE) + 2 * (size_t)k);
     LRK_CUDA(h, cudaFuncSetAttribute(als_wrmf_solve_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_wrmf_solve_kernel<TILE>, 256, smem));
@@ -471,7 +490,7 @@ static int als_wrmf_side(lrk_handle_s* h, const AlsSolveParams& p) {
 
 template <bool ITEM_STEP>
 static int als_eals_side(lrk_handle_s* h, const AlsEalsParams& p) {
-    const size_t smem = sizeof(double) * 8 * (size_t)p.k;
+    const size_t smem = sizeof(double) * (8 * (size_t)p.k + 8 * 64);
     int per_sm = 0;
     LRK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_eals_side_kernel<ITEM_STEP>, 256, smem));
     int64_t grid = (int64_t)h->sm_count * (per_sm < 1 ? 1 : per_sm);
