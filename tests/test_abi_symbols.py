@@ -94,3 +94,16 @@ def test_jni_forwarder_compiles_and_covers_every_export():
     java = open(os.path.join(ROOT, "java", "net", "librec", "recommender", "cuda", "LibrecB200.java")).read()
     natives = set(re.findall(r"static native [\w\[\]]+ (\w+)\(", java))
     assert jni_names == natives, (jni_names ^ natives)
+
+
+def test_every_model_has_a_java_shim_class():
+    """each MODEL_* of LibrecB200.java is returned by the model() of exactly one *CudaRecommender.java (what rec.recommender.class names)"""
+    jdir = os.path.join(ROOT, "java", "net", "librec", "recommender", "cuda")
+    consts = set(re.findall(r"\b(MODEL_[A-Z]+)\s*=", open(os.path.join(jdir, "LibrecB200.java")).read()))
+    used = {}
+    for f in sorted(os.listdir(jdir)):
+        if f.endswith("CudaRecommender.java"):
+            for m in re.findall(r"int model\(\)\s*\{\s*return LibrecB200\.(MODEL_[A-Z]+);", open(os.path.join(jdir, f)).read()):
+                used.setdefault(m, []).append(f)
+    assert set(used) == consts, (sorted(consts - set(used)), sorted(set(used) - consts))
+    assert all(len(v) == 1 for v in used.values()), used
