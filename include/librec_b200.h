@@ -135,7 +135,7 @@ LRK_API int lrk_host_free(void* p);
  * (recommender/MatrixRecommender.java:90) -- the per-row int[]/double[] pieces
  * (math/structure/RowSequentialAccessSparseMatrix.java:19, OrderedIntDoubleMapping) flattened to
  * rowptr[U+1], col[nnz] (ascending inside a row), val[nnz].  Builds the device CSR and a
- * device-shuffled COO stream for the SGD epoch. */
+ * device-shuffled COO stream for the SGD epoch.  nnz < 2^31 per handle (under DSGD / a multi handle: per rank). */
 LRK_API int lrk_set_train_csr(lrk_handle_t h, int32_t num_users, int32_t num_items,
                       const int64_t* rowptr, const int32_t* col, const double* val);
 /* replaces: DenseMatrix userFactors/itemFactors (double[][], math/structure/DenseMatrix.java:20),

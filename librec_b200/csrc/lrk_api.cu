@@ -367,7 +367,7 @@ int lrk_set_train_csr(lrk_handle_t h, int32_t U, int32_t I, const int64_t* rowpt
     if (h->multi) return multi_set_train_csr(h, U, I, rowptr, col, val);
     LRK_REQUIRE(h, !h->has_factors || (h->U == U && h->I == I), "CSR shape differs from the factors already set");
     const int64_t nnz = rowptr[U];
-    LRK_REQUIRE(h, nnz >= 0 && nnz < (int64_t)0xffffffffLL, "nnz out of range");
+    LRK_REQUIRE(h, nnz >= 0 && nnz < (int64_t)0x7fffffffLL, "nnz out of range (the staging sorts take an int count: at most 2^31 - 1 train entries per handle)");
     LRK_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->world > 1) return dsgd_set_train_csr(h, U, I, rowptr, col, val);
     cudaStream_t st = h->stream;
