@@ -163,7 +163,6 @@ def test_dense_inverse_is_the_reference_gauss_jordan(O):
 
 def test_wrmf_epochs_bit_identical_to_the_python_replay(O):
     tr = rng_csr(O, 23, 17, 0.3, 11)
-    tr.col[:] = tr.col                                   # rows ascending already
     k = 5
     val = np.array([O.lib().lro_wrmf_weight(float(v), 4.0) for v in tr.val])
     assert val[0] == math.log(1.0 + 10000.0 * tr.val[0]) or abs(val[0] - math.log(1.0 + 10000.0 * tr.val[0])) < 4e-15
@@ -210,3 +209,22 @@ def test_eals_epochs_bit_identical_to_the_python_replay(O):
             eals_replay(rows, cols, k, X, Y, conf.tolist(), float(np.float32(0.01)), float(np.float32(0.02)))
         assert np.array_equal(P, np.array(X)) and np.array_equal(Q, np.array(Y))
         assert np.isfinite(P).all() and np.abs(P).max() > 0
+
+
+def test_wrmf_hand_worked_k1(O):
+    """k = 1: the system is scalar.  x_u = sum_i (w_ui + 1) y_i / (sum_all y^2 + reg + sum_i w_ui y_i^2), written out by hand
+    (WRMFRecommender.java:103-123 with a 1 x 1 inverse, DenseMatrix.java:373-376)"""
+    rowptr = np.array([0, 2, 3], np.int64)
+    col = np.array([0, 1, 1], np.int32)
+    w = np.array([2.0, 3.0, 0.5])
+    P = np.array([[0.7], [-0.2]])
+    Q = np.array([[0.5], [-1.5]])
+    O.lib().lro_wrmf_epoch(2, 2, rowptr, col, w, 1, P, Q, 0.25, 0.125)
+    yty = 0.0 + 0.5 * 0.5 + (-1.5) * (-1.5)
+    x0 = ((0.0 + 0.5 * 3.0) + (-1.5) * 4.0) * (1.0 / (((yty + 0.25) + (0.5 * 2.0) * 0.5) + (-1.5 * 3.0) * -1.5))
+    x1 = (0.0 + (-1.5) * 1.5) * (1.0 / ((yty + 0.25) + (-1.5 * 0.5) * -1.5))
+    assert P[0, 0] == x0 and P[1, 0] == x1
+    xtx = 0.0 + x0 * x0 + x1 * x1
+    y0 = (0.0 + x0 * 3.0) * (1.0 / ((xtx + 0.125) + (x0 * 2.0) * x0))
+    y1 = ((0.0 + x0 * 4.0) + x1 * 1.5) * (1.0 / (((xtx + 0.125) + (x0 * 3.0) * x0) + (x1 * 0.5) * x1))
+    assert Q[0, 0] == y0 and Q[1, 0] == y1
