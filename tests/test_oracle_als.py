@@ -228,3 +228,30 @@ def test_wrmf_hand_worked_k1(O):
     y0 = (0.0 + x0 * 3.0) * (1.0 / ((xtx + 0.125) + (x0 * 2.0) * x0))
     y1 = ((0.0 + x0 * 4.0) + x1 * 1.5) * (1.0 / (((xtx + 0.125) + (x0 * 3.0) * x0) + (x1 * 0.5) * x1))
     assert Q[0, 0] == y0 and Q[1, 0] == y1
+
+
+def test_eals_hand_worked_k1(O):
+    """k = 1, one user with two items, zero user factor (EALSRecommender.java:125): every sum written out by hand (:128-209)"""
+    rowptr = np.array([0, 2], np.int64)
+    col = np.array([0, 1], np.int32)
+    w = np.array([3.0, 5.0])
+    conf = np.array([0.5, 0.25])
+    P = np.zeros((1, 1))
+    q0, q1 = 0.75, -0.5
+    Q = np.array([[q0], [q1]])
+    O.lib().lro_eals_epoch(1, 2, rowptr, col, w, 1, P, Q, conf, 0.25, 0.125)
+    sq = (0.0 + 0.5 * q0 * q0) + 0.25 * q1 * q1
+    pred0 = 0.0 - 0.0 * q0
+    pred1 = 0.0 - 0.0 * q1
+    numer = (0.0 + (3.0 - (3.0 - 0.5) * pred0) * q0) + (5.0 - (5.0 - 0.25) * pred1) * q1
+    denom = ((0.25 + sq) + (3.0 - 0.5) * q0 * q0) + (5.0 - 0.25) * q1 * q1
+    p = numer / denom
+    assert P[0, 0] == p
+    sp = 0.0 + p * p
+    out = []
+    for q, c, wt in ((q0, 0.5, 3.0), (q1, 0.25, 5.0)):
+        up = (0.0 + q * p) - p * q
+        n = 0.0 * c + (wt - (wt - c) * up) * p
+        d = (c * sp + 0.125) + (wt - c) * p * p
+        out.append(n / d)
+    assert Q[0, 0] == out[0] and Q[1, 0] == out[1]
